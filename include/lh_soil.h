@@ -1,0 +1,246 @@
+/*
+ * lh_soil.h — C ABI of the B200-native soil right-hand-side + SSPRK33 stage path.
+ *
+ * This is the drop-in boundary for ONE hot path of CliMA/LandHydrology.jl: the closure
+ * `rhs!(dY, Y, Ya, t)` returned by `make_rhs(model::SoilModel)`
+ * (reference src/SoilModel/right_hand_side.jl:33-44) and the `step!` / `run!` loop that
+ * `Simulation` drives (reference src/Simulations/simulation.jl:34-87, SSPRK33 stage
+ * combine of OrdinaryDiffEq v5).  The reference has no FFI of its own (it is 100 % Julia),
+ * so every entry point below names the Julia interface it replaces.  A Julia host binds
+ * them with `ccall` (julia/LandHydrologyB200.jl); the tested twin is the
+ * Python/ctypes host in landhydrology.jl_b200/.
+ *
+ * Conventions
+ *   - plain C: pointers, sizes, doubles; no C++/torch types cross this boundary.
+ *   - every function returns an int32 status: LH_OK (0) or a negative LH_ERR_* code; nothing
+ *     throws or aborts.  `lh_soil_last_error(ctx)` gives the message (ctx == NULL: the message
+ *     of the last failed `lh_soil_create` on this thread).
+ *   - a ctx owns its device memory and one CUDA stream; calls on one ctx must be serialised
+ *     by the caller (the reference's rhs! is not re-entrant either); different ctxs are
+ *     independent.  Host pointers are borrowed for the duration of the call only.
+ *   - arithmetic is fp64 throughout.  Vertical index 0 is the BOTTOM cell, nlayer-1 the top
+ *     (reference boundary_conditions.jl:182-185).
+ *   - host arrays are addressed as host[col * col_stride + layer * layer_stride] (strides in
+ *     elements), so the reference's per-column `parent(Y.soil)` matrix (layer fastest, one
+ *     field after the other) and a column-fastest SoA block are both expressible.
+ */
+#ifndef LH_SOIL_H
+#define LH_SOIL_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define LH_SOIL_ABI_VERSION 1
+
+/* ---- status codes ------------------------------------------------------------------- */
+#define LH_OK                   0
+#define LH_ERR_INVALID_ARG     -1  /* NULL pointer, bad field id, bad stride, bad stage ...            */
+#define LH_ERR_DOMAIN          -2  /* zlim[1] < zlim[2] violated (reference Domains/domain.jl:30)      */
+#define LH_ERR_UNSUPPORTED_BC  -3  /* BC/component pair with no `vertical_flux` method in the reference
+                                      (a Julia MethodError, boundary_conditions.jl:295-444)            */
+#define LH_ERR_CUDA            -4  /* CUDA runtime failure (message has the CUDA error string)         */
+#define LH_ERR_NO_DEVICE       -5  /* no CUDA device / bad ordinal: this library has NO CPU fallback   */
+#define LH_ERR_NCCL            -6  /* NCCL missing or failed                                           */
+#define LH_ERR_NONFINITE       -7  /* NaN/Inf in the state (the reference raises DomainError from `^`,
+                                      SoilWaterParameterizations.jl:209-211)                           */
+#define LH_ERR_STATE           -8  /* call sequence error (e.g. comm used before comm_init)            */
+
+/* ---- enums -------------------------------------------------------------------------- */
+/* Which (energy, hydrology) component pair `make_rhs` dispatches on (right_hand_side.jl).  */
+#define LH_MODEL_RICHARDS 0   /* PrescribedTemperatureModel + SoilHydrologyModel  (:118-186) */
+#define LH_MODEL_HEAT     1   /* SoilEnergyModel + PrescribedHydrologyModel       (:192-263) */
+#define LH_MODEL_COUPLED  2   /* SoilEnergyModel + SoilHydrologyModel             (:269-369) */
+
+/* Boundary-condition kinds (boundary_conditions.jl:27,43-46,61-64,77).                      */
+#define LH_BC_NONE          0   /* NoBC          */
+#define LH_BC_FLUX          1   /* VerticalFlux  */
+#define LH_BC_DIRICHLET     2   /* Dirichlet     */
+#define LH_BC_FREE_DRAINAGE 3   /* FreeDrainage  */
+
+/* Conductivity factors (SoilWaterParameterizations.jl:38-65).                               */
+#define LH_FACTOR_NONE        0 /* NoEffect                       */
+#define LH_FACTOR_VISCOSITY   1 /* TemperatureDependentViscosity  */
+#define LH_FACTOR_IMPEDANCE   1 /* IceImpedance                   */
+
+/* Cell-centred fields.  theta_l is the reference's augmented liquid fraction ϑ_l.           */
+#define LH_FIELD_THETA_L   0    /* ϑ_l     prognostic (Richards, coupled) / prescribed (heat) */
+#define LH_FIELD_THETA_I   1    /* θ_i     tendency identically 0 (right_hand_side.jl:182,359) */
+#define LH_FIELD_RHO_E_INT 2    /* ρe_int  prognostic (heat, coupled)                          */
+#define LH_FIELD_T         3    /* T       prescribed aux (Richards only; Ya.soil.T)           */
+#define LH_NUM_FIELDS      4
+
+/* Index into the 4-vector of boundary values: [top energy, top hydrology, bottom energy,
+ * bottom hydrology].  For LH_BC_FLUX the value is the flux (positive along +z at BOTH faces,
+ * boundary_conditions.jl:44); for LH_BC_DIRICHLET it is `state_value(t)` (T or ϑ_l).        */
+#define LH_BCV_TOP_ENERGY       0
+#define LH_BCV_TOP_HYDROLOGY    1
+#define LH_BCV_BOTTOM_ENERGY    2
+#define LH_BCV_BOTTOM_HYDROLOGY 3
+
+/* ---- parameter block ------------------------------------------------------------------
+ * All constants are runtime doubles supplied by the host; nothing is hard-coded in kernels.
+ *   SoilParams{FT}         reference src/SoilModel/parameters.jl:11-43
+ *   vanGenuchten{FT}       reference SoilWaterParameterizations.jl:151-170
+ *   conductivity factors   reference SoilWaterParameterizations.jl:46-65
+ *   CLIMAParameters        values read at SoilHeatParameterizations.jl:12-13
+ */
+typedef struct lh_soil_params {
+    /* SoilParams */
+    double nu;                 /* ν   porosity                                  */
+    double S_s;                /* specific storage                              */
+    double nu_ss_gravel;
+    double nu_ss_om;
+    double nu_ss_quartz;
+    double rho_c_ds;           /* ρc_ds volumetric heat capacity of dry soil    */
+    double kappa_solid;
+    double rho_p;              /* ρp particle density                           */
+    double kappa_sat_unfrozen;
+    double kappa_sat_frozen;
+    double a;                  /* Balland & Arp                                 */
+    double b;
+    double kappa_dry_parameter;
+    double z_0m;               /* carried for API completeness; unused on this path */
+    double z_0s;
+    /* vanGenuchten */
+    double vg_n;
+    double vg_alpha;
+    double vg_m;               /* 1 - 1/n, as stored by the reference constructor */
+    double theta_r;
+    double Ksat;
+    /* conductivity factors */
+    int32_t viscosity_factor;  /* LH_FACTOR_NONE | LH_FACTOR_VISCOSITY */
+    int32_t impedance_factor;  /* LH_FACTOR_NONE | LH_FACTOR_IMPEDANCE */
+    double visc_gamma;         /* γ     (default 2.64e-2) */
+    double visc_T_ref;         /* T_ref (default 288)     */
+    double imp_Omega;          /* Ω     (default 7)       */
+    /* earth parameter set */
+    double rho_cloud_liq;
+    double rho_cloud_ice;
+    double cp_l;
+    double cp_i;
+    double T_0;
+    double LH_f0;
+    double K_therm;
+} lh_soil_params;
+
+/* One face of SoilColumnBC (boundary_conditions.jl:95-101,144-161). */
+typedef struct lh_soil_face_bc {
+    int32_t energy_kind;       /* LH_BC_*                                       */
+    int32_t hydrology_kind;    /* LH_BC_*                                       */
+    double  energy_value;      /* flux, or Dirichlet T at create time           */
+    double  hydrology_value;   /* flux, or Dirichlet ϑ_l at create time         */
+} lh_soil_face_bc;
+
+typedef struct lh_soil_config {
+    int32_t struct_size;       /* sizeof(lh_soil_config): ABI guard                         */
+    int32_t device;            /* CUDA ordinal                                              */
+    int64_t ncol;              /* laterally independent columns (Column: 1; HybridBox: nx*ny) */
+    int32_t nlayer;            /* Column.nelements                                          */
+    int32_t model;             /* LH_MODEL_*                                                */
+    double  zmin, zmax;        /* Column.zlim                                               */
+    lh_soil_params  params;
+    lh_soil_face_bc top;
+    lh_soil_face_bc bottom;
+    int32_t flags;             /* LH_FLAG_*                                                 */
+    int32_t reserved;
+} lh_soil_config;
+
+#define LH_FLAG_CHECK_FINITE 1 /* rhs/step return LH_ERR_NONFINITE when NaN/Inf appears     */
+
+typedef struct lh_soil_ctx lh_soil_ctx;
+
+/* ---- lifetime ------------------------------------------------------------------------ */
+int32_t lh_soil_abi_version(void);
+
+/* Replaces: Column(...), SoilParams{FT}(...), vanGenuchten{FT}(...), SoilColumnBC(...),
+ * SoilModel(FT; ...) (models.jl:115-135) + make_function_space (domain.jl:58-69).
+ * Validates like the reference's method table: an unsupported BC/component pair is
+ * LH_ERR_UNSUPPORTED_BC, zmin >= zmax is LH_ERR_DOMAIN.                                     */
+int32_t lh_soil_create(const lh_soil_config* cfg, lh_soil_ctx** out);
+int32_t lh_soil_destroy(lh_soil_ctx* ctx);
+const char* lh_soil_last_error(const lh_soil_ctx* ctx);
+
+/* Cell-centre coordinates Ya.zc (right_hand_side.jl:7-8): writes nlayer doubles.            */
+int32_t lh_soil_get_zc(const lh_soil_ctx* ctx, double* zc_out);
+
+/* ---- state / aux transfer (replaces initialize_states, initial_conditions.jl:101-107) - */
+int32_t lh_soil_set_state(lh_soil_ctx* ctx, int32_t field, const double* host,
+                          int64_t col_stride, int64_t layer_stride);
+int32_t lh_soil_get_state(lh_soil_ctx* ctx, int32_t field, double* host,
+                          int64_t col_stride, int64_t layer_stride);
+/* Prescribed profiles (make_update_aux, right_hand_side.jl:54-81), evaluated by the host.
+ * col_stride == 0 broadcasts one nlayer-long profile to every column.  Same storage as
+ * set_state; kept as its own entry point because the reference keeps Y and Ya apart.        */
+int32_t lh_soil_set_aux(lh_soil_ctx* ctx, int32_t field, const double* host,
+                        int64_t col_stride, int64_t layer_stride);
+
+/* Boundary values for the NEXT rhs/stage call: the host evaluates Dirichlet
+ * `state_value(t)` closures (boundary_conditions.jl:247,267) and passes 4 doubles indexed
+ * by LH_BCV_*.                                                                              */
+int32_t lh_soil_set_bc_values(lh_soil_ctx* ctx, const double values[4]);
+
+/* ---- the hot path -------------------------------------------------------------------- */
+/* Replaces rhs!(dY, Y, Ya, t) (right_hand_side.jl:37-42): tendency of the current state into
+ * the ctx's tendency buffers; fetch with lh_soil_get_tendency.  This is the 1e-12 parity
+ * entry point.                                                                              */
+int32_t lh_soil_rhs(lh_soil_ctx* ctx, double t);
+int32_t lh_soil_get_tendency(lh_soil_ctx* ctx, int32_t field, double* host,
+                             int64_t col_stride, int64_t layer_stride);
+
+/* One fused RHS + SSPRK33 stage (stage = 1, 2, 3), using the current bc values / aux:
+ *   1: u1 = u0 + dt f(u0)      2: u2 = (3 u0 + u1 + dt f(u1)) / 4
+ *   3: u  = (u0 + 2 u2 + 2 dt f(u2)) / 3
+ * Replaces one third of OrdinaryDiffEq's SSPRK33 perform_step! driven by step!
+ * (simulation.jl:79-80).  Stage times are t, t+dt, t+dt/2.                                  */
+int32_t lh_soil_stage_ssprk33(lh_soil_ctx* ctx, int32_t stage, double dt);
+
+/* nsteps full SSPRK33 steps.  bc_table is NULL (boundary values constant = the current
+ * ones) or nsteps*3*4 doubles: for each step and stage the LH_BCV_* 4-vector evaluated by
+ * the host at that stage's time.  Replaces step!/run! (simulation.jl:79-87).                */
+int32_t lh_soil_step_ssprk33(lh_soil_ctx* ctx, double t, double dt, int64_t nsteps,
+                             const double* bc_table);
+
+/* ---- diagnostics ---------------------------------------------------------------------
+ * Water and energy budgets of THIS ctx's columns: out[0] = sum ϑ_l Δz, out[1] = sum ρe_int Δz
+ * (deterministic fixed-tree reduction).  New in this build.                     */
+int32_t lh_soil_budgets(lh_soil_ctx* ctx, double out[2]);
+/* Column-integrated boundary fluxes of the last rhs/stage call are not stored; conservation
+ * tests use budgets before/after a step.                                                    */
+
+/* Derived cell-centre fields of the CURRENT state, evaluated on the device with the same
+ * closures the RHS kernel uses (host-side in the reference: users call the
+ * parameterisation functions on `parent(Y.soil.*)`, e.g. test/SoilModel/coupled.jl:97-100). */
+#define LH_DIAG_K      0   /* hydraulic_conductivity   (SoilWaterParameterizations.jl:269-282) */
+#define LH_DIAG_PSI    1   /* pressure_head            (:229-242)                              */
+#define LH_DIAG_KAPPA  2   /* thermal_conductivity     (SoilHeatParameterizations.jl:185-188)  */
+#define LH_DIAG_T      3   /* temperature_from_ρe_int  (:42-53) or the prescribed T            */
+#define LH_NUM_DIAGS   4
+int32_t lh_soil_diagnostic(lh_soil_ctx* ctx, int32_t which, double* host,
+                           int64_t col_stride, int64_t layer_stride);
+
+int32_t lh_soil_sync(lh_soil_ctx* ctx);
+
+/* Device time (ms) spent in the kernels of the last lh_soil_step_ssprk33 call, measured with
+ * CUDA events on the ctx stream, and the number of kernels it launched.                     */
+int32_t lh_soil_last_step_timing(lh_soil_ctx* ctx, double* ms_out, int64_t* launches_out);
+
+/* Raw device pointer of a field's column-fastest SoA block [layer][ncol_padded] and the
+ * padded column stride, for zero-copy interop (e.g. wrapping in a torch tensor).            */
+int32_t lh_soil_device_ptr(lh_soil_ctx* ctx, int32_t field, void** dptr, int64_t* ncol_padded);
+
+/* ---- multi-GPU: column shards, one ctx per GPU/process ------------------------------- */
+/* 128-byte NCCL unique id, produced on rank 0 and distributed by the host's own plumbing.   */
+int32_t lh_soil_comm_unique_id(uint8_t id_out[128]);
+int32_t lh_soil_comm_init(lh_soil_ctx* ctx, int32_t nranks, int32_t rank, const uint8_t id[128]);
+/* Global budgets over all ranks' shards: local fixed-tree reduction, then ncclAllReduce(sum)
+ * of 2 doubles on the ctx stream.  The ONLY collective on this path (columns never exchange
+ * halos: right_hand_side.jl uses vertical operators only).                                  */
+int32_t lh_soil_budgets_allreduce(lh_soil_ctx* ctx, double out[2]);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* LH_SOIL_H */

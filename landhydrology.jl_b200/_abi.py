@@ -1,0 +1,341 @@
+"""ctypes binding of the C ABI declared in ``include/lh_soil.h``.
+
+The product library is ``csrc/liblh_soil.so`` (hand-written sm_100a CUDA behind ``extern "C"``).
+There is NO CPU fallback: :func:`cuda_library` raises if the shared object is missing, and
+``lh_soil_create`` returns ``LH_ERR_NO_DEVICE`` when no B200 is visible.
+
+:class:`SoilLibrary` is generic over (path, symbol prefix) only so that the parity tests can
+drive the CPU oracle (``oracle/liblho_soil.so``, prefix ``lho_``) through the very same harness;
+nothing in this package ever names or loads the oracle.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+from typing import Optional, Sequence
+
+import numpy as np
+
+ABI_VERSION = 1
+
+# status codes (include/lh_soil.h)
+LH_OK = 0
+LH_ERR_INVALID_ARG = -1
+LH_ERR_DOMAIN = -2
+LH_ERR_UNSUPPORTED_BC = -3
+LH_ERR_CUDA = -4
+LH_ERR_NO_DEVICE = -5
+LH_ERR_NCCL = -6
+LH_ERR_NONFINITE = -7
+LH_ERR_STATE = -8
+
+LH_MODEL_RICHARDS, LH_MODEL_HEAT, LH_MODEL_COUPLED = 0, 1, 2
+LH_BC_NONE, LH_BC_FLUX, LH_BC_DIRICHLET, LH_BC_FREE_DRAINAGE = 0, 1, 2, 3
+LH_FIELD_THETA_L, LH_FIELD_THETA_I, LH_FIELD_RHO_E_INT, LH_FIELD_T = 0, 1, 2, 3
+LH_DIAG_K, LH_DIAG_PSI, LH_DIAG_KAPPA, LH_DIAG_T = 0, 1, 2, 3
+LH_BCV_TOP_ENERGY, LH_BCV_TOP_HYDROLOGY, LH_BCV_BOTTOM_ENERGY, LH_BCV_BOTTOM_HYDROLOGY = 0, 1, 2, 3
+LH_FLAG_CHECK_FINITE = 1
+
+
+class SoilError(RuntimeError):
+    """Base class; ``status`` holds the LH_ERR_* code."""
+
+    def __init__(self, status: int, message: str):
+        super().__init__(f"[lh_soil status {status}] {message}")
+        self.status = status
+
+
+class UnsupportedBCError(SoilError, TypeError):
+    """The reference raises ``MethodError`` (no ``vertical_flux`` method) for this pair."""
+
+
+class DomainAssertionError(SoilError, AssertionError):
+    """``@assert zlim[1] < zlim[2]`` (reference src/Domains/domain.jl:30)."""
+
+
+class NonFiniteStateError(SoilError, ArithmeticError):
+    """The reference raises ``DomainError`` from ``^`` once ϑ_l leaves the valid range."""
+
+
+class NoDeviceError(SoilError):
+    """No CUDA device: the product has no CPU path."""
+
+
+_ERRORS = {
+    LH_ERR_UNSUPPORTED_BC: UnsupportedBCError,
+    LH_ERR_DOMAIN: DomainAssertionError,
+    LH_ERR_NONFINITE: NonFiniteStateError,
+    LH_ERR_NO_DEVICE: NoDeviceError,
+}
+
+
+class lh_soil_params(C.Structure):
+    _fields_ = [
+        ("nu", C.c_double), ("S_s", C.c_double), ("nu_ss_gravel", C.c_double),
+        ("nu_ss_om", C.c_double), ("nu_ss_quartz", C.c_double), ("rho_c_ds", C.c_double),
+        ("kappa_solid", C.c_double), ("rho_p", C.c_double), ("kappa_sat_unfrozen", C.c_double),
+        ("kappa_sat_frozen", C.c_double), ("a", C.c_double), ("b", C.c_double),
+        ("kappa_dry_parameter", C.c_double), ("z_0m", C.c_double), ("z_0s", C.c_double),
+        ("vg_n", C.c_double), ("vg_alpha", C.c_double), ("vg_m", C.c_double),
+        ("theta_r", C.c_double), ("Ksat", C.c_double),
+        ("viscosity_factor", C.c_int32), ("impedance_factor", C.c_int32),
+        ("visc_gamma", C.c_double), ("visc_T_ref", C.c_double), ("imp_Omega", C.c_double),
+        ("rho_cloud_liq", C.c_double), ("rho_cloud_ice", C.c_double), ("cp_l", C.c_double),
+        ("cp_i", C.c_double), ("T_0", C.c_double), ("LH_f0", C.c_double), ("K_therm", C.c_double),
+    ]
+
+
+class lh_soil_face_bc(C.Structure):
+    _fields_ = [
+        ("energy_kind", C.c_int32), ("hydrology_kind", C.c_int32),
+        ("energy_value", C.c_double), ("hydrology_value", C.c_double),
+    ]
+
+
+class lh_soil_config(C.Structure):
+    _fields_ = [
+        ("struct_size", C.c_int32), ("device", C.c_int32), ("ncol", C.c_int64),
+        ("nlayer", C.c_int32), ("model", C.c_int32), ("zmin", C.c_double), ("zmax", C.c_double),
+        ("params", lh_soil_params), ("top", lh_soil_face_bc), ("bottom", lh_soil_face_bc),
+        ("flags", C.c_int32), ("reserved", C.c_int32),
+    ]
+
+
+_dp = C.POINTER(C.c_double)
+_vp = C.c_void_p
+
+# name -> (argtypes, restype); every entry is declared in include/lh_soil.h
+_SIGNATURES = {
+    "soil_abi_version": ([], C.c_int32),
+    "soil_create": ([C.POINTER(lh_soil_config), C.POINTER(_vp)], C.c_int32),
+    "soil_destroy": ([_vp], C.c_int32),
+    "soil_last_error": ([_vp], C.c_char_p),
+    "soil_get_zc": ([_vp, _dp], C.c_int32),
+    "soil_set_state": ([_vp, C.c_int32, _dp, C.c_int64, C.c_int64], C.c_int32),
+    "soil_get_state": ([_vp, C.c_int32, _dp, C.c_int64, C.c_int64], C.c_int32),
+    "soil_set_aux": ([_vp, C.c_int32, _dp, C.c_int64, C.c_int64], C.c_int32),
+    "soil_set_bc_values": ([_vp, _dp], C.c_int32),
+    "soil_rhs": ([_vp, C.c_double], C.c_int32),
+    "soil_get_tendency": ([_vp, C.c_int32, _dp, C.c_int64, C.c_int64], C.c_int32),
+    "soil_stage_ssprk33": ([_vp, C.c_int32, C.c_double], C.c_int32),
+    "soil_step_ssprk33": ([_vp, C.c_double, C.c_double, C.c_int64, _dp], C.c_int32),
+    "soil_budgets": ([_vp, _dp], C.c_int32),
+    "soil_diagnostic": ([_vp, C.c_int32, _dp, C.c_int64, C.c_int64], C.c_int32),
+    "soil_sync": ([_vp], C.c_int32),
+    "soil_last_step_timing": ([_vp, _dp, C.POINTER(C.c_int64)], C.c_int32),
+    "soil_device_ptr": ([_vp, C.c_int32, C.POINTER(_vp), C.POINTER(C.c_int64)], C.c_int32),
+    "soil_comm_unique_id": ([C.POINTER(C.c_uint8)], C.c_int32),
+    "soil_comm_init": ([_vp, C.c_int32, C.c_int32, C.POINTER(C.c_uint8)], C.c_int32),
+    "soil_budgets_allreduce": ([_vp, _dp], C.c_int32),
+}
+
+ABI_SYMBOLS = tuple("lh_" + k for k in _SIGNATURES)
+
+
+def _as_double_ptr(a: np.ndarray):
+    return a.ctypes.data_as(_dp)
+
+
+class SoilLibrary:
+    """A loaded shared object exporting the lh_soil C ABI under ``prefix``."""
+
+    def __init__(self, path: str, prefix: str = "lh_"):
+        if not os.path.exists(path):
+            raise FileNotFoundError(
+                f"{path} is missing: build it first (python -c 'import __graft_entry__ as g; g.build()'); "
+                "this package has no CPU fallback"
+            )
+        self.path = os.path.abspath(path)
+        self.prefix = prefix
+        self._dll = C.CDLL(self.path, mode=C.RTLD_GLOBAL if prefix == "lh_" else C.RTLD_LOCAL)
+        for name, (argtypes, restype) in _SIGNATURES.items():
+            fn = getattr(self._dll, prefix + name)  # AttributeError if the symbol is not exported
+            fn.argtypes = argtypes
+            fn.restype = restype
+            setattr(self, name, fn)
+        v = self.soil_abi_version()
+        if v != ABI_VERSION:
+            raise RuntimeError(f"{path}: ABI version {v}, expected {ABI_VERSION}")
+
+    def raw(self, symbol: str):
+        """Any other exported symbol (used by the tests for the oracle's scalar closures)."""
+        return getattr(self._dll, symbol)
+
+    def comm_unique_id(self) -> bytes:
+        buf = (C.c_uint8 * 128)()
+        st = self.soil_comm_unique_id(buf)
+        if st != LH_OK:
+            raise SoilError(st, "lh_soil_comm_unique_id failed (is libnccl.so.2 loadable?)")
+        return bytes(buf)
+
+    def __repr__(self):
+        return f"SoilLibrary({self.path!r}, prefix={self.prefix!r})"
+
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+CUDA_LIBRARY_PATH = os.path.join(_HERE, "csrc", "liblh_soil.so")
+_cuda_lib: Optional[SoilLibrary] = None
+
+
+def cuda_library() -> SoilLibrary:
+    """The product library.  Raises (never falls back) when it has not been built."""
+    global _cuda_lib
+    if _cuda_lib is None:
+        _cuda_lib = SoilLibrary(CUDA_LIBRARY_PATH, "lh_")
+    return _cuda_lib
+
+
+class SoilContext:
+    """Owner of one ``lh_soil_ctx``: a shard of ``ncol`` columns on one device."""
+
+    def __init__(self, lib: SoilLibrary, cfg: lh_soil_config):
+        self.lib = lib
+        self.cfg = cfg
+        self.ncol = int(cfg.ncol)
+        self.nlayer = int(cfg.nlayer)
+        self.model = int(cfg.model)
+        self._h = _vp()
+        cfg.struct_size = C.sizeof(lh_soil_config)
+        st = lib.soil_create(C.byref(cfg), C.byref(self._h))
+        if st != LH_OK:
+            msg = lib.soil_last_error(None)
+            self._h = _vp()
+            self._raise(st, msg.decode() if msg else "lh_soil_create failed")
+
+    # -- plumbing ---------------------------------------------------------------------------
+    def _raise(self, st: int, msg: Optional[str] = None):
+        if msg is None:
+            raw = self.lib.soil_last_error(self._h)
+            msg = raw.decode() if raw else ""
+        raise _ERRORS.get(st, SoilError)(st, msg)
+
+    def _check(self, st: int):
+        if st != LH_OK:
+            self._raise(st)
+
+    def close(self):
+        if getattr(self, "_h", None) is not None and self._h.value:
+            self.lib.soil_destroy(self._h)
+            self._h = _vp()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *exc):
+        self.close()
+
+    # -- array helpers: shape (ncol, nlayer) C-order == reference layout (layer fastest) ----
+    def _strides(self, a: np.ndarray):
+        if a.dtype != np.float64:
+            raise TypeError("fp64 arrays only")
+        if a.ndim == 1:
+            if self.ncol != 1 or a.shape[0] != self.nlayer:
+                raise ValueError(f"expected shape ({self.nlayer},) for a single column, got {a.shape}")
+            return 0, a.strides[0] // 8
+        if a.shape != (self.ncol, self.nlayer):
+            raise ValueError(f"expected shape ({self.ncol}, {self.nlayer}), got {a.shape}")
+        if a.strides[0] % 8 or a.strides[1] % 8:
+            raise ValueError("unaligned strides")
+        return a.strides[0] // 8, a.strides[1] // 8
+
+    def zc(self) -> np.ndarray:
+        out = np.empty(self.nlayer, dtype=np.float64)
+        self._check(self.lib.soil_get_zc(self._h, _as_double_ptr(out)))
+        return out
+
+    def set_state(self, field: int, a: np.ndarray):
+        cs, ls = self._strides(a)
+        self._check(self.lib.soil_set_state(self._h, field, _as_double_ptr(a), cs, ls))
+
+    def set_aux(self, field: int, a: np.ndarray, per_layer: bool = False):
+        if per_layer:
+            a = np.ascontiguousarray(a, dtype=np.float64)
+            if a.shape != (self.nlayer,):
+                raise ValueError(f"per-layer profile must have shape ({self.nlayer},)")
+            self._check(self.lib.soil_set_aux(self._h, field, _as_double_ptr(a), 0, 1))
+        else:
+            cs, ls = self._strides(a)
+            self._check(self.lib.soil_set_aux(self._h, field, _as_double_ptr(a), cs, ls))
+
+    def _empty(self, like: Optional[np.ndarray]) -> np.ndarray:
+        if like is not None:
+            return like
+        return np.empty((self.ncol, self.nlayer), dtype=np.float64)
+
+    def get_state(self, field: int, out: Optional[np.ndarray] = None) -> np.ndarray:
+        out = self._empty(out)
+        cs, ls = self._strides(out)
+        self._check(self.lib.soil_get_state(self._h, field, _as_double_ptr(out), cs, ls))
+        return out
+
+    def get_tendency(self, field: int, out: Optional[np.ndarray] = None) -> np.ndarray:
+        out = self._empty(out)
+        cs, ls = self._strides(out)
+        self._check(self.lib.soil_get_tendency(self._h, field, _as_double_ptr(out), cs, ls))
+        return out
+
+    def diagnostic(self, which: int, out: Optional[np.ndarray] = None) -> np.ndarray:
+        out = self._empty(out)
+        cs, ls = self._strides(out)
+        self._check(self.lib.soil_diagnostic(self._h, which, _as_double_ptr(out), cs, ls))
+        return out
+
+    def set_bc_values(self, values: Sequence[float]):
+        v = np.asarray(values, dtype=np.float64)
+        if v.shape != (4,):
+            raise ValueError("bc values: 4 doubles [top energy, top hydrology, bottom energy, bottom hydrology]")
+        self._check(self.lib.soil_set_bc_values(self._h, _as_double_ptr(v)))
+
+    # -- hot path ---------------------------------------------------------------------------
+    def rhs(self, t: float = 0.0):
+        self._check(self.lib.soil_rhs(self._h, float(t)))
+
+    def stage(self, stage: int, dt: float):
+        self._check(self.lib.soil_stage_ssprk33(self._h, int(stage), float(dt)))
+
+    def step(self, t: float, dt: float, nsteps: int = 1, bc_table: Optional[np.ndarray] = None):
+        if bc_table is not None:
+            bc_table = np.ascontiguousarray(bc_table, dtype=np.float64)
+            if bc_table.size != nsteps * 12:
+                raise ValueError("bc_table must hold nsteps*3*4 doubles")
+            ptr = _as_double_ptr(bc_table)
+        else:
+            ptr = None
+        self._check(self.lib.soil_step_ssprk33(self._h, float(t), float(dt), int(nsteps), ptr))
+
+    def budgets(self) -> np.ndarray:
+        out = np.empty(2, dtype=np.float64)
+        self._check(self.lib.soil_budgets(self._h, _as_double_ptr(out)))
+        return out
+
+    def budgets_allreduce(self) -> np.ndarray:
+        out = np.empty(2, dtype=np.float64)
+        self._check(self.lib.soil_budgets_allreduce(self._h, _as_double_ptr(out)))
+        return out
+
+    def sync(self):
+        self._check(self.lib.soil_sync(self._h))
+
+    def last_step_timing(self):
+        ms = C.c_double()
+        n = C.c_int64()
+        self._check(self.lib.soil_last_step_timing(self._h, C.byref(ms), C.byref(n)))
+        return ms.value, n.value
+
+    def device_ptr(self, field: int):
+        p = _vp()
+        n = C.c_int64()
+        self._check(self.lib.soil_device_ptr(self._h, field, C.byref(p), C.byref(n)))
+        return p.value, n.value
+
+    def comm_init(self, nranks: int, rank: int, unique_id: bytes):
+        if len(unique_id) != 128:
+            raise ValueError("NCCL unique id must be 128 bytes")
+        buf = (C.c_uint8 * 128).from_buffer_copy(unique_id)
+        self._check(self.lib.soil_comm_init(self._h, int(nranks), int(rank), buf))

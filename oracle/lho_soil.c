@@ -1,0 +1,788 @@
+/*
+ * lho_soil.c — TEST INFRASTRUCTURE ONLY (see lho_soil.h).
+ *
+ * Plain-C fp64 restatement of the reference's soil right-hand side and the SSPRK33 stage
+ * combine.  Compile with -O2 -ffp-contract=off (no FMA contraction: every expression is
+ * evaluated in the order the Julia source writes it).  Columns are independent, so the only
+ * parallelism is an OpenMP loop over columns.
+ *
+ * Every function cites the reference file:line it follows (paths relative to
+ * /root/reference).  Third-party arithmetic that is NOT in the reference tree:
+ *   - ClimaCore (unpinned, ~v0.2.x) finite-difference operators InterpolateC2F / GradientC2F /
+ *     DivergenceF2C+SetValue on a uniform IntervalMesh: restated as in SURVEY §3.4
+ *     (arithmetic mean, centred difference / dz, flux-form divergence with the boundary face
+ *     fluxes set), call sites right_hand_side.jl:170-181,249-259,337-365.
+ *   - OrdinaryDiffEq v5 SSPRK33 (Shu-Osher), call site src/Simulations/simulation.jl:63-70.
+ *   - CLIMAParameters v0.1 constants arrive through lh_soil_params at run time.
+ */
+#include "lho_soil.h"
+
+#include <float.h>
+#include <math.h>
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+#include <time.h>
+#ifdef _OPENMP
+#include <omp.h>
+#endif
+
+/* ------------------------------------------------------------------------------------------
+ * Scalar closures
+ * ---------------------------------------------------------------------------------------- */
+
+/* Julia's max(a, b) propagates NaN (fmax does not). */
+static inline double jl_max(double a, double b)
+{
+    if (isnan(a) || isnan(b)) return NAN;
+    return a > b ? a : b;
+}
+
+/* SoilWaterParameterizations.jl:181-188 */
+double lho_volumetric_liquid_fraction(double theta_l_aug, double nu_eff)
+{
+    double theta_l;
+    if (theta_l_aug < nu_eff) theta_l = theta_l_aug;
+    else theta_l = nu_eff;
+    return theta_l;
+}
+
+/* SoilWaterParameterizations.jl:213-217; eps(Float64) == DBL_EPSILON */
+double lho_effective_saturation(double porosity, double theta_l_aug, double theta_r)
+{
+    double safe = jl_max(theta_l_aug, theta_r + DBL_EPSILON);
+    double S_l = (safe - theta_r) / (porosity - theta_r);
+    return S_l;
+}
+
+/* SoilWaterParameterizations.jl:196-200:
+ *   ψ_m = -((S^(-FT(1) / m) - FT(1)) * α^(-n))^(FT(1) / n)                                  */
+double lho_matric_potential(const lh_soil_params* p, double S)
+{
+    double n = p->vg_n, alpha = p->vg_alpha, m = p->vg_m;
+    double psi_m = -pow((pow(S, -1.0 / m) - 1.0) * pow(alpha, -n), 1.0 / n);
+    return psi_m;
+}
+
+/* SoilWaterParameterizations.jl:253-258; the reference errors for ψ > 0, here NaN. */
+double lho_inverse_matric_potential(const lh_soil_params* p, double psi)
+{
+    if (psi > 0) return NAN;
+    double n = p->vg_n, m = p->vg_m, alpha = p->vg_alpha;
+    double S = pow(1.0 + pow(alpha * fabs(psi), n), -m);
+    return S;
+}
+
+/* SoilWaterParameterizations.jl:229-242 */
+double lho_pressure_head(const lh_soil_params* p, double theta_l_aug, double nu_eff, double S_s)
+{
+    double S_l_eff = lho_effective_saturation(nu_eff, theta_l_aug, p->theta_r);
+    double psi;
+    if (S_l_eff <= 1.0) psi = lho_matric_potential(p, S_l_eff);
+    else psi = (theta_l_aug - nu_eff) / S_s;
+    return psi;
+}
+
+/* SoilWaterParameterizations.jl:269-282:
+ *   K = sqrt(S) * (FT(1) - (FT(1) - S^(FT(1) / m))^m)^FT(2);  return K * Ksat * visc * imp   */
+double lho_hydraulic_conductivity(const lh_soil_params* p, double S, double visc_f, double imp_f)
+{
+    double Ksat = p->Ksat, m = p->vg_m;
+    double K;
+    if (S < 1.0) K = sqrt(S) * pow(1.0 - pow(1.0 - pow(S, 1.0 / m), m), 2.0);
+    else K = 1.0;
+    return K * Ksat * visc_f * imp_f;
+}
+
+/* SoilWaterParameterizations.jl:104-126 */
+double lho_viscosity_factor(const lh_soil_params* p, double T)
+{
+    if (p->viscosity_factor == LH_FACTOR_NONE) return 1.0;
+    double factor = p->visc_gamma * (T - p->visc_T_ref);
+    return exp(factor);
+}
+
+/* SoilWaterParameterizations.jl:76-93 */
+double lho_impedance_factor(const lh_soil_params* p, double f_i)
+{
+    if (p->impedance_factor == LH_FACTOR_NONE) return 1.0;
+    return pow(10.0, -p->imp_Omega * f_i);
+}
+
+/* SoilWaterParameterizations.jl:290-306 */
+double lho_hydrostatic_profile(const lh_soil_params* p, double z, double z_interface, double nu,
+                               double S_s)
+{
+    double alpha = p->vg_alpha, m = p->vg_m, n = p->vg_n, theta_r = p->theta_r;
+    double theta;
+    if (z > z_interface) {
+        double S = pow(1.0 + pow(alpha * (z - z_interface), n), -m);
+        theta = S * (nu - theta_r) + theta_r;
+    } else {
+        theta = -S_s * (z - z_interface) + nu;
+    }
+    return theta;
+}
+
+/* SoilHeatParameterizations.jl:65-79 */
+double lho_volumetric_heat_capacity(const lh_soil_params* p, double theta_l, double theta_i,
+                                    double rho_c_ds)
+{
+    double rho_i = p->rho_cloud_ice;
+    double rhocp_i = p->cp_i * rho_i;
+    double rho_l = p->rho_cloud_liq;
+    double rhocp_l = p->cp_l * rho_l;
+    double rho_c_s = rho_c_ds + theta_l * rhocp_l + theta_i * rhocp_i;
+    return rho_c_s;
+}
+
+/* SoilHeatParameterizations.jl:42-53 */
+double lho_temperature_from_rho_e_int(const lh_soil_params* p, double rho_e_int, double theta_i,
+                                      double rho_c_s)
+{
+    double T = p->T_0 + (rho_e_int + theta_i * p->rho_cloud_ice * p->LH_f0) / rho_c_s;
+    return T;
+}
+
+/* SoilHeatParameterizations.jl:91-102 */
+double lho_volumetric_internal_energy(const lh_soil_params* p, double theta_i, double rho_c_s,
+                                      double T)
+{
+    double rho_e_int = rho_c_s * (T - p->T_0) - theta_i * p->rho_cloud_ice * p->LH_f0;
+    return rho_e_int;
+}
+
+/* SoilHeatParameterizations.jl:114-128 */
+double lho_saturated_thermal_conductivity(double theta_l, double theta_i, double k_unfrozen,
+                                          double k_frozen)
+{
+    double theta_w = theta_l + theta_i;
+    double k_sat;
+    if (theta_w < DBL_EPSILON) k_sat = 0.0;
+    else k_sat = pow(k_unfrozen, theta_l / theta_w) * pow(k_frozen, theta_i / theta_w);
+    return k_sat;
+}
+
+/* SoilHeatParameterizations.jl:139-142 */
+double lho_relative_saturation(double theta_l, double theta_i, double porosity)
+{
+    return (theta_l + theta_i) / porosity;
+}
+
+/* SoilHeatParameterizations.jl:152-174 */
+double lho_kersten_number(const lh_soil_params* p, double theta_i, double S_r)
+{
+    double a = p->a, b = p->b;
+    double nu_om = p->nu_ss_om, nu_q = p->nu_ss_quartz, nu_g = p->nu_ss_gravel;
+    double K_e;
+    if (theta_i < DBL_EPSILON) {
+        K_e = pow(S_r, (1.0 + nu_om - a * nu_q - nu_g) / 2.0) *
+              pow(pow(1.0 + exp(-b * S_r), -3.0) - pow((1.0 - S_r) / 2.0, 3.0), 1.0 - nu_om);
+    } else {
+        K_e = pow(S_r, 1.0 + nu_om);
+    }
+    return K_e;
+}
+
+/* SoilHeatParameterizations.jl:185-188 */
+double lho_thermal_conductivity(double kappa_dry, double K_e, double kappa_sat)
+{
+    return K_e * kappa_sat + (1.0 - K_e) * kappa_dry;
+}
+
+/* SoilHeatParameterizations.jl:198-207 */
+double lho_volumetric_internal_energy_liq(const lh_soil_params* p, double T)
+{
+    double rhocp_l = p->cp_l * p->rho_cloud_liq;
+    return rhocp_l * (T - p->T_0);
+}
+
+/* SoilHeatParameterizations.jl:223-233 */
+double lho_k_solid(double nu_ss_om, double nu_ss_quartz, double k_quartz, double k_minerals,
+                   double k_om)
+{
+    return pow(k_om, nu_ss_om) * pow(k_quartz, nu_ss_quartz) *
+           pow(k_minerals, 1.0 - nu_ss_om - nu_ss_quartz);
+}
+
+/* SoilHeatParameterizations.jl:245-247 */
+double lho_ksat_frozen(double k_solid, double porosity, double k_ice)
+{
+    return pow(k_solid, 1.0 - porosity) * pow(k_ice, porosity);
+}
+
+/* SoilHeatParameterizations.jl:258-260 */
+double lho_ksat_unfrozen(double k_solid, double porosity, double k_liq)
+{
+    return pow(k_solid, 1.0 - porosity) * pow(k_liq, porosity);
+}
+
+/* SoilHeatParameterizations.jl:268-294 (ρb_ss and k_dry) */
+double lho_k_dry(const lh_soil_params* p)
+{
+    double kdp = p->kappa_dry_parameter;
+    double porosity = p->nu, rho_p = p->rho_p, k_solid = p->kappa_solid;
+    double k_air = p->K_therm;
+    double rho_b = (1.0 - porosity) * rho_p;
+    double numerator = (kdp * k_solid - k_air) * rho_b + k_air * rho_p;
+    double denom = rho_p - (1.0 - kdp) * rho_b;
+    return numerator / denom;
+}
+
+/* ------------------------------------------------------------------------------------------
+ * Context
+ * ---------------------------------------------------------------------------------------- */
+
+struct lho_soil_ctx {
+    lh_soil_config cfg;
+    int64_t ncol;
+    int32_t nlayer;
+    double dz;
+    double* zc;           /* nlayer                                              */
+    double* f[LH_NUM_FIELDS]; /* [col * nlayer + layer]                          */
+    double* u1[3];        /* stage buffer (all three prognostic slots, like the
+                             reference's generic axpy over the whole FieldVector) */
+    double* tend[3];
+    double* Fw;           /* face fluxes of the last rhs call, [col*(nlayer+1)+j] */
+    double* Fe;
+    double bcv[4];
+    double last_ms;
+    int64_t last_launches;
+    char err[256];
+};
+
+static _Thread_local char g_create_err[256];
+
+static int32_t fail(lho_soil_ctx* ctx, int32_t code, const char* msg)
+{
+    if (ctx) snprintf(ctx->err, sizeof ctx->err, "%s", msg);
+    else snprintf(g_create_err, sizeof g_create_err, "%s", msg);
+    return code;
+}
+
+int32_t lho_soil_abi_version(void) { return LH_SOIL_ABI_VERSION; }
+
+const char* lho_soil_last_error(const lho_soil_ctx* ctx) { return ctx ? ctx->err : g_create_err; }
+
+int32_t lho_soil_num_threads(void)
+{
+#ifdef _OPENMP
+    return omp_get_max_threads();
+#else
+    return 1;
+#endif
+}
+
+void lho_soil_set_num_threads(int32_t n)
+{
+#ifdef _OPENMP
+    if (n > 0) omp_set_num_threads(n);
+#else
+    (void)n;
+#endif
+}
+
+static int has_water(int model) { return model == LH_MODEL_RICHARDS || model == LH_MODEL_COUPLED; }
+static int has_heat(int model) { return model == LH_MODEL_HEAT || model == LH_MODEL_COUPLED; }
+
+/* The reference's method table for vertical_flux (boundary_conditions.jl:295-444):
+ *   dynamic energy   : VerticalFlux, Dirichlet            (NoBC -> `nothing` into SetValue)
+ *   dynamic hydrology: VerticalFlux, Dirichlet, FreeDrainage
+ *   prescribed       : NoBC, VerticalFlux (value unused)
+ * anything else is a MethodError.                                                           */
+static int32_t validate_face(const lh_soil_face_bc* bc, int model, const char* face)
+{
+    char msg[200];
+    int ek = bc->energy_kind, hk = bc->hydrology_kind;
+    if (ek < 0 || ek > 3 || hk < 0 || hk > 3) {
+        snprintf(msg, sizeof msg, "%s: unknown BC kind", face);
+        return fail(NULL, LH_ERR_INVALID_ARG, msg);
+    }
+    if (has_heat(model)) {
+        if (!(ek == LH_BC_FLUX || ek == LH_BC_DIRICHLET)) {
+            snprintf(msg, sizeof msg, "%s: energy BC kind %d has no vertical_flux method for SoilEnergyModel", face, ek);
+            return fail(NULL, LH_ERR_UNSUPPORTED_BC, msg);
+        }
+    } else if (!(ek == LH_BC_NONE || ek == LH_BC_FLUX)) {
+        snprintf(msg, sizeof msg, "%s: energy BC kind %d has no vertical_flux method for PrescribedTemperatureModel", face, ek);
+        return fail(NULL, LH_ERR_UNSUPPORTED_BC, msg);
+    }
+    if (has_water(model)) {
+        if (!(hk == LH_BC_FLUX || hk == LH_BC_DIRICHLET || hk == LH_BC_FREE_DRAINAGE)) {
+            snprintf(msg, sizeof msg, "%s: hydrology BC kind %d has no vertical_flux method for SoilHydrologyModel", face, hk);
+            return fail(NULL, LH_ERR_UNSUPPORTED_BC, msg);
+        }
+    } else if (!(hk == LH_BC_NONE || hk == LH_BC_FLUX)) {
+        snprintf(msg, sizeof msg, "%s: hydrology BC kind %d has no vertical_flux method for PrescribedHydrologyModel", face, hk);
+        return fail(NULL, LH_ERR_UNSUPPORTED_BC, msg);
+    }
+    return LH_OK;
+}
+
+int32_t lho_soil_create(const lh_soil_config* cfg, lho_soil_ctx** out)
+{
+    if (!cfg || !out) return fail(NULL, LH_ERR_INVALID_ARG, "cfg/out is NULL");
+    *out = NULL;
+    if (cfg->struct_size != (int32_t)sizeof(lh_soil_config))
+        return fail(NULL, LH_ERR_INVALID_ARG, "lh_soil_config.struct_size mismatch");
+    if (cfg->ncol < 1 || cfg->nlayer < 1) return fail(NULL, LH_ERR_INVALID_ARG, "ncol and nlayer must be >= 1");
+    if (cfg->model < 0 || cfg->model > 2) return fail(NULL, LH_ERR_INVALID_ARG, "unknown model kind");
+    /* Domains/domain.jl:30  @assert zlim[1] < zlim[2] */
+    if (!(cfg->zmin < cfg->zmax)) return fail(NULL, LH_ERR_DOMAIN, "zlim[1] < zlim[2] violated");
+    int32_t st;
+    if ((st = validate_face(&cfg->top, cfg->model, "top")) != LH_OK) return st;
+    if ((st = validate_face(&cfg->bottom, cfg->model, "bottom")) != LH_OK) return st;
+
+    lho_soil_ctx* c = (lho_soil_ctx*)calloc(1, sizeof *c);
+    if (!c) return fail(NULL, LH_ERR_INVALID_ARG, "out of memory");
+    c->cfg = *cfg;
+    c->ncol = cfg->ncol;
+    c->nlayer = cfg->nlayer;
+    int n = cfg->nlayer;
+    /* Domains/domain.jl:58-69: uniform IntervalMesh; faces zmin + j (zmax - zmin) / n, centres
+     * are face midpoints (pinned: zc == -1.95:0.1:-0.05 for (-2, 0), n = 20; coupled.jl:198). */
+    c->dz = (cfg->zmax - cfg->zmin) / n;
+    size_t cells = (size_t)c->ncol * (size_t)n;
+    c->zc = (double*)malloc(sizeof(double) * n);
+    for (int i = 0; i < n; ++i) {
+        double zf0 = cfg->zmin + (cfg->zmax - cfg->zmin) * (double)i / (double)n;
+        double zf1 = cfg->zmin + (cfg->zmax - cfg->zmin) * (double)(i + 1) / (double)n;
+        c->zc[i] = (zf0 + zf1) / 2.0;
+    }
+    for (int k = 0; k < LH_NUM_FIELDS; ++k) c->f[k] = (double*)calloc(cells, sizeof(double));
+    for (int k = 0; k < 3; ++k) {
+        c->u1[k] = (double*)calloc(cells, sizeof(double));
+        c->tend[k] = (double*)calloc(cells, sizeof(double));
+    }
+    c->Fw = (double*)calloc((size_t)c->ncol * (n + 1), sizeof(double));
+    c->Fe = (double*)calloc((size_t)c->ncol * (n + 1), sizeof(double));
+    /* PrescribedTemperatureModel default T ≡ 288 (models.jl:51-54) */
+    for (size_t i = 0; i < cells; ++i) c->f[LH_FIELD_T][i] = 288.0;
+    c->bcv[LH_BCV_TOP_ENERGY] = cfg->top.energy_value;
+    c->bcv[LH_BCV_TOP_HYDROLOGY] = cfg->top.hydrology_value;
+    c->bcv[LH_BCV_BOTTOM_ENERGY] = cfg->bottom.energy_value;
+    c->bcv[LH_BCV_BOTTOM_HYDROLOGY] = cfg->bottom.hydrology_value;
+    *out = c;
+    return LH_OK;
+}
+
+int32_t lho_soil_destroy(lho_soil_ctx* c)
+{
+    if (!c) return LH_OK;
+    free(c->zc);
+    for (int k = 0; k < LH_NUM_FIELDS; ++k) free(c->f[k]);
+    for (int k = 0; k < 3; ++k) { free(c->u1[k]); free(c->tend[k]); }
+    free(c->Fw); free(c->Fe);
+    free(c);
+    return LH_OK;
+}
+
+int32_t lho_soil_get_zc(const lho_soil_ctx* c, double* zc_out)
+{
+    if (!c || !zc_out) return LH_ERR_INVALID_ARG;
+    memcpy(zc_out, c->zc, sizeof(double) * c->nlayer);
+    return LH_OK;
+}
+
+static int32_t copy_in(lho_soil_ctx* c, double* dst, const double* host, int64_t cs, int64_t ls)
+{
+    if (!host) return fail(c, LH_ERR_INVALID_ARG, "host pointer is NULL");
+    int n = c->nlayer;
+#pragma omp parallel for schedule(static) if (c->ncol >= 64)
+    for (int64_t col = 0; col < c->ncol; ++col)
+        for (int i = 0; i < n; ++i) dst[col * n + i] = host[col * cs + i * ls];
+    return LH_OK;
+}
+
+static int32_t copy_out(lho_soil_ctx* c, const double* src, double* host, int64_t cs, int64_t ls)
+{
+    if (!host) return fail(c, LH_ERR_INVALID_ARG, "host pointer is NULL");
+    int n = c->nlayer;
+#pragma omp parallel for schedule(static) if (c->ncol >= 64)
+    for (int64_t col = 0; col < c->ncol; ++col)
+        for (int i = 0; i < n; ++i) host[col * cs + i * ls] = src[col * n + i];
+    return LH_OK;
+}
+
+int32_t lho_soil_set_state(lho_soil_ctx* c, int32_t field, const double* host, int64_t cs, int64_t ls)
+{
+    if (!c) return LH_ERR_INVALID_ARG;
+    if (field < 0 || field >= LH_NUM_FIELDS) return fail(c, LH_ERR_INVALID_ARG, "bad field id");
+    return copy_in(c, c->f[field], host, cs, ls);
+}
+
+int32_t lho_soil_set_aux(lho_soil_ctx* c, int32_t field, const double* host, int64_t cs, int64_t ls)
+{
+    return lho_soil_set_state(c, field, host, cs, ls);
+}
+
+int32_t lho_soil_get_state(lho_soil_ctx* c, int32_t field, double* host, int64_t cs, int64_t ls)
+{
+    if (!c) return LH_ERR_INVALID_ARG;
+    if (field < 0 || field >= LH_NUM_FIELDS) return fail(c, LH_ERR_INVALID_ARG, "bad field id");
+    return copy_out(c, c->f[field], host, cs, ls);
+}
+
+int32_t lho_soil_get_tendency(lho_soil_ctx* c, int32_t field, double* host, int64_t cs, int64_t ls)
+{
+    if (!c) return LH_ERR_INVALID_ARG;
+    if (field < 0 || field >= 3) return fail(c, LH_ERR_INVALID_ARG, "bad field id");
+    return copy_out(c, c->tend[field], host, cs, ls);
+}
+
+int32_t lho_soil_set_bc_values(lho_soil_ctx* c, const double values[4])
+{
+    if (!c || !values) return LH_ERR_INVALID_ARG;
+    memcpy(c->bcv, values, sizeof c->bcv);
+    return LH_OK;
+}
+
+/* ------------------------------------------------------------------------------------------
+ * The right-hand side of one column
+ * ---------------------------------------------------------------------------------------- */
+
+typedef struct { double K, psi, kappa, T; } cell_closures;
+
+/* Pointwise block of right_hand_side.jl:156-167 (Richards), :209-224 (heat), :291-314
+ * (coupled), evaluated for one cell.  T_in is the prescribed T for the Richards model.      */
+static cell_closures closures_at(const lh_soil_params* p, int model, double kappa_dry,
+                                 double th, double ti, double re, double T_in)
+{
+    cell_closures c = {0.0, 0.0, 0.0, T_in};
+    double nu = p->nu;
+    double nu_eff = nu - ti;
+    double tl = lho_volumetric_liquid_fraction(th, nu_eff);
+    if (has_heat(model)) {
+        double rho_c_s = lho_volumetric_heat_capacity(p, tl, ti, p->rho_c_ds);
+        c.T = lho_temperature_from_rho_e_int(p, re, ti, rho_c_s);
+        double S_r = lho_relative_saturation(tl, ti, nu);
+        double kersten = lho_kersten_number(p, ti, S_r);
+        double k_sat = lho_saturated_thermal_conductivity(tl, ti, p->kappa_sat_unfrozen,
+                                                          p->kappa_sat_frozen);
+        c.kappa = lho_thermal_conductivity(kappa_dry, kersten, k_sat);
+    }
+    if (has_water(model)) {
+        double f_i = ti / (tl + ti);
+        double visc = lho_viscosity_factor(p, c.T);
+        double imp = lho_impedance_factor(p, f_i);
+        double S = lho_effective_saturation(nu, th, p->theta_r);
+        c.K = lho_hydraulic_conductivity(p, S, visc, imp);
+        c.psi = lho_pressure_head(p, th, nu_eff, p->S_s);
+    }
+    return c;
+}
+
+/* boundary_fluxes(X, bc::SoilComponentBC, face, model, cs, t)  boundary_conditions.jl:470-489.
+ * (th_c, ti_c, T_c) are interior_values (:174-190) at the cell next to the face; dzb is
+ * boundary_cf_distance (:196-208) = dz/2 on the uniform mesh (assumption A1).
+ * is_bottom flips the sign of the Dirichlet fluxes (:396-398, :439-441).                    */
+static void boundary_fluxes(const lh_soil_params* p, int model, double kappa_dry,
+                            const lh_soil_face_bc* bc, double val_e, double val_h, int is_bottom,
+                            double th_c, double ti_c, double T_c, double dzb,
+                            double* f_energy, double* f_water)
+{
+    /* initialize_boundary_values :218-228: pairs [centre, face], face := centre */
+    double th[2] = {th_c, th_c}, T[2] = {T_c, T_c}, ti[2] = {ti_c, ti_c};
+    /* set_boundary_values! :241-288, energy first then hydrology (:482-483); the Dirichlet
+     * methods exist only for the dynamic components.                                        */
+    if (bc->energy_kind == LH_BC_DIRICHLET && has_heat(model)) T[1] = val_e;
+    if (bc->hydrology_kind == LH_BC_DIRICHLET && has_water(model)) th[1] = val_h;
+
+    double nu = p->nu;
+    *f_energy = 0.0;
+    *f_water = 0.0;
+
+    /* energy: vertical_flux(bc.energy, energy, X_cf, model, dz, face) */
+    if (bc->energy_kind == LH_BC_FLUX) {
+        *f_energy = val_e;                                        /* :295-301 */
+    } else if (bc->energy_kind == LH_BC_DIRICHLET) {              /* :416-444 */
+        double kappa[2];
+        for (int k = 0; k < 2; ++k) {
+            double nu_eff = nu - ti[k];
+            double tl = lho_volumetric_liquid_fraction(th[k], nu_eff);
+            double S_r = lho_relative_saturation(tl, ti[k], nu);
+            double kersten = lho_kersten_number(p, ti[k], S_r);
+            double k_sat = lho_saturated_thermal_conductivity(tl, ti[k], p->kappa_sat_unfrozen,
+                                                              p->kappa_sat_frozen);
+            kappa[k] = lho_thermal_conductivity(kappa_dry, kersten, k_sat);
+        }
+        double flux = -kappa[1] * (T[1] - T[0]) / dzb;
+        if (is_bottom) flux *= -1;
+        *f_energy = flux;
+    }
+
+    /* hydrology: vertical_flux(bc.hydrology, hydrology, X_cf, model, dz, face) */
+    if (bc->hydrology_kind == LH_BC_FLUX) {
+        *f_water = val_h;                                         /* :295-301 */
+    } else if (bc->hydrology_kind == LH_BC_FREE_DRAINAGE) {       /* :328-356, centre values */
+        double nu_eff = nu - ti[0];
+        double tl = lho_volumetric_liquid_fraction(th[0], nu_eff);
+        double f_i = ti[0] / (tl + ti[0]);
+        double imp = lho_impedance_factor(p, f_i);
+        double visc = lho_viscosity_factor(p, T[0]);
+        double S = lho_effective_saturation(nu, th[0], p->theta_r);
+        double K = lho_hydraulic_conductivity(p, S, visc, imp);
+        *f_water = -K;
+    } else if (bc->hydrology_kind == LH_BC_DIRICHLET) {           /* :371-401 */
+        double K[2], psi[2];
+        for (int k = 0; k < 2; ++k) {
+            double nu_eff = nu - ti[k];
+            double tl = lho_volumetric_liquid_fraction(th[k], nu_eff);
+            double f_i = ti[k] / (tl + ti[k]);
+            double imp = lho_impedance_factor(p, f_i);
+            double visc = lho_viscosity_factor(p, T[k]);
+            double S = lho_effective_saturation(nu, th[k], p->theta_r);
+            K[k] = lho_hydraulic_conductivity(p, S, visc, imp);
+            psi[k] = lho_pressure_head(p, th[k], nu_eff, p->S_s);
+        }
+        double flux = -K[1] * (psi[1] - psi[0] + dzb) / dzb;
+        if (is_bottom) flux *= -1;
+        *f_water = flux;
+    }
+}
+
+/* One column.  u_th/u_ti/u_re/u_T: nlayer values each (layer 0 = bottom).  work: 5*nlayer.
+ * Fw/Fe: nlayer+1 face fluxes (outputs).                                                    */
+static void column_rhs(const lho_soil_ctx* c, const double bcv[4], double kappa_dry,
+                       const double* u_th, const double* u_ti, const double* u_re,
+                       const double* u_T, double* d_th, double* d_ti, double* d_re,
+                       double* Fw, double* Fe, double* work)
+{
+    const lh_soil_params* p = &c->cfg.params;
+    const int model = c->cfg.model;
+    const int n = c->nlayer;
+    const double dz = c->dz;
+    double* K = work;
+    double* h = work + n;
+    double* kappa = work + 2 * n;
+    double* T = work + 3 * n;
+    double* eK = work + 4 * n;
+
+    for (int i = 0; i < n; ++i) {
+        cell_closures cc = closures_at(p, model, kappa_dry, u_th[i], u_ti[i], u_re[i], u_T[i]);
+        K[i] = cc.K;
+        h[i] = cc.psi + c->zc[i];                                   /* :167, :314 */
+        kappa[i] = cc.kappa;
+        T[i] = cc.T;
+        /* ρe_int_l * K, :306 and :364 */
+        eK[i] = (model == LH_MODEL_COUPLED) ? lho_volumetric_internal_energy_liq(p, cc.T) * cc.K : 0.0;
+    }
+
+    double fe_top, fw_top, fe_bot, fw_bot;
+    boundary_fluxes(p, model, kappa_dry, &c->cfg.top, bcv[LH_BCV_TOP_ENERGY],
+                    bcv[LH_BCV_TOP_HYDROLOGY], 0, u_th[n - 1], u_ti[n - 1], T[n - 1], dz / 2.0,
+                    &fe_top, &fw_top);
+    boundary_fluxes(p, model, kappa_dry, &c->cfg.bottom, bcv[LH_BCV_BOTTOM_ENERGY],
+                    bcv[LH_BCV_BOTTOM_HYDROLOGY], 1, u_th[0], u_ti[0], T[0], dz / 2.0,
+                    &fe_bot, &fw_bot);
+
+    /* Face fluxes.  Interior face j sits between cells j-1 and j (0-based), j = 1..n-1:
+     *   water  :181/:358   -interpc2f(K) * gradc2f(h)
+     *   energy :259        -interpc2f(κ) * gradc2f(T)
+     *          :361-365    -interpc2f(κ) * gradc2f(T) - interpc2f(ρe_int_l K) * gradc2f(h)
+     * Boundary faces 0 and n carry the SetValue fluxes.                                     */
+    Fw[0] = fw_bot; Fw[n] = fw_top;
+    Fe[0] = fe_bot; Fe[n] = fe_top;
+    for (int j = 1; j < n; ++j) {
+        double grad_h = (h[j] - h[j - 1]) / dz;
+        double grad_T = (T[j] - T[j - 1]) / dz;
+        Fw[j] = has_water(model) ? -((K[j - 1] + K[j]) / 2.0) * grad_h : 0.0;
+        if (model == LH_MODEL_HEAT) Fe[j] = -((kappa[j - 1] + kappa[j]) / 2.0) * grad_T;
+        else if (model == LH_MODEL_COUPLED)
+            Fe[j] = -((kappa[j - 1] + kappa[j]) / 2.0) * grad_T - ((eK[j - 1] + eK[j]) / 2.0) * grad_h;
+        else Fe[j] = 0.0;
+    }
+    for (int i = 0; i < n; ++i) {
+        d_th[i] = has_water(model) ? -((Fw[i + 1] - Fw[i]) / dz) : 0.0;
+        d_ti[i] = 0.0;                                              /* :182, :359 */
+        d_re[i] = has_heat(model) ? -((Fe[i + 1] - Fe[i]) / dz) : 0.0;
+    }
+}
+
+/* rhs over all columns: input state arrays (th, ti, re, T) -> c->tend[] */
+static void rhs_all(lho_soil_ctx* c, const double* th, const double* ti, const double* re,
+                    const double* T)
+{
+    const int n = c->nlayer;
+    const double kappa_dry = lho_k_dry(&c->cfg.params);             /* :214, :295 */
+#pragma omp parallel if (c->ncol >= 64)
+    {
+        double* work = (double*)malloc(sizeof(double) * 5 * n);
+#pragma omp for schedule(static)
+        for (int64_t col = 0; col < c->ncol; ++col) {
+            size_t o = (size_t)col * n;
+            column_rhs(c, c->bcv, kappa_dry, th + o, ti + o, re + o, T + o, c->tend[0] + o,
+                       c->tend[1] + o, c->tend[2] + o, c->Fw + (size_t)col * (n + 1),
+                       c->Fe + (size_t)col * (n + 1), work);
+        }
+        free(work);
+    }
+}
+
+int32_t lho_soil_rhs(lho_soil_ctx* c, double t)
+{
+    (void)t;
+    if (!c) return LH_ERR_INVALID_ARG;
+    rhs_all(c, c->f[0], c->f[1], c->f[2], c->f[3]);
+    return LH_OK;
+}
+
+int32_t lho_soil_face_fluxes(lho_soil_ctx* c, int64_t col, double* Fw_out, double* Fe_out)
+{
+    if (!c || col < 0 || col >= c->ncol) return LH_ERR_INVALID_ARG;
+    size_t o = (size_t)col * (c->nlayer + 1);
+    if (Fw_out) memcpy(Fw_out, c->Fw + o, sizeof(double) * (c->nlayer + 1));
+    if (Fe_out) memcpy(Fe_out, c->Fe + o, sizeof(double) * (c->nlayer + 1));
+    return LH_OK;
+}
+
+/* ------------------------------------------------------------------------------------------
+ * SSPRK33 (OrdinaryDiffEq v5, Shu-Osher form).  The combine runs over every
+ * prognostic field of the model's FieldVector, θ_i included, like the reference's broadcast.
+ * ---------------------------------------------------------------------------------------- */
+
+static int prognostic(int model, int field)
+{
+    if (model == LH_MODEL_RICHARDS) return field == 0 || field == 1;   /* (ϑ_l, θ_i)         */
+    if (model == LH_MODEL_HEAT) return field == 2;                     /* (ρe_int)           */
+    return 1;                                                          /* (ϑ_l, θ_i, ρe_int) */
+}
+
+int32_t lho_soil_stage_ssprk33(lho_soil_ctx* c, int32_t stage, double dt)
+{
+    if (!c) return LH_ERR_INVALID_ARG;
+    if (stage < 1 || stage > 3) return fail(c, LH_ERR_INVALID_ARG, "stage must be 1, 2 or 3");
+    const int model = c->cfg.model;
+    const size_t cells = (size_t)c->ncol * c->nlayer;
+    /* stage input: u0 for stage 1, the stage buffer otherwise (non-prognostic slots always
+     * come from f[]).                                                                       */
+    const double* in[3];
+    for (int k = 0; k < 3; ++k) in[k] = (stage == 1 || !prognostic(model, k)) ? c->f[k] : c->u1[k];
+    rhs_all(c, in[0], in[1], in[2], c->f[3]);
+    for (int k = 0; k < 3; ++k) {
+        if (!prognostic(model, k)) continue;
+        double* u0 = c->f[k];
+        double* u = c->u1[k];
+        const double* kk = c->tend[k];
+        if (stage == 1) {
+#pragma omp parallel for schedule(static) if (c->ncol >= 64)
+            for (size_t i = 0; i < cells; ++i) u[i] = u0[i] + dt * kk[i];
+        } else if (stage == 2) {
+#pragma omp parallel for schedule(static) if (c->ncol >= 64)
+            for (size_t i = 0; i < cells; ++i) u[i] = (3 * u0[i] + u[i] + dt * kk[i]) / 4;
+        } else {
+#pragma omp parallel for schedule(static) if (c->ncol >= 64)
+            for (size_t i = 0; i < cells; ++i) u0[i] = (u0[i] + 2 * u[i] + 2 * dt * kk[i]) / 3;
+        }
+    }
+    return LH_OK;
+}
+
+static double now_ms(void)
+{
+    struct timespec ts;
+    clock_gettime(CLOCK_MONOTONIC, &ts);
+    return ts.tv_sec * 1e3 + ts.tv_nsec * 1e-6;
+}
+
+int32_t lho_soil_step_ssprk33(lho_soil_ctx* c, double t, double dt, int64_t nsteps,
+                              const double* bc_table)
+{
+    (void)t;
+    if (!c) return LH_ERR_INVALID_ARG;
+    if (nsteps < 0) return fail(c, LH_ERR_INVALID_ARG, "nsteps < 0");
+    double t0 = now_ms();
+    for (int64_t s = 0; s < nsteps; ++s) {
+        for (int stage = 1; stage <= 3; ++stage) {
+            if (bc_table) memcpy(c->bcv, bc_table + (s * 3 + (stage - 1)) * 4, sizeof c->bcv);
+            int32_t st = lho_soil_stage_ssprk33(c, stage, dt);
+            if (st != LH_OK) return st;
+        }
+    }
+    c->last_ms = now_ms() - t0;
+    c->last_launches = 0;
+    if (c->cfg.flags & LH_FLAG_CHECK_FINITE) {
+        const size_t cells = (size_t)c->ncol * c->nlayer;
+        for (int k = 0; k < 3; ++k)
+            for (size_t i = 0; i < cells; ++i)
+                if (!isfinite(c->f[k][i])) return fail(c, LH_ERR_NONFINITE, "non-finite state");
+    }
+    return LH_OK;
+}
+
+/* Budgets (new in this build): W = Σ ϑ_l dz, E = Σ ρe_int dz.  Neumaier-compensated
+ * so the oracle's sum is accurate to ~1 ulp independent of order.                           */
+static void comp_add(double* s, double* comp, double x)
+{
+    double t = *s + x;
+    if (fabs(*s) >= fabs(x)) *comp += (*s - t) + x;
+    else *comp += (x - t) + *s;
+    *s = t;
+}
+
+int32_t lho_soil_budgets(lho_soil_ctx* c, double out[2])
+{
+    if (!c || !out) return LH_ERR_INVALID_ARG;
+    const size_t cells = (size_t)c->ncol * c->nlayer;
+    double s0 = 0, c0 = 0, s1 = 0, c1 = 0;
+    for (size_t i = 0; i < cells; ++i) {
+        comp_add(&s0, &c0, c->f[0][i]);
+        comp_add(&s1, &c1, c->f[2][i]);
+    }
+    out[0] = (s0 + c0) * c->dz;
+    out[1] = (s1 + c1) * c->dz;
+    return LH_OK;
+}
+
+int32_t lho_soil_budgets_allreduce(lho_soil_ctx* c, double out[2]) { return lho_soil_budgets(c, out); }
+
+int32_t lho_soil_diagnostic(lho_soil_ctx* c, int32_t which, double* host, int64_t cs, int64_t ls)
+{
+    if (!c || !host) return LH_ERR_INVALID_ARG;
+    if (which < 0 || which >= LH_NUM_DIAGS) return fail(c, LH_ERR_INVALID_ARG, "bad diagnostic id");
+    const int n = c->nlayer;
+    const int model = c->cfg.model;
+    const double kappa_dry = lho_k_dry(&c->cfg.params);
+    /* K/ψ are defined whenever ϑ_l, θ_i exist (all models); κ/T from ρe_int need an energy
+     * model, otherwise T is the prescribed aux and κ is evaluated with it.                  */
+    for (int64_t col = 0; col < c->ncol; ++col)
+        for (int i = 0; i < n; ++i) {
+            size_t o = (size_t)col * n + i;
+            int m = has_heat(model) ? LH_MODEL_COUPLED : LH_MODEL_RICHARDS;
+            cell_closures cc = closures_at(&c->cfg.params, m, kappa_dry, c->f[0][o], c->f[1][o],
+                                           c->f[2][o], c->f[3][o]);
+            if (which == LH_DIAG_KAPPA && !has_heat(model)) {
+                cell_closures ch = closures_at(&c->cfg.params, LH_MODEL_HEAT, kappa_dry, c->f[0][o],
+                                               c->f[1][o], 0.0, c->f[3][o]);
+                cc.kappa = ch.kappa;
+            }
+            double v = which == LH_DIAG_K ? cc.K : which == LH_DIAG_PSI ? cc.psi
+                     : which == LH_DIAG_KAPPA ? cc.kappa : cc.T;
+            host[col * cs + i * ls] = v;
+        }
+    return LH_OK;
+}
+
+int32_t lho_soil_sync(lho_soil_ctx* c) { (void)c; return LH_OK; }
+
+int32_t lho_soil_last_step_timing(lho_soil_ctx* c, double* ms_out, int64_t* launches_out)
+{
+    if (!c) return LH_ERR_INVALID_ARG;
+    if (ms_out) *ms_out = c->last_ms;
+    if (launches_out) *launches_out = c->last_launches;
+    return LH_OK;
+}
+
+int32_t lho_soil_device_ptr(lho_soil_ctx* c, int32_t field, void** dptr, int64_t* ncol_padded)
+{
+    (void)field; (void)dptr; (void)ncol_padded;
+    return fail(c, LH_ERR_NO_DEVICE, "the oracle has no device memory");
+}
+
+int32_t lho_soil_comm_unique_id(uint8_t id_out[128]) { memset(id_out, 0, 128); return LH_OK; }
+
+int32_t lho_soil_comm_init(lho_soil_ctx* c, int32_t nranks, int32_t rank, const uint8_t id[128])
+{
+    (void)c; (void)nranks; (void)rank; (void)id;
+    return LH_OK;
+}
