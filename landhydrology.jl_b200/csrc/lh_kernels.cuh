@@ -1,0 +1,67 @@
+// lh_kernels.cuh — kernel argument block and launch entry points (implemented in lh_kernels.cu).
+#pragma once
+
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "lh_closures.cuh"
+
+// Device layout of every cell field: column-fastest SoA, element (layer, col) at
+// [layer * ncol_pad + col]; ncol_pad is a multiple of 32 so that a warp (32 adjacent columns)
+// reads/writes two full, aligned 128-byte lines per field per layer.
+struct LhKernelArgs {
+    LhDevParams p;
+    const double* in_th;   // stage input ϑ_l            (state U, or stage buffer V)
+    const double* in_ti;   // θ_i                         (always U: its tendency is 0)
+    const double* in_re;   // stage input ρe_int          (U or V)
+    const double* aux_T;   // prescribed T                (Richards; read only if viscosity is on)
+    const double* u0_th;   // U, for the stage-2/3 combine
+    const double* u0_re;
+    double* out_th;        // V (stage 1, 2) / U (stage 3) / tendency buffer (stage 0)
+    double* out_re;
+    const double* zc;      // nlayer centre coordinates
+    int64_t ncol_pad;
+    int32_t nlayer;
+    int32_t Lc;            // layers per thread (vertical chunk)
+    int32_t W;             // chunks per column = blockDim.y
+    int32_t top_e_kind, top_h_kind, bot_e_kind, bot_h_kind;
+    double bcv[4];         // LH_BCV_* boundary values for THIS launch
+    double dt;
+};
+
+struct LhLaunchShape {
+    int32_t Lc, W, G;      // chunk length, chunks per column, column groups (of 32) per block
+    int64_t nblocks;
+    size_t smem_bytes;
+};
+
+LhLaunchShape lh_choose_shape(int model, int64_t ncol_pad, int32_t nlayer, int sm_count);
+
+// stage 0 = tendency only; 1..3 = fused RHS + SSPRK33 stage.
+cudaError_t lh_launch_stage(int model, int stage, const LhKernelArgs& args, const LhLaunchShape& shape,
+                            cudaStream_t stream);
+
+// Pointwise diagnostics (LH_DIAG_*): out[layer*ncol_pad+col].
+cudaError_t lh_launch_diagnostic(int model, int which, const LhDevParams& p, const double* th,
+                                 const double* ti, const double* re, const double* T, double* out,
+                                 int64_t ncells_pad, cudaStream_t stream);
+
+// Deterministic budgets: out2[0] = sum ϑ_l dz, out2[1] = sum ρe_int dz over columns < ncol.
+cudaError_t lh_launch_budgets(const double* th, const double* re, int64_t ncol, int64_t ncol_pad,
+                              int32_t nlayer, double dz, double* partials, int32_t npartials,
+                              double* out2, cudaStream_t stream);
+
+// Layout transforms between a dense host-layout staging block [col][layer] (layer fastest) and
+// the device SoA [layer][ncol_pad].
+cudaError_t lh_launch_to_soa(const double* staged, double* soa, int64_t col0, int64_t ncols,
+                             int32_t nlayer, int64_t ncol_pad, cudaStream_t stream);
+cudaError_t lh_launch_from_soa(const double* soa, double* staged, int64_t col0, int64_t ncols,
+                               int32_t nlayer, int64_t ncol_pad, cudaStream_t stream);
+// Broadcast an nlayer profile to all columns; replicate the last valid column into the padding.
+cudaError_t lh_launch_fill_profile(const double* profile, double* soa, int32_t nlayer, int64_t ncol_pad,
+                                   cudaStream_t stream);
+cudaError_t lh_launch_fill_padding(double* soa, int64_t ncol, int64_t ncol_pad, int32_t nlayer,
+                                   cudaStream_t stream);
+// Counts non-finite values of a field into *count (uint64).
+cudaError_t lh_launch_count_nonfinite(const double* soa, int64_t n, unsigned long long* count,
+                                      cudaStream_t stream);

@@ -1,0 +1,705 @@
+// lh_soil_api.cu — the C ABI of include/lh_soil.h over the sm_100a kernels of lh_kernels.cu.
+//
+// There is NO CPU path in this library: without a CUDA device lh_soil_create returns
+// LH_ERR_NO_DEVICE.  NCCL is resolved lazily with dlopen("libnccl.so.2") so a single-GPU host
+// needs no NCCL at all; it is used for exactly one thing, the 2-double budget all-reduce.
+#include "lh_soil.h"
+
+#include <cuda_runtime.h>
+#include <dlfcn.h>
+#include <math.h>
+#include <stdarg.h>
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+
+#include <algorithm>
+#include <new>
+#include <vector>
+
+#include "lh_kernels.cuh"
+
+// ------------------------------------------------------------------------------------------------
+// NCCL, resolved at run time
+// ------------------------------------------------------------------------------------------------
+namespace {
+typedef struct ncclComm* ncclComm_t_;
+struct NcclUniqueId_ { char internal[128]; };
+struct NcclApi {
+    void* handle = nullptr;
+    int (*GetUniqueId)(NcclUniqueId_*) = nullptr;
+    int (*CommInitRank)(ncclComm_t_*, int, NcclUniqueId_, int) = nullptr;
+    int (*AllReduce)(const void*, void*, size_t, int, int, ncclComm_t_, cudaStream_t) = nullptr;
+    int (*CommDestroy)(ncclComm_t_) = nullptr;
+    const char* (*GetErrorString)(int) = nullptr;
+    bool ok = false;
+};
+constexpr int NCCL_FLOAT64 = 8;   // ncclDouble
+constexpr int NCCL_SUM = 0;       // ncclSum
+
+NcclApi& nccl()
+{
+    static NcclApi api;
+    static bool tried = false;
+    if (!tried) {
+        tried = true;
+        // RTLD_NOLOAD first: reuse the libnccl already mapped by the host process (e.g. torch's)
+        api.handle = dlopen("libnccl.so.2", RTLD_NOW | RTLD_NOLOAD);
+        if (!api.handle) api.handle = dlopen("libnccl.so.2", RTLD_NOW | RTLD_GLOBAL);
+        if (!api.handle) api.handle = dlopen("libnccl.so", RTLD_NOW | RTLD_GLOBAL);
+        if (api.handle) {
+            api.GetUniqueId = (int (*)(NcclUniqueId_*))dlsym(api.handle, "ncclGetUniqueId");
+            api.CommInitRank = (int (*)(ncclComm_t_*, int, NcclUniqueId_, int))dlsym(api.handle, "ncclCommInitRank");
+            api.AllReduce = (int (*)(const void*, void*, size_t, int, int, ncclComm_t_, cudaStream_t))dlsym(api.handle, "ncclAllReduce");
+            api.CommDestroy = (int (*)(ncclComm_t_))dlsym(api.handle, "ncclCommDestroy");
+            api.GetErrorString = (const char* (*)(int))dlsym(api.handle, "ncclGetErrorString");
+            api.ok = api.GetUniqueId && api.CommInitRank && api.AllReduce && api.CommDestroy;
+        }
+    }
+    return api;
+}
+
+thread_local char g_create_err[256] = "";
+}  // namespace
+
+// ------------------------------------------------------------------------------------------------
+// Context
+// ------------------------------------------------------------------------------------------------
+struct lh_soil_ctx {
+    lh_soil_config cfg;
+    int device = 0;
+    int sm_count = 148;
+    int64_t ncol = 0, ncol_pad = 0;
+    int32_t nlayer = 0;
+    int model = 0;
+    LhDevParams dp;
+    LhLaunchShape shape;
+    cudaStream_t stream = nullptr, copy_stream = nullptr;
+    cudaEvent_t ev_start = nullptr, ev_stop = nullptr, ev_copy[2] = {nullptr, nullptr}, ev_xpose[2] = {nullptr, nullptr};
+    double* U[LH_NUM_FIELDS] = {nullptr, nullptr, nullptr, nullptr};   // ϑ_l, θ_i, ρe_int, T
+    double* V[3] = {nullptr, nullptr, nullptr};                        // stage buffer (ϑ_l, -, ρe_int)
+    double* tend[3] = {nullptr, nullptr, nullptr};                     // lazily allocated (ϑ_l, -, ρe_int)
+    double* zc_dev = nullptr;
+    std::vector<double> zc;
+    double* stage_dev[2] = {nullptr, nullptr};   // layout staging blocks [chunk_cols][nlayer]
+    double* stage_host = nullptr;                // pinned, 2 * chunk
+    int64_t chunk_cols = 0;
+    double* partials = nullptr;
+    int32_t npartials = 0;
+    double* budget_dev = nullptr;                // 2 doubles (+2 for the all-reduce result)
+    unsigned long long* nonfinite_dev = nullptr;
+    double bcv[4] = {0, 0, 0, 0};
+    ncclComm_t_ comm = nullptr;
+    int nranks = 1, rank = 0;
+    bool timing_valid = false;
+    int64_t last_launches = 0;
+    char err[512] = "";
+};
+
+namespace {
+
+int32_t fail(lh_soil_ctx* ctx, int32_t code, const char* fmt, ...)
+{
+    char* dst = ctx ? ctx->err : g_create_err;
+    size_t cap = ctx ? sizeof(ctx->err) : sizeof(g_create_err);
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(dst, cap, fmt, ap);
+    va_end(ap);
+    return code;
+}
+
+#define LH_CUDA(ctx, expr)                                                                          \
+    do {                                                                                            \
+        cudaError_t e_ = (expr);                                                                    \
+        if (e_ != cudaSuccess)                                                                      \
+            return fail(ctx, LH_ERR_CUDA, "%s failed: %s (%s:%d)", #expr, cudaGetErrorString(e_), __FILE__, __LINE__); \
+    } while (0)
+
+bool has_water(int m) { return m == LH_MODEL_RICHARDS || m == LH_MODEL_COUPLED; }
+bool has_heat(int m) { return m == LH_MODEL_HEAT || m == LH_MODEL_COUPLED; }
+
+// The reference's vertical_flux method table (boundary_conditions.jl:295-444).
+int32_t validate_face(const lh_soil_face_bc& bc, int model, const char* face)
+{
+    const int ek = bc.energy_kind, hk = bc.hydrology_kind;
+    if (ek < 0 || ek > 3 || hk < 0 || hk > 3) return fail(nullptr, LH_ERR_INVALID_ARG, "%s: unknown BC kind", face);
+    if (has_heat(model)) {
+        if (!(ek == LH_BC_FLUX || ek == LH_BC_DIRICHLET))
+            return fail(nullptr, LH_ERR_UNSUPPORTED_BC, "%s: energy BC kind %d has no vertical_flux method for SoilEnergyModel", face, ek);
+    } else if (!(ek == LH_BC_NONE || ek == LH_BC_FLUX)) {
+        return fail(nullptr, LH_ERR_UNSUPPORTED_BC, "%s: energy BC kind %d has no vertical_flux method for PrescribedTemperatureModel", face, ek);
+    }
+    if (has_water(model)) {
+        if (!(hk == LH_BC_FLUX || hk == LH_BC_DIRICHLET || hk == LH_BC_FREE_DRAINAGE))
+            return fail(nullptr, LH_ERR_UNSUPPORTED_BC, "%s: hydrology BC kind %d has no vertical_flux method for SoilHydrologyModel", face, hk);
+    } else if (!(hk == LH_BC_NONE || hk == LH_BC_FLUX)) {
+        return fail(nullptr, LH_ERR_UNSUPPORTED_BC, "%s: hydrology BC kind %d has no vertical_flux method for PrescribedHydrologyModel", face, hk);
+    }
+    return LH_OK;
+}
+
+LhDevParams derive_params(const lh_soil_config& cfg)
+{
+    const lh_soil_params& q = cfg.params;
+    LhDevParams d;
+    memset(&d, 0, sizeof d);
+    d.dz = (cfg.zmax - cfg.zmin) / cfg.nlayer;
+    d.inv_dz = 1.0 / d.dz;
+    d.half_dz = d.dz / 2.0;            // boundary_cf_distance, boundary_conditions.jl:196-208 (A1)
+    d.inv_half_dz = 1.0 / d.half_dz;
+    d.nu = q.nu;
+    d.theta_r = q.theta_r;
+    d.theta_r_eps = q.theta_r + LH_EPS;
+    d.inv_nu_thr = 1.0 / (q.nu - q.theta_r);
+    d.S_s_inv = 1.0 / q.S_s;
+    d.vg_m = q.vg_m;
+    d.vg_inv_m = 1.0 / q.vg_m;
+    d.vg_inv_n = 1.0 / q.vg_n;
+    d.neg_inv_alpha = -1.0 / q.vg_alpha;
+    d.Ksat = q.Ksat;
+    d.visc_gamma = q.visc_gamma;
+    d.visc_T_ref = q.visc_T_ref;
+    d.imp_c = -q.imp_Omega * log(10.0);
+    d.rho_c_ds = q.rho_c_ds;
+    d.rhocp_l = q.cp_l * q.rho_cloud_liq;
+    d.rhocp_i = q.cp_i * q.rho_cloud_ice;
+    d.rhoi_LH = q.rho_cloud_ice * q.LH_f0;
+    d.T_0 = q.T_0;
+    d.inv_nu = 1.0 / q.nu;
+    d.kersten_p1 = (1.0 + q.nu_ss_om - q.a * q.nu_ss_quartz - q.nu_ss_gravel) / 2.0;
+    d.kersten_p2 = 1.0 - q.nu_ss_om;
+    d.kersten_p3 = 1.0 + q.nu_ss_om;
+    d.neg_b = -q.b;
+    d.k_unfrozen = q.kappa_sat_unfrozen;
+    d.k_frozen = q.kappa_sat_frozen;
+    d.ln_k_unfrozen = log(q.kappa_sat_unfrozen);
+    d.ln_k_frozen = log(q.kappa_sat_frozen);
+    {   // k_dry, SoilHeatParameterizations.jl:268-294 (a per-call scalar in the reference)
+        const double rho_b = (1.0 - q.nu) * q.rho_p;
+        const double numerator = (q.kappa_dry_parameter * q.kappa_solid - q.K_therm) * rho_b + q.K_therm * q.rho_p;
+        const double denom = q.rho_p - (1.0 - q.kappa_dry_parameter) * rho_b;
+        d.kappa_dry = numerator / denom;
+    }
+    d.visc_on = q.viscosity_factor != LH_FACTOR_NONE;
+    d.imp_on = q.impedance_factor != LH_FACTOR_NONE;
+    d.om_zero = q.nu_ss_om == 0.0;
+    return d;
+}
+
+void free_all(lh_soil_ctx* c)
+{
+    if (!c) return;
+    cudaSetDevice(c->device);
+    if (c->comm && nccl().ok) nccl().CommDestroy(c->comm);
+    for (auto& p : c->U) if (p) cudaFree(p);
+    for (auto& p : c->V) if (p) cudaFree(p);
+    for (auto& p : c->tend) if (p) cudaFree(p);
+    for (auto& p : c->stage_dev) if (p) cudaFree(p);
+    if (c->stage_host) cudaFreeHost(c->stage_host);
+    if (c->zc_dev) cudaFree(c->zc_dev);
+    if (c->partials) cudaFree(c->partials);
+    if (c->budget_dev) cudaFree(c->budget_dev);
+    if (c->nonfinite_dev) cudaFree(c->nonfinite_dev);
+    if (c->ev_start) cudaEventDestroy(c->ev_start);
+    if (c->ev_stop) cudaEventDestroy(c->ev_stop);
+    for (auto& e : c->ev_copy) if (e) cudaEventDestroy(e);
+    for (auto& e : c->ev_xpose) if (e) cudaEventDestroy(e);
+    if (c->stream) cudaStreamDestroy(c->stream);
+    if (c->copy_stream) cudaStreamDestroy(c->copy_stream);
+    delete c;
+}
+
+size_t field_bytes(const lh_soil_ctx* c) { return (size_t)c->ncol_pad * c->nlayer * sizeof(double); }
+
+bool field_ok(int f) { return f >= 0 && f < LH_NUM_FIELDS; }
+
+int32_t ensure_staging(lh_soil_ctx* c)
+{
+    if (c->stage_dev[0]) return LH_OK;
+    // ~32 MiB blocks: large enough for PCIe efficiency, small enough to pipeline copy and transpose
+    int64_t cols = std::max<int64_t>(32, (32ll << 20) / ((int64_t)c->nlayer * 8));
+    cols = std::min<int64_t>((cols + 31) / 32 * 32, c->ncol_pad);
+    c->chunk_cols = cols;
+    const size_t bytes = (size_t)cols * c->nlayer * sizeof(double);
+    for (int k = 0; k < 2; ++k) LH_CUDA(c, cudaMalloc(&c->stage_dev[k], bytes));
+    LH_CUDA(c, cudaMallocHost(&c->stage_host, 2 * bytes));
+    return LH_OK;
+}
+
+// host (col_stride, layer_stride) -> device SoA.  Pipelined in column blocks over two staging
+// buffers: [gather into pinned block if the host layout is not dense] -> H2D -> transpose kernel.
+int32_t upload_field(lh_soil_ctx* c, double* soa, const double* host, int64_t cs, int64_t ls)
+{
+    if (!host) return fail(c, LH_ERR_INVALID_ARG, "host pointer is NULL");
+    LH_CUDA(c, cudaSetDevice(c->device));
+    const int n = c->nlayer;
+    if (cs == 0) {   // one nlayer profile broadcast to all columns
+        std::vector<double> prof(n);
+        for (int i = 0; i < n; ++i) prof[i] = host[(int64_t)i * ls];
+        LH_CUDA(c, cudaMemcpyAsync((c->zc_dev + c->nlayer), prof.data(), n * sizeof(double), cudaMemcpyHostToDevice, c->stream));
+        LH_CUDA(c, cudaStreamSynchronize(c->stream));   // prof is a stack vector
+        LH_CUDA(c, lh_launch_fill_profile((c->zc_dev + c->nlayer), soa, n, c->ncol_pad, c->stream));
+        return LH_OK;
+    }
+    if (cs == 1 && ls == c->ncol_pad && c->ncol == c->ncol_pad) {   // already device layout
+        LH_CUDA(c, cudaMemcpyAsync(soa, host, field_bytes(c), cudaMemcpyHostToDevice, c->stream));
+        LH_CUDA(c, cudaStreamSynchronize(c->stream));
+        return LH_OK;
+    }
+    if (cs == 1) {   // column-fastest host block with its own layer stride
+        LH_CUDA(c, cudaMemcpy2DAsync(soa, c->ncol_pad * sizeof(double), host, ls * sizeof(double),
+                                     c->ncol * sizeof(double), n, cudaMemcpyHostToDevice, c->stream));
+        LH_CUDA(c, lh_launch_fill_padding(soa, c->ncol, c->ncol_pad, n, c->stream));
+        LH_CUDA(c, cudaStreamSynchronize(c->stream));
+        return LH_OK;
+    }
+    int32_t st = ensure_staging(c);
+    if (st != LH_OK) return st;
+    const bool dense = (ls == 1 && cs == n);
+    const size_t blk = (size_t)c->chunk_cols * n;
+    int k = 0;
+    for (int64_t c0 = 0; c0 < c->ncol; c0 += c->chunk_cols, k ^= 1) {
+        const int64_t m = std::min<int64_t>(c->chunk_cols, c->ncol - c0);
+        // buffer k is free once the transpose that last read it has finished
+        LH_CUDA(c, cudaEventSynchronize(c->ev_xpose[k]));
+        const double* src;
+        if (dense) {
+            src = host + c0 * n;
+        } else {
+            double* pin = c->stage_host + (size_t)k * blk;
+            for (int64_t cc = 0; cc < m; ++cc)
+                for (int i = 0; i < n; ++i) pin[cc * n + i] = host[(c0 + cc) * cs + (int64_t)i * ls];
+            src = pin;
+        }
+        LH_CUDA(c, cudaMemcpyAsync(c->stage_dev[k], src, (size_t)m * n * sizeof(double), cudaMemcpyHostToDevice, c->copy_stream));
+        LH_CUDA(c, cudaEventRecord(c->ev_copy[k], c->copy_stream));
+        LH_CUDA(c, cudaStreamWaitEvent(c->stream, c->ev_copy[k], 0));
+        LH_CUDA(c, lh_launch_to_soa(c->stage_dev[k], soa, c0, m, n, c->ncol_pad, c->stream));
+        LH_CUDA(c, cudaEventRecord(c->ev_xpose[k], c->stream));
+    }
+    LH_CUDA(c, lh_launch_fill_padding(soa, c->ncol, c->ncol_pad, n, c->stream));
+    LH_CUDA(c, cudaStreamSynchronize(c->stream));   // host pointers are borrowed for the call only
+    return LH_OK;
+}
+
+int32_t download_field(lh_soil_ctx* c, const double* soa, double* host, int64_t cs, int64_t ls)
+{
+    if (!host) return fail(c, LH_ERR_INVALID_ARG, "host pointer is NULL");
+    if (cs == 0 && c->ncol != 1) return fail(c, LH_ERR_INVALID_ARG, "col_stride 0 is only valid for uploads");
+    LH_CUDA(c, cudaSetDevice(c->device));
+    const int n = c->nlayer;
+    if (cs == 1 || c->ncol == 1) {
+        const int64_t lstride = (c->ncol == 1) ? ls : ls;
+        LH_CUDA(c, cudaMemcpy2DAsync(host, lstride * sizeof(double), soa, c->ncol_pad * sizeof(double),
+                                     c->ncol * sizeof(double), n, cudaMemcpyDeviceToHost, c->stream));
+        LH_CUDA(c, cudaStreamSynchronize(c->stream));
+        return LH_OK;
+    }
+    int32_t st = ensure_staging(c);
+    if (st != LH_OK) return st;
+    const bool dense = (ls == 1 && cs == n);
+    const size_t blk = (size_t)c->chunk_cols * n;
+    // pipeline: transpose block j on `stream`, D2H on `copy_stream`, scatter on the host
+    struct Pending { int64_t c0, m; bool active; } pend[2] = {{0, 0, false}, {0, 0, false}};
+    auto finish = [&](int k) -> int32_t {
+        if (!pend[k].active) return LH_OK;
+        LH_CUDA(c, cudaEventSynchronize(c->ev_copy[k]));
+        if (!dense) {
+            const double* pin = c->stage_host + (size_t)k * blk;
+            for (int64_t cc = 0; cc < pend[k].m; ++cc)
+                for (int i = 0; i < n; ++i) host[(pend[k].c0 + cc) * cs + (int64_t)i * ls] = pin[cc * n + i];
+        }
+        pend[k].active = false;
+        return LH_OK;
+    };
+    int k = 0;
+    for (int64_t c0 = 0; c0 < c->ncol; c0 += c->chunk_cols, k ^= 1) {
+        const int64_t m = std::min<int64_t>(c->chunk_cols, c->ncol - c0);
+        if ((st = finish(k)) != LH_OK) return st;   // staging buffer k must be drained first
+        LH_CUDA(c, lh_launch_from_soa(soa, c->stage_dev[k], c0, m, n, c->ncol_pad, c->stream));
+        LH_CUDA(c, cudaEventRecord(c->ev_xpose[k], c->stream));
+        LH_CUDA(c, cudaStreamWaitEvent(c->copy_stream, c->ev_xpose[k], 0));
+        double* dst = dense ? host + c0 * n : c->stage_host + (size_t)k * blk;
+        LH_CUDA(c, cudaMemcpyAsync(dst, c->stage_dev[k], (size_t)m * n * sizeof(double), cudaMemcpyDeviceToHost, c->copy_stream));
+        LH_CUDA(c, cudaEventRecord(c->ev_copy[k], c->copy_stream));
+        pend[k] = {c0, m, true};
+    }
+    if ((st = finish(0)) != LH_OK) return st;
+    if ((st = finish(1)) != LH_OK) return st;
+    LH_CUDA(c, cudaStreamSynchronize(c->copy_stream));
+    // later kernels on `stream` must not overwrite a staging buffer that copy_stream still reads:
+    // both events are complete here.
+    return LH_OK;
+}
+
+void fill_args(lh_soil_ctx* c, int stage, double dt, LhKernelArgs& a)
+{
+    a.p = c->dp;
+    const bool from_V = stage >= 2;
+    a.in_th = (from_V && has_water(c->model)) ? c->V[0] : c->U[0];
+    a.in_ti = c->U[1];
+    a.in_re = (from_V && has_heat(c->model)) ? c->V[2] : c->U[2];
+    a.aux_T = c->U[3];
+    a.u0_th = c->U[0];
+    a.u0_re = c->U[2];
+    if (stage == 0) { a.out_th = c->tend[0]; a.out_re = c->tend[2]; }
+    else if (stage == 3) { a.out_th = c->U[0]; a.out_re = c->U[2]; }
+    else { a.out_th = c->V[0]; a.out_re = c->V[2]; }
+    a.zc = c->zc_dev;
+    a.ncol_pad = c->ncol_pad;
+    a.nlayer = c->nlayer;
+    a.Lc = c->shape.Lc;
+    a.W = c->shape.W;
+    a.top_e_kind = c->cfg.top.energy_kind;
+    a.top_h_kind = c->cfg.top.hydrology_kind;
+    a.bot_e_kind = c->cfg.bottom.energy_kind;
+    a.bot_h_kind = c->cfg.bottom.hydrology_kind;
+    memcpy(a.bcv, c->bcv, sizeof a.bcv);
+    a.dt = dt;
+}
+
+int32_t check_finite(lh_soil_ctx* c)
+{
+    LH_CUDA(c, cudaMemsetAsync(c->nonfinite_dev, 0, sizeof(unsigned long long), c->stream));
+    const int64_t n = (int64_t)c->ncol_pad * c->nlayer;
+    if (has_water(c->model)) LH_CUDA(c, lh_launch_count_nonfinite(c->U[0], n, c->nonfinite_dev, c->stream));
+    if (has_heat(c->model)) LH_CUDA(c, lh_launch_count_nonfinite(c->U[2], n, c->nonfinite_dev, c->stream));
+    unsigned long long cnt = 0;
+    LH_CUDA(c, cudaMemcpyAsync(&cnt, c->nonfinite_dev, sizeof cnt, cudaMemcpyDeviceToHost, c->stream));
+    LH_CUDA(c, cudaStreamSynchronize(c->stream));
+    if (cnt) return fail(c, LH_ERR_NONFINITE, "%llu non-finite state values (the reference raises DomainError)", cnt);
+    return LH_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+int32_t lh_soil_abi_version(void) { return LH_SOIL_ABI_VERSION; }
+
+const char* lh_soil_last_error(const lh_soil_ctx* ctx) { return ctx ? ctx->err : g_create_err; }
+
+int32_t lh_soil_create(const lh_soil_config* cfg, lh_soil_ctx** out)
+{
+    if (!cfg || !out) return fail(nullptr, LH_ERR_INVALID_ARG, "cfg/out is NULL");
+    *out = nullptr;
+    if (cfg->struct_size != (int32_t)sizeof(lh_soil_config))
+        return fail(nullptr, LH_ERR_INVALID_ARG, "lh_soil_config.struct_size mismatch (%d != %zu)", cfg->struct_size, sizeof(lh_soil_config));
+    if (cfg->ncol < 1 || cfg->nlayer < 1) return fail(nullptr, LH_ERR_INVALID_ARG, "ncol and nlayer must be >= 1");
+    if (cfg->model < 0 || cfg->model > 2) return fail(nullptr, LH_ERR_INVALID_ARG, "unknown model kind %d", cfg->model);
+    if (!(cfg->zmin < cfg->zmax)) return fail(nullptr, LH_ERR_DOMAIN, "zlim[1] < zlim[2] violated");   // domain.jl:30
+    int32_t st;
+    if ((st = validate_face(cfg->top, cfg->model, "top")) != LH_OK) return st;
+    if ((st = validate_face(cfg->bottom, cfg->model, "bottom")) != LH_OK) return st;
+
+    int ndev = 0;
+    cudaError_t e = cudaGetDeviceCount(&ndev);
+    if (e != cudaSuccess || ndev == 0)
+        return fail(nullptr, LH_ERR_NO_DEVICE, "no CUDA device (%s); this library has no CPU fallback", cudaGetErrorString(e));
+    if (cfg->device < 0 || cfg->device >= ndev)
+        return fail(nullptr, LH_ERR_NO_DEVICE, "device ordinal %d out of range (%d devices)", cfg->device, ndev);
+
+    lh_soil_ctx* c = new (std::nothrow) lh_soil_ctx();
+    if (!c) return fail(nullptr, LH_ERR_INVALID_ARG, "out of memory");
+    c->cfg = *cfg;
+    c->device = cfg->device;
+    c->ncol = cfg->ncol;
+    c->ncol_pad = (cfg->ncol + 31) / 32 * 32;
+    c->nlayer = cfg->nlayer;
+    c->model = cfg->model;
+    c->dp = derive_params(*cfg);
+    c->bcv[LH_BCV_TOP_ENERGY] = cfg->top.energy_value;
+    c->bcv[LH_BCV_TOP_HYDROLOGY] = cfg->top.hydrology_value;
+    c->bcv[LH_BCV_BOTTOM_ENERGY] = cfg->bottom.energy_value;
+    c->bcv[LH_BCV_BOTTOM_HYDROLOGY] = cfg->bottom.hydrology_value;
+
+#define LH_CREATE_CUDA(expr)                                                                        \
+    do {                                                                                            \
+        cudaError_t e_ = (expr);                                                                    \
+        if (e_ != cudaSuccess) {                                                                    \
+            fail(nullptr, LH_ERR_CUDA, "%s failed: %s", #expr, cudaGetErrorString(e_));             \
+            free_all(c);                                                                            \
+            return LH_ERR_CUDA;                                                                     \
+        }                                                                                           \
+    } while (0)
+
+    LH_CREATE_CUDA(cudaSetDevice(c->device));
+    cudaDeviceProp prop;
+    LH_CREATE_CUDA(cudaGetDeviceProperties(&prop, c->device));
+    c->sm_count = prop.multiProcessorCount;
+    LH_CREATE_CUDA(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
+    LH_CREATE_CUDA(cudaStreamCreateWithFlags(&c->copy_stream, cudaStreamNonBlocking));
+    LH_CREATE_CUDA(cudaEventCreate(&c->ev_start));
+    LH_CREATE_CUDA(cudaEventCreate(&c->ev_stop));
+    for (int k = 0; k < 2; ++k) {
+        LH_CREATE_CUDA(cudaEventCreateWithFlags(&c->ev_copy[k], cudaEventDisableTiming));
+        LH_CREATE_CUDA(cudaEventCreateWithFlags(&c->ev_xpose[k], cudaEventDisableTiming));
+    }
+    c->shape = lh_choose_shape(c->model, c->ncol_pad, c->nlayer, c->sm_count);
+
+    const size_t fb = field_bytes(c);
+    // ϑ_l, θ_i always exist (prognostic or prescribed); ρe_int with an energy model; T aux only
+    // for the Richards model (Ya.soil.T)
+    LH_CREATE_CUDA(cudaMalloc(&c->U[0], fb));
+    LH_CREATE_CUDA(cudaMalloc(&c->U[1], fb));
+    LH_CREATE_CUDA(cudaMemsetAsync(c->U[0], 0, fb, c->stream));
+    LH_CREATE_CUDA(cudaMemsetAsync(c->U[1], 0, fb, c->stream));
+    if (has_heat(c->model)) {
+        LH_CREATE_CUDA(cudaMalloc(&c->U[2], fb));
+        LH_CREATE_CUDA(cudaMemsetAsync(c->U[2], 0, fb, c->stream));
+        LH_CREATE_CUDA(cudaMalloc(&c->V[2], fb));
+    }
+    if (has_water(c->model)) LH_CREATE_CUDA(cudaMalloc(&c->V[0], fb));
+
+    // z_c: faces zmin + j (zmax - zmin) / n, centres are face midpoints (domain.jl:58-69)
+    c->zc.resize(c->nlayer);
+    for (int i = 0; i < c->nlayer; ++i) {
+        const double zf0 = cfg->zmin + (cfg->zmax - cfg->zmin) * (double)i / (double)c->nlayer;
+        const double zf1 = cfg->zmin + (cfg->zmax - cfg->zmin) * (double)(i + 1) / (double)c->nlayer;
+        c->zc[i] = (zf0 + zf1) / 2.0;
+    }
+    // zc_dev holds zc followed by an nlayer profile scratch
+    LH_CREATE_CUDA(cudaMalloc(&c->zc_dev, 2 * c->nlayer * sizeof(double)));
+    LH_CREATE_CUDA(cudaMemcpyAsync(c->zc_dev, c->zc.data(), c->nlayer * sizeof(double), cudaMemcpyHostToDevice, c->stream));
+
+    if (c->model == LH_MODEL_RICHARDS) {
+        // PrescribedTemperatureModel default T ≡ 288 (models.jl:51-54)
+        LH_CREATE_CUDA(cudaMalloc(&c->U[3], fb));
+        std::vector<double> prof(c->nlayer, 288.0);
+        LH_CREATE_CUDA(cudaMemcpyAsync(c->zc_dev + c->nlayer, prof.data(), c->nlayer * sizeof(double), cudaMemcpyHostToDevice, c->stream));
+        LH_CREATE_CUDA(cudaStreamSynchronize(c->stream));
+        LH_CREATE_CUDA(lh_launch_fill_profile(c->zc_dev + c->nlayer, c->U[3], c->nlayer, c->ncol_pad, c->stream));
+    }
+    c->npartials = (int32_t)std::min<int64_t>(1024, std::max<int64_t>(1, (c->ncol + 255) / 256));
+    LH_CREATE_CUDA(cudaMalloc(&c->partials, 2 * c->npartials * sizeof(double)));
+    LH_CREATE_CUDA(cudaMalloc(&c->budget_dev, 4 * sizeof(double)));
+    LH_CREATE_CUDA(cudaMalloc(&c->nonfinite_dev, sizeof(unsigned long long)));
+    LH_CREATE_CUDA(cudaStreamSynchronize(c->stream));
+#undef LH_CREATE_CUDA
+    *out = c;
+    return LH_OK;
+}
+
+int32_t lh_soil_destroy(lh_soil_ctx* ctx)
+{
+    free_all(ctx);
+    return LH_OK;
+}
+
+int32_t lh_soil_get_zc(const lh_soil_ctx* ctx, double* zc_out)
+{
+    if (!ctx || !zc_out) return LH_ERR_INVALID_ARG;
+    memcpy(zc_out, ctx->zc.data(), ctx->nlayer * sizeof(double));
+    return LH_OK;
+}
+
+int32_t lh_soil_set_state(lh_soil_ctx* c, int32_t field, const double* host, int64_t cs, int64_t ls)
+{
+    if (!c) return LH_ERR_INVALID_ARG;
+    if (!field_ok(field)) return fail(c, LH_ERR_INVALID_ARG, "bad field id %d", field);
+    if (!c->U[field]) return fail(c, LH_ERR_INVALID_ARG, "field %d does not exist for model kind %d", field, c->model);
+    return upload_field(c, c->U[field], host, cs, ls);
+}
+
+int32_t lh_soil_set_aux(lh_soil_ctx* c, int32_t field, const double* host, int64_t cs, int64_t ls)
+{
+    return lh_soil_set_state(c, field, host, cs, ls);
+}
+
+int32_t lh_soil_get_state(lh_soil_ctx* c, int32_t field, double* host, int64_t cs, int64_t ls)
+{
+    if (!c) return LH_ERR_INVALID_ARG;
+    if (!field_ok(field)) return fail(c, LH_ERR_INVALID_ARG, "bad field id %d", field);
+    if (!c->U[field]) return fail(c, LH_ERR_INVALID_ARG, "field %d does not exist for model kind %d", field, c->model);
+    return download_field(c, c->U[field], host, cs, ls);
+}
+
+int32_t lh_soil_set_bc_values(lh_soil_ctx* c, const double values[4])
+{
+    if (!c || !values) return LH_ERR_INVALID_ARG;
+    memcpy(c->bcv, values, sizeof c->bcv);
+    return LH_OK;
+}
+
+static int32_t launch_stage(lh_soil_ctx* c, int stage, double dt)
+{
+    LhKernelArgs a;
+    fill_args(c, stage, dt, a);
+    LH_CUDA(c, lh_launch_stage(c->model, stage, a, c->shape, c->stream));
+    return LH_OK;
+}
+
+int32_t lh_soil_rhs(lh_soil_ctx* c, double t)
+{
+    (void)t;
+    if (!c) return LH_ERR_INVALID_ARG;
+    LH_CUDA(c, cudaSetDevice(c->device));
+    const size_t fb = field_bytes(c);
+    if (has_water(c->model) && !c->tend[0]) LH_CUDA(c, cudaMalloc(&c->tend[0], fb));
+    if (has_heat(c->model) && !c->tend[2]) LH_CUDA(c, cudaMalloc(&c->tend[2], fb));
+    int32_t st = launch_stage(c, 0, 0.0);
+    if (st != LH_OK) return st;
+    if (c->cfg.flags & LH_FLAG_CHECK_FINITE) {
+        LH_CUDA(c, cudaMemsetAsync(c->nonfinite_dev, 0, sizeof(unsigned long long), c->stream));
+        const int64_t n = (int64_t)c->ncol_pad * c->nlayer;
+        if (c->tend[0]) LH_CUDA(c, lh_launch_count_nonfinite(c->tend[0], n, c->nonfinite_dev, c->stream));
+        if (c->tend[2]) LH_CUDA(c, lh_launch_count_nonfinite(c->tend[2], n, c->nonfinite_dev, c->stream));
+        unsigned long long cnt = 0;
+        LH_CUDA(c, cudaMemcpyAsync(&cnt, c->nonfinite_dev, sizeof cnt, cudaMemcpyDeviceToHost, c->stream));
+        LH_CUDA(c, cudaStreamSynchronize(c->stream));
+        if (cnt) return fail(c, LH_ERR_NONFINITE, "%llu non-finite tendency values (the reference raises DomainError)", cnt);
+    }
+    return LH_OK;
+}
+
+int32_t lh_soil_get_tendency(lh_soil_ctx* c, int32_t field, double* host, int64_t cs, int64_t ls)
+{
+    if (!c) return LH_ERR_INVALID_ARG;
+    if (field < 0 || field > 2) return fail(c, LH_ERR_INVALID_ARG, "bad field id %d", field);
+    if (!host) return fail(c, LH_ERR_INVALID_ARG, "host pointer is NULL");
+    if (field == LH_FIELD_THETA_I || !c->tend[field]) {
+        // dθ_i ≡ 0 (right_hand_side.jl:182,359); non-prognostic fields have no tendency
+        if (field != LH_FIELD_THETA_I && !((field == 0 && has_water(c->model)) || (field == 2 && has_heat(c->model))))
+            return fail(c, LH_ERR_INVALID_ARG, "field %d is not prognostic for model kind %d", field, c->model);
+        if (field != LH_FIELD_THETA_I) return fail(c, LH_ERR_STATE, "lh_soil_rhs has not been called");
+        for (int64_t col = 0; col < c->ncol; ++col)
+            for (int i = 0; i < c->nlayer; ++i) host[col * cs + (int64_t)i * ls] = 0.0;
+        return LH_OK;
+    }
+    return download_field(c, c->tend[field], host, cs, ls);
+}
+
+int32_t lh_soil_stage_ssprk33(lh_soil_ctx* c, int32_t stage, double dt)
+{
+    if (!c) return LH_ERR_INVALID_ARG;
+    if (stage < 1 || stage > 3) return fail(c, LH_ERR_INVALID_ARG, "stage must be 1, 2 or 3");
+    LH_CUDA(c, cudaSetDevice(c->device));
+    return launch_stage(c, stage, dt);
+}
+
+int32_t lh_soil_step_ssprk33(lh_soil_ctx* c, double t, double dt, int64_t nsteps, const double* bc_table)
+{
+    (void)t;
+    if (!c) return LH_ERR_INVALID_ARG;
+    if (nsteps < 0) return fail(c, LH_ERR_INVALID_ARG, "nsteps < 0");
+    LH_CUDA(c, cudaSetDevice(c->device));
+    LH_CUDA(c, cudaEventRecord(c->ev_start, c->stream));
+    for (int64_t s = 0; s < nsteps; ++s) {
+        for (int stage = 1; stage <= 3; ++stage) {
+            if (bc_table) memcpy(c->bcv, bc_table + (s * 3 + (stage - 1)) * 4, sizeof c->bcv);
+            int32_t st = launch_stage(c, stage, dt);
+            if (st != LH_OK) return st;
+        }
+    }
+    LH_CUDA(c, cudaEventRecord(c->ev_stop, c->stream));
+    c->timing_valid = true;
+    c->last_launches = 3 * nsteps;
+    if (c->cfg.flags & LH_FLAG_CHECK_FINITE) return check_finite(c);
+    return LH_OK;
+}
+
+int32_t lh_soil_budgets(lh_soil_ctx* c, double out[2])
+{
+    if (!c || !out) return LH_ERR_INVALID_ARG;
+    LH_CUDA(c, cudaSetDevice(c->device));
+    const double* re = c->U[2] ? c->U[2] : c->U[1];   // no energy model: E budget of θ_i slot is meaningless -> report 0
+    LH_CUDA(c, lh_launch_budgets(c->U[0], re, c->ncol, c->ncol_pad, c->nlayer, c->dp.dz, c->partials,
+                                 c->npartials, c->budget_dev, c->stream));
+    LH_CUDA(c, cudaMemcpyAsync(out, c->budget_dev, 2 * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+    LH_CUDA(c, cudaStreamSynchronize(c->stream));
+    if (!c->U[2]) out[1] = 0.0;
+    return LH_OK;
+}
+
+int32_t lh_soil_diagnostic(lh_soil_ctx* c, int32_t which, double* host, int64_t cs, int64_t ls)
+{
+    if (!c || !host) return LH_ERR_INVALID_ARG;
+    if (which < 0 || which >= LH_NUM_DIAGS) return fail(c, LH_ERR_INVALID_ARG, "bad diagnostic id %d", which);
+    LH_CUDA(c, cudaSetDevice(c->device));
+    const size_t fb = field_bytes(c);
+    // reuse (or create) a tendency buffer as scratch
+    const int slot = has_water(c->model) ? 0 : 2;
+    if (!c->tend[slot]) LH_CUDA(c, cudaMalloc(&c->tend[slot], fb));
+    LH_CUDA(c, lh_launch_diagnostic(c->model, which, c->dp, c->U[0], c->U[1], c->U[2], c->U[3], c->tend[slot],
+                                    (int64_t)c->ncol_pad * c->nlayer, c->stream));
+    return download_field(c, c->tend[slot], host, cs, ls);
+}
+
+int32_t lh_soil_sync(lh_soil_ctx* c)
+{
+    if (!c) return LH_ERR_INVALID_ARG;
+    LH_CUDA(c, cudaSetDevice(c->device));
+    LH_CUDA(c, cudaStreamSynchronize(c->stream));
+    return LH_OK;
+}
+
+int32_t lh_soil_last_step_timing(lh_soil_ctx* c, double* ms_out, int64_t* launches_out)
+{
+    if (!c) return LH_ERR_INVALID_ARG;
+    if (!c->timing_valid) return fail(c, LH_ERR_STATE, "no lh_soil_step_ssprk33 call to time yet");
+    LH_CUDA(c, cudaSetDevice(c->device));
+    LH_CUDA(c, cudaEventSynchronize(c->ev_stop));
+    float ms = 0.f;
+    LH_CUDA(c, cudaEventElapsedTime(&ms, c->ev_start, c->ev_stop));
+    if (ms_out) *ms_out = (double)ms;
+    if (launches_out) *launches_out = c->last_launches;
+    return LH_OK;
+}
+
+int32_t lh_soil_device_ptr(lh_soil_ctx* c, int32_t field, void** dptr, int64_t* ncol_padded)
+{
+    if (!c || !dptr) return LH_ERR_INVALID_ARG;
+    if (!field_ok(field) || !c->U[field]) return fail(c, LH_ERR_INVALID_ARG, "field %d does not exist", field);
+    *dptr = c->U[field];
+    if (ncol_padded) *ncol_padded = c->ncol_pad;
+    return LH_OK;
+}
+
+int32_t lh_soil_comm_unique_id(uint8_t id_out[128])
+{
+    if (!id_out) return LH_ERR_INVALID_ARG;
+    NcclApi& n = nccl();
+    if (!n.ok) return fail(nullptr, LH_ERR_NCCL, "libnccl.so.2 could not be loaded");
+    NcclUniqueId_ id;
+    int r = n.GetUniqueId(&id);
+    if (r != 0) return fail(nullptr, LH_ERR_NCCL, "ncclGetUniqueId failed: %s", n.GetErrorString ? n.GetErrorString(r) : "?");
+    memcpy(id_out, id.internal, 128);
+    return LH_OK;
+}
+
+int32_t lh_soil_comm_init(lh_soil_ctx* c, int32_t nranks, int32_t rank, const uint8_t id[128])
+{
+    if (!c || !id) return LH_ERR_INVALID_ARG;
+    if (nranks < 1 || rank < 0 || rank >= nranks) return fail(c, LH_ERR_INVALID_ARG, "bad rank %d of %d", rank, nranks);
+    NcclApi& n = nccl();
+    if (!n.ok) return fail(c, LH_ERR_NCCL, "libnccl.so.2 could not be loaded");
+    LH_CUDA(c, cudaSetDevice(c->device));
+    if (c->comm) { n.CommDestroy(c->comm); c->comm = nullptr; }
+    NcclUniqueId_ uid;
+    memcpy(uid.internal, id, 128);
+    int r = n.CommInitRank(&c->comm, nranks, uid, rank);
+    if (r != 0) return fail(c, LH_ERR_NCCL, "ncclCommInitRank failed: %s", n.GetErrorString ? n.GetErrorString(r) : "?");
+    c->nranks = nranks;
+    c->rank = rank;
+    return LH_OK;
+}
+
+int32_t lh_soil_budgets_allreduce(lh_soil_ctx* c, double out[2])
+{
+    if (!c || !out) return LH_ERR_INVALID_ARG;
+    if (!c->comm) return fail(c, LH_ERR_STATE, "lh_soil_comm_init has not been called");
+    NcclApi& n = nccl();
+    LH_CUDA(c, cudaSetDevice(c->device));
+    const double* re = c->U[2] ? c->U[2] : c->U[1];
+    LH_CUDA(c, lh_launch_budgets(c->U[0], re, c->ncol, c->ncol_pad, c->nlayer, c->dp.dz, c->partials,
+                                 c->npartials, c->budget_dev, c->stream));
+    int r = n.AllReduce(c->budget_dev, c->budget_dev + 2, 2, NCCL_FLOAT64, NCCL_SUM, c->comm, c->stream);
+    if (r != 0) return fail(c, LH_ERR_NCCL, "ncclAllReduce failed: %s", n.GetErrorString ? n.GetErrorString(r) : "?");
+    LH_CUDA(c, cudaMemcpyAsync(out, c->budget_dev + 2, 2 * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+    LH_CUDA(c, cudaStreamSynchronize(c->stream));
+    if (!c->U[2]) out[1] = 0.0;
+    return LH_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,268 @@
+"""GPU parity tests proper: the CUDA library (through the C ABI) against the CPU oracle on the
+same seeded inputs.
+
+Gates (BASELINE.json north_star / SURVEY §8d):
+  * per tendency evaluation:  max_i |a_i - r_i| <= 1e-12 * max(‖r‖∞ over the column, max_j|F_j|/Δz)
+  * state after N SSPRK33 steps: max |u - u_ref| <= 1e-10 * max |u_ref| per field
+"""
+import numpy as np
+import pytest
+
+import workloads as w
+
+pytestmark = pytest.mark.gpu
+
+lh = w.lh
+abi = w.abi
+D, F, FD, N = abi.LH_BC_DIRICHLET, abi.LH_BC_FLUX, abi.LH_BC_FREE_DRAINAGE, abi.LH_BC_NONE
+
+TOL_TENDENCY = 1e-12
+TOL_STATE = 1e-10
+
+
+def _pair(cuda, oracle, wl):
+    g = lh.SoilContext(cuda, wl.config())
+    o = lh.SoilContext(oracle, wl.config())
+    wl.upload(g)
+    wl.upload(o)
+    return g, o
+
+
+def _prognostic(model):
+    return {abi.LH_MODEL_RICHARDS: (0,), abi.LH_MODEL_HEAT: (2,), abi.LH_MODEL_COUPLED: (0, 2)}[model]
+
+
+def assert_tendency_parity(g, o, model, tol=TOL_TENDENCY):
+    g.rhs(0.0)
+    o.rhs(0.0)
+    worst = 0.0
+    for f in _prognostic(model):
+        a, r = g.get_tendency(f), o.get_tendency(f)
+        assert np.all(np.isfinite(r)), "oracle produced non-finite tendencies: bad test input"
+        scale = w.tendency_scale(o, f)
+        err = np.max(np.abs(a - r) / scale[:, None])
+        worst = max(worst, err)
+        assert err <= tol, f"field {f}: scaled tendency error {err:.3e} > {tol:g}"
+    assert np.all(g.get_tendency(1) == 0.0)      # dθ_i ≡ 0 (right_hand_side.jl:182,359)
+    return worst
+
+
+def assert_state_parity(g, o, model, dt, nsteps, table=None, tol=TOL_STATE):
+    g.step(0.0, dt, nsteps, table)
+    o.step(0.0, dt, nsteps, table)
+    for f in _prognostic(model):
+        a, r = g.get_state(f), o.get_state(f)
+        assert np.all(np.isfinite(r))
+        err = np.max(np.abs(a - r)) / np.max(np.abs(r))
+        assert err <= tol, f"field {f}: state error {err:.3e} > {tol:g} after {nsteps} steps"
+    # θ_i is never rewritten on the device; the oracle's generic axpy must leave it unchanged too
+    assert np.array_equal(g.get_state(1), o.get_state(1))
+
+
+# ---- the BASELINE configs at oracle-sized shapes ---------------------------------------------------
+@pytest.mark.parametrize("ncol,nlayer", [(1, 20), (1, 64), (96, 64), (33, 16), (257, 100), (64, 256)])
+def test_coupled_tendency_and_state(cuda, oracle, ncol, nlayer):
+    """C2/C4: coupled water+heat, Dirichlet top (ϑ_l, T), FreeDrainage/zero-flux bottom."""
+    wl = w.coupled_workload(ncol=ncol, nlayer=nlayer, seed=100 + ncol + nlayer)
+    g, o = _pair(cuda, oracle, wl)
+    assert_tendency_parity(g, o, wl.model)
+    assert_state_parity(g, o, wl.model, wl.dt, 10)
+
+
+@pytest.mark.parametrize("ncol,nlayer", [(1, 150), (1, 50), (1024, 100), (40, 37)])
+def test_richards_tendency_and_state(cuda, oracle, ncol, nlayer):
+    """C1/C3: Richards only, Bonan sand, Dirichlet top 0.267, FreeDrainage bottom."""
+    wl = w.richards_workload(ncol=ncol, nlayer=nlayer, seed=200 + ncol + nlayer)
+    g, o = _pair(cuda, oracle, wl)
+    assert_tendency_parity(g, o, wl.model)
+    assert_state_parity(g, o, wl.model, wl.dt, 10)
+
+
+@pytest.mark.parametrize("ncol,nlayer", [(1, 60), (128, 60), (70, 24)])
+def test_heat_tendency_and_state(cuda, oracle, ncol, nlayer):
+    wl = w.heat_workload(ncol=ncol, nlayer=nlayer, seed=300 + ncol + nlayer)
+    g, o = _pair(cuda, oracle, wl)
+    assert_tendency_parity(g, o, wl.model)
+    assert_state_parity(g, o, wl.model, wl.dt, 10)
+
+
+# ---- every BC kind at both faces ---------------------------------------------------------------------
+BC_FACES_COUPLED = [
+    (F, 0.0, F, 0.0), (F, 3.0, F, -1e-7), (D, 284.0, D, 0.35), (D, 292.0, F, 2e-8), (F, -2.0, D, 0.45),
+    (F, 0.0, FD, 0.0), (D, 280.0, FD, 0.0),
+]
+
+
+@pytest.mark.parametrize("top", BC_FACES_COUPLED)
+@pytest.mark.parametrize("bottom", BC_FACES_COUPLED)
+def test_coupled_all_bc_kinds(cuda, oracle, top, bottom):
+    wl = w.coupled_workload(ncol=40, nlayer=24, seed=17, top=top, bottom=bottom)
+    g, o = _pair(cuda, oracle, wl)
+    assert_tendency_parity(g, o, wl.model)
+
+
+@pytest.mark.parametrize("top", [(N, 0.0, F, 1e-7), (N, 0.0, D, 0.2), (N, 0.0, FD, 0.0), (F, 1.0, D, 0.26)])
+@pytest.mark.parametrize("bottom", [(N, 0.0, F, 0.0), (N, 0.0, D, 0.15), (N, 0.0, FD, 0.0)])
+def test_richards_all_bc_kinds(cuda, oracle, top, bottom):
+    wl = w.richards_workload(ncol=40, nlayer=30, seed=18, top=top, bottom=bottom)
+    g, o = _pair(cuda, oracle, wl)
+    assert_tendency_parity(g, o, wl.model)
+
+
+@pytest.mark.parametrize("top", [(F, 5.0, N, 0.0), (D, 300.0, N, 0.0), (D, 275.0, F, 0.0)])
+@pytest.mark.parametrize("bottom", [(F, -5.0, N, 0.0), (D, 281.0, N, 0.0)])
+def test_heat_all_bc_kinds(cuda, oracle, top, bottom):
+    wl = w.heat_workload(ncol=40, nlayer=30, seed=19, top=top, bottom=bottom)
+    g, o = _pair(cuda, oracle, wl)
+    assert_tendency_parity(g, o, wl.model)
+
+
+# ---- branch coverage of the closures ---------------------------------------------------------------
+def test_ice_and_factors(cuda, oracle):
+    """θ_i > 0 (Kersten frozen branch, κ_sat mix, S != S_eff), TemperatureDependentViscosity and
+    IceImpedance on (SoilWaterParameterizations.jl:76-126)."""
+    wl = w.coupled_workload(ncol=64, nlayer=32, seed=23, ice=True,
+                            viscosity=lh.TemperatureDependentViscosity(), impedance=lh.IceImpedance())
+    g, o = _pair(cuda, oracle, wl)
+    assert_tendency_parity(g, o, wl.model)
+    assert_state_parity(g, o, wl.model, wl.dt, 10)
+    wl = w.richards_workload(ncol=64, nlayer=32, seed=24, ice=True,
+                             viscosity=lh.TemperatureDependentViscosity(), impedance=lh.IceImpedance())
+    g, o = _pair(cuda, oracle, wl)
+    assert_tendency_parity(g, o, wl.model)
+    assert_state_parity(g, o, wl.model, wl.dt, 10)
+    wl = w.heat_workload(ncol=64, nlayer=32, seed=25, ice=True)
+    g, o = _pair(cuda, oracle, wl)
+    assert_tendency_parity(g, o, wl.model)
+
+
+def test_saturated_cells(cuda, oracle):
+    """ϑ_l > ν_eff: the positive pressure-head branch (SoilWaterParameterizations.jl:236-240) and
+    the S >= 1 clamp of K (:276-280), mixed with unsaturated cells in the same columns."""
+    wl = w.coupled_workload(ncol=48, nlayer=32, seed=31)
+    th = wl.fields[0]
+    rng = np.random.default_rng(5)
+    mask = rng.uniform(size=th.shape) < 0.3
+    th[mask] = wl.params.nu + rng.uniform(0.0, 5e-4, size=mask.sum())      # ψ = (ϑ_l - ν)/S_s up to 0.5 m
+    th[0, :4] = wl.params.nu                                              # exactly S = 1
+    g, o = _pair(cuda, oracle, wl)
+    assert_tendency_parity(g, o, wl.model)
+
+
+def test_dry_soil_heat(cuda, oracle):
+    """θ_w < eps: κ_sat = 0, κ = κ_dry (SoilHeatParameterizations.jl:121-123) — the analytic heat
+    test's regime (heat_test_interface.jl)."""
+    wl = w.heat_workload(ncol=16, nlayer=60, seed=41)
+    wl.fields[0][...] = 0.0
+    wl.fields[1][...] = 0.0
+    g, o = _pair(cuda, oracle, wl)
+    assert_tendency_parity(g, o, wl.model)
+
+
+def test_diagnostics_match_oracle(cuda, oracle):
+    """K, ψ, κ, T closures evaluated on the device vs the literal reference formulas."""
+    for ice in (False, True):
+        wl = w.coupled_workload(ncol=64, nlayer=48, seed=51, ice=ice)
+        g, o = _pair(cuda, oracle, wl)
+        for which, tol in ((abi.LH_DIAG_K, 2e-13), (abi.LH_DIAG_PSI, 1e-13), (abi.LH_DIAG_KAPPA, 1e-13), (abi.LH_DIAG_T, 1e-14)):
+            a, r = g.diagnostic(which), o.diagnostic(which)
+            rel = np.max(np.abs(a - r) / np.abs(r))
+            assert rel <= tol, f"diag {which} ice={ice}: rel err {rel:.3e}"
+
+
+# ---- time-dependent Dirichlet values through the bc table ------------------------------------------
+def test_bc_table(cuda, oracle):
+    wl = w.heat_workload(ncol=32, nlayer=40, seed=61)
+    g, o = _pair(cuda, oracle, wl)
+    nsteps = 12
+    table = np.zeros((nsteps, 3, 4))
+    t = 0.0
+    for s in range(nsteps):
+        for k, ts in enumerate((t, t + wl.dt, t + wl.dt / 2)):
+            table[s, k, abi.LH_BCV_TOP_ENERGY] = 290.0 + 3.0 * np.sin(ts / 200.0)
+            table[s, k, abi.LH_BCV_BOTTOM_ENERGY] = 280.0 + 2.0 * np.cos(ts / 300.0)
+        t += wl.dt
+    assert_state_parity(g, o, wl.model, wl.dt, nsteps, table)
+
+
+# ---- transfers / layouts -----------------------------------------------------------------------------
+@pytest.mark.parametrize("ncol,nlayer", [(1, 7), (31, 5), (100, 64), (1000, 33)])
+def test_state_roundtrip_layouts(cuda, ncol, nlayer):
+    wl = w.coupled_workload(ncol=ncol, nlayer=nlayer, seed=71)
+    g = lh.SoilContext(cuda, wl.config())
+    rng = np.random.default_rng(1)
+    a = rng.standard_normal((ncol, nlayer))
+    g.set_state(0, a)                                   # reference layout, dense
+    assert np.array_equal(g.get_state(0), a)
+    big = rng.standard_normal((ncol, 3, nlayer + 2))    # strided view: field-interleaved host block
+    view = big[:, 1, 1:-1]
+    g.set_state(2, view)
+    out = np.zeros_like(big)
+    g.get_state(2, out[:, 1, 1:-1])
+    assert np.array_equal(out[:, 1, 1:-1], view) and np.all(out[:, 0] == 0) and np.all(out[:, 2] == 0)
+    soa = np.ascontiguousarray(a.T)                     # column-fastest host block
+    g.set_state(1, soa.T)
+    assert np.array_equal(g.get_state(1), a)
+    back = np.empty_like(soa)
+    g.get_state(1, back.T)
+    assert np.array_equal(back, soa)
+
+
+def test_budgets_match_oracle(cuda, oracle):
+    wl = w.coupled_workload(ncol=777, nlayer=64, seed=81)
+    g, o = _pair(cuda, oracle, wl)
+    bg, bo = g.budgets(), o.budgets()
+    assert np.all(np.abs(bg - bo) <= 1e-13 * np.abs(bo))
+    bg2 = g.budgets()
+    assert np.array_equal(bg, bg2)                      # fixed-tree reduction: bitwise reproducible
+
+
+# ---- size-independent properties at the BASELINE's full size ---------------------------------------
+def test_full_size_properties(cuda, oracle):
+    """C4 shape (2^20 columns x 64 layers, coupled).  The oracle cannot run this in seconds, so:
+    (1) columns are independent and deterministic: the first 64 columns evolve bit-identically
+        inside the 1M batch and alone;  (2) those 64 columns match the oracle to 1e-10;
+    (3) with zero-flux BCs the water and energy budgets are conserved to round-off."""
+    ncol, nlayer, nsteps = 1 << 20, 64, 5
+    wl = w.coupled_workload(ncol=ncol, nlayer=nlayer, seed=w.BASE_SEED + 3,
+                            top=(F, 0.0, F, 0.0), bottom=(F, 0.0, F, 0.0))
+    g = lh.SoilContext(cuda, wl.config())
+    wl.upload(g)
+    W0 = g.budgets()
+    g.step(0.0, wl.dt, nsteps)
+    W1 = g.budgets()
+    assert abs(W1[0] - W0[0]) <= 1e-12 * abs(W0[0])
+    assert abs(W1[1] - W0[1]) <= 1e-12 * abs(W0[1])
+    sub = 64
+    th_big = g.get_state(0)[:sub].copy()
+    re_big = g.get_state(2)[:sub].copy()
+    g.close()
+    small = w.Workload(model=wl.model, ncol=sub, nlayer=nlayer, zmin=wl.zmin, zmax=wl.zmax, params=wl.params,
+                       top=wl.top, bottom=wl.bottom, dt=wl.dt,
+                       fields={k: v[:sub].copy() for k, v in wl.fields.items()})
+    gs, os_ = _pair(cuda, oracle, small)
+    gs.step(0.0, wl.dt, nsteps)
+    os_.step(0.0, wl.dt, nsteps)
+    assert np.array_equal(gs.get_state(0), th_big) and np.array_equal(gs.get_state(2), re_big)
+    for f, big in ((0, th_big), (2, re_big)):
+        r = os_.get_state(f)
+        assert np.max(np.abs(big - r)) <= TOL_STATE * np.max(np.abs(r))
+
+
+def test_vertical_sweep_shapes(cuda, oracle):
+    """C5: layers 16..1024 at a fixed (oracle-sized) cell count: every chunking of the vertical."""
+    for nlayer in (16, 32, 64, 128, 256, 512, 1024):
+        ncol = max(1, 16384 // nlayer)
+        wl = w.coupled_workload(ncol=ncol, nlayer=nlayer, seed=900 + nlayer, zlim=(-2.0 * nlayer / 64, 0.0))
+        g, o = _pair(cuda, oracle, wl)
+        assert_tendency_parity(g, o, wl.model)
+        assert_state_parity(g, o, wl.model, wl.dt / 4, 4)
+
+
+def test_check_finite_flag(cuda):
+    wl = w.richards_workload(ncol=8, nlayer=16, seed=3)
+    wl.fields[0][3, 5] = np.nan
+    g = lh.SoilContext(cuda, wl.config(flags=abi.LH_FLAG_CHECK_FINITE))
+    wl.upload(g)
+    with pytest.raises(lh.NonFiniteStateError):
+        g.step(0.0, wl.dt, 1)
