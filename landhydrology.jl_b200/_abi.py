@@ -5,8 +5,8 @@ There is NO CPU fallback: :func:`cuda_library` raises if the shared object is mi
 ``lh_soil_create`` returns ``LH_ERR_NO_DEVICE`` when no B200 is visible.
 
 :class:`SoilLibrary` is generic over (path, symbol prefix) only so that the parity tests can
-drive the CPU oracle (``oracle/liblho_soil.so``, prefix ``lho_``) through the very same harness;
-nothing in this package ever names or loads the oracle.
+drive their CPU checker library (same ABI under another prefix) through the very same harness;
+nothing in this package ever names or loads it.
 """
 from __future__ import annotations
 

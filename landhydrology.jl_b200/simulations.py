@@ -42,7 +42,7 @@ class Integrator:
     def __init__(self, engine: SoilEngine, Y: FieldVector, Ya: FieldVector, tspan, dt, saveat, callback,
                  max_chunk: int):
         self.engine = engine
-        self.u = Y
+        self.u = copy_state(Y)   # DiffEqBase.init does not alias u0
         self.p = Ya
         self.t0, self.tf = float(tspan[0]), float(tspan[1])
         self.t = self.t0
@@ -63,7 +63,7 @@ class Integrator:
         self._next_save = 0
         self._device_fresh = True
         self._dynamic_aux = engine.has_time_dependent_aux(self.t0, self.dt)
-        engine.upload(Y)
+        engine.upload(self.u)
         self._save_if_due(force_first=True)
 
     # -- saving ------------------------------------------------------------------------------------

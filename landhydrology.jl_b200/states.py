@@ -146,13 +146,13 @@ def _broadcast_over_cells(fn: Callable, zc: np.ndarray, shape, names_hint=None) 
     if getattr(fn, "vectorized", False):
         z = np.broadcast_to(zc, shape)
         res = fn(z)
-        return {nf(k): np.ascontiguousarray(np.broadcast_to(np.asarray(v, dtype=np.float64), shape)) for k, v in dict(res).items()}
+        return {nf(k): np.array(np.broadcast_to(np.asarray(v, dtype=np.float64), shape), dtype=np.float64, order="C") for k, v in dict(res).items()}
     per_layer = [dict(fn(float(z))) for z in zc]
     names = list(per_layer[0].keys()) if per_layer else list(names_hint or [])
     out = {}
     for k in names:
         col = np.array([d[k] for d in per_layer], dtype=np.float64)
-        out[nf(k)] = np.ascontiguousarray(np.broadcast_to(col, shape))
+        out[nf(k)] = np.array(np.broadcast_to(col, shape), dtype=np.float64, order="C")
     return out
 
 

@@ -55,8 +55,10 @@ def assert_state_parity(g, o, model, dt, nsteps, table=None, tol=TOL_STATE):
         assert np.all(np.isfinite(r))
         err = np.max(np.abs(a - r)) / np.max(np.abs(r))
         assert err <= tol, f"field {f}: state error {err:.3e} > {tol:g} after {nsteps} steps"
-    # θ_i is never rewritten on the device; the oracle's generic axpy must leave it unchanged too
-    assert np.array_equal(g.get_state(1), o.get_state(1))
+    # dθ_i ≡ 0.  The device never rewrites θ_i (bitwise constant); the reference's generic axpy
+    # (u0 + 2 u2 + 2 dt 0)/3 may move a non-zero θ_i by an ulp per step, which the oracle reproduces.
+    ti_g, ti_o = g.get_state(1), o.get_state(1)
+    assert np.max(np.abs(ti_g - ti_o)) <= 4 * nsteps * np.finfo(np.float64).eps * max(np.max(np.abs(ti_o)), 1e-300)
 
 
 # ---- the BASELINE configs at oracle-sized shapes ---------------------------------------------------

@@ -1,0 +1,277 @@
+"""The host-side mirror of the reference API, exercised the way the reference's own tests do.
+
+Each test restates a reference test (file:line under /root/reference/test) through the Python
+mirror: Column / SoilParams / vanGenuchten / SoilColumnBC / SoilModel / initialize_states / make_rhs /
+Simulation / step! / run!.  Parametrised over the backend library: "oracle" runs on CPU (host logic
+only, via the test-only ``use_library`` hook), "cuda" is the product on the B200 (marked gpu).
+"""
+import math
+
+import numpy as np
+import pytest
+
+import workloads as w
+
+lh = w.lh
+abi = w.abi
+
+
+@pytest.fixture(params=["oracle", pytest.param("cuda", marks=pytest.mark.gpu)])
+def backend(request, oracle):
+    lib = oracle if request.param == "oracle" else lh.cuda_library()
+    with lh.use_library(lib):
+        yield request.param
+
+
+param_set = lh.EarthParameterSet()
+
+
+def coupled_model(bc=None, n=20):
+    sp = w.coupled_soil_params()
+    domain = lh.Column(np.float64, zlim=(-2.0, 0.0), nelements=n)
+    bc = bc or lh.SoilColumnBC(
+        top=lh.SoilComponentBC(hydrology=lh.VerticalFlux(0.0), energy=lh.VerticalFlux(0.0)),
+        bottom=lh.SoilComponentBC(hydrology=lh.VerticalFlux(0.0), energy=lh.VerticalFlux(0.0)),
+    )
+    return lh.SoilModel(
+        np.float64, domain=domain, energy_model=lh.SoilEnergyModel(),
+        hydrology_model=lh.SoilHydrologyModel(hydraulic_model=w.coupled_vg()),
+        boundary_conditions=bc, soil_param_set=sp, earth_param_set=param_set,
+    )
+
+
+# ---- test/test_domains.jl ---------------------------------------------------------------------------
+def test_domains():
+    for FT in (np.float32, np.float64):
+        d = lh.Column(FT, zlim=(0.0, 1.0), nelements=2)
+        assert d.zlim == (0.0, 1.0) and d.nelements == 2                      # :2-8
+        assert lh.ndims(d) == 1                                               # :18
+        assert lh.length(lh.Column(FT, zlim=(1.0, 2.0), nelements=2)) == 1.0  # :22
+        assert lh.size(lh.Column(FT, zlim=(1.0, 4.0), nelements=2)) == 3.0    # :26
+        assert str(d) == "[0.0, 1.0]"                                         # :29-31 (show)
+        assert isinstance(d, lh.Column) and d.FT is FT
+    with pytest.raises(AssertionError):                                       # domain.jl:30
+        lh.Column(zlim=(1.0, 1.0), nelements=2)
+    box = lh.HybridBox(zlim=(-1.5, 0.0), nelements=(32, 32, 100))
+    assert box.ncolumns == 1024 and box.nelements == 100 and lh.ndims(box) == 3
+    cs, fs = lh.make_function_space(lh.Column(zlim=(-2.0, 0.0), nelements=20))
+    assert np.allclose(lh.coordinates(cs), np.arange(-1.95, 0.0, 0.1), atol=1e-14) and len(fs.z) == 21
+
+
+# ---- test/SoilModel/test_rhs.jl ---------------------------------------------------------------------
+def test_empty_rhs_and_update_aux():
+    domain = lh.Column(np.float64, zlim=(-2.0, 0.0), nelements=20)
+    Tp = lambda z, t: 10.0 * z + t
+    ϑ_lp = lambda z, t: 10.0 * z * t
+    θ_ip = lambda z, t: 0.0
+    soil_model = lh.SoilModel(
+        np.float64, domain=domain, energy_model=lh.PrescribedTemperatureModel(T_profile=Tp),
+        hydrology_model=lh.PrescribedHydrologyModel(ϑ_l_profile=ϑ_lp, θ_i_profile=θ_ip),
+        boundary_conditions=None, earth_param_set=None,
+    )
+    Y = lh.FieldVector()
+    t = 0.0
+    space_c, _ = lh.make_function_space(domain)
+    zc = lh.coordinates(space_c)
+    p = lh.initialize_auxiliary(soil_model, t, zc)
+    soil_rhs_ = lh.make_rhs(soil_model)
+    dY = lh.similar(Y)
+    soil_rhs_(dY, Y, p, t)
+    assert dY == Y                                                            # :32
+    update_aux_en_ = lh.make_update_aux(soil_model.energy_model)
+    update_aux_hydr_ = lh.make_update_aux(soil_model.hydrology_model)
+    t = 10.0
+    update_aux_en_(p, t)
+    update_aux_hydr_(p, t)
+    assert np.allclose(lh.parent(p.soil.T), [Tp(z, t) for z in p.zc])         # :39
+    assert np.allclose(lh.parent(p.soil.ϑ_l), [ϑ_lp(z, t) for z in p.zc])     # :40
+    assert np.allclose(lh.parent(p.soil.θ_i), [θ_ip(z, t) for z in p.zc])     # :41
+
+
+# ---- test/SoilModel/coupled.jl:123-235 --------------------------------------------------------------
+def test_default_ic_and_rhs_known_answer(backend):
+    soil_model = coupled_model()
+    Y_init, Ya_init = lh.default_initial_conditions(soil_model)
+    assert np.allclose(lh.parent(Ya_init.zc), np.arange(-1.95, 0.0, 0.1), atol=1e-14)   # :198
+    assert np.allclose(lh.parent(Y_init.soil.ϑ_l), 0.25)                                # :199
+    assert np.allclose(lh.parent(Y_init.soil.θ_i), 0.0)                                 # :200
+    T0 = lh.T_0(soil_model.earth_param_set)
+    ρc_s = lh.volumetric_heat_capacity(0.25, 0.0, soil_model.soil_param_set.ρc_ds, param_set)
+    ρe_int = lh.volumetric_internal_energy(0.0, ρc_s, T0, param_set)
+    assert np.allclose(lh.parent(Y_init.soil.ρe_int), ρe_int)                           # :217
+    dY = lh.similar(Y_init)
+    soil_rhs_ = lh.make_rhs(soil_model)
+    out = soil_rhs_(dY, Y_init, Ya_init, 0.0)
+    assert out is dY
+    assert np.allclose(lh.parent(dY.soil.θ_i), 0.0)                                     # :221
+    assert np.allclose(lh.parent(dY.soil.ρe_int), 0.0, atol=1e-8)                       # :222
+    S = lh.effective_saturation(0.5, 0.25, 0.0)
+    K = lh.hydraulic_conductivity(soil_model.hydrology_model.hydraulic_model, S, 1.0, 1.0)
+    expected_flux = np.zeros(21) - K
+    expected_flux[-1] = 0.0
+    expected_flux[0] = 0.0
+    minus_div_flux = -(expected_flux[1:] - expected_flux[:-1]) / 0.1
+    assert np.sum(lh.parent(dY.soil.ϑ_l) - minus_div_flux) < np.finfo(float).eps       # :234
+    assert np.max(np.abs(lh.parent(dY.soil.ϑ_l) - minus_div_flux)) <= 1e-12 * K / 0.1
+
+
+def test_default_ic_errors_for_other_models():
+    """richards_equation.jl:53, heat_test_interface.jl:55: @test_throws ErrorException."""
+    domain = lh.Column(zlim=(-10.0, 0.0), nelements=50)
+    m = lh.SoilModel(domain=domain, energy_model=lh.PrescribedTemperatureModel(),
+                     hydrology_model=lh.SoilHydrologyModel(), boundary_conditions=lh.SoilColumnBC(),
+                     earth_param_set=param_set)
+    with pytest.raises(RuntimeError, match="No default IC"):
+        lh.default_initial_conditions(m)
+
+
+# ---- test/SoilModel/richards_equation.jl:1-95, shortened --------------------------------------------
+def test_richards_simulation_step_and_run(backend):
+    ν = 0.495
+    msp = lh.SoilParams(ν=ν, S_s=1e-3)
+    t0, dt, n = 0.0, 100.0, 50
+    tf = 60 * 60 * 24 * 2.5      # 2.5 of the reference's 36 days: same code path, CPU-test sized
+    domain = lh.Column(np.float64, zlim=(-10.0, 0.0), nelements=n)
+    bc = lh.SoilColumnBC(top=lh.SoilComponentBC(hydrology=lh.VerticalFlux(0.0)),
+                         bottom=lh.SoilComponentBC(hydrology=lh.VerticalFlux(0.0)))
+    hydraulics_model = lh.vanGenuchten(n=2.0, α=2.6, Ksat=0.0443 / 3600 / 100, θr=0.0)
+    soil_model = lh.SoilModel(np.float64, domain=domain, energy_model=lh.PrescribedTemperatureModel(),
+                              hydrology_model=lh.SoilHydrologyModel(hydraulic_model=hydraulics_model),
+                              boundary_conditions=bc, soil_param_set=msp, earth_param_set=param_set)
+
+    def initial_conditions(z, model):
+        return dict(ϑ_l=0.494, θ_i=0.0)
+
+    Y, Ya = lh.initialize_states(soil_model, initial_conditions, t0)
+    assert set(Ya.soil.keys()) == {"T"} and np.all(Ya.soil.T == 288.0)       # models.jl:53 default profile
+    soil_sim = lh.Simulation(soil_model, lh.SSPRK33(), Y_init=Y, dt=dt, tspan=(t0, tf), Ya_init=Ya,
+                             saveat=60 * dt, progress=True, progress_message=lambda dt, u, p, t: t)
+    assert lh.step_(soil_sim) is None                                        # :73
+    assert soil_sim.integrator.t == dt
+    lh.run_(soil_sim)                                                        # :74
+    sol = soil_sim.integrator.sol
+    assert sol.t[0] == t0 and sol.t[-1] == tf
+    assert np.allclose(np.diff(sol.t), 60 * dt)
+    assert len(sol.u) == len(sol.t) == int(tf / (60 * dt)) + 1
+    W = [np.sum(u.soil.ϑ_l) for u in sol.u]
+    assert np.allclose(W, W[0], rtol=1e-12)                                  # zero-flux BCs conserve water
+    ϑ = sol.u[-1].soil.ϑ_l
+    assert ϑ[0] > 0.494 > ϑ[-1]                                              # draining towards hydrostatic
+
+
+# ---- test/SoilModel/heat_test_interface.jl, shortened: time-dependent Dirichlet through Simulation ---
+def test_heat_simulation_time_dependent_dirichlet(backend):
+    sp = lh.SoilParams(ν=0.495, ν_ss_gravel=0.1, ν_ss_om=0.1, ν_ss_quartz=0.1, ρc_ds=0.43314518988433487,
+                       κ_solid=8.0, κ_sat_unfrozen=0.57, κ_sat_frozen=2.29)
+    t0, tf, dt, n = 0.0, 0.25, 1e-4, 60
+    domain = lh.Column(np.float64, zlim=(0.0, 1.0), nelements=n)
+    A, ω = 5.0, 2 * math.pi
+    bc = lh.SoilColumnBC(top=lh.SoilComponentBC(energy=lh.Dirichlet(lambda t: 0.0)),
+                         bottom=lh.SoilComponentBC(energy=lh.Dirichlet(lambda t: A * math.cos(ω * t))))
+    soil_model = lh.SoilModel(np.float64, domain=domain, energy_model=lh.SoilEnergyModel(),
+                              hydrology_model=lh.PrescribedHydrologyModel(), boundary_conditions=bc,
+                              soil_param_set=sp, earth_param_set=param_set)
+
+    def energy_ic(z, model):
+        ρc_s = lh.volumetric_heat_capacity(0.0, 0.0, model.soil_param_set.ρc_ds, model.earth_param_set)
+        return dict(ρe_int=lh.volumetric_internal_energy(0.0, ρc_s, 0.0, model.earth_param_set))
+
+    Y, Ya = lh.initialize_states(soil_model, energy_ic, t0)
+    assert set(Ya.soil.keys()) == {lh.states.nf("ϑ_l"), lh.states.nf("θ_i")}
+    sim = lh.Simulation(soil_model, lh.SSPRK33(), Y_init=Y, dt=dt, tspan=(t0, tf), Ya_init=Ya, saveat=60 * dt)
+    assert lh.step_(sim) is None
+    lh.run_(sim)
+    sol = sim.integrator.sol
+    assert abs(sol.t[-1] - tf) < 1e-12
+    # same integration at the ABI level with an explicitly built bc table must agree bit for bit
+    eng = lh.SoilEngine(soil_model, t0)
+    eng.upload(Y)
+    nsteps = int(round(tf / dt))
+    table = np.zeros((nsteps, 3, 4))
+    t = 0.0
+    for s in range(nsteps):
+        for k, ts in enumerate((t, t + dt, t + 0.5 * dt)):
+            table[s, k, abi.LH_BCV_BOTTOM_ENERGY] = A * math.cos(ω * ts)
+        t = t + dt
+    eng.ctx.step(0.0, dt, nsteps, table)
+    ref = eng.ctx.get_state(abi.LH_FIELD_RHO_E_INT)[0]
+    assert np.array_equal(sol.u[-1].soil.ρe_int, ref)
+    ρc_s = lh.volumetric_heat_capacity(0.0, 0.0, sp.ρc_ds, param_set)
+    T = np.array([lh.temperature_from_ρe_int(e, 0.0, ρc_s, param_set) for e in ref])
+    assert T[0] > T[-1] and abs(T[-1]) < 0.5      # bottom forcing at 5 cos(2π·0.25) decays upward to the 0 K top
+
+
+def test_time_dependent_prescribed_profile(backend):
+    """make_update_aux (right_hand_side.jl:54-62): a T profile that depends on t must be
+    re-evaluated at every stage time; checked against a stage-by-stage ABI-level integration."""
+    vg = w.sand_vg()
+    domain = lh.Column(zlim=(-1.5, 0.0), nelements=30)
+    Tp = lambda z, t: 288.0 + 5.0 * z + 0.5 * t
+    model = lh.SoilModel(
+        domain=domain, energy_model=lh.PrescribedTemperatureModel(T_profile=Tp),
+        hydrology_model=lh.SoilHydrologyModel(hydraulic_model=vg, viscosity_factor=lh.TemperatureDependentViscosity()),
+        boundary_conditions=lh.SoilColumnBC(top=lh.SoilComponentBC(hydrology=lh.Dirichlet(lambda t: 0.267)),
+                                            bottom=lh.SoilComponentBC(hydrology=lh.FreeDrainage())),
+        soil_param_set=w.sand_soil_params(), earth_param_set=param_set)
+    Y, Ya = lh.initialize_states(model, lambda z, m: dict(ϑ_l=0.1 + 0.05 * (z + 1.5), θ_i=0.0), 0.0)
+    dt, nsteps = 0.25, 8
+    sim = lh.Simulation(model, lh.SSPRK33(), Y_init=lh.copy(Y), dt=dt, tspan=(0.0, dt * nsteps), Ya_init=Ya)
+    lh.run_(sim)
+    assert len(sim.integrator.sol.t) == nsteps + 1       # DiffEq default: save every step
+    eng = lh.SoilEngine(model, 0.0)
+    eng.upload(Y)
+    t = 0.0
+    for _ in range(nsteps):
+        for stage, ts in ((1, t), (2, t + dt), (3, t + 0.5 * dt)):
+            prof = np.array([Tp(z, ts) for z in eng.zc])
+            eng.ctx.set_aux(abi.LH_FIELD_T, prof, per_layer=True)
+            eng.ctx.set_bc_values([0.0, 0.267, 0.0, 0.0])
+            eng.ctx.stage(stage, dt)
+        t += dt
+    assert np.array_equal(sim.integrator.sol.u[-1].soil.ϑ_l, eng.ctx.get_state(0)[0])
+    assert np.allclose(Ya.soil.T, [Tp(z, dt * nsteps - 0.5 * dt) for z in Ya.zc])   # last stage time seen by update_aux!
+
+
+def test_hybridbox_columns_equal_column(backend):
+    """HybridBox (BASELINE config C3) = a batch of independent columns: every column of a box with
+    identical ICs equals the single-Column result bit for bit."""
+    vg, sp = w.sand_vg(), w.sand_soil_params()
+    bc = lh.SoilColumnBC(top=lh.SoilComponentBC(hydrology=lh.Dirichlet(lambda t: 0.267)),
+                         bottom=lh.SoilComponentBC(hydrology=lh.FreeDrainage()))
+    kw = dict(energy_model=lh.PrescribedTemperatureModel(), hydrology_model=lh.SoilHydrologyModel(hydraulic_model=vg),
+              boundary_conditions=bc, soil_param_set=sp, earth_param_set=param_set)
+    ic = lambda z, m: dict(ϑ_l=0.1 + 0.02 * math.sin(5 * z), θ_i=0.0)
+    col = lh.SoilModel(domain=lh.Column(zlim=(-1.5, 0.0), nelements=25), **kw)
+    box = lh.SoilModel(domain=lh.HybridBox(zlim=(-1.5, 0.0), nelements=(4, 3, 25)), **kw)
+    res = []
+    for m in (col, box):
+        Y, Ya = lh.initialize_states(m, ic, 0.0)
+        sim = lh.Simulation(m, lh.SSPRK33(), Y_init=Y, dt=0.25, tspan=(0.0, 5.0), Ya_init=Ya, saveat=[5.0])
+        lh.run_(sim)
+        res.append(sim.integrator.sol.u[-1].soil.ϑ_l)
+    assert res[1].shape == (12, 25)
+    for c in range(12):
+        assert np.array_equal(res[1][c], res[0])
+
+
+def test_unsupported_bc_raises(backend):
+    """MethodError analogue, raised when the device context is built (boundary_conditions.jl:295-444)."""
+    bc = lh.SoilColumnBC(top=lh.SoilComponentBC(energy=lh.FreeDrainage(), hydrology=lh.VerticalFlux(0.0)),
+                         bottom=lh.SoilComponentBC(energy=lh.VerticalFlux(0.0), hydrology=lh.VerticalFlux(0.0)))
+    m = coupled_model(bc)
+    Y, Ya = lh.default_initial_conditions(m)
+    with pytest.raises(lh.UnsupportedBCError):
+        lh.make_rhs(m)(lh.similar(Y), Y, Ya, 0.0)
+    with pytest.raises(NotImplementedError):
+        lh.build_config(coupled_model(lh.SoilColumnBC(
+            top=lh.PrescribedAtmosForcing(u_atm=1.0, θ_atm=300.0, z_atm=2.0, θ_scale=300.0, ρ_a_sfc=1.2, q_atm=0.01),
+            bottom=lh.SoilComponentBC(energy=lh.VerticalFlux(0.0), hydrology=lh.VerticalFlux(0.0)))))
+
+
+def test_simulation_argument_errors():
+    m = coupled_model()
+    Y, Ya = lh.default_initial_conditions(m)
+    with pytest.raises(NameError):          # simulation.jl:46-51 dead default-state branch
+        lh.Simulation(m, lh.SSPRK33(), Y_init=None, dt=1.0, tspan=(0.0, 1.0), Ya_init=None)
+    with pytest.raises(NotImplementedError):
+        lh.Simulation(m, object(), Y_init=Y, dt=1.0, tspan=(0.0, 1.0), Ya_init=Ya)
