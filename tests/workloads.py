@@ -118,35 +118,55 @@ def zc_of(zmin, zmax, n):
     return (zf[:-1] + zf[1:]) / 2.0
 
 
-def saturation_profiles(rng, ncol, nlayer, zmin, zmax, lo=0.05, hi=0.98, chunk=65536):
-    """S = clip(s0 + a sin(2π (z - zmin)/L + φ) + 0.02 N(0,1), lo, hi)   (SURVEY §8d)."""
+CHUNK = 16384  # columns per independently seeded block: any shard can generate just its own columns
+
+
+def _chunks(col_range):
+    lo, hi = col_range
+    for k in range(lo // CHUNK, (hi - 1) // CHUNK + 1):
+        c0, c1 = k * CHUNK, (k + 1) * CHUNK
+        yield k, max(lo, c0) - c0, min(hi, c1) - c0, max(lo, c0) - lo, min(hi, c1) - lo
+
+
+def saturation_profiles(seed, col_range, nlayer, zmin, zmax, lo=0.05, hi=0.98):
+    """S = clip(s0 + a sin(2π (z - zmin)/L + φ) + 0.02 N(0,1), lo, hi)   (SURVEY §8d).
+    Block k of CHUNK columns is drawn from default_rng([seed, 1, k]), so the profile of a column
+    does not depend on how the column set is sharded."""
     z = zc_of(zmin, zmax, nlayer)
     L = zmax - zmin
-    S = np.empty((ncol, nlayer), dtype=np.float64)
-    for c0 in range(0, ncol, chunk):
-        c1 = min(ncol, c0 + chunk)
-        m = c1 - c0
-        s0 = rng.uniform(0.3, 0.8, size=(m, 1))
-        a = rng.uniform(0.0, 0.15, size=(m, 1))
-        phi = rng.uniform(0.0, 2 * np.pi, size=(m, 1))
-        noise = rng.standard_normal(size=(m, nlayer))
-        S[c0:c1] = np.clip(s0 + a * np.sin(2 * np.pi * (z[None, :] - zmin) / L + phi) + 0.02 * noise, lo, hi)
+    S = np.empty((col_range[1] - col_range[0], nlayer), dtype=np.float64)
+    for k, a0, a1, o0, o1 in _chunks(col_range):
+        rng = np.random.default_rng([seed, 1, k])
+        s0 = rng.uniform(0.3, 0.8, size=(CHUNK, 1))
+        a = rng.uniform(0.0, 0.15, size=(CHUNK, 1))
+        phi = rng.uniform(0.0, 2 * np.pi, size=(CHUNK, 1))
+        noise = rng.standard_normal(size=(CHUNK, nlayer))
+        blk = np.clip(s0 + a * np.sin(2 * np.pi * (z[None, :] - zmin) / L + phi) + 0.02 * noise, lo, hi)
+        S[o0:o1] = blk[a0:a1]
     return S
 
 
-def temperature_profiles(rng, ncol, nlayer, zmin, zmax, chunk=65536):
+def temperature_profiles(seed, col_range, nlayer, zmin, zmax):
     """T = 285 + 10 U(0,1), smooth in z."""
     z = zc_of(zmin, zmax, nlayer)
     L = zmax - zmin
-    T = np.empty((ncol, nlayer), dtype=np.float64)
-    for c0 in range(0, ncol, chunk):
-        c1 = min(ncol, c0 + chunk)
-        m = c1 - c0
-        base = rng.uniform(0.0, 1.0, size=(m, 1))
-        amp = rng.uniform(0.0, 0.3, size=(m, 1))
-        phi = rng.uniform(0.0, 2 * np.pi, size=(m, 1))
-        T[c0:c1] = 285.0 + 10.0 * np.clip(base + amp * np.sin(2 * np.pi * (z[None, :] - zmin) / L + phi), 0.0, 1.0)
+    T = np.empty((col_range[1] - col_range[0], nlayer), dtype=np.float64)
+    for k, a0, a1, o0, o1 in _chunks(col_range):
+        rng = np.random.default_rng([seed, 2, k])
+        base = rng.uniform(0.0, 1.0, size=(CHUNK, 1))
+        amp = rng.uniform(0.0, 0.3, size=(CHUNK, 1))
+        phi = rng.uniform(0.0, 2 * np.pi, size=(CHUNK, 1))
+        blk = 285.0 + 10.0 * np.clip(base + amp * np.sin(2 * np.pi * (z[None, :] - zmin) / L + phi), 0.0, 1.0)
+        T[o0:o1] = blk[a0:a1]
     return T
+
+
+def ice_profiles(seed, col_range, nlayer, hi):
+    out = np.empty((col_range[1] - col_range[0], nlayer), dtype=np.float64)
+    for k, a0, a1, o0, o1 in _chunks(col_range):
+        rng = np.random.default_rng([seed, 3, k])
+        out[o0:o1] = rng.uniform(0.0, hi, size=(CHUNK, nlayer))[a0:a1]
+    return out
 
 
 def rho_e_int_from_T(p, theta_l_aug, theta_i, T):
@@ -161,16 +181,18 @@ D, F, FD, N = abi.LH_BC_DIRICHLET, abi.LH_BC_FLUX, abi.LH_BC_FREE_DRAINAGE, abi.
 
 
 def coupled_workload(ncol=1 << 20, nlayer=64, seed=None, ice=False, zlim=(-2.0, 0.0),
-                     viscosity=None, impedance=None, top=None, bottom=None, sat_hi=0.98):
+                     viscosity=None, impedance=None, top=None, bottom=None, sat_hi=0.98, col_range=None):
     """BASELINE configs C2/C4/C5-coupled: coupled.jl parameters, Dirichlet top (ϑ_l, T),
     FreeDrainage (water) / zero flux (energy) bottom, dt = 20 s."""
-    rng = np.random.default_rng(BASE_SEED + 3 if seed is None else seed)
+    seed = BASE_SEED + 3 if seed is None else seed
+    cr = (0, ncol) if col_range is None else tuple(col_range)
+    ncol = cr[1] - cr[0]       # the workload holds only the requested shard of columns
     p = make_params(coupled_soil_params(), coupled_vg(), viscosity=viscosity, impedance=impedance)
     zmin, zmax = zlim
-    S = saturation_profiles(rng, ncol, nlayer, zmin, zmax, hi=sat_hi)
-    theta_i = rng.uniform(0.0, 0.05, size=(ncol, nlayer)) if ice else np.zeros((ncol, nlayer))
+    S = saturation_profiles(seed, cr, nlayer, zmin, zmax, hi=sat_hi)
+    theta_i = ice_profiles(seed, cr, nlayer, 0.05) if ice else np.zeros((ncol, nlayer))
     theta = p.theta_r + S * ((p.nu - theta_i) - p.theta_r)
-    T = temperature_profiles(rng, ncol, nlayer, zmin, zmax)
+    T = temperature_profiles(seed, cr, nlayer, zmin, zmax)
     rho_e = rho_e_int_from_T(p, theta, theta_i, T)
     return Workload(
         model=abi.LH_MODEL_COUPLED, ncol=ncol, nlayer=nlayer, zmin=zmin, zmax=zmax, params=p,
@@ -180,14 +202,16 @@ def coupled_workload(ncol=1 << 20, nlayer=64, seed=None, ice=False, zlim=(-2.0, 
 
 
 def richards_workload(ncol=1024, nlayer=100, seed=None, ice=False, zlim=(-1.5, 0.0),
-                      viscosity=None, impedance=None, top=None, bottom=None, sat_hi=0.98):
+                      viscosity=None, impedance=None, top=None, bottom=None, sat_hi=0.98, col_range=None):
     """BASELINE configs C1/C3/C5-Richards: Bonan sand, Dirichlet top ϑ_l = 0.267, FreeDrainage
     bottom, dt = 0.25 s (richards_equation.jl:98-167)."""
-    rng = np.random.default_rng(BASE_SEED + 2 if seed is None else seed)
+    seed = BASE_SEED + 2 if seed is None else seed
+    cr = (0, ncol) if col_range is None else tuple(col_range)
+    ncol = cr[1] - cr[0]
     p = make_params(sand_soil_params(), sand_vg(), viscosity=viscosity, impedance=impedance)
     zmin, zmax = zlim
-    S = saturation_profiles(rng, ncol, nlayer, zmin, zmax, hi=sat_hi)
-    theta_i = rng.uniform(0.0, 0.03, size=(ncol, nlayer)) if ice else np.zeros((ncol, nlayer))
+    S = saturation_profiles(seed, cr, nlayer, zmin, zmax, hi=sat_hi)
+    theta_i = ice_profiles(seed, cr, nlayer, 0.03) if ice else np.zeros((ncol, nlayer))
     theta = p.theta_r + S * ((p.nu - theta_i) - p.theta_r)
     aux_T = None
     if viscosity is not None:
@@ -201,13 +225,14 @@ def richards_workload(ncol=1024, nlayer=100, seed=None, ice=False, zlim=(-1.5, 0
 
 def heat_workload(ncol=256, nlayer=60, seed=None, ice=False, zlim=(0.0, 1.0), top=None, bottom=None):
     """Heat-only model (prescribed hydrology), coupled.jl soil parameters, Dirichlet T both ends."""
-    rng = np.random.default_rng(BASE_SEED + 1 if seed is None else seed)
+    seed = BASE_SEED + 1 if seed is None else seed
+    cr = (0, ncol)
     p = make_params(coupled_soil_params(), coupled_vg())
     zmin, zmax = zlim
-    S = saturation_profiles(rng, ncol, nlayer, zmin, zmax)
-    theta_i = rng.uniform(0.0, 0.05, size=(ncol, nlayer)) if ice else np.zeros((ncol, nlayer))
+    S = saturation_profiles(seed, cr, nlayer, zmin, zmax)
+    theta_i = ice_profiles(seed, cr, nlayer, 0.05) if ice else np.zeros((ncol, nlayer))
     theta = p.theta_r + S * ((p.nu - theta_i) - p.theta_r)
-    T = temperature_profiles(rng, ncol, nlayer, zmin, zmax)
+    T = temperature_profiles(seed, cr, nlayer, zmin, zmax)
     rho_e = rho_e_int_from_T(p, theta, theta_i, T)
     return Workload(
         model=abi.LH_MODEL_HEAT, ncol=ncol, nlayer=nlayer, zmin=zmin, zmax=zmax, params=p,
