@@ -181,7 +181,8 @@ def cuda_library() -> SoilLibrary:
     """The product library.  Raises (never falls back) when it has not been built."""
     global _cuda_lib
     if _cuda_lib is None:
-        _cuda_lib = SoilLibrary(CUDA_LIBRARY_PATH, "lh_")
+        # LH_SOIL_LIBRARY: an alternative BUILD of the same CUDA library (kernel tuning experiments)
+        _cuda_lib = SoilLibrary(os.environ.get("LH_SOIL_LIBRARY", CUDA_LIBRARY_PATH), "lh_")
     return _cuda_lib
 
 

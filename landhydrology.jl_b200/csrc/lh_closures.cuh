@@ -16,7 +16,8 @@
 // the parity gate is 1e-12 (cancellation-aware norm) per tendency evaluation.
 //
 // The fp64 pipe (64 DFMA/clk/SM on B200), not HBM, is the binding unit for this path, so the
-// elementary functions in lh_math.cuh are written for minimum DFMA count.
+// elementary functions in lh_math.cuh are written for minimum DFMA count.  `tab` is the 16-entry
+// 2^(j/16) table of lh_exp, staged in shared memory by every kernel (lh_stage_exp_table).
 #pragma once
 
 #include <cuda_runtime.h>
@@ -49,10 +50,18 @@ struct LhDevParams {
     double neg_b;
     double k_unfrozen, k_frozen, ln_k_unfrozen, ln_k_frozen;
     double kappa_dry;
+    double log_Sr_sat;                 // log(nu * (1/nu)): log of the relative saturation of a saturated, ice-free cell
     int32_t visc_on, imp_on;
     int32_t om_zero;                   // nu_ss_om == 0: outer Kersten exponents are exactly 1
     int32_t pad_;
+    double mc[LHC_COUNT];              // elementary-function coefficients (lh_math.cuh)
 };
+
+// Copies the exp table from the parameter block to shared memory; the caller must __syncthreads().
+__device__ __forceinline__ void lh_stage_exp_table(const LhDevParams& p, double* tab_smem, int linear_tid)
+{
+    if (linear_tid < 16) tab_smem[linear_tid] = p.mc[LHC_EXP2_TAB0 + linear_tid];
+}
 
 struct LhCell {
     double K;      // hydraulic conductivity
@@ -61,118 +70,145 @@ struct LhCell {
     double T;      // temperature
 };
 
+// Kernel variants (template flags).  Both are properties of the uploaded problem, decided on the
+// host: θ_i never changes (dθ_i ≡ 0, right_hand_side.jl:182,359), so "no ice anywhere" is known
+// once θ_i has been uploaded.
+//   ICE : θ_i may be non-zero somewhere.  !ICE: θ_i ≡ 0, the kernels do not even read the field.
+//   GEN : general parameters (viscosity/impedance factor on, ν_ss_om != 0 or θr != 0).  !GEN is the
+//         branch-free fast path: NoEffect factors (the reference's defaults, models.jl:31-32),
+//         ν_ss_om = 0 (outer Kersten exponents exactly 1) and θr = 0 (S_r == S bit for bit, so the
+//         Kersten number reuses log S).
+#define LH_FLAG_ICE 1
+#define LH_FLAG_GEN 2
+
 // ---------------------------------------------------------------------------------------------
 // Water: K and psi of one cell.  Reference: right_hand_side.jl:156-166 / :308-313.
 //   th = ϑ_l, ti = θ_i, T = temperature (only read when the viscosity factor is on).
+// The two data-dependent conditionals of the reference (S_l_eff <= 1, S < 1) are selects on the
+// results: the unsaturated expressions are evaluated unconditionally (they are the common case and
+// yield NaN/garbage only where the select discards them).
 // ---------------------------------------------------------------------------------------------
-__device__ __forceinline__ void lh_water_closures(const LhDevParams& p, double th, double ti, double T,
-                                                  double& K_out, double& psi_out, double& logS_K,
-                                                  double& S_K_out)
+template <bool ICE, bool GEN>
+__device__ __forceinline__ void lh_water_closures(const LhDevParams& p, const double* __restrict__ tab,
+                                                  double th, double ti, double T,
+                                                  double& K_out, double& psi_out, double& logS_K)
 {
-    const double nu_eff = p.nu - ti;
-    // effective_saturation (SoilWaterParameterizations.jl:213-217); NaN-propagating max
-    const double safe = (th > p.theta_r_eps || th != th) ? th : p.theta_r_eps;
+    const double* __restrict__ mc = p.mc;
+    const double nu_eff = ICE ? p.nu - ti : p.nu;
+    // effective_saturation (SoilWaterParameterizations.jl:213-217); NaN stays NaN
+    const double safe = !(th <= p.theta_r_eps) ? th : p.theta_r_eps;
     const double num = safe - p.theta_r;
     const double S_K = num * p.inv_nu_thr;                                   // porosity = nu (:163/:311)
-    const bool no_ice = (ti == 0.0);
-    const double S_eff = no_ice ? S_K : num / (nu_eff - p.theta_r);          // porosity = nu_eff (:235)
+    const bool icy = ICE && (ti != 0.0);
+    double S_eff = S_K;                                                      // porosity = nu_eff (:235)
+    if (icy) S_eff = lh_div(num, nu_eff - p.theta_r);
 
     // ---- pressure head (:229-242) and the shared logs
-    double L_eff = lh_log(S_eff);
-    double u = L_eff * p.vg_inv_m;
-    double em1 = lh_expm1(u);            // y - 1
-    double w = -em1;                     // 1 - S^(1/m)
-    double a = lh_log(w);
-    double psi;
-    if (S_eff <= 1.0) {
-        psi = p.neg_inv_alpha * lh_exp((a - u) * p.vg_inv_n);
-    } else {
-        psi = (th - nu_eff) * p.S_s_inv;
-    }
+    const double L_eff = lh_log(mc, S_eff);
+    const double u = L_eff * p.vg_inv_m;
+    const double w = -lh_expm1(mc, tab, u);                                  // 1 - S^(1/m)
+    const double a = lh_log(mc, w);
+    const double psi_unsat = p.neg_inv_alpha * lh_exp(mc, tab, (a - u) * p.vg_inv_n);
+    const double psi_sat = (th - nu_eff) * p.S_s_inv;
+    const double psi = (S_eff <= 1.0) ? psi_unsat : psi_sat;
 
     // ---- hydraulic conductivity (:269-282)
     double L_K = L_eff, a_K = a;
-    if (!no_ice) {                       // S differs from S_eff only when ice is present
-        L_K = lh_log(S_K);
-        a_K = lh_log(-lh_expm1(L_K * p.vg_inv_m));
+    if (icy) {                           // S differs from S_eff only when ice is present
+        L_K = lh_log(mc, S_K);
+        a_K = lh_log(mc, -lh_expm1(mc, tab, L_K * p.vg_inv_m));
     }
-    double Kr;
-    if (S_K < 1.0) {
-        const double q = lh_expm1(p.vg_m * a_K);     // (1 - y)^m - 1
-        Kr = sqrt(S_K) * (q * q);
-    } else {
-        Kr = 1.0;
-    }
+    const double q = lh_expm1(mc, tab, p.vg_m * a_K);                        // (1 - y)^m - 1
+    const double Kr = (S_K < 1.0) ? lh_sqrt(S_K) * (q * q) : 1.0;
     double K = Kr * p.Ksat;
-    if (p.visc_on) K *= lh_exp(p.visc_gamma * (T - p.visc_T_ref));          // :117-126
-    if (p.imp_on) {                                                          // :89-93, f_i :159/:308
-        const double tl = (th < nu_eff) ? th : nu_eff;
-        const double f_i = ti / (tl + ti);
-        K *= lh_exp(p.imp_c * f_i);
+    if (GEN) {
+        if (p.visc_on) K *= lh_exp(mc, tab, p.visc_gamma * (T - p.visc_T_ref));   // :117-126
+        if (p.imp_on) {                                                      // :89-93, f_i :159/:308
+            const double tl = (th < nu_eff) ? th : nu_eff;
+            const double f_i = lh_div(ti, tl + ti);
+            K *= lh_exp(mc, tab, p.imp_c * f_i);
+        }
     }
     K_out = K;
     psi_out = psi;
     logS_K = L_K;
-    S_K_out = S_K;
 }
 
 // ---------------------------------------------------------------------------------------------
 // Heat: thermal conductivity from (θ_l, θ_i).  Reference: right_hand_side.jl:296-305,
-// SoilHeatParameterizations.jl:114-188.  `S_hint`/`logS_hint`: a saturation whose log is
-// already known (reused when S_r == S_hint bit for bit, which holds for θr = 0, θ_i = 0).
+// SoilHeatParameterizations.jl:114-188.
+//   REUSE: the caller has log S of the SAME cell (coupled model, fast path): with θr = 0 and no ice,
+//   S_r = θ_l/ν equals S = ϑ_l/ν bit for bit while ϑ_l < ν, and is the constant ν(1/ν) once the cell
+//   is saturated, so no second log is needed.  (For ϑ_l <= eps the two differ, but there the
+//   Kersten base E3 - c^3 is ~0 and K_e vanishes either way.)
 // ---------------------------------------------------------------------------------------------
-__device__ __forceinline__ double lh_thermal_conductivity(const LhDevParams& p, double tl, double ti,
-                                                          double S_hint, double logS_hint)
+template <bool ICE, bool GEN, bool REUSE>
+__device__ __forceinline__ double lh_thermal_conductivity(const LhDevParams& p, const double* __restrict__ tab,
+                                                          double tl, double ti, bool unsat, double logS)
 {
-    const double tw = tl + ti;
+    const double* __restrict__ mc = p.mc;
+    const double tw = ICE ? tl + ti : tl;
     const double S_r = tw * p.inv_nu;                                        // relative_saturation :139-142
-    const double Lr = (S_r == S_hint) ? logS_hint : lh_log(S_r);
+    double Lr;
+    if (REUSE && !ICE && !GEN) Lr = unsat ? logS : p.log_Sr_sat;
+    else Lr = lh_log(mc, S_r);
     double K_e;
-    if (ti < LH_EPS) {                                                       // kersten_number :163-169
-        const double e = lh_exp(p.neg_b * S_r);
+    if (!ICE || ti < LH_EPS) {                                               // kersten_number :163-169
+        const double e = lh_exp(mc, tab, p.neg_b * S_r);
         const double g = 1.0 + e;
-        const double E3 = 1.0 / (g * g * g);
+        const double E3 = lh_rcp(g * g * g);
         const double c = (1.0 - S_r) * 0.5;
         double base = E3 - c * c * c;
-        if (!p.om_zero) base = lh_exp(p.kersten_p2 * lh_log(base));
-        K_e = lh_exp(p.kersten_p1 * Lr) * base;
+        if (GEN && !p.om_zero) base = lh_exp(mc, tab, p.kersten_p2 * lh_log(mc, base));
+        K_e = lh_exp(mc, tab, p.kersten_p1 * Lr) * base;
     } else {                                                                 // :171
-        K_e = p.om_zero ? S_r : lh_exp(p.kersten_p3 * Lr);
+        K_e = (!GEN || p.om_zero) ? S_r : lh_exp(mc, tab, p.kersten_p3 * Lr);
     }
-    double k_sat;                                                            // :114-128
-    if (tw < LH_EPS) k_sat = 0.0;
-    else if (ti == 0.0) k_sat = p.k_unfrozen;                                // x^1 * y^0, exact
-    else k_sat = lh_exp((tl * p.ln_k_unfrozen + ti * p.ln_k_frozen) / tw);
+    double k_sat = p.k_unfrozen;                                             // :114-128; x^1 * y^0 is exact
+    if (ICE && ti != 0.0) k_sat = lh_exp(mc, tab, lh_div(tl * p.ln_k_unfrozen + ti * p.ln_k_frozen, tw));
+    k_sat = (tw < LH_EPS) ? 0.0 : k_sat;
     return K_e * k_sat + (1.0 - K_e) * p.kappa_dry;                          // thermal_conductivity :185-188
 }
 
 // Temperature from ρe_int (SoilHeatParameterizations.jl:42-79).
+template <bool ICE>
 __device__ __forceinline__ double lh_temperature(const LhDevParams& p, double tl, double ti, double re)
 {
-    const double rho_c_s = p.rho_c_ds + tl * p.rhocp_l + ti * p.rhocp_i;     // :65-79
-    return p.T_0 + (re + ti * p.rhoi_LH) / rho_c_s;                          // :42-53
+    if (ICE) {
+        const double rho_c_s = p.rho_c_ds + tl * p.rhocp_l + ti * p.rhocp_i; // :65-79
+        return p.T_0 + lh_div(re + ti * p.rhoi_LH, rho_c_s);                 // :42-53
+    }
+    const double rho_c_s = p.rho_c_ds + tl * p.rhocp_l;
+    return p.T_0 + lh_div(re, rho_c_s);
 }
 
 // All closures of one cell for model MODEL (0 Richards, 1 heat, 2 coupled).
 //   Richards: T_or_re = prescribed T.   heat/coupled: T_or_re = ρe_int.
-template <int MODEL>
-__device__ __forceinline__ LhCell lh_cell_closures(const LhDevParams& p, double th, double ti, double T_or_re)
+template <int MODEL, int FLAGS>
+__device__ __forceinline__ LhCell lh_cell_closures(const LhDevParams& p, const double* __restrict__ tab,
+                                                   double th, double ti, double T_or_re)
 {
+    constexpr bool ICE = (FLAGS & LH_FLAG_ICE) != 0, GEN = (FLAGS & LH_FLAG_GEN) != 0;
     LhCell c;
     c.K = 0.0; c.psi = 0.0; c.kappa = 0.0; c.T = T_or_re;
-    const double nu_eff = p.nu - ti;
-    const double tl = (th < nu_eff) ? th : nu_eff;                           // volumetric_liquid_fraction :181-188
-    if (MODEL != 0) c.T = lh_temperature(p, tl, ti, T_or_re);
-    double logS = 0.0, S_K = -1.0;
-    if (MODEL != 1) lh_water_closures(p, th, ti, c.T, c.K, c.psi, logS, S_K);
-    if (MODEL != 0) c.kappa = lh_thermal_conductivity(p, tl, ti, S_K, logS);
+    const double nu_eff = ICE ? p.nu - ti : p.nu;
+    const bool unsat = th < nu_eff;
+    const double tl = unsat ? th : nu_eff;                                   // volumetric_liquid_fraction :181-188
+    if (MODEL != 0) c.T = lh_temperature<ICE>(p, tl, ti, T_or_re);
+    double logS = 0.0;
+    if (MODEL != 1) lh_water_closures<ICE, GEN>(p, tab, th, ti, c.T, c.K, c.psi, logS);
+    if (MODEL == 1) c.kappa = lh_thermal_conductivity<ICE, GEN, false>(p, tab, tl, ti, unsat, 0.0);
+    if (MODEL == 2) c.kappa = lh_thermal_conductivity<ICE, GEN, true>(p, tab, tl, ti, unsat, logS);
     return c;
 }
 
 // κ at a boundary "face state" (boundary_conditions.jl:429-436).
-__device__ __forceinline__ double lh_face_kappa(const LhDevParams& p, double th, double ti)
+template <int FLAGS>
+__device__ __forceinline__ double lh_face_kappa(const LhDevParams& p, const double* __restrict__ tab, double th, double ti)
 {
-    const double nu_eff = p.nu - ti;
-    const double tl = (th < nu_eff) ? th : nu_eff;
-    return lh_thermal_conductivity(p, tl, ti, -1.0, 0.0);
+    constexpr bool ICE = (FLAGS & LH_FLAG_ICE) != 0, GEN = (FLAGS & LH_FLAG_GEN) != 0;
+    const double nu_eff = ICE ? p.nu - ti : p.nu;
+    const bool unsat = th < nu_eff;
+    const double tl = unsat ? th : nu_eff;
+    return lh_thermal_conductivity<ICE, GEN, false>(p, tab, tl, ti, unsat, 0.0);
 }

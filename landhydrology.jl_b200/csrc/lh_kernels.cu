@@ -79,11 +79,12 @@ __device__ __forceinline__ Flux face_flux(const LhDevParams& p, const Q<MODEL>& 
 
 // boundary_fluxes(X, bc::SoilComponentBC, face, ...) boundary_conditions.jl:470-489 for one face.
 // (th, ti) raw centre values, `c` the centre closures (c.T is the centre temperature).
-template <int MODEL>
-__device__ __forceinline__ Flux boundary_flux(const LhDevParams& p, int e_kind, int h_kind, double val_e,
-                                              double val_h, bool is_bottom, double th, double ti,
-                                              const LhCell& c)
+template <int MODEL, int FLAGS>
+__device__ __forceinline__ Flux boundary_flux(const LhDevParams& p, const double* __restrict__ tab, int e_kind,
+                                              int h_kind, double val_e, double val_h, bool is_bottom,
+                                              double th, double ti, const LhCell& c)
 {
+    constexpr bool ICE = (FLAGS & LH_FLAG_ICE) != 0, GEN = (FLAGS & LH_FLAG_GEN) != 0;
     Flux f;
     f.w = 0.0; f.e = 0.0;
     // X_cf face values (:218-228, :241-288): Dirichlet overrides, energy first then hydrology
@@ -95,8 +96,8 @@ __device__ __forceinline__ Flux boundary_flux(const LhDevParams& p, int e_kind, 
         } else if (h_kind == LH_BC_FREE_DRAINAGE) {
             f.w = -c.K;                                                      // :328-356 (K of the centre cell)
         } else if (h_kind == LH_BC_DIRICHLET) {                              // :371-401
-            double K_f, psi_f, l_, s_;
-            lh_water_closures(p, th_f, ti, T_f, K_f, psi_f, l_, s_);
+            double K_f, psi_f, l_;
+            lh_water_closures<ICE, GEN>(p, tab, th_f, ti, T_f, K_f, psi_f, l_);
             double flux = (-K_f * (psi_f - c.psi + p.half_dz)) * p.inv_half_dz;
             f.w = is_bottom ? -flux : flux;
         }
@@ -105,7 +106,7 @@ __device__ __forceinline__ Flux boundary_flux(const LhDevParams& p, int e_kind, 
         if (e_kind == LH_BC_FLUX) {
             f.e = val_e;
         } else if (e_kind == LH_BC_DIRICHLET) {                              // :416-444
-            const double kappa_f = lh_face_kappa(p, th_f, ti);
+            const double kappa_f = lh_face_kappa<FLAGS>(p, tab, th_f, ti);
             double flux = (-kappa_f * (T_f - c.T)) * p.inv_half_dz;
             f.e = is_bottom ? -flux : flux;
         }
@@ -131,13 +132,26 @@ __device__ __forceinline__ double stage_out(double base, double k, double dt)
 }
 
 struct Base { double th, re; };
+struct Raw { double th, ti, x, u0th, u0re; };
+template <int MODEL> struct Cell { Q<MODEL> q; double psi; Base base; };
 
-template <int MODEL, int STAGE>
-__global__ void __launch_bounds__(512, 1)
+// Shared-memory slot of one (column group, chunk): [bot: NQ + psi][top: NQ + psi][pending: 4], each x32 lanes.
+template <int MODEL> struct Slot { static constexpr int NQv = NQ<MODEL>::value; static constexpr int doubles = (2 * (NQv + 1) + 4) * 32; };
+
+#ifndef LH_MIN_BLOCKS
+#define LH_MIN_BLOCKS 1
+#endif
+#ifndef LH_MAX_THREADS
+#define LH_MAX_THREADS 512
+#endif
+
+template <int MODEL, int STAGE, int FLAGS>
+__global__ void __launch_bounds__(LH_MAX_THREADS, LH_MIN_BLOCKS)
 lh_soil_stage_kernel(const __grid_constant__ LhKernelArgs A)
 {
     extern __shared__ double smem[];
     constexpr int NQv = NQ<MODEL>::value;
+    constexpr bool ICE = (FLAGS & LH_FLAG_ICE) != 0;
     const LhDevParams& p = A.p;
     const int lane = threadIdx.x, w = threadIdx.y, g = threadIdx.z;
     const int W = blockDim.y;
@@ -147,133 +161,196 @@ lh_soil_stage_kernel(const __grid_constant__ LhKernelArgs A)
     const int a = w * A.Lc;
     const int b = min(n, a + A.Lc);
     const int64_t stride = A.ncol_pad;
+    const bool active = valid && a < n;
+    const bool need_T = (MODEL == 0) && (FLAGS & LH_FLAG_GEN) && p.visc_on;
 
-    // shared slots: [g][w][bot|top][NQ][32]
-    double* sm_bot = smem + ((size_t)(g * W + w) * 2 + 0) * NQv * 32 + lane;
-    double* sm_top = smem + ((size_t)(g * W + w) * 2 + 1) * NQv * 32 + lane;
+    // shared memory: [16] exp table, then one Slot per (g, w)
+    const double* tab = smem;
+    lh_stage_exp_table(p, smem, (threadIdx.z * blockDim.y + threadIdx.y) * 32 + threadIdx.x);
+    double* slot = smem + 16 + (size_t)(g * W + w) * Slot<MODEL>::doubles + lane;
+    double* sm_bot = slot;                               // Q then psi
+    double* sm_top = slot + (NQv + 1) * 32;
+    double* sm_pend = slot + 2 * (NQv + 1) * 32;         // base.th, base.re, F_first_up.w, F_first_up.e
+    __syncthreads();
 
-    Q<MODEL> prev;            // closures of the cell below the current one
-    Base base_prev;           // stage-combine base of that cell
-    Base base_first;
-    Flux F_below, F_first_up, F_bc_bot, F_bc_top;
-    F_below.w = F_below.e = 0.0;
-    F_first_up = F_below; F_bc_bot = F_below; F_bc_top = F_below;
-    base_prev.th = base_prev.re = 0.0;
-    base_first = base_prev;
+    const double* pth = A.in_th + col;
+    const double* pti = A.in_ti + col;
+    const double* pre = A.in_re + col;
+    const double* pT = A.aux_T + col;
+    const double* p0th = A.u0_th + col;
+    const double* p0re = A.u0_re + col;
+    double* oth = A.out_th + col;
+    double* ore = A.out_re + col;
 
-    if (valid && a < n) {
-        const double* pth = A.in_th + col;
-        const double* pti = A.in_ti + col;
-        const double* pre = A.in_re + col;
-        const double* pT = A.aux_T + col;
-        const double* p0th = A.u0_th + col;
-        const double* p0re = A.u0_re + col;
-        double* oth = A.out_th + col;
-        double* ore = A.out_re + col;
-        const bool need_T = (MODEL == 0) && p.visc_on;
-
-        // software prefetch of the next layer's raw values
-        double n_th = pth[(int64_t)a * stride];
-        double n_ti = pti[(int64_t)a * stride];
-        double n_x = (MODEL != 0) ? pre[(int64_t)a * stride] : (need_T ? pT[(int64_t)a * stride] : 288.0);
-        double n_u0th = 0.0, n_u0re = 0.0;
+    // Raw values of cell i.  No register software-pipeline: ptxas sinks such loads down to the next
+    // possibly-aliasing store (the stage buffers are updated in place) and spills them.  Instead the
+    // lines of cell i+2 are pulled into L1 with prefetch instructions, which cost no registers.
+    auto prefetch = [&](int i) {
+        const int64_t o = (int64_t)min(i, n - 1) * stride;
+        asm volatile("prefetch.global.L1 [%0];" ::"l"(pth + o));
+        if (ICE) asm volatile("prefetch.global.L1 [%0];" ::"l"(pti + o));
+        if (MODEL != 0) asm volatile("prefetch.global.L1 [%0];" ::"l"(pre + o));
+        else if (need_T) asm volatile("prefetch.global.L1 [%0];" ::"l"(pT + o));
         if constexpr (STAGE >= 2) {
-            if constexpr (MODEL != 1) n_u0th = p0th[(int64_t)a * stride];
-            if constexpr (MODEL != 0) n_u0re = p0re[(int64_t)a * stride];
+            if constexpr (MODEL != 1) asm volatile("prefetch.global.L1 [%0];" ::"l"(p0th + o));
+            if constexpr (MODEL != 0) asm volatile("prefetch.global.L1 [%0];" ::"l"(p0re + o));
         }
+    };
+    auto load_raw = [&](int i) {
+        Raw r;
+        const int64_t o = (int64_t)i * stride;
+        r.th = pth[o];
+        r.ti = ICE ? pti[o] : 0.0;
+        r.x = (MODEL != 0) ? pre[o] : (need_T ? pT[o] : 288.0);
+        r.u0th = 0.0; r.u0re = 0.0;
+        if constexpr (STAGE >= 2) {
+            if constexpr (MODEL != 1) r.u0th = p0th[o];
+            if constexpr (MODEL != 0) r.u0re = p0re[o];
+        }
+        return r;
+    };
+    auto eval = [&](const Raw& r, int i) {
+        const LhCell c = lh_cell_closures<MODEL, FLAGS>(p, tab, r.th, r.ti, r.x);
+        Cell<MODEL> o;
+        if constexpr (MODEL == 0) { o.q.K = c.K; o.q.h = c.psi + A.zc[i]; }
+        else if constexpr (MODEL == 1) { o.q.kappa = c.kappa; o.q.T = c.T; }
+        else {
+            o.q.K = c.K; o.q.h = c.psi + A.zc[i]; o.q.kappa = c.kappa; o.q.T = c.T;
+            o.q.eK = (p.rhocp_l * (c.T - p.T_0)) * c.K;                      // ρe_int_l * K (:306, :364)
+        }
+        o.psi = c.psi;
+        o.base.th = (MODEL != 1) ? stage_base<STAGE>(r.th, r.u0th) : 0.0;
+        o.base.re = (MODEL != 0) ? stage_base<STAGE>(r.x, r.u0re) : 0.0;
+        return o;
+    };
+    auto write_cell = [&](int i, const Base& base, const Flux& lo, const Flux& hi) {
+        const int64_t o = (int64_t)i * stride;
+        if constexpr (MODEL != 1) oth[o] = stage_out<STAGE>(base.th, -(hi.w - lo.w) * p.inv_dz, A.dt);
+        if constexpr (MODEL != 0) ore[o] = stage_out<STAGE>(base.re, -(hi.e - lo.e) * p.inv_dz, A.dt);
+    };
 
-        for (int i = a; i < b; ++i) {
-            const double th = n_th, ti = n_ti, x = n_x, u0th = n_u0th, u0re = n_u0re;
-            if (i + 1 < b) {
-                const int64_t o = (int64_t)(i + 1) * stride;
-                n_th = pth[o];
-                n_ti = pti[o];
-                if constexpr (MODEL != 0) n_x = pre[o];
-                else if (need_T) n_x = pT[o];
-                if constexpr (STAGE >= 2) {
-                    if constexpr (MODEL != 1) n_u0th = p0th[o];
-                    if constexpr (MODEL != 0) n_u0re = p0re[o];
-                }
-            }
-            // ---- pointwise closures of cell i
-            const LhCell c = lh_cell_closures<MODEL>(p, th, ti, x);
-            Q<MODEL> cur;
-            if constexpr (MODEL == 0) { cur.K = c.K; cur.h = c.psi + A.zc[i]; }
-            else if constexpr (MODEL == 1) { cur.kappa = c.kappa; cur.T = c.T; }
-            else {
-                cur.K = c.K; cur.h = c.psi + A.zc[i]; cur.kappa = c.kappa; cur.T = c.T;
-                cur.eK = (p.rhocp_l * (c.T - p.T_0)) * c.K;                 // ρe_int_l * K (:306, :364)
-            }
-            Base base_cur;
-            base_cur.th = (MODEL != 1) ? stage_base<STAGE>(th, u0th) : 0.0;
-            base_cur.re = (MODEL != 0) ? stage_base<STAGE>(x, u0re) : 0.0;
+    Q<MODEL> prev;            // closures of the last evaluated cell
+    Base base_prev;
+    Flux F_below;
+    F_below.w = F_below.e = 0.0;
+    base_prev.th = base_prev.re = 0.0;
 
-            if (i == 0)
-                F_bc_bot = boundary_flux<MODEL>(p, A.bot_e_kind, A.bot_h_kind, A.bcv[LH_BCV_BOTTOM_ENERGY],
-                                                A.bcv[LH_BCV_BOTTOM_HYDROLOGY], true, th, ti, c);
-            if (i == n - 1)
-                F_bc_top = boundary_flux<MODEL>(p, A.top_e_kind, A.top_h_kind, A.bcv[LH_BCV_TOP_ENERGY],
-                                                A.bcv[LH_BCV_TOP_HYDROLOGY], false, th, ti, c);
-
-            if (i == a) {
-                q_store<MODEL>(sm_bot, cur);
-                base_first = base_cur;
-            } else {
-                const Flux F = face_flux<MODEL>(p, prev, cur);
-                if (i - 1 == a) {
-                    F_first_up = F;        // first cell of the chunk waits for the face below it
-                } else {
-                    const int64_t o = (int64_t)(i - 1) * stride;
-                    if constexpr (MODEL != 1) oth[o] = stage_out<STAGE>(base_prev.th, -(F.w - F_below.w) * p.inv_dz, A.dt);
-                    if constexpr (MODEL != 0) ore[o] = stage_out<STAGE>(base_prev.re, -(F.e - F_below.e) * p.inv_dz, A.dt);
-                }
-                F_below = F;
-            }
-            prev = cur;
-            base_prev = base_cur;
+    if (active) {
+        prefetch(a + 1);
+        int i = a;
+        {   // first cell of the chunk: no face below it yet -> park what its update needs in shared memory
+            prefetch(i + 2);
+            const Cell<MODEL> c = eval(load_raw(i), i);
+            q_store<MODEL>(sm_bot, c.q);
+            sm_bot[NQv * 32] = c.psi;
+            sm_pend[0] = c.base.th; sm_pend[32] = c.base.re;
+            sm_top[NQv * 32] = c.psi;          // also the last cell so far
+            prev = c.q; base_prev = c.base;
+            ++i;
+        }
+        if (i < b) {   // second cell: the face above the first cell
+            prefetch(i + 2);
+            const Cell<MODEL> c = eval(load_raw(i), i);
+            const Flux F = face_flux<MODEL>(p, prev, c.q);
+            sm_pend[64] = F.w; sm_pend[96] = F.e;
+            if (i + 1 == b) sm_top[NQv * 32] = c.psi;
+            F_below = F; prev = c.q; base_prev = c.base;
+            ++i;
+        }
+        for (; i + 1 < b; i += 2) {   // two cells per trip: no sliding-window register moves
+            prefetch(i + 2);
+            prefetch(i + 3);
+            const Cell<MODEL> c0 = eval(load_raw(i), i);
+            const Flux F0 = face_flux<MODEL>(p, prev, c0.q);
+            write_cell(i - 1, base_prev, F_below, F0);
+            const Cell<MODEL> c1 = eval(load_raw(i + 1), i + 1);
+            const Flux F1 = face_flux<MODEL>(p, c0.q, c1.q);
+            write_cell(i, c0.base, F0, F1);
+            if (i + 2 == b) sm_top[NQv * 32] = c1.psi;
+            F_below = F1; prev = c1.q; base_prev = c1.base;
+        }
+        if (i < b) {   // odd tail
+            const Cell<MODEL> c = eval(load_raw(i), i);
+            const Flux F = face_flux<MODEL>(p, prev, c.q);
+            write_cell(i - 1, base_prev, F_below, F);
+            sm_top[NQv * 32] = c.psi;
+            F_below = F; prev = c.q; base_prev = c.base;
         }
         q_store<MODEL>(sm_top, prev);
     }
     __syncthreads();
-    if (valid && a < n) {
-        double* oth = A.out_th + col;
-        double* ore = A.out_re + col;
+    if (active) {
         const Q<MODEL> first = q_load<MODEL>(sm_bot);
         Flux F_lo, F_hi;
-        if (a == 0) F_lo = F_bc_bot;
-        else F_lo = face_flux<MODEL>(p, q_load<MODEL>(sm_bot - 1 * NQv * 32), first);   // top slot of chunk w-1
-        if (b == n) F_hi = F_bc_top;
-        else F_hi = face_flux<MODEL>(p, prev, q_load<MODEL>(sm_top + 1 * NQv * 32));    // bot slot of chunk w+1
-        const int64_t oa = (int64_t)a * stride, ob = (int64_t)(b - 1) * stride;
-        if (b - a == 1) {
-            if constexpr (MODEL != 1) oth[oa] = stage_out<STAGE>(base_first.th, -(F_hi.w - F_lo.w) * p.inv_dz, A.dt);
-            if constexpr (MODEL != 0) ore[oa] = stage_out<STAGE>(base_first.re, -(F_hi.e - F_lo.e) * p.inv_dz, A.dt);
+        if (a == 0) {
+            // bottom boundary flux from the first cell (its raw values are still unwritten in global memory)
+            LhCell c;
+            c.K = 0.0; c.psi = sm_bot[NQv * 32]; c.kappa = 0.0; c.T = 288.0;
+            if constexpr (MODEL != 1) c.K = first.K;
+            if constexpr (MODEL != 0) c.T = first.T;
+            else if (need_T) c.T = pT[0];
+            F_lo = boundary_flux<MODEL, FLAGS>(p, tab, A.bot_e_kind, A.bot_h_kind, A.bcv[LH_BCV_BOTTOM_ENERGY],
+                                               A.bcv[LH_BCV_BOTTOM_HYDROLOGY], true, pth[0], ICE ? pti[0] : 0.0, c);
         } else {
-            if constexpr (MODEL != 1) {
-                oth[oa] = stage_out<STAGE>(base_first.th, -(F_first_up.w - F_lo.w) * p.inv_dz, A.dt);
-                oth[ob] = stage_out<STAGE>(base_prev.th, -(F_hi.w - F_below.w) * p.inv_dz, A.dt);
-            }
-            if constexpr (MODEL != 0) {
-                ore[oa] = stage_out<STAGE>(base_first.re, -(F_first_up.e - F_lo.e) * p.inv_dz, A.dt);
-                ore[ob] = stage_out<STAGE>(base_prev.re, -(F_hi.e - F_below.e) * p.inv_dz, A.dt);
-            }
+            F_lo = face_flux<MODEL>(p, q_load<MODEL>(sm_top - Slot<MODEL>::doubles), first);   // top of chunk w-1
+        }
+        if (b == n) {
+            const int64_t o = (int64_t)(n - 1) * stride;
+            LhCell c;
+            c.K = 0.0; c.psi = sm_top[NQv * 32]; c.kappa = 0.0; c.T = 288.0;
+            if constexpr (MODEL != 1) c.K = prev.K;
+            if constexpr (MODEL != 0) c.T = prev.T;
+            else if (need_T) c.T = pT[o];
+            F_hi = boundary_flux<MODEL, FLAGS>(p, tab, A.top_e_kind, A.top_h_kind, A.bcv[LH_BCV_TOP_ENERGY],
+                                               A.bcv[LH_BCV_TOP_HYDROLOGY], false, pth[o], ICE ? pti[o] : 0.0, c);
+        } else {
+            F_hi = face_flux<MODEL>(p, prev, q_load<MODEL>(sm_bot + Slot<MODEL>::doubles));    // bot of chunk w+1
+        }
+        Base base_first;
+        base_first.th = sm_pend[0]; base_first.re = sm_pend[32];
+        if (b - a == 1) {
+            write_cell(a, base_first, F_lo, F_hi);
+        } else {
+            Flux F_first_up;
+            F_first_up.w = sm_pend[64]; F_first_up.e = sm_pend[96];
+            write_cell(a, base_first, F_lo, F_first_up);
+            write_cell(b - 1, base_prev, F_below, F_hi);
         }
     }
 }
 
-template <int MODEL>
-cudaError_t launch_model(int stage, const LhKernelArgs& args, const LhLaunchShape& s, cudaStream_t stream)
+template <int MODEL, int FLAGS>
+cudaError_t launch_variant(int stage, const LhKernelArgs& args, const LhLaunchShape& s, cudaStream_t stream)
 {
     dim3 block(32, s.W, s.G);
     dim3 grid((unsigned)s.nblocks);
+    if (s.smem_bytes > 48 * 1024) {
+        cudaError_t e;
+        const int bytes = (int)s.smem_bytes;
+        if ((e = cudaFuncSetAttribute(lh_soil_stage_kernel<MODEL, 0, FLAGS>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes))) return e;
+        if ((e = cudaFuncSetAttribute(lh_soil_stage_kernel<MODEL, 1, FLAGS>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes))) return e;
+        if ((e = cudaFuncSetAttribute(lh_soil_stage_kernel<MODEL, 2, FLAGS>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes))) return e;
+        if ((e = cudaFuncSetAttribute(lh_soil_stage_kernel<MODEL, 3, FLAGS>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes))) return e;
+    }
     switch (stage) {
-    case 0: lh_soil_stage_kernel<MODEL, 0><<<grid, block, s.smem_bytes, stream>>>(args); break;
-    case 1: lh_soil_stage_kernel<MODEL, 1><<<grid, block, s.smem_bytes, stream>>>(args); break;
-    case 2: lh_soil_stage_kernel<MODEL, 2><<<grid, block, s.smem_bytes, stream>>>(args); break;
-    case 3: lh_soil_stage_kernel<MODEL, 3><<<grid, block, s.smem_bytes, stream>>>(args); break;
+    case 0: lh_soil_stage_kernel<MODEL, 0, FLAGS><<<grid, block, s.smem_bytes, stream>>>(args); break;
+    case 1: lh_soil_stage_kernel<MODEL, 1, FLAGS><<<grid, block, s.smem_bytes, stream>>>(args); break;
+    case 2: lh_soil_stage_kernel<MODEL, 2, FLAGS><<<grid, block, s.smem_bytes, stream>>>(args); break;
+    case 3: lh_soil_stage_kernel<MODEL, 3, FLAGS><<<grid, block, s.smem_bytes, stream>>>(args); break;
     default: return cudaErrorInvalidValue;
     }
     return cudaGetLastError();
+}
+
+template <int MODEL>
+cudaError_t launch_model(int stage, int flags, const LhKernelArgs& args, const LhLaunchShape& s, cudaStream_t stream)
+{
+    switch (flags & 3) {
+    case 0: return launch_variant<MODEL, 0>(stage, args, s, stream);
+    case 1: return launch_variant<MODEL, 1>(stage, args, s, stream);
+    case 2: return launch_variant<MODEL, 2>(stage, args, s, stream);
+    default: return launch_variant<MODEL, 3>(stage, args, s, stream);
+    }
 }
 
 }  // namespace
@@ -287,28 +364,30 @@ LhLaunchShape lh_choose_shape(int model, int64_t ncol_pad, int32_t nlayer, int s
     int Lc = 16;
     const int64_t want_warps = (int64_t)sm_count * 8;
     while (Lc > 2 && groups * ((nlayer + Lc - 1) / Lc) < want_warps) Lc >>= 1;
+    const int max_warps = LH_MAX_THREADS / 32;             // register budget: 64K / (warps * 32 * regs)
     int W = (nlayer + Lc - 1) / Lc;
-    if (W > 16) { W = 16; }           // <= 512 threads per block (128 registers per thread)
+    if (W > max_warps) W = max_warps;
     Lc = (nlayer + W - 1) / W;
     W = (nlayer + Lc - 1) / Lc;          // no empty chunks
     int G = 1;
-    while (W * G * 2 <= 8 && (int64_t)G * 2 <= groups) G *= 2;   // at least ~8 warps per block when possible
+    const int want = max_warps < 8 ? max_warps : 8;        // ~8 warps per block when possible
+    while (W * G * 2 <= want && (int64_t)G * 2 <= groups) G *= 2;
     s.Lc = Lc; s.W = W; s.G = G;
     s.nblocks = (groups + G - 1) / G;
     const int nq = model == LH_MODEL_COUPLED ? 5 : 2;
-    s.smem_bytes = (size_t)G * W * 2 * nq * 32 * sizeof(double);
+    s.smem_bytes = (16 + (size_t)G * W * (2 * (nq + 1) + 4) * 32) * sizeof(double);
     return s;
 }
 
-cudaError_t lh_launch_stage(int model, int stage, const LhKernelArgs& args, const LhLaunchShape& shape,
+cudaError_t lh_launch_stage(int model, int stage, int flags, const LhKernelArgs& args, const LhLaunchShape& shape,
                             cudaStream_t stream)
 {
     if (model < 0 || model > 2) return cudaErrorInvalidValue;
-    if (shape.W * shape.G * 32 > 512 || shape.smem_bytes > 48 * 1024) return cudaErrorInvalidConfiguration;
+    if (shape.W * shape.G * 32 > LH_MAX_THREADS || shape.smem_bytes > 200 * 1024) return cudaErrorInvalidConfiguration;
     switch (model) {
-    case 0: return launch_model<0>(stage, args, shape, stream);
-    case 1: return launch_model<1>(stage, args, shape, stream);
-    default: return launch_model<2>(stage, args, shape, stream);
+    case 0: return launch_model<0>(stage, flags, args, shape, stream);
+    case 1: return launch_model<1>(stage, flags, args, shape, stream);
+    default: return launch_model<2>(stage, flags, args, shape, stream);
     }
 }
 
@@ -321,20 +400,23 @@ __global__ void lh_diag_kernel(const __grid_constant__ LhDevParams p, int which,
                                const double* __restrict__ ti, const double* __restrict__ re,
                                const double* __restrict__ T, double* __restrict__ out, int64_t n)
 {
+    __shared__ double tab[16];
+    lh_stage_exp_table(p, tab, threadIdx.x);
+    __syncthreads();
     const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
     // K/ψ exist for every model; κ/T come from ρe_int when there is an energy model, otherwise
     // from the prescribed T.
     double v;
     if (MODEL == 0) {
-        const LhCell c = lh_cell_closures<0>(p, th[i], ti[i], T[i]);
+        const LhCell c = lh_cell_closures<0, 3>(p, tab, th[i], ti[i], T[i]);
         if (which == LH_DIAG_KAPPA) {
             const double nu_eff = p.nu - ti[i];
             const double tl = th[i] < nu_eff ? th[i] : nu_eff;
-            v = lh_thermal_conductivity(p, tl, ti[i], -1.0, 0.0);
+            v = lh_thermal_conductivity<true, true, false>(p, tab, tl, ti[i], th[i] < nu_eff, 0.0);
         } else v = which == LH_DIAG_K ? c.K : which == LH_DIAG_PSI ? c.psi : c.T;
     } else {
-        const LhCell c = lh_cell_closures<2>(p, th[i], ti[i], re[i]);
+        const LhCell c = lh_cell_closures<2, 3>(p, tab, th[i], ti[i], re[i]);
         v = which == LH_DIAG_K ? c.K : which == LH_DIAG_PSI ? c.psi : which == LH_DIAG_KAPPA ? c.kappa : c.T;
     }
     out[i] = v;
@@ -479,6 +561,14 @@ __global__ void lh_fill_padding_kernel(double* __restrict__ soa, int64_t ncol, i
     soa[l * ncol_pad + c] = soa[l * ncol_pad + ncol - 1];
 }
 
+__global__ void lh_any_nonzero_kernel(const double* __restrict__ x, int64_t n, int* flag)
+{
+    bool any = false;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x)
+        any |= !(x[i] == 0.0);
+    if (__syncthreads_or(any) && threadIdx.x == 0) *flag = 1;
+}
+
 __global__ void lh_count_nonfinite_kernel(const double* __restrict__ x, int64_t n, unsigned long long* count)
 {
     unsigned long long local = 0;
@@ -518,6 +608,12 @@ cudaError_t lh_launch_fill_padding(double* soa, int64_t ncol, int64_t ncol_pad, 
     const int64_t n = (ncol_pad - ncol) * nlayer;
     if (n <= 0) return cudaSuccess;
     lh_fill_padding_kernel<<<(unsigned)((n + 255) / 256), 256, 0, stream>>>(soa, ncol, ncol_pad, nlayer);
+    return cudaGetLastError();
+}
+
+cudaError_t lh_launch_any_nonzero(const double* x, int64_t n, int* flag, cudaStream_t stream)
+{
+    lh_any_nonzero_kernel<<<592, 256, 0, stream>>>(x, n, flag);
     return cudaGetLastError();
 }
 

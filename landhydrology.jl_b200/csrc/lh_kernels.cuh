@@ -37,9 +37,12 @@ struct LhLaunchShape {
 
 LhLaunchShape lh_choose_shape(int model, int64_t ncol_pad, int32_t nlayer, int sm_count);
 
-// stage 0 = tendency only; 1..3 = fused RHS + SSPRK33 stage.
-cudaError_t lh_launch_stage(int model, int stage, const LhKernelArgs& args, const LhLaunchShape& shape,
-                            cudaStream_t stream);
+// stage 0 = tendency only; 1..3 = fused RHS + SSPRK33 stage.  flags: LH_FLAG_ICE | LH_FLAG_GEN
+// (lh_closures.cuh) select the compiled kernel variant.
+cudaError_t lh_launch_stage(int model, int stage, int flags, const LhKernelArgs& args,
+                            const LhLaunchShape& shape, cudaStream_t stream);
+// *flag (int32, device) := 1 if any element of x[0..n) is non-zero (NaN counts), else unchanged.
+cudaError_t lh_launch_any_nonzero(const double* x, int64_t n, int* flag, cudaStream_t stream);
 
 // Pointwise diagnostics (LH_DIAG_*): out[layer*ncol_pad+col].
 cudaError_t lh_launch_diagnostic(int model, int which, const LhDevParams& p, const double* th,

@@ -1,11 +1,182 @@
-// lh_math.cuh — fp64 elementary functions used by the soil closures.
+// lh_math.cuh — branch-free fp64 elementary functions for the soil closures (sm_100a).
 //
-// Accuracy contract: <= ~2 ulp on the ranges the closures use; the parity gate downstream is
-// 1e-12 in a cancellation-aware norm (tests/test_gpu_parity.py).
+// Why not libdevice's log/exp/expm1/pow: the ncu profile of the first kernel (profiles/r01_a_*)
+// showed only 32 % of issued instructions on the fp64 pipe — 157 UMOV + 117 IMAD per cell were
+// nvcc materialising 64-bit polynomial constants as pairs of 32-bit immediates, and ~77 were the
+// branches of libdevice's special-case slow paths.  Here
+//   * every coefficient is read from a table the caller passes in; the kernels keep that table in
+//     their __grid_constant__ parameter block (constant bank 0), which sm_100a loads with LDCU into
+//     UNIFORM registers and hoists out of the layer loop (a __constant__ array in bank 3 was tried:
+//     ptxas emits one LDC.64 into a vector register per use, which costs an issue slot and spills);
+//   * special cases are handled by selects on the result, never by branches;
+//   * reciprocal / rsqrt seeds come from the MUFU pipe (rcp.approx.ftz.f64 / rsqrt.approx.ftz.f64)
+//     and are refined by Newton steps on the fp64 pipe.
+// Accuracy (tests/test_device_math.py, host emulation of the same code against mpmath): <= 2 ulp on
+// the closures' ranges.  Coefficients: tools/gen_math_coeffs.py.
+//
+// The same source compiles on the host (LH_MATH_HOST) so the algorithms can be verified here
+// without a GPU; that build is test infrastructure only.
 #pragma once
 
-#include <cuda_runtime.h>
+#include <stdint.h>
+#include <string.h>
 
-__device__ __forceinline__ double lh_log(double x) { return log(x); }
-__device__ __forceinline__ double lh_exp(double x) { return exp(x); }
-__device__ __forceinline__ double lh_expm1(double x) { return expm1(x); }
+#include "lh_math_coeffs.inc"
+
+#ifdef LH_MATH_HOST
+#include <math.h>
+#define LH_DEV static inline
+static const double lh_c_host[LHC_COUNT] = {LH_MATH_COEFFS};
+LH_DEV double lh_fma(double a, double b, double c) { return fma(a, b, c); }
+LH_DEV int32_t lh_hi(double x) { int64_t b; memcpy(&b, &x, 8); return (int32_t)(b >> 32); }
+LH_DEV int32_t lh_lo(double x) { int64_t b; memcpy(&b, &x, 8); return (int32_t)(b & 0xffffffff); }
+LH_DEV double lh_mk(int32_t hi, int32_t lo) { int64_t b = ((int64_t)hi << 32) | (uint32_t)lo; double x; memcpy(&x, &b, 8); return x; }
+// MUFU.RCP64H / RSQ64H emulation: ~20 good bits, low word zero
+LH_DEV double lh_rcp_seed(double x) { double r = 1.0 / x; return lh_mk(lh_hi(r) & ~0x7, 0); }
+LH_DEV double lh_rsqrt_seed(double x) { double r = 1.0 / sqrt(x); return lh_mk(lh_hi(r) & ~0x7, 0); }
+#define LH_INF (INFINITY)
+#define LH_NAN (NAN)
+#else
+#include <cuda_runtime.h>
+#define LH_DEV __device__ __forceinline__
+LH_DEV double lh_fma(double a, double b, double c) { return fma(a, b, c); }
+LH_DEV int32_t lh_hi(double x) { return __double2hiint(x); }
+LH_DEV int32_t lh_lo(double x) { return __double2loint(x); }
+LH_DEV double lh_mk(int32_t hi, int32_t lo) { return __hiloint2double(hi, lo); }
+LH_DEV double lh_rcp_seed(double x) { double r; asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(x)); return r; }
+LH_DEV double lh_rsqrt_seed(double x) { double r; asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(x)); return r; }
+#define LH_INF (__longlong_as_double(0x7ff0000000000000LL))
+#define LH_NAN (__longlong_as_double(0x7ff8000000000000LL))
+#endif
+
+// 1/x for normal, finite, non-zero x: seed (2^-20) + 2 Newton steps -> ~1 ulp.  6 fp64-pipe ops.
+LH_DEV double lh_rcp(double x)
+{
+    double r = lh_rcp_seed(x);
+    double e = lh_fma(-x, r, 1.0);
+    r = lh_fma(r, e, r);
+    e = lh_fma(-x, r, 1.0);
+    r = lh_fma(r, e, r);
+    return r;
+}
+
+// a/b for normal finite b != 0, |a/b| in range: reciprocal + one residual correction (<= 1 ulp).
+LH_DEV double lh_div(double a, double b)
+{
+    const double r = lh_rcp(b);
+    double q = a * r;
+    const double rem = lh_fma(-q, b, a);
+    return lh_fma(rem, r, q);
+}
+
+// sqrt(x), x >= 0 finite (x == 0 -> 0).  rsqrt seed, coupled Newton on (g ~ sqrt x, h ~ 1/(2 sqrt x)).
+LH_DEV double lh_sqrt(double x)
+{
+    const double r = lh_rsqrt_seed(x);
+    double g = x * r;
+    double h = 0.5 * r;
+    double e = lh_fma(-h, g, 0.5);
+    g = lh_fma(g, e, g);
+    h = lh_fma(h, e, h);
+    e = lh_fma(-h, g, 0.5);
+    g = lh_fma(g, e, g);
+    h = lh_fma(h, e, h);
+    const double d = lh_fma(-g, g, x);
+    g = lh_fma(d, h, g);
+    return x > 0.0 ? g : x;            // 0 -> 0 (seed is inf), negative/NaN -> x*... NaN below
+}
+
+// ---------------------------------------------------------------------------------------------------
+// exp core: x = k (ln2/16) + r, |r| <= ln2/32;  e^x = 2^(k>>4) * T[k&15] * (1 + p),  p = r + r^2 q(r),
+// T[j] = 2^(j/16).  `tab` points at the 16-entry table: the kernels stage it in SHARED memory, where a
+// 16 x 8-byte table spans the 32 banks exactly once, so any pattern of per-lane indices is
+// conflict-free (one LDS.64).  Returns the scale s = 2^(k>>4) T[j] and p.
+// ---------------------------------------------------------------------------------------------------
+struct LhExpParts { double s, p; };
+
+LH_DEV LhExpParts lh_exp_parts(const double* __restrict__ lh_c, const double* __restrict__ tab, double x)
+{
+    // Lower clamp in the INTEGER domain (an fp64 compare+select costs a DSETP on the fp64 pipe
+    // plus two FSELs): for negative x the unsigned high word grows with |x|, so
+    // hi > 0xC0862000 <=> x < -708 (or x is a negative-signed NaN, which then reads as -708).
+    // Positive NaN propagates through the arithmetic; x > 709 is outside the contract (the
+    // closures never produce it from a finite state).
+    int32_t xhi = lh_hi(x);
+    xhi = ((uint32_t)xhi > 0xC0862000u) ? (int32_t)0xC0862000 : xhi;
+    const double xc = lh_mk(xhi, lh_lo(x));
+    const double MAGIC = 6755399441055744.0;                 // 1.5 * 2^52: low word of t is k
+    const double t = lh_fma(xc, lh_c[LHC_L2E16], MAGIC);
+    const int32_t k = lh_lo(t);
+    const double kf = t - MAGIC;
+    double r = lh_fma(kf, -lh_c[LHC_LN2_16_HI], xc);
+    r = lh_fma(kf, -lh_c[LHC_LN2_16_LO], r);
+    const double T = tab[k & 15];
+    double q = lh_c[LHC_EXP_Q5];
+    q = lh_fma(q, r, lh_c[LHC_EXP_Q4]);
+    q = lh_fma(q, r, lh_c[LHC_EXP_Q3]);
+    q = lh_fma(q, r, lh_c[LHC_EXP_Q2]);
+    q = lh_fma(q, r, lh_c[LHC_EXP_Q1]);
+    q = lh_fma(q, r, lh_c[LHC_EXP_Q0]);
+    LhExpParts o;
+    o.p = lh_fma(r * r, q, r);
+    o.s = lh_mk(lh_hi(T) + ((k >> 4) << 20), lh_lo(T));     // T * 2^(k>>4): exponent-field add
+    return o;
+}
+
+// e^x for x <= 709.  x < -708 (incl. -inf) returns e^-708 ~ 3e-308 (not exactly 0: nothing downstream
+// distinguishes them), NaN -> NaN.
+LH_DEV double lh_exp(const double* __restrict__ lh_c, const double* __restrict__ tab, double x)
+{
+    const LhExpParts e = lh_exp_parts(lh_c, tab, x);
+    return lh_fma(e.s, e.p, e.s);
+}
+
+// e^x - 1.  |x| <= ln2/32: k == 0, s == 1 and the result is p itself (full accuracy where 1 - e^x
+// cancels).  Otherwise s - 1 carries the rounding of T[j]: relative error <= 2^-53 / |e^x - 1| < 6e-15.
+LH_DEV double lh_expm1(const double* __restrict__ lh_c, const double* __restrict__ tab, double x)
+{
+    const LhExpParts e = lh_exp_parts(lh_c, tab, x);
+    return lh_fma(e.s, e.p, e.s - 1.0);
+}
+
+// ---------------------------------------------------------------------------------------------------
+// log(x): x = 2^e m, m in [sqrt(1/2), sqrt(2));  s = (m-1)/(m+1);  log m = 2 s + s z P(z), z = s^2.
+// x < 0, NaN (and +inf) -> NaN.  x == 0 and subnormals read as 2^-1023 m: log(0) = -709.09 instead of
+// -inf, which is what the closures need (exp of it underflows; nothing tests for -inf).
+// ---------------------------------------------------------------------------------------------------
+LH_DEV double lh_log(const double* __restrict__ lh_c, double x)
+{
+    int32_t hi = lh_hi(x) & 0x7fffffff;      // log|x|; the sign only matters for the NaN flag below
+    const int32_t lo = lh_lo(x);
+    // exponent such that the mantissa lands in [sqrt(1/2), sqrt(2))
+    const int32_t e = (hi - 0x3fe6a09e) >> 20;
+    hi -= e << 20;
+    const double m = lh_mk(hi, lo);
+    const double f = m - 1.0;
+    const double d = m + 1.0;
+    // s = f / (2 + f): reciprocal of the (rounded) d, then one correction whose residual
+    // f - 2 s - s f is formed from f itself (f - 2 s is exact by Sterbenz), so the rounding of
+    // d = m + 1 does not leak into s.
+    const double r = lh_rcp(d);
+    double s = f * r;
+    s = lh_fma(lh_fma(-s, f, lh_fma(-2.0, s, f)), r, s);
+    const double z = s * s;
+    double P = lh_c[LHC_LOG_P6];
+    P = lh_fma(P, z, lh_c[LHC_LOG_P5]);
+    P = lh_fma(P, z, lh_c[LHC_LOG_P4]);
+    P = lh_fma(P, z, lh_c[LHC_LOG_P3]);
+    P = lh_fma(P, z, lh_c[LHC_LOG_P2]);
+    P = lh_fma(P, z, lh_c[LHC_LOG_P1]);
+    P = lh_fma(P, z, lh_c[LHC_LOG_P0]);
+    const double ef = (double)e;
+    // e ln2_hi is exact (ln2_hi has 38 bits, |e| < 2^11); sum small terms first
+    const double tail = lh_fma(s * z, P, ef * lh_c[LHC_LN2_LO]);
+    const double y = lh_fma(ef, lh_c[LHC_LN2_HI], 2.0 * s) + tail;
+    // x < 0, NaN, +inf: force NaN with integer compares on the high word (cheaper than an fp64
+    // compare, which occupies the fp64 pipe).  -0.0 (high word exactly 0x80000000: the closures
+    // produce it as -(expm1(0))) is NOT flagged: like +0 it yields a huge negative finite value.
+    const uint32_t xh = (uint32_t)lh_hi(x);
+    const bool bad = (xh > 0x80000000u) || (xh - 0x7ff00000u < 0x00100000u);
+    const int32_t yhi = bad ? 0x7ff80000 : lh_hi(y);
+    return lh_mk(yhi, lh_lo(y));
+}

@@ -91,6 +91,8 @@ struct lh_soil_ctx {
     double bcv[4] = {0, 0, 0, 0};
     ncclComm_t_ comm = nullptr;
     int nranks = 1, rank = 0;
+    bool has_ice = false;        // some θ_i != 0 (θ_i is constant in time: dθ_i ≡ 0), re-evaluated on every θ_i upload
+    int kernel_flags = 0;        // LH_FLAG_ICE | LH_FLAG_GEN -> compiled kernel variant
     bool timing_valid = false;
     int64_t last_launches = 0;
     char err[512] = "";
@@ -184,6 +186,9 @@ LhDevParams derive_params(const lh_soil_config& cfg)
     d.visc_on = q.viscosity_factor != LH_FACTOR_NONE;
     d.imp_on = q.impedance_factor != LH_FACTOR_NONE;
     d.om_zero = q.nu_ss_om == 0.0;
+    d.log_Sr_sat = log(q.nu * d.inv_nu);
+    static const double coeffs[LHC_COUNT] = {LH_MATH_COEFFS};
+    memcpy(d.mc, coeffs, sizeof coeffs);
     return d;
 }
 
@@ -333,6 +338,27 @@ int32_t download_field(lh_soil_ctx* c, const double* soa, double* host, int64_t 
     return LH_OK;
 }
 
+void update_kernel_flags(lh_soil_ctx* c)
+{
+    const lh_soil_params& q = c->cfg.params;
+    const bool gen = c->dp.visc_on || c->dp.imp_on || !c->dp.om_zero || q.theta_r != 0.0;
+    c->kernel_flags = (c->has_ice ? LH_FLAG_ICE : 0) | (gen ? LH_FLAG_GEN : 0);
+}
+
+// θ_i was (re)written: is there any ice?  One pass over the field; θ_i never changes afterwards.
+int32_t detect_ice(lh_soil_ctx* c)
+{
+    int* flag = (int*)c->nonfinite_dev;
+    LH_CUDA(c, cudaMemsetAsync(flag, 0, sizeof(int), c->stream));
+    LH_CUDA(c, lh_launch_any_nonzero(c->U[1], (int64_t)c->ncol_pad * c->nlayer, flag, c->stream));
+    int h = 0;
+    LH_CUDA(c, cudaMemcpyAsync(&h, flag, sizeof h, cudaMemcpyDeviceToHost, c->stream));
+    LH_CUDA(c, cudaStreamSynchronize(c->stream));
+    c->has_ice = h != 0;
+    update_kernel_flags(c);
+    return LH_OK;
+}
+
 void fill_args(lh_soil_ctx* c, int stage, double dt, LhKernelArgs& a)
 {
     a.p = c->dp;
@@ -437,6 +463,7 @@ int32_t lh_soil_create(const lh_soil_config* cfg, lh_soil_ctx** out)
         LH_CREATE_CUDA(cudaEventCreateWithFlags(&c->ev_xpose[k], cudaEventDisableTiming));
     }
     c->shape = lh_choose_shape(c->model, c->ncol_pad, c->nlayer, c->sm_count);
+    update_kernel_flags(c);
 
     const size_t fb = field_bytes(c);
     // ϑ_l, θ_i always exist (prognostic or prescribed); ρe_int with an energy model; T aux only
@@ -499,7 +526,9 @@ int32_t lh_soil_set_state(lh_soil_ctx* c, int32_t field, const double* host, int
     if (!c) return LH_ERR_INVALID_ARG;
     if (!field_ok(field)) return fail(c, LH_ERR_INVALID_ARG, "bad field id %d", field);
     if (!c->U[field]) return fail(c, LH_ERR_INVALID_ARG, "field %d does not exist for model kind %d", field, c->model);
-    return upload_field(c, c->U[field], host, cs, ls);
+    int32_t st = upload_field(c, c->U[field], host, cs, ls);
+    if (st == LH_OK && field == LH_FIELD_THETA_I) st = detect_ice(c);
+    return st;
 }
 
 int32_t lh_soil_set_aux(lh_soil_ctx* c, int32_t field, const double* host, int64_t cs, int64_t ls)
@@ -526,7 +555,7 @@ static int32_t launch_stage(lh_soil_ctx* c, int stage, double dt)
 {
     LhKernelArgs a;
     fill_args(c, stage, dt, a);
-    LH_CUDA(c, lh_launch_stage(c->model, stage, a, c->shape, c->stream));
+    LH_CUDA(c, lh_launch_stage(c->model, stage, c->kernel_flags, a, c->shape, c->stream));
     return LH_OK;
 }
 
@@ -653,6 +682,10 @@ int32_t lh_soil_device_ptr(lh_soil_ctx* c, int32_t field, void** dptr, int64_t* 
     if (!field_ok(field) || !c->U[field]) return fail(c, LH_ERR_INVALID_ARG, "field %d does not exist", field);
     *dptr = c->U[field];
     if (ncol_padded) *ncol_padded = c->ncol_pad;
+    if (field == LH_FIELD_THETA_I) {   // the caller may write ice through the raw pointer: assume it does
+        c->has_ice = true;
+        update_kernel_flags(c);
+    }
     return LH_OK;
 }
 

@@ -1,0 +1,14 @@
+// Host build of csrc/lh_math.cuh (LH_MATH_HOST): the SAME source the kernels compile, with the
+// MUFU seeds emulated at 20-bit precision, so the algorithms' accuracy can be checked on a box
+// without a GPU (tests/test_device_math.py).  Test infrastructure only.
+#define LH_MATH_HOST 1
+#include "lh_math.cuh"
+
+extern "C" {
+void lhm_log(const double* x, double* y, long n) { for (long i = 0; i < n; ++i) y[i] = lh_log(lh_c_host, x[i]); }
+void lhm_exp(const double* x, double* y, long n) { for (long i = 0; i < n; ++i) y[i] = lh_exp(lh_c_host, lh_c_host + LHC_EXP2_TAB0, x[i]); }
+void lhm_expm1(const double* x, double* y, long n) { for (long i = 0; i < n; ++i) y[i] = lh_expm1(lh_c_host, lh_c_host + LHC_EXP2_TAB0, x[i]); }
+void lhm_sqrt(const double* x, double* y, long n) { for (long i = 0; i < n; ++i) y[i] = lh_sqrt(x[i]); }
+void lhm_rcp(const double* x, double* y, long n) { for (long i = 0; i < n; ++i) y[i] = lh_rcp(x[i]); }
+void lhm_div(const double* a, const double* b, double* y, long n) { for (long i = 0; i < n; ++i) y[i] = lh_div(a[i], b[i]); }
+}

@@ -1,0 +1,96 @@
+"""Accuracy of the device elementary functions (csrc/lh_math.cuh), checked on the CPU.
+
+The header compiles in a host-emulation mode (same algorithm, same coefficients, MUFU seeds
+emulated at 20 bits), so the ulp error of lh_log / lh_exp / lh_expm1 / lh_sqrt / lh_div is measured
+here against mpmath at 40 digits.  The GPU build of the same source is covered by
+tests/test_gpu_parity.py::test_diagnostics_match_oracle."""
+import ctypes as C
+import os
+import subprocess
+
+import mpmath as mp
+import numpy as np
+import pytest
+
+import workloads as w
+
+ROOT = w.ROOT
+CSRC = os.path.join(ROOT, "landhydrology.jl_b200", "csrc")
+SRC = os.path.join(ROOT, "tests", "support", "device_math_host.cpp")
+
+
+@pytest.fixture(scope="module")
+def mathlib(tmp_path_factory):
+    out = tmp_path_factory.mktemp("lhm") / "liblhm.so"
+    env = {k: v for k, v in os.environ.items() if k not in ("CC", "CXX")}
+    subprocess.run(["g++", "-O2", "-ffp-contract=off", "-shared", "-fPIC", "-I", CSRC, SRC, "-o", str(out)],
+                   check=True, env=env)
+    return C.CDLL(str(out))
+
+
+def _call(lib, name, *arrays):
+    n = len(arrays[0])
+    y = np.empty(n)
+    dp = C.POINTER(C.c_double)
+    fn = getattr(lib, name)
+    fn.restype = None
+    fn(*[np.ascontiguousarray(a).ctypes.data_as(dp) for a in arrays], y.ctypes.data_as(dp), C.c_long(n))
+    return y
+
+
+def _ulp_err(y, exact):
+    mp.mp.dps = 40
+    errs = []
+    for a, e in zip(y, exact):
+        e = mp.mpf(e)
+        if e == 0:
+            errs.append(0.0 if a == 0 else np.inf)
+            continue
+        ulp = mp.mpf(2) ** (mp.floor(mp.log(abs(e), 2)) - 52)
+        errs.append(float(abs(mp.mpf(float(a)) - e) / ulp))
+    return np.array(errs)
+
+
+def test_log(mathlib):
+    rng = np.random.default_rng(1)
+    x = np.concatenate([rng.uniform(1e-16, 2.0, 4000), 1.0 + rng.uniform(-1e-3, 1e-3, 1000),
+                        np.exp(rng.uniform(-40, 40, 2000)), [0.5, 1.0, 2.0, 0.70710678118654752, 1.4142135623730951]])
+    y = _call(mathlib, "lhm_log", x)
+    mp.mp.dps = 40
+    err = _ulp_err(y, [mp.log(mp.mpf(float(v))) for v in x])
+    assert err.max() <= 1.5, err.max()
+    sp = _call(mathlib, "lhm_log", np.array([0.0, -1.0, np.inf, np.nan, -0.5, -0.0]))
+    assert -710 < sp[0] < -709 and np.isnan(sp[1]) and np.isnan(sp[2]) and np.isnan(sp[3]) and np.isnan(sp[4])
+    assert np.isfinite(sp[5]) and sp[5] < -700      # -0.0 reads as a huge negative number, like +0
+
+
+def test_exp_and_expm1(mathlib):
+    rng = np.random.default_rng(2)
+    x = np.concatenate([rng.uniform(-50, 50, 4000), rng.uniform(-1, 1, 3000), rng.uniform(-0.1, 0.1, 1000),
+                        rng.uniform(-700, 700, 1000), [0.0, -0.0, 1e-300, -1e-20]])
+    mp.mp.dps = 40
+    y = _call(mathlib, "lhm_exp", x)
+    err = _ulp_err(y, [mp.e ** mp.mpf(float(v)) for v in x])
+    assert err.max() <= 1.5, err.max()
+    ym = _call(mathlib, "lhm_expm1", x)
+    errm = _ulp_err(ym, [mp.expm1(mp.mpf(float(v))) for v in x])
+    rel = np.abs(ym - np.array([float(mp.expm1(mp.mpf(float(v)))) for v in x])) / np.maximum(np.abs(ym), 1e-300)
+    assert rel.max() <= 6e-15, rel.max()          # s - 1 carries the table entry's rounding when k != 0
+    small = np.abs(x) < 0.0216
+    assert errm[small].max() <= 1.5               # the cancellation-sensitive range takes the exact path
+    sp = _call(mathlib, "lhm_exp", np.array([-np.inf, -800.0, -709.09, np.nan]))
+    assert 0 <= sp[0] < 1e-300 and 0 <= sp[1] < 1e-300 and 0 <= sp[2] < 1e-300 and np.isnan(sp[3])
+    sp = _call(mathlib, "lhm_expm1", np.array([-np.inf, -800.0, 0.0, np.nan]))
+    assert sp[0] == -1 and sp[1] == -1 and sp[2] == 0 and np.isnan(sp[3])
+
+
+def test_sqrt_rcp_div(mathlib):
+    rng = np.random.default_rng(3)
+    x = np.concatenate([rng.uniform(1e-16, 4.0, 4000), np.exp(rng.uniform(-200, 200, 2000))])
+    mp.mp.dps = 40
+    assert _ulp_err(_call(mathlib, "lhm_sqrt", x), [mp.sqrt(mp.mpf(float(v))) for v in x]).max() <= 1.0
+    assert _call(mathlib, "lhm_sqrt", np.array([0.0]))[0] == 0.0
+    assert _ulp_err(_call(mathlib, "lhm_rcp", x), [1 / mp.mpf(float(v)) for v in x]).max() <= 1.5
+    a = rng.uniform(-1e8, 1e8, len(x))
+    q = _call(mathlib, "lhm_div", a, x)
+    assert _ulp_err(q, [mp.mpf(float(u)) / mp.mpf(float(v)) for u, v in zip(a, x)]).max() <= 1.0
