@@ -149,6 +149,8 @@ typedef struct lh_soil_config {
 } lh_soil_config;
 
 #define LH_FLAG_CHECK_FINITE 1 /* rhs/step return LH_ERR_NONFINITE when NaN/Inf appears     */
+#define LH_FLAG_GENERAL_VG   2 /* never use the van Genuchten n == 2 (m == 1/2) square-root
+                                  specialisation: always evaluate the general-n log/exp form   */
 
 typedef struct lh_soil_ctx lh_soil_ctx;
 

@@ -35,6 +35,7 @@ LH_FIELD_THETA_L, LH_FIELD_THETA_I, LH_FIELD_RHO_E_INT, LH_FIELD_T = 0, 1, 2, 3
 LH_DIAG_K, LH_DIAG_PSI, LH_DIAG_KAPPA, LH_DIAG_T = 0, 1, 2, 3
 LH_BCV_TOP_ENERGY, LH_BCV_TOP_HYDROLOGY, LH_BCV_BOTTOM_ENERGY, LH_BCV_BOTTOM_HYDROLOGY = 0, 1, 2, 3
 LH_FLAG_CHECK_FINITE = 1
+LH_FLAG_GENERAL_VG = 2
 
 
 class SoilError(RuntimeError):

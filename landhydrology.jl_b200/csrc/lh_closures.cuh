@@ -78,8 +78,15 @@ struct LhCell {
 //         branch-free fast path: NoEffect factors (the reference's defaults, models.jl:31-32),
 //         ν_ss_om = 0 (outer Kersten exponents exactly 1) and θr = 0 (S_r == S bit for bit, so the
 //         Kersten number reuses log S).
+//   VG2 : van Genuchten n == 2 (m == 1/2) exactly, as in the reference's coupled tests
+//         (test/SoilModel/coupled.jl:6): S^(1/m) = S^2 and x^m = sqrt(x), so the retention curve and the
+//         conductivity need no log/exp at all:
+//             w = 1 - S^2 = (1 - S)(1 + S)       psi = -(1/alpha) sqrt(w) / S
+//             1 - sqrt(w) = S^2 / (1 + sqrt(w))  K = Ksat sqrt(S) (S^2 / (1 + sqrt(w)))^2
+//         (exact identities; the second also removes the cancellation of the literal form).
 #define LH_FLAG_ICE 1
 #define LH_FLAG_GEN 2
+#define LH_FLAG_VG2 4
 
 // ---------------------------------------------------------------------------------------------
 // Water: K and psi of one cell.  Reference: right_hand_side.jl:156-166 / :308-313.
@@ -88,7 +95,7 @@ struct LhCell {
 // results: the unsaturated expressions are evaluated unconditionally (they are the common case and
 // yield NaN/garbage only where the select discards them).
 // ---------------------------------------------------------------------------------------------
-template <bool ICE, bool GEN>
+template <bool ICE, bool GEN, bool VG2, bool NEED_LOG>
 __device__ __forceinline__ void lh_water_closures(const LhDevParams& p, const double* __restrict__ tab,
                                                   double th, double ti, double T,
                                                   double& K_out, double& psi_out, double& logS_K)
@@ -102,24 +109,37 @@ __device__ __forceinline__ void lh_water_closures(const LhDevParams& p, const do
     const bool icy = ICE && (ti != 0.0);
     double S_eff = S_K;                                                      // porosity = nu_eff (:235)
     if (icy) S_eff = lh_div(num, nu_eff - p.theta_r);
-
-    // ---- pressure head (:229-242) and the shared logs
-    const double L_eff = lh_log(mc, S_eff);
-    const double u = L_eff * p.vg_inv_m;
-    const double w = -lh_expm1(mc, tab, u);                                  // 1 - S^(1/m)
-    const double a = lh_log(mc, w);
-    const double psi_unsat = p.neg_inv_alpha * lh_exp(mc, tab, (a - u) * p.vg_inv_n);
     const double psi_sat = (th - nu_eff) * p.S_s_inv;
-    const double psi = (S_eff <= 1.0) ? psi_unsat : psi_sat;
+    double psi_unsat, Kr_unsat, L_K = 0.0;
 
-    // ---- hydraulic conductivity (:269-282)
-    double L_K = L_eff, a_K = a;
-    if (icy) {                           // S differs from S_eff only when ice is present
-        L_K = lh_log(mc, S_K);
-        a_K = lh_log(mc, -lh_expm1(mc, tab, L_K * p.vg_inv_m));
+    if (VG2) {
+        // ---- n = 2: square roots only
+        const double sw = lh_sqrt((1.0 - S_eff) * (1.0 + S_eff));            // (1 - S^(1/m))^m
+        psi_unsat = p.neg_inv_alpha * (sw * lh_rcp(S_eff));                  // :196-200
+        double swK = sw;
+        if (icy) swK = lh_sqrt((1.0 - S_K) * (1.0 + S_K));
+        const double t = (S_K * S_K) * lh_rcp(1.0 + swK);                    // 1 - (1 - S^(1/m))^m
+        Kr_unsat = lh_sqrt(S_K) * (t * t);                                   // :277
+        if (NEED_LOG) L_K = lh_log(mc, S_K);
+    } else {
+        // ---- general n: pressure head (:229-242) and the shared logs
+        const double L_eff = lh_log(mc, S_eff);
+        const double u = L_eff * p.vg_inv_m;
+        const double w = -lh_expm1(mc, tab, u);                              // 1 - S^(1/m)
+        const double a = lh_log(mc, w);
+        psi_unsat = p.neg_inv_alpha * lh_exp(mc, tab, (a - u) * p.vg_inv_n);
+        // ---- hydraulic conductivity (:269-282)
+        double a_K = a;
+        L_K = L_eff;
+        if (icy) {                       // S differs from S_eff only when ice is present
+            L_K = lh_log(mc, S_K);
+            a_K = lh_log(mc, -lh_expm1(mc, tab, L_K * p.vg_inv_m));
+        }
+        const double q = lh_expm1(mc, tab, p.vg_m * a_K);                    // (1 - y)^m - 1
+        Kr_unsat = lh_sqrt(S_K) * (q * q);
     }
-    const double q = lh_expm1(mc, tab, p.vg_m * a_K);                        // (1 - y)^m - 1
-    const double Kr = (S_K < 1.0) ? lh_sqrt(S_K) * (q * q) : 1.0;
+    const double psi = (S_eff <= 1.0) ? psi_unsat : psi_sat;
+    const double Kr = (S_K < 1.0) ? Kr_unsat : 1.0;
     double K = Kr * p.Ksat;
     if (GEN) {
         if (p.visc_on) K *= lh_exp(mc, tab, p.visc_gamma * (T - p.visc_T_ref));   // :117-126
@@ -188,7 +208,8 @@ template <int MODEL, int FLAGS>
 __device__ __forceinline__ LhCell lh_cell_closures(const LhDevParams& p, const double* __restrict__ tab,
                                                    double th, double ti, double T_or_re)
 {
-    constexpr bool ICE = (FLAGS & LH_FLAG_ICE) != 0, GEN = (FLAGS & LH_FLAG_GEN) != 0;
+    constexpr bool ICE = (FLAGS & LH_FLAG_ICE) != 0, GEN = (FLAGS & LH_FLAG_GEN) != 0, VG2 = (FLAGS & LH_FLAG_VG2) != 0;
+    constexpr bool REUSE = (MODEL == 2) && !ICE && !GEN;   // the Kersten number takes log S from the water closure
     LhCell c;
     c.K = 0.0; c.psi = 0.0; c.kappa = 0.0; c.T = T_or_re;
     const double nu_eff = ICE ? p.nu - ti : p.nu;
@@ -196,7 +217,7 @@ __device__ __forceinline__ LhCell lh_cell_closures(const LhDevParams& p, const d
     const double tl = unsat ? th : nu_eff;                                   // volumetric_liquid_fraction :181-188
     if (MODEL != 0) c.T = lh_temperature<ICE>(p, tl, ti, T_or_re);
     double logS = 0.0;
-    if (MODEL != 1) lh_water_closures<ICE, GEN>(p, tab, th, ti, c.T, c.K, c.psi, logS);
+    if (MODEL != 1) lh_water_closures<ICE, GEN, VG2, REUSE>(p, tab, th, ti, c.T, c.K, c.psi, logS);
     if (MODEL == 1) c.kappa = lh_thermal_conductivity<ICE, GEN, false>(p, tab, tl, ti, unsat, 0.0);
     if (MODEL == 2) c.kappa = lh_thermal_conductivity<ICE, GEN, true>(p, tab, tl, ti, unsat, logS);
     return c;

@@ -6,6 +6,15 @@
 
 #include "lh_closures.cuh"
 
+// Register budget of the stage kernels: threads per block <= LH_MAX_THREADS, blocks per SM >=
+// LH_MIN_BLOCKS (tuning knobs; tools/build_variant.sh builds alternatives).
+#ifndef LH_MIN_BLOCKS
+#define LH_MIN_BLOCKS 1
+#endif
+#ifndef LH_MAX_THREADS
+#define LH_MAX_THREADS 512
+#endif
+
 // Device layout of every cell field: column-fastest SoA, element (layer, col) at
 // [layer * ncol_pad + col]; ncol_pad is a multiple of 32 so that a warp (32 adjacent columns)
 // reads/writes two full, aligned 128-byte lines per field per layer.

@@ -92,7 +92,8 @@ struct lh_soil_ctx {
     ncclComm_t_ comm = nullptr;
     int nranks = 1, rank = 0;
     bool has_ice = false;        // some θ_i != 0 (θ_i is constant in time: dθ_i ≡ 0), re-evaluated on every θ_i upload
-    int kernel_flags = 0;        // LH_FLAG_ICE | LH_FLAG_GEN -> compiled kernel variant
+    int kernel_flags = 0;        // LH_FLAG_ICE | LH_FLAG_GEN | LH_FLAG_VG2 -> compiled kernel variant
+    bool force_general_vg = false;   // LH_FLAG_GENERAL_VG: never take the n == 2 shortcut (benchmark the general path)
     bool timing_valid = false;
     int64_t last_launches = 0;
     char err[512] = "";
@@ -342,7 +343,8 @@ void update_kernel_flags(lh_soil_ctx* c)
 {
     const lh_soil_params& q = c->cfg.params;
     const bool gen = c->dp.visc_on || c->dp.imp_on || !c->dp.om_zero || q.theta_r != 0.0;
-    c->kernel_flags = (c->has_ice ? LH_FLAG_ICE : 0) | (gen ? LH_FLAG_GEN : 0);
+    const bool vg2 = q.vg_n == 2.0 && q.vg_m == 0.5;      // S^(1/m) = S^2, x^m = sqrt(x): no log/exp needed
+    c->kernel_flags = (c->has_ice ? LH_FLAG_ICE : 0) | (gen ? LH_FLAG_GEN : 0) | (vg2 && !c->force_general_vg ? LH_FLAG_VG2 : 0);
 }
 
 // θ_i was (re)written: is there any ice?  One pass over the field; θ_i never changes afterwards.
@@ -435,6 +437,7 @@ int32_t lh_soil_create(const lh_soil_config* cfg, lh_soil_ctx** out)
     c->nlayer = cfg->nlayer;
     c->model = cfg->model;
     c->dp = derive_params(*cfg);
+    c->force_general_vg = (cfg->flags & LH_FLAG_GENERAL_VG) != 0;
     c->bcv[LH_BCV_TOP_ENERGY] = cfg->top.energy_value;
     c->bcv[LH_BCV_TOP_HYDROLOGY] = cfg->top.hydrology_value;
     c->bcv[LH_BCV_BOTTOM_ENERGY] = cfg->bottom.energy_value;

@@ -1,0 +1,339 @@
+// lh_stage_kernel.cuh — the fused soil RHS (+ SSPRK33 stage) kernel template and its launcher.
+// Included by one translation unit per model (lh_kernels_m0/m1/m2.cu) so the 3 x 4 x 8 kernel variants
+// compile in parallel.  See lh_kernels.cu for the design notes.
+#pragma once
+
+#include "lh_kernels.cuh"
+
+#include "lh_soil.h"
+
+namespace {
+
+// Quantities exchanged across a chunk face / kept in the sliding window.
+template <int MODEL> struct Q;
+template <> struct Q<0> { double K, h; };                       // Richards
+template <> struct Q<1> { double kappa, T; };                   // heat
+template <> struct Q<2> { double K, h, kappa, T, eK; };         // coupled
+
+template <int MODEL> struct NQ { static constexpr int value = sizeof(Q<MODEL>) / sizeof(double); };
+
+struct Flux { double w, e; };
+
+template <int MODEL>
+__device__ __forceinline__ void q_store(double* sm, const Q<MODEL>& q)
+{
+    // sm points at this lane's slot; quantities are strided by 32 lanes (conflict-free)
+    if constexpr (MODEL == 0) { sm[0] = q.K; sm[32] = q.h; }
+    else if constexpr (MODEL == 1) { sm[0] = q.kappa; sm[32] = q.T; }
+    else { sm[0] = q.K; sm[32] = q.h; sm[64] = q.kappa; sm[96] = q.T; sm[128] = q.eK; }
+}
+
+template <int MODEL>
+__device__ __forceinline__ Q<MODEL> q_load(const double* sm)
+{
+    Q<MODEL> q;
+    if constexpr (MODEL == 0) { q.K = sm[0]; q.h = sm[32]; }
+    else if constexpr (MODEL == 1) { q.kappa = sm[0]; q.T = sm[32]; }
+    else { q.K = sm[0]; q.h = sm[32]; q.kappa = sm[64]; q.T = sm[96]; q.eK = sm[128]; }
+    return q;
+}
+
+// Interior face between cell `lo` (below) and `hi` (above).
+//   water  right_hand_side.jl:181/:358   -interpc2f(K) * gradc2f(h)
+//   energy :259 / :361-365               -interpc2f(κ) * gradc2f(T) - interpc2f(ρe_int_l K) * gradc2f(h)
+template <int MODEL>
+__device__ __forceinline__ Flux face_flux(const LhDevParams& p, const Q<MODEL>& lo, const Q<MODEL>& hi)
+{
+    Flux f;
+    f.w = 0.0; f.e = 0.0;
+    if constexpr (MODEL == 0) {
+        const double gh = (hi.h - lo.h) * p.inv_dz;
+        f.w = -(0.5 * (lo.K + hi.K)) * gh;
+    } else if constexpr (MODEL == 1) {
+        const double gT = (hi.T - lo.T) * p.inv_dz;
+        f.e = -(0.5 * (lo.kappa + hi.kappa)) * gT;
+    } else {
+        const double gh = (hi.h - lo.h) * p.inv_dz;
+        const double gT = (hi.T - lo.T) * p.inv_dz;
+        f.w = -(0.5 * (lo.K + hi.K)) * gh;
+        f.e = -(0.5 * (lo.kappa + hi.kappa)) * gT - (0.5 * (lo.eK + hi.eK)) * gh;
+    }
+    return f;
+}
+
+// boundary_fluxes(X, bc::SoilComponentBC, face, ...) boundary_conditions.jl:470-489 for one face.
+// (th, ti) raw centre values, `c` the centre closures (c.T is the centre temperature).
+template <int MODEL, int FLAGS>
+__device__ __forceinline__ Flux boundary_flux(const LhDevParams& p, const double* __restrict__ tab, int e_kind,
+                                              int h_kind, double val_e, double val_h, bool is_bottom,
+                                              double th, double ti, const LhCell& c)
+{
+    constexpr bool ICE = (FLAGS & LH_FLAG_ICE) != 0, GEN = (FLAGS & LH_FLAG_GEN) != 0;
+    Flux f;
+    f.w = 0.0; f.e = 0.0;
+    // X_cf face values (:218-228, :241-288): Dirichlet overrides, energy first then hydrology
+    const double th_f = (MODEL != 1 && h_kind == LH_BC_DIRICHLET) ? val_h : th;
+    const double T_f = (MODEL != 0 && e_kind == LH_BC_DIRICHLET) ? val_e : c.T;
+    if constexpr (MODEL != 1) {
+        if (h_kind == LH_BC_FLUX) {
+            f.w = val_h;                                                     // :295-301
+        } else if (h_kind == LH_BC_FREE_DRAINAGE) {
+            f.w = -c.K;                                                      // :328-356 (K of the centre cell)
+        } else if (h_kind == LH_BC_DIRICHLET) {                              // :371-401
+            double K_f, psi_f, l_;
+            lh_water_closures<ICE, GEN, (FLAGS & LH_FLAG_VG2) != 0, false>(p, tab, th_f, ti, T_f, K_f, psi_f, l_);
+            double flux = (-K_f * (psi_f - c.psi + p.half_dz)) * p.inv_half_dz;
+            f.w = is_bottom ? -flux : flux;
+        }
+    }
+    if constexpr (MODEL != 0) {
+        if (e_kind == LH_BC_FLUX) {
+            f.e = val_e;
+        } else if (e_kind == LH_BC_DIRICHLET) {                              // :416-444
+            const double kappa_f = lh_face_kappa<FLAGS>(p, tab, th_f, ti);
+            double flux = (-kappa_f * (T_f - c.T)) * p.inv_half_dz;
+            f.e = is_bottom ? -flux : flux;
+        }
+    }
+    return f;
+}
+
+template <int STAGE>
+__device__ __forceinline__ double stage_base(double v, double u0)
+{
+    if constexpr (STAGE == 2) return fma(3.0, u0, v);       // 3 u0 + u1
+    else if constexpr (STAGE == 3) return fma(2.0, v, u0);  // u0 + 2 u2
+    else return v;
+}
+
+template <int STAGE>
+__device__ __forceinline__ double stage_out(double base, double k, double dt)
+{
+    if constexpr (STAGE == 0) return k;
+    else if constexpr (STAGE == 1) return fma(dt, k, base);
+    else if constexpr (STAGE == 2) return 0.25 * fma(dt, k, base);
+    else return (1.0 / 3.0) * fma(2.0 * dt, k, base);
+}
+
+struct Base { double th, re; };
+struct Raw { double th, ti, x, u0th, u0re; };
+template <int MODEL> struct Cell { Q<MODEL> q; double psi; Base base; };
+
+// Shared-memory slot of one (column group, chunk): [bot: NQ + psi][top: NQ + psi][pending: 4], each x32 lanes.
+template <int MODEL> struct Slot { static constexpr int NQv = NQ<MODEL>::value; static constexpr int doubles = (2 * (NQv + 1) + 4) * 32; };
+
+template <int MODEL, int STAGE, int FLAGS>
+__global__ void __launch_bounds__(LH_MAX_THREADS, LH_MIN_BLOCKS)
+lh_soil_stage_kernel(const __grid_constant__ LhKernelArgs A)
+{
+    extern __shared__ double smem[];
+    constexpr int NQv = NQ<MODEL>::value;
+    constexpr bool ICE = (FLAGS & LH_FLAG_ICE) != 0;
+    const LhDevParams& p = A.p;
+    const int lane = threadIdx.x, w = threadIdx.y, g = threadIdx.z;
+    const int W = blockDim.y;
+    const int64_t col = ((int64_t)blockIdx.x * blockDim.z + g) * 32 + lane;
+    const bool valid = col < A.ncol_pad;      // whole column groups are valid or not (ncol_pad % 32 == 0)
+    const int n = A.nlayer;
+    const int a = w * A.Lc;
+    const int b = min(n, a + A.Lc);
+    const int64_t stride = A.ncol_pad;
+    const bool active = valid && a < n;
+    const bool need_T = (MODEL == 0) && (FLAGS & LH_FLAG_GEN) && p.visc_on;
+
+    // shared memory: [16] exp table, then one Slot per (g, w)
+    const double* tab = smem;
+    lh_stage_exp_table(p, smem, (threadIdx.z * blockDim.y + threadIdx.y) * 32 + threadIdx.x);
+    double* slot = smem + 16 + (size_t)(g * W + w) * Slot<MODEL>::doubles + lane;
+    double* sm_bot = slot;                               // Q then psi
+    double* sm_top = slot + (NQv + 1) * 32;
+    double* sm_pend = slot + 2 * (NQv + 1) * 32;         // base.th, base.re, F_first_up.w, F_first_up.e
+    __syncthreads();
+
+    const double* pth = A.in_th + col;
+    const double* pti = A.in_ti + col;
+    const double* pre = A.in_re + col;
+    const double* pT = A.aux_T + col;
+    const double* p0th = A.u0_th + col;
+    const double* p0re = A.u0_re + col;
+    double* oth = A.out_th + col;
+    double* ore = A.out_re + col;
+
+    // Raw values of cell i.  No register software-pipeline: ptxas sinks such loads down to the next
+    // possibly-aliasing store (the stage buffers are updated in place) and spills them.  Instead the
+    // lines of cell i+2 are pulled into L1 with prefetch instructions, which cost no registers.
+    auto prefetch = [&](int i) {
+        const int64_t o = (int64_t)min(i, n - 1) * stride;
+        asm volatile("prefetch.global.L1 [%0];" ::"l"(pth + o));
+        if (ICE) asm volatile("prefetch.global.L1 [%0];" ::"l"(pti + o));
+        if (MODEL != 0) asm volatile("prefetch.global.L1 [%0];" ::"l"(pre + o));
+        else if (need_T) asm volatile("prefetch.global.L1 [%0];" ::"l"(pT + o));
+        if constexpr (STAGE >= 2) {
+            if constexpr (MODEL != 1) asm volatile("prefetch.global.L1 [%0];" ::"l"(p0th + o));
+            if constexpr (MODEL != 0) asm volatile("prefetch.global.L1 [%0];" ::"l"(p0re + o));
+        }
+    };
+    auto load_raw = [&](int i) {
+        Raw r;
+        const int64_t o = (int64_t)i * stride;
+        r.th = pth[o];
+        r.ti = ICE ? pti[o] : 0.0;
+        r.x = (MODEL != 0) ? pre[o] : (need_T ? pT[o] : 288.0);
+        r.u0th = 0.0; r.u0re = 0.0;
+        if constexpr (STAGE >= 2) {
+            if constexpr (MODEL != 1) r.u0th = p0th[o];
+            if constexpr (MODEL != 0) r.u0re = p0re[o];
+        }
+        return r;
+    };
+    auto eval = [&](const Raw& r, int i) {
+        const LhCell c = lh_cell_closures<MODEL, FLAGS>(p, tab, r.th, r.ti, r.x);
+        Cell<MODEL> o;
+        if constexpr (MODEL == 0) { o.q.K = c.K; o.q.h = c.psi + A.zc[i]; }
+        else if constexpr (MODEL == 1) { o.q.kappa = c.kappa; o.q.T = c.T; }
+        else {
+            o.q.K = c.K; o.q.h = c.psi + A.zc[i]; o.q.kappa = c.kappa; o.q.T = c.T;
+            o.q.eK = (p.rhocp_l * (c.T - p.T_0)) * c.K;                      // ρe_int_l * K (:306, :364)
+        }
+        o.psi = c.psi;
+        o.base.th = (MODEL != 1) ? stage_base<STAGE>(r.th, r.u0th) : 0.0;
+        o.base.re = (MODEL != 0) ? stage_base<STAGE>(r.x, r.u0re) : 0.0;
+        return o;
+    };
+    auto write_cell = [&](int i, const Base& base, const Flux& lo, const Flux& hi) {
+        const int64_t o = (int64_t)i * stride;
+        if constexpr (MODEL != 1) oth[o] = stage_out<STAGE>(base.th, -(hi.w - lo.w) * p.inv_dz, A.dt);
+        if constexpr (MODEL != 0) ore[o] = stage_out<STAGE>(base.re, -(hi.e - lo.e) * p.inv_dz, A.dt);
+    };
+
+    Q<MODEL> prev;            // closures of the last evaluated cell
+    Base base_prev;
+    Flux F_below;
+    F_below.w = F_below.e = 0.0;
+    base_prev.th = base_prev.re = 0.0;
+
+    if (active) {
+        prefetch(a + 1);
+        int i = a;
+        {   // first cell of the chunk: no face below it yet -> park what its update needs in shared memory
+            prefetch(i + 2);
+            const Cell<MODEL> c = eval(load_raw(i), i);
+            q_store<MODEL>(sm_bot, c.q);
+            sm_bot[NQv * 32] = c.psi;
+            sm_pend[0] = c.base.th; sm_pend[32] = c.base.re;
+            sm_top[NQv * 32] = c.psi;          // also the last cell so far
+            prev = c.q; base_prev = c.base;
+            ++i;
+        }
+        if (i < b) {   // second cell: the face above the first cell
+            prefetch(i + 2);
+            const Cell<MODEL> c = eval(load_raw(i), i);
+            const Flux F = face_flux<MODEL>(p, prev, c.q);
+            sm_pend[64] = F.w; sm_pend[96] = F.e;
+            if (i + 1 == b) sm_top[NQv * 32] = c.psi;
+            F_below = F; prev = c.q; base_prev = c.base;
+            ++i;
+        }
+        for (; i + 1 < b; i += 2) {   // two cells per trip: no sliding-window register moves
+            prefetch(i + 2);
+            prefetch(i + 3);
+            const Cell<MODEL> c0 = eval(load_raw(i), i);
+            const Flux F0 = face_flux<MODEL>(p, prev, c0.q);
+            write_cell(i - 1, base_prev, F_below, F0);
+            const Cell<MODEL> c1 = eval(load_raw(i + 1), i + 1);
+            const Flux F1 = face_flux<MODEL>(p, c0.q, c1.q);
+            write_cell(i, c0.base, F0, F1);
+            if (i + 2 == b) sm_top[NQv * 32] = c1.psi;
+            F_below = F1; prev = c1.q; base_prev = c1.base;
+        }
+        if (i < b) {   // odd tail
+            const Cell<MODEL> c = eval(load_raw(i), i);
+            const Flux F = face_flux<MODEL>(p, prev, c.q);
+            write_cell(i - 1, base_prev, F_below, F);
+            sm_top[NQv * 32] = c.psi;
+            F_below = F; prev = c.q; base_prev = c.base;
+        }
+        q_store<MODEL>(sm_top, prev);
+    }
+    __syncthreads();
+    if (active) {
+        const Q<MODEL> first = q_load<MODEL>(sm_bot);
+        Flux F_lo, F_hi;
+        if (a == 0) {
+            // bottom boundary flux from the first cell (its raw values are still unwritten in global memory)
+            LhCell c;
+            c.K = 0.0; c.psi = sm_bot[NQv * 32]; c.kappa = 0.0; c.T = 288.0;
+            if constexpr (MODEL != 1) c.K = first.K;
+            if constexpr (MODEL != 0) c.T = first.T;
+            else if (need_T) c.T = pT[0];
+            F_lo = boundary_flux<MODEL, FLAGS>(p, tab, A.bot_e_kind, A.bot_h_kind, A.bcv[LH_BCV_BOTTOM_ENERGY],
+                                               A.bcv[LH_BCV_BOTTOM_HYDROLOGY], true, pth[0], ICE ? pti[0] : 0.0, c);
+        } else {
+            F_lo = face_flux<MODEL>(p, q_load<MODEL>(sm_top - Slot<MODEL>::doubles), first);   // top of chunk w-1
+        }
+        if (b == n) {
+            const int64_t o = (int64_t)(n - 1) * stride;
+            LhCell c;
+            c.K = 0.0; c.psi = sm_top[NQv * 32]; c.kappa = 0.0; c.T = 288.0;
+            if constexpr (MODEL != 1) c.K = prev.K;
+            if constexpr (MODEL != 0) c.T = prev.T;
+            else if (need_T) c.T = pT[o];
+            F_hi = boundary_flux<MODEL, FLAGS>(p, tab, A.top_e_kind, A.top_h_kind, A.bcv[LH_BCV_TOP_ENERGY],
+                                               A.bcv[LH_BCV_TOP_HYDROLOGY], false, pth[o], ICE ? pti[o] : 0.0, c);
+        } else {
+            F_hi = face_flux<MODEL>(p, prev, q_load<MODEL>(sm_bot + Slot<MODEL>::doubles));    // bot of chunk w+1
+        }
+        Base base_first;
+        base_first.th = sm_pend[0]; base_first.re = sm_pend[32];
+        if (b - a == 1) {
+            write_cell(a, base_first, F_lo, F_hi);
+        } else {
+            Flux F_first_up;
+            F_first_up.w = sm_pend[64]; F_first_up.e = sm_pend[96];
+            write_cell(a, base_first, F_lo, F_first_up);
+            write_cell(b - 1, base_prev, F_below, F_hi);
+        }
+    }
+}
+
+template <int MODEL, int FLAGS>
+cudaError_t launch_variant(int stage, const LhKernelArgs& args, const LhLaunchShape& s, cudaStream_t stream)
+{
+    dim3 block(32, s.W, s.G);
+    dim3 grid((unsigned)s.nblocks);
+    if (s.smem_bytes > 48 * 1024) {
+        cudaError_t e;
+        const int bytes = (int)s.smem_bytes;
+        if ((e = cudaFuncSetAttribute(lh_soil_stage_kernel<MODEL, 0, FLAGS>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes))) return e;
+        if ((e = cudaFuncSetAttribute(lh_soil_stage_kernel<MODEL, 1, FLAGS>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes))) return e;
+        if ((e = cudaFuncSetAttribute(lh_soil_stage_kernel<MODEL, 2, FLAGS>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes))) return e;
+        if ((e = cudaFuncSetAttribute(lh_soil_stage_kernel<MODEL, 3, FLAGS>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes))) return e;
+    }
+    switch (stage) {
+    case 0: lh_soil_stage_kernel<MODEL, 0, FLAGS><<<grid, block, s.smem_bytes, stream>>>(args); break;
+    case 1: lh_soil_stage_kernel<MODEL, 1, FLAGS><<<grid, block, s.smem_bytes, stream>>>(args); break;
+    case 2: lh_soil_stage_kernel<MODEL, 2, FLAGS><<<grid, block, s.smem_bytes, stream>>>(args); break;
+    case 3: lh_soil_stage_kernel<MODEL, 3, FLAGS><<<grid, block, s.smem_bytes, stream>>>(args); break;
+    default: return cudaErrorInvalidValue;
+    }
+    return cudaGetLastError();
+}
+
+template <int MODEL>
+cudaError_t launch_model(int stage, int flags, const LhKernelArgs& args, const LhLaunchShape& s, cudaStream_t stream)
+{
+    if (MODEL == 1) flags &= ~LH_FLAG_VG2;   // the heat-only model has no water closures
+    switch (flags & 7) {
+    case 0: return launch_variant<MODEL, 0>(stage, args, s, stream);
+    case 1: return launch_variant<MODEL, 1>(stage, args, s, stream);
+    case 2: return launch_variant<MODEL, 2>(stage, args, s, stream);
+    case 3: return launch_variant<MODEL, 3>(stage, args, s, stream);
+    case 4: return launch_variant<MODEL, (MODEL == 1 ? 0 : 4)>(stage, args, s, stream);
+    case 5: return launch_variant<MODEL, (MODEL == 1 ? 1 : 5)>(stage, args, s, stream);
+    case 6: return launch_variant<MODEL, (MODEL == 1 ? 2 : 6)>(stage, args, s, stream);
+    default: return launch_variant<MODEL, (MODEL == 1 ? 3 : 7)>(stage, args, s, stream);
+    }
+}
+
+}  // namespace
+

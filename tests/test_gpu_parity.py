@@ -20,8 +20,8 @@ TOL_TENDENCY = 1e-12
 TOL_STATE = 1e-10
 
 
-def _pair(cuda, oracle, wl):
-    g = lh.SoilContext(cuda, wl.config())
+def _pair(cuda, oracle, wl, flags=0):
+    g = lh.SoilContext(cuda, wl.config(flags=flags))
     o = lh.SoilContext(oracle, wl.config())
     wl.upload(g)
     wl.upload(o)
@@ -83,6 +83,23 @@ def test_richards_tendency_and_state(cuda, oracle, ncol, nlayer):
 @pytest.mark.parametrize("ncol,nlayer", [(1, 60), (128, 60), (70, 24)])
 def test_heat_tendency_and_state(cuda, oracle, ncol, nlayer):
     wl = w.heat_workload(ncol=ncol, nlayer=nlayer, seed=300 + ncol + nlayer)
+    g, o = _pair(cuda, oracle, wl)
+    assert_tendency_parity(g, o, wl.model)
+    assert_state_parity(g, o, wl.model, wl.dt, 10)
+
+
+@pytest.mark.parametrize("ice", [False, True])
+def test_coupled_general_van_genuchten_path(cuda, oracle, ice):
+    """The coupled workload has n = 2, which the library evaluates with the square-root
+    specialisation (LH_FLAG_VG2 kernels); LH_FLAG_GENERAL_VG forces the general-n log/exp closures on
+    the same inputs, and a non-integer n exercises them without the flag."""
+    wl = w.coupled_workload(ncol=96, nlayer=64, seed=411, ice=ice)
+    g, o = _pair(cuda, oracle, wl, flags=abi.LH_FLAG_GENERAL_VG)
+    assert_tendency_parity(g, o, wl.model)
+    assert_state_parity(g, o, wl.model, wl.dt, 10)
+    wl = w.coupled_workload(ncol=96, nlayer=64, seed=412, ice=ice)
+    wl.params.vg_n = 1.56
+    wl.params.vg_m = 1.0 - 1.0 / 1.56
     g, o = _pair(cuda, oracle, wl)
     assert_tendency_parity(g, o, wl.model)
     assert_state_parity(g, o, wl.model, wl.dt, 10)

@@ -5,4 +5,4 @@ out=$1; shift
 cd "$(dirname "$0")/.."
 unset CC CXX
 nvcc -gencode arch=compute_100a,code=sm_100a -O3 -lineinfo -std=c++17 --fmad=true -Xcompiler -fPIC,-O2 -shared -cudart static \
-  -I include -I landhydrology.jl_b200/csrc "$@" -o "$out" landhydrology.jl_b200/csrc/lh_kernels.cu landhydrology.jl_b200/csrc/lh_soil_api.cu -ldl
+  -I include -I landhydrology.jl_b200/csrc "$@" -o "$out" -t 4 landhydrology.jl_b200/csrc/*.cu -ldl
