@@ -120,6 +120,9 @@ struct Raw { double th, ti, x, u0th, u0re; };
 template <int MODEL> struct Cell { Q<MODEL> q; double psi; Base base; };
 
 // Shared-memory slot of one (column group, chunk): [bot: NQ + psi][top: NQ + psi][pending: 4], each x32 lanes.
+// Input ring (cp.async): RING_DEPTH cells x RING_FIELDS fields x 32 lanes per warp.
+constexpr int RING_DEPTH = 4, RING_FIELDS = 5, RING_DOUBLES = RING_DEPTH * RING_FIELDS * 32;
+
 template <int MODEL> struct Slot { static constexpr int NQv = NQ<MODEL>::value; static constexpr int doubles = (2 * (NQv + 1) + 4) * 32; };
 
 template <int MODEL, int STAGE, int FLAGS>
@@ -141,13 +144,16 @@ lh_soil_stage_kernel(const __grid_constant__ LhKernelArgs A)
     const bool active = valid && a < n;
     const bool need_T = (MODEL == 0) && (FLAGS & LH_FLAG_GEN) && p.visc_on;
 
-    // shared memory: [16] exp table, then one Slot per (g, w)
+    // shared memory: [16] exp table, then per (g, w): one Slot (chunk-face exchange) and one input ring
     const double* tab = smem;
     lh_stage_exp_table(p, smem, (threadIdx.z * blockDim.y + threadIdx.y) * 32 + threadIdx.x);
-    double* slot = smem + 16 + (size_t)(g * W + w) * Slot<MODEL>::doubles + lane;
+    double* warp_base = smem + 16 + (size_t)(g * W + w) * (Slot<MODEL>::doubles + RING_DOUBLES);
+    double* slot = warp_base + lane;
     double* sm_bot = slot;                               // Q then psi
     double* sm_top = slot + (NQv + 1) * 32;
     double* sm_pend = slot + 2 * (NQv + 1) * 32;         // base.th, base.re, F_first_up.w, F_first_up.e
+    double* ring = warp_base + Slot<MODEL>::doubles + lane;   // [RING_DEPTH][RING_FIELDS][32]
+    const uint32_t ring_s = (uint32_t)__cvta_generic_to_shared(ring);
     __syncthreads();
 
     const double* pth = A.in_th + col;
@@ -159,31 +165,44 @@ lh_soil_stage_kernel(const __grid_constant__ LhKernelArgs A)
     double* oth = A.out_th + col;
     double* ore = A.out_re + col;
 
-    // Raw values of cell i.  No register software-pipeline: ptxas sinks such loads down to the next
-    // possibly-aliasing store (the stage buffers are updated in place) and spills them.  Instead the
-    // lines of cell i+2 are pulled into L1 with prefetch instructions, which cost no registers.
-    auto prefetch = [&](int i) {
-        const int64_t o = (int64_t)min(i, n - 1) * stride;
-        asm volatile("prefetch.global.L1 [%0];" ::"l"(pth + o));
-        if (ICE) asm volatile("prefetch.global.L1 [%0];" ::"l"(pti + o));
-        if (MODEL != 0) asm volatile("prefetch.global.L1 [%0];" ::"l"(pre + o));
-        else if (need_T) asm volatile("prefetch.global.L1 [%0];" ::"l"(pT + o));
-        if constexpr (STAGE >= 2) {
-            if constexpr (MODEL != 1) asm volatile("prefetch.global.L1 [%0];" ::"l"(p0th + o));
-            if constexpr (MODEL != 0) asm volatile("prefetch.global.L1 [%0];" ::"l"(p0re + o));
+    // Input pipeline.  The raw values of cell i travel global -> shared with cp.async (LDGSTS): no
+    // registers are held while the copy is in flight (a register software pipeline was tried: ptxas
+    // sinks such loads down to the next possibly-aliasing store and spills them; prefetch.global.L1
+    // was tried too and only reaches L2 on this part — 3 % L1 hit rate, profiles/r01_d_*).  Each lane
+    // copies and later reads back only ITS OWN 8 bytes, so cp.async.wait_group is the only
+    // synchronisation needed.  Ring of RING_DEPTH cells; one commit group per cell, always committed
+    // (empty past the end of the chunk) so that wait_group's constant stays valid.
+    auto cp8 = [&](uint32_t dst, const double* src) {
+        asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(dst), "l"(src) : "memory");
+    };
+    auto issue = [&](int i) {
+        if (i < b) {
+            const int64_t o = (int64_t)i * stride;
+            const uint32_t d = ring_s + (uint32_t)(i & (RING_DEPTH - 1)) * (RING_FIELDS * 256);
+            cp8(d, pth + o);
+            if (ICE) cp8(d + 256, pti + o);
+            if (MODEL != 0) cp8(d + 512, pre + o);
+            else if (need_T) cp8(d + 512, pT + o);
+            if constexpr (STAGE >= 2) {
+                if constexpr (MODEL != 1) cp8(d + 768, p0th + o);
+                if constexpr (MODEL != 0) cp8(d + 1024, p0re + o);
+            }
         }
+        asm volatile("cp.async.commit_group;" ::: "memory");
     };
     auto load_raw = [&](int i) {
+        asm volatile("cp.async.wait_group %0;" ::"n"(RING_DEPTH - 2) : "memory");
+        const double* d = ring + (i & (RING_DEPTH - 1)) * (RING_FIELDS * 32);
         Raw r;
-        const int64_t o = (int64_t)i * stride;
-        r.th = pth[o];
-        r.ti = ICE ? pti[o] : 0.0;
-        r.x = (MODEL != 0) ? pre[o] : (need_T ? pT[o] : 288.0);
+        r.th = d[0];
+        r.ti = ICE ? d[32] : 0.0;
+        r.x = (MODEL != 0 || need_T) ? d[64] : 288.0;
         r.u0th = 0.0; r.u0re = 0.0;
         if constexpr (STAGE >= 2) {
-            if constexpr (MODEL != 1) r.u0th = p0th[o];
-            if constexpr (MODEL != 0) r.u0re = p0re[o];
+            if constexpr (MODEL != 1) r.u0th = d[96];
+            if constexpr (MODEL != 0) r.u0re = d[128];
         }
+        issue(i + RING_DEPTH - 1);       // refill the slot cell i-1 has just vacated
         return r;
     };
     auto eval = [&](const Raw& r, int i) {
@@ -213,10 +232,9 @@ lh_soil_stage_kernel(const __grid_constant__ LhKernelArgs A)
     base_prev.th = base_prev.re = 0.0;
 
     if (active) {
-        prefetch(a + 1);
+        for (int k = 0; k < RING_DEPTH - 1; ++k) issue(a + k);
         int i = a;
         {   // first cell of the chunk: no face below it yet -> park what its update needs in shared memory
-            prefetch(i + 2);
             const Cell<MODEL> c = eval(load_raw(i), i);
             q_store<MODEL>(sm_bot, c.q);
             sm_bot[NQv * 32] = c.psi;
@@ -226,7 +244,6 @@ lh_soil_stage_kernel(const __grid_constant__ LhKernelArgs A)
             ++i;
         }
         if (i < b) {   // second cell: the face above the first cell
-            prefetch(i + 2);
             const Cell<MODEL> c = eval(load_raw(i), i);
             const Flux F = face_flux<MODEL>(p, prev, c.q);
             sm_pend[64] = F.w; sm_pend[96] = F.e;
@@ -235,8 +252,6 @@ lh_soil_stage_kernel(const __grid_constant__ LhKernelArgs A)
             ++i;
         }
         for (; i + 1 < b; i += 2) {   // two cells per trip: no sliding-window register moves
-            prefetch(i + 2);
-            prefetch(i + 3);
             const Cell<MODEL> c0 = eval(load_raw(i), i);
             const Flux F0 = face_flux<MODEL>(p, prev, c0.q);
             write_cell(i - 1, base_prev, F_below, F0);
@@ -269,7 +284,7 @@ lh_soil_stage_kernel(const __grid_constant__ LhKernelArgs A)
             F_lo = boundary_flux<MODEL, FLAGS>(p, tab, A.bot_e_kind, A.bot_h_kind, A.bcv[LH_BCV_BOTTOM_ENERGY],
                                                A.bcv[LH_BCV_BOTTOM_HYDROLOGY], true, pth[0], ICE ? pti[0] : 0.0, c);
         } else {
-            F_lo = face_flux<MODEL>(p, q_load<MODEL>(sm_top - Slot<MODEL>::doubles), first);   // top of chunk w-1
+            F_lo = face_flux<MODEL>(p, q_load<MODEL>(sm_top - (Slot<MODEL>::doubles + RING_DOUBLES)), first);   // top of chunk w-1
         }
         if (b == n) {
             const int64_t o = (int64_t)(n - 1) * stride;
@@ -281,7 +296,7 @@ lh_soil_stage_kernel(const __grid_constant__ LhKernelArgs A)
             F_hi = boundary_flux<MODEL, FLAGS>(p, tab, A.top_e_kind, A.top_h_kind, A.bcv[LH_BCV_TOP_ENERGY],
                                                A.bcv[LH_BCV_TOP_HYDROLOGY], false, pth[o], ICE ? pti[o] : 0.0, c);
         } else {
-            F_hi = face_flux<MODEL>(p, prev, q_load<MODEL>(sm_bot + Slot<MODEL>::doubles));    // bot of chunk w+1
+            F_hi = face_flux<MODEL>(p, prev, q_load<MODEL>(sm_bot + (Slot<MODEL>::doubles + RING_DOUBLES)));    // bot of chunk w+1
         }
         Base base_first;
         base_first.th = sm_pend[0]; base_first.re = sm_pend[32];
