@@ -113,13 +113,17 @@ __device__ __forceinline__ void lh_water_closures(const LhDevParams& p, const do
     double psi_unsat, Kr_unsat, L_K = 0.0;
 
     if (VG2) {
-        // ---- n = 2: square roots only
+        // ---- n = 2: square roots only.  One rsqrt(S) gives both sqrt(S) = S r and 1/S = r r.
+        const double rS = lh_rsqrt(S_K);
         const double sw = lh_sqrt((1.0 - S_eff) * (1.0 + S_eff));            // (1 - S^(1/m))^m
-        psi_unsat = p.neg_inv_alpha * (sw * lh_rcp(S_eff));                  // :196-200
-        double swK = sw;
-        if (icy) swK = lh_sqrt((1.0 - S_K) * (1.0 + S_K));
+        double inv_S_eff = rS * rS, swK = sw;
+        if (icy) {
+            inv_S_eff = lh_rcp(S_eff);
+            swK = lh_sqrt((1.0 - S_K) * (1.0 + S_K));
+        }
+        psi_unsat = p.neg_inv_alpha * (sw * inv_S_eff);                      // :196-200
         const double t = (S_K * S_K) * lh_rcp(1.0 + swK);                    // 1 - (1 - S^(1/m))^m
-        Kr_unsat = lh_sqrt(S_K) * (t * t);                                   // :277
+        Kr_unsat = (S_K * rS) * (t * t);                                     // :277
         if (NEED_LOG) L_K = lh_log(mc, S_K);
     } else {
         // ---- general n: pressure head (:229-242) and the shared logs
@@ -196,10 +200,10 @@ __device__ __forceinline__ double lh_temperature(const LhDevParams& p, double tl
 {
     if (ICE) {
         const double rho_c_s = p.rho_c_ds + tl * p.rhocp_l + ti * p.rhocp_i; // :65-79
-        return p.T_0 + lh_div(re + ti * p.rhoi_LH, rho_c_s);                 // :42-53
+        return p.T_0 + lh_div_fast(re + ti * p.rhoi_LH, rho_c_s);            // :42-53 (quotient << T_0: 2 ulp of it is below ulp(T))
     }
     const double rho_c_s = p.rho_c_ds + tl * p.rhocp_l;
-    return p.T_0 + lh_div(re, rho_c_s);
+    return p.T_0 + lh_div_fast(re, rho_c_s);
 }
 
 // All closures of one cell for model MODEL (0 Richards, 1 heat, 2 coupled).

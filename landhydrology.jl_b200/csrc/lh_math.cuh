@@ -69,10 +69,20 @@ LH_DEV double lh_div(double a, double b)
     return lh_fma(rem, r, q);
 }
 
+// Seed for 1/sqrt(x) with its high word clamped below 0x7fe00000 (an INTEGER min: no fp64 compare):
+// rsqrt(0) = +inf would turn x * r into NaN; clamped to ~9e307 the Newton steps below stay finite and
+// give exactly 0 for x == 0.  Negative x still yields NaN.
+LH_DEV double lh_rsqrt_seed_clamped(double x)
+{
+    const double r = lh_rsqrt_seed(x);
+    const int32_t hi = lh_hi(r);
+    return lh_mk((uint32_t)hi > 0x7fe00000u && hi > 0 ? 0x7fe00000 : hi, lh_lo(r));
+}
+
 // sqrt(x), x >= 0 finite (x == 0 -> 0).  rsqrt seed, coupled Newton on (g ~ sqrt x, h ~ 1/(2 sqrt x)).
 LH_DEV double lh_sqrt(double x)
 {
-    const double r = lh_rsqrt_seed(x);
+    const double r = lh_rsqrt_seed_clamped(x);
     double g = x * r;
     double h = 0.5 * r;
     double e = lh_fma(-h, g, 0.5);
@@ -82,9 +92,22 @@ LH_DEV double lh_sqrt(double x)
     g = lh_fma(g, e, g);
     h = lh_fma(h, e, h);
     const double d = lh_fma(-g, g, x);
-    g = lh_fma(d, h, g);
-    return x > 0.0 ? g : x;            // 0 -> 0 (seed is inf), negative/NaN -> x*... NaN below
+    return lh_fma(d, h, g);
 }
+
+// 1/sqrt(x) for normal x > 0 (~1.5 ulp): from it sqrt(x) = x r and 1/x = r r come for one multiply each.
+LH_DEV double lh_rsqrt(double x)
+{
+    double r = lh_rsqrt_seed(x);
+    const double h = 0.5 * x;
+    double e = lh_fma(-h, r * r, 0.5);
+    r = lh_fma(r, e, r);
+    e = lh_fma(-h, r * r, 0.5);          // seed 2^-20 -> 2^-39 -> 2^-77: two steps are enough
+    return lh_fma(r, e, r);
+}
+
+// a / b without the residual correction (~2 ulp): for quotients that are added to something larger.
+LH_DEV double lh_div_fast(double a, double b) { return a * lh_rcp(b); }
 
 // ---------------------------------------------------------------------------------------------------
 // exp core: x = k (ln2/16) + r, |r| <= ln2/32;  e^x = 2^(k>>4) * T[k&15] * (1 + p),  p = r + r^2 q(r),

@@ -9,6 +9,7 @@ void lhm_log(const double* x, double* y, long n) { for (long i = 0; i < n; ++i) 
 void lhm_exp(const double* x, double* y, long n) { for (long i = 0; i < n; ++i) y[i] = lh_exp(lh_c_host, lh_c_host + LHC_EXP2_TAB0, x[i]); }
 void lhm_expm1(const double* x, double* y, long n) { for (long i = 0; i < n; ++i) y[i] = lh_expm1(lh_c_host, lh_c_host + LHC_EXP2_TAB0, x[i]); }
 void lhm_sqrt(const double* x, double* y, long n) { for (long i = 0; i < n; ++i) y[i] = lh_sqrt(x[i]); }
+void lhm_rsqrt(const double* x, double* y, long n) { for (long i = 0; i < n; ++i) y[i] = lh_rsqrt(x[i]); }
 void lhm_rcp(const double* x, double* y, long n) { for (long i = 0; i < n; ++i) y[i] = lh_rcp(x[i]); }
 void lhm_div(const double* a, const double* b, double* y, long n) { for (long i = 0; i < n; ++i) y[i] = lh_div(a[i], b[i]); }
 }

@@ -90,6 +90,8 @@ def test_sqrt_rcp_div(mathlib):
     mp.mp.dps = 40
     assert _ulp_err(_call(mathlib, "lhm_sqrt", x), [mp.sqrt(mp.mpf(float(v))) for v in x]).max() <= 1.0
     assert _call(mathlib, "lhm_sqrt", np.array([0.0]))[0] == 0.0
+    assert np.isnan(_call(mathlib, "lhm_sqrt", np.array([-1.0]))[0])
+    assert _ulp_err(_call(mathlib, "lhm_rsqrt", x), [1 / mp.sqrt(mp.mpf(float(v))) for v in x]).max() <= 2.0
     assert _ulp_err(_call(mathlib, "lhm_rcp", x), [1 / mp.mpf(float(v)) for v in x]).max() <= 1.5
     a = rng.uniform(-1e8, 1e8, len(x))
     q = _call(mathlib, "lhm_div", a, x)
