@@ -145,6 +145,11 @@ def time_oracle(w, lh, graft, model, nlayer, steps, warmup, target_seconds=None)
 
     wl = make_workload(w, model, REF_SAMPLE_COLS, nlayer, (0, REF_SAMPLE_COLS))
     lib = lh.SoilLibrary(graft.build_oracle(), "lho_")
+    # all the host threads this process may use (torchrun exports OMP_NUM_THREADS=1: override it)
+    set_threads = lib.raw("lho_soil_set_num_threads")
+    set_threads.restype = None
+    set_threads.argtypes = [C.c_int32]
+    set_threads(len(os.sched_getaffinity(0)))
     nthreads = lib.raw("lho_soil_num_threads")
     nthreads.restype = C.c_int32
     cores = int(nthreads())
@@ -258,6 +263,7 @@ def main():
     ms_max = float(ms_t.item())
 
     # ---- the one collective: global water/energy budgets ----
+    budgets = ctx.budgets_allreduce() if world > 1 else ctx.budgets()     # first call: NCCL lazy set-up
     tb0 = time.perf_counter()
     budgets = ctx.budgets_allreduce() if world > 1 else ctx.budgets()
     budget_ms = 1e3 * (time.perf_counter() - tb0)
