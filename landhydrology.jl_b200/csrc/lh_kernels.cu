@@ -42,7 +42,7 @@ LhLaunchShape lh_choose_shape(int model, int64_t ncol_pad, int32_t nlayer, int s
     Lc = (nlayer + W - 1) / W;
     W = (nlayer + Lc - 1) / Lc;          // no empty chunks
     int G = 1;
-    const int want = max_warps < 8 ? max_warps : 8;        // ~8 warps per block when possible
+    const int want = max_warps < 4 ? max_warps : 4;        // 4-warp blocks: same occupancy as 8, less barrier wait
     while (W * G * 2 <= want && (int64_t)G * 2 <= groups) G *= 2;
     s.Lc = Lc; s.W = W; s.G = G;
     s.nblocks = (groups + G - 1) / G;

@@ -342,7 +342,10 @@ int32_t download_field(lh_soil_ctx* c, const double* soa, double* host, int64_t 
 void update_kernel_flags(lh_soil_ctx* c)
 {
     const lh_soil_params& q = c->cfg.params;
-    const bool gen = c->dp.visc_on || c->dp.imp_on || !c->dp.om_zero || q.theta_r != 0.0;
+    // theta_r != 0 only matters where the Kersten number reuses log S (coupled model); Richards has no
+    // Kersten number and the heat-only model no water closures.
+    const bool gen = c->dp.visc_on || c->dp.imp_on || !c->dp.om_zero ||
+                     (c->model == LH_MODEL_COUPLED && q.theta_r != 0.0);
     const bool vg2 = q.vg_n == 2.0 && q.vg_m == 0.5;      // S^(1/m) = S^2, x^m = sqrt(x): no log/exp needed
     c->kernel_flags = (c->has_ice ? LH_FLAG_ICE : 0) | (gen ? LH_FLAG_GEN : 0) | (vg2 && !c->force_general_vg ? LH_FLAG_VG2 : 0);
 }
