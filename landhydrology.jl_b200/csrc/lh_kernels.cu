@@ -36,7 +36,7 @@ LhLaunchShape lh_choose_shape(int model, int64_t ncol_pad, int32_t nlayer, int s
     int Lc = 16;
     const int64_t want_warps = (int64_t)sm_count * 8;
     while (Lc > 2 && groups * ((nlayer + Lc - 1) / Lc) < want_warps) Lc >>= 1;
-    const int max_warps = LH_MAX_THREADS / 32;             // register budget: 64K / (warps * 32 * regs)
+    const int max_warps = lh_max_threads(model) / 32;      // register budget: 64K / (warps * 32 * regs)
     int W = (nlayer + Lc - 1) / Lc;
     if (W > max_warps) W = max_warps;
     Lc = (nlayer + W - 1) / W;
@@ -55,7 +55,7 @@ cudaError_t lh_launch_stage(int model, int stage, int flags, const LhKernelArgs&
                             cudaStream_t stream)
 {
     if (model < 0 || model > 2) return cudaErrorInvalidValue;
-    if (shape.W * shape.G * 32 > LH_MAX_THREADS || shape.smem_bytes > 200 * 1024) return cudaErrorInvalidConfiguration;
+    if (shape.W * shape.G * 32 > lh_max_threads(model) || shape.smem_bytes > 200 * 1024) return cudaErrorInvalidConfiguration;
     switch (model) {
     case 0: return lh_launch_stage_m0(stage, flags, args, shape, stream);
     case 1: return lh_launch_stage_m1(stage, flags, args, shape, stream);

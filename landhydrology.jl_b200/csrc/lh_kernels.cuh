@@ -6,14 +6,25 @@
 
 #include "lh_closures.cuh"
 
-// Register budget of the stage kernels: threads per block <= LH_MAX_THREADS, blocks per SM >=
-// LH_MIN_BLOCKS (tuning knobs; tools/build_variant.sh builds alternatives).
+// Register budget of the stage kernels, per model (measured, profiles/r01_g_*): the coupled and heat
+// closures keep ~120 registers busy and lose from spilling, so they run at 128 registers (<= 512
+// threads per block, 16 warps/SM); the Richards closures are one long dependent chain with few
+// temporaries and gain 20 % from 24 warps/SM at <= 85 registers (<= 256 threads per block, 3 blocks).
 #ifndef LH_MIN_BLOCKS
 #define LH_MIN_BLOCKS 1
 #endif
 #ifndef LH_MAX_THREADS
 #define LH_MAX_THREADS 512
 #endif
+#ifndef LH_MIN_BLOCKS_RICHARDS
+#define LH_MIN_BLOCKS_RICHARDS 3
+#endif
+#ifndef LH_MAX_THREADS_RICHARDS
+#define LH_MAX_THREADS_RICHARDS 256
+#endif
+template <int MODEL> struct LhBounds { static constexpr int max_threads = LH_MAX_THREADS, min_blocks = LH_MIN_BLOCKS; };
+template <> struct LhBounds<0> { static constexpr int max_threads = LH_MAX_THREADS_RICHARDS, min_blocks = LH_MIN_BLOCKS_RICHARDS; };
+inline int lh_max_threads(int model) { return model == 0 ? LhBounds<0>::max_threads : LhBounds<1>::max_threads; }
 
 // Device layout of every cell field: column-fastest SoA, element (layer, col) at
 // [layer * ncol_pad + col]; ncol_pad is a multiple of 32 so that a warp (32 adjacent columns)

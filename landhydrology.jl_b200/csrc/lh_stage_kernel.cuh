@@ -126,7 +126,7 @@ constexpr int RING_DEPTH = 4, RING_FIELDS = 5, RING_DOUBLES = RING_DEPTH * RING_
 template <int MODEL> struct Slot { static constexpr int NQv = NQ<MODEL>::value; static constexpr int doubles = (2 * (NQv + 1) + 4) * 32; };
 
 template <int MODEL, int STAGE, int FLAGS>
-__global__ void __launch_bounds__(LH_MAX_THREADS, LH_MIN_BLOCKS)
+__global__ void __launch_bounds__(LhBounds<MODEL>::max_threads, LhBounds<MODEL>::min_blocks)
 lh_soil_stage_kernel(const __grid_constant__ LhKernelArgs A)
 {
     extern __shared__ double smem[];
