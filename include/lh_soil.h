@@ -225,6 +225,22 @@ int32_t lh_soil_diagnostic(lh_soil_ctx* ctx, int32_t which, double* host,
 
 int32_t lh_soil_sync(lh_soil_ctx* ctx);
 
+/* Evaluates one of the device elementary functions of csrc/lh_math.cuh on n host values
+ * (y[i] = f(x[i]) computed ON THE GPU): the accuracy of the hand-written log2/exp2/exp2m1/sqrt/
+ * rsqrt/rcp/div that replace the reference's `^`, `exp`, `sqrt`, `/` is thereby testable against
+ * a high-precision host reference.  For LH_MATH_DIV, x holds n numerators followed by n
+ * denominators.                                                                              */
+#define LH_MATH_LOG2   0   /* log2(x)  */
+#define LH_MATH_EXP2   1   /* 2^x      */
+#define LH_MATH_EXP2M1 2   /* 2^x - 1  */
+#define LH_MATH_SQRT  3
+#define LH_MATH_RSQRT 4
+#define LH_MATH_RCP   5
+#define LH_MATH_DIV   6
+#define LH_MATH_RCP_SEED   7   /* the raw MUFU.RCP64H seed (rcp.approx.ftz.f64)     */
+#define LH_MATH_RSQRT_SEED 8   /* the raw MUFU.RSQ64H seed (rsqrt.approx.ftz.f64)   */
+int32_t lh_soil_eval_math(lh_soil_ctx* ctx, int32_t fn, const double* x, double* y, int64_t n);
+
 /* Device time (ms) spent in the kernels of the last lh_soil_step_ssprk33 call, measured with
  * CUDA events on the ctx stream, and the number of kernels it launched.                     */
 int32_t lh_soil_last_step_timing(lh_soil_ctx* ctx, double* ms_out, int64_t* launches_out);

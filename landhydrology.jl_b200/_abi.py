@@ -123,6 +123,7 @@ _SIGNATURES = {
     "soil_budgets": ([_vp, _dp], C.c_int32),
     "soil_diagnostic": ([_vp, C.c_int32, _dp, C.c_int64, C.c_int64], C.c_int32),
     "soil_sync": ([_vp], C.c_int32),
+    "soil_eval_math": ([_vp, C.c_int32, _dp, _dp, C.c_int64], C.c_int32),
     "soil_last_step_timing": ([_vp, _dp, C.POINTER(C.c_int64)], C.c_int32),
     "soil_device_ptr": ([_vp, C.c_int32, C.POINTER(_vp), C.POINTER(C.c_int64)], C.c_int32),
     "soil_comm_unique_id": ([C.POINTER(C.c_uint8)], C.c_int32),
@@ -323,6 +324,14 @@ class SoilContext:
 
     def sync(self):
         self._check(self.lib.soil_sync(self._h))
+
+    def eval_math(self, fn: int, x: np.ndarray) -> np.ndarray:
+        """y = f(x) with the library's own elementary functions (LH_MATH_*); DIV: x = [num..., den...]."""
+        x = np.ascontiguousarray(x, dtype=np.float64)
+        n = x.size // 2 if fn == 6 else x.size
+        y = np.empty(n, dtype=np.float64)
+        self._check(self.lib.soil_eval_math(self._h, int(fn), _as_double_ptr(x), _as_double_ptr(y), n))
+        return y
 
     def last_step_timing(self):
         ms = C.c_double()

@@ -6,13 +6,13 @@
 // algebra is re-associated so that the van Genuchten retention curve and conductivity share
 // ONE log(S) and ONE log(1 - S^(1/m)):
 //
-//     u = log(S)/m            y = S^(1/m) = e^u          w = 1 - y = -expm1(u)
-//     a = log(w)
-//     psi = -((S^(-1/m) - 1) alpha^(-n))^(1/n) = -(1/alpha) exp((a - u)/n)
-//     K   = Ksat sqrt(S) (1 - (1 - y)^m)^2     = Ksat sqrt(S) expm1(m a)^2
+//     u = log2(S)/m           y = S^(1/m) = 2^u          w = 1 - y = -exp2m1(u)
+//     a = log2(w)
+//     psi = -((S^(-1/m) - 1) alpha^(-n))^(1/n) = -(1/alpha) exp2((a - u)/n)
+//     K   = Ksat sqrt(S) (1 - (1 - y)^m)^2     = Ksat sqrt(S) exp2m1(m a)^2
 //
 // which is also better conditioned than the literal form (1 - y and 1 - (1-y)^m are formed by
-// expm1, not by subtraction).  Results agree with the literal fp64 evaluation to a few ulp;
+// exp2m1, not by subtraction).  Results agree with the literal fp64 evaluation to a few ulp;
 // the parity gate is 1e-12 (cancellation-aware norm) per tendency evaluation.
 //
 // The fp64 pipe (64 DFMA/clk/SM on B200), not HBM, is the binding unit for this path, so the
@@ -32,6 +32,7 @@
 struct LhDevParams {
     // geometry
     double dz, inv_dz, half_dz, inv_half_dz;
+    double neg_half_inv_dz;            // -1 / (2 dz): interior face fluxes
     // water
     double nu, theta_r, theta_r_eps;   // theta_r + eps(Float64)
     double inv_nu_thr;                 // 1 / (nu - theta_r)
@@ -39,18 +40,18 @@ struct LhDevParams {
     double vg_m, vg_inv_m, vg_inv_n;
     double neg_inv_alpha;              // -1 / alpha
     double Ksat;
-    double visc_gamma, visc_T_ref;
-    double imp_c;                      // -Omega * ln(10)
+    double visc_gamma_l2e, visc_T_ref; // gamma * log2(e)
+    double imp_c2;                     // -Omega * log2(10)
     // heat
     double rho_c_ds, rhocp_l, rhocp_i, rhoi_LH, T_0;
     double inv_nu;
     double kersten_p1;                 // (1 + nu_om - a nu_quartz - nu_gravel) / 2
     double kersten_p2;                 // 1 - nu_om
     double kersten_p3;                 // 1 + nu_om
-    double neg_b;
-    double k_unfrozen, k_frozen, ln_k_unfrozen, ln_k_frozen;
+    double neg_b_l2e;                  // -b * log2(e)
+    double k_unfrozen, k_frozen, log2_k_unfrozen, log2_k_frozen;
     double kappa_dry;
-    double log_Sr_sat;                 // log(nu * (1/nu)): log of the relative saturation of a saturated, ice-free cell
+    double log2_Sr_sat;                // log2(nu * (1/nu)): relative saturation of a saturated, ice-free cell
     int32_t visc_on, imp_on;
     int32_t om_zero;                   // nu_ss_om == 0: outer Kersten exponents are exactly 1
     int32_t pad_;
@@ -124,33 +125,33 @@ __device__ __forceinline__ void lh_water_closures(const LhDevParams& p, const do
         psi_unsat = p.neg_inv_alpha * (sw * inv_S_eff);                      // :196-200
         const double t = (S_K * S_K) * lh_rcp(1.0 + swK);                    // 1 - (1 - S^(1/m))^m
         Kr_unsat = (S_K * rS) * (t * t);                                     // :277
-        if (NEED_LOG) L_K = lh_log(mc, S_K);
+        if (NEED_LOG) L_K = lh_log2(mc, S_K);
     } else {
         // ---- general n: pressure head (:229-242) and the shared logs
-        const double L_eff = lh_log(mc, S_eff);
+        const double L_eff = lh_log2(mc, S_eff);
         const double u = L_eff * p.vg_inv_m;
-        const double w = -lh_expm1(mc, tab, u);                              // 1 - S^(1/m)
-        const double a = lh_log(mc, w);
-        psi_unsat = p.neg_inv_alpha * lh_exp(mc, tab, (a - u) * p.vg_inv_n);
+        const double w = -lh_exp2m1(mc, tab, u);                             // 1 - S^(1/m)
+        const double a = lh_log2(mc, w);
+        psi_unsat = p.neg_inv_alpha * lh_exp2(mc, tab, (a - u) * p.vg_inv_n);
         // ---- hydraulic conductivity (:269-282)
         double a_K = a;
         L_K = L_eff;
         if (icy) {                       // S differs from S_eff only when ice is present
-            L_K = lh_log(mc, S_K);
-            a_K = lh_log(mc, -lh_expm1(mc, tab, L_K * p.vg_inv_m));
+            L_K = lh_log2(mc, S_K);
+            a_K = lh_log2(mc, -lh_exp2m1(mc, tab, L_K * p.vg_inv_m));
         }
-        const double q = lh_expm1(mc, tab, p.vg_m * a_K);                    // (1 - y)^m - 1
+        const double q = lh_exp2m1(mc, tab, p.vg_m * a_K);                   // (1 - y)^m - 1
         Kr_unsat = lh_sqrt(S_K) * (q * q);
     }
     const double psi = (S_eff <= 1.0) ? psi_unsat : psi_sat;
     const double Kr = (S_K < 1.0) ? Kr_unsat : 1.0;
     double K = Kr * p.Ksat;
     if (GEN) {
-        if (p.visc_on) K *= lh_exp(mc, tab, p.visc_gamma * (T - p.visc_T_ref));   // :117-126
+        if (p.visc_on) K *= lh_exp2(mc, tab, p.visc_gamma_l2e * (T - p.visc_T_ref));   // :117-126
         if (p.imp_on) {                                                      // :89-93, f_i :159/:308
             const double tl = (th < nu_eff) ? th : nu_eff;
             const double f_i = lh_div(ti, tl + ti);
-            K *= lh_exp(mc, tab, p.imp_c * f_i);
+            K *= lh_exp2(mc, tab, p.imp_c2 * f_i);                              // 10^(-Omega f_i)
         }
     }
     K_out = K;
@@ -161,7 +162,7 @@ __device__ __forceinline__ void lh_water_closures(const LhDevParams& p, const do
 // ---------------------------------------------------------------------------------------------
 // Heat: thermal conductivity from (θ_l, θ_i).  Reference: right_hand_side.jl:296-305,
 // SoilHeatParameterizations.jl:114-188.
-//   REUSE: the caller has log S of the SAME cell (coupled model, fast path): with θr = 0 and no ice,
+//   REUSE: the caller has log2 S of the SAME cell (coupled model, fast path): with θr = 0 and no ice,
 //   S_r = θ_l/ν equals S = ϑ_l/ν bit for bit while ϑ_l < ν, and is the constant ν(1/ν) once the cell
 //   is saturated, so no second log is needed.  (For ϑ_l <= eps the two differ, but there the
 //   Kersten base E3 - c^3 is ~0 and K_e vanishes either way.)
@@ -174,22 +175,22 @@ __device__ __forceinline__ double lh_thermal_conductivity(const LhDevParams& p, 
     const double tw = ICE ? tl + ti : tl;
     const double S_r = tw * p.inv_nu;                                        // relative_saturation :139-142
     double Lr;
-    if (REUSE && !ICE && !GEN) Lr = unsat ? logS : p.log_Sr_sat;
-    else Lr = lh_log(mc, S_r);
+    if (REUSE && !ICE && !GEN) Lr = unsat ? logS : p.log2_Sr_sat;
+    else Lr = lh_log2(mc, S_r);
     double K_e;
     if (!ICE || ti < LH_EPS) {                                               // kersten_number :163-169
-        const double e = lh_exp(mc, tab, p.neg_b * S_r);
+        const double e = lh_exp2(mc, tab, p.neg_b_l2e * S_r);                // exp(-b S_r)
         const double g = 1.0 + e;
         const double E3 = lh_rcp(g * g * g);
         const double c = (1.0 - S_r) * 0.5;
         double base = E3 - c * c * c;
-        if (GEN && !p.om_zero) base = lh_exp(mc, tab, p.kersten_p2 * lh_log(mc, base));
-        K_e = lh_exp(mc, tab, p.kersten_p1 * Lr) * base;
+        if (GEN && !p.om_zero) base = lh_exp2(mc, tab, p.kersten_p2 * lh_log2(mc, base));
+        K_e = lh_exp2(mc, tab, p.kersten_p1 * Lr) * base;
     } else {                                                                 // :171
-        K_e = (!GEN || p.om_zero) ? S_r : lh_exp(mc, tab, p.kersten_p3 * Lr);
+        K_e = (!GEN || p.om_zero) ? S_r : lh_exp2(mc, tab, p.kersten_p3 * Lr);
     }
     double k_sat = p.k_unfrozen;                                             // :114-128; x^1 * y^0 is exact
-    if (ICE && ti != 0.0) k_sat = lh_exp(mc, tab, lh_div(tl * p.ln_k_unfrozen + ti * p.ln_k_frozen, tw));
+    if (ICE && ti != 0.0) k_sat = lh_exp2(mc, tab, lh_div(tl * p.log2_k_unfrozen + ti * p.log2_k_frozen, tw));
     k_sat = (tw < LH_EPS) ? 0.0 : k_sat;
     return K_e * k_sat + (1.0 - K_e) * p.kappa_dry;                          // thermal_conductivity :185-188
 }

@@ -283,6 +283,38 @@ cudaError_t lh_launch_fill_padding(double* soa, int64_t ncol, int64_t ncol_pad, 
     return cudaGetLastError();
 }
 
+namespace {
+__global__ void lh_eval_math_kernel(const __grid_constant__ LhDevParams p, int fn, const double* __restrict__ x,
+                                    double* __restrict__ y, int64_t n)
+{
+    __shared__ double tab[16];
+    lh_stage_exp_table(p, tab, threadIdx.x);
+    __syncthreads();
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const double v = x[i];
+    double r;
+    switch (fn) {
+    case LH_MATH_LOG2: r = lh_log2(p.mc, v); break;
+    case LH_MATH_EXP2: r = lh_exp2(p.mc, tab, v); break;
+    case LH_MATH_EXP2M1: r = lh_exp2m1(p.mc, tab, v); break;
+    case LH_MATH_SQRT: r = lh_sqrt(v); break;
+    case LH_MATH_RSQRT: r = lh_rsqrt(v); break;
+    case LH_MATH_RCP: r = lh_rcp(v); break;
+    case LH_MATH_RCP_SEED: r = lh_rcp_seed(v); break;
+    case LH_MATH_RSQRT_SEED: r = lh_rsqrt_seed(v); break;
+    default: r = lh_div(v, x[n + i]); break;
+    }
+    y[i] = r;
+}
+}  // namespace
+
+cudaError_t lh_launch_eval_math(const LhDevParams& p, int fn, const double* x, double* y, int64_t n, cudaStream_t stream)
+{
+    lh_eval_math_kernel<<<(unsigned)((n + 255) / 256), 256, 0, stream>>>(p, fn, x, y, n);
+    return cudaGetLastError();
+}
+
 cudaError_t lh_launch_any_nonzero(const double* x, int64_t n, int* flag, cudaStream_t stream)
 {
     lh_any_nonzero_kernel<<<592, 256, 0, stream>>>(x, n, flag);

@@ -85,6 +85,8 @@ cudaError_t lh_launch_fill_profile(const double* profile, double* soa, int32_t n
                                    cudaStream_t stream);
 cudaError_t lh_launch_fill_padding(double* soa, int64_t ncol, int64_t ncol_pad, int32_t nlayer,
                                    cudaStream_t stream);
+// y[i] = f(x[i]) for the elementary function `fn` (LH_MATH_*), all device pointers.
+cudaError_t lh_launch_eval_math(const LhDevParams& p, int fn, const double* x, double* y, int64_t n, cudaStream_t stream);
 // Counts non-finite values of a field into *count (uint64).
 cudaError_t lh_launch_count_nonfinite(const double* soa, int64_t n, unsigned long long* count,
                                       cudaStream_t stream);

@@ -31,9 +31,10 @@ LH_DEV double lh_fma(double a, double b, double c) { return fma(a, b, c); }
 LH_DEV int32_t lh_hi(double x) { int64_t b; memcpy(&b, &x, 8); return (int32_t)(b >> 32); }
 LH_DEV int32_t lh_lo(double x) { int64_t b; memcpy(&b, &x, 8); return (int32_t)(b & 0xffffffff); }
 LH_DEV double lh_mk(int32_t hi, int32_t lo) { int64_t b = ((int64_t)hi << 32) | (uint32_t)lo; double x; memcpy(&x, &b, 8); return x; }
-// MUFU.RCP64H / RSQ64H emulation: ~20 good bits, low word zero
-LH_DEV double lh_rcp_seed(double x) { double r = 1.0 / x; return lh_mk(lh_hi(r) & ~0x7, 0); }
-LH_DEV double lh_rsqrt_seed(double x) { double r = 1.0 / sqrt(x); return lh_mk(lh_hi(r) & ~0x7, 0); }
+// MUFU.RCP64H / RSQ64H emulation: the high word only (20 mantissa bits, truncated), low word zero —
+// the measured accuracy of the hardware seeds (2^-19.95 / 2^-20.06, tools/seed_accuracy.py).
+LH_DEV double lh_rcp_seed(double x) { double r = 1.0 / x; return lh_mk(lh_hi(r), 0); }
+LH_DEV double lh_rsqrt_seed(double x) { double r = 1.0 / sqrt(x); return lh_mk(lh_hi(r), 0); }
 #define LH_INF (INFINITY)
 #define LH_NAN (NAN)
 #else
@@ -49,125 +50,115 @@ LH_DEV double lh_rsqrt_seed(double x) { double r; asm("rsqrt.approx.ftz.f64 %0, 
 #define LH_NAN (__longlong_as_double(0x7ff8000000000000LL))
 #endif
 
-// 1/x for normal, finite, non-zero x: seed (2^-20) + 2 Newton steps -> ~1 ulp.  6 fp64-pipe ops.
+// The MUFU seeds are accurate to 2^-20 (measured on B200: tools/seed_accuracy.py gives 2^-19.95 for
+// rcp.approx.ftz.f64 and 2^-20.06 for rsqrt.approx.ftz.f64), so ONE third-order step reaches fp64:
+// the truncation error is e^3 ~ 2^-60, well below 2^-53.  That is 3 (rcp) / 5 (rsqrt) dependent fp64
+// operations instead of the 4 / 6+ of two Newton steps.
+
+// 1/x for normal, finite, non-zero x:  r0 (1 + e + e^2),  e = 1 - x r0.   ~1 ulp.
 LH_DEV double lh_rcp(double x)
 {
-    double r = lh_rcp_seed(x);
-    double e = lh_fma(-x, r, 1.0);
-    r = lh_fma(r, e, r);
-    e = lh_fma(-x, r, 1.0);
-    r = lh_fma(r, e, r);
-    return r;
+    const double r0 = lh_rcp_seed(x);
+    const double e = lh_fma(-x, r0, 1.0);
+    return lh_fma(r0, lh_fma(e, e, e), r0);
 }
 
 // a/b for normal finite b != 0, |a/b| in range: reciprocal + one residual correction (<= 1 ulp).
 LH_DEV double lh_div(double a, double b)
 {
     const double r = lh_rcp(b);
-    double q = a * r;
-    const double rem = lh_fma(-q, b, a);
-    return lh_fma(rem, r, q);
-}
-
-// Seed for 1/sqrt(x) with its high word clamped below 0x7fe00000 (an INTEGER min: no fp64 compare):
-// rsqrt(0) = +inf would turn x * r into NaN; clamped to ~9e307 the Newton steps below stay finite and
-// give exactly 0 for x == 0.  Negative x still yields NaN.
-LH_DEV double lh_rsqrt_seed_clamped(double x)
-{
-    const double r = lh_rsqrt_seed(x);
-    const int32_t hi = lh_hi(r);
-    return lh_mk((uint32_t)hi > 0x7fe00000u && hi > 0 ? 0x7fe00000 : hi, lh_lo(r));
-}
-
-// sqrt(x), x >= 0 finite (x == 0 -> 0).  rsqrt seed, coupled Newton on (g ~ sqrt x, h ~ 1/(2 sqrt x)).
-LH_DEV double lh_sqrt(double x)
-{
-    const double r = lh_rsqrt_seed_clamped(x);
-    double g = x * r;
-    double h = 0.5 * r;
-    double e = lh_fma(-h, g, 0.5);
-    g = lh_fma(g, e, g);
-    h = lh_fma(h, e, h);
-    e = lh_fma(-h, g, 0.5);
-    g = lh_fma(g, e, g);
-    h = lh_fma(h, e, h);
-    const double d = lh_fma(-g, g, x);
-    return lh_fma(d, h, g);
-}
-
-// 1/sqrt(x) for normal x > 0 (~1.5 ulp): from it sqrt(x) = x r and 1/x = r r come for one multiply each.
-LH_DEV double lh_rsqrt(double x)
-{
-    double r = lh_rsqrt_seed(x);
-    const double h = 0.5 * x;
-    double e = lh_fma(-h, r * r, 0.5);
-    r = lh_fma(r, e, r);
-    e = lh_fma(-h, r * r, 0.5);          // seed 2^-20 -> 2^-39 -> 2^-77: two steps are enough
-    return lh_fma(r, e, r);
+    const double q = a * r;
+    return lh_fma(lh_fma(-q, b, a), r, q);
 }
 
 // a / b without the residual correction (~2 ulp): for quotients that are added to something larger.
 LH_DEV double lh_div_fast(double a, double b) { return a * lh_rcp(b); }
 
+// 1/sqrt(x) from a seed r0:  r0 (1 + e/2 + 3 e^2/8),  e = 1 - x r0^2.
+LH_DEV double lh_rsqrt_refine(double x, double r0)
+{
+    const double e = lh_fma(-(x * r0), r0, 1.0);
+    const double p = lh_fma(0.375, e, 0.5) * e;
+    return lh_fma(r0, p, r0);
+}
+
+// 1/sqrt(x) for normal x > 0 (~1.5 ulp): sqrt(x) = x r and 1/x = r r then cost one multiply each.
+LH_DEV double lh_rsqrt(double x) { return lh_rsqrt_refine(x, lh_rsqrt_seed(x)); }
+
+// sqrt(x), x >= 0 finite.  The seed's high word is clamped below 0x7fe00000 with an INTEGER min (an fp64
+// compare would occupy the fp64 pipe): rsqrt(0) = +inf would turn x r into NaN; clamped to ~9e307
+// every step below stays finite and gives exactly 0 for x == 0.  Negative x yields NaN.
+LH_DEV double lh_sqrt(double x)
+{
+    const double s0 = lh_rsqrt_seed(x);
+    const int32_t hi = lh_hi(s0);
+    const double r0 = lh_mk(((uint32_t)hi > 0x7fe00000u && hi > 0) ? 0x7fe00000 : hi, lh_lo(s0));
+    const double r = lh_rsqrt_refine(x, r0);
+    const double g = x * r;
+    return lh_fma(lh_fma(-g, g, x), 0.5 * r, g);       // one correction of g = x r: <= 1 ulp
+}
+
 // ---------------------------------------------------------------------------------------------------
-// exp core: x = k (ln2/16) + r, |r| <= ln2/32;  e^x = 2^(k>>4) * T[k&15] * (1 + p),  p = r + r^2 q(r),
-// T[j] = 2^(j/16).  `tab` points at the 16-entry table: the kernels stage it in SHARED memory, where a
-// 16 x 8-byte table spans the 32 banks exactly once, so any pattern of per-lane indices is
-// conflict-free (one LDS.64).  Returns the scale s = 2^(k>>4) T[j] and p.
+// Every transcendental on the soil path is a power x^c, so base 2 serves everywhere and saves the ln 2
+// scalings of a natural log/exp pair.
+//
+// exp2 core: x = k/16 + r, |r| <= 1/32 (the reduction r = x - k/16 is EXACT);
+//   2^x = 2^(k>>4) * T[k&15] * (1 + p),  p = r g(r) (degree-5 g),  T[j] = 2^(j/16).
+// `tab` points at the 16-entry table: the kernels stage it in SHARED memory, where a 16 x 8-byte table
+// spans the 32 banks exactly once, so any pattern of per-lane indices is conflict-free (one LDS.64).
 // ---------------------------------------------------------------------------------------------------
 struct LhExpParts { double s, p; };
 
-LH_DEV LhExpParts lh_exp_parts(const double* __restrict__ lh_c, const double* __restrict__ tab, double x)
+LH_DEV LhExpParts lh_exp2_parts(const double* __restrict__ lh_c, const double* __restrict__ tab, double x)
 {
-    // Lower clamp in the INTEGER domain (an fp64 compare+select costs a DSETP on the fp64 pipe
-    // plus two FSELs): for negative x the unsigned high word grows with |x|, so
-    // hi > 0xC0862000 <=> x < -708 (or x is a negative-signed NaN, which then reads as -708).
-    // Positive NaN propagates through the arithmetic; x > 709 is outside the contract (the
-    // closures never produce it from a finite state).
+    // Lower clamp in the INTEGER domain (an fp64 compare+select costs a DSETP on the fp64 pipe plus
+    // two FSELs): for negative x the unsigned high word grows with |x|, so hi > 0xC08FF000 <=> x < -1022
+    // (or x is a negative-signed NaN, which then reads as -1022).  Positive NaN propagates through the
+    // arithmetic; x >= 1024 is outside the contract (the closures never produce it from a finite state).
     int32_t xhi = lh_hi(x);
-    xhi = ((uint32_t)xhi > 0xC0862000u) ? (int32_t)0xC0862000 : xhi;
+    xhi = ((uint32_t)xhi > 0xC08FF000u) ? (int32_t)0xC08FF000 : xhi;
     const double xc = lh_mk(xhi, lh_lo(x));
-    const double MAGIC = 6755399441055744.0;                 // 1.5 * 2^52: low word of t is k
-    const double t = lh_fma(xc, lh_c[LHC_L2E16], MAGIC);
+    const double MAGIC = 6755399441055744.0;                 // 1.5 * 2^52: low word of t is k = rint(16 x)
+    const double t = lh_fma(xc, 16.0, MAGIC);
     const int32_t k = lh_lo(t);
-    const double kf = t - MAGIC;
-    double r = lh_fma(kf, -lh_c[LHC_LN2_16_HI], xc);
-    r = lh_fma(kf, -lh_c[LHC_LN2_16_LO], r);
+    const double r = lh_fma(t - MAGIC, -0.0625, xc);         // exact
     const double T = tab[k & 15];
-    double q = lh_c[LHC_EXP_Q5];
-    q = lh_fma(q, r, lh_c[LHC_EXP_Q4]);
-    q = lh_fma(q, r, lh_c[LHC_EXP_Q3]);
-    q = lh_fma(q, r, lh_c[LHC_EXP_Q2]);
-    q = lh_fma(q, r, lh_c[LHC_EXP_Q1]);
-    q = lh_fma(q, r, lh_c[LHC_EXP_Q0]);
+    double g = lh_c[LHC_EXP2_G5];
+    g = lh_fma(g, r, lh_c[LHC_EXP2_G4]);
+    g = lh_fma(g, r, lh_c[LHC_EXP2_G3]);
+    g = lh_fma(g, r, lh_c[LHC_EXP2_G2]);
+    g = lh_fma(g, r, lh_c[LHC_EXP2_G1]);
+    g = lh_fma(g, r, lh_c[LHC_EXP2_G0]);
     LhExpParts o;
-    o.p = lh_fma(r * r, q, r);
+    o.p = r * g;
     o.s = lh_mk(lh_hi(T) + ((k >> 4) << 20), lh_lo(T));     // T * 2^(k>>4): exponent-field add
     return o;
 }
 
-// e^x for x <= 709.  x < -708 (incl. -inf) returns e^-708 ~ 3e-308 (not exactly 0: nothing downstream
+// 2^x for x < 1024.  x < -1022 (incl. -inf) returns 2^-1022 (not exactly 0: nothing downstream
 // distinguishes them), NaN -> NaN.
-LH_DEV double lh_exp(const double* __restrict__ lh_c, const double* __restrict__ tab, double x)
+LH_DEV double lh_exp2(const double* __restrict__ lh_c, const double* __restrict__ tab, double x)
 {
-    const LhExpParts e = lh_exp_parts(lh_c, tab, x);
+    const LhExpParts e = lh_exp2_parts(lh_c, tab, x);
     return lh_fma(e.s, e.p, e.s);
 }
 
-// e^x - 1.  |x| <= ln2/32: k == 0, s == 1 and the result is p itself (full accuracy where 1 - e^x
-// cancels).  Otherwise s - 1 carries the rounding of T[j]: relative error <= 2^-53 / |e^x - 1| < 6e-15.
-LH_DEV double lh_expm1(const double* __restrict__ lh_c, const double* __restrict__ tab, double x)
+// 2^x - 1.  |x| <= 1/32: k == 0, s == 1 and the result is p itself (<= 8 ulp = 1.8e-15 relative where
+// 1 - 2^x cancels; the literal fp64 form 1 - x^c the reference uses is off by 1.1e-16 / |1 - 2^x| there).
+// Otherwise s - 1 carries the rounding of T[j]: relative error <= 2^-53 / |2^x - 1| < 6e-15.
+LH_DEV double lh_exp2m1(const double* __restrict__ lh_c, const double* __restrict__ tab, double x)
 {
-    const LhExpParts e = lh_exp_parts(lh_c, tab, x);
+    const LhExpParts e = lh_exp2_parts(lh_c, tab, x);
     return lh_fma(e.s, e.p, e.s - 1.0);
 }
 
 // ---------------------------------------------------------------------------------------------------
-// log(x): x = 2^e m, m in [sqrt(1/2), sqrt(2));  s = (m-1)/(m+1);  log m = 2 s + s z P(z), z = s^2.
-// x < 0, NaN (and +inf) -> NaN.  x == 0 and subnormals read as 2^-1023 m: log(0) = -709.09 instead of
-// -inf, which is what the closures need (exp of it underflows; nothing tests for -inf).
+// log2(x): x = 2^e m, m in [sqrt(1/2), sqrt(2));  s = (m-1)/(m+1);  ln m = 2 s + s z P(z), z = s^2;
+// log2 x = e + ln(m) log2(e).
+// x < 0, NaN (and +inf) -> NaN.  x == 0 and subnormals read as 2^-1023 m: log2(0) = -1023 instead of
+// -inf, which is what the closures need (exp2 of it underflows; nothing tests for -inf).
 // ---------------------------------------------------------------------------------------------------
-LH_DEV double lh_log(const double* __restrict__ lh_c, double x)
+LH_DEV double lh_log2(const double* __restrict__ lh_c, double x)
 {
     int32_t hi = lh_hi(x) & 0x7fffffff;      // log|x|; the sign only matters for the NaN flag below
     const int32_t lo = lh_lo(x);
@@ -191,13 +182,11 @@ LH_DEV double lh_log(const double* __restrict__ lh_c, double x)
     P = lh_fma(P, z, lh_c[LHC_LOG_P2]);
     P = lh_fma(P, z, lh_c[LHC_LOG_P1]);
     P = lh_fma(P, z, lh_c[LHC_LOG_P0]);
-    const double ef = (double)e;
-    // e ln2_hi is exact (ln2_hi has 38 bits, |e| < 2^11); sum small terms first
-    const double tail = lh_fma(s * z, P, ef * lh_c[LHC_LN2_LO]);
-    const double y = lh_fma(ef, lh_c[LHC_LN2_HI], 2.0 * s) + tail;
+    const double lnm = lh_fma(s * z, P, s + s);
+    const double y = lh_fma(lnm, lh_c[LHC_L2E], (double)e);
     // x < 0, NaN, +inf: force NaN with integer compares on the high word (cheaper than an fp64
     // compare, which occupies the fp64 pipe).  -0.0 (high word exactly 0x80000000: the closures
-    // produce it as -(expm1(0))) is NOT flagged: like +0 it yields a huge negative finite value.
+    // produce it as -(exp2m1(0))) is NOT flagged: like +0 it yields a huge negative finite value.
     const uint32_t xh = (uint32_t)lh_hi(x);
     const bool bad = (xh > 0x80000000u) || (xh - 0x7ff00000u < 0x00100000u);
     const int32_t yhi = bad ? 0x7ff80000 : lh_hi(y);

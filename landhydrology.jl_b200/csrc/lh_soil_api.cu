@@ -151,6 +151,7 @@ LhDevParams derive_params(const lh_soil_config& cfg)
     d.inv_dz = 1.0 / d.dz;
     d.half_dz = d.dz / 2.0;            // boundary_cf_distance, boundary_conditions.jl:196-208 (A1)
     d.inv_half_dz = 1.0 / d.half_dz;
+    d.neg_half_inv_dz = -0.5 / d.dz;
     d.nu = q.nu;
     d.theta_r = q.theta_r;
     d.theta_r_eps = q.theta_r + LH_EPS;
@@ -161,9 +162,9 @@ LhDevParams derive_params(const lh_soil_config& cfg)
     d.vg_inv_n = 1.0 / q.vg_n;
     d.neg_inv_alpha = -1.0 / q.vg_alpha;
     d.Ksat = q.Ksat;
-    d.visc_gamma = q.visc_gamma;
+    d.visc_gamma_l2e = q.visc_gamma * 1.4426950408889634074;   // exp(x) = 2^(x log2 e)
     d.visc_T_ref = q.visc_T_ref;
-    d.imp_c = -q.imp_Omega * log(10.0);
+    d.imp_c2 = -q.imp_Omega * log2(10.0);                      // 10^x = 2^(x log2 10)
     d.rho_c_ds = q.rho_c_ds;
     d.rhocp_l = q.cp_l * q.rho_cloud_liq;
     d.rhocp_i = q.cp_i * q.rho_cloud_ice;
@@ -173,11 +174,11 @@ LhDevParams derive_params(const lh_soil_config& cfg)
     d.kersten_p1 = (1.0 + q.nu_ss_om - q.a * q.nu_ss_quartz - q.nu_ss_gravel) / 2.0;
     d.kersten_p2 = 1.0 - q.nu_ss_om;
     d.kersten_p3 = 1.0 + q.nu_ss_om;
-    d.neg_b = -q.b;
+    d.neg_b_l2e = -q.b * 1.4426950408889634074;
     d.k_unfrozen = q.kappa_sat_unfrozen;
     d.k_frozen = q.kappa_sat_frozen;
-    d.ln_k_unfrozen = log(q.kappa_sat_unfrozen);
-    d.ln_k_frozen = log(q.kappa_sat_frozen);
+    d.log2_k_unfrozen = log2(q.kappa_sat_unfrozen);
+    d.log2_k_frozen = log2(q.kappa_sat_frozen);
     {   // k_dry, SoilHeatParameterizations.jl:268-294 (a per-call scalar in the reference)
         const double rho_b = (1.0 - q.nu) * q.rho_p;
         const double numerator = (q.kappa_dry_parameter * q.kappa_solid - q.K_therm) * rho_b + q.K_therm * q.rho_p;
@@ -187,7 +188,7 @@ LhDevParams derive_params(const lh_soil_config& cfg)
     d.visc_on = q.viscosity_factor != LH_FACTOR_NONE;
     d.imp_on = q.impedance_factor != LH_FACTOR_NONE;
     d.om_zero = q.nu_ss_om == 0.0;
-    d.log_Sr_sat = log(q.nu * d.inv_nu);
+    d.log2_Sr_sat = log2(q.nu * d.inv_nu);
     static const double coeffs[LHC_COUNT] = {LH_MATH_COEFFS};
     memcpy(d.mc, coeffs, sizeof coeffs);
     return d;
@@ -659,6 +660,26 @@ int32_t lh_soil_diagnostic(lh_soil_ctx* c, int32_t which, double* host, int64_t 
     LH_CUDA(c, lh_launch_diagnostic(c->model, which, c->dp, c->U[0], c->U[1], c->U[2], c->U[3], c->tend[slot],
                                     (int64_t)c->ncol_pad * c->nlayer, c->stream));
     return download_field(c, c->tend[slot], host, cs, ls);
+}
+
+int32_t lh_soil_eval_math(lh_soil_ctx* c, int32_t fn, const double* x, double* y, int64_t n)
+{
+    if (!c || !x || !y || n < 0) return LH_ERR_INVALID_ARG;
+    if (fn < LH_MATH_LOG2 || fn > LH_MATH_RSQRT_SEED) return fail(c, LH_ERR_INVALID_ARG, "bad math function id %d", fn);
+    if (n == 0) return LH_OK;
+    LH_CUDA(c, cudaSetDevice(c->device));
+    const int64_t nin = fn == LH_MATH_DIV ? 2 * n : n;
+    double *dx = nullptr, *dy = nullptr;
+    LH_CUDA(c, cudaMalloc(&dx, nin * sizeof(double)));
+    cudaError_t e = cudaMalloc(&dy, n * sizeof(double));
+    if (e == cudaSuccess) e = cudaMemcpyAsync(dx, x, nin * sizeof(double), cudaMemcpyHostToDevice, c->stream);
+    if (e == cudaSuccess) e = lh_launch_eval_math(c->dp, fn, dx, dy, n, c->stream);
+    if (e == cudaSuccess) e = cudaMemcpyAsync(y, dy, n * sizeof(double), cudaMemcpyDeviceToHost, c->stream);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(c->stream);
+    cudaFree(dx);
+    if (dy) cudaFree(dy);
+    if (e != cudaSuccess) return fail(c, LH_ERR_CUDA, "lh_soil_eval_math: %s", cudaGetErrorString(e));
+    return LH_OK;
 }
 
 int32_t lh_soil_sync(lh_soil_ctx* c)

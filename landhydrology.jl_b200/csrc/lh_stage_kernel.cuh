@@ -44,19 +44,18 @@ __device__ __forceinline__ Q<MODEL> q_load(const double* sm)
 template <int MODEL>
 __device__ __forceinline__ Flux face_flux(const LhDevParams& p, const Q<MODEL>& lo, const Q<MODEL>& hi)
 {
+    // -interp(a) * grad(b) = -(a_lo + a_hi)/2 * (b_hi - b_lo)/dz = c (a_lo + a_hi)(b_hi - b_lo),  c = -1/(2 dz)
     Flux f;
     f.w = 0.0; f.e = 0.0;
+    const double c = p.neg_half_inv_dz;
     if constexpr (MODEL == 0) {
-        const double gh = (hi.h - lo.h) * p.inv_dz;
-        f.w = -(0.5 * (lo.K + hi.K)) * gh;
+        f.w = (c * (lo.K + hi.K)) * (hi.h - lo.h);
     } else if constexpr (MODEL == 1) {
-        const double gT = (hi.T - lo.T) * p.inv_dz;
-        f.e = -(0.5 * (lo.kappa + hi.kappa)) * gT;
+        f.e = (c * (lo.kappa + hi.kappa)) * (hi.T - lo.T);
     } else {
-        const double gh = (hi.h - lo.h) * p.inv_dz;
-        const double gT = (hi.T - lo.T) * p.inv_dz;
-        f.w = -(0.5 * (lo.K + hi.K)) * gh;
-        f.e = -(0.5 * (lo.kappa + hi.kappa)) * gT - (0.5 * (lo.eK + hi.eK)) * gh;
+        const double dh = hi.h - lo.h;
+        f.w = (c * (lo.K + hi.K)) * dh;
+        f.e = c * fma(lo.kappa + hi.kappa, hi.T - lo.T, (lo.eK + hi.eK) * dh);
     }
     return f;
 }
@@ -106,13 +105,16 @@ __device__ __forceinline__ double stage_base(double v, double u0)
     else return v;
 }
 
+// Stage combine with the flux-form divergence folded in:  k = -(F_hi - F_lo)/dz and
+//   stage 0: k     1: base + dt k     2: (base + dt k)/4     3: (base + 2 dt k)/3
+// are evaluated as  s (base + cdt (F_hi - F_lo))  with cdt = -dt/dz (stage 3: -2 dt/dz; stage 0: -1/dz).
 template <int STAGE>
-__device__ __forceinline__ double stage_out(double base, double k, double dt)
+__device__ __forceinline__ double stage_out(double base, double dF, double cdt)
 {
-    if constexpr (STAGE == 0) return k;
-    else if constexpr (STAGE == 1) return fma(dt, k, base);
-    else if constexpr (STAGE == 2) return 0.25 * fma(dt, k, base);
-    else return (1.0 / 3.0) * fma(2.0 * dt, k, base);
+    if constexpr (STAGE == 0) return cdt * dF;
+    else if constexpr (STAGE == 1) return fma(cdt, dF, base);
+    else if constexpr (STAGE == 2) return 0.25 * fma(cdt, dF, base);
+    else return (1.0 / 3.0) * fma(cdt, dF, base);
 }
 
 struct Base { double th, re; };
@@ -219,10 +221,11 @@ lh_soil_stage_kernel(const __grid_constant__ LhKernelArgs A)
         o.base.re = (MODEL != 0) ? stage_base<STAGE>(r.x, r.u0re) : 0.0;
         return o;
     };
+    const double cdt = STAGE == 0 ? -p.inv_dz : (STAGE == 3 ? -2.0 * (A.dt * p.inv_dz) : -(A.dt * p.inv_dz));
     auto write_cell = [&](int i, const Base& base, const Flux& lo, const Flux& hi) {
         const int64_t o = (int64_t)i * stride;
-        if constexpr (MODEL != 1) oth[o] = stage_out<STAGE>(base.th, -(hi.w - lo.w) * p.inv_dz, A.dt);
-        if constexpr (MODEL != 0) ore[o] = stage_out<STAGE>(base.re, -(hi.e - lo.e) * p.inv_dz, A.dt);
+        if constexpr (MODEL != 1) oth[o] = stage_out<STAGE>(base.th, hi.w - lo.w, cdt);
+        if constexpr (MODEL != 0) ore[o] = stage_out<STAGE>(base.re, hi.e - lo.e, cdt);
     };
 
     Q<MODEL> prev;            // closures of the last evaluated cell

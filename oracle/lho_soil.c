@@ -765,6 +765,27 @@ int32_t lho_soil_diagnostic(lho_soil_ctx* c, int32_t which, double* host, int64_
 
 int32_t lho_soil_sync(lho_soil_ctx* c) { (void)c; return LH_OK; }
 
+/* libm versions of the functions the device library hand-writes */
+int32_t lho_soil_eval_math(lho_soil_ctx* c, int32_t fn, const double* x, double* y, int64_t n)
+{
+    (void)c;
+    if (!x || !y || n < 0) return LH_ERR_INVALID_ARG;
+    for (int64_t i = 0; i < n; ++i) {
+        switch (fn) {
+        case LH_MATH_LOG2: y[i] = log2(x[i]); break;
+        case LH_MATH_EXP2: y[i] = exp2(x[i]); break;
+        case LH_MATH_EXP2M1: y[i] = exp2(x[i]) - 1.0; break;
+        case LH_MATH_SQRT: y[i] = sqrt(x[i]); break;
+        case LH_MATH_RSQRT: y[i] = 1.0 / sqrt(x[i]); break;
+        case LH_MATH_RCP: case LH_MATH_RCP_SEED: y[i] = 1.0 / x[i]; break;
+        case LH_MATH_RSQRT_SEED: y[i] = 1.0 / sqrt(x[i]); break;
+        case LH_MATH_DIV: y[i] = x[i] / x[n + i]; break;
+        default: return LH_ERR_INVALID_ARG;
+        }
+    }
+    return LH_OK;
+}
+
 int32_t lho_soil_last_step_timing(lho_soil_ctx* c, double* ms_out, int64_t* launches_out)
 {
     if (!c) return LH_ERR_INVALID_ARG;

@@ -36,6 +36,7 @@
 #define lh_soil_budgets           lho_soil_budgets
 #define lh_soil_diagnostic        lho_soil_diagnostic
 #define lh_soil_sync              lho_soil_sync
+#define lh_soil_eval_math         lho_soil_eval_math
 #define lh_soil_last_step_timing  lho_soil_last_step_timing
 #define lh_soil_device_ptr        lho_soil_device_ptr
 #define lh_soil_comm_unique_id    lho_soil_comm_unique_id

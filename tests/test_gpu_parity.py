@@ -285,3 +285,40 @@ def test_check_finite_flag(cuda):
     wl.upload(g)
     with pytest.raises(lh.NonFiniteStateError):
         g.step(0.0, wl.dt, 1)
+
+
+# ---- the device elementary functions themselves, evaluated on the GPU ------------------------------
+def test_device_math_accuracy_on_gpu(cuda):
+    """lh_log2 / lh_exp2 / lh_exp2m1 / lh_sqrt / lh_rsqrt / lh_rcp / lh_div (csrc/lh_math.cuh) evaluated ON
+    THE B200 through lh_soil_eval_math, against mpmath at 40 digits.  This is what validates the MUFU
+    seed accuracy the Newton/cubic refinements rely on (tests/test_device_math.py checks the same
+    source on the host with emulated 20-bit seeds)."""
+    import mpmath as mp
+
+    mp.mp.dps = 40
+    wl = w.coupled_workload(ncol=32, nlayer=4, seed=1)
+    ctx = lh.SoilContext(cuda, wl.config())
+    rng = np.random.default_rng(12)
+
+    def ulps(y, exact):
+        out = []
+        for a, e in zip(y, exact):
+            ulp = mp.mpf(2) ** (mp.floor(mp.log(abs(e), 2)) - 52)
+            out.append(float(abs(mp.mpf(float(a)) - e) / ulp))
+        return np.array(out)
+
+    x = np.concatenate([rng.uniform(1e-16, 2.0, 3000), np.exp(rng.uniform(-40, 40, 1500)), 1 + rng.uniform(-1e-3, 1e-3, 500)])
+    assert ulps(ctx.eval_math(0, x), [mp.log(mp.mpf(float(v)), 2) for v in x]).max() <= 2.5
+    assert ulps(ctx.eval_math(3, x), [mp.sqrt(mp.mpf(float(v))) for v in x]).max() <= 1.5
+    assert ulps(ctx.eval_math(4, x), [1 / mp.sqrt(mp.mpf(float(v))) for v in x]).max() <= 2.5
+    assert ulps(ctx.eval_math(5, x), [1 / mp.mpf(float(v)) for v in x]).max() <= 2.0
+    num = rng.uniform(-1e8, 1e8, x.size)
+    assert ulps(ctx.eval_math(6, np.concatenate([num, x])), [mp.mpf(float(a)) / mp.mpf(float(b)) for a, b in zip(num, x)]).max() <= 1.5
+    xe = np.concatenate([rng.uniform(-50, 50, 3000), rng.uniform(-1, 1, 1500), rng.uniform(-700, 700, 500)])
+    assert ulps(ctx.eval_math(1, xe), [mp.mpf(2) ** mp.mpf(float(v)) for v in xe]).max() <= 2.0
+    ym = ctx.eval_math(2, xe)
+    exact = np.array([float(mp.expm1(mp.mpf(float(v)) * mp.log(2))) for v in xe])
+    assert np.max(np.abs(ym - exact) / np.abs(exact)) <= 6e-15
+    small = np.abs(xe) < 1 / 32
+    assert ulps(ym[small], [mp.expm1(mp.mpf(float(v)) * mp.log(2)) for v in xe[small]]).max() <= 8.0
+    assert ctx.eval_math(3, np.array([0.0]))[0] == 0.0 and np.isnan(ctx.eval_math(0, np.array([-1.0]))[0])
