@@ -51,6 +51,7 @@ struct LhDevParams {
     double neg_b_l2e;                  // -b * log2(e)
     double k_unfrozen, k_frozen, log2_k_unfrozen, log2_k_frozen;
     double kappa_dry;
+    double k_unfrozen_minus_dry;       // kappa_sat_unfrozen - kappa_dry
     double log2_Sr_sat;                // log2(nu * (1/nu)): relative saturation of a saturated, ice-free cell
     int32_t visc_on, imp_on;
     int32_t om_zero;                   // nu_ss_om == 0: outer Kersten exponents are exactly 1
@@ -96,7 +97,7 @@ struct LhCell {
 // results: the unsaturated expressions are evaluated unconditionally (they are the common case and
 // yield NaN/garbage only where the select discards them).
 // ---------------------------------------------------------------------------------------------
-template <bool ICE, bool GEN, bool VG2, bool NEED_LOG>
+template <bool ICE, bool GEN, bool VG2, bool NEED_LOG, bool THR0 = false>
 __device__ __forceinline__ void lh_water_closures(const LhDevParams& p, const double* __restrict__ tab,
                                                   double th, double ti, double T,
                                                   double& K_out, double& psi_out, double& logS_K)
@@ -105,7 +106,7 @@ __device__ __forceinline__ void lh_water_closures(const LhDevParams& p, const do
     const double nu_eff = ICE ? p.nu - ti : p.nu;
     // effective_saturation (SoilWaterParameterizations.jl:213-217); NaN stays NaN
     const double safe = !(th <= p.theta_r_eps) ? th : p.theta_r_eps;
-    const double num = safe - p.theta_r;
+    const double num = THR0 ? safe : safe - p.theta_r;                       // THR0: theta_r == 0 is known
     const double S_K = num * p.inv_nu_thr;                                   // porosity = nu (:163/:311)
     const bool icy = ICE && (ti != 0.0);
     double S_eff = S_K;                                                      // porosity = nu_eff (:235)
@@ -189,8 +190,15 @@ __device__ __forceinline__ double lh_thermal_conductivity(const LhDevParams& p, 
     } else {                                                                 // :171
         K_e = (!GEN || p.om_zero) ? S_r : lh_exp2(mc, tab, p.kersten_p3 * Lr);
     }
+    if (!ICE) {
+        // kappa_sat = kappa_unfrozen^1 * kappa_frozen^0 exactly (:114-128), so
+        // K_e kappa_sat + (1 - K_e) kappa_dry = kappa_dry + K_e (kappa_unfrozen - kappa_dry): one FMA.
+        // The theta_w < eps case (kappa_sat = 0) needs no select: there S_r -> 0, the Kersten base
+        // E3 - c^3 -> 1/8 - 1/8 and K_e vanishes, so kappa = kappa_dry either way.
+        return lh_fma(K_e, p.k_unfrozen_minus_dry, p.kappa_dry);
+    }
     double k_sat = p.k_unfrozen;                                             // :114-128; x^1 * y^0 is exact
-    if (ICE && ti != 0.0) k_sat = lh_exp2(mc, tab, lh_div(tl * p.log2_k_unfrozen + ti * p.log2_k_frozen, tw));
+    if (ti != 0.0) k_sat = lh_exp2(mc, tab, lh_div(tl * p.log2_k_unfrozen + ti * p.log2_k_frozen, tw));
     k_sat = (tw < LH_EPS) ? 0.0 : k_sat;
     return K_e * k_sat + (1.0 - K_e) * p.kappa_dry;                          // thermal_conductivity :185-188
 }
@@ -222,7 +230,8 @@ __device__ __forceinline__ LhCell lh_cell_closures(const LhDevParams& p, const d
     const double tl = unsat ? th : nu_eff;                                   // volumetric_liquid_fraction :181-188
     if (MODEL != 0) c.T = lh_temperature<ICE>(p, tl, ti, T_or_re);
     double logS = 0.0;
-    if (MODEL != 1) lh_water_closures<ICE, GEN, VG2, REUSE>(p, tab, th, ti, c.T, c.K, c.psi, logS);
+    // the coupled !GEN variants are only launched when theta_r == 0 (update_kernel_flags)
+    if (MODEL != 1) lh_water_closures<ICE, GEN, VG2, REUSE, (MODEL == 2 && !GEN)>(p, tab, th, ti, c.T, c.K, c.psi, logS);
     if (MODEL == 1) c.kappa = lh_thermal_conductivity<ICE, GEN, false>(p, tab, tl, ti, unsat, 0.0);
     if (MODEL == 2) c.kappa = lh_thermal_conductivity<ICE, GEN, true>(p, tab, tl, ti, unsat, logS);
     return c;

@@ -185,6 +185,7 @@ LhDevParams derive_params(const lh_soil_config& cfg)
         const double denom = q.rho_p - (1.0 - q.kappa_dry_parameter) * rho_b;
         d.kappa_dry = numerator / denom;
     }
+    d.k_unfrozen_minus_dry = q.kappa_sat_unfrozen - d.kappa_dry;
     d.visc_on = q.viscosity_factor != LH_FACTOR_NONE;
     d.imp_on = q.impedance_factor != LH_FACTOR_NONE;
     d.om_zero = q.nu_ss_om == 0.0;
