@@ -6,21 +6,24 @@
 
 #include "lh_closures.cuh"
 
-// Register budget of the stage kernels, per model (measured, profiles/r01_g_*): the coupled and heat
-// closures keep ~120 registers busy and lose from spilling, so they run at 128 registers (<= 512
-// threads per block, 16 warps/SM); the Richards closures are one long dependent chain with few
-// temporaries and gain 20 % from 24 warps/SM at <= 85 registers (<= 256 threads per block, 3 blocks).
+// Register budget of the stage kernels (measured, gpurun_out/variants_i.log -> profiles/r01_i_*): once the
+// layer loop is provably warp-uniform (lh_stage_kernel.cuh) the coupled n = 2 variant needs ~96 registers
+// and every model runs best as 4-warp blocks, 5 resident blocks per SM (20 warps/SM, <= 102 registers):
+// coupled 80 %, general-n 61 %, Richards 51 % of the HBM roofline, against 79 / 58 / 49 % at 16 warps/SM.
+#ifndef LH_ILP2
+#define LH_ILP2 0      // 1: issue both cells' loads before either closure chain (measured: no gain)
+#endif
 #ifndef LH_MIN_BLOCKS
-#define LH_MIN_BLOCKS 1
+#define LH_MIN_BLOCKS 5
 #endif
 #ifndef LH_MAX_THREADS
-#define LH_MAX_THREADS 512
+#define LH_MAX_THREADS 128
 #endif
 #ifndef LH_MIN_BLOCKS_RICHARDS
-#define LH_MIN_BLOCKS_RICHARDS 3
+#define LH_MIN_BLOCKS_RICHARDS 5
 #endif
 #ifndef LH_MAX_THREADS_RICHARDS
-#define LH_MAX_THREADS_RICHARDS 256
+#define LH_MAX_THREADS_RICHARDS 128
 #endif
 template <int MODEL> struct LhBounds { static constexpr int max_threads = LH_MAX_THREADS, min_blocks = LH_MIN_BLOCKS; };
 template <> struct LhBounds<0> { static constexpr int max_threads = LH_MAX_THREADS_RICHARDS, min_blocks = LH_MIN_BLOCKS_RICHARDS; };

@@ -135,10 +135,17 @@ lh_soil_stage_kernel(const __grid_constant__ LhKernelArgs A)
     constexpr int NQv = NQ<MODEL>::value;
     constexpr bool ICE = (FLAGS & LH_FLAG_ICE) != 0;
     const LhDevParams& p = A.p;
-    const int lane = threadIdx.x, w = threadIdx.y, g = threadIdx.z;
+    // A warp is one (column group g, chunk w) pair, so w, g and everything derived from them (loop
+    // bounds, `active`) are warp-uniform.  ptxas cannot see that from threadIdx.y/z and then treats the
+    // layer loop as divergent: no uniform-register operands inside it, every constant copied to vector
+    // registers (128 registers, 260 instructions per cell).  Reading them through a lane-0 shuffle
+    // proves uniformity: 100 registers, 230 instructions per cell, the coefficients stay in UR.
+    const int lane = threadIdx.x;
+    const int w = __shfl_sync(0xffffffffu, (int)threadIdx.y, 0), g = __shfl_sync(0xffffffffu, (int)threadIdx.z, 0);
     const int W = blockDim.y;
-    const int64_t col = ((int64_t)blockIdx.x * blockDim.z + g) * 32 + lane;
-    const bool valid = col < A.ncol_pad;      // whole column groups are valid or not (ncol_pad % 32 == 0)
+    const int64_t col0 = ((int64_t)blockIdx.x * blockDim.z + g) * 32;
+    const int64_t col = col0 + lane;
+    const bool valid = col0 < A.ncol_pad;     // whole column groups are valid or not (ncol_pad % 32 == 0)
     const int n = A.nlayer;
     const int a = w * A.Lc;
     const int b = min(n, a + A.Lc);
@@ -255,12 +262,24 @@ lh_soil_stage_kernel(const __grid_constant__ LhKernelArgs A)
             ++i;
         }
         for (; i + 1 < b; i += 2) {   // two cells per trip: no sliding-window register moves
+#if LH_ILP2
+            // both cells' inputs first, so that the two (independent) closure chains can be interleaved
+            const Raw r0 = load_raw(i);
+            const Raw r1 = load_raw(i + 1);
+            const Cell<MODEL> c0 = eval(r0, i);
+            const Cell<MODEL> c1 = eval(r1, i + 1);
+            const Flux F0 = face_flux<MODEL>(p, prev, c0.q);
+            const Flux F1 = face_flux<MODEL>(p, c0.q, c1.q);
+            write_cell(i - 1, base_prev, F_below, F0);
+            write_cell(i, c0.base, F0, F1);
+#else
             const Cell<MODEL> c0 = eval(load_raw(i), i);
             const Flux F0 = face_flux<MODEL>(p, prev, c0.q);
             write_cell(i - 1, base_prev, F_below, F0);
             const Cell<MODEL> c1 = eval(load_raw(i + 1), i + 1);
             const Flux F1 = face_flux<MODEL>(p, c0.q, c1.q);
             write_cell(i, c0.base, F0, F1);
+#endif
             if (i + 2 == b) sm_top[NQv * 32] = c1.psi;
             F_below = F1; prev = c1.q; base_prev = c1.base;
         }
