@@ -16,8 +16,8 @@
 // the parity gate is 1e-12 (cancellation-aware norm) per tendency evaluation.
 //
 // The fp64 pipe (64 DFMA/clk/SM on B200), not HBM, is the binding unit for this path, so the
-// elementary functions in lh_math.cuh are written for minimum DFMA count.  `tab` is the 16-entry
-// 2^(j/16) table of lh_exp, staged in shared memory by every kernel (lh_stage_exp_table).
+// elementary functions in lh_math.cuh are written for minimum DFMA count.  `tab` points at the exp2 / log2
+// tables of lh_math.cuh, staged in shared memory by every kernel (lh_stage_tables).
 #pragma once
 
 #include <cuda_runtime.h>
@@ -59,10 +59,11 @@ struct LhDevParams {
     double mc[LHC_COUNT];              // elementary-function coefficients (lh_math.cuh)
 };
 
-// Copies the exp table from the parameter block to shared memory; the caller must __syncthreads().
-__device__ __forceinline__ void lh_stage_exp_table(const LhDevParams& p, double* tab_smem, int linear_tid)
+// Copies the exp2 / log2 tables from the parameter block to shared memory (LH_TAB_DOUBLES doubles, 16-byte
+// aligned destination); the caller must __syncthreads().
+__device__ __forceinline__ void lh_stage_tables(const LhDevParams& p, double* tab_smem, int linear_tid, int nthreads)
 {
-    if (linear_tid < 16) tab_smem[linear_tid] = p.mc[LHC_EXP2_TAB0 + linear_tid];
+    for (int k = linear_tid; k < LH_TAB_DOUBLES; k += nthreads) tab_smem[k] = p.mc[LHC_TAB0 + k];
 }
 
 struct LhCell {
@@ -70,6 +71,7 @@ struct LhCell {
     double psi;    // pressure head
     double kappa;  // thermal conductivity
     double T;      // temperature
+    double dT;     // T - T_0 as computed (the quotient of temperature_from_ρe_int), for ρe_int_l = ρc_l (T - T_0)
 };
 
 // Kernel variants (template flags).  Both are properties of the uploaded problem, decided on the
@@ -126,20 +128,20 @@ __device__ __forceinline__ void lh_water_closures(const LhDevParams& p, const do
         psi_unsat = p.neg_inv_alpha * (sw * inv_S_eff);                      // :196-200
         const double t = (S_K * S_K) * lh_rcp(1.0 + swK);                    // 1 - (1 - S^(1/m))^m
         Kr_unsat = (S_K * rS) * (t * t);                                     // :277
-        if (NEED_LOG) L_K = lh_log2(mc, S_K);
+        if (NEED_LOG) L_K = lh_log2<false>(mc, tab, S_K);   // Kersten exponent only; a NaN state already poisons psi and K
     } else {
         // ---- general n: pressure head (:229-242) and the shared logs
-        const double L_eff = lh_log2(mc, S_eff);
+        const double L_eff = lh_log2(mc, tab, S_eff);
         const double u = L_eff * p.vg_inv_m;
         const double w = -lh_exp2m1(mc, tab, u);                             // 1 - S^(1/m)
-        const double a = lh_log2(mc, w);
+        const double a = lh_log2(mc, tab, w);
         psi_unsat = p.neg_inv_alpha * lh_exp2(mc, tab, (a - u) * p.vg_inv_n);
         // ---- hydraulic conductivity (:269-282)
         double a_K = a;
         L_K = L_eff;
         if (icy) {                       // S differs from S_eff only when ice is present
-            L_K = lh_log2(mc, S_K);
-            a_K = lh_log2(mc, -lh_exp2m1(mc, tab, L_K * p.vg_inv_m));
+            L_K = lh_log2(mc, tab, S_K);
+            a_K = lh_log2(mc, tab, -lh_exp2m1(mc, tab, L_K * p.vg_inv_m));
         }
         const double q = lh_exp2m1(mc, tab, p.vg_m * a_K);                   // (1 - y)^m - 1
         Kr_unsat = lh_sqrt(S_K) * (q * q);
@@ -177,7 +179,7 @@ __device__ __forceinline__ double lh_thermal_conductivity(const LhDevParams& p, 
     const double S_r = tw * p.inv_nu;                                        // relative_saturation :139-142
     double Lr;
     if (REUSE && !ICE && !GEN) Lr = unsat ? logS : p.log2_Sr_sat;
-    else Lr = lh_log2(mc, S_r);
+    else Lr = lh_log2(mc, tab, S_r);
     double K_e;
     if (!ICE || ti < LH_EPS) {                                               // kersten_number :163-169
         const double e = lh_exp2(mc, tab, p.neg_b_l2e * S_r);                // exp(-b S_r)
@@ -185,7 +187,7 @@ __device__ __forceinline__ double lh_thermal_conductivity(const LhDevParams& p, 
         const double E3 = lh_rcp(g * g * g);
         const double c = (1.0 - S_r) * 0.5;
         double base = E3 - c * c * c;
-        if (GEN && !p.om_zero) base = lh_exp2(mc, tab, p.kersten_p2 * lh_log2(mc, base));
+        if (GEN && !p.om_zero) base = lh_exp2(mc, tab, p.kersten_p2 * lh_log2(mc, tab, base));
         K_e = lh_exp2(mc, tab, p.kersten_p1 * Lr) * base;
     } else {                                                                 // :171
         K_e = (!GEN || p.om_zero) ? S_r : lh_exp2(mc, tab, p.kersten_p3 * Lr);
@@ -203,16 +205,16 @@ __device__ __forceinline__ double lh_thermal_conductivity(const LhDevParams& p, 
     return K_e * k_sat + (1.0 - K_e) * p.kappa_dry;                          // thermal_conductivity :185-188
 }
 
-// Temperature from ρe_int (SoilHeatParameterizations.jl:42-79).
+// Temperature from ρe_int (SoilHeatParameterizations.jl:42-79): returns T - T_0 (the quotient); T = T_0 + it.
 template <bool ICE>
-__device__ __forceinline__ double lh_temperature(const LhDevParams& p, double tl, double ti, double re)
+__device__ __forceinline__ double lh_temperature_minus_T0(const LhDevParams& p, double tl, double ti, double re)
 {
     if (ICE) {
         const double rho_c_s = p.rho_c_ds + tl * p.rhocp_l + ti * p.rhocp_i; // :65-79
-        return p.T_0 + lh_div_fast(re + ti * p.rhoi_LH, rho_c_s);            // :42-53 (quotient << T_0: 2 ulp of it is below ulp(T))
+        return lh_div_fast(re + ti * p.rhoi_LH, rho_c_s);                    // :42-53 (quotient << T_0: 2 ulp of it is below ulp(T))
     }
     const double rho_c_s = p.rho_c_ds + tl * p.rhocp_l;
-    return p.T_0 + lh_div_fast(re, rho_c_s);
+    return lh_div_fast(re, rho_c_s);
 }
 
 // All closures of one cell for model MODEL (0 Richards, 1 heat, 2 coupled).
@@ -224,11 +226,16 @@ __device__ __forceinline__ LhCell lh_cell_closures(const LhDevParams& p, const d
     constexpr bool ICE = (FLAGS & LH_FLAG_ICE) != 0, GEN = (FLAGS & LH_FLAG_GEN) != 0, VG2 = (FLAGS & LH_FLAG_VG2) != 0;
     constexpr bool REUSE = (MODEL == 2) && !ICE && !GEN;   // the Kersten number takes log S from the water closure
     LhCell c;
-    c.K = 0.0; c.psi = 0.0; c.kappa = 0.0; c.T = T_or_re;
+    c.K = 0.0; c.psi = 0.0; c.kappa = 0.0; c.T = T_or_re; c.dT = 0.0;
     const double nu_eff = ICE ? p.nu - ti : p.nu;
     const bool unsat = th < nu_eff;
     const double tl = unsat ? th : nu_eff;                                   // volumetric_liquid_fraction :181-188
-    if (MODEL != 0) c.T = lh_temperature<ICE>(p, tl, ti, T_or_re);
+    if (MODEL != 0) {
+        // ρe_int_l = ρc_l (T - T_0) (SoilHeatParameterizations.jl:198-207) takes the quotient itself: the
+        // reference's T - T_0 re-rounds it to ulp(T) ~ 5.7e-14, which this form does not
+        c.dT = lh_temperature_minus_T0<ICE>(p, tl, ti, T_or_re);
+        c.T = p.T_0 + c.dT;
+    }
     double logS = 0.0;
     // the coupled !GEN variants are only launched when theta_r == 0 (update_kernel_flags)
     if (MODEL != 1) lh_water_closures<ICE, GEN, VG2, REUSE, (MODEL == 2 && !GEN)>(p, tab, th, ti, c.T, c.K, c.psi, logS);

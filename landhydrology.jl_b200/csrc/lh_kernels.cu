@@ -47,7 +47,7 @@ LhLaunchShape lh_choose_shape(int model, int64_t ncol_pad, int32_t nlayer, int s
     s.Lc = Lc; s.W = W; s.G = G;
     s.nblocks = (groups + G - 1) / G;
     const int nq = model == LH_MODEL_COUPLED ? 5 : 2;
-    s.smem_bytes = (16 + (size_t)G * W * ((2 * (nq + 1) + 4) * 32 + 4 * 5 * 32)) * sizeof(double);   // + cp.async input ring
+    s.smem_bytes = (LH_TAB_DOUBLES + (size_t)G * W * ((2 * nq + 4) * 32 + 4 * 5 * 32)) * sizeof(double);   // + cp.async input ring
     return s;
 }
 
@@ -72,8 +72,8 @@ __global__ void lh_diag_kernel(const __grid_constant__ LhDevParams p, int which,
                                const double* __restrict__ ti, const double* __restrict__ re,
                                const double* __restrict__ T, double* __restrict__ out, int64_t n)
 {
-    __shared__ double tab[16];
-    lh_stage_exp_table(p, tab, threadIdx.x);
+    __shared__ __align__(16) double tab[LH_TAB_DOUBLES];
+    lh_stage_tables(p, tab, threadIdx.x, blockDim.x);
     __syncthreads();
     const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
@@ -287,15 +287,15 @@ namespace {
 __global__ void lh_eval_math_kernel(const __grid_constant__ LhDevParams p, int fn, const double* __restrict__ x,
                                     double* __restrict__ y, int64_t n)
 {
-    __shared__ double tab[16];
-    lh_stage_exp_table(p, tab, threadIdx.x);
+    __shared__ __align__(16) double tab[LH_TAB_DOUBLES];
+    lh_stage_tables(p, tab, threadIdx.x, blockDim.x);
     __syncthreads();
     const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
     const double v = x[i];
     double r;
     switch (fn) {
-    case LH_MATH_LOG2: r = lh_log2(p.mc, v); break;
+    case LH_MATH_LOG2: r = lh_log2(p.mc, tab, v); break;
     case LH_MATH_EXP2: r = lh_exp2(p.mc, tab, v); break;
     case LH_MATH_EXP2M1: r = lh_exp2m1(p.mc, tab, v); break;
     case LH_MATH_SQRT: r = lh_sqrt(v); break;

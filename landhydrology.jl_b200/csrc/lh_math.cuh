@@ -100,13 +100,19 @@ LH_DEV double lh_sqrt(double x)
 
 // ---------------------------------------------------------------------------------------------------
 // Every transcendental on the soil path is a power x^c, so base 2 serves everywhere and saves the ln 2
-// scalings of a natural log/exp pair.
+// scalings of a natural log/exp pair.  Both functions are table driven; `tab` points at the LH_TAB_DOUBLES
+// constants (lh_math_coeffs.inc from LHC_TAB0 on) that every kernel stages in SHARED memory:
+//   tab[0 .. 63]            2^(j/64)
+//   tab[64 + 2j], [65 + 2j] r_j, -log2 r_j for the 128 mantissa intervals of lh_log2 (one 16-byte load)
+// The stage kernel is issue bound and an fp64 instruction holds the issue port for two cycles, so a table
+// load (one LDS, bank conflicts cost LSU cycles, not issue slots) is worth more than one polynomial term.
 //
-// exp2 core: x = k/16 + r, |r| <= 1/32 (the reduction r = x - k/16 is EXACT);
-//   2^x = 2^(k>>4) * T[k&15] * (1 + p),  p = r g(r) (degree-5 g),  T[j] = 2^(j/16).
-// `tab` points at the 16-entry table: the kernels stage it in SHARED memory, where a 16 x 8-byte table
-// spans the 32 banks exactly once, so any pattern of per-lane indices is conflict-free (one LDS.64).
+// exp2 core: x = k/64 + r, |r| <= 1/128 (the reduction r = x - k/64 is EXACT);
+//   2^x = 2^(k>>6) * T[k&63] * (1 + p),  p = r g(r) (degree-4 g).
 // ---------------------------------------------------------------------------------------------------
+#define LH_TAB_EXP 0
+#define LH_TAB_LOG LH_EXP_TAB
+
 struct LhExpParts { double s, p; };
 
 LH_DEV LhExpParts lh_exp2_parts(const double* __restrict__ lh_c, const double* __restrict__ tab, double x)
@@ -118,20 +124,19 @@ LH_DEV LhExpParts lh_exp2_parts(const double* __restrict__ lh_c, const double* _
     int32_t xhi = lh_hi(x);
     xhi = ((uint32_t)xhi > 0xC08FF000u) ? (int32_t)0xC08FF000 : xhi;
     const double xc = lh_mk(xhi, lh_lo(x));
-    const double MAGIC = 6755399441055744.0;                 // 1.5 * 2^52: low word of t is k = rint(16 x)
-    const double t = lh_fma(xc, 16.0, MAGIC);
+    const double MAGIC = 6755399441055744.0;                 // 1.5 * 2^52: low word of t is k = rint(64 x)
+    const double t = lh_fma(xc, (double)LH_EXP_TAB, MAGIC);
     const int32_t k = lh_lo(t);
-    const double r = lh_fma(t - MAGIC, -0.0625, xc);         // exact
-    const double T = tab[k & 15];
-    double g = lh_c[LHC_EXP2_G5];
-    g = lh_fma(g, r, lh_c[LHC_EXP2_G4]);
+    const double r = lh_fma(t - MAGIC, -1.0 / LH_EXP_TAB, xc);   // exact
+    const double T = tab[LH_TAB_EXP + (k & (LH_EXP_TAB - 1))];
+    double g = lh_c[LHC_EXP2_G4];
     g = lh_fma(g, r, lh_c[LHC_EXP2_G3]);
     g = lh_fma(g, r, lh_c[LHC_EXP2_G2]);
     g = lh_fma(g, r, lh_c[LHC_EXP2_G1]);
     g = lh_fma(g, r, lh_c[LHC_EXP2_G0]);
     LhExpParts o;
     o.p = r * g;
-    o.s = lh_mk(lh_hi(T) + ((k >> 4) << 20), lh_lo(T));     // T * 2^(k>>4): exponent-field add
+    o.s = lh_mk(lh_hi(T) + ((k >> 6) << 20), lh_lo(T));     // T * 2^(k>>6): exponent-field add
     return o;
 }
 
@@ -143,9 +148,9 @@ LH_DEV double lh_exp2(const double* __restrict__ lh_c, const double* __restrict_
     return lh_fma(e.s, e.p, e.s);
 }
 
-// 2^x - 1.  |x| <= 1/32: k == 0, s == 1 and the result is p itself (<= 8 ulp = 1.8e-15 relative where
-// 1 - 2^x cancels; the literal fp64 form 1 - x^c the reference uses is off by 1.1e-16 / |1 - 2^x| there).
-// Otherwise s - 1 carries the rounding of T[j]: relative error <= 2^-53 / |2^x - 1| < 6e-15.
+// 2^x - 1.  |x| <= 1/128: k == 0, s == 1 and the result is p itself (a few ulp where 1 - 2^x cancels; the
+// literal fp64 form 1 - x^c the reference uses is off by 1.1e-16 / |1 - 2^x| there).
+// Otherwise s - 1 carries the rounding of T[j]: relative error <= 2^-53 / |2^x - 1| < 2e-14.
 LH_DEV double lh_exp2m1(const double* __restrict__ lh_c, const double* __restrict__ tab, double x)
 {
     const LhExpParts e = lh_exp2_parts(lh_c, tab, x);
@@ -153,37 +158,40 @@ LH_DEV double lh_exp2m1(const double* __restrict__ lh_c, const double* __restric
 }
 
 // ---------------------------------------------------------------------------------------------------
-// log2(x): x = 2^e m, m in [sqrt(1/2), sqrt(2));  s = (m-1)/(m+1);  ln m = 2 s + s z P(z), z = s^2;
-// log2 x = e + ln(m) log2(e).
-// x < 0, NaN (and +inf) -> NaN.  x == 0 and subnormals read as 2^-1023 m: log2(0) = -1023 instead of
+// log2(x), table driven (Tang): x = 2^e m, m in [0.709, 1.418); j = top 7 bits of m's position in
+// that range; t = m r_j - 1 by ONE FMA (|t| <= 2^-8, relative error 2^-53 whatever r_j's rounding was);
+//   log2 x = (e + L_j) + t Q(t),  L_j = -log2 r_j,  Q of degree 5.
+// The interval around m = 1 has r = 1, L = 0 exactly, so the RELATIVE accuracy is kept as x -> 1 (the
+// closures need log2 S for S -> 1-).  8 fp64 operations, no division.
+// CHECK: x < 0, NaN (and +inf) -> NaN.  x == 0 and subnormals read as 2^-1023 m: log2(0) ~ -1023 instead of
 // -inf, which is what the closures need (exp2 of it underflows; nothing tests for -inf).
 // ---------------------------------------------------------------------------------------------------
-LH_DEV double lh_log2(const double* __restrict__ lh_c, double x)
+template <bool CHECK = true>
+LH_DEV double lh_log2(const double* __restrict__ lh_c, const double* __restrict__ tab, double x)
 {
     int32_t hi = lh_hi(x) & 0x7fffffff;      // log|x|; the sign only matters for the NaN flag below
     const int32_t lo = lh_lo(x);
     // exponent such that the mantissa lands in [sqrt(1/2), sqrt(2))
-    const int32_t e = (hi - 0x3fe6a09e) >> 20;
+    const int32_t off = hi - LH_LOG_HI0;
+    const int32_t e = off >> 20;
+    const int32_t j = (off >> LH_LOG_SHIFT) & (LH_LOG_TAB - 1);
     hi -= e << 20;
     const double m = lh_mk(hi, lo);
-    const double f = m - 1.0;
-    const double d = m + 1.0;
-    // s = f / (2 + f): reciprocal of the (rounded) d, then one correction whose residual
-    // f - 2 s - s f is formed from f itself (f - 2 s is exact by Sterbenz), so the rounding of
-    // d = m + 1 does not leak into s.
-    const double r = lh_rcp(d);
-    double s = f * r;
-    s = lh_fma(lh_fma(-s, f, lh_fma(-2.0, s, f)), r, s);
-    const double z = s * s;
-    double P = lh_c[LHC_LOG_P6];
-    P = lh_fma(P, z, lh_c[LHC_LOG_P5]);
-    P = lh_fma(P, z, lh_c[LHC_LOG_P4]);
-    P = lh_fma(P, z, lh_c[LHC_LOG_P3]);
-    P = lh_fma(P, z, lh_c[LHC_LOG_P2]);
-    P = lh_fma(P, z, lh_c[LHC_LOG_P1]);
-    P = lh_fma(P, z, lh_c[LHC_LOG_P0]);
-    const double lnm = lh_fma(s * z, P, s + s);
-    const double y = lh_fma(lnm, lh_c[LHC_L2E], (double)e);
+#ifdef LH_MATH_HOST
+    const double r = tab[LH_TAB_LOG + 2 * j], L = tab[LH_TAB_LOG + 2 * j + 1];
+#else
+    const double2 rl = *reinterpret_cast<const double2*>(tab + LH_TAB_LOG + 2 * j);
+    const double r = rl.x, L = rl.y;
+#endif
+    const double t = lh_fma(m, r, -1.0);
+    double Q = lh_c[LHC_LOG_Q5];
+    Q = lh_fma(Q, t, lh_c[LHC_LOG_Q4]);
+    Q = lh_fma(Q, t, lh_c[LHC_LOG_Q3]);
+    Q = lh_fma(Q, t, lh_c[LHC_LOG_Q2]);
+    Q = lh_fma(Q, t, lh_c[LHC_LOG_Q1]);
+    Q = lh_fma(Q, t, lh_c[LHC_LOG_Q0]);
+    const double y = lh_fma(t, Q, (double)e + L);
+    if (!CHECK) return y;
     // x < 0, NaN, +inf: force NaN with integer compares on the high word (cheaper than an fp64
     // compare, which occupies the fp64 pipe).  -0.0 (high word exactly 0x80000000: the closures
     // produce it as -(exp2m1(0))) is NOT flagged: like +0 it yields a huge negative finite value.
