@@ -133,7 +133,7 @@ __device__ __forceinline__ void lh_water_closures(const LhDevParams& p, const do
         // ---- general n: pressure head (:229-242) and the shared logs
         const double L_eff = lh_log2(mc, tab, S_eff);
         const double u = L_eff * p.vg_inv_m;
-        const double w = -lh_exp2m1(mc, tab, u);                             // 1 - S^(1/m)
+        const double w = lh_one_minus_exp2(mc, tab, u);                      // 1 - S^(1/m)
         const double a = lh_log2(mc, tab, w);
         psi_unsat = p.neg_inv_alpha * lh_exp2(mc, tab, (a - u) * p.vg_inv_n);
         // ---- hydraulic conductivity (:269-282)
@@ -141,10 +141,10 @@ __device__ __forceinline__ void lh_water_closures(const LhDevParams& p, const do
         L_K = L_eff;
         if (icy) {                       // S differs from S_eff only when ice is present
             L_K = lh_log2(mc, tab, S_K);
-            a_K = lh_log2(mc, tab, -lh_exp2m1(mc, tab, L_K * p.vg_inv_m));
+            a_K = lh_log2(mc, tab, lh_one_minus_exp2(mc, tab, L_K * p.vg_inv_m));
         }
         const double q = lh_exp2m1(mc, tab, p.vg_m * a_K);                   // (1 - y)^m - 1
-        Kr_unsat = lh_sqrt(S_K) * (q * q);
+        Kr_unsat = (S_K * lh_rsqrt(S_K)) * (q * q);                          // sqrt(S) = S rsqrt(S): S >= eps > 0 here
     }
     const double psi = (S_eff <= 1.0) ? psi_unsat : psi_sat;
     const double Kr = (S_K < 1.0) ? Kr_unsat : 1.0;

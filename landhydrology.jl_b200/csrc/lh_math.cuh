@@ -157,26 +157,31 @@ LH_DEV double lh_exp2m1(const double* __restrict__ lh_c, const double* __restric
     return lh_fma(e.s, e.p, e.s - 1.0);
 }
 
+// 1 - 2^x, same accuracy.  Its zero is +0 (fma(-1, 0, +0)), never -0, which lh_log2 would flag as negative.
+LH_DEV double lh_one_minus_exp2(const double* __restrict__ lh_c, const double* __restrict__ tab, double x)
+{
+    const LhExpParts e = lh_exp2_parts(lh_c, tab, x);
+    return lh_fma(-e.s, e.p, 1.0 - e.s);
+}
+
 // ---------------------------------------------------------------------------------------------------
 // log2(x), table driven (Tang): x = 2^e m, m in [0.709, 1.418); j = top 7 bits of m's position in
 // that range; t = m r_j - 1 by ONE FMA (|t| <= 2^-8, relative error 2^-53 whatever r_j's rounding was);
 //   log2 x = (e + L_j) + t Q(t),  L_j = -log2 r_j,  Q of degree 5.
 // The interval around m = 1 has r = 1, L = 0 exactly, so the RELATIVE accuracy is kept as x -> 1 (the
 // closures need log2 S for S -> 1-).  8 fp64 operations, no division.
-// CHECK: x < 0, NaN (and +inf) -> NaN.  x == 0 and subnormals read as 2^-1023 m: log2(0) ~ -1023 instead of
+// CHECK: x < 0, -0.0, NaN (and +inf) -> NaN.  x == +0 and subnormals read as 2^-1023 m: log2(0) ~ -1023 instead of
 // -inf, which is what the closures need (exp2 of it underflows; nothing tests for -inf).
 // ---------------------------------------------------------------------------------------------------
 template <bool CHECK = true>
 LH_DEV double lh_log2(const double* __restrict__ lh_c, const double* __restrict__ tab, double x)
 {
-    int32_t hi = lh_hi(x) & 0x7fffffff;      // log|x|; the sign only matters for the NaN flag below
-    const int32_t lo = lh_lo(x);
-    // exponent such that the mantissa lands in [sqrt(1/2), sqrt(2))
-    const int32_t off = hi - LH_LOG_HI0;
+    // exponent such that the mantissa lands in [0.709, 1.418), and the interval index of that mantissa.
+    // No sign masking: for a negative x everything below stays finite garbage and the flag overrides it.
+    const int32_t off = lh_hi(x) - LH_LOG_HI0;
     const int32_t e = off >> 20;
     const int32_t j = (off >> LH_LOG_SHIFT) & (LH_LOG_TAB - 1);
-    hi -= e << 20;
-    const double m = lh_mk(hi, lo);
+    const double m = lh_mk(LH_LOG_HI0 + (off & 0xfffff), lh_lo(x));
 #ifdef LH_MATH_HOST
     const double r = tab[LH_TAB_LOG + 2 * j], L = tab[LH_TAB_LOG + 2 * j + 1];
 #else
@@ -192,11 +197,8 @@ LH_DEV double lh_log2(const double* __restrict__ lh_c, const double* __restrict_
     Q = lh_fma(Q, t, lh_c[LHC_LOG_Q0]);
     const double y = lh_fma(t, Q, (double)e + L);
     if (!CHECK) return y;
-    // x < 0, NaN, +inf: force NaN with integer compares on the high word (cheaper than an fp64
-    // compare, which occupies the fp64 pipe).  -0.0 (high word exactly 0x80000000: the closures
-    // produce it as -(exp2m1(0))) is NOT flagged: like +0 it yields a huge negative finite value.
-    const uint32_t xh = (uint32_t)lh_hi(x);
-    const bool bad = (xh > 0x80000000u) || (xh - 0x7ff00000u < 0x00100000u);
-    const int32_t yhi = bad ? 0x7ff80000 : lh_hi(y);
-    return lh_mk(yhi, lh_lo(y));
+    // sign bit set (x < 0, and -0.0: callers form 1 - 2^u with lh_one_minus_exp2, whose zero is +0), NaN,
+    // +inf: force NaN with ONE unsigned compare on the high word (an fp64 compare occupies the fp64 pipe).
+    const bool bad = (uint32_t)lh_hi(x) > 0x7fefffffu;
+    return lh_mk(bad ? 0x7ff80000 : lh_hi(y), lh_lo(y));
 }

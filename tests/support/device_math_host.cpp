@@ -8,6 +8,7 @@ extern "C" {
 void lhm_log2(const double* x, double* y, long n) { for (long i = 0; i < n; ++i) y[i] = lh_log2(lh_c_host, lh_c_host + LHC_TAB0, x[i]); }
 void lhm_exp2(const double* x, double* y, long n) { for (long i = 0; i < n; ++i) y[i] = lh_exp2(lh_c_host, lh_c_host + LHC_TAB0, x[i]); }
 void lhm_exp2m1(const double* x, double* y, long n) { for (long i = 0; i < n; ++i) y[i] = lh_exp2m1(lh_c_host, lh_c_host + LHC_TAB0, x[i]); }
+void lhm_one_minus_exp2(const double* x, double* y, long n) { for (long i = 0; i < n; ++i) y[i] = lh_one_minus_exp2(lh_c_host, lh_c_host + LHC_TAB0, x[i]); }
 void lhm_sqrt(const double* x, double* y, long n) { for (long i = 0; i < n; ++i) y[i] = lh_sqrt(x[i]); }
 void lhm_rsqrt(const double* x, double* y, long n) { for (long i = 0; i < n; ++i) y[i] = lh_rsqrt(x[i]); }
 void lhm_rcp(const double* x, double* y, long n) { for (long i = 0; i < n; ++i) y[i] = lh_rcp(x[i]); }

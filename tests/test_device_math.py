@@ -61,7 +61,10 @@ def test_log2(mathlib):
     assert err.max() <= 2.0, err.max()
     sp = _call(mathlib, "lhm_log2", np.array([0.0, -1.0, np.inf, np.nan, -0.5, -0.0]))
     assert -1024 < sp[0] < -1022 and np.isnan(sp[1]) and np.isnan(sp[2]) and np.isnan(sp[3]) and np.isnan(sp[4])
-    assert np.isfinite(sp[5]) and sp[5] < -1000     # -0.0 reads as a huge negative number, like +0
+    assert np.isnan(sp[5])      # -0.0 is flagged like any negative number: the closures form 1 - 2^u with
+                                # lh_one_minus_exp2, whose zero is +0
+    z = _call(mathlib, "lhm_one_minus_exp2", np.array([0.0, -0.0, -1.0, 1.0]))
+    assert z[0] == 0.0 and not np.signbit(z[0]) and not np.signbit(z[1]) and z[2] == 0.5 and z[3] == -1.0
 
 
 def test_exp2_and_exp2m1(mathlib):
