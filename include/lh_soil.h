@@ -205,6 +205,43 @@ int32_t lh_soil_stage_ssprk33(lh_soil_ctx* ctx, int32_t stage, double dt);
 int32_t lh_soil_step_ssprk33(lh_soil_ctx* ctx, double t, double dt, int64_t nsteps,
                              const double* bc_table);
 
+/* ---- other explicit steppers on the same fused kernel ----------------------------------
+ * The reference's test driver also imports SSPRK73 and CarpenterKennedy2N54 next to SSPRK33
+ * (test/runtests.jl:5-10); only SSPRK33 is ever used.  The fused RHS+stage kernel generalises by
+ * coefficients to the two low-storage families those methods belong to, each stage still ONE launch:
+ *   LH_STEPPER_SHU_OSHER  two-register Shu-Osher form
+ *        u_i = a[i] u^n + b[i] u_{i-1} + g[i] dt f(u_{i-1}, t + c[i] dt),  u_0 = u^n,  u^{n+1} = u_s
+ *        (Euler, SSPRK22, SSPRK33, SSPRK43, any method whose stages only need u^n and u_{i-1})
+ *   LH_STEPPER_2N         Williamson 2N storage
+ *        r = a[i] r + dt f(u, t + c[i] dt);   u = u + b[i] r          (a[0] must be 0)
+ *        (CarpenterKennedy2N54 and the other LowStorageRK2N methods of OrdinaryDiffEq)
+ * SSPRK73's coefficients are numerically optimised constants that live only in OrdinaryDiffEq (not
+ * vendored under the reference): a Julia host passes them through this table API. */
+#define LH_MAX_STAGES        16
+#define LH_STEPPER_SHU_OSHER 0
+#define LH_STEPPER_2N        1
+typedef struct lh_soil_stepper {
+    int32_t kind;                 /* LH_STEPPER_*                                   */
+    int32_t nstages;              /* 1 .. LH_MAX_STAGES                             */
+    double  a[LH_MAX_STAGES];
+    double  b[LH_MAX_STAGES];
+    double  g[LH_MAX_STAGES];     /* Shu-Osher only                                 */
+    double  c[LH_MAX_STAGES];     /* stage time offsets: row s of bc_table is for t + c[s] dt */
+} lh_soil_stepper;
+
+/* Built-in tables (OrdinaryDiffEq names). */
+#define LH_METHOD_EULER    0
+#define LH_METHOD_SSPRK22  1
+#define LH_METHOD_SSPRK33  2      /* same scheme as lh_soil_step_ssprk33, through the generic stage kernel */
+#define LH_METHOD_SSPRK43  3
+#define LH_METHOD_CK2N54   4      /* CarpenterKennedy2N54 */
+int32_t lh_soil_stepper_named(int32_t method, lh_soil_stepper* out);
+
+/* nsteps steps of `stepper`.  bc_table is NULL or nsteps * nstages * 4 doubles (LH_BCV_* per stage).
+ * Replaces step!/run! for a Simulation built with another OrdinaryDiffEq method (simulation.jl:34-87). */
+int32_t lh_soil_step(lh_soil_ctx* ctx, const lh_soil_stepper* stepper, double t, double dt,
+                     int64_t nsteps, const double* bc_table);
+
 /* ---- diagnostics ---------------------------------------------------------------------
  * Water and energy budgets of THIS ctx's columns: out[0] = sum ϑ_l Δz, out[1] = sum ρe_int Δz
  * (deterministic fixed-tree reduction).  New in this build.                     */

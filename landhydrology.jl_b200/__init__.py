@@ -59,7 +59,8 @@ from .parameterizations import *  # noqa: F401,F403  (the reference exports ever
 from .parameterizations import EarthParameterSet
 from .rhs import make_rhs, make_update_aux
 from .sharding import ColumnShards, init_budget_comm, shard_range
-from .simulations import SSPRK33, Simulation, run_, step_
+from .simulations import (SSPRK22, SSPRK33, SSPRK43, CarpenterKennedy2N54, Euler, LowStorageRK2N, ShuOsherRK,
+                          Simulation, run_, step_)
 from .states import (
     FieldVector,
     NamedFields,

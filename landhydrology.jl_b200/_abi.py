@@ -102,6 +102,19 @@ class lh_soil_config(C.Structure):
     ]
 
 
+LH_MAX_STAGES = 16
+LH_STEPPER_SHU_OSHER, LH_STEPPER_2N = 0, 1
+LH_METHOD_EULER, LH_METHOD_SSPRK22, LH_METHOD_SSPRK33, LH_METHOD_SSPRK43, LH_METHOD_CK2N54 = 0, 1, 2, 3, 4
+
+
+class lh_soil_stepper(C.Structure):
+    _fields_ = [
+        ("kind", C.c_int32), ("nstages", C.c_int32),
+        ("a", C.c_double * LH_MAX_STAGES), ("b", C.c_double * LH_MAX_STAGES),
+        ("g", C.c_double * LH_MAX_STAGES), ("c", C.c_double * LH_MAX_STAGES),
+    ]
+
+
 _dp = C.POINTER(C.c_double)
 _vp = C.c_void_p
 
@@ -120,6 +133,8 @@ _SIGNATURES = {
     "soil_get_tendency": ([_vp, C.c_int32, _dp, C.c_int64, C.c_int64], C.c_int32),
     "soil_stage_ssprk33": ([_vp, C.c_int32, C.c_double], C.c_int32),
     "soil_step_ssprk33": ([_vp, C.c_double, C.c_double, C.c_int64, _dp], C.c_int32),
+    "soil_stepper_named": ([C.c_int32, C.POINTER(lh_soil_stepper)], C.c_int32),
+    "soil_step": ([_vp, C.POINTER(lh_soil_stepper), C.c_double, C.c_double, C.c_int64, _dp], C.c_int32),
     "soil_budgets": ([_vp, _dp], C.c_int32),
     "soil_diagnostic": ([_vp, C.c_int32, _dp, C.c_int64, C.c_int64], C.c_int32),
     "soil_sync": ([_vp], C.c_int32),
@@ -311,6 +326,18 @@ class SoilContext:
         else:
             ptr = None
         self._check(self.lib.soil_step_ssprk33(self._h, float(t), float(dt), int(nsteps), ptr))
+
+    def step_with(self, stepper: "lh_soil_stepper", t: float, dt: float, nsteps: int = 1,
+                  bc_table: Optional[np.ndarray] = None):
+        """``lh_soil_step``: nsteps of a Shu-Osher / 2N low-storage stepper (one launch per stage)."""
+        if bc_table is not None:
+            bc_table = np.ascontiguousarray(bc_table, dtype=np.float64)
+            if bc_table.size != nsteps * stepper.nstages * 4:
+                raise ValueError("bc_table must hold nsteps*nstages*4 doubles")
+            ptr = _as_double_ptr(bc_table)
+        else:
+            ptr = None
+        self._check(self.lib.soil_step(self._h, C.byref(stepper), float(t), float(dt), int(nsteps), ptr))
 
     def budgets(self) -> np.ndarray:
         out = np.empty(2, dtype=np.float64)

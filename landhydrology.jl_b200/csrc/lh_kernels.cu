@@ -47,7 +47,7 @@ LhLaunchShape lh_choose_shape(int model, int64_t ncol_pad, int32_t nlayer, int s
     s.Lc = Lc; s.W = W; s.G = G;
     s.nblocks = (groups + G - 1) / G;
     const int nq = model == LH_MODEL_COUPLED ? 5 : 2;
-    s.smem_bytes = (LH_TAB_DOUBLES + (size_t)G * W * ((2 * nq + 4) * 32 + 4 * 5 * 32)) * sizeof(double);   // + cp.async input ring
+    s.smem_bytes = (LH_TAB_DOUBLES + (size_t)G * W * ((2 * nq + 6) * 32 + 4 * 5 * 32)) * sizeof(double);   // + cp.async input ring
     return s;
 }
 

@@ -13,9 +13,6 @@
 #ifndef LH_ILP2
 #define LH_ILP2 0      // 1: issue both cells' loads before either closure chain (measured: no gain)
 #endif
-#ifndef LH_LDG_PIPE
-#define LH_LDG_PIPE 0
-#endif
 #ifndef LH_MIN_BLOCKS
 #define LH_MIN_BLOCKS 5
 #endif
@@ -45,6 +42,8 @@ struct LhKernelArgs {
     const double* u0_re;
     double* out_th;        // V (stage 1, 2) / U (stage 3) / tendency buffer (stage 0)
     double* out_re;
+    double* out2_th;       // 2N stages (STAGE 5): the residual register r, updated in place (== u0_th)
+    double* out2_re;
     const double* zc;      // nlayer centre coordinates
     int64_t ncol_pad;
     int32_t nlayer;
@@ -53,6 +52,9 @@ struct LhKernelArgs {
     int32_t top_e_kind, top_h_kind, bot_e_kind, bot_h_kind;
     double bcv[4];         // LH_BCV_* boundary values for THIS launch
     double dt;
+    double sa, sb, sg;     // stage coefficients of the generic steppers (STAGE 4: a, b, g; STAGE 5: a, b)
+    int32_t first2n;       // STAGE 5, first stage: r is not read (a == 0 and r may hold anything)
+    int32_t pad_;
 };
 
 struct LhLaunchShape {
@@ -63,7 +65,7 @@ struct LhLaunchShape {
 
 LhLaunchShape lh_choose_shape(int model, int64_t ncol_pad, int32_t nlayer, int sm_count);
 
-// stage 0 = tendency only; 1..3 = fused RHS + SSPRK33 stage.  flags: LH_FLAG_ICE | LH_FLAG_GEN
+// stage 0 = tendency only; 1..3 = fused RHS + SSPRK33 stage; 4 = generic Shu-Osher stage; 5 = 2N stage.  flags: LH_FLAG_ICE | LH_FLAG_GEN
 // (lh_closures.cuh) select the compiled kernel variant.
 cudaError_t lh_launch_stage(int model, int stage, int flags, const LhKernelArgs& args,
                             const LhLaunchShape& shape, cudaStream_t stream);

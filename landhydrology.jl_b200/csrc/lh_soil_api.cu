@@ -390,6 +390,11 @@ void fill_args(lh_soil_ctx* c, int stage, double dt, LhKernelArgs& a)
     a.bot_h_kind = c->cfg.bottom.hydrology_kind;
     memcpy(a.bcv, c->bcv, sizeof a.bcv);
     a.dt = dt;
+    a.out2_th = c->V[0];
+    a.out2_re = c->V[2];
+    a.sa = 0.0; a.sb = 1.0; a.sg = 1.0;
+    a.first2n = 0;
+    a.pad_ = 0;
 }
 
 int32_t check_finite(lh_soil_ctx* c)
@@ -632,6 +637,106 @@ int32_t lh_soil_step_ssprk33(lh_soil_ctx* c, double t, double dt, int64_t nsteps
     LH_CUDA(c, cudaEventRecord(c->ev_stop, c->stream));
     c->timing_valid = true;
     c->last_launches = 3 * nsteps;
+    if (c->cfg.flags & LH_FLAG_CHECK_FINITE) return check_finite(c);
+    return LH_OK;
+}
+
+// Built-in tables.  Euler; SSPRK22 / SSPRK33 (Shu & Osher 1988); SSPRK43 (the 4-stage, third-order SSP
+// method with SSP coefficient 2); CarpenterKennedy2N54 (Carpenter & Kennedy 1994, the (5,4) 2N scheme).
+int32_t lh_soil_stepper_named(int32_t method, lh_soil_stepper* out)
+{
+    if (!out) return LH_ERR_INVALID_ARG;
+    lh_soil_stepper s;
+    memset(&s, 0, sizeof s);
+    auto so = [&](int i, double a, double b, double g, double cc) { s.a[i] = a; s.b[i] = b; s.g[i] = g; s.c[i] = cc; };
+    switch (method) {
+    case LH_METHOD_EULER:
+        s.kind = LH_STEPPER_SHU_OSHER; s.nstages = 1;
+        so(0, 0.0, 1.0, 1.0, 0.0);
+        break;
+    case LH_METHOD_SSPRK22:
+        s.kind = LH_STEPPER_SHU_OSHER; s.nstages = 2;
+        so(0, 0.0, 1.0, 1.0, 0.0);
+        so(1, 0.5, 0.5, 0.5, 1.0);
+        break;
+    case LH_METHOD_SSPRK33:
+        s.kind = LH_STEPPER_SHU_OSHER; s.nstages = 3;
+        so(0, 0.0, 1.0, 1.0, 0.0);
+        so(1, 0.75, 0.25, 0.25, 1.0);
+        so(2, 1.0 / 3.0, 2.0 / 3.0, 2.0 / 3.0, 0.5);
+        break;
+    case LH_METHOD_SSPRK43:
+        s.kind = LH_STEPPER_SHU_OSHER; s.nstages = 4;
+        so(0, 0.0, 1.0, 0.5, 0.0);
+        so(1, 0.0, 1.0, 0.5, 0.5);
+        so(2, 2.0 / 3.0, 1.0 / 3.0, 1.0 / 6.0, 1.0);
+        so(3, 0.0, 1.0, 0.5, 0.5);
+        break;
+    case LH_METHOD_CK2N54: {
+        static const double A[5] = {0.0, -567301805773.0 / 1357537059087.0, -2404267990393.0 / 2016746695238.0,
+                                    -3550918686646.0 / 2091501179385.0, -1275806237668.0 / 842570457699.0};
+        static const double B[5] = {1432997174477.0 / 9575080441755.0, 5161836677717.0 / 13612068292357.0,
+                                    1720146321549.0 / 2090206949498.0, 3134564353537.0 / 4481467310338.0,
+                                    2277821191437.0 / 14882151754819.0};
+        static const double Cc[5] = {0.0, 1432997174477.0 / 9575080441755.0, 2526269341429.0 / 6820363962896.0,
+                                     2006345519317.0 / 3224310063776.0, 2802321613138.0 / 2924317926251.0};
+        s.kind = LH_STEPPER_2N; s.nstages = 5;
+        for (int i = 0; i < 5; ++i) { s.a[i] = A[i]; s.b[i] = B[i]; s.c[i] = Cc[i]; }
+        break;
+    }
+    default:
+        return fail(nullptr, LH_ERR_INVALID_ARG, "unknown stepper method %d", method);
+    }
+    *out = s;
+    return LH_OK;
+}
+
+int32_t lh_soil_step(lh_soil_ctx* c, const lh_soil_stepper* sp, double t, double dt, int64_t nsteps, const double* bc_table)
+{
+    (void)t;
+    if (!c || !sp) return LH_ERR_INVALID_ARG;
+    if (nsteps < 0) return fail(c, LH_ERR_INVALID_ARG, "nsteps < 0");
+    if (sp->nstages < 1 || sp->nstages > LH_MAX_STAGES) return fail(c, LH_ERR_INVALID_ARG, "stepper.nstages must be 1..%d", LH_MAX_STAGES);
+    if (sp->kind != LH_STEPPER_SHU_OSHER && sp->kind != LH_STEPPER_2N) return fail(c, LH_ERR_INVALID_ARG, "unknown stepper kind %d", sp->kind);
+    if (sp->kind == LH_STEPPER_2N && sp->a[0] != 0.0) return fail(c, LH_ERR_INVALID_ARG, "a 2N scheme needs a[0] == 0");
+    LH_CUDA(c, cudaSetDevice(c->device));
+    const int ns = sp->nstages;
+    LH_CUDA(c, cudaEventRecord(c->ev_start, c->stream));
+    for (int64_t s = 0; s < nsteps; ++s) {
+        for (int i = 0; i < ns; ++i) {
+            if (bc_table) memcpy(c->bcv, bc_table + (s * ns + i) * 4, sizeof c->bcv);
+            LhKernelArgs a;
+            int stage;
+            if (sp->kind == LH_STEPPER_SHU_OSHER) {
+                // u_i = a u^n + b u_{i-1} + g dt f(u_{i-1}); first stage reads U, the last writes U, the
+                // stage register is V.  A stage with a == 0, b == 1 is a plain forward-Euler update and
+                // takes the STAGE 1 kernel (no u^n read) with dt scaled by g.
+                const bool first = i == 0, last = i == ns - 1;
+                const bool euler = sp->a[i] == 0.0 && sp->b[i] == 1.0;
+                stage = euler ? 1 : 4;
+                fill_args(c, stage, euler ? sp->g[i] * dt : dt, a);
+                a.in_th = (!first && has_water(c->model)) ? c->V[0] : c->U[0];
+                a.in_re = (!first && has_heat(c->model)) ? c->V[2] : c->U[2];
+                a.out_th = last ? c->U[0] : c->V[0];
+                a.out_re = last ? c->U[2] : c->V[2];
+                a.sa = sp->a[i]; a.sb = sp->b[i]; a.sg = sp->g[i];
+            } else {
+                // r = a r + dt f(u); u = u + b r: reads and writes U (u) and V (r) in place
+                stage = 5;
+                fill_args(c, stage, dt, a);
+                a.in_th = c->U[0]; a.in_re = c->U[2];
+                a.u0_th = c->V[0]; a.u0_re = c->V[2];
+                a.out_th = c->U[0]; a.out_re = c->U[2];
+                a.out2_th = c->V[0]; a.out2_re = c->V[2];
+                a.sa = sp->a[i]; a.sb = sp->b[i];
+                a.first2n = i == 0;
+            }
+            LH_CUDA(c, lh_launch_stage(c->model, stage, c->kernel_flags, a, c->shape, c->stream));
+        }
+    }
+    LH_CUDA(c, cudaEventRecord(c->ev_stop, c->stream));
+    c->timing_valid = true;
+    c->last_launches = ns * nsteps;
     if (c->cfg.flags & LH_FLAG_CHECK_FINITE) return check_finite(c);
     return LH_OK;
 }

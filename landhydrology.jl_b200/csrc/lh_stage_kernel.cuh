@@ -100,40 +100,46 @@ __device__ __forceinline__ Flux boundary_flux(const LhDevParams& p, const double
     return f;
 }
 
+// STAGE: 0 tendency; 1, 2, 3 the SSPRK33 stages; 4 a generic two-register Shu-Osher stage
+// (a u^n + b u_{i-1} + g dt f); 5 a Williamson 2N stage (r = a r + dt f, u = u + b r), include/lh_soil.h.
 template <int STAGE>
-__device__ __forceinline__ double stage_base(double v, double u0)
+__device__ __forceinline__ double stage_base(const LhKernelArgs& A, double v, double u0)
 {
     if constexpr (STAGE == 2) return fma(3.0, u0, v);       // 3 u0 + u1
     else if constexpr (STAGE == 3) return fma(2.0, v, u0);  // u0 + 2 u2
+    else if constexpr (STAGE == 4) return fma(A.sa, u0, A.sb * v);
+    else if constexpr (STAGE == 5) return A.first2n ? 0.0 : A.sa * u0;   // a r (r is not read as a number in the first stage)
     else return v;
 }
 
 // Stage combine with the flux-form divergence folded in:  k = -(F_hi - F_lo)/dz and
-//   stage 0: k     1: base + dt k     2: (base + dt k)/4     3: (base + 2 dt k)/3
-// are evaluated as  s (base + cdt (F_hi - F_lo))  with cdt = -dt/dz (stage 3: -2 dt/dz; stage 0: -1/dz).
+//   stage 0: k     1: base + dt k     2: (base + dt k)/4     3: (base + 2 dt k)/3     4: base + g dt k     5: base + dt k
+// are evaluated as  s (base + cdt (F_hi - F_lo))  with cdt = -dt/dz (stage 3: -2 dt/dz; stage 0: -1/dz; stage 4: -g dt/dz).
 template <int STAGE>
 __device__ __forceinline__ double stage_out(double base, double dF, double cdt)
 {
     if constexpr (STAGE == 0) return cdt * dF;
-    else if constexpr (STAGE == 1) return fma(cdt, dF, base);
+    else if constexpr (STAGE == 1 || STAGE == 4 || STAGE == 5) return fma(cdt, dF, base);
     else if constexpr (STAGE == 2) return 0.25 * fma(cdt, dF, base);
     else return (1.0 / 3.0) * fma(cdt, dF, base);
 }
 
-struct Base { double th, re; };
+struct Base { double th, re, th2, re2; };   // th2/re2: the state itself, 2N stages only
 struct Raw { double th, ti, x, u0th, u0re; };
 template <int MODEL> struct Cell { Q<MODEL> q; Base base; };
 
-// Shared-memory slot of one (column group, chunk): [bot: NQ][top: NQ][pending: 4], each x32 lanes.
+// Shared-memory slot of one (column group, chunk): [bot: NQ][top: NQ][pending: 6], each x32 lanes.
 // Input ring (cp.async): RING_DEPTH cells x RING_FIELDS fields x 32 lanes per warp.
 constexpr int RING_DEPTH = 4, RING_FIELDS = 5, RING_DOUBLES = RING_DEPTH * RING_FIELDS * 32;
 constexpr uint32_t RING_CELL_BYTES = RING_FIELDS * 256;
 
-template <int MODEL> struct Slot { static constexpr int NQv = NQ<MODEL>::value; static constexpr int doubles = (2 * NQv + 4) * 32; };
+template <int MODEL> struct Slot { static constexpr int NQv = NQ<MODEL>::value; static constexpr int doubles = (2 * NQv + 6) * 32; };
 
-__device__ __forceinline__ void lh_cp8(uint32_t dst, const double* src)
+// 16-byte cp.async that bypasses L1 (.cg): global -> shared without allocating an L1 line while in flight.
+__device__ __forceinline__ void lh_cp16(uint32_t dst, const double* src, bool pred)
 {
-    asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(dst), "l"(src) : "memory");
+    asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %2, 0;\n\t@p cp.async.cg.shared.global [%0], [%1], 16;\n\t}"
+                 ::"r"(dst), "l"(src), "r"((int)pred) : "memory");
 }
 template <int OFF>
 __device__ __forceinline__ double lh_lds(uint32_t addr)
@@ -176,57 +182,77 @@ lh_soil_stage_kernel(const __grid_constant__ LhKernelArgs A)
     double* slot = warp_base + lane;
     double* sm_bot = slot;                               // Q of the chunk's first cell
     double* sm_top = slot + NQv * 32;                    // Q of the chunk's last cell
-    double* sm_pend = slot + 2 * NQv * 32;               // base.th, base.re, F_first_up.w, F_first_up.e
-    const uint32_t ring_s = (uint32_t)__cvta_generic_to_shared(warp_base + Slot<MODEL>::doubles + lane);   // [RING_DEPTH][RING_FIELDS][32]
+    double* sm_pend = slot + 2 * NQv * 32;               // base.th, base.re, F_first_up.w, F_first_up.e, base.th2, base.re2
     __syncthreads();
 
-    // Stage 2 reads and writes V, stage 3 reads U (as u0) and writes it (lh_soil_api.cu fill_args): the
-    // store addresses are formed from the same base registers as the loads.
     const double* pth = A.in_th + col;
     const double* pti = A.in_ti + col;
-    const double* pre = A.in_re + col;
     const double* pT = A.aux_T + col;
-    const double* p0th = A.u0_th + col;
-    const double* p0re = A.u0_re + col;
-    double* oth = STAGE == 2 ? const_cast<double*>(pth) : STAGE == 3 ? const_cast<double*>(p0th) : A.out_th + col;
-    double* ore = STAGE == 2 ? const_cast<double*>(pre) : STAGE == 3 ? const_cast<double*>(p0re) : A.out_re + col;
+    double* oth = A.out_th + col;
+    double* ore = A.out_re + col;
 
     // Input pipeline.  The raw values of cell i travel global -> shared with cp.async (LDGSTS): no
     // registers are held while the copy is in flight (a register software pipeline was tried: ptxas
     // sinks such loads down to the next possibly-aliasing store and spills them; prefetch.global.L1
-    // was tried too and only reaches L2 on this part — 3 % L1 hit rate, profiles/r01_d_*).  Each lane
-    // copies and later reads back only ITS OWN 8 bytes, so cp.async.wait_group is the only
-    // synchronisation needed.  Ring of RING_DEPTH cells; one commit group per cell, always committed
-    // (empty past the end of the chunk) so that wait_group's constant stays valid.  Cell a + k sits in
-    // ring cell k mod 4; the layer loop handles two cells per trip, so its ring cells are a PAIR
-    // (0,1) or (2,3) and every ring address is `pair base + constant`; the pair base toggles with one
-    // subtraction per trip.
+    // was tried too and only reaches L2 on this part — 3 % L1 hit rate, profiles/r01_d_*).
+    // One field of one layer is a 256-byte row (32 columns); every lane copies 16 bytes, so ONE
+    // instruction moves two rows (lanes 0-15 the first, lanes 16-31 the second) and the copy can take
+    // the L1-bypassing .cg path: with 8-byte .ca copies the ~60 KB in flight per SM had to be resident
+    // in L1, which shrinks to 22 KB once five blocks' shared memory is carved out.  A lane later reads
+    // back values copied by OTHER lanes, hence the __syncwarp after cp.async.wait_group.
+    // Ring of RING_DEPTH cells; one commit group per cell, always committed (empty past the end of the
+    // chunk) so that wait_group's constant stays valid.  Cell a + k sits in ring cell k mod 4; the layer
+    // loop handles two cells per trip, so its ring cells are a PAIR (0,1) or (2,3) and every ring address
+    // is `pair base + constant`; the pair base toggles with one subtraction per trip.
+    constexpr bool HAS_X = MODEL != 0 || (FLAGS & LH_FLAG_GEN) != 0;       // ρe_int, or the prescribed T
+    constexpr int NROWS = 1 + (ICE ? 1 : 0) + (HAS_X ? 1 : 0) + ((STAGE >= 2 && MODEL != 1) ? 1 : 0) + ((STAGE >= 2 && MODEL != 0) ? 1 : 0);
+    constexpr int NG = (NROWS + 1) / 2;
+    const double* rowptr[5];
+    int rowpos[5];                            // position of the row inside a ring cell: th 0, ti 1, x 2, u0th 3, u0re 4
+    {
+        int k = 0;
+        rowptr[k] = A.in_th; rowpos[k++] = 0;
+        if (ICE) { rowptr[k] = A.in_ti; rowpos[k++] = 1; }
+        if (HAS_X) { rowptr[k] = MODEL != 0 ? A.in_re : A.aux_T; rowpos[k++] = 2; }
+        if (STAGE >= 2 && MODEL != 1) { rowptr[k] = A.u0_th; rowpos[k++] = 3; }
+        if (STAGE >= 2 && MODEL != 0) { rowptr[k] = A.u0_re; rowpos[k++] = 4; }
+    }
+    const bool upper = lane >= 16;
+    const int sub = lane & 15;
+    const double* sp[NG];                     // this lane's source (column pair) of copy instruction g, layer 0
+    uint32_t doff[NG];                        // and its destination offset inside a ring cell
+    bool pred[NG];
+#pragma unroll
+    for (int gi = 0; gi < NG; ++gi) {
+        const int lo = 2 * gi, hi = 2 * gi + 1 < NROWS ? 2 * gi + 1 : 2 * gi;
+        sp[gi] = (upper ? rowptr[hi] : rowptr[lo]) + col0 + 2 * sub;
+        doff[gi] = (uint32_t)((upper ? rowpos[hi] : rowpos[lo]) * 256 + sub * 16);
+        pred[gi] = !upper || 2 * gi + 1 < NROWS;
+    }
+    const uint32_t ring_w = (uint32_t)__cvta_generic_to_shared(warp_base + Slot<MODEL>::doubles);   // warp's ring, lane 0
     int64_t o_ld = (int64_t)a * stride;       // element offset of the next cell to request
-    auto issue = [&](uint32_t d, int i) {     // request cell i (whose offset o_ld is) into ring address d
+    auto issue = [&](uint32_t d, int i) {     // request cell i (whose offset o_ld is) into the ring cell at d (lane-0 address)
         if (i < b) {
-            lh_cp8(d, pth + o_ld);
-            if (ICE) lh_cp8(d + 256, pti + o_ld);
-            if (MODEL != 0) lh_cp8(d + 512, pre + o_ld);
-            else if (need_T) lh_cp8(d + 512, pT + o_ld);
-            if constexpr (STAGE >= 2) {
-                if constexpr (MODEL != 1) lh_cp8(d + 768, p0th + o_ld);
-                if constexpr (MODEL != 0) lh_cp8(d + 1024, p0re + o_ld);
-            }
+#pragma unroll
+            for (int gi = 0; gi < NG; ++gi) lh_cp16(d + doff[gi], sp[gi] + o_ld, pred[gi]);
             o_ld += stride;
         }
         asm volatile("cp.async.commit_group;" ::: "memory");
     };
-    // wait for the oldest outstanding cell, read it from ring address d, then request cell i_next into d_next
+    // wait for the oldest outstanding cell, read it from the ring cell at d, then request cell i_next into d_next
+    const uint32_t lane8 = (uint32_t)lane * 8;
     auto load_raw = [&](uint32_t d, uint32_t d_next, int i_next) {
         asm volatile("cp.async.wait_group %0;" ::"n"(RING_DEPTH - 2) : "memory");
+        __syncwarp();
+        const uint32_t dl = d + lane8;
         Raw r;
-        r.th = lh_lds<0>(d);
-        r.ti = ICE ? lh_lds<256>(d) : 0.0;
-        r.x = (MODEL != 0 || need_T) ? lh_lds<512>(d) : 288.0;
+        r.th = lh_lds<0>(dl);
+        r.ti = ICE ? lh_lds<256>(dl) : 0.0;
+        r.x = HAS_X ? lh_lds<512>(dl) : 288.0;
         r.u0th = 0.0; r.u0re = 0.0;
         if constexpr (STAGE >= 2) {
-            if constexpr (MODEL != 1) r.u0th = lh_lds<768>(d);
-            if constexpr (MODEL != 0) r.u0re = lh_lds<1024>(d);
+            if constexpr (MODEL != 1) r.u0th = lh_lds<768>(dl);
+            if constexpr (MODEL != 0) r.u0re = lh_lds<1024>(dl);
         }
         issue(d_next, i_next);
         return r;
@@ -240,105 +266,63 @@ lh_soil_stage_kernel(const __grid_constant__ LhKernelArgs A)
             o.q.K = c.K; o.q.psi = c.psi; o.q.kappa = c.kappa; o.q.T = c.T;
             o.q.eK = (p.rhocp_l * c.dT) * c.K;                               // ρe_int_l * K (:306, :364)
         }
-        o.base.th = (MODEL != 1) ? stage_base<STAGE>(r.th, r.u0th) : 0.0;
-        o.base.re = (MODEL != 0) ? stage_base<STAGE>(r.x, r.u0re) : 0.0;
+        o.base.th = (MODEL != 1) ? stage_base<STAGE>(A, r.th, r.u0th) : 0.0;
+        o.base.re = (MODEL != 0) ? stage_base<STAGE>(A, r.x, r.u0re) : 0.0;
+        o.base.th2 = (STAGE == 5 && MODEL != 1) ? r.th : 0.0;
+        o.base.re2 = (STAGE == 5 && MODEL != 0) ? r.x : 0.0;
         return o;
     };
-    const double cdt = STAGE == 0 ? -p.inv_dz : (STAGE == 3 ? -2.0 * (A.dt * p.inv_dz) : -(A.dt * p.inv_dz));
+    const double cdt = STAGE == 0 ? -p.inv_dz : (STAGE == 3 ? -2.0 * (A.dt * p.inv_dz) : STAGE == 4 ? -((A.sg * A.dt) * p.inv_dz) : -(A.dt * p.inv_dz));
+    double* o2th = A.out2_th + col;     // 2N stages: the residual register r
+    double* o2re = A.out2_re + col;
+    auto store_cell = [&](int64_t o, const Base& base, const Flux& lo, const Flux& hi) {
+        if constexpr (MODEL != 1) {
+            const double v = stage_out<STAGE>(base.th, hi.w - lo.w, cdt);
+            if constexpr (STAGE == 5) { o2th[o] = v; oth[o] = fma(A.sb, v, base.th2); }
+            else oth[o] = v;
+        }
+        if constexpr (MODEL != 0) {
+            const double v = stage_out<STAGE>(base.re, hi.e - lo.e, cdt);
+            if constexpr (STAGE == 5) { o2re[o] = v; ore[o] = fma(A.sb, v, base.re2); }
+            else ore[o] = v;
+        }
+    };
     int64_t o_st = (int64_t)(a + 1) * stride;   // element offset of the next cell to store (cell a is stored last)
     auto write_next = [&](const Base& base, const Flux& lo, const Flux& hi) {
-        if constexpr (MODEL != 1) oth[o_st] = stage_out<STAGE>(base.th, hi.w - lo.w, cdt);
-        if constexpr (MODEL != 0) ore[o_st] = stage_out<STAGE>(base.re, hi.e - lo.e, cdt);
+        store_cell(o_st, base, lo, hi);
         o_st += stride;
     };
     auto write_at = [&](int i, const Base& base, const Flux& lo, const Flux& hi) {
-        const int64_t o = (int64_t)i * stride;
-        if constexpr (MODEL != 1) oth[o] = stage_out<STAGE>(base.th, hi.w - lo.w, cdt);
-        if constexpr (MODEL != 0) ore[o] = stage_out<STAGE>(base.re, hi.e - lo.e, cdt);
+        store_cell((int64_t)i * stride, base, lo, hi);
     };
 
     Q<MODEL> prev;            // closures of the last evaluated cell
     Base base_prev;
     Flux F_below;
     F_below.w = F_below.e = 0.0;
-    base_prev.th = base_prev.re = 0.0;
+    base_prev.th = base_prev.re = base_prev.th2 = base_prev.re2 = 0.0;
 
-#if LH_LDG_PIPE
-    if (active) {
-        // Register pipeline: the inputs of cell i + 1 are requested (plain LDG) before cell i is evaluated and
-        // consumed one cell later; two cells per trip alternate between two fixed register sets.
-        auto ldg_raw = [&](int i) {
-            Raw r;
-            r.th = 0.0; r.ti = 0.0; r.x = 288.0; r.u0th = 0.0; r.u0re = 0.0;
-            if (i < b) {
-                r.th = pth[o_ld];
-                if (ICE) r.ti = pti[o_ld];
-                if (MODEL != 0) r.x = pre[o_ld];
-                else if (need_T) r.x = pT[o_ld];
-                if constexpr (STAGE >= 2) {
-                    if constexpr (MODEL != 1) r.u0th = p0th[o_ld];
-                    if constexpr (MODEL != 0) r.u0re = p0re[o_ld];
-                }
-                o_ld += stride;
-            }
-            return r;
-        };
-        int i = a;
-        Raw rA = ldg_raw(i);
-        Raw rB = ldg_raw(i + 1);
-        {   // first cell of the chunk: no face below it yet -> park what its update needs in shared memory
-            const Cell<MODEL> c = eval(rA);
-            rA = ldg_raw(i + 2);
-            q_store<MODEL>(sm_bot, c.q);
-            sm_pend[0] = c.base.th; sm_pend[32] = c.base.re;
-            prev = c.q; base_prev = c.base;
-            ++i;
-        }
-        if (i < b) {   // second cell: the face above the first cell
-            const Cell<MODEL> c = eval(rB);
-            const Flux F = face_flux<MODEL>(p, prev, c.q);
-            sm_pend[64] = F.w; sm_pend[96] = F.e;
-            F_below = F; prev = c.q; base_prev = c.base;
-            ++i;
-        }
-        for (; i + 1 < b; i += 2) {   // two cells per trip: no sliding-window register moves
-            rB = ldg_raw(i + 1);
-            const Cell<MODEL> c0 = eval(rA);
-            const Flux F0 = face_flux<MODEL>(p, prev, c0.q);
-            write_next(base_prev, F_below, F0);
-            rA = ldg_raw(i + 2);
-            const Cell<MODEL> c1 = eval(rB);
-            const Flux F1 = face_flux<MODEL>(p, c0.q, c1.q);
-            write_next(c0.base, F0, F1);
-            F_below = F1; prev = c1.q; base_prev = c1.base;
-        }
-        if (i < b) {   // odd tail
-            const Cell<MODEL> c = eval(rA);
-            const Flux F = face_flux<MODEL>(p, prev, c.q);
-            write_next(base_prev, F_below, F);
-            F_below = F; prev = c.q; base_prev = c.base;
-        }
-#else
     if (active) {
         constexpr uint32_t CB = RING_CELL_BYTES;
-        for (int k = 0; k < RING_DEPTH - 1; ++k) issue(ring_s + k * CB, a + k);
+        for (int k = 0; k < RING_DEPTH - 1; ++k) issue(ring_w + k * CB, a + k);
         int i = a;
         {   // first cell of the chunk: no face below it yet -> park what its update needs in shared memory
-            const Cell<MODEL> c = eval(load_raw(ring_s, ring_s + 3 * CB, i + 3));
+            const Cell<MODEL> c = eval(load_raw(ring_w, ring_w + 3 * CB, i + 3));
             q_store<MODEL>(sm_bot, c.q);
             sm_pend[0] = c.base.th; sm_pend[32] = c.base.re;
+            if constexpr (STAGE == 5) { sm_pend[128] = c.base.th2; sm_pend[160] = c.base.re2; }
             prev = c.q; base_prev = c.base;
             ++i;
         }
         if (i < b) {   // second cell: the face above the first cell
-            const Cell<MODEL> c = eval(load_raw(ring_s + CB, ring_s, i + 3));
+            const Cell<MODEL> c = eval(load_raw(ring_w + CB, ring_w, i + 3));
             const Flux F = face_flux<MODEL>(p, prev, c.q);
             sm_pend[64] = F.w; sm_pend[96] = F.e;
             F_below = F; prev = c.q; base_prev = c.base;
             ++i;
         }
-        uint32_t dA = ring_s + 2 * CB;                    // ring pair of cells (i, i + 1)
-        const uint32_t dsum = 2 * ring_s + 2 * CB;        // pair (0,1) base + pair (2,3) base
+        uint32_t dA = ring_w + 2 * CB;                    // ring pair of cells (i, i + 1)
+        const uint32_t dsum = 2 * ring_w + 2 * CB;        // pair (0,1) base + pair (2,3) base
         for (; i + 1 < b; i += 2) {   // two cells per trip: no sliding-window register moves
             const uint32_t dB = dsum - dA;                // the other pair: cells (i + 2, i + 3)
 #if LH_ILP2
@@ -368,7 +352,6 @@ lh_soil_stage_kernel(const __grid_constant__ LhKernelArgs A)
             write_next(base_prev, F_below, F);
             F_below = F; prev = c.q; base_prev = c.base;
         }
-#endif
         q_store<MODEL>(sm_top, prev);
     }
     __syncthreads();
@@ -401,6 +384,8 @@ lh_soil_stage_kernel(const __grid_constant__ LhKernelArgs A)
         }
         Base base_first;
         base_first.th = sm_pend[0]; base_first.re = sm_pend[32];
+        base_first.th2 = base_first.re2 = 0.0;
+        if constexpr (STAGE == 5) { base_first.th2 = sm_pend[128]; base_first.re2 = sm_pend[160]; }
         if (b - a == 1) {
             write_at(a, base_first, F_lo, F_hi);
         } else {
@@ -417,19 +402,34 @@ cudaError_t launch_variant(int stage, const LhKernelArgs& args, const LhLaunchSh
 {
     dim3 block(32, s.W, s.G);
     dim3 grid((unsigned)s.nblocks);
-    if (s.smem_bytes > 48 * 1024) {
+    // Once per variant and device: allow > 48 KB of dynamic shared memory, and ask for the largest shared
+    // memory carve-out.  Five resident blocks need 5 x (38.5 + 1) KB = 197.5 KB, just above the 196 KB
+    // configuration; left to its default the driver picks a smaller carve-out and only four blocks fit.
+    static int configured_smem[64];                      // per device ordinal: largest size configured so far
+    int dev = 0;
+    cudaGetDevice(&dev);
+    if (dev < 64 && configured_smem[dev] < (int)s.smem_bytes + 1) {
         cudaError_t e;
-        const int bytes = (int)s.smem_bytes;
-        if ((e = cudaFuncSetAttribute(lh_soil_stage_kernel<MODEL, 0, FLAGS>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes))) return e;
-        if ((e = cudaFuncSetAttribute(lh_soil_stage_kernel<MODEL, 1, FLAGS>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes))) return e;
-        if ((e = cudaFuncSetAttribute(lh_soil_stage_kernel<MODEL, 2, FLAGS>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes))) return e;
-        if ((e = cudaFuncSetAttribute(lh_soil_stage_kernel<MODEL, 3, FLAGS>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes))) return e;
+        const int bytes = (int)s.smem_bytes > 48 * 1024 ? (int)s.smem_bytes : 48 * 1024;
+        auto configure = [&](auto kernel) -> cudaError_t {
+            if ((e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes))) return e;
+            return cudaFuncSetAttribute(kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+        };
+        if ((e = configure(lh_soil_stage_kernel<MODEL, 0, FLAGS>))) return e;
+        if ((e = configure(lh_soil_stage_kernel<MODEL, 1, FLAGS>))) return e;
+        if ((e = configure(lh_soil_stage_kernel<MODEL, 2, FLAGS>))) return e;
+        if ((e = configure(lh_soil_stage_kernel<MODEL, 3, FLAGS>))) return e;
+        if ((e = configure(lh_soil_stage_kernel<MODEL, 4, FLAGS>))) return e;
+        if ((e = configure(lh_soil_stage_kernel<MODEL, 5, FLAGS>))) return e;
+        configured_smem[dev] = (int)s.smem_bytes + 1;
     }
     switch (stage) {
     case 0: lh_soil_stage_kernel<MODEL, 0, FLAGS><<<grid, block, s.smem_bytes, stream>>>(args); break;
     case 1: lh_soil_stage_kernel<MODEL, 1, FLAGS><<<grid, block, s.smem_bytes, stream>>>(args); break;
     case 2: lh_soil_stage_kernel<MODEL, 2, FLAGS><<<grid, block, s.smem_bytes, stream>>>(args); break;
     case 3: lh_soil_stage_kernel<MODEL, 3, FLAGS><<<grid, block, s.smem_bytes, stream>>>(args); break;
+    case 4: lh_soil_stage_kernel<MODEL, 4, FLAGS><<<grid, block, s.smem_bytes, stream>>>(args); break;
+    case 5: lh_soil_stage_kernel<MODEL, 5, FLAGS><<<grid, block, s.smem_bytes, stream>>>(args); break;
     default: return cudaErrorInvalidValue;
     }
     return cudaGetLastError();

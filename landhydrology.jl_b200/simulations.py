@@ -14,18 +14,97 @@ from typing import Callable, List, Optional, Sequence
 
 import numpy as np
 
+from . import _abi
 from .engine import SoilEngine, current_library
 from .models import AbstractModel, SoilModel
 from .states import FieldVector, copy as copy_state
 
 
-class SSPRK33:
-    """OrdinaryDiffEq's 3-stage, third-order SSP Runge-Kutta method (Shu-Osher form)."""
+class _Stepper:
+    """An explicit low-storage Runge-Kutta method that runs as one fused RHS+stage launch per stage.
 
-    stages = 3
+    ``table(lib)`` returns the ``lh_soil_stepper`` coefficient table (``None`` for SSPRK33, which has its own
+    specialised stage kernels); ``c`` are the stage time offsets the host needs to evaluate the Dirichlet
+    closures and prescribed profiles at ``t + c[i] dt``."""
+
+    method_id = None
+    c: Sequence[float] = ()
+
+    def table(self, lib):
+        tab = _abi.lh_soil_stepper()
+        st = lib.soil_stepper_named(self.method_id, tab)
+        if st != _abi.LH_OK:
+            raise ValueError(f"lh_soil_stepper_named({self.method_id}) failed with status {st}")
+        return tab
+
+    @property
+    def stages(self):
+        return len(self.c)
 
     def __repr__(self):
-        return "SSPRK33()"
+        return f"{type(self).__name__}()"
+
+
+class SSPRK33(_Stepper):
+    """OrdinaryDiffEq's 3-stage, third-order SSP Runge-Kutta method (Shu-Osher form): the only stepper the
+    reference's tests and experiment use."""
+
+    method_id = _abi.LH_METHOD_SSPRK33
+    c = (0.0, 1.0, 0.5)
+
+    def table(self, lib):
+        return None          # lh_soil_step_ssprk33: the specialised stage kernels
+
+
+class Euler(_Stepper):
+    method_id = _abi.LH_METHOD_EULER
+    c = (0.0,)
+
+
+class SSPRK22(_Stepper):
+    method_id = _abi.LH_METHOD_SSPRK22
+    c = (0.0, 1.0)
+
+
+class SSPRK43(_Stepper):
+    method_id = _abi.LH_METHOD_SSPRK43
+    c = (0.0, 0.5, 1.0, 0.5)
+
+
+class CarpenterKennedy2N54(_Stepper):
+    """Imported (and marked "does not work") by the reference's test driver, test/runtests.jl:5-10."""
+
+    method_id = _abi.LH_METHOD_CK2N54
+    c = (0.0, 1432997174477.0 / 9575080441755.0, 2526269341429.0 / 6820363962896.0,
+         2006345519317.0 / 3224310063776.0, 2802321613138.0 / 2924317926251.0)
+
+
+class ShuOsherRK(_Stepper):
+    """Any two-register Shu-Osher method: ``u_i = a[i] u^n + b[i] u_{i-1} + g[i] dt f(u_{i-1}, t + c[i] dt)``
+    (e.g. OrdinaryDiffEq's SSPRK73 with its own coefficient table)."""
+
+    kind = _abi.LH_STEPPER_SHU_OSHER
+
+    def __init__(self, a, b, g, c):
+        if not (len(a) == len(b) == len(g) == len(c)) or not 1 <= len(a) <= _abi.LH_MAX_STAGES:
+            raise ValueError("a, b, g, c must have the same length, 1..LH_MAX_STAGES")
+        self.a, self.b, self.g, self.c = map(lambda v: tuple(float(x) for x in v), (a, b, g, c))
+
+    def table(self, lib):
+        tab = _abi.lh_soil_stepper()
+        tab.kind, tab.nstages = self.kind, len(self.c)
+        for i in range(len(self.c)):
+            tab.a[i], tab.b[i], tab.g[i], tab.c[i] = self.a[i], self.b[i], self.g[i], self.c[i]
+        return tab
+
+
+class LowStorageRK2N(ShuOsherRK):
+    """Any Williamson 2N method: ``r = A[i] r + dt f(u, t + c[i] dt); u = u + B[i] r`` (``A[0] == 0``)."""
+
+    kind = _abi.LH_STEPPER_2N
+
+    def __init__(self, A, B, c):
+        super().__init__(A, B, [0.0] * len(A), c)
 
 
 class Solution:
@@ -40,8 +119,10 @@ class Integrator:
     """Minimal DEIntegrator: ``u``, ``p`` (= Ya), ``t``, ``dt``, ``sol``."""
 
     def __init__(self, engine: SoilEngine, Y: FieldVector, Ya: FieldVector, tspan, dt, saveat, callback,
-                 max_chunk: int):
+                 max_chunk: int, method: Optional[_Stepper] = None):
         self.engine = engine
+        self.method = method if method is not None else SSPRK33()
+        self._table = self.method.table(engine.lib)
         self.u = copy_state(Y)   # DiffEqBase.init does not alias u0
         self.p = Ya
         self.t0, self.tf = float(tspan[0]), float(tspan[1])
@@ -62,7 +143,7 @@ class Integrator:
             self._saveat = sorted(float(s) for s in saveat)
         self._next_save = 0
         self._device_fresh = True
-        self._dynamic_aux = engine.has_time_dependent_aux(self.t0, self.dt)
+        self._dynamic_aux = engine.has_time_dependent_aux(self.t0, self.dt) and self._table is None
         engine.upload(self.u)
         self._save_if_due(force_first=True)
 
@@ -100,6 +181,7 @@ class Integrator:
     # -- stepping ----------------------------------------------------------------------------------
     def _advance(self, nsteps: int, dt: float):
         eng = self.engine
+        cs = self.method.c
         if self._dynamic_aux:
             # time-dependent prescribed profiles: stage by stage so update_aux! sees every stage time
             t = self.t
@@ -114,16 +196,18 @@ class Integrator:
             table = None
             t = self.t
             if eng.has_dirichlet():
-                table = np.empty((nsteps, 3, 4))
+                table = np.empty((nsteps, len(cs), 4))
                 for s in range(nsteps):
-                    table[s, 0] = eng.bc_values(t)
-                    table[s, 1] = eng.bc_values(t + dt)
-                    table[s, 2] = eng.bc_values(t + 0.5 * dt)
+                    for i, ci in enumerate(cs):
+                        table[s, i] = eng.bc_values(t + ci * dt)
                     t = t + dt
             else:
                 for _ in range(nsteps):
                     t = t + dt
-            eng.ctx.step(self.t, dt, nsteps, table)
+            if self._table is None:
+                eng.ctx.step(self.t, dt, nsteps, table)
+            else:
+                eng.ctx.step_with(self._table, self.t, dt, nsteps, table)
             self.t = t
         self.iter += nsteps
         self._device_fresh = False
@@ -177,8 +261,10 @@ class Simulation(AbstractSimulation):
     def __init__(self, model: AbstractModel, method, *, Y_init, dt, tspan, Ya_init, callbacks=None,
                  saveat=None, progress=False, progress_message=None, max_steps_per_call: int = 4096,
                  device: int = 0, check_finite: bool = False):
-        if not isinstance(method, SSPRK33):
-            raise NotImplementedError("only SSPRK33() is on the B200 path (the only stepper the reference uses)")
+        if not isinstance(method, _Stepper):
+            raise NotImplementedError(
+                "the B200 path runs explicit low-storage methods: SSPRK33 (the only stepper the reference uses), Euler, "
+                "SSPRK22, SSPRK43, CarpenterKennedy2N54, or a ShuOsherRK / LowStorageRK2N coefficient table")
         if not isinstance(model, SoilModel) or model.kind is None:
             raise TypeError("Simulation needs a SoilModel with at least one dynamic component")
         if Y_init is None:
@@ -189,7 +275,9 @@ class Simulation(AbstractSimulation):
         self.callbacks = callbacks
         engine = SoilEngine(model, float(tspan[0]), device=device, library=current_library(),
                             check_finite=check_finite)
-        self.integrator = Integrator(engine, Y_init, Ya_init, tspan, dt, saveat, callbacks, max_steps_per_call)
+        if engine.has_time_dependent_aux(float(tspan[0]), float(dt)) and not isinstance(method, SSPRK33):
+            raise NotImplementedError("time-dependent prescribed profiles are streamed stage by stage for SSPRK33 only")
+        self.integrator = Integrator(engine, Y_init, Ya_init, tspan, dt, saveat, callbacks, max_steps_per_call, method)
 
 
 def step_(simulation: AbstractSimulation) -> None:

@@ -710,6 +710,126 @@ int32_t lho_soil_step_ssprk33(lho_soil_ctx* c, double t, double dt, int64_t nste
     return LH_OK;
 }
 
+/* ------------------------------------------------------------------------------------------
+ * Other explicit low-storage steppers (include/lh_soil.h, "other explicit steppers").  The
+ * combine runs over every prognostic field, like the reference's broadcast over the FieldVector.
+ *   Shu-Osher, two registers:  u_i = a[i] u^n + b[i] u_{i-1} + g[i] dt f(u_{i-1})
+ *   Williamson 2N:             r = a[i] r + dt f(u);  u = u + b[i] r
+ * Built-in tables: forward Euler; SSPRK22 and SSPRK33 (Shu & Osher 1988); SSPRK43 (Kraaijevanger
+ * 1991 / Spiteri & Ruuth 2002, the 4-stage third-order SSP method with C = 2);
+ * CarpenterKennedy2N54 (Carpenter & Kennedy 1994, NASA TM 109112, the rational coefficients of
+ * its table for the (5,4) 2N-storage scheme).
+ * ---------------------------------------------------------------------------------------- */
+int32_t lho_soil_stepper_named(int32_t method, lh_soil_stepper* out)
+{
+    if (!out) return LH_ERR_INVALID_ARG;
+    memset(out, 0, sizeof *out);
+    switch (method) {
+    case LH_METHOD_EULER:
+        out->kind = LH_STEPPER_SHU_OSHER; out->nstages = 1;
+        out->a[0] = 0.0; out->b[0] = 1.0; out->g[0] = 1.0; out->c[0] = 0.0;
+        return LH_OK;
+    case LH_METHOD_SSPRK22:
+        out->kind = LH_STEPPER_SHU_OSHER; out->nstages = 2;
+        out->a[0] = 0.0; out->b[0] = 1.0; out->g[0] = 1.0; out->c[0] = 0.0;
+        out->a[1] = 0.5; out->b[1] = 0.5; out->g[1] = 0.5; out->c[1] = 1.0;
+        return LH_OK;
+    case LH_METHOD_SSPRK33:
+        out->kind = LH_STEPPER_SHU_OSHER; out->nstages = 3;
+        out->a[0] = 0.0; out->b[0] = 1.0; out->g[0] = 1.0; out->c[0] = 0.0;
+        out->a[1] = 0.75; out->b[1] = 0.25; out->g[1] = 0.25; out->c[1] = 1.0;
+        out->a[2] = 1.0 / 3.0; out->b[2] = 2.0 / 3.0; out->g[2] = 2.0 / 3.0; out->c[2] = 0.5;
+        return LH_OK;
+    case LH_METHOD_SSPRK43:
+        out->kind = LH_STEPPER_SHU_OSHER; out->nstages = 4;
+        out->a[0] = 0.0; out->b[0] = 1.0; out->g[0] = 0.5; out->c[0] = 0.0;
+        out->a[1] = 0.0; out->b[1] = 1.0; out->g[1] = 0.5; out->c[1] = 0.5;
+        out->a[2] = 2.0 / 3.0; out->b[2] = 1.0 / 3.0; out->g[2] = 1.0 / 6.0; out->c[2] = 1.0;
+        out->a[3] = 0.0; out->b[3] = 1.0; out->g[3] = 0.5; out->c[3] = 0.5;
+        return LH_OK;
+    case LH_METHOD_CK2N54:
+        out->kind = LH_STEPPER_2N; out->nstages = 5;
+        out->a[0] = 0.0;
+        out->a[1] = -567301805773.0 / 1357537059087.0;
+        out->a[2] = -2404267990393.0 / 2016746695238.0;
+        out->a[3] = -3550918686646.0 / 2091501179385.0;
+        out->a[4] = -1275806237668.0 / 842570457699.0;
+        out->b[0] = 1432997174477.0 / 9575080441755.0;
+        out->b[1] = 5161836677717.0 / 13612068292357.0;
+        out->b[2] = 1720146321549.0 / 2090206949498.0;
+        out->b[3] = 3134564353537.0 / 4481467310338.0;
+        out->b[4] = 2277821191437.0 / 14882151754819.0;
+        out->c[0] = 0.0;
+        out->c[1] = 1432997174477.0 / 9575080441755.0;
+        out->c[2] = 2526269341429.0 / 6820363962896.0;
+        out->c[3] = 2006345519317.0 / 3224310063776.0;
+        out->c[4] = 2802321613138.0 / 2924317926251.0;
+        return LH_OK;
+    default:
+        return LH_ERR_INVALID_ARG;
+    }
+}
+
+int32_t lho_soil_step(lho_soil_ctx* c, const lh_soil_stepper* sp, double t, double dt, int64_t nsteps,
+                      const double* bc_table)
+{
+    (void)t;
+    if (!c || !sp) return LH_ERR_INVALID_ARG;
+    if (nsteps < 0) return fail(c, LH_ERR_INVALID_ARG, "nsteps < 0");
+    if (sp->nstages < 1 || sp->nstages > LH_MAX_STAGES) return fail(c, LH_ERR_INVALID_ARG, "bad stage count");
+    if (sp->kind != LH_STEPPER_SHU_OSHER && sp->kind != LH_STEPPER_2N) return fail(c, LH_ERR_INVALID_ARG, "bad stepper kind");
+    if (sp->kind == LH_STEPPER_2N && sp->a[0] != 0.0) return fail(c, LH_ERR_INVALID_ARG, "2N scheme needs a[0] == 0");
+    const int model = c->cfg.model;
+    const int ns = sp->nstages;
+    const size_t cells = (size_t)c->ncol * c->nlayer;
+    double t0 = now_ms();
+    for (int64_t s = 0; s < nsteps; ++s) {
+        for (int i = 0; i < ns; ++i) {
+            if (bc_table) memcpy(c->bcv, bc_table + (s * ns + i) * 4, sizeof c->bcv);
+            if (sp->kind == LH_STEPPER_SHU_OSHER) {
+                /* stage input: u^n for the first stage, the stage register otherwise; the last stage
+                 * writes u^{n+1} over u^n                                                           */
+                const double* in[3];
+                for (int k = 0; k < 3; ++k) in[k] = (i == 0 || !prognostic(model, k)) ? c->f[k] : c->u1[k];
+                rhs_all(c, in[0], in[1], in[2], c->f[3]);
+                const double a = sp->a[i], b = sp->b[i], g = sp->g[i];
+                for (int k = 0; k < 3; ++k) {
+                    if (!prognostic(model, k)) continue;
+                    double* u0 = c->f[k];
+                    const double* v = in[k];
+                    double* out = (i == ns - 1) ? c->f[k] : c->u1[k];
+                    const double* kk = c->tend[k];
+#pragma omp parallel for schedule(static) if (c->ncol >= 64)
+                    for (size_t j = 0; j < cells; ++j) out[j] = a * u0[j] + b * v[j] + (g * dt) * kk[j];
+                }
+            } else {
+                rhs_all(c, c->f[0], c->f[1], c->f[2], c->f[3]);
+                const double A = sp->a[i], B = sp->b[i];
+                for (int k = 0; k < 3; ++k) {
+                    if (!prognostic(model, k)) continue;
+                    double* u = c->f[k];
+                    double* r = c->u1[k];
+                    const double* kk = c->tend[k];
+#pragma omp parallel for schedule(static) if (c->ncol >= 64)
+                    for (size_t j = 0; j < cells; ++j) {
+                        const double rn = (i == 0) ? dt * kk[j] : A * r[j] + dt * kk[j];
+                        r[j] = rn;
+                        u[j] = u[j] + B * rn;
+                    }
+                }
+            }
+        }
+    }
+    c->last_ms = now_ms() - t0;
+    c->last_launches = 0;
+    if (c->cfg.flags & LH_FLAG_CHECK_FINITE) {
+        for (int k = 0; k < 3; ++k)
+            for (size_t i = 0; i < cells; ++i)
+                if (!isfinite(c->f[k][i])) return fail(c, LH_ERR_NONFINITE, "non-finite state");
+    }
+    return LH_OK;
+}
+
 /* Budgets (new in this build): W = Σ ϑ_l dz, E = Σ ρe_int dz.  Neumaier-compensated
  * so the oracle's sum is accurate to ~1 ulp independent of order.                           */
 static void comp_add(double* s, double* comp, double x)
