@@ -170,6 +170,8 @@ def time_oracle(w, lh, graft, model, nlayer, steps, warmup, target_seconds=None)
 
 def main():
     args = parse_args()
+    # stdout carries exactly one JSON line: NCCL's own banner / debug output goes to stderr
+    os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
@@ -324,6 +326,8 @@ def main():
     if os.path.exists(tpath):
         try:
             traffic = json.load(open(tpath)).get(f"{args.model}_{args.ncol}x{args.nlayer}_bytes_per_launch")
+            if traffic is not None:
+                traffic = traffic * cells_rank / (args.ncol * args.nlayer)     # measured at N = 1; per launch of this rank's shard
         except Exception:
             traffic = None
     line = {
@@ -336,8 +340,9 @@ def main():
             "traffic": traffic, "peak_source": peak_src,
             "kernel": "lh_soil_stage_kernel (fused closures + stencil + SSPRK33 stage)",
             "algorithmic_bytes_per_cell_step": bpcs, "launch_ms": launch_ms,
-            "note": "per-launch average over the 3 stage launches of each step (40/56/56 B per cell coupled); "
-                    "the fp64 pipe, not HBM, is the binding unit (DESIGN.md)",
+            "note": "per-launch average over the 3 stage launches of each step (40/56/56 B per cell coupled, 24/32/32 Richards); "
+                    "besides HBM the kernel is bounded by issue slots: an fp64 instruction holds the issue port for two "
+                    "cycles on B200 (DESIGN.md §4.1)",
         },
         "budgets": {"water": float(budgets[0]), "energy": float(budgets[1]), "allreduce_ms": budget_ms},
     }

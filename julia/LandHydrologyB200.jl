@@ -18,6 +18,7 @@ using LandHydrology.SoilInterface: SoilModel, SoilEnergyModel, SoilHydrologyMode
 using LandHydrology.SoilInterface.SoilWaterParameterizations: NoEffect, TemperatureDependentViscosity, IceImpedance
 using CLIMAParameters.Planet: ρ_cloud_liq, ρ_cloud_ice, cp_l, cp_i, T_0, LH_f0
 using CLIMAParameters.Atmos.Microphysics: K_therm
+import OrdinaryDiffEq        # only for the method types (SSPRK33, CarpenterKennedy2N54, ...) Simulation dispatches on
 
 const LIB = get(ENV, "LH_SOIL_LIBRARY", "liblh_soil.so")
 
@@ -165,6 +166,33 @@ function make_rhs(model::SoilModel)
     return rhs!
 end
 
+# lh_soil_stepper (include/lh_soil.h): coefficient table of a two-register Shu-Osher or a Williamson 2N method
+const LH_MAX_STAGES = 16
+struct LhSoilStepper
+    kind::Int32
+    nstages::Int32
+    a::NTuple{LH_MAX_STAGES, Float64}
+    b::NTuple{LH_MAX_STAGES, Float64}
+    g::NTuple{LH_MAX_STAGES, Float64}
+    c::NTuple{LH_MAX_STAGES, Float64}
+end
+
+"OrdinaryDiffEq method -> built-in table id (LH_METHOD_*); `nothing` selects the specialised SSPRK33 kernels."
+method_id(::OrdinaryDiffEq.SSPRK33) = nothing
+method_id(::OrdinaryDiffEq.Euler) = Int32(0)
+method_id(::OrdinaryDiffEq.SSPRK22) = Int32(1)
+method_id(::OrdinaryDiffEq.SSPRK43) = Int32(3)
+method_id(::OrdinaryDiffEq.CarpenterKennedy2N54) = Int32(4)
+
+function stepper_table(method)
+    id = method_id(method)
+    id === nothing && return nothing
+    tab = Ref{LhSoilStepper}()
+    status = ccall((:lh_soil_stepper_named, LIB), Int32, (Int32, Ref{LhSoilStepper}), id, tab)
+    status == 0 || error("lh_soil_stepper_named($id) failed with status $status")
+    return tab[]
+end
+
 mutable struct Simulation
     model::SoilModel
     engine::Engine
@@ -173,37 +201,47 @@ mutable struct Simulation
     t::Float64
     dt::Float64
     tf::Float64
+    table::Union{Nothing, LhSoilStepper}      # nothing: SSPRK33
 end
 
 """
     Simulation(model, method; Y_init, dt, tspan, Ya_init, ...)
 
-Drop-in for src/Simulations/simulation.jl:34-73 for `method = SSPRK33()`; the state stays on the GPU.
+Drop-in for src/Simulations/simulation.jl:34-73; the state stays on the GPU.  `method` is `SSPRK33()` (what every
+reference test uses) or one of `Euler()`, `SSPRK22()`, `SSPRK43()`, `CarpenterKennedy2N54()`.
 """
 function Simulation(model::SoilModel, method; Y_init, dt, tspan, Ya_init, kwargs...)
     e = Engine(model, tspan[1])
     u = deepcopy(Y_init)
     update_aux!(e, Ya_init, tspan[1])
     upload!(e, u)
-    return Simulation(model, e, u, Ya_init, tspan[1], dt, tspan[2])
+    return Simulation(model, e, u, Ya_init, tspan[1], dt, tspan[2], stepper_table(method))
 end
 
 function advance!(sim::Simulation, nsteps::Integer)
-    table = Vector{Float64}(undef, 12 * nsteps)
+    cs = sim.table === nothing ? (0.0, 1.0, 0.5) : sim.table.c[1:sim.table.nstages]   # stage times t + c dt
+    ns = length(cs)
+    table = Vector{Float64}(undef, 4 * ns * nsteps)
     t = sim.t
     for s in 0:(nsteps - 1)
-        for (k, ts) in enumerate((t, t + sim.dt, t + sim.dt / 2))      # SSPRK33 stage times
-            table[(12s + 4(k - 1) + 1):(12s + 4k)] .= bc_values(sim.model, ts)
+        for (k, c) in enumerate(cs)
+            table[(4ns * s + 4(k - 1) + 1):(4ns * s + 4k)] .= bc_values(sim.model, t + c * sim.dt)
         end
         t += sim.dt
     end
-    GC.@preserve table check(sim.engine.ctx, ccall((:lh_soil_step_ssprk33, LIB), Int32,
-        (Ptr{Cvoid}, Cdouble, Cdouble, Int64, Ptr{Cdouble}), sim.engine.ctx, sim.t, sim.dt, nsteps, table))
+    if sim.table === nothing
+        GC.@preserve table check(sim.engine.ctx, ccall((:lh_soil_step_ssprk33, LIB), Int32,
+            (Ptr{Cvoid}, Cdouble, Cdouble, Int64, Ptr{Cdouble}), sim.engine.ctx, sim.t, sim.dt, nsteps, table))
+    else
+        GC.@preserve table check(sim.engine.ctx, ccall((:lh_soil_step, LIB), Int32,
+            (Ptr{Cvoid}, Ref{LhSoilStepper}, Cdouble, Cdouble, Int64, Ptr{Cdouble}),
+            sim.engine.ctx, sim.table, sim.t, sim.dt, nsteps, table))
+    end
     sim.t = t
     return nothing
 end
 
-"step!(simulation): one SSPRK33 step = three fused RHS+stage kernel launches (simulation.jl:79-80)."
+"step!(simulation): one step = one fused RHS+stage kernel launch per stage (simulation.jl:79-80)."
 step!(sim::Simulation) = advance!(sim, 1)
 
 "run!(simulation): integrate to tspan[2] and bring the state back (simulation.jl:86-87)."
