@@ -36,6 +36,8 @@ LH_DIAG_K, LH_DIAG_PSI, LH_DIAG_KAPPA, LH_DIAG_T = 0, 1, 2, 3
 LH_BCV_TOP_ENERGY, LH_BCV_TOP_HYDROLOGY, LH_BCV_BOTTOM_ENERGY, LH_BCV_BOTTOM_HYDROLOGY = 0, 1, 2, 3
 LH_FLAG_CHECK_FINITE = 1
 LH_FLAG_GENERAL_VG = 2
+LH_FLAG_STAGE_LAUNCHES = 4
+LH_FLAG_PERSISTENT = 8
 
 
 class SoilError(RuntimeError):

@@ -26,6 +26,9 @@
 cudaError_t lh_launch_stage_m0(int, int, const LhKernelArgs&, const LhLaunchShape&, cudaStream_t);
 cudaError_t lh_launch_stage_m1(int, int, const LhKernelArgs&, const LhLaunchShape&, cudaStream_t);
 cudaError_t lh_launch_stage_m2(int, int, const LhKernelArgs&, const LhLaunchShape&, cudaStream_t);
+cudaError_t lh_launch_persistent_m0(int, const LhKernelArgs&, const LhLaunchShape&, cudaStream_t);
+cudaError_t lh_launch_persistent_m1(int, const LhKernelArgs&, const LhLaunchShape&, cudaStream_t);
+cudaError_t lh_launch_persistent_m2(int, const LhKernelArgs&, const LhLaunchShape&, cudaStream_t);
 
 LhLaunchShape lh_choose_shape(int model, int64_t ncol_pad, int32_t nlayer, int sm_count)
 {
@@ -48,6 +51,10 @@ LhLaunchShape lh_choose_shape(int model, int64_t ncol_pad, int32_t nlayer, int s
     s.nblocks = (groups + G - 1) / G;
     const int nq = model == LH_MODEL_COUPLED ? 5 : 2;
     s.smem_bytes = (LH_TAB_DOUBLES + (size_t)G * W * ((2 * nq + 6) * 32 + 4 * 5 * 32)) * sizeof(double);   // + cp.async input ring
+    const int by_smem = (int)((227 * 1024) / (s.smem_bytes + 1024));
+    const int by_threads = (model == 0 ? LhBounds<0>::min_blocks : LhBounds<1>::min_blocks);   // the register cap of __launch_bounds__
+    const int resident = by_smem < by_threads ? (by_smem < 1 ? 1 : by_smem) : by_threads;
+    s.waves = (double)s.nblocks / ((double)sm_count * resident);
     return s;
 }
 
@@ -60,6 +67,18 @@ cudaError_t lh_launch_stage(int model, int stage, int flags, const LhKernelArgs&
     case 0: return lh_launch_stage_m0(stage, flags, args, shape, stream);
     case 1: return lh_launch_stage_m1(stage, flags, args, shape, stream);
     default: return lh_launch_stage_m2(stage, flags, args, shape, stream);
+    }
+}
+
+cudaError_t lh_launch_ssprk33_persistent(int model, int flags, const LhKernelArgs& args, const LhLaunchShape& shape,
+                                         cudaStream_t stream)
+{
+    if (model < 0 || model > 2) return cudaErrorInvalidValue;
+    if (shape.W * shape.G * 32 > lh_max_threads(model) || shape.smem_bytes > 200 * 1024) return cudaErrorInvalidConfiguration;
+    switch (model) {
+    case 0: return lh_launch_persistent_m0(flags, args, shape, stream);
+    case 1: return lh_launch_persistent_m1(flags, args, shape, stream);
+    default: return lh_launch_persistent_m2(flags, args, shape, stream);
     }
 }
 

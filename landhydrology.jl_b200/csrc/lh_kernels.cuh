@@ -32,8 +32,8 @@ inline int lh_max_threads(int model) { return model == 0 ? LhBounds<0>::max_thre
 // Device layout of every cell field: column-fastest SoA, element (layer, col) at
 // [layer * ncol_pad + col]; ncol_pad is a multiple of 32 so that a warp (32 adjacent columns)
 // reads/writes two full, aligned 128-byte lines per field per layer.
-struct LhKernelArgs {
-    LhDevParams p;
+// What one stage reads and writes (device pointers to column-fastest SoA blocks) and its scalars.
+struct LhStageIO {
     const double* in_th;   // stage input ϑ_l            (state U, or stage buffer V)
     const double* in_ti;   // θ_i                         (always U: its tendency is 0)
     const double* in_re;   // stage input ρe_int          (U or V)
@@ -44,23 +44,32 @@ struct LhKernelArgs {
     double* out_re;
     double* out2_th;       // 2N stages (STAGE 5): the residual register r, updated in place (== u0_th)
     double* out2_re;
-    const double* zc;      // nlayer centre coordinates
-    int64_t ncol_pad;
-    int32_t nlayer;
-    int32_t Lc;            // layers per thread (vertical chunk)
-    int32_t W;             // chunks per column = blockDim.y
-    int32_t top_e_kind, top_h_kind, bot_e_kind, bot_h_kind;
-    double bcv[4];         // LH_BCV_* boundary values for THIS launch
+    double bcv[4];         // LH_BCV_* boundary values for THIS stage
     double dt;
     double sa, sb, sg;     // stage coefficients of the generic steppers (STAGE 4: a, b, g; STAGE 5: a, b)
     int32_t first2n;       // STAGE 5, first stage: r is not read (a == 0 and r may hold anything)
     int32_t pad_;
 };
 
+struct LhKernelArgs {
+    LhDevParams p;
+    LhStageIO io;          // one-stage launches: this stage; persistent SSPRK33 launches: stage 1 (in = U, out = V)
+    const double* zc;      // nlayer centre coordinates
+    int64_t ncol_pad;
+    int32_t nlayer;
+    int32_t Lc;            // layers per thread (vertical chunk)
+    int32_t W;             // chunks per column = blockDim.y
+    int32_t top_e_kind, top_h_kind, bot_e_kind, bot_h_kind;
+    // persistent SSPRK33 launches only
+    int64_t nsteps;
+    const double* bc_dev;  // NULL (io.bcv for every stage) or nsteps * 3 * 4 boundary values in device memory
+};
+
 struct LhLaunchShape {
     int32_t Lc, W, G;      // chunk length, chunks per column, column groups (of 32) per block
     int64_t nblocks;
     size_t smem_bytes;
+    double waves;          // nblocks / (SMs x resident blocks per SM)
 };
 
 LhLaunchShape lh_choose_shape(int model, int64_t ncol_pad, int32_t nlayer, int sm_count);
@@ -69,6 +78,9 @@ LhLaunchShape lh_choose_shape(int model, int64_t ncol_pad, int32_t nlayer, int s
 // (lh_closures.cuh) select the compiled kernel variant.
 cudaError_t lh_launch_stage(int model, int stage, int flags, const LhKernelArgs& args,
                             const LhLaunchShape& shape, cudaStream_t stream);
+// args.nsteps whole SSPRK33 steps in ONE launch: every block keeps its column group for all 3 nsteps stages.
+cudaError_t lh_launch_ssprk33_persistent(int model, int flags, const LhKernelArgs& args,
+                                         const LhLaunchShape& shape, cudaStream_t stream);
 // *flag (int32, device) := 1 if any element of x[0..n) is non-zero (NaN counts), else unchanged.
 cudaError_t lh_launch_any_nonzero(const double* x, int64_t n, int* flag, cudaStream_t stream);
 

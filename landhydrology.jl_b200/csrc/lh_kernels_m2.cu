@@ -6,3 +6,8 @@ cudaError_t lh_launch_stage_m2(int stage, int flags, const LhKernelArgs& args, c
 {
     return launch_model<2>(stage, flags, args, shape, stream);
 }
+
+cudaError_t lh_launch_persistent_m2(int flags, const LhKernelArgs& args, const LhLaunchShape& shape, cudaStream_t stream)
+{
+    return launch_persistent_model<2>(flags, args, shape, stream);
+}

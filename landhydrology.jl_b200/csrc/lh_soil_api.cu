@@ -87,6 +87,8 @@ struct lh_soil_ctx {
     double* partials = nullptr;
     int32_t npartials = 0;
     double* budget_dev = nullptr;                // 2 doubles (+2 for the all-reduce result)
+    double* bc_dev = nullptr;                    // boundary-value table of a persistent launch
+    int64_t bc_dev_steps = 0;
     unsigned long long* nonfinite_dev = nullptr;
     double bcv[4] = {0, 0, 0, 0};
     ncclComm_t_ comm = nullptr;
@@ -208,6 +210,7 @@ void free_all(lh_soil_ctx* c)
     if (c->zc_dev) cudaFree(c->zc_dev);
     if (c->partials) cudaFree(c->partials);
     if (c->budget_dev) cudaFree(c->budget_dev);
+    if (c->bc_dev) cudaFree(c->bc_dev);
     if (c->nonfinite_dev) cudaFree(c->nonfinite_dev);
     if (c->ev_start) cudaEventDestroy(c->ev_start);
     if (c->ev_stop) cudaEventDestroy(c->ev_stop);
@@ -255,6 +258,12 @@ int32_t upload_field(lh_soil_ctx* c, double* soa, const double* host, int64_t cs
         LH_CUDA(c, cudaStreamSynchronize(c->stream));
         return LH_OK;
     }
+    if (cs == 1 && n == 1) {   // a single layer: the row of columns is contiguous whatever the layer stride says
+        LH_CUDA(c, cudaMemcpyAsync(soa, host, c->ncol * sizeof(double), cudaMemcpyHostToDevice, c->stream));
+        LH_CUDA(c, lh_launch_fill_padding(soa, c->ncol, c->ncol_pad, n, c->stream));
+        LH_CUDA(c, cudaStreamSynchronize(c->stream));
+        return LH_OK;
+    }
     if (cs == 1) {   // column-fastest host block with its own layer stride
         LH_CUDA(c, cudaMemcpy2DAsync(soa, c->ncol_pad * sizeof(double), host, ls * sizeof(double),
                                      c->ncol * sizeof(double), n, cudaMemcpyHostToDevice, c->stream));
@@ -297,8 +306,13 @@ int32_t download_field(lh_soil_ctx* c, const double* soa, double* host, int64_t 
     if (cs == 0 && c->ncol != 1) return fail(c, LH_ERR_INVALID_ARG, "col_stride 0 is only valid for uploads");
     LH_CUDA(c, cudaSetDevice(c->device));
     const int n = c->nlayer;
+    if (cs == 1 && n == 1) {
+        LH_CUDA(c, cudaMemcpyAsync(host, soa, c->ncol * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+        LH_CUDA(c, cudaStreamSynchronize(c->stream));
+        return LH_OK;
+    }
     if (cs == 1 || c->ncol == 1) {
-        const int64_t lstride = (c->ncol == 1) ? ls : ls;
+        const int64_t lstride = ls;
         LH_CUDA(c, cudaMemcpy2DAsync(host, lstride * sizeof(double), soa, c->ncol_pad * sizeof(double),
                                      c->ncol * sizeof(double), n, cudaMemcpyDeviceToHost, c->stream));
         LH_CUDA(c, cudaStreamSynchronize(c->stream));
@@ -370,15 +384,15 @@ void fill_args(lh_soil_ctx* c, int stage, double dt, LhKernelArgs& a)
 {
     a.p = c->dp;
     const bool from_V = stage >= 2;
-    a.in_th = (from_V && has_water(c->model)) ? c->V[0] : c->U[0];
-    a.in_ti = c->U[1];
-    a.in_re = (from_V && has_heat(c->model)) ? c->V[2] : c->U[2];
-    a.aux_T = c->U[3];
-    a.u0_th = c->U[0];
-    a.u0_re = c->U[2];
-    if (stage == 0) { a.out_th = c->tend[0]; a.out_re = c->tend[2]; }
-    else if (stage == 3) { a.out_th = c->U[0]; a.out_re = c->U[2]; }
-    else { a.out_th = c->V[0]; a.out_re = c->V[2]; }
+    a.io.in_th = (from_V && has_water(c->model)) ? c->V[0] : c->U[0];
+    a.io.in_ti = c->U[1];
+    a.io.in_re = (from_V && has_heat(c->model)) ? c->V[2] : c->U[2];
+    a.io.aux_T = c->U[3];
+    a.io.u0_th = c->U[0];
+    a.io.u0_re = c->U[2];
+    if (stage == 0) { a.io.out_th = c->tend[0]; a.io.out_re = c->tend[2]; }
+    else if (stage == 3) { a.io.out_th = c->U[0]; a.io.out_re = c->U[2]; }
+    else { a.io.out_th = c->V[0]; a.io.out_re = c->V[2]; }
     a.zc = c->zc_dev;
     a.ncol_pad = c->ncol_pad;
     a.nlayer = c->nlayer;
@@ -388,13 +402,15 @@ void fill_args(lh_soil_ctx* c, int stage, double dt, LhKernelArgs& a)
     a.top_h_kind = c->cfg.top.hydrology_kind;
     a.bot_e_kind = c->cfg.bottom.energy_kind;
     a.bot_h_kind = c->cfg.bottom.hydrology_kind;
-    memcpy(a.bcv, c->bcv, sizeof a.bcv);
-    a.dt = dt;
-    a.out2_th = c->V[0];
-    a.out2_re = c->V[2];
-    a.sa = 0.0; a.sb = 1.0; a.sg = 1.0;
-    a.first2n = 0;
-    a.pad_ = 0;
+    memcpy(a.io.bcv, c->bcv, sizeof a.io.bcv);
+    a.io.dt = dt;
+    a.io.out2_th = c->V[0];
+    a.io.out2_re = c->V[2];
+    a.io.sa = 0.0; a.io.sb = 1.0; a.io.sg = 1.0;
+    a.io.first2n = 0;
+    a.io.pad_ = 0;
+    a.nsteps = 0;
+    a.bc_dev = nullptr;
 }
 
 int32_t check_finite(lh_soil_ctx* c)
@@ -620,23 +636,56 @@ int32_t lh_soil_stage_ssprk33(lh_soil_ctx* c, int32_t stage, double dt)
     return launch_stage(c, stage, dt);
 }
 
+// Few waves per launch: launch gaps (~3 us per kernel) and wave quantisation are then >= 5 % of a stage.
+static bool use_persistent(const lh_soil_ctx* c)
+{
+    if (c->cfg.flags & LH_FLAG_STAGE_LAUNCHES) return false;
+    if (c->cfg.flags & LH_FLAG_PERSISTENT) return true;
+    return c->shape.waves <= 16.0;
+}
+
 int32_t lh_soil_step_ssprk33(lh_soil_ctx* c, double t, double dt, int64_t nsteps, const double* bc_table)
 {
     (void)t;
     if (!c) return LH_ERR_INVALID_ARG;
     if (nsteps < 0) return fail(c, LH_ERR_INVALID_ARG, "nsteps < 0");
     LH_CUDA(c, cudaSetDevice(c->device));
-    LH_CUDA(c, cudaEventRecord(c->ev_start, c->stream));
-    for (int64_t s = 0; s < nsteps; ++s) {
-        for (int stage = 1; stage <= 3; ++stage) {
-            if (bc_table) memcpy(c->bcv, bc_table + (s * 3 + (stage - 1)) * 4, sizeof c->bcv);
-            int32_t st = launch_stage(c, stage, dt);
-            if (st != LH_OK) return st;
+    const bool persistent = use_persistent(c) && nsteps > 0;
+    if (persistent && bc_table) {
+        if (c->bc_dev_steps < nsteps) {
+            if (c->bc_dev) { LH_CUDA(c, cudaFree(c->bc_dev)); c->bc_dev = nullptr; c->bc_dev_steps = 0; }
+            LH_CUDA(c, cudaMalloc(&c->bc_dev, (size_t)nsteps * 12 * sizeof(double)));
+            c->bc_dev_steps = nsteps;
         }
+        // pageable source: the call returns once the table has been staged, so the host buffer is only borrowed
+        LH_CUDA(c, cudaMemcpyAsync(c->bc_dev, bc_table, (size_t)nsteps * 12 * sizeof(double), cudaMemcpyHostToDevice, c->stream));
+    }
+    LH_CUDA(c, cudaEventRecord(c->ev_start, c->stream));
+    int64_t launches = 0;
+    if (persistent) {
+        const int64_t MAX_STEPS_PER_LAUNCH = 4096;
+        for (int64_t s0 = 0; s0 < nsteps; s0 += MAX_STEPS_PER_LAUNCH) {
+            LhKernelArgs a;
+            fill_args(c, 1, dt, a);
+            a.nsteps = std::min<int64_t>(MAX_STEPS_PER_LAUNCH, nsteps - s0);
+            a.bc_dev = bc_table ? c->bc_dev + s0 * 12 : nullptr;
+            LH_CUDA(c, lh_launch_ssprk33_persistent(c->model, c->kernel_flags, a, c->shape, c->stream));
+            ++launches;
+        }
+        if (bc_table) memcpy(c->bcv, bc_table + (nsteps * 3 - 1) * 4, sizeof c->bcv);   // what the per-stage path leaves behind
+    } else {
+        for (int64_t s = 0; s < nsteps; ++s) {
+            for (int stage = 1; stage <= 3; ++stage) {
+                if (bc_table) memcpy(c->bcv, bc_table + (s * 3 + (stage - 1)) * 4, sizeof c->bcv);
+                int32_t st = launch_stage(c, stage, dt);
+                if (st != LH_OK) return st;
+            }
+        }
+        launches = 3 * nsteps;
     }
     LH_CUDA(c, cudaEventRecord(c->ev_stop, c->stream));
     c->timing_valid = true;
-    c->last_launches = 3 * nsteps;
+    c->last_launches = launches;
     if (c->cfg.flags & LH_FLAG_CHECK_FINITE) return check_finite(c);
     return LH_OK;
 }
@@ -715,21 +764,21 @@ int32_t lh_soil_step(lh_soil_ctx* c, const lh_soil_stepper* sp, double t, double
                 const bool euler = sp->a[i] == 0.0 && sp->b[i] == 1.0;
                 stage = euler ? 1 : 4;
                 fill_args(c, stage, euler ? sp->g[i] * dt : dt, a);
-                a.in_th = (!first && has_water(c->model)) ? c->V[0] : c->U[0];
-                a.in_re = (!first && has_heat(c->model)) ? c->V[2] : c->U[2];
-                a.out_th = last ? c->U[0] : c->V[0];
-                a.out_re = last ? c->U[2] : c->V[2];
-                a.sa = sp->a[i]; a.sb = sp->b[i]; a.sg = sp->g[i];
+                a.io.in_th = (!first && has_water(c->model)) ? c->V[0] : c->U[0];
+                a.io.in_re = (!first && has_heat(c->model)) ? c->V[2] : c->U[2];
+                a.io.out_th = last ? c->U[0] : c->V[0];
+                a.io.out_re = last ? c->U[2] : c->V[2];
+                a.io.sa = sp->a[i]; a.io.sb = sp->b[i]; a.io.sg = sp->g[i];
             } else {
                 // r = a r + dt f(u); u = u + b r: reads and writes U (u) and V (r) in place
                 stage = 5;
                 fill_args(c, stage, dt, a);
-                a.in_th = c->U[0]; a.in_re = c->U[2];
-                a.u0_th = c->V[0]; a.u0_re = c->V[2];
-                a.out_th = c->U[0]; a.out_re = c->U[2];
-                a.out2_th = c->V[0]; a.out2_re = c->V[2];
-                a.sa = sp->a[i]; a.sb = sp->b[i];
-                a.first2n = i == 0;
+                a.io.in_th = c->U[0]; a.io.in_re = c->U[2];
+                a.io.u0_th = c->V[0]; a.io.u0_re = c->V[2];
+                a.io.out_th = c->U[0]; a.io.out_re = c->U[2];
+                a.io.out2_th = c->V[0]; a.io.out2_re = c->V[2];
+                a.io.sa = sp->a[i]; a.io.sb = sp->b[i];
+                a.io.first2n = i == 0;
             }
             LH_CUDA(c, lh_launch_stage(c->model, stage, c->kernel_flags, a, c->shape, c->stream));
         }

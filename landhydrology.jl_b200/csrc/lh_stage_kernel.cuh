@@ -103,12 +103,12 @@ __device__ __forceinline__ Flux boundary_flux(const LhDevParams& p, const double
 // STAGE: 0 tendency; 1, 2, 3 the SSPRK33 stages; 4 a generic two-register Shu-Osher stage
 // (a u^n + b u_{i-1} + g dt f); 5 a Williamson 2N stage (r = a r + dt f, u = u + b r), include/lh_soil.h.
 template <int STAGE>
-__device__ __forceinline__ double stage_base(const LhKernelArgs& A, double v, double u0)
+__device__ __forceinline__ double stage_base(const LhStageIO& io, double v, double u0)
 {
     if constexpr (STAGE == 2) return fma(3.0, u0, v);       // 3 u0 + u1
     else if constexpr (STAGE == 3) return fma(2.0, v, u0);  // u0 + 2 u2
-    else if constexpr (STAGE == 4) return fma(A.sa, u0, A.sb * v);
-    else if constexpr (STAGE == 5) return A.first2n ? 0.0 : A.sa * u0;   // a r (r is not read as a number in the first stage)
+    else if constexpr (STAGE == 4) return fma(io.sa, u0, io.sb * v);
+    else if constexpr (STAGE == 5) return io.first2n ? 0.0 : io.sa * u0;   // a r (r is not read as a number in the first stage)
     else return v;
 }
 
@@ -149,11 +149,12 @@ __device__ __forceinline__ double lh_lds(uint32_t addr)
     return v;
 }
 
+// One stage over this block's column groups.  `smem` = the block's dynamic shared memory with the exp2 / log2
+// tables already staged at its start.  Contains ONE __syncthreads (the chunk-face exchange): every thread of
+// the block must call it.
 template <int MODEL, int STAGE, int FLAGS>
-__global__ void __launch_bounds__(LhBounds<MODEL>::max_threads, LhBounds<MODEL>::min_blocks)
-lh_soil_stage_kernel(const __grid_constant__ LhKernelArgs A)
+__device__ __forceinline__ void lh_stage_body(const LhKernelArgs& A, const LhStageIO& io, double* smem)
 {
-    extern __shared__ __align__(16) double smem[];
     constexpr int NQv = NQ<MODEL>::value;
     constexpr bool ICE = (FLAGS & LH_FLAG_ICE) != 0;
     const LhDevParams& p = A.p;
@@ -177,19 +178,17 @@ lh_soil_stage_kernel(const __grid_constant__ LhKernelArgs A)
 
     // shared memory: the exp2 / log2 tables, then per (g, w): one Slot (chunk-face exchange) and one input ring
     const double* tab = smem;
-    lh_stage_tables(p, smem, (threadIdx.z * blockDim.y + threadIdx.y) * 32 + threadIdx.x, blockDim.x * blockDim.y * blockDim.z);
     double* warp_base = smem + LH_TAB_DOUBLES + (size_t)(g * W + w) * (Slot<MODEL>::doubles + RING_DOUBLES);
     double* slot = warp_base + lane;
     double* sm_bot = slot;                               // Q of the chunk's first cell
     double* sm_top = slot + NQv * 32;                    // Q of the chunk's last cell
     double* sm_pend = slot + 2 * NQv * 32;               // base.th, base.re, F_first_up.w, F_first_up.e, base.th2, base.re2
-    __syncthreads();
 
-    const double* pth = A.in_th + col;
-    const double* pti = A.in_ti + col;
-    const double* pT = A.aux_T + col;
-    double* oth = A.out_th + col;
-    double* ore = A.out_re + col;
+    const double* pth = io.in_th + col;
+    const double* pti = io.in_ti + col;
+    const double* pT = io.aux_T + col;
+    double* oth = io.out_th + col;
+    double* ore = io.out_re + col;
 
     // Input pipeline.  The raw values of cell i travel global -> shared with cp.async (LDGSTS): no
     // registers are held while the copy is in flight (a register software pipeline was tried: ptxas
@@ -211,11 +210,11 @@ lh_soil_stage_kernel(const __grid_constant__ LhKernelArgs A)
     int rowpos[5];                            // position of the row inside a ring cell: th 0, ti 1, x 2, u0th 3, u0re 4
     {
         int k = 0;
-        rowptr[k] = A.in_th; rowpos[k++] = 0;
-        if (ICE) { rowptr[k] = A.in_ti; rowpos[k++] = 1; }
-        if (HAS_X) { rowptr[k] = MODEL != 0 ? A.in_re : A.aux_T; rowpos[k++] = 2; }
-        if (STAGE >= 2 && MODEL != 1) { rowptr[k] = A.u0_th; rowpos[k++] = 3; }
-        if (STAGE >= 2 && MODEL != 0) { rowptr[k] = A.u0_re; rowpos[k++] = 4; }
+        rowptr[k] = io.in_th; rowpos[k++] = 0;
+        if (ICE) { rowptr[k] = io.in_ti; rowpos[k++] = 1; }
+        if (HAS_X) { rowptr[k] = MODEL != 0 ? io.in_re : io.aux_T; rowpos[k++] = 2; }
+        if (STAGE >= 2 && MODEL != 1) { rowptr[k] = io.u0_th; rowpos[k++] = 3; }
+        if (STAGE >= 2 && MODEL != 0) { rowptr[k] = io.u0_re; rowpos[k++] = 4; }
     }
     const bool upper = lane >= 16;
     const int sub = lane & 15;
@@ -266,24 +265,24 @@ lh_soil_stage_kernel(const __grid_constant__ LhKernelArgs A)
             o.q.K = c.K; o.q.psi = c.psi; o.q.kappa = c.kappa; o.q.T = c.T;
             o.q.eK = (p.rhocp_l * c.dT) * c.K;                               // ρe_int_l * K (:306, :364)
         }
-        o.base.th = (MODEL != 1) ? stage_base<STAGE>(A, r.th, r.u0th) : 0.0;
-        o.base.re = (MODEL != 0) ? stage_base<STAGE>(A, r.x, r.u0re) : 0.0;
+        o.base.th = (MODEL != 1) ? stage_base<STAGE>(io, r.th, r.u0th) : 0.0;
+        o.base.re = (MODEL != 0) ? stage_base<STAGE>(io, r.x, r.u0re) : 0.0;
         o.base.th2 = (STAGE == 5 && MODEL != 1) ? r.th : 0.0;
         o.base.re2 = (STAGE == 5 && MODEL != 0) ? r.x : 0.0;
         return o;
     };
-    const double cdt = STAGE == 0 ? -p.inv_dz : (STAGE == 3 ? -2.0 * (A.dt * p.inv_dz) : STAGE == 4 ? -((A.sg * A.dt) * p.inv_dz) : -(A.dt * p.inv_dz));
-    double* o2th = A.out2_th + col;     // 2N stages: the residual register r
-    double* o2re = A.out2_re + col;
+    const double cdt = STAGE == 0 ? -p.inv_dz : (STAGE == 3 ? -2.0 * (io.dt * p.inv_dz) : STAGE == 4 ? -((io.sg * io.dt) * p.inv_dz) : -(io.dt * p.inv_dz));
+    double* o2th = io.out2_th + col;     // 2N stages: the residual register r
+    double* o2re = io.out2_re + col;
     auto store_cell = [&](int64_t o, const Base& base, const Flux& lo, const Flux& hi) {
         if constexpr (MODEL != 1) {
             const double v = stage_out<STAGE>(base.th, hi.w - lo.w, cdt);
-            if constexpr (STAGE == 5) { o2th[o] = v; oth[o] = fma(A.sb, v, base.th2); }
+            if constexpr (STAGE == 5) { o2th[o] = v; oth[o] = fma(io.sb, v, base.th2); }
             else oth[o] = v;
         }
         if constexpr (MODEL != 0) {
             const double v = stage_out<STAGE>(base.re, hi.e - lo.e, cdt);
-            if constexpr (STAGE == 5) { o2re[o] = v; ore[o] = fma(A.sb, v, base.re2); }
+            if constexpr (STAGE == 5) { o2re[o] = v; ore[o] = fma(io.sb, v, base.re2); }
             else ore[o] = v;
         }
     };
@@ -365,8 +364,8 @@ lh_soil_stage_kernel(const __grid_constant__ LhKernelArgs A)
             if constexpr (MODEL != 1) { c.K = first.K; c.psi = first.psi; }
             if constexpr (MODEL != 0) c.T = first.T;
             else if (need_T) c.T = pT[0];
-            F_lo = boundary_flux<MODEL, FLAGS>(p, tab, A.bot_e_kind, A.bot_h_kind, A.bcv[LH_BCV_BOTTOM_ENERGY],
-                                               A.bcv[LH_BCV_BOTTOM_HYDROLOGY], true, pth[0], ICE ? pti[0] : 0.0, c);
+            F_lo = boundary_flux<MODEL, FLAGS>(p, tab, A.bot_e_kind, A.bot_h_kind, io.bcv[LH_BCV_BOTTOM_ENERGY],
+                                               io.bcv[LH_BCV_BOTTOM_HYDROLOGY], true, pth[0], ICE ? pti[0] : 0.0, c);
         } else {
             F_lo = face_flux<MODEL>(p, q_load<MODEL>(sm_top - (Slot<MODEL>::doubles + RING_DOUBLES)), first);   // top of chunk w-1
         }
@@ -377,8 +376,8 @@ lh_soil_stage_kernel(const __grid_constant__ LhKernelArgs A)
             if constexpr (MODEL != 1) { c.K = prev.K; c.psi = prev.psi; }
             if constexpr (MODEL != 0) c.T = prev.T;
             else if (need_T) c.T = pT[o];
-            F_hi = boundary_flux<MODEL, FLAGS>(p, tab, A.top_e_kind, A.top_h_kind, A.bcv[LH_BCV_TOP_ENERGY],
-                                               A.bcv[LH_BCV_TOP_HYDROLOGY], false, pth[o], ICE ? pti[o] : 0.0, c);
+            F_hi = boundary_flux<MODEL, FLAGS>(p, tab, A.top_e_kind, A.top_h_kind, io.bcv[LH_BCV_TOP_ENERGY],
+                                               io.bcv[LH_BCV_TOP_HYDROLOGY], false, pth[o], ICE ? pti[o] : 0.0, c);
         } else {
             F_hi = face_flux<MODEL>(p, prev, q_load<MODEL>(sm_bot + (Slot<MODEL>::doubles + RING_DOUBLES)));    // bot of chunk w+1
         }
@@ -394,6 +393,58 @@ lh_soil_stage_kernel(const __grid_constant__ LhKernelArgs A)
             write_at(a, base_first, F_lo, F_first_up);
             write_at(b - 1, base_prev, F_below, F_hi);
         }
+    }
+}
+
+template <int MODEL, int STAGE, int FLAGS>
+__global__ void __launch_bounds__(LhBounds<MODEL>::max_threads, LhBounds<MODEL>::min_blocks)
+lh_soil_stage_kernel(const __grid_constant__ LhKernelArgs A)
+{
+    extern __shared__ __align__(16) double smem[];
+    lh_stage_tables(A.p, smem, (threadIdx.z * blockDim.y + threadIdx.y) * 32 + threadIdx.x, blockDim.x * blockDim.y * blockDim.z);
+    __syncthreads();
+    lh_stage_body<MODEL, STAGE, FLAGS>(A, A.io, smem);
+}
+
+// A.nsteps whole SSPRK33 steps in one launch.  A block keeps its column groups for all 3 nsteps stages: columns
+// are laterally independent, so there is no grid-wide dependency between stages, only the block's own — the
+// stage register V and the state U of the resident blocks (~60 MB for 740 blocks of 64 layers) stay in the
+// 126 MB L2 between stages, there are no launch gaps and only one tail per call instead of one per stage.
+// Used for grids of few waves (column shards of a multi-GPU run, small domains), where launch gaps and wave
+// quantisation cost more than 5 %; results are bit-identical to the per-stage launches.
+template <int MODEL, int FLAGS>
+__global__ void __launch_bounds__(LhBounds<MODEL>::max_threads, LhBounds<MODEL>::min_blocks)
+lh_soil_ssprk33_persistent_kernel(const __grid_constant__ LhKernelArgs A)
+{
+    extern __shared__ __align__(16) double smem[];
+    lh_stage_tables(A.p, smem, (threadIdx.z * blockDim.y + threadIdx.y) * 32 + threadIdx.x, blockDim.x * blockDim.y * blockDim.z);
+    __syncthreads();
+    // stage 1 as passed: in = U, out = V
+    const double* Uth = A.io.in_th;
+    const double* Ure = A.io.in_re;
+    double* Vth = A.io.out_th;
+    double* Vre = A.io.out_re;
+    for (int64_t s = 0; s < A.nsteps; ++s) {
+        LhStageIO io = A.io;
+        auto set_bcv = [&](int stage) {
+            if (A.bc_dev) {
+                const double* b = A.bc_dev + (s * 3 + stage) * 4;
+                io.bcv[0] = b[0]; io.bcv[1] = b[1]; io.bcv[2] = b[2]; io.bcv[3] = b[3];
+            }
+        };
+        set_bcv(0);
+        lh_stage_body<MODEL, 1, FLAGS>(A, io, smem);
+        __syncthreads();                       // the exchange slots and rings are reused by the next stage
+        if (MODEL != 1) io.in_th = Vth;        // the heat-only model reads the prescribed ϑ_l from U in every stage
+        if (MODEL != 0) io.in_re = Vre;
+        io.u0_th = Uth; io.u0_re = Ure;
+        set_bcv(1);
+        lh_stage_body<MODEL, 2, FLAGS>(A, io, smem);
+        __syncthreads();
+        io.out_th = const_cast<double*>(Uth); io.out_re = const_cast<double*>(Ure);
+        set_bcv(2);
+        lh_stage_body<MODEL, 3, FLAGS>(A, io, smem);
+        __syncthreads();
     }
 }
 
@@ -451,5 +502,39 @@ cudaError_t launch_model(int stage, int flags, const LhKernelArgs& args, const L
     }
 }
 
-}  // namespace
+template <int MODEL, int FLAGS>
+cudaError_t launch_persistent_variant(const LhKernelArgs& args, const LhLaunchShape& s, cudaStream_t stream)
+{
+    dim3 block(32, s.W, s.G);
+    dim3 grid((unsigned)s.nblocks);
+    static int configured_smem[64];
+    int dev = 0;
+    cudaGetDevice(&dev);
+    if (dev < 64 && configured_smem[dev] < (int)s.smem_bytes + 1) {
+        cudaError_t e;
+        const int bytes = (int)s.smem_bytes > 48 * 1024 ? (int)s.smem_bytes : 48 * 1024;
+        if ((e = cudaFuncSetAttribute(lh_soil_ssprk33_persistent_kernel<MODEL, FLAGS>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes))) return e;
+        if ((e = cudaFuncSetAttribute(lh_soil_ssprk33_persistent_kernel<MODEL, FLAGS>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared))) return e;
+        configured_smem[dev] = (int)s.smem_bytes + 1;
+    }
+    lh_soil_ssprk33_persistent_kernel<MODEL, FLAGS><<<grid, block, s.smem_bytes, stream>>>(args);
+    return cudaGetLastError();
+}
 
+template <int MODEL>
+cudaError_t launch_persistent_model(int flags, const LhKernelArgs& args, const LhLaunchShape& s, cudaStream_t stream)
+{
+    if (MODEL == 1) flags &= ~LH_FLAG_VG2;
+    switch (flags & 7) {
+    case 0: return launch_persistent_variant<MODEL, 0>(args, s, stream);
+    case 1: return launch_persistent_variant<MODEL, 1>(args, s, stream);
+    case 2: return launch_persistent_variant<MODEL, 2>(args, s, stream);
+    case 3: return launch_persistent_variant<MODEL, 3>(args, s, stream);
+    case 4: return launch_persistent_variant<MODEL, (MODEL == 1 ? 0 : 4)>(args, s, stream);
+    case 5: return launch_persistent_variant<MODEL, (MODEL == 1 ? 1 : 5)>(args, s, stream);
+    case 6: return launch_persistent_variant<MODEL, (MODEL == 1 ? 2 : 6)>(args, s, stream);
+    default: return launch_persistent_variant<MODEL, (MODEL == 1 ? 3 : 7)>(args, s, stream);
+    }
+}
+
+}  // namespace
