@@ -49,6 +49,9 @@ def parse_args():
     ap.add_argument("--nlayer", type=int, default=64)
     ap.add_argument("--general-vg", action="store_true",
                     help="never use the van Genuchten n == 2 square-root specialisation (LH_FLAG_GENERAL_VG)")
+    ap.add_argument("--launch", default="auto", choices=["auto", "stage", "persistent"],
+                    help="lh_soil_step_ssprk33 strategy: one launch per stage, one persistent launch per call, or the library's "
+                         "own choice (persistent for small launch-bound grids of <= 3 waves)")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     return ap.parse_args()
@@ -186,7 +189,7 @@ def main():
         "workload": f"{args.ncol} columns x {args.nlayer} layers, {args.model} "
                     f"(BASELINE.json configs[3]: 1M columns x 64 layers coupled water+heat)"
                     if args.model == "coupled" else f"{args.ncol} columns x {args.nlayer} layers, richards (Bonan sand)",
-        "columns": args.ncol, "layers": args.nlayer, "stepper": "SSPRK33, 3 fused RHS+stage launches per step",
+        "columns": args.ncol, "layers": args.nlayer, "stepper": "SSPRK33, fused RHS+stage kernel",
         "sharding": f"contiguous column ranges over {world} GPU(s), no halo",
         "l2": "state (2.7 GB at N=1) is larger than the 126 MB L2; no flush needed",
         "closures": "general van Genuchten n (log/exp form)" if (args.general_vg or args.model != "coupled")
@@ -224,7 +227,9 @@ def main():
     wl = make_workload(w, args.model, args.ncol, args.nlayer, (lo, hi))
     wl.device = local_rank
     lib = lh.cuda_library()
-    ctx = lh.SoilContext(lib, wl.config(flags=lh._abi.LH_FLAG_GENERAL_VG if args.general_vg else 0))
+    flags = (lh._abi.LH_FLAG_GENERAL_VG if args.general_vg else 0) | \
+            {"auto": 0, "stage": lh._abi.LH_FLAG_STAGE_LAUNCHES, "persistent": lh._abi.LH_FLAG_PERSISTENT}[args.launch]
+    ctx = lh.SoilContext(lib, wl.config(flags=flags))
     host = {fid: pinned_like(a) for fid, a in wl.fields.items()}
     for fid, a in host.items():
         ctx.set_state(fid, a)
@@ -314,22 +319,38 @@ def main():
     cells_total = args.ncol * args.nlayer
     value = cells_total * args.steps / (ms_max * 1e-3)
     peak, peak_src = load_peaks()
-    bpcs = BYTES_PER_CELL_STEP[args.model]
-    # dominant kernel = lh_soil_stage_kernel<model, stage 1|2|3>: every launch in the timed region is one
-    # of its three stage instantiations; per-launch figures are the averages over the 3K launches.
     cells_rank = (hi - lo) * args.nlayer
-    bytes_per_launch = cells_rank * bpcs / 3.0
-    launch_ms = ms_max / (3 * args.steps)
+    persistent = int(launches) != 3 * args.steps
+    if not persistent:
+        # dominant kernel = lh_soil_stage_kernel<model, stage 1|2|3>: every launch in the timed region is one of its three
+        # stage instantiations; per-launch figures are the averages over the 3K launches.
+        bpcs = BYTES_PER_CELL_STEP[args.model]
+        bytes_per_launch = cells_rank * bpcs / 3.0
+        launch_ms = ms_max / (3 * args.steps)
+        kernel = "lh_soil_stage_kernel (fused closures + stencil + SSPRK33 stage)"
+        note = ("per-launch average over the 3 stage launches of each step (40/56/56 B per cell coupled, 24/32/32 Richards); "
+                "besides HBM the kernel is bounded by issue slots: an fp64 instruction holds the issue port for two "
+                "cycles on B200 (DESIGN.md §4.1)")
+    else:
+        # one persistent launch for all K steps: a block keeps its columns, the stage registers stay in L2, and the
+        # compulsory traffic of a launch is one read of the state and one write of the prognostic fields per STEP
+        bpcs = {"coupled": 40, "richards": 24}[args.model]
+        bytes_per_launch = cells_rank * bpcs * args.steps / max(int(launches), 1)
+        launch_ms = ms_max / max(int(launches), 1)
+        kernel = "lh_soil_ssprk33_persistent_kernel (all stages of all steps in one launch, columns L2-resident)"
+        note = ("persistent launch (grid of few waves): algorithmic bytes are 40 B (coupled) / 24 B (Richards) per cell-STEP, "
+                "the path is issue-bound, not HBM-bound (DESIGN.md §4.1)")
     achieved = bytes_per_launch / (launch_ms * 1e-3) / 1e9
     traffic = None
     tpath = os.path.join(ROOT, "profiles", "dram_traffic.json")
-    if os.path.exists(tpath):
+    if os.path.exists(tpath) and not persistent:
         try:
             traffic = json.load(open(tpath)).get(f"{args.model}_{args.ncol}x{args.nlayer}_bytes_per_launch")
             if traffic is not None:
                 traffic = traffic * cells_rank / (args.ncol * args.nlayer)     # measured at N = 1; per launch of this rank's shard
         except Exception:
             traffic = None
+    config["launch"] = "persistent (1 launch per call)" if persistent else "3 launches per step"
     line = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": ms_max / args.steps, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
@@ -338,11 +359,7 @@ def main():
         "roofline": {
             "bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
             "traffic": traffic, "peak_source": peak_src,
-            "kernel": "lh_soil_stage_kernel (fused closures + stencil + SSPRK33 stage)",
-            "algorithmic_bytes_per_cell_step": bpcs, "launch_ms": launch_ms,
-            "note": "per-launch average over the 3 stage launches of each step (40/56/56 B per cell coupled, 24/32/32 Richards); "
-                    "besides HBM the kernel is bounded by issue slots: an fp64 instruction holds the issue port for two "
-                    "cycles on B200 (DESIGN.md §4.1)",
+            "kernel": kernel, "algorithmic_bytes_per_cell_step": bpcs, "launch_ms": launch_ms, "note": note,
         },
         "budgets": {"water": float(budgets[0]), "energy": float(budgets[1]), "allreduce_ms": budget_ms},
     }

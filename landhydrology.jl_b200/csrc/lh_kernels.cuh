@@ -13,6 +13,9 @@
 #ifndef LH_ILP2
 #define LH_ILP2 0      // 1: issue both cells' loads before either closure chain (measured: no gain)
 #endif
+#ifndef LH_PDL
+#define LH_PDL 1      // programmatic dependent launch between consecutive stage kernels
+#endif
 #ifndef LH_MIN_BLOCKS
 #define LH_MIN_BLOCKS 5
 #endif

@@ -101,7 +101,10 @@ __device__ __forceinline__ Flux boundary_flux(const LhDevParams& p, const double
 }
 
 // STAGE: 0 tendency; 1, 2, 3 the SSPRK33 stages; 4 a generic two-register Shu-Osher stage
-// (a u^n + b u_{i-1} + g dt f); 5 a Williamson 2N stage (r = a r + dt f, u = u + b r), include/lh_soil.h.
+// (a u^n + b u_{i-1} + g dt f); 5 a Williamson 2N stage (r = a r + dt f, u = u + b r), include/lh_soil.h;
+// 6 an SSPRK33 stage chosen at RUN time, sg (sa u0 + sb v + cdt dF) with (sa, sb, sg) = (0, 1, 1), (3, 1, 1/4),
+// (1, 2, 1/3): bit-identical to stages 1, 2, 3 (the products with 0, 1, 2 are exact) — one loop body for the
+// persistent kernel instead of three.
 template <int STAGE>
 __device__ __forceinline__ double stage_base(const LhStageIO& io, double v, double u0)
 {
@@ -109,6 +112,7 @@ __device__ __forceinline__ double stage_base(const LhStageIO& io, double v, doub
     else if constexpr (STAGE == 3) return fma(2.0, v, u0);  // u0 + 2 u2
     else if constexpr (STAGE == 4) return fma(io.sa, u0, io.sb * v);
     else if constexpr (STAGE == 5) return io.first2n ? 0.0 : io.sa * u0;   // a r (r is not read as a number in the first stage)
+    else if constexpr (STAGE == 6) return fma(io.sa, u0, io.sb * v);
     else return v;
 }
 
@@ -116,8 +120,9 @@ __device__ __forceinline__ double stage_base(const LhStageIO& io, double v, doub
 //   stage 0: k     1: base + dt k     2: (base + dt k)/4     3: (base + 2 dt k)/3     4: base + g dt k     5: base + dt k
 // are evaluated as  s (base + cdt (F_hi - F_lo))  with cdt = -dt/dz (stage 3: -2 dt/dz; stage 0: -1/dz; stage 4: -g dt/dz).
 template <int STAGE>
-__device__ __forceinline__ double stage_out(double base, double dF, double cdt)
+__device__ __forceinline__ double stage_out(double base, double dF, double cdt, double sg)
 {
+    if constexpr (STAGE == 6) return sg * fma(cdt, dF, base);
     if constexpr (STAGE == 0) return cdt * dF;
     else if constexpr (STAGE == 1 || STAGE == 4 || STAGE == 5) return fma(cdt, dF, base);
     else if constexpr (STAGE == 2) return 0.25 * fma(cdt, dF, base);
@@ -271,17 +276,17 @@ __device__ __forceinline__ void lh_stage_body(const LhKernelArgs& A, const LhSta
         o.base.re2 = (STAGE == 5 && MODEL != 0) ? r.x : 0.0;
         return o;
     };
-    const double cdt = STAGE == 0 ? -p.inv_dz : (STAGE == 3 ? -2.0 * (io.dt * p.inv_dz) : STAGE == 4 ? -((io.sg * io.dt) * p.inv_dz) : -(io.dt * p.inv_dz));
+    const double cdt = STAGE == 6 ? io.dt /* the caller passes cdt itself */ : STAGE == 0 ? -p.inv_dz : (STAGE == 3 ? -2.0 * (io.dt * p.inv_dz) : STAGE == 4 ? -((io.sg * io.dt) * p.inv_dz) : -(io.dt * p.inv_dz));
     double* o2th = io.out2_th + col;     // 2N stages: the residual register r
     double* o2re = io.out2_re + col;
     auto store_cell = [&](int64_t o, const Base& base, const Flux& lo, const Flux& hi) {
         if constexpr (MODEL != 1) {
-            const double v = stage_out<STAGE>(base.th, hi.w - lo.w, cdt);
+            const double v = stage_out<STAGE>(base.th, hi.w - lo.w, cdt, io.sg);
             if constexpr (STAGE == 5) { o2th[o] = v; oth[o] = fma(io.sb, v, base.th2); }
             else oth[o] = v;
         }
         if constexpr (MODEL != 0) {
-            const double v = stage_out<STAGE>(base.re, hi.e - lo.e, cdt);
+            const double v = stage_out<STAGE>(base.re, hi.e - lo.e, cdt, io.sg);
             if constexpr (STAGE == 5) { o2re[o] = v; ore[o] = fma(io.sb, v, base.re2); }
             else ore[o] = v;
         }
@@ -401,7 +406,17 @@ __global__ void __launch_bounds__(LhBounds<MODEL>::max_threads, LhBounds<MODEL>:
 lh_soil_stage_kernel(const __grid_constant__ LhKernelArgs A)
 {
     extern __shared__ __align__(16) double smem[];
+#if LH_PDL
+    // Programmatic dependent launch: the NEXT stage's blocks may be scheduled as soon as this grid's blocks have
+    // all started, into the SM slots its last wave frees; they stage their tables (parameter block only) and then
+    // wait here until the previous stage has completed and flushed.  Hides the launch gap and the block prologue
+    // behind the previous stage's tail — what matters when a launch is only ~80 us (column shards at 8 GPUs).
+    asm volatile("griddepcontrol.launch_dependents;");
+#endif
     lh_stage_tables(A.p, smem, (threadIdx.z * blockDim.y + threadIdx.y) * 32 + threadIdx.x, blockDim.x * blockDim.y * blockDim.z);
+#if LH_PDL
+    asm volatile("griddepcontrol.wait;" ::: "memory");
+#endif
     __syncthreads();
     lh_stage_body<MODEL, STAGE, FLAGS>(A, A.io, smem);
 }
@@ -424,27 +439,26 @@ lh_soil_ssprk33_persistent_kernel(const __grid_constant__ LhKernelArgs A)
     const double* Ure = A.io.in_re;
     double* Vth = A.io.out_th;
     double* Vre = A.io.out_re;
-    for (int64_t s = 0; s < A.nsteps; ++s) {
+    const double cdt1 = -(A.io.dt * A.p.inv_dz), cdt3 = -2.0 * (A.io.dt * A.p.inv_dz);    // as stages 1/2 and 3 form them
+    int st = 0;                                   // 0, 1, 2: which SSPRK33 stage
+    for (int64_t k = 0; k < 3 * A.nsteps; ++k) {
         LhStageIO io = A.io;
-        auto set_bcv = [&](int stage) {
-            if (A.bc_dev) {
-                const double* b = A.bc_dev + (s * 3 + stage) * 4;
-                io.bcv[0] = b[0]; io.bcv[1] = b[1]; io.bcv[2] = b[2]; io.bcv[3] = b[3];
-            }
-        };
-        set_bcv(0);
-        lh_stage_body<MODEL, 1, FLAGS>(A, io, smem);
-        __syncthreads();                       // the exchange slots and rings are reused by the next stage
-        if (MODEL != 1) io.in_th = Vth;        // the heat-only model reads the prescribed ϑ_l from U in every stage
-        if (MODEL != 0) io.in_re = Vre;
+        if (MODEL != 1) io.in_th = st == 0 ? Uth : Vth;     // the heat-only model reads the prescribed ϑ_l from U in every stage
+        if (MODEL != 0) io.in_re = st == 0 ? Ure : Vre;
         io.u0_th = Uth; io.u0_re = Ure;
-        set_bcv(1);
-        lh_stage_body<MODEL, 2, FLAGS>(A, io, smem);
-        __syncthreads();
-        io.out_th = const_cast<double*>(Uth); io.out_re = const_cast<double*>(Ure);
-        set_bcv(2);
-        lh_stage_body<MODEL, 3, FLAGS>(A, io, smem);
-        __syncthreads();
+        io.out_th = st == 2 ? const_cast<double*>(Uth) : Vth;
+        io.out_re = st == 2 ? const_cast<double*>(Ure) : Vre;
+        io.sa = st == 0 ? 0.0 : st == 1 ? 3.0 : 1.0;
+        io.sb = st == 2 ? 2.0 : 1.0;
+        io.sg = st == 0 ? 1.0 : st == 1 ? 0.25 : 1.0 / 3.0;
+        io.dt = st == 2 ? cdt3 : cdt1;
+        if (A.bc_dev) {
+            const double* b = A.bc_dev + k * 4;
+            io.bcv[0] = b[0]; io.bcv[1] = b[1]; io.bcv[2] = b[2]; io.bcv[3] = b[3];
+        }
+        lh_stage_body<MODEL, 6, FLAGS>(A, io, smem);
+        __syncthreads();                          // the exchange slots and rings are reused by the next stage
+        st = st == 2 ? 0 : st + 1;
     }
 }
 
@@ -474,16 +488,25 @@ cudaError_t launch_variant(int stage, const LhKernelArgs& args, const LhLaunchSh
         if ((e = configure(lh_soil_stage_kernel<MODEL, 5, FLAGS>))) return e;
         configured_smem[dev] = (int)s.smem_bytes + 1;
     }
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = grid;
+    cfg.blockDim = block;
+    cfg.dynamicSmemBytes = s.smem_bytes;
+    cfg.stream = stream;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = LH_PDL;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
     switch (stage) {
-    case 0: lh_soil_stage_kernel<MODEL, 0, FLAGS><<<grid, block, s.smem_bytes, stream>>>(args); break;
-    case 1: lh_soil_stage_kernel<MODEL, 1, FLAGS><<<grid, block, s.smem_bytes, stream>>>(args); break;
-    case 2: lh_soil_stage_kernel<MODEL, 2, FLAGS><<<grid, block, s.smem_bytes, stream>>>(args); break;
-    case 3: lh_soil_stage_kernel<MODEL, 3, FLAGS><<<grid, block, s.smem_bytes, stream>>>(args); break;
-    case 4: lh_soil_stage_kernel<MODEL, 4, FLAGS><<<grid, block, s.smem_bytes, stream>>>(args); break;
-    case 5: lh_soil_stage_kernel<MODEL, 5, FLAGS><<<grid, block, s.smem_bytes, stream>>>(args); break;
+    case 0: return cudaLaunchKernelEx(&cfg, lh_soil_stage_kernel<MODEL, 0, FLAGS>, args);
+    case 1: return cudaLaunchKernelEx(&cfg, lh_soil_stage_kernel<MODEL, 1, FLAGS>, args);
+    case 2: return cudaLaunchKernelEx(&cfg, lh_soil_stage_kernel<MODEL, 2, FLAGS>, args);
+    case 3: return cudaLaunchKernelEx(&cfg, lh_soil_stage_kernel<MODEL, 3, FLAGS>, args);
+    case 4: return cudaLaunchKernelEx(&cfg, lh_soil_stage_kernel<MODEL, 4, FLAGS>, args);
+    case 5: return cudaLaunchKernelEx(&cfg, lh_soil_stage_kernel<MODEL, 5, FLAGS>, args);
     default: return cudaErrorInvalidValue;
     }
-    return cudaGetLastError();
 }
 
 template <int MODEL>

@@ -53,7 +53,7 @@ def test_persistent_is_bit_identical(cuda, name, with_table):
 
 def test_automatic_choice_and_oracle(cuda, oracle):
     """Small grids take the persistent launch on their own; large ones keep one launch per stage."""
-    small = w.coupled_workload(ncol=4096, nlayer=64, seed=71)
+    small = w.coupled_workload(ncol=2048, nlayer=64, seed=71)
     g, o = lh.SoilContext(cuda, small.config()), lh.SoilContext(oracle, small.config())
     for ctx in (g, o):
         small.upload(ctx)
