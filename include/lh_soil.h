@@ -107,7 +107,7 @@ typedef struct lh_soil_params {
     /* vanGenuchten */
     double vg_n;
     double vg_alpha;
-    double vg_m;               /* 1 - 1/n, as stored by the reference constructor */
+    double vg_m;               /* 1 - 1/n, as stored by the reference constructor (anything else: LH_ERR_INVALID_ARG) */
     double theta_r;
     double Ksat;
     /* conductivity factors */

@@ -9,6 +9,7 @@
 //     u = log2(S)/m           y = S^(1/m) = 2^u          w = 1 - y = -exp2m1(u)
 //     a = log2(w)
 //     psi = -((S^(-1/m) - 1) alpha^(-n))^(1/n) = -(1/alpha) exp2((a - u)/n)
+//         = -(1/alpha) w S / (y W),  W = (1 - y)^m,  when m = 1 - 1/n (Mualem, the reference's constructor)
 //     K   = Ksat sqrt(S) (1 - (1 - y)^m)^2     = Ksat sqrt(S) exp2m1(m a)^2
 //
 // which is also better conditioned than the literal form (1 - y and 1 - (1-y)^m are formed by
@@ -133,9 +134,9 @@ __device__ __forceinline__ void lh_water_closures(const LhDevParams& p, const do
         // ---- general n: pressure head (:229-242) and the shared logs
         const double L_eff = lh_log2(mc, tab, S_eff);
         const double u = L_eff * p.vg_inv_m;
-        const double w = lh_one_minus_exp2(mc, tab, u);                      // 1 - S^(1/m)
+        const LhExpParts ey = lh_exp2_parts(mc, tab, u);                     // y = S^(1/m) = s (1 + p)
+        const double w = lh_fma(-ey.s, ey.p, 1.0 - ey.s);                    // 1 - y; its zero is +0
         const double a = lh_log2(mc, tab, w);
-        psi_unsat = p.neg_inv_alpha * lh_exp2(mc, tab, (a - u) * p.vg_inv_n);
         // ---- hydraulic conductivity (:269-282)
         double a_K = a;
         L_K = L_eff;
@@ -143,8 +144,20 @@ __device__ __forceinline__ void lh_water_closures(const LhDevParams& p, const do
             L_K = lh_log2(mc, tab, S_K);
             a_K = lh_log2(mc, tab, lh_one_minus_exp2(mc, tab, L_K * p.vg_inv_m));
         }
-        const double q = lh_exp2m1(mc, tab, p.vg_m * a_K);                   // (1 - y)^m - 1
+        const LhExpParts eW = lh_exp2_parts(mc, tab, p.vg_m * a_K);          // W = (1 - y)^m
+        const double q = lh_fma(eW.s, eW.p, eW.s - 1.0);                     // W - 1
         Kr_unsat = (S_K * lh_rsqrt(S_K)) * (q * q);                          // sqrt(S) = S rsqrt(S): S >= eps > 0 here
+        if (!icy) {
+            // Mualem's m = 1 - 1/n (what the reference constructor stores, SoilWaterParameterizations.jl:162-169;
+            // lh_soil_create rejects anything else):
+            // 1/n = 1 - m and y^m = S, so ((1 - y)/y)^(1/n) = (w/y) (y/w)^m = w S / (y W) with the W of the
+            // conductivity: a reciprocal instead of a third exp2.
+            const double y = lh_fma(ey.s, ey.p, ey.s);
+            const double W = lh_fma(eW.s, eW.p, eW.s);
+            psi_unsat = p.neg_inv_alpha * ((w * S_eff) * lh_rcp(y * W));
+        } else {
+            psi_unsat = p.neg_inv_alpha * lh_exp2(mc, tab, (a - u) * p.vg_inv_n);
+        }
     }
     const double psi = (S_eff <= 1.0) ? psi_unsat : psi_sat;
     const double Kr = (S_K < 1.0) ? Kr_unsat : 1.0;

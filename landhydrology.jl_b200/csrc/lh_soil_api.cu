@@ -443,6 +443,10 @@ int32_t lh_soil_create(const lh_soil_config* cfg, lh_soil_ctx** out)
     if (cfg->ncol < 1 || cfg->nlayer < 1) return fail(nullptr, LH_ERR_INVALID_ARG, "ncol and nlayer must be >= 1");
     if (cfg->model < 0 || cfg->model > 2) return fail(nullptr, LH_ERR_INVALID_ARG, "unknown model kind %d", cfg->model);
     if (!(cfg->zmin < cfg->zmax)) return fail(nullptr, LH_ERR_DOMAIN, "zlim[1] < zlim[2] violated");   // domain.jl:30
+    // vanGenuchten{FT}(; n, α, Ksat, θr) stores m = 1 - 1/n (SoilWaterParameterizations.jl:162-169); the closures use
+    // 1/n = 1 - m (lh_closures.cuh)
+    if (!(fabs(cfg->params.vg_m - (1.0 - 1.0 / cfg->params.vg_n)) <= 4.0 * LH_EPS))
+        return fail(nullptr, LH_ERR_INVALID_ARG, "vg_m must be 1 - 1/vg_n (van Genuchten-Mualem, as the reference constructor stores it)");
     int32_t st;
     if ((st = validate_face(cfg->top, cfg->model, "top")) != LH_OK) return st;
     if ((st = validate_face(cfg->bottom, cfg->model, "bottom")) != LH_OK) return st;

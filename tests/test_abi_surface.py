@@ -116,6 +116,16 @@ def test_no_cpu_fallback():
         lh.SoilContext(lh.cuda_library(), wl.config())
 
 
+def test_config_validation_needs_no_device():
+    """lh_soil_create validates the config before it looks for a device: the reference constructor stores
+    m = 1 - 1/n (SoilWaterParameterizations.jl:162-169) and the closures rely on it."""
+    wl = w.richards_workload(ncol=2, nlayer=4)
+    wl.params.vg_m = 0.6
+    with pytest.raises(lh._abi.SoilError) as e:
+        lh.SoilContext(lh.cuda_library(), wl.config())
+    assert e.value.status == lh._abi.LH_ERR_INVALID_ARG and "vg_m" in str(e.value)
+
+
 def test_product_never_references_oracle():
     """Nothing in the package directory names the oracle directory or library."""
     pkg = os.path.join(ROOT, "landhydrology.jl_b200")
