@@ -37,6 +37,7 @@ struct LhDevParams {
     // water
     double nu, theta_r, theta_r_eps;   // theta_r + eps(Float64)
     double inv_nu_thr;                 // 1 / (nu - theta_r)
+    double nu_thr;                     // nu - theta_r
     double S_s_inv;                    // 1 / S_s
     double vg_m, vg_inv_m, vg_inv_n;
     double neg_inv_alpha;              // -1 / alpha
@@ -113,7 +114,15 @@ __device__ __forceinline__ void lh_water_closures(const LhDevParams& p, const do
     const double S_K = num * p.inv_nu_thr;                                   // porosity = nu (:163/:311)
     const bool icy = ICE && (ti != 0.0);
     double S_eff = S_K;                                                      // porosity = nu_eff (:235)
-    if (icy) S_eff = lh_div(num, nu_eff - p.theta_r);
+    const double den_K = THR0 ? p.nu : p.nu_thr;
+    double den_eff = den_K;
+    if (icy) { den_eff = nu_eff - p.theta_r; S_eff = lh_div(num, den_eff); }
+    // The reference branches on the ROUNDED quotients (S_l_eff <= 1, S < 1).  A correctly rounded num/den is < 1
+    // exactly when num < den, and at num == den both branches of the pressure head give 0, so the branches are
+    // decided on num and den themselves: the product num (1/den) used for S here can be 1 - 2^-53 where the
+    // quotient is exactly 1 (it is for ~15 % of (nu, theta_r) pairs), and a cell that sits exactly at saturation
+    // would otherwise get psi = -(1/alpha) sqrt(2^-52) and K (1 - 3e-8) instead of 0 and K_sat.
+    const bool unsat_eff = num < den_eff, unsat_K = num < den_K;
     const double psi_sat = (th - nu_eff) * p.S_s_inv;
     double psi_unsat, Kr_unsat, L_K = 0.0;
 
@@ -159,8 +168,8 @@ __device__ __forceinline__ void lh_water_closures(const LhDevParams& p, const do
             psi_unsat = p.neg_inv_alpha * lh_exp2(mc, tab, (a - u) * p.vg_inv_n);
         }
     }
-    const double psi = (S_eff <= 1.0) ? psi_unsat : psi_sat;
-    const double Kr = (S_K < 1.0) ? Kr_unsat : 1.0;
+    const double psi = unsat_eff ? psi_unsat : psi_sat;
+    const double Kr = unsat_K ? Kr_unsat : 1.0;
     double K = Kr * p.Ksat;
     if (GEN) {
         if (p.visc_on) K *= lh_exp2(mc, tab, p.visc_gamma_l2e * (T - p.visc_T_ref));   // :117-126

@@ -158,6 +158,7 @@ LhDevParams derive_params(const lh_soil_config& cfg)
     d.theta_r = q.theta_r;
     d.theta_r_eps = q.theta_r + LH_EPS;
     d.inv_nu_thr = 1.0 / (q.nu - q.theta_r);
+    d.nu_thr = q.nu - q.theta_r;
     d.S_s_inv = 1.0 / q.S_s;
     d.vg_m = q.vg_m;
     d.vg_inv_m = 1.0 / q.vg_m;

@@ -168,6 +168,34 @@ def test_saturated_cells(cuda, oracle):
     assert_tendency_parity(g, o, wl.model)
 
 
+@pytest.mark.parametrize("nu,theta_r", [(0.4547846749285817, 0.002831967114546297), (0.44265431030687197, 0.09972099357892111),
+                                         (0.287, 0.075)])
+def test_exactly_saturated_cells(cuda, oracle, nu, theta_r):
+    """ϑ_l == ν bit for bit (a saturated initial condition, a ponded Dirichlet top): the reference's quotient is exactly 1
+    there, K = K_sat and ψ = 0.  The first two (ν, θr) pairs are ones for which (ν - θr) * (1 / (ν - θr)) rounds to
+    1 - 2^-53, i.e. a device S computed with the reciprocal would fall on the wrong side of the S < 1 branches."""
+    for make in (w.richards_workload, w.coupled_workload):
+        wl = make(ncol=40, nlayer=24, seed=33, top=(w.F if make is w.coupled_workload else w.N, 0.0, w.D, nu),
+                  bottom=(w.F if make is w.coupled_workload else w.N, 0.0, w.FD, 0.0))
+        p = wl.params
+        S = (wl.fields[0] - p.theta_r) / (p.nu - p.theta_r)
+        p.nu, p.theta_r = nu, theta_r
+        if make is w.coupled_workload:
+            p.vg_n, p.vg_m = 1.9, 1.0 - 1.0 / 1.9          # general-n closures with theta_r != 0
+        th = theta_r + S * (nu - theta_r)
+        th[:, 8:14] = nu                                     # a saturated band, and the boundary cells
+        th[::2, 0] = nu
+        th[1::2, -1] = nu
+        wl.fields[0] = th
+        if 2 in wl.fields:
+            wl.fields[2] = w.rho_e_int_from_T(p, th, wl.fields[1], w.temperature_profiles(33, (0, 40), 24, wl.zmin, wl.zmax))
+        g, o = _pair(cuda, oracle, wl)
+        assert_tendency_parity(g, o, wl.model)
+        for which in (abi.LH_DIAG_K, abi.LH_DIAG_PSI):
+            a = g.diagnostic(which)
+            assert np.all(a[:, 8:14] == (p.Ksat if which == abi.LH_DIAG_K else 0.0))
+
+
 def test_dry_soil_heat(cuda, oracle):
     """θ_w < eps: κ_sat = 0, κ = κ_dry (SoilHeatParameterizations.jl:121-123) — the analytic heat
     test's regime (heat_test_interface.jl)."""
