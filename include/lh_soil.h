@@ -185,6 +185,15 @@ int32_t lh_soil_get_state(lh_soil_ctx* ctx, int32_t field, double* host,
 int32_t lh_soil_set_aux(lh_soil_ctx* ctx, int32_t field, const double* host,
                         int64_t col_stride, int64_t layer_stride);
 
+/* Heterogeneous soils: per-column hydraulic parameters (new; the reference's SoilParams / vanGenuchten are one
+ * set of scalars per model, parameters.jl:11-43, SoilWaterParameterizations.jl:151-170 — a land model over many
+ * columns needs them per column).  Each array holds ncol doubles; NULL keeps the model's scalar for that parameter;
+ * all NULL returns to the homogeneous kernels.  m = 1 - 1/n per column, as the reference constructor computes it;
+ * κ_dry follows ν per column (k_dry, SoilHeatParameterizations.jl:280-294).  The kernels then read these values per
+ * lane (one load per column and launch, +96 B per column, nothing per cell).                                    */
+int32_t lh_soil_set_column_params(lh_soil_ctx* ctx, const double* nu, const double* theta_r,
+                                  const double* vg_n, const double* vg_alpha, const double* Ksat);
+
 /* Boundary values for the NEXT rhs/stage call: the host evaluates Dirichlet
  * `state_value(t)` closures (boundary_conditions.jl:247,267) and passes 4 doubles indexed
  * by LH_BCV_*.                                                                              */

@@ -130,6 +130,7 @@ _SIGNATURES = {
     "soil_set_state": ([_vp, C.c_int32, _dp, C.c_int64, C.c_int64], C.c_int32),
     "soil_get_state": ([_vp, C.c_int32, _dp, C.c_int64, C.c_int64], C.c_int32),
     "soil_set_aux": ([_vp, C.c_int32, _dp, C.c_int64, C.c_int64], C.c_int32),
+    "soil_set_column_params": ([_vp, _dp, _dp, _dp, _dp, _dp], C.c_int32),
     "soil_set_bc_values": ([_vp, _dp], C.c_int32),
     "soil_rhs": ([_vp, C.c_double], C.c_int32),
     "soil_get_tendency": ([_vp, C.c_int32, _dp, C.c_int64, C.c_int64], C.c_int32),
@@ -305,6 +306,20 @@ class SoilContext:
         cs, ls = self._strides(out)
         self._check(self.lib.soil_diagnostic(self._h, which, _as_double_ptr(out), cs, ls))
         return out
+
+    def set_column_params(self, nu=None, theta_r=None, vg_n=None, vg_alpha=None, Ksat=None):
+        """Per-column hydraulic parameters (``lh_soil_set_column_params``); ``None`` keeps the model's scalar."""
+        ptrs, keep = [], []
+        for a in (nu, theta_r, vg_n, vg_alpha, Ksat):
+            if a is None:
+                ptrs.append(None)
+                continue
+            a = np.ascontiguousarray(a, dtype=np.float64)
+            if a.shape != (self.ncol,):
+                raise ValueError(f"per-column parameter must have shape ({self.ncol},)")
+            keep.append(a)
+            ptrs.append(_as_double_ptr(a))
+        self._check(self.lib.soil_set_column_params(self._h, *ptrs))
 
     def set_bc_values(self, values: Sequence[float]):
         v = np.asarray(values, dtype=np.float64)

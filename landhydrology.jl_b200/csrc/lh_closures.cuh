@@ -30,7 +30,7 @@
 
 // Host-derived constants (all fp64, computed once in lh_soil_create).  Passed to kernels by
 // value (__grid_constant__), so every use is a constant-bank operand, not a register.
-struct LhDevParams {
+struct LhPhys {
     // geometry
     double dz, inv_dz, half_dz, inv_half_dz;
     double neg_half_inv_dz;            // -1 / (2 dz): interior face fluxes
@@ -58,8 +58,23 @@ struct LhDevParams {
     int32_t visc_on, imp_on;
     int32_t om_zero;                   // nu_ss_om == 0: outer Kersten exponents are exactly 1
     int32_t pad_;
-    double mc[LHC_COUNT];              // elementary-function coefficients (lh_math.cuh)
 };
+
+// The uniform parameter block of a launch: physics + the elementary-function coefficients and tables.
+struct LhDevParams : LhPhys {
+    double mc[LHC_COUNT];              // lh_math.cuh
+};
+
+// The same physics seen by ONE lane when the hydraulic parameters differ from column to column
+// (lh_soil_set_column_params): a per-thread copy whose column-dependent members were overwritten; the members
+// that stay uniform still come from the parameter block (constant propagation through the copy).
+struct LhLaneParams : LhPhys {
+    const double* mc;
+};
+
+// Per-column derived parameters, one [ncol_pad] array each (lh_soil_api.cu derive_column_params).
+enum { LHCP_NU, LHCP_THETA_R, LHCP_THETA_R_EPS, LHCP_INV_NU_THR, LHCP_NU_THR, LHCP_VG_M, LHCP_VG_INV_M, LHCP_VG_INV_N,
+       LHCP_NEG_INV_ALPHA, LHCP_KSAT, LHCP_INV_NU, LHCP_KAPPA_DRY, LHCP_COUNT };
 
 // Copies the exp2 / log2 tables from the parameter block to shared memory (LH_TAB_DOUBLES doubles, 16-byte
 // aligned destination); the caller must __syncthreads().
@@ -93,6 +108,9 @@ struct LhCell {
 #define LH_FLAG_ICE 1
 #define LH_FLAG_GEN 2
 #define LH_FLAG_VG2 4
+//   HET : per-column hydraulic parameters (lh_soil_set_column_params): nu, theta_r, van Genuchten n and alpha, Ksat
+//         and what derives from them are per-lane values.  Implies GEN and excludes VG2.
+#define LH_FLAG_HET 8
 
 // ---------------------------------------------------------------------------------------------
 // Water: K and psi of one cell.  Reference: right_hand_side.jl:156-166 / :308-313.
@@ -101,8 +119,8 @@ struct LhCell {
 // results: the unsaturated expressions are evaluated unconditionally (they are the common case and
 // yield NaN/garbage only where the select discards them).
 // ---------------------------------------------------------------------------------------------
-template <bool ICE, bool GEN, bool VG2, bool NEED_LOG, bool THR0 = false>
-__device__ __forceinline__ void lh_water_closures(const LhDevParams& p, const double* __restrict__ tab,
+template <bool ICE, bool GEN, bool VG2, bool NEED_LOG, bool THR0 = false, class P = LhDevParams>
+__device__ __forceinline__ void lh_water_closures(const P& p, const double* __restrict__ tab,
                                                   double th, double ti, double T,
                                                   double& K_out, double& psi_out, double& logS_K)
 {
@@ -192,8 +210,8 @@ __device__ __forceinline__ void lh_water_closures(const LhDevParams& p, const do
 //   is saturated, so no second log is needed.  (For ϑ_l <= eps the two differ, but there the
 //   Kersten base E3 - c^3 is ~0 and K_e vanishes either way.)
 // ---------------------------------------------------------------------------------------------
-template <bool ICE, bool GEN, bool REUSE>
-__device__ __forceinline__ double lh_thermal_conductivity(const LhDevParams& p, const double* __restrict__ tab,
+template <bool ICE, bool GEN, bool REUSE, class P = LhDevParams>
+__device__ __forceinline__ double lh_thermal_conductivity(const P& p, const double* __restrict__ tab,
                                                           double tl, double ti, bool unsat, double logS)
 {
     const double* __restrict__ mc = p.mc;
@@ -219,7 +237,7 @@ __device__ __forceinline__ double lh_thermal_conductivity(const LhDevParams& p, 
         // K_e kappa_sat + (1 - K_e) kappa_dry = kappa_dry + K_e (kappa_unfrozen - kappa_dry): one FMA.
         // The theta_w < eps case (kappa_sat = 0) needs no select: there S_r -> 0, the Kersten base
         // E3 - c^3 -> 1/8 - 1/8 and K_e vanishes, so kappa = kappa_dry either way.
-        return lh_fma(K_e, p.k_unfrozen_minus_dry, p.kappa_dry);
+        return lh_fma(K_e, p.k_unfrozen_minus_dry, p.kappa_dry);   // (the per-column view overrides both members)
     }
     double k_sat = p.k_unfrozen;                                             // :114-128; x^1 * y^0 is exact
     if (ti != 0.0) k_sat = lh_exp2(mc, tab, lh_div(tl * p.log2_k_unfrozen + ti * p.log2_k_frozen, tw));
@@ -228,8 +246,8 @@ __device__ __forceinline__ double lh_thermal_conductivity(const LhDevParams& p, 
 }
 
 // Temperature from ρe_int (SoilHeatParameterizations.jl:42-79): returns T - T_0 (the quotient); T = T_0 + it.
-template <bool ICE>
-__device__ __forceinline__ double lh_temperature_minus_T0(const LhDevParams& p, double tl, double ti, double re)
+template <bool ICE, class P = LhDevParams>
+__device__ __forceinline__ double lh_temperature_minus_T0(const P& p, double tl, double ti, double re)
 {
     if (ICE) {
         const double rho_c_s = p.rho_c_ds + tl * p.rhocp_l + ti * p.rhocp_i; // :65-79
@@ -241,8 +259,8 @@ __device__ __forceinline__ double lh_temperature_minus_T0(const LhDevParams& p, 
 
 // All closures of one cell for model MODEL (0 Richards, 1 heat, 2 coupled).
 //   Richards: T_or_re = prescribed T.   heat/coupled: T_or_re = ρe_int.
-template <int MODEL, int FLAGS>
-__device__ __forceinline__ LhCell lh_cell_closures(const LhDevParams& p, const double* __restrict__ tab,
+template <int MODEL, int FLAGS, class P = LhDevParams>
+__device__ __forceinline__ LhCell lh_cell_closures(const P& p, const double* __restrict__ tab,
                                                    double th, double ti, double T_or_re)
 {
     constexpr bool ICE = (FLAGS & LH_FLAG_ICE) != 0, GEN = (FLAGS & LH_FLAG_GEN) != 0, VG2 = (FLAGS & LH_FLAG_VG2) != 0;
@@ -267,8 +285,8 @@ __device__ __forceinline__ LhCell lh_cell_closures(const LhDevParams& p, const d
 }
 
 // κ at a boundary "face state" (boundary_conditions.jl:429-436).
-template <int FLAGS>
-__device__ __forceinline__ double lh_face_kappa(const LhDevParams& p, const double* __restrict__ tab, double th, double ti)
+template <int FLAGS, class P = LhDevParams>
+__device__ __forceinline__ double lh_face_kappa(const P& p, const double* __restrict__ tab, double th, double ti)
 {
     constexpr bool ICE = (FLAGS & LH_FLAG_ICE) != 0, GEN = (FLAGS & LH_FLAG_GEN) != 0;
     const double nu_eff = ICE ? p.nu - ti : p.nu;

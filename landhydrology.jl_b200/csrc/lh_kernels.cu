@@ -86,16 +86,43 @@ cudaError_t lh_launch_ssprk33_persistent(int model, int flags, const LhKernelArg
 // Diagnostics
 // -------------------------------------------------------------------------------------------------
 namespace {
+// The per-lane parameter view of column `col` (see lh_stage_body).
+__device__ __forceinline__ LhLaneParams lh_lane_params(const LhDevParams& p, const double* colp, int64_t col, int64_t st)
+{
+    LhLaneParams pl;
+    static_cast<LhPhys&>(pl) = static_cast<const LhPhys&>(p);
+    pl.mc = p.mc;
+    if (colp) {
+        const double* cp = colp + col;
+        pl.nu = cp[LHCP_NU * st];
+        pl.theta_r = cp[LHCP_THETA_R * st];
+        pl.theta_r_eps = cp[LHCP_THETA_R_EPS * st];
+        pl.inv_nu_thr = cp[LHCP_INV_NU_THR * st];
+        pl.nu_thr = cp[LHCP_NU_THR * st];
+        pl.vg_m = cp[LHCP_VG_M * st];
+        pl.vg_inv_m = cp[LHCP_VG_INV_M * st];
+        pl.vg_inv_n = cp[LHCP_VG_INV_N * st];
+        pl.neg_inv_alpha = cp[LHCP_NEG_INV_ALPHA * st];
+        pl.Ksat = cp[LHCP_KSAT * st];
+        pl.inv_nu = cp[LHCP_INV_NU * st];
+        pl.kappa_dry = cp[LHCP_KAPPA_DRY * st];
+        pl.k_unfrozen_minus_dry = p.k_unfrozen - pl.kappa_dry;
+    }
+    return pl;
+}
+
 template <int MODEL>
-__global__ void lh_diag_kernel(const __grid_constant__ LhDevParams p, int which, const double* __restrict__ th,
+__global__ void lh_diag_kernel(const __grid_constant__ LhDevParams pu, int which, const double* __restrict__ th,
                                const double* __restrict__ ti, const double* __restrict__ re,
-                               const double* __restrict__ T, double* __restrict__ out, int64_t n)
+                               const double* __restrict__ T, double* __restrict__ out, int64_t n,
+                               const double* __restrict__ colp, int64_t ncol_pad)
 {
     __shared__ __align__(16) double tab[LH_TAB_DOUBLES];
-    lh_stage_tables(p, tab, threadIdx.x, blockDim.x);
+    lh_stage_tables(pu, tab, threadIdx.x, blockDim.x);
     __syncthreads();
     const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
+    const LhLaneParams p = lh_lane_params(pu, colp, i % ncol_pad, ncol_pad);
     // K/ψ exist for every model; κ/T come from ρe_int when there is an energy model, otherwise
     // from the prescribed T.
     double v;
@@ -116,12 +143,12 @@ __global__ void lh_diag_kernel(const __grid_constant__ LhDevParams p, int which,
 
 cudaError_t lh_launch_diagnostic(int model, int which, const LhDevParams& p, const double* th,
                                  const double* ti, const double* re, const double* T, double* out,
-                                 int64_t n, cudaStream_t stream)
+                                 int64_t n, const double* colp, int64_t ncol_pad, cudaStream_t stream)
 {
     const int block = 256;
     const unsigned grid = (unsigned)((n + block - 1) / block);
-    if (model == LH_MODEL_RICHARDS) lh_diag_kernel<0><<<grid, block, 0, stream>>>(p, which, th, ti, re, T, out, n);
-    else lh_diag_kernel<2><<<grid, block, 0, stream>>>(p, which, th, ti, re, T, out, n);
+    if (model == LH_MODEL_RICHARDS) lh_diag_kernel<0><<<grid, block, 0, stream>>>(p, which, th, ti, re, T, out, n, colp, ncol_pad);
+    else lh_diag_kernel<2><<<grid, block, 0, stream>>>(p, which, th, ti, re, T, out, n, colp, ncol_pad);
     return cudaGetLastError();
 }
 

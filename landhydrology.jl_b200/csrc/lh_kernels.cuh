@@ -16,6 +16,9 @@
 #ifndef LH_PDL
 #define LH_PDL 1      // programmatic dependent launch between consecutive stage kernels
 #endif
+#ifndef LH_MIN_BLOCKS_HET
+#define LH_MIN_BLOCKS_HET 4   // per-column parameters keep ~24 more registers live: 128 registers, 16 warps/SM
+#endif
 #ifndef LH_MIN_BLOCKS
 #define LH_MIN_BLOCKS 5
 #endif
@@ -58,6 +61,7 @@ struct LhKernelArgs {
     LhDevParams p;
     LhStageIO io;          // one-stage launches: this stage; persistent SSPRK33 launches: stage 1 (in = U, out = V)
     const double* zc;      // nlayer centre coordinates
+    const double* colp;    // HET variants: [LHCP_COUNT][ncol_pad] per-column derived parameters
     int64_t ncol_pad;
     int32_t nlayer;
     int32_t Lc;            // layers per thread (vertical chunk)
@@ -90,7 +94,7 @@ cudaError_t lh_launch_any_nonzero(const double* x, int64_t n, int* flag, cudaStr
 // Pointwise diagnostics (LH_DIAG_*): out[layer*ncol_pad+col].
 cudaError_t lh_launch_diagnostic(int model, int which, const LhDevParams& p, const double* th,
                                  const double* ti, const double* re, const double* T, double* out,
-                                 int64_t ncells_pad, cudaStream_t stream);
+                                 int64_t ncells_pad, const double* colp, int64_t ncol_pad, cudaStream_t stream);
 
 // Deterministic budgets: out2[0] = sum ϑ_l dz, out2[1] = sum ρe_int dz over columns < ncol.
 cudaError_t lh_launch_budgets(const double* th, const double* re, int64_t ncol, int64_t ncol_pad,

@@ -87,6 +87,7 @@ struct lh_soil_ctx {
     double* partials = nullptr;
     int32_t npartials = 0;
     double* budget_dev = nullptr;                // 2 doubles (+2 for the all-reduce result)
+    double* colp_dev = nullptr;                  // [LHCP_COUNT][ncol_pad] per-column derived parameters (heterogeneous soils)
     double* bc_dev = nullptr;                    // boundary-value table of a persistent launch
     int64_t bc_dev_steps = 0;
     unsigned long long* nonfinite_dev = nullptr;
@@ -144,10 +145,9 @@ int32_t validate_face(const lh_soil_face_bc& bc, int model, const char* face)
     return LH_OK;
 }
 
-LhDevParams derive_params(const lh_soil_config& cfg)
+void derive_phys(const lh_soil_config& cfg, LhPhys& d)
 {
     const lh_soil_params& q = cfg.params;
-    LhDevParams d;
     memset(&d, 0, sizeof d);
     d.dz = (cfg.zmax - cfg.zmin) / cfg.nlayer;
     d.inv_dz = 1.0 / d.dz;
@@ -193,6 +193,12 @@ LhDevParams derive_params(const lh_soil_config& cfg)
     d.imp_on = q.impedance_factor != LH_FACTOR_NONE;
     d.om_zero = q.nu_ss_om == 0.0;
     d.log2_Sr_sat = log2(q.nu * d.inv_nu);
+}
+
+LhDevParams derive_params(const lh_soil_config& cfg)
+{
+    LhDevParams d;
+    derive_phys(cfg, d);
     static const double coeffs[LHC_COUNT] = {LH_MATH_COEFFS};
     memcpy(d.mc, coeffs, sizeof coeffs);
     return d;
@@ -212,6 +218,7 @@ void free_all(lh_soil_ctx* c)
     if (c->partials) cudaFree(c->partials);
     if (c->budget_dev) cudaFree(c->budget_dev);
     if (c->bc_dev) cudaFree(c->bc_dev);
+    if (c->colp_dev) cudaFree(c->colp_dev);
     if (c->nonfinite_dev) cudaFree(c->nonfinite_dev);
     if (c->ev_start) cudaEventDestroy(c->ev_start);
     if (c->ev_stop) cudaEventDestroy(c->ev_stop);
@@ -361,10 +368,12 @@ void update_kernel_flags(lh_soil_ctx* c)
     const lh_soil_params& q = c->cfg.params;
     // theta_r != 0 only matters where the Kersten number reuses log S (coupled model); Richards has no
     // Kersten number and the heat-only model no water closures.
-    const bool gen = c->dp.visc_on || c->dp.imp_on || !c->dp.om_zero ||
+    const bool het = c->colp_dev != nullptr;             // per-column parameters: general closures, per-lane values
+    const bool gen = het || c->dp.visc_on || c->dp.imp_on || !c->dp.om_zero ||
                      (c->model == LH_MODEL_COUPLED && q.theta_r != 0.0);
-    const bool vg2 = q.vg_n == 2.0 && q.vg_m == 0.5;      // S^(1/m) = S^2, x^m = sqrt(x): no log/exp needed
-    c->kernel_flags = (c->has_ice ? LH_FLAG_ICE : 0) | (gen ? LH_FLAG_GEN : 0) | (vg2 && !c->force_general_vg ? LH_FLAG_VG2 : 0);
+    const bool vg2 = !het && q.vg_n == 2.0 && q.vg_m == 0.5;      // S^(1/m) = S^2, x^m = sqrt(x): no log/exp needed
+    c->kernel_flags = (c->has_ice ? LH_FLAG_ICE : 0) | (gen ? LH_FLAG_GEN : 0) | (vg2 && !c->force_general_vg ? LH_FLAG_VG2 : 0) |
+                      (het ? LH_FLAG_HET : 0);
 }
 
 // θ_i was (re)written: is there any ice?  One pass over the field; θ_i never changes afterwards.
@@ -395,6 +404,7 @@ void fill_args(lh_soil_ctx* c, int stage, double dt, LhKernelArgs& a)
     else if (stage == 3) { a.io.out_th = c->U[0]; a.io.out_re = c->U[2]; }
     else { a.io.out_th = c->V[0]; a.io.out_re = c->V[2]; }
     a.zc = c->zc_dev;
+    a.colp = c->colp_dev;
     a.ncol_pad = c->ncol_pad;
     a.nlayer = c->nlayer;
     a.Lc = c->shape.Lc;
@@ -576,6 +586,49 @@ int32_t lh_soil_get_state(lh_soil_ctx* c, int32_t field, double* host, int64_t c
     if (!field_ok(field)) return fail(c, LH_ERR_INVALID_ARG, "bad field id %d", field);
     if (!c->U[field]) return fail(c, LH_ERR_INVALID_ARG, "field %d does not exist for model kind %d", field, c->model);
     return download_field(c, c->U[field], host, cs, ls);
+}
+
+int32_t lh_soil_set_column_params(lh_soil_ctx* c, const double* nu, const double* theta_r, const double* vg_n,
+                                  const double* vg_alpha, const double* Ksat)
+{
+    if (!c) return LH_ERR_INVALID_ARG;
+    LH_CUDA(c, cudaSetDevice(c->device));
+    LH_CUDA(c, cudaStreamSynchronize(c->stream));
+    if (!nu && !theta_r && !vg_n && !vg_alpha && !Ksat) {      // back to the homogeneous kernels
+        if (c->colp_dev) { LH_CUDA(c, cudaFree(c->colp_dev)); c->colp_dev = nullptr; }
+        update_kernel_flags(c);
+        return LH_OK;
+    }
+    // derive, per column, exactly what derive_params derives for the model (same expressions, same rounding)
+    const lh_soil_params& q0 = c->cfg.params;
+    std::vector<double> h((size_t)LHCP_COUNT * c->ncol_pad);
+    for (int64_t j = 0; j < c->ncol_pad; ++j) {
+        const int64_t col = std::min<int64_t>(j, c->ncol - 1);                  // padding replicates the last column
+        lh_soil_config cfg = c->cfg;
+        lh_soil_params& q = cfg.params;
+        if (nu) q.nu = nu[col];
+        if (theta_r) q.theta_r = theta_r[col];
+        if (vg_n) { q.vg_n = vg_n[col]; q.vg_m = 1.0 - 1.0 / q.vg_n; }          // the reference constructor's m
+        if (vg_alpha) q.vg_alpha = vg_alpha[col];
+        if (Ksat) q.Ksat = Ksat[col];
+        if (!(q.nu > q.theta_r) || !(q.vg_n > 1.0) || !(q.vg_alpha > 0.0) || !std::isfinite(q.Ksat))
+            return fail(c, LH_ERR_INVALID_ARG, "column %lld: need nu > theta_r, vg_n > 1, vg_alpha > 0, finite Ksat", (long long)col);
+        LhPhys d;
+        derive_phys(cfg, d);
+        double* o = h.data() + j;
+        const int64_t st = c->ncol_pad;
+        o[LHCP_NU * st] = d.nu; o[LHCP_THETA_R * st] = d.theta_r; o[LHCP_THETA_R_EPS * st] = d.theta_r_eps;
+        o[LHCP_INV_NU_THR * st] = d.inv_nu_thr; o[LHCP_NU_THR * st] = d.nu_thr;
+        o[LHCP_VG_M * st] = d.vg_m; o[LHCP_VG_INV_M * st] = d.vg_inv_m; o[LHCP_VG_INV_N * st] = d.vg_inv_n;
+        o[LHCP_NEG_INV_ALPHA * st] = d.neg_inv_alpha; o[LHCP_KSAT * st] = d.Ksat;
+        o[LHCP_INV_NU * st] = d.inv_nu; o[LHCP_KAPPA_DRY * st] = d.kappa_dry;
+    }
+    if (!c->colp_dev) LH_CUDA(c, cudaMalloc(&c->colp_dev, h.size() * sizeof(double)));
+    LH_CUDA(c, cudaMemcpyAsync(c->colp_dev, h.data(), h.size() * sizeof(double), cudaMemcpyHostToDevice, c->stream));
+    LH_CUDA(c, cudaStreamSynchronize(c->stream));
+    (void)q0;
+    update_kernel_flags(c);
+    return LH_OK;
 }
 
 int32_t lh_soil_set_bc_values(lh_soil_ctx* c, const double values[4])
@@ -821,7 +874,7 @@ int32_t lh_soil_diagnostic(lh_soil_ctx* c, int32_t which, double* host, int64_t 
     const int slot = has_water(c->model) ? 0 : 2;
     if (!c->tend[slot]) LH_CUDA(c, cudaMalloc(&c->tend[slot], fb));
     LH_CUDA(c, lh_launch_diagnostic(c->model, which, c->dp, c->U[0], c->U[1], c->U[2], c->U[3], c->tend[slot],
-                                    (int64_t)c->ncol_pad * c->nlayer, c->stream));
+                                    (int64_t)c->ncol_pad * c->nlayer, c->colp_dev, c->ncol_pad, c->stream));
     return download_field(c, c->tend[slot], host, cs, ls);
 }
 

@@ -44,8 +44,8 @@ __device__ __forceinline__ Q<MODEL> q_load(const double* sm)
 // Interior face between cell `lo` (below) and `hi` (above).
 //   water  right_hand_side.jl:181/:358   -interpc2f(K) * gradc2f(h)
 //   energy :259 / :361-365               -interpc2f(κ) * gradc2f(T) - interpc2f(ρe_int_l K) * gradc2f(h)
-template <int MODEL>
-__device__ __forceinline__ Flux face_flux(const LhDevParams& p, const Q<MODEL>& lo, const Q<MODEL>& hi)
+template <int MODEL, class P>
+__device__ __forceinline__ Flux face_flux(const P& p, const Q<MODEL>& lo, const Q<MODEL>& hi)
 {
     // -interp(a) * grad(b) = -(a_lo + a_hi)/2 * (b_hi - b_lo)/dz = c (a_lo + a_hi)(b_hi - b_lo),  c = -1/(2 dz)
     Flux f;
@@ -65,8 +65,8 @@ __device__ __forceinline__ Flux face_flux(const LhDevParams& p, const Q<MODEL>& 
 
 // boundary_fluxes(X, bc::SoilComponentBC, face, ...) boundary_conditions.jl:470-489 for one face.
 // (th, ti) raw centre values, `c` the centre closures (c.T is the centre temperature).
-template <int MODEL, int FLAGS>
-__device__ __forceinline__ Flux boundary_flux(const LhDevParams& p, const double* __restrict__ tab, int e_kind,
+template <int MODEL, int FLAGS, class P>
+__device__ __forceinline__ Flux boundary_flux(const P& p, const double* __restrict__ tab, int e_kind,
                                               int h_kind, double val_e, double val_h, bool is_bottom,
                                               double th, double ti, const LhCell& c)
 {
@@ -157,12 +157,11 @@ __device__ __forceinline__ double lh_lds(uint32_t addr)
 // One stage over this block's column groups.  `smem` = the block's dynamic shared memory with the exp2 / log2
 // tables already staged at its start.  Contains ONE __syncthreads (the chunk-face exchange): every thread of
 // the block must call it.
-template <int MODEL, int STAGE, int FLAGS>
-__device__ __forceinline__ void lh_stage_body(const LhKernelArgs& A, const LhStageIO& io, double* smem)
+template <int MODEL, int STAGE, int FLAGS, class P>
+__device__ __forceinline__ void lh_stage_body_impl(const LhKernelArgs& A, const LhStageIO& io, double* smem, const P& p)
 {
     constexpr int NQv = NQ<MODEL>::value;
     constexpr bool ICE = (FLAGS & LH_FLAG_ICE) != 0;
-    const LhDevParams& p = A.p;
     // A warp is one (column group g, chunk w) pair, so w, g and everything derived from them (loop
     // bounds, `active`) are warp-uniform.  ptxas cannot see that from threadIdx.y/z and then treats the
     // layer loop as divergent: no uniform-register operands inside it, every constant copied to vector
@@ -401,8 +400,41 @@ __device__ __forceinline__ void lh_stage_body(const LhKernelArgs& A, const LhSta
     }
 }
 
+// Homogeneous soils: the parameters are the launch's uniform block.  HET (lh_soil_set_column_params): every lane
+// overrides the column-dependent members with its own column's values, loaded once per stage.
 template <int MODEL, int STAGE, int FLAGS>
-__global__ void __launch_bounds__(LhBounds<MODEL>::max_threads, LhBounds<MODEL>::min_blocks)
+__device__ __forceinline__ void lh_stage_body(const LhKernelArgs& A, const LhStageIO& io, double* smem)
+{
+    if constexpr ((FLAGS & LH_FLAG_HET) == 0) {
+        lh_stage_body_impl<MODEL, STAGE, FLAGS>(A, io, smem, A.p);
+    } else {
+        const int g = __shfl_sync(0xffffffffu, (int)threadIdx.z, 0);
+        int64_t col = ((int64_t)blockIdx.x * blockDim.z + g) * 32 + threadIdx.x;
+        if (col >= A.ncol_pad) col = A.ncol_pad - 1;           // an idle column group of the last block
+        const double* cp = A.colp + col;
+        const int64_t st = A.ncol_pad;
+        LhLaneParams pl;
+        static_cast<LhPhys&>(pl) = static_cast<const LhPhys&>(A.p);
+        pl.mc = A.p.mc;
+        pl.nu = cp[LHCP_NU * st];
+        pl.theta_r = cp[LHCP_THETA_R * st];
+        pl.theta_r_eps = cp[LHCP_THETA_R_EPS * st];
+        pl.inv_nu_thr = cp[LHCP_INV_NU_THR * st];
+        pl.nu_thr = cp[LHCP_NU_THR * st];
+        pl.vg_m = cp[LHCP_VG_M * st];
+        pl.vg_inv_m = cp[LHCP_VG_INV_M * st];
+        pl.vg_inv_n = cp[LHCP_VG_INV_N * st];
+        pl.neg_inv_alpha = cp[LHCP_NEG_INV_ALPHA * st];
+        pl.Ksat = cp[LHCP_KSAT * st];
+        pl.inv_nu = cp[LHCP_INV_NU * st];
+        pl.kappa_dry = cp[LHCP_KAPPA_DRY * st];
+        pl.k_unfrozen_minus_dry = A.p.k_unfrozen - pl.kappa_dry;
+        lh_stage_body_impl<MODEL, STAGE, FLAGS>(A, io, smem, pl);
+    }
+}
+
+template <int MODEL, int STAGE, int FLAGS>
+__global__ void __launch_bounds__(LhBounds<MODEL>::max_threads, (FLAGS & LH_FLAG_HET) ? LH_MIN_BLOCKS_HET : LhBounds<MODEL>::min_blocks)
 lh_soil_stage_kernel(const __grid_constant__ LhKernelArgs A)
 {
     extern __shared__ __align__(16) double smem[];
@@ -428,7 +460,7 @@ lh_soil_stage_kernel(const __grid_constant__ LhKernelArgs A)
 // Used for grids of few waves (column shards of a multi-GPU run, small domains), where launch gaps and wave
 // quantisation cost more than 5 %; results are bit-identical to the per-stage launches.
 template <int MODEL, int FLAGS>
-__global__ void __launch_bounds__(LhBounds<MODEL>::max_threads, LhBounds<MODEL>::min_blocks)
+__global__ void __launch_bounds__(LhBounds<MODEL>::max_threads, (FLAGS & LH_FLAG_HET) ? LH_MIN_BLOCKS_HET : LhBounds<MODEL>::min_blocks)
 lh_soil_ssprk33_persistent_kernel(const __grid_constant__ LhKernelArgs A)
 {
     extern __shared__ __align__(16) double smem[];
@@ -513,6 +545,12 @@ template <int MODEL>
 cudaError_t launch_model(int stage, int flags, const LhKernelArgs& args, const LhLaunchShape& s, cudaStream_t stream)
 {
     if (MODEL == 1) flags &= ~LH_FLAG_VG2;   // the heat-only model has no water closures
+    if (flags & LH_FLAG_HET) {               // per-column parameters: always the general closures
+        switch (flags & LH_FLAG_ICE) {
+        case 0: return launch_variant<MODEL, LH_FLAG_HET | LH_FLAG_GEN>(stage, args, s, stream);
+        default: return launch_variant<MODEL, LH_FLAG_HET | LH_FLAG_GEN | LH_FLAG_ICE>(stage, args, s, stream);
+        }
+    }
     switch (flags & 7) {
     case 0: return launch_variant<MODEL, 0>(stage, args, s, stream);
     case 1: return launch_variant<MODEL, 1>(stage, args, s, stream);
@@ -548,6 +586,12 @@ template <int MODEL>
 cudaError_t launch_persistent_model(int flags, const LhKernelArgs& args, const LhLaunchShape& s, cudaStream_t stream)
 {
     if (MODEL == 1) flags &= ~LH_FLAG_VG2;
+    if (flags & LH_FLAG_HET) {
+        switch (flags & LH_FLAG_ICE) {
+        case 0: return launch_persistent_variant<MODEL, LH_FLAG_HET | LH_FLAG_GEN>(args, s, stream);
+        default: return launch_persistent_variant<MODEL, LH_FLAG_HET | LH_FLAG_GEN | LH_FLAG_ICE>(args, s, stream);
+        }
+    }
     switch (flags & 7) {
     case 0: return launch_persistent_variant<MODEL, 0>(args, s, stream);
     case 1: return launch_persistent_variant<MODEL, 1>(args, s, stream);

@@ -245,6 +245,7 @@ struct lho_soil_ctx {
     double* tend[3];
     double* Fw;           /* face fluxes of the last rhs call, [col*(nlayer+1)+j] */
     double* Fe;
+    double* colp[5];      /* per-column nu, theta_r, vg_n, vg_alpha, Ksat (NULL: uniform), lho_soil_set_column_params */
     double bcv[4];
     double last_ms;
     int64_t last_launches;
@@ -373,6 +374,7 @@ int32_t lho_soil_destroy(lho_soil_ctx* c)
     for (int k = 0; k < LH_NUM_FIELDS; ++k) free(c->f[k]);
     for (int k = 0; k < 3; ++k) { free(c->u1[k]); free(c->tend[k]); }
     free(c->Fw); free(c->Fe);
+    for (int k = 0; k < 5; ++k) free(c->colp[k]);
     free(c);
     return LH_OK;
 }
@@ -541,14 +543,26 @@ static void boundary_fluxes(const lh_soil_params* p, int model, double kappa_dry
     }
 }
 
+/* The parameter set of one column: the model's SoilParams / vanGenuchten with the per-column overrides of
+ * lho_soil_set_column_params (m = 1 - 1/n as the reference constructor computes it).                          */
+static lh_soil_params params_of_column(const lho_soil_ctx* c, int64_t col)
+{
+    lh_soil_params p = c->cfg.params;
+    if (c->colp[0]) p.nu = c->colp[0][col];
+    if (c->colp[1]) p.theta_r = c->colp[1][col];
+    if (c->colp[2]) { p.vg_n = c->colp[2][col]; p.vg_m = 1.0 - 1.0 / p.vg_n; }
+    if (c->colp[3]) p.vg_alpha = c->colp[3][col];
+    if (c->colp[4]) p.Ksat = c->colp[4][col];
+    return p;
+}
+
 /* One column.  u_th/u_ti/u_re/u_T: nlayer values each (layer 0 = bottom).  work: 5*nlayer.
  * Fw/Fe: nlayer+1 face fluxes (outputs).                                                    */
-static void column_rhs(const lho_soil_ctx* c, const double bcv[4], double kappa_dry,
+static void column_rhs(const lho_soil_ctx* c, const lh_soil_params* p, const double bcv[4], double kappa_dry,
                        const double* u_th, const double* u_ti, const double* u_re,
                        const double* u_T, double* d_th, double* d_ti, double* d_re,
                        double* Fw, double* Fe, double* work)
 {
-    const lh_soil_params* p = &c->cfg.params;
     const int model = c->cfg.model;
     const int n = c->nlayer;
     const double dz = c->dz;
@@ -604,14 +618,15 @@ static void rhs_all(lho_soil_ctx* c, const double* th, const double* ti, const d
                     const double* T)
 {
     const int n = c->nlayer;
-    const double kappa_dry = lho_k_dry(&c->cfg.params);             /* :214, :295 */
 #pragma omp parallel if (c->ncol >= 64)
     {
         double* work = (double*)malloc(sizeof(double) * 5 * n);
 #pragma omp for schedule(static)
         for (int64_t col = 0; col < c->ncol; ++col) {
             size_t o = (size_t)col * n;
-            column_rhs(c, c->bcv, kappa_dry, th + o, ti + o, re + o, T + o, c->tend[0] + o,
+            const lh_soil_params pc = params_of_column(c, col);
+            const double kappa_dry = lho_k_dry(&pc);                /* :214, :295 */
+            column_rhs(c, &pc, c->bcv, kappa_dry, th + o, ti + o, re + o, T + o, c->tend[0] + o,
                        c->tend[1] + o, c->tend[2] + o, c->Fw + (size_t)col * (n + 1),
                        c->Fe + (size_t)col * (n + 1), work);
         }
@@ -862,17 +877,18 @@ int32_t lho_soil_diagnostic(lho_soil_ctx* c, int32_t which, double* host, int64_
     if (which < 0 || which >= LH_NUM_DIAGS) return fail(c, LH_ERR_INVALID_ARG, "bad diagnostic id");
     const int n = c->nlayer;
     const int model = c->cfg.model;
-    const double kappa_dry = lho_k_dry(&c->cfg.params);
     /* K/ψ are defined whenever ϑ_l, θ_i exist (all models); κ/T from ρe_int need an energy
      * model, otherwise T is the prescribed aux and κ is evaluated with it.                  */
-    for (int64_t col = 0; col < c->ncol; ++col)
+    for (int64_t col = 0; col < c->ncol; ++col) {
+        const lh_soil_params pc = params_of_column(c, col);
+        const double kappa_dry = lho_k_dry(&pc);
         for (int i = 0; i < n; ++i) {
             size_t o = (size_t)col * n + i;
             int m = has_heat(model) ? LH_MODEL_COUPLED : LH_MODEL_RICHARDS;
-            cell_closures cc = closures_at(&c->cfg.params, m, kappa_dry, c->f[0][o], c->f[1][o],
+            cell_closures cc = closures_at(&pc, m, kappa_dry, c->f[0][o], c->f[1][o],
                                            c->f[2][o], c->f[3][o]);
             if (which == LH_DIAG_KAPPA && !has_heat(model)) {
-                cell_closures ch = closures_at(&c->cfg.params, LH_MODEL_HEAT, kappa_dry, c->f[0][o],
+                cell_closures ch = closures_at(&pc, LH_MODEL_HEAT, kappa_dry, c->f[0][o],
                                                c->f[1][o], 0.0, c->f[3][o]);
                 cc.kappa = ch.kappa;
             }
@@ -880,6 +896,25 @@ int32_t lho_soil_diagnostic(lho_soil_ctx* c, int32_t which, double* host, int64_
                      : which == LH_DIAG_KAPPA ? cc.kappa : cc.T;
             host[col * cs + i * ls] = v;
         }
+    }
+    return LH_OK;
+}
+
+/* Per-column hydraulic parameters (include/lh_soil.h): each array ncol doubles, NULL keeps the model's value. */
+int32_t lho_soil_set_column_params(lho_soil_ctx* c, const double* nu, const double* theta_r, const double* vg_n,
+                                   const double* vg_alpha, const double* Ksat)
+{
+    if (!c) return LH_ERR_INVALID_ARG;
+    const double* src[5] = {nu, theta_r, vg_n, vg_alpha, Ksat};
+    for (int k = 0; k < 5; ++k) {
+        free(c->colp[k]);
+        c->colp[k] = NULL;
+        if (src[k]) {
+            c->colp[k] = (double*)malloc(sizeof(double) * (size_t)c->ncol);
+            if (!c->colp[k]) return fail(c, LH_ERR_INVALID_ARG, "out of memory");
+            memcpy(c->colp[k], src[k], sizeof(double) * (size_t)c->ncol);
+        }
+    }
     return LH_OK;
 }
 

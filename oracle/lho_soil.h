@@ -33,6 +33,7 @@
 #define lh_soil_get_tendency      lho_soil_get_tendency
 #define lh_soil_stage_ssprk33     lho_soil_stage_ssprk33
 #define lh_soil_step_ssprk33      lho_soil_step_ssprk33
+#define lh_soil_set_column_params lho_soil_set_column_params
 #define lh_soil_stepper_named     lho_soil_stepper_named
 #define lh_soil_step              lho_soil_step
 #define lh_soil_budgets           lho_soil_budgets

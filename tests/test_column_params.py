@@ -1,0 +1,122 @@
+"""Heterogeneous soils: per-column hydraulic parameters (lh_soil_set_column_params — ν, θr, van Genuchten n and α,
+K_sat per column).  CPU: the oracle with constant arrays equals the homogeneous oracle bit for bit and
+really uses the arrays.  GPU: the per-lane-parameter kernels against the oracle for every model, all launch paths,
+and the diagnostics."""
+import numpy as np
+import pytest
+
+import workloads as w
+
+lh, abi = w.lh, w.abi
+
+
+def random_column_params(wl, seed, which=("nu", "theta_r", "vg_n", "vg_alpha", "Ksat")):
+    rng = np.random.default_rng(seed)
+    p, n = wl.params, wl.ncol
+    out = {}
+    if "nu" in which:
+        out["nu"] = p.nu * rng.uniform(0.85, 1.15, n)
+    if "theta_r" in which:
+        out["theta_r"] = rng.uniform(0.0, 0.06, n)
+    if "vg_n" in which:
+        out["vg_n"] = rng.uniform(1.3, 4.0, n)
+    if "vg_alpha" in which:
+        out["vg_alpha"] = p.vg_alpha * rng.uniform(0.5, 2.0, n)
+    if "Ksat" in which:
+        out["Ksat"] = p.Ksat * 10.0 ** rng.uniform(-1.5, 1.5, n)
+    return out
+
+
+def rescale_state(wl, cp):
+    """Keep the workload's saturation profile under the new per-column porosity / residual water content."""
+    p = wl.params
+    S = (wl.fields[0] - p.theta_r) / ((p.nu - wl.fields[1]) - p.theta_r)
+    nu = cp.get("nu", np.full(wl.ncol, p.nu))[:, None]
+    thr = cp.get("theta_r", np.full(wl.ncol, p.theta_r))[:, None]
+    wl.fields[0] = thr + S * ((nu - wl.fields[1]) - thr)
+
+
+def test_oracle_constant_arrays_equal_homogeneous(oracle):
+    wl = w.coupled_workload(ncol=6, nlayer=20, seed=81)
+    a, b = lh.SoilContext(oracle, wl.config()), lh.SoilContext(oracle, wl.config())
+    p = wl.params
+    b.set_column_params(nu=np.full(6, p.nu), theta_r=np.full(6, p.theta_r), vg_n=np.full(6, p.vg_n),
+                        vg_alpha=np.full(6, p.vg_alpha), Ksat=np.full(6, p.Ksat))
+    for ctx in (a, b):
+        wl.upload(ctx)
+        ctx.step(0.0, wl.dt, 3)
+    for f in (0, 2):
+        assert np.array_equal(a.get_state(f), b.get_state(f))
+    c = lh.SoilContext(oracle, wl.config())
+    c.set_column_params(Ksat=p.Ksat * np.array([1.0, 2.0, 1.0, 1.0, 0.5, 1.0]))
+    wl.upload(c)
+    c.step(0.0, wl.dt, 3)
+    same = [np.array_equal(a.get_state(0)[k], c.get_state(0)[k]) for k in range(6)]
+    assert same == [True, False, True, True, False, True]         # columns are independent; only the changed ones move
+    with pytest.raises(ValueError):
+        c.set_column_params(nu=np.zeros(5))
+    c.set_column_params()                                         # all None: homogeneous again
+    wl.upload(c)
+    c.step(0.0, wl.dt, 3)
+    assert np.array_equal(a.get_state(0), c.get_state(0))
+
+
+CASES = {
+    "coupled": lambda: w.coupled_workload(ncol=200, nlayer=64, seed=82),
+    "coupled_ice": lambda: w.coupled_workload(ncol=96, nlayer=24, seed=83, ice=True, viscosity=lh.TemperatureDependentViscosity(),
+                                              impedance=lh.IceImpedance()),
+    "richards": lambda: w.richards_workload(ncol=130, nlayer=100, seed=84),
+    "richards_tall": lambda: w.richards_workload(ncol=40, nlayer=300, seed=85, zlim=(-4.5, 0.0)),
+    "heat": lambda: w.heat_workload(ncol=64, nlayer=37, seed=86),
+}
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("name", sorted(CASES))
+@pytest.mark.parametrize("launch", ["stage", "persistent"])
+def test_cuda_matches_oracle(cuda, oracle, name, launch):
+    wl = CASES[name]()
+    cp = random_column_params(wl, seed=7)
+    rescale_state(wl, cp)
+    if wl.model == abi.LH_MODEL_COUPLED:      # the Dirichlet top value must stay below every column's porosity
+        wl.top = (wl.top[0], wl.top[1], wl.top[2], 0.3)
+    flags = abi.LH_FLAG_STAGE_LAUNCHES if launch == "stage" else abi.LH_FLAG_PERSISTENT
+    g, o = lh.SoilContext(cuda, wl.config(flags=flags)), lh.SoilContext(oracle, wl.config())
+    for ctx in (g, o):
+        ctx.set_column_params(**cp)
+        wl.upload(ctx)
+        ctx.rhs(0.0)
+    fields = (0, 2) if wl.model == abi.LH_MODEL_COUPLED else (0,) if wl.model == abi.LH_MODEL_RICHARDS else (2,)
+    for f in fields:
+        a, r = g.get_tendency(f), o.get_tendency(f)
+        scale = w.tendency_scale(o, f)
+        err = np.max(np.abs(a - r) / scale[:, None])
+        assert err <= 1e-12, (name, f, err)
+    for which in (abi.LH_DIAG_K, abi.LH_DIAG_PSI, abi.LH_DIAG_KAPPA):
+        a, r = g.diagnostic(which), o.diagnostic(which)
+        assert np.max(np.abs(a - r) / np.maximum(np.abs(r), 1e-300)) <= 2e-13, (name, which)
+    for ctx in (g, o):
+        ctx.step(0.0, wl.dt, 6)
+    for f in fields:
+        a, r = g.get_state(f), o.get_state(f)
+        assert np.max(np.abs(a - r)) <= 1e-10 * np.max(np.abs(r)), (name, f)
+
+
+@pytest.mark.gpu
+def test_cuda_constant_arrays_match_homogeneous(cuda):
+    """Constant arrays take the per-lane kernels (general closures); the homogeneous context takes the n = 2 fast path:
+    two different evaluation orders of the same closures, agreeing to round-off."""
+    wl = w.coupled_workload(ncol=128, nlayer=64, seed=87)
+    p = wl.params
+    a, b = lh.SoilContext(cuda, wl.config()), lh.SoilContext(cuda, wl.config())
+    b.set_column_params(nu=np.full(128, p.nu), vg_n=np.full(128, p.vg_n), Ksat=np.full(128, p.Ksat))
+    for ctx in (a, b):
+        wl.upload(ctx)
+        ctx.step(0.0, wl.dt, 5)
+    for f in (0, 2):
+        ra, rb = a.get_state(f), b.get_state(f)
+        assert np.max(np.abs(ra - rb)) <= 1e-11 * np.max(np.abs(ra))
+    b.set_column_params()                       # back to the homogeneous kernels
+    wl.upload(b)
+    b.step(0.0, wl.dt, 5)
+    assert np.array_equal(a.get_state(0), b.get_state(0))
