@@ -52,6 +52,8 @@ def parse_args():
     ap.add_argument("--launch", default="auto", choices=["auto", "stage", "persistent"],
                     help="lh_soil_step_ssprk33 strategy: one launch per stage, one persistent launch per call, or the library's "
                          "own choice (persistent for small launch-bound grids of <= 3 waves)")
+    ap.add_argument("--het", action="store_true",
+                    help="heterogeneous soils: random per-column nu / theta_r / van Genuchten n, alpha / Ksat (lh_soil_set_column_params)")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     return ap.parse_args()
@@ -230,6 +232,13 @@ def main():
     flags = (lh._abi.LH_FLAG_GENERAL_VG if args.general_vg else 0) | \
             {"auto": 0, "stage": lh._abi.LH_FLAG_STAGE_LAUNCHES, "persistent": lh._abi.LH_FLAG_PERSISTENT}[args.launch]
     ctx = lh.SoilContext(lib, wl.config(flags=flags))
+    if args.het:
+        rng = np.random.default_rng(11 + rank)
+        n_ = wl.ncol
+        ctx.set_column_params(nu=wl.params.nu * rng.uniform(0.98, 1.15, n_), theta_r=rng.uniform(0.0, 0.02, n_),
+                              vg_n=rng.uniform(1.5, 3.5, n_), vg_alpha=wl.params.vg_alpha * rng.uniform(0.5, 2.0, n_),
+                              Ksat=wl.params.Ksat * 10.0 ** rng.uniform(-1.0, 1.0, n_))
+        config["closures"] = "heterogeneous: per-column nu, theta_r, van Genuchten n and alpha, Ksat (general closures, per-lane parameters)"
     host = {fid: pinned_like(a) for fid, a in wl.fields.items()}
     for fid, a in host.items():
         ctx.set_state(fid, a)
