@@ -10,9 +10,6 @@
 // layer loop is provably warp-uniform (lh_stage_kernel.cuh) the coupled n = 2 variant needs ~96 registers
 // and every model runs best as 4-warp blocks, 5 resident blocks per SM (20 warps/SM, <= 102 registers):
 // coupled 80 %, general-n 61 %, Richards 51 % of the HBM roofline, against 79 / 58 / 49 % at 16 warps/SM.
-#ifndef LH_ILP2
-#define LH_ILP2 0      // 1: issue both cells' loads before either closure chain (measured: no gain)
-#endif
 #ifndef LH_PDL
 #define LH_PDL 1      // programmatic dependent launch between consecutive stage kernels
 #endif

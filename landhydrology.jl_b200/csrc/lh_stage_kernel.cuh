@@ -116,17 +116,29 @@ __device__ __forceinline__ double stage_base(const LhStageIO& io, double v, doub
     else return v;
 }
 
+// x / 3, correctly rounded (Markstein: one residual correction of x * fl(1/3)).  A bare multiplication by fl(1/3)
+// is biased by -5.6e-17 relative, EVERY step, on the whole state: over the 138 240 steps of the reference's coupled
+// equilibrium test (coupled.jl:36-39) the water budget drifts by 8e-12 — the reference divides by 3.
+__device__ __forceinline__ double lh_third(double x)
+{
+    const double q = x * (1.0 / 3.0);
+    return fma(fma(-3.0, q, x), 1.0 / 3.0, q);
+}
+
 // Stage combine with the flux-form divergence folded in:  k = -(F_hi - F_lo)/dz and
 //   stage 0: k     1: base + dt k     2: (base + dt k)/4     3: (base + 2 dt k)/3     4: base + g dt k     5: base + dt k
 // are evaluated as  s (base + cdt (F_hi - F_lo))  with cdt = -dt/dz (stage 3: -2 dt/dz; stage 0: -1/dz; stage 4: -g dt/dz).
 template <int STAGE>
 __device__ __forceinline__ double stage_out(double base, double dF, double cdt, double sg)
 {
-    if constexpr (STAGE == 6) return sg * fma(cdt, dF, base);
+    if constexpr (STAGE == 6) {
+        const double x = fma(cdt, dF, base);
+        return sg == 1.0 / 3.0 ? lh_third(x) : sg * x;     // uniform select; 1 and 1/4 scale exactly
+    }
     if constexpr (STAGE == 0) return cdt * dF;
     else if constexpr (STAGE == 1 || STAGE == 4 || STAGE == 5) return fma(cdt, dF, base);
     else if constexpr (STAGE == 2) return 0.25 * fma(cdt, dF, base);
-    else return (1.0 / 3.0) * fma(cdt, dF, base);
+    else return lh_third(fma(cdt, dF, base));
 }
 
 struct Base { double th, re, th2, re2; };   // th2/re2: the state itself, 2N stages only
@@ -328,24 +340,12 @@ __device__ __forceinline__ void lh_stage_body_impl(const LhKernelArgs& A, const 
         const uint32_t dsum = 2 * ring_w + 2 * CB;        // pair (0,1) base + pair (2,3) base
         for (; i + 1 < b; i += 2) {   // two cells per trip: no sliding-window register moves
             const uint32_t dB = dsum - dA;                // the other pair: cells (i + 2, i + 3)
-#if LH_ILP2
-            // both cells' inputs first, so that the two (independent) closure chains can be interleaved
-            const Raw r0 = load_raw(dA, dB + CB, i + 3);
-            const Raw r1 = load_raw(dA + CB, dA, i + 4);
-            const Cell<MODEL> c0 = eval(r0);
-            const Cell<MODEL> c1 = eval(r1);
-            const Flux F0 = face_flux<MODEL>(p, prev, c0.q);
-            const Flux F1 = face_flux<MODEL>(p, c0.q, c1.q);
-            write_next(base_prev, F_below, F0);
-            write_next(c0.base, F0, F1);
-#else
             const Cell<MODEL> c0 = eval(load_raw(dA, dB + CB, i + 3));
             const Flux F0 = face_flux<MODEL>(p, prev, c0.q);
             write_next(base_prev, F_below, F0);
             const Cell<MODEL> c1 = eval(load_raw(dA + CB, dA, i + 4));
             const Flux F1 = face_flux<MODEL>(p, c0.q, c1.q);
             write_next(c0.base, F0, F1);
-#endif
             F_below = F1; prev = c1.q; base_prev = c1.base;
             dA = dB;
         }
