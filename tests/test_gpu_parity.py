@@ -351,3 +351,59 @@ def test_device_math_accuracy_on_gpu(cuda):
     ys = ctx.eval_math(2, xs)
     assert ulps(ys, [mp.expm1(mp.mpf(float(v)) * mp.log(2)) for v in xs]).max() <= 8.0
     assert ctx.eval_math(3, np.array([0.0]))[0] == 0.0 and np.isnan(ctx.eval_math(0, np.array([-1.0]))[0])
+
+
+# ---- randomized sweep over parameters, shapes, BC kinds and flags -------------------------------------------
+def _random_case(seed):
+    rng = np.random.default_rng(1000 + seed)
+    model = [abi.LH_MODEL_COUPLED, abi.LH_MODEL_RICHARDS, abi.LH_MODEL_HEAT][seed % 3]
+    nu = rng.uniform(0.25, 0.6)
+    sp = lh.SoilParams(
+        ν=nu, S_s=10.0 ** rng.uniform(-4, -2), ν_ss_gravel=rng.uniform(0, 0.2), ν_ss_om=rng.choice([0.0, rng.uniform(0, 0.2)]),
+        ν_ss_quartz=rng.uniform(0.2, 0.9), ρc_ds=rng.uniform(0.8e6, 2.5e6), κ_solid=rng.uniform(2.0, 8.0),
+        κ_sat_unfrozen=rng.uniform(0.8, 2.5), κ_sat_frozen=rng.uniform(2.0, 4.0), a=rng.uniform(0.1, 0.4), b=rng.uniform(10.0, 25.0))
+    vg = lh.vanGenuchten(n=rng.choice([2.0, rng.uniform(1.2, 5.0)]), α=rng.uniform(0.5, 6.0), Ksat=10.0 ** rng.uniform(-8, -4),
+                         θr=rng.choice([0.0, rng.uniform(0.0, 0.1)]))
+    ice = bool(rng.integers(0, 2)) and seed % 4 == 0
+    visc = lh.TemperatureDependentViscosity() if rng.integers(0, 3) == 0 else None
+    imp = lh.IceImpedance() if (ice and rng.integers(0, 2)) else None
+    p = w.make_params(sp, vg, viscosity=visc, impedance=imp)
+    ncol, nlayer = int(rng.integers(1, 200)), int(rng.integers(1, 150))
+    zmax = 0.0
+    zmin = -float(rng.uniform(0.02, 0.2)) * nlayer
+    S = w.saturation_profiles(2000 + seed, (0, ncol), nlayer, zmin, zmax, hi=0.97)
+    ti = w.ice_profiles(2000 + seed, (0, ncol), nlayer, 0.04) if ice else np.zeros((ncol, nlayer))
+    th = p.theta_r + S * ((p.nu - ti) - p.theta_r)
+    fields = {0: th, 1: ti}
+    if model != abi.LH_MODEL_RICHARDS:
+        fields[2] = w.rho_e_int_from_T(p, th, ti, w.temperature_profiles(2000 + seed, (0, ncol), nlayer, zmin, zmax))
+    th_bc = p.theta_r + rng.uniform(0.3, 0.95) * (p.nu - p.theta_r)
+
+    def face(bottom):
+        if model == abi.LH_MODEL_HEAT:
+            e = [(D, rng.uniform(275, 295)), (F, rng.uniform(-5, 5))][rng.integers(0, 2)]
+            return (e[0], e[1], N, 0.0)
+        hk = [(D, th_bc), (F, -p.Ksat * rng.uniform(0, 0.5))] + ([(FD, 0.0)] if bottom else [])
+        h = hk[rng.integers(0, len(hk))]
+        if model == abi.LH_MODEL_RICHARDS:
+            return (N, 0.0, h[0], h[1])
+        e = [(D, rng.uniform(275, 295)), (F, rng.uniform(-5, 5))][rng.integers(0, 2)]
+        return (e[0], e[1], h[0], h[1])
+
+    aux_T = 288.0 + 6.0 * np.sin(np.linspace(0, 2, nlayer)) if (model == abi.LH_MODEL_RICHARDS and visc is not None) else None
+    dz = (zmax - zmin) / nlayer
+    dt = 0.02 * dz * dz / max(p.Ksat * 50.0, 1e-6)              # well inside the explicit stability limit
+    wl = w.Workload(model=model, ncol=ncol, nlayer=nlayer, zmin=zmin, zmax=zmax, params=p, top=face(False), bottom=face(True),
+                    dt=min(dt, 50.0), fields=fields, aux_T=aux_T, name=f"fuzz{seed}")
+    flags = [0, abi.LH_FLAG_STAGE_LAUNCHES, abi.LH_FLAG_PERSISTENT, abi.LH_FLAG_GENERAL_VG][seed % 4]
+    return wl, flags
+
+
+@pytest.mark.parametrize("seed", range(36))
+def test_randomized_parity(cuda, oracle, seed):
+    """Random soil / van Genuchten / Balland-Arp parameters, column counts 1..199, 1..149 layers, every BC kind, ice and
+    conductivity factors, all launch strategies: tendency 1e-12 (scaled), state 1e-10 after 4 steps."""
+    wl, flags = _random_case(seed)
+    g, o = _pair(cuda, oracle, wl, flags=flags)
+    assert_tendency_parity(g, o, wl.model)
+    assert_state_parity(g, o, wl.model, wl.dt, 4)
