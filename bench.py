@@ -175,8 +175,18 @@ def time_oracle(w, lh, graft, model, nlayer, steps, warmup, target_seconds=None)
 
 def main():
     args = parse_args()
-    # stdout carries exactly one JSON line: NCCL's own banner / debug output goes to stderr
-    os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
+    # stdout carries exactly ONE JSON line.  Native libraries write to file descriptor 1 behind Python's back (NCCL prints
+    # its version banner there): point fd 1 at stderr for the duration of the run and keep the real stdout for the result.
+    sys.stdout.flush()
+    real_stdout = os.fdopen(os.dup(1), "w")
+    os.dup2(2, 1)
+    try:
+        return _main(args, real_stdout)
+    finally:
+        real_stdout.flush()
+
+
+def _main(args, out):
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
@@ -212,7 +222,7 @@ def main():
             "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0,
         }
-        print(json.dumps(line))
+        print(json.dumps(line), file=out)
         return 0
 
     # ---------------- this repo's arm ------------------------------------------------------------------
@@ -377,7 +387,8 @@ def main():
     if world == 1 and not args.no_cpu_baseline:
         v, cores, sample, sec, steps, _ = time_oracle(w, lh, graft, args.model, args.nlayer, 0, 0, target_seconds=12.0)
         line["cpu_baseline"] = {"value": v, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample}
-    print(json.dumps(line))
+    print(json.dumps(line), file=out)
+    out.flush()
     if world > 1:
         dist.destroy_process_group()
     return 0
