@@ -23,6 +23,12 @@
 
 #include "lh_soil.h"
 
+#include <stdlib.h>
+
+#ifndef LH_MIN_CHUNK
+#define LH_MIN_CHUNK 16
+#endif
+
 cudaError_t lh_launch_stage_m0(int, int, const LhKernelArgs&, const LhLaunchShape&, cudaStream_t);
 cudaError_t lh_launch_stage_m1(int, int, const LhKernelArgs&, const LhLaunchShape&, cudaStream_t);
 cudaError_t lh_launch_stage_m2(int, int, const LhKernelArgs&, const LhLaunchShape&, cudaStream_t);
@@ -30,30 +36,41 @@ cudaError_t lh_launch_persistent_m0(int, const LhKernelArgs&, const LhLaunchShap
 cudaError_t lh_launch_persistent_m1(int, const LhKernelArgs&, const LhLaunchShape&, cudaStream_t);
 cudaError_t lh_launch_persistent_m2(int, const LhKernelArgs&, const LhLaunchShape&, cudaStream_t);
 
-LhLaunchShape lh_choose_shape(int model, int64_t ncol_pad, int32_t nlayer, int sm_count)
+LhLaunchShape lh_choose_shape(int model, int64_t ncol_pad, int32_t nlayer, int sm_count, bool het)
 {
     LhLaunchShape s;
     const int64_t groups = ncol_pad / 32;
-    // Chunk length: 16 layers per thread amortises the chunk-face exchange; shorter chunks when
-    // there are too few columns to fill the machine (>= ~8 warps per SM wanted).
-    int Lc = 16;
+    const int budget = het ? LH_WARPS_PER_SM_HET : LH_WARPS_PER_SM;
+    // Chunks per column (= warps per column group): divisors of the warp budget, so that whole blocks fill it.
+    // Long chunks are cheaper (the first two cells of a chunk and its two faces are handled outside the layer loop:
+    // one thread per whole 64-layer column runs at 94 % of the HBM roofline, 16-layer chunks at 90 %,
+    // profiles/r01_z_chunk_length.log), so the column is cut only as far as needed for >= 8 waves of resident warps,
+    // and never below LH_MIN_CHUNK layers per thread — unless there are too few columns to even put 8 warps on
+    // every SM, when the chunks shrink down to 2 layers.
+    static const int cand20[] = {1, 2, 4, 5, 10, 20}, cand16[] = {1, 2, 4, 8, 16};
+    const int* cand = het ? cand16 : cand20;
+    const int ncand = het ? 5 : 6;
+    int min_chunk = LH_MIN_CHUNK;
+    if (const char* e = getenv("LH_MIN_CHUNK")) min_chunk = atoi(e) > 0 ? atoi(e) : min_chunk;   // tuning knob
+    const int64_t enough_warps = (int64_t)8 * sm_count * budget;
+    int k = 0;
+    while (k + 1 < ncand && groups * cand[k] < enough_warps && nlayer >= min_chunk * cand[k + 1]) ++k;
     const int64_t want_warps = (int64_t)sm_count * 8;
-    while (Lc > 2 && groups * ((nlayer + Lc - 1) / Lc) < want_warps) Lc >>= 1;
-    const int max_warps = lh_max_threads(model) / 32;      // register budget: 64K / (warps * 32 * regs)
-    int W = (nlayer + Lc - 1) / Lc;
-    if (W > max_warps) W = max_warps;
-    Lc = (nlayer + W - 1) / W;
+    while (k + 1 < ncand && groups * cand[k] < want_warps && nlayer >= 2 * cand[k + 1]) ++k;
+    int W = cand[k];
+    const int Lc = (nlayer + W - 1) / W;
     W = (nlayer + Lc - 1) / Lc;          // no empty chunks
     int G = 1;
-    const int want = max_warps < 4 ? max_warps : 4;        // 4-warp blocks: same occupancy as 8, less barrier wait
-    while (W * G * 2 <= want && (int64_t)G * 2 <= groups) G *= 2;
+    while (W * G * 2 <= 4 && (int64_t)G * 2 <= groups) G *= 2;     // 4-warp blocks at least (when there are that many groups)
     s.Lc = Lc; s.W = W; s.G = G;
     s.nblocks = (groups + G - 1) / G;
     const int nq = model == LH_MODEL_COUPLED ? 5 : 2;
     s.smem_bytes = (LH_TAB_DOUBLES + (size_t)G * W * ((2 * nq + 6) * 32 + 4 * 5 * 32)) * sizeof(double);   // + cp.async input ring
+    s.warp_budget = budget;
     const int by_smem = (int)((227 * 1024) / (s.smem_bytes + 1024));
-    const int by_threads = (model == 0 ? LhBounds<0>::min_blocks : LhBounds<1>::min_blocks);   // the register cap of __launch_bounds__
-    const int resident = by_smem < by_threads ? (by_smem < 1 ? 1 : by_smem) : by_threads;
+    const int by_regs = budget / (W * G);
+    int resident = by_smem < by_regs ? by_smem : by_regs;
+    if (resident < 1) resident = 1;
     s.waves = (double)s.nblocks / ((double)sm_count * resident);
     return s;
 }
@@ -62,7 +79,7 @@ cudaError_t lh_launch_stage(int model, int stage, int flags, const LhKernelArgs&
                             cudaStream_t stream)
 {
     if (model < 0 || model > 2) return cudaErrorInvalidValue;
-    if (shape.W * shape.G * 32 > lh_max_threads(model) || shape.smem_bytes > 200 * 1024) return cudaErrorInvalidConfiguration;
+    if (shape.W * shape.G > shape.warp_budget || shape.smem_bytes > 226 * 1024) return cudaErrorInvalidConfiguration;
     switch (model) {
     case 0: return lh_launch_stage_m0(stage, flags, args, shape, stream);
     case 1: return lh_launch_stage_m1(stage, flags, args, shape, stream);
@@ -74,7 +91,7 @@ cudaError_t lh_launch_ssprk33_persistent(int model, int flags, const LhKernelArg
                                          cudaStream_t stream)
 {
     if (model < 0 || model > 2) return cudaErrorInvalidValue;
-    if (shape.W * shape.G * 32 > lh_max_threads(model) || shape.smem_bytes > 200 * 1024) return cudaErrorInvalidConfiguration;
+    if (shape.W * shape.G > shape.warp_budget || shape.smem_bytes > 226 * 1024) return cudaErrorInvalidConfiguration;
     switch (model) {
     case 0: return lh_launch_persistent_m0(flags, args, shape, stream);
     case 1: return lh_launch_persistent_m1(flags, args, shape, stream);

@@ -6,35 +6,19 @@
 
 #include "lh_closures.cuh"
 
-// Register budget of the stage kernels (measured, gpurun_out/variants_i.log -> profiles/r01_i_*): once the
-// layer loop is provably warp-uniform (lh_stage_kernel.cuh) the coupled n = 2 variant needs ~96 registers
-// and every model runs best as 4-warp blocks, 5 resident blocks per SM (20 warps/SM, <= 102 registers):
-// coupled 80 %, general-n 61 %, Richards 51 % of the HBM roofline, against 79 / 58 / 49 % at 16 warps/SM.
+// Register budget of the stage kernels.  Once the layer loop is provably warp-uniform (lh_stage_kernel.cuh) the
+// coupled n = 2 variant needs ~96 registers and every model runs best with 20 resident warps per SM (<= 102
+// registers; profiles/r01_i_*: coupled 80 %, general-n 61 %, Richards 51 % of the HBM roofline, against 79 / 58 / 49 %
+// at 16 warps/SM).  The bound is expressed as __launch_bounds__(640, 1): the same register cap as (128, 5) and
+// byte-identical code, but blocks may hold up to 20 warps, which tall columns use for more chunks per column.
+// The per-column-parameter (HET) variants keep ~24 more registers live: (512, 1), 128 registers, 16 warps/SM.
 #ifndef LH_PDL
 #define LH_PDL 1      // programmatic dependent launch between consecutive stage kernels
 #endif
-#ifndef LH_MIN_BLOCKS_HET
-#define LH_MIN_BLOCKS_HET 4   // per-column parameters keep ~24 more registers live: 128 registers, 16 warps/SM
-#endif
-#ifndef LH_MIN_BLOCKS
-#define LH_MIN_BLOCKS 5
-#endif
-#ifndef LH_MAX_THREADS
-#define LH_MAX_THREADS 128
-#endif
-#ifndef LH_MIN_BLOCKS_RICHARDS
-#define LH_MIN_BLOCKS_RICHARDS 5
-#endif
-#ifndef LH_MAX_THREADS_RICHARDS
-#define LH_MAX_THREADS_RICHARDS 128
-#endif
-template <int MODEL> struct LhBounds { static constexpr int max_threads = LH_MAX_THREADS, min_blocks = LH_MIN_BLOCKS; };
-template <> struct LhBounds<0> { static constexpr int max_threads = LH_MAX_THREADS_RICHARDS, min_blocks = LH_MIN_BLOCKS_RICHARDS; };
-inline int lh_max_threads(int model) { return model == 0 ? LhBounds<0>::max_threads : LhBounds<1>::max_threads; }
+#define LH_WARPS_PER_SM 20
+#define LH_WARPS_PER_SM_HET 16
+template <int FLAGS> struct LhBounds { static constexpr int max_threads = ((FLAGS & LH_FLAG_HET) ? LH_WARPS_PER_SM_HET : LH_WARPS_PER_SM) * 32; };
 
-// Device layout of every cell field: column-fastest SoA, element (layer, col) at
-// [layer * ncol_pad + col]; ncol_pad is a multiple of 32 so that a warp (32 adjacent columns)
-// reads/writes two full, aligned 128-byte lines per field per layer.
 // What one stage reads and writes (device pointers to column-fastest SoA blocks) and its scalars.
 struct LhStageIO {
     const double* in_th;   // stage input ϑ_l            (state U, or stage buffer V)
@@ -73,10 +57,11 @@ struct LhLaunchShape {
     int32_t Lc, W, G;      // chunk length, chunks per column, column groups (of 32) per block
     int64_t nblocks;
     size_t smem_bytes;
+    int32_t warp_budget;   // resident warps per SM the variant's register cap allows (20, HET: 16)
     double waves;          // nblocks / (SMs x resident blocks per SM)
 };
 
-LhLaunchShape lh_choose_shape(int model, int64_t ncol_pad, int32_t nlayer, int sm_count);
+LhLaunchShape lh_choose_shape(int model, int64_t ncol_pad, int32_t nlayer, int sm_count, bool het);
 
 // stage 0 = tendency only; 1..3 = fused RHS + SSPRK33 stage; 4 = generic Shu-Osher stage; 5 = 2N stage.  flags: LH_FLAG_ICE | LH_FLAG_GEN
 // (lh_closures.cuh) select the compiled kernel variant.

@@ -374,6 +374,7 @@ void update_kernel_flags(lh_soil_ctx* c)
     const bool vg2 = !het && q.vg_n == 2.0 && q.vg_m == 0.5;      // S^(1/m) = S^2, x^m = sqrt(x): no log/exp needed
     c->kernel_flags = (c->has_ice ? LH_FLAG_ICE : 0) | (gen ? LH_FLAG_GEN : 0) | (vg2 && !c->force_general_vg ? LH_FLAG_VG2 : 0) |
                       (het ? LH_FLAG_HET : 0);
+    c->shape = lh_choose_shape(c->model, c->ncol_pad, c->nlayer, c->sm_count, het);   // the HET variants have a smaller warp budget
 }
 
 // θ_i was (re)written: is there any ice?  One pass over the field; θ_i never changes afterwards.
@@ -506,7 +507,7 @@ int32_t lh_soil_create(const lh_soil_config* cfg, lh_soil_ctx** out)
         LH_CREATE_CUDA(cudaEventCreateWithFlags(&c->ev_copy[k], cudaEventDisableTiming));
         LH_CREATE_CUDA(cudaEventCreateWithFlags(&c->ev_xpose[k], cudaEventDisableTiming));
     }
-    c->shape = lh_choose_shape(c->model, c->ncol_pad, c->nlayer, c->sm_count);
+    c->shape = lh_choose_shape(c->model, c->ncol_pad, c->nlayer, c->sm_count, false);
     update_kernel_flags(c);
 
     const size_t fb = field_bytes(c);

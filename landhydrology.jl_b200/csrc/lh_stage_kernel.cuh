@@ -434,7 +434,7 @@ __device__ __forceinline__ void lh_stage_body(const LhKernelArgs& A, const LhSta
 }
 
 template <int MODEL, int STAGE, int FLAGS>
-__global__ void __launch_bounds__(LhBounds<MODEL>::max_threads, (FLAGS & LH_FLAG_HET) ? LH_MIN_BLOCKS_HET : LhBounds<MODEL>::min_blocks)
+__global__ void __launch_bounds__(LhBounds<FLAGS>::max_threads, 1)
 lh_soil_stage_kernel(const __grid_constant__ LhKernelArgs A)
 {
     extern __shared__ __align__(16) double smem[];
@@ -460,7 +460,7 @@ lh_soil_stage_kernel(const __grid_constant__ LhKernelArgs A)
 // Used for grids of few waves (column shards of a multi-GPU run, small domains), where launch gaps and wave
 // quantisation cost more than 5 %; results are bit-identical to the per-stage launches.
 template <int MODEL, int FLAGS>
-__global__ void __launch_bounds__(LhBounds<MODEL>::max_threads, (FLAGS & LH_FLAG_HET) ? LH_MIN_BLOCKS_HET : LhBounds<MODEL>::min_blocks)
+__global__ void __launch_bounds__(LhBounds<FLAGS>::max_threads, 1)
 lh_soil_ssprk33_persistent_kernel(const __grid_constant__ LhKernelArgs A)
 {
     extern __shared__ __align__(16) double smem[];
