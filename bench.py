@@ -186,7 +186,7 @@ def main():
         real_stdout.flush()
 
 
-def _main(args, out):
+def _main(args, result_stream):
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
@@ -222,7 +222,7 @@ def _main(args, out):
             "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0,
         }
-        print(json.dumps(line), file=out)
+        print(json.dumps(line), file=result_stream)
         return 0
 
     # ---------------- this repo's arm ------------------------------------------------------------------
@@ -387,8 +387,8 @@ def _main(args, out):
     if world == 1 and not args.no_cpu_baseline:
         v, cores, sample, sec, steps, _ = time_oracle(w, lh, graft, args.model, args.nlayer, 0, 0, target_seconds=12.0)
         line["cpu_baseline"] = {"value": v, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample}
-    print(json.dumps(line), file=out)
-    out.flush()
+    print(json.dumps(line), file=result_stream)
+    result_stream.flush()
     if world > 1:
         dist.destroy_process_group()
     return 0

@@ -275,3 +275,47 @@ def test_simulation_argument_errors():
         lh.Simulation(m, lh.SSPRK33(), Y_init=None, dt=1.0, tspan=(0.0, 1.0), Ya_init=None)
     with pytest.raises(NotImplementedError):
         lh.Simulation(m, object(), Y_init=Y, dt=1.0, tspan=(0.0, 1.0), Ya_init=Ya)
+
+
+# ---- bench.py contract (CPU part): the reference arm prints exactly one JSON line with the agreed keys -------------
+def test_bench_reference_arm_json_line():
+    import json
+    import subprocess
+    import sys
+
+    res = subprocess.run([sys.executable, w.ROOT + "/bench.py", "--impl", "reference", "--steps", "1", "--warmup", "1",
+                          "--ncol", "1048576"], capture_output=True, text=True, timeout=600)
+    assert res.returncode == 0, res.stderr[-2000:]
+    lines = [l for l in res.stdout.splitlines() if l.strip()]
+    assert len(lines) == 1, res.stdout
+    d = json.loads(lines[0])
+    for key in ("impl", "metric", "value", "unit", "n_gpus", "steps", "warmup", "ms_per_step", "higher_is_better", "scaling",
+                "vs_baseline", "dtype", "data", "config", "cpu_baseline", "e2e"):
+        assert key in d, key
+    assert d["impl"] == "reference" and d["dtype"] == "f64" and d["unit"] == "cell-steps/s" and d["value"] > 0
+    assert d["cpu_baseline"]["kind"] == "port" and d["cpu_baseline"]["cores"] >= 1 and "workload" in d["config"]
+    assert d["e2e"]["h2d_bytes_per_step"] == 0 and d["e2e"]["d2h_bytes_per_step"] == 0
+
+
+@pytest.mark.gpu
+def test_bench_b200_arm_json_line():
+    """The whole bench.py contract on a small shard: one JSON line, device-timed value, roofline, e2e with host copies,
+    clocks, kernel launch count, CPU baseline."""
+    import json
+    import subprocess
+    import sys
+
+    res = subprocess.run([sys.executable, w.ROOT + "/bench.py", "--ncol", "65536", "--steps", "3", "--warmup", "3"],
+                         capture_output=True, text=True, timeout=900)
+    assert res.returncode == 0, res.stderr[-2000:]
+    lines = [l for l in res.stdout.splitlines() if l.strip()]
+    assert len(lines) == 1, res.stdout
+    d = json.loads(lines[0])
+    for key in ("metric", "value", "unit", "n_gpus", "steps", "warmup", "ms_per_step", "higher_is_better", "scaling", "vs_baseline",
+                "dtype", "data", "config", "clocks", "gpu_launches", "roofline", "e2e", "cpu_baseline", "budgets"):
+        assert key in d, key
+    assert d["n_gpus"] == 1 and d["steps"] == 3 and d["gpu_launches"] in (9, 1) and d["value"] > 1e9
+    r = d["roofline"]
+    assert r["bound"] == "hbm" and 0 < r["frac"] < 1.2 and abs(r["frac"] - r["achieved"] / r["peak"]) < 1e-12
+    assert d["e2e"]["h2d_bytes_per_step"] > 0 and d["e2e"]["d2h_bytes_per_step"] > 0 and 0 < d["e2e"]["value"] < d["value"]
+    assert d["cpu_baseline"]["kind"] == "port" and d["cpu_baseline"]["value"] > 0
