@@ -166,6 +166,20 @@ function make_rhs(model::SoilModel)
     return rhs!
 end
 
+"""
+    set_column_params!(engine; ν, θr, n, α, Ksat)
+
+Heterogeneous soils (new): per-column vectors instead of the scalars of `SoilParams` / `vanGenuchten`; `nothing` keeps
+the model's value.
+"""
+function set_column_params!(e::Engine; ν = nothing, θr = nothing, n = nothing, α = nothing, Ksat = nothing)
+    ptr(a) = a === nothing ? Ptr{Cdouble}(C_NULL) : pointer(a)
+    arrs = map(a -> a === nothing ? nothing : Vector{Float64}(a), (ν, θr, n, α, Ksat))
+    GC.@preserve arrs check(e.ctx, ccall((:lh_soil_set_column_params, LIB), Int32,
+        (Ptr{Cvoid}, Ptr{Cdouble}, Ptr{Cdouble}, Ptr{Cdouble}, Ptr{Cdouble}, Ptr{Cdouble}), e.ctx, map(ptr, arrs)...))
+    return nothing
+end
+
 # lh_soil_stepper (include/lh_soil.h): coefficient table of a two-register Shu-Osher or a Williamson 2N method
 const LH_MAX_STAGES = 16
 struct LhSoilStepper

@@ -178,6 +178,21 @@ class SoilEngine:
         a, b, c = self.prescribed_profiles(t), self.prescribed_profiles(t + dt), self.prescribed_profiles(t + 0.5 * dt)
         return any(not (np.array_equal(a[k], b[k]) and np.array_equal(a[k], c[k])) for k in a)
 
+    # -- heterogeneous soils (new): per-column hydraulic parameters ---------------------------------
+    def set_column_params(self, *, ν=None, θr=None, n=None, α=None, Ksat=None):
+        """Per-column ``ν``, ``θr``, van Genuchten ``n`` and ``α``, ``Ksat`` (arrays over ALL columns of the domain; this
+        engine takes its own column range) instead of the scalars of ``SoilParams`` / ``vanGenuchten``
+        (reference parameters.jl:11-43, SoilWaterParameterizations.jl:151-170).  ``None`` keeps the model's scalar."""
+        def shard(a):
+            if a is None:
+                return None
+            a = np.asarray(a, dtype=np.float64)
+            if a.shape != (self.model.domain.ncolumns,):
+                raise ValueError(f"per-column parameter must have shape ({self.model.domain.ncolumns},)")
+            lo, hi = self.column_range
+            return np.ascontiguousarray(a[lo:hi])
+        self.ctx.set_column_params(nu=shard(ν), theta_r=shard(θr), vg_n=shard(n), vg_alpha=shard(α), Ksat=shard(Ksat))
+
     # -- state transfer ----------------------------------------------------------------------------
     def _shard(self, a: np.ndarray) -> np.ndarray:
         if a.ndim == 1:

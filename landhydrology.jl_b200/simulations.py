@@ -255,12 +255,13 @@ class Simulation(AbstractSimulation):
 
     ``kwargs`` understood: ``saveat`` (scalar spacing or list of times); ``progress`` /
     ``progress_message`` are accepted and ignored; ``max_steps_per_call`` bounds how many steps are
-    fused into one ``lh_soil_step_ssprk33`` call.
+    fused into one ``lh_soil_step_ssprk33`` call; ``column_params`` (new) = per-column ``ν``, ``θr``, ``n``, ``α``,
+    ``Ksat`` arrays for heterogeneous soils (``SoilEngine.set_column_params``).
     """
 
     def __init__(self, model: AbstractModel, method, *, Y_init, dt, tspan, Ya_init, callbacks=None,
                  saveat=None, progress=False, progress_message=None, max_steps_per_call: int = 4096,
-                 device: int = 0, check_finite: bool = False):
+                 device: int = 0, check_finite: bool = False, column_params: Optional[dict] = None):
         if not isinstance(method, _Stepper):
             raise NotImplementedError(
                 "the B200 path runs explicit low-storage methods: SSPRK33 (the only stepper the reference uses), Euler, "
@@ -275,6 +276,8 @@ class Simulation(AbstractSimulation):
         self.callbacks = callbacks
         engine = SoilEngine(model, float(tspan[0]), device=device, library=current_library(),
                             check_finite=check_finite)
+        if column_params:
+            engine.set_column_params(**column_params)       # heterogeneous soils: ν, θr, n, α, Ksat per column
         if engine.has_time_dependent_aux(float(tspan[0]), float(dt)) and not isinstance(method, SSPRK33):
             raise NotImplementedError("time-dependent prescribed profiles are streamed stage by stage for SSPRK33 only")
         self.integrator = Integrator(engine, Y_init, Ya_init, tspan, dt, saveat, callbacks, max_steps_per_call, method)

@@ -120,3 +120,42 @@ def test_cuda_constant_arrays_match_homogeneous(cuda):
     wl.upload(b)
     b.step(0.0, wl.dt, 5)
     assert np.array_equal(a.get_state(0), b.get_state(0))
+
+
+@pytest.fixture(params=["oracle", pytest.param("cuda", marks=pytest.mark.gpu)])
+def backend(request, oracle):
+    lib = oracle if request.param == "oracle" else lh.cuda_library()
+    with lh.use_library(lib):
+        yield lib
+
+
+def test_simulation_with_column_params(backend, oracle):
+    """HybridBox of 6 x 4 columns with per-column K_sat and van Genuchten n through Simulation(column_params=...)."""
+    box = lh.HybridBox(zlim=(-1.0, 0.0), nelements=(6, 4, 16))
+    model = lh.SoilModel(
+        np.float64, domain=box, energy_model=lh.PrescribedTemperatureModel(),
+        hydrology_model=lh.SoilHydrologyModel(hydraulic_model=w.sand_vg()),
+        boundary_conditions=lh.SoilColumnBC(top=lh.SoilComponentBC(hydrology=lh.Dirichlet(lambda t: 0.25)),
+                                            bottom=lh.SoilComponentBC(hydrology=lh.FreeDrainage())),
+        soil_param_set=w.sand_soil_params(), earth_param_set=lh.EarthParameterSet())
+    Y, Ya = lh.initialize_states(model, lambda z, m: {"ϑ_l": 0.12, "θ_i": 0.0}, 0.0)
+    rng = np.random.default_rng(3)
+    cp = {"Ksat": w.sand_vg().Ksat * 10.0 ** rng.uniform(-1, 1, 24), "n": rng.uniform(2.0, 4.5, 24)}
+    sim = lh.Simulation(model, lh.SSPRK33(), Y_init=Y, dt=0.25, tspan=(0.0, 5.0), Ya_init=Ya, column_params=cp)
+    sol = lh.run_(sim)
+    got = np.asarray(lh.parent(sol.u[-1].soil.ϑ_l))
+    assert got.shape[0] == 24 and np.all(np.isfinite(got))
+    # columns differ because their parameters do
+    assert np.max(np.abs(got - got[0])) > 1e-6
+    # column k equals a single Column run with that column's parameters
+    k = 5
+    vg = lh.vanGenuchten(n=cp["n"][k], α=w.sand_vg().α, Ksat=cp["Ksat"][k], θr=w.sand_vg().θr)
+    p = w.make_params(w.sand_soil_params(), vg)
+    D, FD, N = abi.LH_BC_DIRICHLET, abi.LH_BC_FREE_DRAINAGE, abi.LH_BC_NONE
+    wl = w.Workload(model=abi.LH_MODEL_RICHARDS, ncol=1, nlayer=16, zmin=-1.0, zmax=0.0, params=p,
+                    top=(N, 0.0, D, 0.25), bottom=(N, 0.0, FD, 0.0), dt=0.25)
+    ctx = lh.SoilContext(oracle, wl.config())
+    ctx.set_state(0, np.full((1, 16), 0.12)); ctx.set_state(1, np.zeros((1, 16)))
+    ctx.step(0.0, 0.25, 20)
+    ref = ctx.get_state(0)[0]
+    assert np.max(np.abs(got[k] - ref)) <= 1e-10 * np.max(np.abs(ref))
