@@ -65,7 +65,7 @@ LhLaunchShape lh_choose_shape(int model, int64_t ncol_pad, int32_t nlayer, int s
     s.Lc = Lc; s.W = W; s.G = G;
     s.nblocks = (groups + G - 1) / G;
     const int nq = model == LH_MODEL_COUPLED ? 5 : 2;
-    s.smem_bytes = (LH_TAB_DOUBLES + (size_t)G * W * ((2 * nq + 6) * 32 + 4 * 5 * 32)) * sizeof(double);   // + cp.async input ring
+    s.smem_bytes = (LH_TAB_DOUBLES + 2 * LH_WARPS_PER_SM + (size_t)G * W * ((2 * nq + 6) * 32 + 4 * 5 * 32)) * sizeof(double);   // + cp.async input ring
     s.warp_budget = budget;
     const int by_smem = (int)((227 * 1024) / (s.smem_bytes + 1024));
     const int by_regs = budget / (W * G);
@@ -215,12 +215,12 @@ __global__ void lh_budget_partial_kernel(const double* __restrict__ th, const do
     if (threadIdx.x == 0) { partials[2 * blockIdx.x] = bw; partials[2 * blockIdx.x + 1] = be; }
 }
 
-__global__ void lh_budget_final_kernel(const double* __restrict__ partials, int32_t npartials, double dz,
+__global__ void lh_budget_final_kernel(const double* __restrict__ partials, int64_t npartials, double dz,
                                        double* __restrict__ out2)
 {
     __shared__ double sh[32];
     double sw = 0.0, se = 0.0;
-    for (int i = threadIdx.x; i < npartials; i += blockDim.x) { sw += partials[2 * i]; se += partials[2 * i + 1]; }
+    for (int64_t i = threadIdx.x; i < npartials; i += blockDim.x) { sw += partials[2 * i]; se += partials[2 * i + 1]; }
     const double bw = block_sum(sw, sh);
     const double be = block_sum(se, sh);
     if (threadIdx.x == 0) { out2[0] = bw * dz; out2[1] = be * dz; }
@@ -232,6 +232,12 @@ cudaError_t lh_launch_budgets(const double* th, const double* re, int64_t ncol, 
                               double* out2, cudaStream_t stream)
 {
     lh_budget_partial_kernel<<<npartials, BUDGET_THREADS, 0, stream>>>(th, re, ncol, ncol_pad, nlayer, partials);
+    lh_budget_final_kernel<<<1, BUDGET_THREADS, 0, stream>>>(partials, npartials, dz, out2);
+    return cudaGetLastError();
+}
+
+cudaError_t lh_launch_budgets_from_partials(const double* partials, int64_t npartials, double dz, double* out2, cudaStream_t stream)
+{
     lh_budget_final_kernel<<<1, BUDGET_THREADS, 0, stream>>>(partials, npartials, dz, out2);
     return cudaGetLastError();
 }

@@ -35,7 +35,7 @@ struct LhStageIO {
     double dt;
     double sa, sb, sg;     // stage coefficients of the generic steppers (STAGE 4: a, b, g; STAGE 5: a, b)
     int32_t first2n;       // STAGE 5, first stage: r is not read (a == 0 and r may hold anything)
-    int32_t pad_;
+    int32_t budget;        // STAGE 6: this is the last stage of a step (accumulate the budgets of what it writes)
 };
 
 struct LhKernelArgs {
@@ -43,6 +43,8 @@ struct LhKernelArgs {
     LhStageIO io;          // one-stage launches: this stage; persistent SSPRK33 launches: stage 1 (in = U, out = V)
     const double* zc;      // nlayer centre coordinates
     const double* colp;    // HET variants: [LHCP_COUNT][ncol_pad] per-column derived parameters
+    double* budget_partials;   // [nblocks][2]: per-block sums of the ϑ_l and ρe_int values the last stage writes (or NULL)
+    int64_t ncol;          // valid columns (<= ncol_pad): the padding is left out of the budgets
     int64_t ncol_pad;
     int32_t nlayer;
     int32_t Lc;            // layers per thread (vertical chunk)
@@ -82,6 +84,8 @@ cudaError_t lh_launch_diagnostic(int model, int which, const LhDevParams& p, con
 cudaError_t lh_launch_budgets(const double* th, const double* re, int64_t ncol, int64_t ncol_pad,
                               int32_t nlayer, double dz, double* partials, int32_t npartials,
                               double* out2, cudaStream_t stream);
+// The same from the per-block sums a last-stage launch left behind (fixed-shape tree over the blocks).
+cudaError_t lh_launch_budgets_from_partials(const double* partials, int64_t npartials, double dz, double* out2, cudaStream_t stream);
 
 // Layout transforms between a dense host-layout staging block [col][layer] (layer fastest) and
 // the device SoA [layer][ncol_pad].

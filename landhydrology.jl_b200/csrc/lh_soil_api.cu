@@ -88,6 +88,10 @@ struct lh_soil_ctx {
     int32_t npartials = 0;
     double* budget_dev = nullptr;                // 2 doubles (+2 for the all-reduce result)
     double* colp_dev = nullptr;                  // [LHCP_COUNT][ncol_pad] per-column derived parameters (heterogeneous soils)
+    double* fused_partials = nullptr;            // [shape.nblocks][2] budget sums left by the last-stage launches
+    int64_t fused_nblocks = 0;
+    bool budget_fresh = false;                   // fused_partials describe the current state U
+    bool external_writes = false;                // lh_soil_device_ptr handed out U: never trust the fused sums
     double* bc_dev = nullptr;                    // boundary-value table of a persistent launch
     int64_t bc_dev_steps = 0;
     unsigned long long* nonfinite_dev = nullptr;
@@ -218,6 +222,7 @@ void free_all(lh_soil_ctx* c)
     if (c->partials) cudaFree(c->partials);
     if (c->budget_dev) cudaFree(c->budget_dev);
     if (c->bc_dev) cudaFree(c->bc_dev);
+    if (c->fused_partials) cudaFree(c->fused_partials);
     if (c->colp_dev) cudaFree(c->colp_dev);
     if (c->nonfinite_dev) cudaFree(c->nonfinite_dev);
     if (c->ev_start) cudaEventDestroy(c->ev_start);
@@ -375,6 +380,14 @@ void update_kernel_flags(lh_soil_ctx* c)
     c->kernel_flags = (c->has_ice ? LH_FLAG_ICE : 0) | (gen ? LH_FLAG_GEN : 0) | (vg2 && !c->force_general_vg ? LH_FLAG_VG2 : 0) |
                       (het ? LH_FLAG_HET : 0);
     c->shape = lh_choose_shape(c->model, c->ncol_pad, c->nlayer, c->sm_count, het);   // the HET variants have a smaller warp budget
+    c->budget_fresh = false;
+    if (c->fused_nblocks < c->shape.nblocks) {        // per-block budget sums of the last-stage launches
+        if (c->fused_partials) cudaFree(c->fused_partials);
+        c->fused_partials = nullptr;
+        c->fused_nblocks = 0;
+        if (cudaMalloc(&c->fused_partials, (size_t)c->shape.nblocks * 2 * sizeof(double)) == cudaSuccess) c->fused_nblocks = c->shape.nblocks;
+        else c->fused_partials = nullptr;              // the budgets then come from the full pass
+    }
 }
 
 // θ_i was (re)written: is there any ice?  One pass over the field; θ_i never changes afterwards.
@@ -406,6 +419,8 @@ void fill_args(lh_soil_ctx* c, int stage, double dt, LhKernelArgs& a)
     else { a.io.out_th = c->V[0]; a.io.out_re = c->V[2]; }
     a.zc = c->zc_dev;
     a.colp = c->colp_dev;
+    a.budget_partials = c->fused_partials;
+    a.ncol = c->ncol;
     a.ncol_pad = c->ncol_pad;
     a.nlayer = c->nlayer;
     a.Lc = c->shape.Lc;
@@ -420,7 +435,7 @@ void fill_args(lh_soil_ctx* c, int stage, double dt, LhKernelArgs& a)
     a.io.out2_re = c->V[2];
     a.io.sa = 0.0; a.io.sb = 1.0; a.io.sg = 1.0;
     a.io.first2n = 0;
-    a.io.pad_ = 0;
+    a.io.budget = 0;
     a.nsteps = 0;
     a.bc_dev = nullptr;
 }
@@ -571,6 +586,7 @@ int32_t lh_soil_set_state(lh_soil_ctx* c, int32_t field, const double* host, int
     if (!c) return LH_ERR_INVALID_ARG;
     if (!field_ok(field)) return fail(c, LH_ERR_INVALID_ARG, "bad field id %d", field);
     if (!c->U[field]) return fail(c, LH_ERR_INVALID_ARG, "field %d does not exist for model kind %d", field, c->model);
+    c->budget_fresh = false;
     int32_t st = upload_field(c, c->U[field], host, cs, ls);
     if (st == LH_OK && field == LH_FIELD_THETA_I) st = detect_ice(c);
     return st;
@@ -692,7 +708,9 @@ int32_t lh_soil_stage_ssprk33(lh_soil_ctx* c, int32_t stage, double dt)
     if (!c) return LH_ERR_INVALID_ARG;
     if (stage < 1 || stage > 3) return fail(c, LH_ERR_INVALID_ARG, "stage must be 1, 2 or 3");
     LH_CUDA(c, cudaSetDevice(c->device));
-    return launch_stage(c, stage, dt);
+    int32_t st = launch_stage(c, stage, dt);
+    if (st == LH_OK && stage == 3) c->budget_fresh = c->fused_partials != nullptr;   // stages 1, 2 do not touch U
+    return st;
 }
 
 // The persistent launch pays for grids of at most ~3 waves (<= ~2000 blocks: small domains, launch-bound): measured
@@ -748,6 +766,7 @@ int32_t lh_soil_step_ssprk33(lh_soil_ctx* c, double t, double dt, int64_t nsteps
     LH_CUDA(c, cudaEventRecord(c->ev_stop, c->stream));
     c->timing_valid = true;
     c->last_launches = launches;
+    if (nsteps > 0) c->budget_fresh = c->fused_partials != nullptr;       // the last stage-3 launch summed what it wrote
     if (c->cfg.flags & LH_FLAG_CHECK_FINITE) return check_finite(c);
     return LH_OK;
 }
@@ -847,8 +866,25 @@ int32_t lh_soil_step(lh_soil_ctx* c, const lh_soil_stepper* sp, double t, double
     }
     LH_CUDA(c, cudaEventRecord(c->ev_stop, c->stream));
     c->timing_valid = true;
+    c->budget_fresh = false;
     c->last_launches = ns * nsteps;
     if (c->cfg.flags & LH_FLAG_CHECK_FINITE) return check_finite(c);
+    return LH_OK;
+}
+
+// Local budgets into c->budget_dev[0..1].  Right after a step the last-stage launches have already summed, per block,
+// the values they wrote (fused epilogue): only the fixed-shape reduction over the blocks is left.  Otherwise (fresh
+// upload, generic stepper, heat-only model whose ϑ_l is prescribed, raw device pointer handed out) one pass over the state.
+static int32_t local_budgets(lh_soil_ctx* c)
+{
+    const bool fused = c->budget_fresh && !c->external_writes && c->fused_partials && has_water(c->model);
+    if (fused) {
+        LH_CUDA(c, lh_launch_budgets_from_partials(c->fused_partials, c->shape.nblocks, c->dp.dz, c->budget_dev, c->stream));
+        return LH_OK;
+    }
+    const double* re = c->U[2] ? c->U[2] : c->U[1];   // no energy model: E budget of θ_i slot is meaningless -> report 0
+    LH_CUDA(c, lh_launch_budgets(c->U[0], re, c->ncol, c->ncol_pad, c->nlayer, c->dp.dz, c->partials,
+                                 c->npartials, c->budget_dev, c->stream));
     return LH_OK;
 }
 
@@ -856,9 +892,8 @@ int32_t lh_soil_budgets(lh_soil_ctx* c, double out[2])
 {
     if (!c || !out) return LH_ERR_INVALID_ARG;
     LH_CUDA(c, cudaSetDevice(c->device));
-    const double* re = c->U[2] ? c->U[2] : c->U[1];   // no energy model: E budget of θ_i slot is meaningless -> report 0
-    LH_CUDA(c, lh_launch_budgets(c->U[0], re, c->ncol, c->ncol_pad, c->nlayer, c->dp.dz, c->partials,
-                                 c->npartials, c->budget_dev, c->stream));
+    int32_t st = local_budgets(c);
+    if (st != LH_OK) return st;
     LH_CUDA(c, cudaMemcpyAsync(out, c->budget_dev, 2 * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
     LH_CUDA(c, cudaStreamSynchronize(c->stream));
     if (!c->U[2]) out[1] = 0.0;
@@ -925,6 +960,7 @@ int32_t lh_soil_device_ptr(lh_soil_ctx* c, int32_t field, void** dptr, int64_t* 
     if (!c || !dptr) return LH_ERR_INVALID_ARG;
     if (!field_ok(field) || !c->U[field]) return fail(c, LH_ERR_INVALID_ARG, "field %d does not exist", field);
     *dptr = c->U[field];
+    c->external_writes = true;
     if (ncol_padded) *ncol_padded = c->ncol_pad;
     if (field == LH_FIELD_THETA_I) {   // the caller may write ice through the raw pointer: assume it does
         c->has_ice = true;
@@ -968,9 +1004,8 @@ int32_t lh_soil_budgets_allreduce(lh_soil_ctx* c, double out[2])
     if (!c->comm) return fail(c, LH_ERR_STATE, "lh_soil_comm_init has not been called");
     NcclApi& n = nccl();
     LH_CUDA(c, cudaSetDevice(c->device));
-    const double* re = c->U[2] ? c->U[2] : c->U[1];
-    LH_CUDA(c, lh_launch_budgets(c->U[0], re, c->ncol, c->ncol_pad, c->nlayer, c->dp.dz, c->partials,
-                                 c->npartials, c->budget_dev, c->stream));
+    int32_t st = local_budgets(c);
+    if (st != LH_OK) return st;
     int r = n.AllReduce(c->budget_dev, c->budget_dev + 2, 2, NCCL_FLOAT64, NCCL_SUM, c->comm, c->stream);
     if (r != 0) return fail(c, LH_ERR_NCCL, "ncclAllReduce failed: %s", n.GetErrorString ? n.GetErrorString(r) : "?");
     LH_CUDA(c, cudaMemcpyAsync(out, c->budget_dev + 2, 2 * sizeof(double), cudaMemcpyDeviceToHost, c->stream));

@@ -149,6 +149,7 @@ template <int MODEL> struct Cell { Q<MODEL> q; Base base; };
 // Input ring (cp.async): RING_DEPTH cells x RING_FIELDS fields x 32 lanes per warp.
 constexpr int RING_DEPTH = 4, RING_FIELDS = 5, RING_DOUBLES = RING_DEPTH * RING_FIELDS * 32;
 constexpr uint32_t RING_CELL_BYTES = RING_FIELDS * 256;
+constexpr int LH_RED_DOUBLES = 2 * LH_WARPS_PER_SM;      // per-warp budget partial sums (after the tables)
 
 template <int MODEL> struct Slot { static constexpr int NQv = NQ<MODEL>::value; static constexpr int doubles = (2 * NQv + 6) * 32; };
 
@@ -194,7 +195,7 @@ __device__ __forceinline__ void lh_stage_body_impl(const LhKernelArgs& A, const 
 
     // shared memory: the exp2 / log2 tables, then per (g, w): one Slot (chunk-face exchange) and one input ring
     const double* tab = smem;
-    double* warp_base = smem + LH_TAB_DOUBLES + (size_t)(g * W + w) * (Slot<MODEL>::doubles + RING_DOUBLES);
+    double* warp_base = smem + LH_TAB_DOUBLES + LH_RED_DOUBLES + (size_t)(g * W + w) * (Slot<MODEL>::doubles + RING_DOUBLES);
     double* slot = warp_base + lane;
     double* sm_bot = slot;                               // Q of the chunk's first cell
     double* sm_top = slot + NQv * 32;                    // Q of the chunk's last cell
@@ -290,16 +291,23 @@ __device__ __forceinline__ void lh_stage_body_impl(const LhKernelArgs& A, const 
     const double cdt = STAGE == 6 ? io.dt /* the caller passes cdt itself */ : STAGE == 0 ? -p.inv_dz : (STAGE == 3 ? -2.0 * (io.dt * p.inv_dz) : STAGE == 4 ? -((io.sg * io.dt) * p.inv_dz) : -(io.dt * p.inv_dz));
     double* o2th = io.out2_th + col;     // 2N stages: the residual register r
     double* o2re = io.out2_re + col;
+    // The last SSPRK33 stage writes the new state: its values are summed on the way out (water and energy budgets of this
+    // thread's cells), so that lh_soil_budgets after a step needs no pass over the state.
+    constexpr bool BUDGET = STAGE == 3 || STAGE == 6;
+    const bool budget = BUDGET && (STAGE == 3 || io.budget) && A.budget_partials != nullptr;     // block-uniform
+    double bud_w = 0.0, bud_e = 0.0;
     auto store_cell = [&](int64_t o, const Base& base, const Flux& lo, const Flux& hi) {
         if constexpr (MODEL != 1) {
             const double v = stage_out<STAGE>(base.th, hi.w - lo.w, cdt, io.sg);
             if constexpr (STAGE == 5) { o2th[o] = v; oth[o] = fma(io.sb, v, base.th2); }
             else oth[o] = v;
+            if constexpr (BUDGET) bud_w += v;
         }
         if constexpr (MODEL != 0) {
             const double v = stage_out<STAGE>(base.re, hi.e - lo.e, cdt, io.sg);
             if constexpr (STAGE == 5) { o2re[o] = v; ore[o] = fma(io.sb, v, base.re2); }
             else ore[o] = v;
+            if constexpr (BUDGET) bud_e += v;
         }
     };
     int64_t o_st = (int64_t)(a + 1) * stride;   // element offset of the next cell to store (cell a is stored last)
@@ -398,6 +406,27 @@ __device__ __forceinline__ void lh_stage_body_impl(const LhKernelArgs& A, const 
             write_at(b - 1, base_prev, F_below, F_hi);
         }
     }
+    if constexpr (BUDGET) {
+        if (budget) {
+            // fixed-shape tree: lanes (padding columns masked), then the block's warps in order -> one pair per block
+            if (!active || col >= A.ncol) { bud_w = 0.0; bud_e = 0.0; }
+            for (int o = 16; o > 0; o >>= 1) {
+                bud_w += __shfl_down_sync(0xffffffffu, bud_w, o);
+                bud_e += __shfl_down_sync(0xffffffffu, bud_e, o);
+            }
+            double* red = smem + LH_TAB_DOUBLES;
+            const int wib = g * W + w;
+            if (lane == 0) { red[2 * wib] = bud_w; red[2 * wib + 1] = bud_e; }
+            __syncthreads();
+            if (wib == 0 && lane == 0) {
+                double sw = 0.0, se = 0.0;
+                const int nw = (int)(blockDim.y * blockDim.z);
+                for (int k = 0; k < nw; ++k) { sw += red[2 * k]; se += red[2 * k + 1]; }
+                A.budget_partials[2 * (int64_t)blockIdx.x] = sw;
+                A.budget_partials[2 * (int64_t)blockIdx.x + 1] = se;
+            }
+        }
+    }
 }
 
 // Homogeneous soils: the parameters are the launch's uniform block.  HET (lh_soil_set_column_params): every lane
@@ -484,6 +513,7 @@ lh_soil_ssprk33_persistent_kernel(const __grid_constant__ LhKernelArgs A)
         io.sb = st == 2 ? 2.0 : 1.0;
         io.sg = st == 0 ? 1.0 : st == 1 ? 0.25 : 1.0 / 3.0;
         io.dt = st == 2 ? cdt3 : cdt1;
+        io.budget = st == 2;
         if (A.bc_dev) {
             const double* b = A.bc_dev + k * 4;
             io.bcv[0] = b[0]; io.bcv[1] = b[1]; io.bcv[2] = b[2]; io.bcv[3] = b[3];

@@ -407,3 +407,36 @@ def test_randomized_parity(cuda, oracle, seed):
     g, o = _pair(cuda, oracle, wl, flags=flags)
     assert_tendency_parity(g, o, wl.model)
     assert_state_parity(g, o, wl.model, wl.dt, 4)
+
+
+@pytest.mark.parametrize("kind,ncol,nlayer", [("coupled", 777, 64), ("coupled", 33, 300), ("richards", 1000, 100), ("coupled", 5, 1),
+                                              ("heat", 100, 37)])
+@pytest.mark.parametrize("launch", ["stage", "persistent"])
+def test_fused_budgets_equal_full_pass(cuda, oracle, kind, ncol, nlayer, launch):
+    """After a step the budgets come from the per-block sums the last-stage launches leave behind (fused epilogue); after
+    an upload, from one pass over the state.  Both must agree (round-off of two summation orders), leave the padding
+    columns out, and match the oracle."""
+    make = {"coupled": w.coupled_workload, "richards": w.richards_workload, "heat": w.heat_workload}[kind]
+    wl = make(ncol=ncol, nlayer=nlayer, seed=91) if kind == "heat" else make(ncol=ncol, nlayer=nlayer, seed=91, zlim=(-0.03 * nlayer, 0.0))
+    flags = abi.LH_FLAG_STAGE_LAUNCHES if launch == "stage" else abi.LH_FLAG_PERSISTENT
+    g, o = _pair(cuda, oracle, wl, flags=flags)
+    for ctx in (g, o):
+        ctx.step(0.0, wl.dt, 3)
+    fused = g.budgets()                                  # right after the step
+    state = {f: g.get_state(f) for f in wl.fields}
+    for f, a in state.items():
+        g.set_state(f, a)                                # an upload invalidates the fused sums
+    full = g.budgets()
+    ref = o.budgets()
+    scale = np.maximum(np.abs(ref), 1e-300)
+    assert np.all(np.abs(fused - full) <= 1e-14 * scale), (fused, full)
+    assert np.all(np.abs(fused - ref) <= 1e-12 * scale), (fused, ref)
+    g.step_with(_named(cuda, abi.LH_METHOD_SSPRK22), 0.0, wl.dt, 1)     # a generic stepper falls back to the full pass
+    o.step_with(_named(oracle, abi.LH_METHOD_SSPRK22), 0.0, wl.dt, 1)
+    assert np.all(np.abs(g.budgets() - o.budgets()) <= 1e-12 * np.maximum(np.abs(o.budgets()), 1e-300))
+
+
+def _named(lib, method):
+    t = abi.lh_soil_stepper()
+    assert lib.soil_stepper_named(method, t) == abi.LH_OK
+    return t
