@@ -261,6 +261,9 @@ int32_t lh_soil_step(lh_soil_ctx* ctx, const lh_soil_stepper* stepper, double t,
  * Water and energy budgets of THIS ctx's columns: out[0] = sum ϑ_l Δz, out[1] = sum ρe_int Δz
  * (deterministic fixed-tree reduction).  New in this build.                     */
 int32_t lh_soil_budgets(lh_soil_ctx* ctx, double out[2]);
+/* Right after lh_soil_step_ssprk33 / lh_soil_stage_ssprk33(3) this costs one small reduction: the last stage has
+ * already summed, per thread block, the values it wrote.  After an upload or a generic stepper it is one pass over the
+ * state.  Both are fixed-shape trees (bitwise reproducible for a given shard).                                     */
 /* Column-integrated boundary fluxes of the last rhs/stage call are not stored; conservation
  * tests use budgets before/after a step.                                                    */
 
