@@ -1,6 +1,6 @@
-// lh_stage_kernel.cuh — the fused soil RHS (+ SSPRK33 stage) kernel template and its launcher.
-// Included by one translation unit per model (lh_kernels_m0/m1/m2.cu) so the 3 x 4 x 8 kernel variants
-// compile in parallel.  See lh_kernels.cu for the design notes.
+// lh_stage_kernel.cuh — the fused soil RHS (+ Runge-Kutta stage) kernel template, the persistent SSPRK33 kernel and
+// their launchers.  Included by one translation unit per model (lh_kernels_m0/m1/m2.cu) so that the variants
+// (3 models x 7 stage kinds x 12 flag combinations) compile in parallel.  See lh_kernels.cu for the design notes.
 #pragma once
 
 #include "lh_kernels.cuh"
@@ -210,7 +210,7 @@ __device__ __forceinline__ void lh_stage_body_impl(const LhKernelArgs& A, const 
     // Input pipeline.  The raw values of cell i travel global -> shared with cp.async (LDGSTS): no
     // registers are held while the copy is in flight (a register software pipeline was tried: ptxas
     // sinks such loads down to the next possibly-aliasing store and spills them; prefetch.global.L1
-    // was tried too and only reaches L2 on this part — 3 % L1 hit rate, profiles/r01_d_*).
+    // was tried too and only reaches L2 on this part — 3 % L1 hit rate in the ncu capture of that build).
     // One field of one layer is a 256-byte row (32 columns); every lane copies 16 bytes, so ONE
     // instruction moves two rows (lanes 0-15 the first, lanes 16-31 the second) and the copy can take
     // the L1-bypassing .cg path: with 8-byte .ca copies the ~60 KB in flight per SM had to be resident
