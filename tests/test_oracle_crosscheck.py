@@ -80,3 +80,45 @@ def test_ssprk33_step_matches(oracle):
     for f in range(3):
         got = ctx.get_state(f)[0]
         assert np.max(np.abs(got - u[f])) <= 8 * EPS * max(np.max(np.abs(u[f])), 1e-300)
+
+
+@pytest.mark.parametrize("method", [abi.LH_METHOD_EULER, abi.LH_METHOD_SSPRK22, abi.LH_METHOD_SSPRK33, abi.LH_METHOD_SSPRK43,
+                                    abi.LH_METHOD_CK2N54])
+def test_generic_steppers_match_python(oracle, method):
+    """lho_soil_step (two-register Shu-Osher and Williamson 2N recurrences) against the same recurrences written out in
+    Python over np_soil's right-hand side, per-stage boundary values included."""
+    wl = w.coupled_workload(ncol=1, nlayer=14, seed=19, top=(D, 288.0, D, 0.4), bottom=(F, 0.0, FD, 0.0))
+    tab = abi.lh_soil_stepper()
+    assert oracle.soil_stepper_named(method, tab) == abi.LH_OK
+    ns, nsteps = tab.nstages, 3
+    rng = np.random.default_rng(8)
+    base = np.array([wl.top[1], wl.top[3], wl.bottom[1], wl.bottom[3]])
+    bct = base * (1.0 + 1e-3 * rng.standard_normal((nsteps, ns, 4)))
+    ctx = lh.SoilContext(oracle, wl.config())
+    wl.upload(ctx)
+    ctx.step_with(tab, 0.0, wl.dt, nsteps, bct)
+    p = wl.params
+
+    def rhs(u, bcv):
+        dth, dti, dre, _, _ = np_soil.column_rhs(p, wl.model, wl.zmin, wl.zmax, (wl.top[0], wl.top[2]), (wl.bottom[0], wl.bottom[2]),
+                                                 list(bcv), list(u[0]), list(u[1]), list(u[2]), [288.0] * wl.nlayer)
+        return [dth, dti, dre]
+
+    u = [wl.fields[k][0].copy() for k in range(3)]
+    dt = wl.dt
+    for s in range(nsteps):
+        if tab.kind == abi.LH_STEPPER_SHU_OSHER:
+            u0, v = [x.copy() for x in u], [x.copy() for x in u]
+            for i in range(ns):
+                k = rhs(v, bct[s, i])
+                v = [tab.a[i] * a0 + tab.b[i] * vi + (tab.g[i] * dt) * ki for a0, vi, ki in zip(u0, v, k)]
+            u = v
+        else:
+            r = [np.zeros_like(x) for x in u]
+            for i in range(ns):
+                k = rhs(u, bct[s, i])
+                r = [dt * ki if i == 0 else tab.a[i] * ri + dt * ki for ri, ki in zip(r, k)]
+                u = [ui + tab.b[i] * ri for ui, ri in zip(u, r)]
+    for f in range(3):
+        got = ctx.get_state(f)[0]
+        assert np.max(np.abs(got - u[f])) <= 16 * EPS * max(np.max(np.abs(u[f])), 1e-300), (method, f)
