@@ -158,18 +158,20 @@ __device__ __forceinline__ void lh_water_closures(const P& p, const double* __re
         Kr_unsat = (S_K * rS) * (t * t);                                     // :277
         if (NEED_LOG) L_K = lh_log2<false>(mc, tab, S_K);   // Kersten exponent only; a NaN state already poisons psi and K
     } else {
-        // ---- general n: pressure head (:229-242) and the shared logs
-        const double L_eff = lh_log2(mc, tab, S_eff);
+        // ---- general n: pressure head (:229-242) and the shared logs.  The logs run unchecked (no NaN flag for a
+        // negative argument): S_eff > 0 always; 1 - y < 0 only for S_eff > 1, where both selects below discard the
+        // unsaturated expressions; and a NaN state still reaches psi and K through their explicit factors of S.
+        const double L_eff = lh_log2<false>(mc, tab, S_eff);
         const double u = L_eff * p.vg_inv_m;
         const LhExpParts ey = lh_exp2_parts(mc, tab, u);                     // y = S^(1/m) = s (1 + p)
         const double w = lh_fma(-ey.s, ey.p, 1.0 - ey.s);                    // 1 - y; its zero is +0
-        const double a = lh_log2(mc, tab, w);
+        const double a = lh_log2<false>(mc, tab, w);
         // ---- hydraulic conductivity (:269-282)
         double a_K = a;
         L_K = L_eff;
         if (icy) {                       // S differs from S_eff only when ice is present
-            L_K = lh_log2(mc, tab, S_K);
-            a_K = lh_log2(mc, tab, lh_one_minus_exp2(mc, tab, L_K * p.vg_inv_m));
+            L_K = lh_log2<false>(mc, tab, S_K);
+            a_K = lh_log2<false>(mc, tab, lh_one_minus_exp2(mc, tab, L_K * p.vg_inv_m));
         }
         const LhExpParts eW = lh_exp2_parts(mc, tab, p.vg_m * a_K);          // W = (1 - y)^m
         const double q = lh_fma(eW.s, eW.p, eW.s - 1.0);                     // W - 1
@@ -219,7 +221,7 @@ __device__ __forceinline__ double lh_thermal_conductivity(const P& p, const doub
     const double S_r = tw * p.inv_nu;                                        // relative_saturation :139-142
     double Lr;
     if (REUSE && !ICE && !GEN) Lr = unsat ? logS : p.log2_Sr_sat;
-    else Lr = lh_log2(mc, tab, S_r);
+    else Lr = lh_log2(mc, tab, S_r);             // checked: a negative water content must not yield a finite kappa
     double K_e;
     if (!ICE || ti < LH_EPS) {                                               // kersten_number :163-169
         const double e = lh_exp2(mc, tab, p.neg_b_l2e * S_r);                // exp(-b S_r)
