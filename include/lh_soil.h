@@ -152,7 +152,7 @@ typedef struct lh_soil_config {
 #define LH_FLAG_GENERAL_VG   2 /* never use the van Genuchten n == 2 (m == 1/2) square-root
                                   specialisation: always evaluate the general-n log/exp form   */
 /* lh_soil_step_ssprk33 launch strategy.  Default: one launch per stage (chained with programmatic dependent
- * launch), except for small, launch-bound grids (<= ~3 waves of resident blocks) where ONE persistent launch
+ * launch), except for small, launch-bound grids (<= ~1.5 waves of resident blocks) where ONE persistent launch
  * runs all 3 nsteps stages, every block keeping its columns (L2-resident stage registers, no launch gaps).
  * Results are bit-identical either way.                                                          */
 #define LH_FLAG_STAGE_LAUNCHES 4 /* always one launch per stage                                  */

@@ -713,7 +713,7 @@ int32_t lh_soil_stage_ssprk33(lh_soil_ctx* c, int32_t stage, double dt)
     return st;
 }
 
-// The persistent launch pays for grids of at most ~3 waves (<= ~2000 blocks: small domains, launch-bound): measured
+// The persistent launch pays for grids of at most ~1.5 waves (small domains, launch-bound): measured
 // +25..40 % there (profiles/r01_s_persistent_vs_stage.log).  From ~5 waves on it ties with, then loses to, the
 // per-stage launches: it executes ~10 % more instructions per stage (its one run-time-stage body reads u^n in
 // every stage) and the kernel is issue-bound.
@@ -721,7 +721,7 @@ static bool use_persistent(const lh_soil_ctx* c)
 {
     if (c->cfg.flags & LH_FLAG_STAGE_LAUNCHES) return false;
     if (c->cfg.flags & LH_FLAG_PERSISTENT) return true;
-    return c->shape.waves <= 3.0;
+    return c->shape.waves <= 1.5;
 }
 
 int32_t lh_soil_step_ssprk33(lh_soil_ctx* c, double t, double dt, int64_t nsteps, const double* bc_table)
