@@ -76,3 +76,21 @@ def test_persistent_check_finite(cuda):
     wl.upload(ctx)
     with pytest.raises(lh.NonFiniteStateError):
         ctx.step(0.0, wl.dt, 3)
+
+
+@pytest.mark.parametrize("flag", [abi.LH_FLAG_STAGE_LAUNCHES, abi.LH_FLAG_PERSISTENT])
+def test_zero_steps_is_a_no_op(cuda, flag):
+    wl = w.coupled_workload(ncol=40, nlayer=12, seed=74)
+    ctx = lh.SoilContext(cuda, wl.config(flags=flag))
+    wl.upload(ctx)
+    before = {f: ctx.get_state(f) for f in wl.fields}
+    b0 = ctx.budgets()
+    ctx.step(0.0, wl.dt, 0)
+    ctx.step(0.0, wl.dt, 0, np.zeros((0, 3, 4)))
+    assert ctx.last_step_timing()[1] == 0
+    for f, a in before.items():
+        assert np.array_equal(ctx.get_state(f), a)
+    assert np.array_equal(ctx.budgets(), b0)
+    with pytest.raises(lh._abi.SoilError):
+        ctx.lib.soil_step_ssprk33  # symbol exists
+        ctx._check(ctx.lib.soil_step_ssprk33(ctx._h, 0.0, wl.dt, -1, None))
