@@ -88,6 +88,89 @@ def cases():
     return out
 
 
+# Coefficient tables of the explicit low-storage steppers, typed here from the literature (NOT read from the libraries
+# under test): Shu & Osher 1988 (SSPRK22, SSPRK33), Spiteri & Ruuth 2002 (SSPRK43), Carpenter & Kennedy 1994 (2N54).
+STEPPERS = {
+    "Euler": ("shu_osher", [0.0], [1.0], [1.0]),
+    "SSPRK22": ("shu_osher", [0.0, 0.5], [1.0, 0.5], [1.0, 0.5]),
+    "SSPRK33": ("shu_osher", [0.0, 0.75, 1.0 / 3.0], [1.0, 0.25, 2.0 / 3.0], [1.0, 0.25, 2.0 / 3.0]),
+    "SSPRK43": ("shu_osher", [0.0, 0.0, 2.0 / 3.0, 0.0], [1.0, 1.0, 1.0 / 3.0, 1.0], [0.5, 0.5, 1.0 / 6.0, 0.5]),
+    "CarpenterKennedy2N54": ("2n",
+                             [0.0, -567301805773.0 / 1357537059087.0, -2404267990393.0 / 2016746695238.0,
+                              -3550918686646.0 / 2091501179385.0, -1275806237668.0 / 842570457699.0],
+                             [1432997174477.0 / 9575080441755.0, 5161836677717.0 / 13612068292357.0,
+                              1720146321549.0 / 2090206949498.0, 3134564353537.0 / 4481467310338.0,
+                              2277821191437.0 / 14882151754819.0], None),
+}
+
+
+def stepper_cases():
+    """State of one coupled column after 2 steps of every stepper (recurrences written out here over np_soil's RHS)."""
+    wl = w.coupled_workload(ncol=1, nlayer=16, seed=111)
+    bcv = [wl.top[1], wl.top[3], wl.bottom[1], wl.bottom[3]]
+    top, bottom = (wl.top[0], wl.top[2]), (wl.bottom[0], wl.bottom[2])
+
+    def rhs(u):
+        dth, dti, dre, _, _ = np_soil.column_rhs(wl.params, wl.model, wl.zmin, wl.zmax, top, bottom, bcv,
+                                                 list(u[0]), list(u[1]), list(u[2]), [288.0] * wl.nlayer)
+        return [dth, dti, dre]
+
+    out = {"nlayer": wl.nlayer, "zmin": wl.zmin, "zmax": wl.zmax, "dt": wl.dt, "nsteps": 2, "params": params_dict(wl.params),
+           "top": list(wl.top), "bottom": list(wl.bottom), "theta_l": wl.fields[0][0].tolist(), "theta_i": wl.fields[1][0].tolist(),
+           "rho_e_int": wl.fields[2][0].tolist(), "methods": {}}
+    for name, (kind, a, b, g) in STEPPERS.items():
+        u = [wl.fields[k][0].copy() for k in range(3)]
+        for _ in range(2):
+            if kind == "shu_osher":
+                u0, v = [x.copy() for x in u], [x.copy() for x in u]
+                for i in range(len(a)):
+                    k = rhs(v)
+                    v = [a[i] * x0 + b[i] * vi + (g[i] * wl.dt) * ki for x0, vi, ki in zip(u0, v, k)]
+                u = v
+            else:
+                r = [np.zeros_like(x) for x in u]
+                for i in range(len(a)):
+                    k = rhs(u)
+                    r = [wl.dt * ki if i == 0 else a[i] * ri + wl.dt * ki for ri, ki in zip(r, k)]
+                    u = [ui + b[i] * ri for ui, ri in zip(u, r)]
+        out["methods"][name] = {"theta_l_after": np.asarray(u[0]).tolist(), "rho_e_int_after": np.asarray(u[2]).tolist()}
+    return out
+
+
+def column_param_case():
+    """Three Richards columns with different (nu, theta_r, n, alpha, Ksat): each is an independent np_soil column."""
+    wl = w.richards_workload(ncol=3, nlayer=20, seed=112)
+    cp = {"nu": [0.287, 0.35, 0.42], "theta_r": [0.075, 0.02, 0.0], "vg_n": [3.96, 1.8, 2.4], "vg_alpha": [2.7, 1.1, 3.6],
+          "Ksat": [34 / 3600 / 100, 2.0e-6, 5.0e-5]}
+    p0 = wl.params
+    S = (wl.fields[0] - p0.theta_r) / (p0.nu - p0.theta_r)
+    rec = {"nlayer": wl.nlayer, "zmin": wl.zmin, "zmax": wl.zmax, "dt": wl.dt, "nsteps": NSTEPS, "params": params_dict(p0),
+           "top": list(wl.top), "bottom": list(wl.bottom), "column_params": cp, "columns": []}
+    bcv = [wl.top[1], wl.top[3], wl.bottom[1], wl.bottom[3]]
+    top, bottom = (wl.top[0], wl.top[2]), (wl.bottom[0], wl.bottom[2])
+    import copy
+    for c in range(3):
+        p = copy.copy(p0)
+        p.nu, p.theta_r, p.vg_n, p.vg_alpha, p.Ksat = (cp[k][c] for k in ("nu", "theta_r", "vg_n", "vg_alpha", "Ksat"))
+        p.vg_m = 1.0 - 1.0 / p.vg_n
+        th = p.theta_r + S[c] * (p.nu - p.theta_r)
+        ti, re = np.zeros(wl.nlayer), np.zeros(wl.nlayer)
+
+        def rhs(u, stage, p=p):
+            dth, dti, dre, _, _ = np_soil.column_rhs(p, wl.model, wl.zmin, wl.zmax, top, bottom, bcv,
+                                                     list(u[0]), list(u[1]), list(u[2]), [288.0] * wl.nlayer)
+            return dth, dti, dre
+
+        dth, _, _, Fw, _ = np_soil.column_rhs(p, wl.model, wl.zmin, wl.zmax, top, bottom, bcv, list(th), list(ti), list(re),
+                                              [288.0] * wl.nlayer)
+        u = (th.copy(), ti.copy(), re.copy())
+        for _ in range(NSTEPS):
+            u = np_soil.ssprk33_step(rhs, u, wl.dt)
+        rec["columns"].append({"theta_l": th.tolist(), "d_theta_l": dth.tolist(), "Fw": Fw.tolist(),
+                               "theta_l_after": np.asarray(u[0]).tolist()})
+    return rec
+
+
 # The reference's own expectations for this path, typed from its tests (paths relative to /root/reference).
 KNOWN_ANSWERS = [
     {"what": "effective_saturation(0.5, [0.25, 0.5, 0.75], 0.0)", "ref": "test/SoilModel/test_water_parameterizations.jl:10-13",
@@ -114,6 +197,8 @@ def main():
         "generator": "oracle/np_soil.py (pure-Python restatement of the reference), numpy " + np.__version__,
         "known_answers": KNOWN_ANSWERS,
         "cases": cases(),
+        "steppers": stepper_cases(),
+        "column_params": column_param_case(),
     }
     path = os.path.join(HERE, "soil_golden.json")
     with open(path, "w") as f:

@@ -179,3 +179,60 @@ def test_known_rhs_cuda(cuda):
 @pytest.mark.parametrize("name", sorted(CASES))
 def test_cuda_reproduces_golden(cuda, name):
     _check_case(cuda, CASES[name], 1e-12, 1e-10)
+
+
+# ---- steppers and per-column parameters (fixtures generated with literature coefficient tables / per-column np_soil) ----
+_METHOD_IDS = {"Euler": abi.LH_METHOD_EULER, "SSPRK22": abi.LH_METHOD_SSPRK22, "SSPRK33": abi.LH_METHOD_SSPRK33,
+               "SSPRK43": abi.LH_METHOD_SSPRK43, "CarpenterKennedy2N54": abi.LH_METHOD_CK2N54}
+
+
+def _check_steppers(lib, tol):
+    rec = GOLDEN["steppers"]
+    fields = {0: np.array([rec["theta_l"]]), 1: np.array([rec["theta_i"]]), 2: np.array([rec["rho_e_int"]])}
+    wl = w.Workload(model=abi.LH_MODEL_COUPLED, ncol=1, nlayer=rec["nlayer"], zmin=rec["zmin"], zmax=rec["zmax"], params=_params(rec),
+                    top=tuple(rec["top"]), bottom=tuple(rec["bottom"]), dt=rec["dt"], fields=fields)
+    for name, ref in rec["methods"].items():
+        tab = abi.lh_soil_stepper()
+        assert lib.soil_stepper_named(_METHOD_IDS[name], tab) == abi.LH_OK
+        ctx = lh.SoilContext(lib, wl.config())
+        wl.upload(ctx)
+        ctx.step_with(tab, 0.0, rec["dt"], rec["nsteps"])
+        for fid, key in ((0, "theta_l_after"), (2, "rho_e_int_after")):
+            r = np.array(ref[key])
+            err = np.max(np.abs(ctx.get_state(fid)[0] - r)) / np.max(np.abs(r))
+            assert err <= tol, (name, fid, err)
+        ctx.close()
+
+
+def _check_column_params(lib, tend_tol, state_tol):
+    rec = GOLDEN["column_params"]
+    cols = rec["columns"]
+    n = rec["nlayer"]
+    fields = {0: np.array([c["theta_l"] for c in cols]), 1: np.zeros((len(cols), n))}
+    wl = w.Workload(model=abi.LH_MODEL_RICHARDS, ncol=len(cols), nlayer=n, zmin=rec["zmin"], zmax=rec["zmax"], params=_params(rec),
+                    top=tuple(rec["top"]), bottom=tuple(rec["bottom"]), dt=rec["dt"], fields=fields)
+    ctx = lh.SoilContext(lib, wl.config())
+    ctx.set_column_params(**{k: np.array(v) for k, v in rec["column_params"].items()})
+    wl.upload(ctx)
+    ctx.rhs(0.0)
+    got = ctx.get_tendency(0)
+    dz = (rec["zmax"] - rec["zmin"]) / n
+    for c, col in enumerate(cols):
+        r = np.array(col["d_theta_l"])
+        scale = max(np.max(np.abs(r)), np.max(np.abs(col["Fw"])) / dz)
+        assert np.max(np.abs(got[c] - r)) <= tend_tol * scale, c
+    ctx.step(0.0, rec["dt"], rec["nsteps"])
+    ref = np.array([c["theta_l_after"] for c in cols])
+    assert np.max(np.abs(ctx.get_state(0) - ref)) <= state_tol * np.max(np.abs(ref))
+    ctx.close()
+
+
+def test_oracle_reproduces_golden_steppers_and_column_params(oracle):
+    _check_steppers(oracle, 64 * EPS)
+    _check_column_params(oracle, 8 * EPS, 64 * EPS)
+
+
+@pytest.mark.gpu
+def test_cuda_reproduces_golden_steppers_and_column_params(cuda):
+    _check_steppers(cuda, 1e-10)
+    _check_column_params(cuda, 1e-12, 1e-10)
