@@ -55,13 +55,22 @@ struct LhPhys {
     double kappa_dry;
     double k_unfrozen_minus_dry;       // kappa_sat_unfrozen - kappa_dry
     double log2_Sr_sat;                // log2(nu * (1/nu)): relative saturation of a saturated, ice-free cell
+    double pow_p1_Sr_sat;              // (nu * (1/nu))^kersten_p1
+    LhPowCoef pw[3];                   // fixed-exponent powers (lh_math.cuh): LHPW_INVM x^(1/m), LHPW_M x^m, LHPW_P1 x^kersten_p1
     int32_t visc_on, imp_on;
     int32_t om_zero;                   // nu_ss_om == 0: outer Kersten exponents are exactly 1
     int32_t pad_;
 };
 
+enum { LHPW_INVM, LHPW_M, LHPW_P1, LHPW_COUNT };
+// Shared-memory table block of every kernel: the exp2 / log2 tables, then one table per fixed exponent.
+#define LH_TAB_ALL (LH_TAB_DOUBLES + LHPW_COUNT * LH_POW_DOUBLES)
+
 // The uniform parameter block of a launch: physics + the elementary-function coefficients and tables.
+// POW: the exponents 1/m, m and the Kersten exponent are per-model constants, so x^c is one table-driven evaluation
+// (lh_pow_fixed) instead of exp2(c log2 x).
 struct LhDevParams : LhPhys {
+    static constexpr bool POW = true;
     double mc[LHC_COUNT];              // lh_math.cuh
 };
 
@@ -69,6 +78,7 @@ struct LhDevParams : LhPhys {
 // (lh_soil_set_column_params): a per-thread copy whose column-dependent members were overwritten; the members
 // that stay uniform still come from the parameter block (constant propagation through the copy).
 struct LhLaneParams : LhPhys {
+    static constexpr bool POW = false; // per-column van Genuchten n: the exponents differ from lane to lane
     const double* mc;
 };
 
@@ -76,11 +86,14 @@ struct LhLaneParams : LhPhys {
 enum { LHCP_NU, LHCP_THETA_R, LHCP_THETA_R_EPS, LHCP_INV_NU_THR, LHCP_NU_THR, LHCP_VG_M, LHCP_VG_INV_M, LHCP_VG_INV_N,
        LHCP_NEG_INV_ALPHA, LHCP_KSAT, LHCP_INV_NU, LHCP_KAPPA_DRY, LHCP_COUNT };
 
-// Copies the exp2 / log2 tables from the parameter block to shared memory (LH_TAB_DOUBLES doubles, 16-byte
-// aligned destination); the caller must __syncthreads().
-__device__ __forceinline__ void lh_stage_tables(const LhDevParams& p, double* tab_smem, int linear_tid, int nthreads)
+// Copies the exp2 / log2 tables from the parameter block, and the fixed-exponent power tables from `pow_tab`
+// (LHPW_COUNT * LH_POW_DOUBLES doubles in global memory, written once by lh_soil_create), to shared memory
+// (LH_TAB_ALL doubles, 16-byte aligned destination); the caller must __syncthreads().
+__device__ __forceinline__ void lh_stage_tables(const LhDevParams& p, const double* __restrict__ pow_tab, double* tab_smem,
+                                                int linear_tid, int nthreads)
 {
     for (int k = linear_tid; k < LH_TAB_DOUBLES; k += nthreads) tab_smem[k] = p.mc[LHC_TAB0 + k];
+    if (pow_tab) for (int k = linear_tid; k < LHPW_COUNT * LH_POW_DOUBLES; k += nthreads) tab_smem[LH_TAB_DOUBLES + k] = pow_tab[k];
 }
 
 struct LhCell {
@@ -122,7 +135,7 @@ struct LhCell {
 template <bool ICE, bool GEN, bool VG2, bool NEED_LOG, bool THR0 = false, class P = LhDevParams>
 __device__ __forceinline__ void lh_water_closures(const P& p, const double* __restrict__ tab,
                                                   double th, double ti, double T,
-                                                  double& K_out, double& psi_out, double& logS_K)
+                                                  double& K_out, double& psi_out, double& logS_K, LhPowArg& argS_K)
 {
     const double* __restrict__ mc = p.mc;
     const double nu_eff = ICE ? p.nu - ti : p.nu;
@@ -156,7 +169,40 @@ __device__ __forceinline__ void lh_water_closures(const P& p, const double* __re
         psi_unsat = p.neg_inv_alpha * (sw * inv_S_eff);                      // :196-200
         const double t = (S_K * S_K) * lh_rcp(1.0 + swK);                    // 1 - (1 - S^(1/m))^m
         Kr_unsat = (S_K * rS) * (t * t);                                     // :277
-        if (NEED_LOG) L_K = lh_log2<false>(mc, tab, S_K);   // Kersten exponent only; a NaN state already poisons psi and K
+        if (NEED_LOG) {                                      // Kersten exponent only; a NaN state already poisons psi and K
+            if constexpr (P::POW) argS_K = lh_pow_arg(tab, S_K);
+            else L_K = lh_log2<false>(mc, tab, S_K);
+        }
+    } else if constexpr (P::POW) {
+        // ---- general n, exponents fixed per model: y = S^(1/m), W = (1 - y)^m are fixed-exponent powers.  Nothing is
+        // checked: S_eff > 0 always; 1 - y <= 0 only for S_eff >= 1, where both selects below discard the unsaturated
+        // expressions (lh_pow_* return finite garbage there); a NaN state reaches psi and K through their factors of S.
+        const double* __restrict__ pt_invm = tab + LH_TAB_DOUBLES + LHPW_INVM * LH_POW_DOUBLES;
+        const double* __restrict__ pt_m = tab + LH_TAB_DOUBLES + LHPW_M * LH_POW_DOUBLES;
+        const LhPowArg aS = lh_pow_arg(tab, S_eff);
+        const LhExpParts ey = lh_pow_parts(p.pw[LHPW_INVM], pt_invm, aS);    // y = S^(1/m) = s (1 + p)
+        const double w = lh_fma(-ey.s, ey.p, 1.0 - ey.s);                    // 1 - y (exactly -p when S is within 2^-9 of 1)
+        const LhPowArg aw = lh_pow_arg(tab, w);
+        const double y = lh_fma(ey.s, ey.p, ey.s);
+        argS_K = aS;
+        if (!icy) {
+            const LhExpParts eW = lh_pow_parts(p.pw[LHPW_M], pt_m, aw);      // W = (1 - y)^m
+            const double q = lh_fma(eW.s, eW.p, eW.s - 1.0);                 // W - 1 (exactly p for dry cells: y < 2^-9)
+            Kr_unsat = (S_K * lh_rsqrt(S_K)) * (q * q);                      // :277; sqrt(S) = S rsqrt(S): S >= eps > 0 here
+            // Mualem's m = 1 - 1/n (what the reference constructor stores; lh_soil_create rejects anything else):
+            // 1/n = 1 - m and y^m = S, so ((1 - y)/y)^(1/n) = (w/y) (y/w)^m = w S / (y W): a reciprocal, no third power.
+            const double W = lh_fma(eW.s, eW.p, eW.s);
+            psi_unsat = p.neg_inv_alpha * ((w * S_eff) * lh_rcp(y * W));     // :196-200
+        } else {                           // S (porosity nu) differs from S_eff (nu - theta_i) only when ice is present
+            const double W = lh_pow_fixed(p.pw[LHPW_M], pt_m, aw);
+            psi_unsat = p.neg_inv_alpha * ((w * S_eff) * lh_rcp(y * W));
+            argS_K = lh_pow_arg(tab, S_K);
+            const LhExpParts eyK = lh_pow_parts(p.pw[LHPW_INVM], pt_invm, argS_K);
+            const LhPowArg awK = lh_pow_arg(tab, lh_fma(-eyK.s, eyK.p, 1.0 - eyK.s));
+            const LhExpParts eW = lh_pow_parts(p.pw[LHPW_M], pt_m, awK);
+            const double q = lh_fma(eW.s, eW.p, eW.s - 1.0);
+            Kr_unsat = (S_K * lh_rsqrt(S_K)) * (q * q);
+        }
     } else {
         // ---- general n: pressure head (:229-242) and the shared logs.  The logs run unchecked (no NaN flag for a
         // negative argument): S_eff > 0 always; 1 - y < 0 only for S_eff > 1, where both selects below discard the
@@ -214,14 +260,17 @@ __device__ __forceinline__ void lh_water_closures(const P& p, const double* __re
 // ---------------------------------------------------------------------------------------------
 template <bool ICE, bool GEN, bool REUSE, class P = LhDevParams>
 __device__ __forceinline__ double lh_thermal_conductivity(const P& p, const double* __restrict__ tab,
-                                                          double tl, double ti, bool unsat, double logS)
+                                                          double tl, double ti, bool unsat, double logS, const LhPowArg& argS)
 {
     const double* __restrict__ mc = p.mc;
     const double tw = ICE ? tl + ti : tl;
     const double S_r = tw * p.inv_nu;                                        // relative_saturation :139-142
-    double Lr;
-    if (REUSE && !ICE && !GEN) Lr = unsat ? logS : p.log2_Sr_sat;
-    else Lr = lh_log2(mc, tab, S_r);             // checked: a negative water content must not yield a finite kappa
+    constexpr bool REUSED = REUSE && !ICE && !GEN;
+    double Lr = 0.0;
+    if constexpr (!P::POW) {
+        if (REUSED) Lr = unsat ? logS : p.log2_Sr_sat;
+        else Lr = lh_log2(mc, tab, S_r);         // checked: a negative water content must not yield a finite kappa
+    }
     double K_e;
     if (!ICE || ti < LH_EPS) {                                               // kersten_number :163-169
         const double e = lh_exp2(mc, tab, p.neg_b_l2e * S_r);                // exp(-b S_r)
@@ -230,9 +279,30 @@ __device__ __forceinline__ double lh_thermal_conductivity(const P& p, const doub
         const double c = (1.0 - S_r) * 0.5;
         double base = E3 - c * c * c;
         if (GEN && !p.om_zero) base = lh_exp2(mc, tab, p.kersten_p2 * lh_log2(mc, tab, base));
-        K_e = lh_exp2(mc, tab, p.kersten_p1 * Lr) * base;
+        if constexpr (P::POW) {
+            // S_r^p1 with the per-model exponent table; REUSED: the water closure already reduced S == S_r
+            const double* __restrict__ pt = tab + LH_TAB_DOUBLES + LHPW_P1 * LH_POW_DOUBLES;
+            double Sp;
+            if (REUSED) {
+                Sp = lh_pow_fixed(p.pw[LHPW_P1], pt, argS);
+                Sp = unsat ? Sp : p.pow_p1_Sr_sat;
+            } else {
+                Sp = lh_pow_fixed(p.pw[LHPW_P1], pt, lh_pow_arg(tab, S_r));
+                // a negative water content (or a NaN) must not yield a finite kappa
+                Sp = lh_mk(lh_pow_bad(S_r) ? 0x7ff80000 : lh_hi(Sp), lh_lo(Sp));
+            }
+            K_e = Sp * base;
+        } else {
+            K_e = lh_exp2(mc, tab, p.kersten_p1 * Lr) * base;
+        }
     } else {                                                                 // :171
-        K_e = (!GEN || p.om_zero) ? S_r : lh_exp2(mc, tab, p.kersten_p3 * Lr);
+        if constexpr (P::POW) {
+            K_e = S_r;
+            if (GEN && !p.om_zero) K_e = lh_exp2(mc, tab, p.kersten_p3 * lh_log2(mc, tab, S_r));
+            else K_e = lh_mk(lh_pow_bad(S_r) ? 0x7ff80000 : lh_hi(K_e), lh_lo(K_e));
+        } else {
+            K_e = (!GEN || p.om_zero) ? S_r : lh_exp2(mc, tab, p.kersten_p3 * Lr);
+        }
     }
     if (!ICE) {
         // kappa_sat = kappa_unfrozen^1 * kappa_frozen^0 exactly (:114-128), so
@@ -279,10 +349,12 @@ __device__ __forceinline__ LhCell lh_cell_closures(const P& p, const double* __r
         c.T = p.T_0 + c.dT;
     }
     double logS = 0.0;
+    LhPowArg argS;
+    argS.t = 0.0; argS.j = 0; argS.be = 0;
     // the coupled !GEN variants are only launched when theta_r == 0 (update_kernel_flags)
-    if (MODEL != 1) lh_water_closures<ICE, GEN, VG2, REUSE, (MODEL == 2 && !GEN)>(p, tab, th, ti, c.T, c.K, c.psi, logS);
-    if (MODEL == 1) c.kappa = lh_thermal_conductivity<ICE, GEN, false>(p, tab, tl, ti, unsat, 0.0);
-    if (MODEL == 2) c.kappa = lh_thermal_conductivity<ICE, GEN, true>(p, tab, tl, ti, unsat, logS);
+    if (MODEL != 1) lh_water_closures<ICE, GEN, VG2, REUSE, (MODEL == 2 && !GEN)>(p, tab, th, ti, c.T, c.K, c.psi, logS, argS);
+    if (MODEL == 1) c.kappa = lh_thermal_conductivity<ICE, GEN, false>(p, tab, tl, ti, unsat, 0.0, argS);
+    if (MODEL == 2) c.kappa = lh_thermal_conductivity<ICE, GEN, true>(p, tab, tl, ti, unsat, logS, argS);
     return c;
 }
 
@@ -294,5 +366,7 @@ __device__ __forceinline__ double lh_face_kappa(const P& p, const double* __rest
     const double nu_eff = ICE ? p.nu - ti : p.nu;
     const bool unsat = th < nu_eff;
     const double tl = unsat ? th : nu_eff;
-    return lh_thermal_conductivity<ICE, GEN, false>(p, tab, tl, ti, unsat, 0.0);
+    LhPowArg none;
+    none.t = 0.0; none.j = 0; none.be = 0;
+    return lh_thermal_conductivity<ICE, GEN, false>(p, tab, tl, ti, unsat, 0.0, none);
 }

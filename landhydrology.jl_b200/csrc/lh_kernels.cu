@@ -51,8 +51,8 @@ LhLaunchShape lh_choose_shape(int model, int64_t ncol_pad, int32_t nlayer, int s
     static const int cand20[] = {1, 2, 4, 5, 10, 20}, cand16[] = {1, 2, 4, 8, 16};
     const int* cand = het ? cand16 : cand20;
     const int ncand = het ? 5 : 6;
-    int min_chunk = LH_MIN_CHUNK;
-    if (const char* e = getenv("LH_MIN_CHUNK")) min_chunk = atoi(e) > 0 ? atoi(e) : min_chunk;   // tuning knob
+    // tuning knob, read ONCE per process (not on every call of the product path)
+    static const int min_chunk = [] { const char* e = getenv("LH_MIN_CHUNK"); const int v = e ? atoi(e) : 0; return v > 0 ? v : LH_MIN_CHUNK; }();
     const int64_t enough_warps = (int64_t)5 * sm_count * budget / 2;
     int k = 0;
     while (k + 1 < ncand && groups * cand[k] < enough_warps && nlayer >= min_chunk * cand[k + 1]) ++k;
@@ -66,7 +66,7 @@ LhLaunchShape lh_choose_shape(int model, int64_t ncol_pad, int32_t nlayer, int s
     s.Lc = Lc; s.W = W; s.G = G;
     s.nblocks = (groups + G - 1) / G;
     const int nq = model == LH_MODEL_COUPLED ? 5 : 2;
-    s.smem_bytes = (LH_TAB_DOUBLES + 2 * LH_WARPS_PER_SM + (size_t)G * W * ((2 * nq + 6) * 32 + 4 * 5 * 32)) * sizeof(double);   // + cp.async input ring
+    s.smem_bytes = (LH_TAB_ALL + 2 * LH_WARPS_PER_SM + (size_t)G * W * ((2 * nq + 6) * 32 + 4 * 5 * 32)) * sizeof(double);   // + cp.async input ring
     s.warp_budget = budget;
     const int by_smem = (int)((227 * 1024) / (s.smem_bytes + 1024));
     const int by_regs = budget / (W * G);
@@ -129,44 +129,61 @@ __device__ __forceinline__ LhLaneParams lh_lane_params(const LhDevParams& p, con
     return pl;
 }
 
-template <int MODEL>
-__global__ void lh_diag_kernel(const __grid_constant__ LhDevParams pu, int which, const double* __restrict__ th,
-                               const double* __restrict__ ti, const double* __restrict__ re,
+template <int MODEL, class P>
+__device__ __forceinline__ double lh_diag_value(const P& p, const double* tab, int which, double th, double ti, double x)
+{
+    // K/ψ exist for every model; κ/T come from ρe_int when there is an energy model, otherwise from the prescribed T.
+    if (MODEL == 0) {
+        const LhCell c = lh_cell_closures<0, 3>(p, tab, th, ti, x);
+        if (which == LH_DIAG_KAPPA) {
+            const double nu_eff = p.nu - ti;
+            const double tl = th < nu_eff ? th : nu_eff;
+            LhPowArg none;
+            none.t = 0.0; none.j = 0; none.be = 0;
+            return lh_thermal_conductivity<true, true, false>(p, tab, tl, ti, th < nu_eff, 0.0, none);
+        }
+        return which == LH_DIAG_K ? c.K : which == LH_DIAG_PSI ? c.psi : c.T;
+    }
+    const LhCell c = lh_cell_closures<2, 3>(p, tab, th, ti, x);
+    return which == LH_DIAG_K ? c.K : which == LH_DIAG_PSI ? c.psi : which == LH_DIAG_KAPPA ? c.kappa : c.T;
+}
+
+// HET: per-column parameters (the per-lane view, general log2/exp2 closures); otherwise the uniform parameter block and
+// the fixed-exponent power tables, exactly what the stage kernels of a homogeneous soil evaluate.
+template <int MODEL, bool HET>
+__global__ void lh_diag_kernel(const __grid_constant__ LhDevParams pu, const double* __restrict__ pow_tab, int which,
+                               const double* __restrict__ th, const double* __restrict__ ti, const double* __restrict__ re,
                                const double* __restrict__ T, double* __restrict__ out, int64_t n,
                                const double* __restrict__ colp, int64_t ncol_pad)
 {
-    __shared__ __align__(16) double tab[LH_TAB_DOUBLES];
-    lh_stage_tables(pu, tab, threadIdx.x, blockDim.x);
+    __shared__ __align__(16) double tab[LH_TAB_ALL];
+    lh_stage_tables(pu, pow_tab, tab, threadIdx.x, blockDim.x);
     __syncthreads();
     const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
-    const LhLaneParams p = lh_lane_params(pu, colp, i % ncol_pad, ncol_pad);
-    // K/ψ exist for every model; κ/T come from ρe_int when there is an energy model, otherwise
-    // from the prescribed T.
-    double v;
-    if (MODEL == 0) {
-        const LhCell c = lh_cell_closures<0, 3>(p, tab, th[i], ti[i], T[i]);
-        if (which == LH_DIAG_KAPPA) {
-            const double nu_eff = p.nu - ti[i];
-            const double tl = th[i] < nu_eff ? th[i] : nu_eff;
-            v = lh_thermal_conductivity<true, true, false>(p, tab, tl, ti[i], th[i] < nu_eff, 0.0);
-        } else v = which == LH_DIAG_K ? c.K : which == LH_DIAG_PSI ? c.psi : c.T;
+    const double x = MODEL == 0 ? T[i] : re[i];
+    if constexpr (HET) {
+        const LhLaneParams p = lh_lane_params(pu, colp, i % ncol_pad, ncol_pad);
+        out[i] = lh_diag_value<MODEL>(p, tab, which, th[i], ti[i], x);
     } else {
-        const LhCell c = lh_cell_closures<2, 3>(p, tab, th[i], ti[i], re[i]);
-        v = which == LH_DIAG_K ? c.K : which == LH_DIAG_PSI ? c.psi : which == LH_DIAG_KAPPA ? c.kappa : c.T;
+        out[i] = lh_diag_value<MODEL>(pu, tab, which, th[i], ti[i], x);
     }
-    out[i] = v;
 }
 }  // namespace
 
-cudaError_t lh_launch_diagnostic(int model, int which, const LhDevParams& p, const double* th,
+cudaError_t lh_launch_diagnostic(int model, int which, const LhDevParams& p, const double* pow_tab, const double* th,
                                  const double* ti, const double* re, const double* T, double* out,
                                  int64_t n, const double* colp, int64_t ncol_pad, cudaStream_t stream)
 {
     const int block = 256;
     const unsigned grid = (unsigned)((n + block - 1) / block);
-    if (model == LH_MODEL_RICHARDS) lh_diag_kernel<0><<<grid, block, 0, stream>>>(p, which, th, ti, re, T, out, n, colp, ncol_pad);
-    else lh_diag_kernel<2><<<grid, block, 0, stream>>>(p, which, th, ti, re, T, out, n, colp, ncol_pad);
+    if (model == LH_MODEL_RICHARDS) {
+        if (colp) lh_diag_kernel<0, true><<<grid, block, 0, stream>>>(p, pow_tab, which, th, ti, re, T, out, n, colp, ncol_pad);
+        else lh_diag_kernel<0, false><<<grid, block, 0, stream>>>(p, pow_tab, which, th, ti, re, T, out, n, colp, ncol_pad);
+    } else {
+        if (colp) lh_diag_kernel<2, true><<<grid, block, 0, stream>>>(p, pow_tab, which, th, ti, re, T, out, n, colp, ncol_pad);
+        else lh_diag_kernel<2, false><<<grid, block, 0, stream>>>(p, pow_tab, which, th, ti, re, T, out, n, colp, ncol_pad);
+    }
     return cudaGetLastError();
 }
 
@@ -358,7 +375,7 @@ __global__ void lh_eval_math_kernel(const __grid_constant__ LhDevParams p, int f
                                     double* __restrict__ y, int64_t n)
 {
     __shared__ __align__(16) double tab[LH_TAB_DOUBLES];
-    lh_stage_tables(p, tab, threadIdx.x, blockDim.x);
+    lh_stage_tables(p, nullptr, tab, threadIdx.x, blockDim.x);
     __syncthreads();
     const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;

@@ -42,6 +42,7 @@ struct LhKernelArgs {
     LhDevParams p;
     LhStageIO io;          // one-stage launches: this stage; persistent SSPRK33 launches: stage 1 (in = U, out = V)
     const double* zc;      // nlayer centre coordinates
+    const double* pow_tab; // LHPW_COUNT fixed-exponent power tables (lh_math.cuh), written once by lh_soil_create
     const double* colp;    // HET variants: [LHCP_COUNT][ncol_pad] per-column derived parameters
     double* budget_partials;   // [nblocks][2]: per-block sums of the ϑ_l and ρe_int values the last stage writes (or NULL)
     int64_t ncol;          // valid columns (<= ncol_pad): the padding is left out of the budgets
@@ -76,7 +77,7 @@ cudaError_t lh_launch_ssprk33_persistent(int model, int flags, const LhKernelArg
 cudaError_t lh_launch_any_nonzero(const double* x, int64_t n, int* flag, cudaStream_t stream);
 
 // Pointwise diagnostics (LH_DIAG_*): out[layer*ncol_pad+col].
-cudaError_t lh_launch_diagnostic(int model, int which, const LhDevParams& p, const double* th,
+cudaError_t lh_launch_diagnostic(int model, int which, const LhDevParams& p, const double* pow_tab, const double* th,
                                  const double* ti, const double* re, const double* T, double* out,
                                  int64_t ncells_pad, const double* colp, int64_t ncol_pad, cudaStream_t stream);
 

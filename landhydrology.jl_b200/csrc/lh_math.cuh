@@ -202,3 +202,100 @@ LH_DEV double lh_log2(const double* __restrict__ lh_c, const double* __restrict_
     const bool bad = (uint32_t)lh_hi(x) > 0x7fefffffu;
     return lh_mk(bad ? 0x7ff80000 : lh_hi(y), lh_lo(y));
 }
+
+// ---------------------------------------------------------------------------------------------------
+// x^c for an exponent c that is FIXED per parameter set (the van Genuchten 1/m and m, the Kersten exponent):
+// the log2 / exp2 pair collapses into one table-driven evaluation.  With the decomposition of lh_log2,
+//   x = 2^e m,  m = (1 + t) / r_j,  t = m r_j - 1  (|t| <= 2^-8, ONE FMA)
+//   x^c = 2^(e c) * r_j^(-c) * (1 + t)^c = B_e A_j (1 + t g(t)),   g of degree LH_POW_DEG
+// A_j = r_j^-c (128 entries), B_e = 2^(e c) (e = -64 .. 1) and the coefficients of g are built on the host for
+// each exponent when the context is created (lh_pow_build, long double) and staged in shared memory next to
+// the exp2 / log2 tables.  8 fp64 operations (7 for a second power of the same x) instead of the 20 of
+// exp2(c log2 x), and half the integer glue.  The interval around m = 1 has r = A = 1 exactly and B_0 = 1, so for
+// x in [1 - 2^-8, 1 + 2^-8] the parts are s = 1, p = (1 + t)^c - 1 with t = x - 1 exact: x^c - 1 and 1 - x^c keep
+// their RELATIVE accuracy there, which the conductivity 1 - (1 - S^(1/m))^m needs for dry cells.
+// x must be positive and normal; 0 <= x < 2^-64 returns 0 (B table entry 0); x >= 2.83, negative x and NaN give
+// FINITE garbage (the closures discard those lanes: oversaturated cells take the saturated branches, and a NaN state
+// reaches the results through their explicit factors of S; lh_pow_bad flags them where that is not so).
+// ---------------------------------------------------------------------------------------------------
+#define LH_POW_DEG 4
+#define LH_POW_EMIN 64
+#define LH_POW_NB (LH_POW_EMIN + 2)
+#define LH_POW_DOUBLES (LH_LOG_TAB + LH_POW_NB)     // one exponent's table: A_j, then B_e
+
+struct LhPowCoef { double c[LH_POW_DEG + 1]; };     // (1 + t)^c = 1 + t (c[0] + c[1] t + ... + c[4] t^4)
+
+struct LhPowArg { double t; int32_t j, be; };       // reduced argument: shared by every power of the same x
+
+LH_DEV LhPowArg lh_pow_arg(const double* __restrict__ tab, double x)
+{
+    const int32_t off = lh_hi(x) - LH_LOG_HI0;
+    int32_t e = off >> 20;
+    e = e < -LH_POW_EMIN ? -LH_POW_EMIN : e;
+    e = e > 1 ? 1 : e;
+    LhPowArg a;
+    a.be = LH_LOG_TAB + LH_POW_EMIN + e;
+    a.j = (off >> LH_LOG_SHIFT) & (LH_LOG_TAB - 1);
+    const double m = lh_mk(LH_LOG_HI0 + (off & 0xfffff), lh_lo(x));
+    a.t = lh_fma(m, tab[LH_TAB_LOG + 2 * a.j], -1.0);
+    return a;
+}
+
+// x < 0 (incl. -0.0), NaN, +inf: one unsigned compare on the high word.
+LH_DEV bool lh_pow_bad(double x) { return (uint32_t)lh_hi(x) > 0x7fefffffu; }
+
+// x^c = s (1 + p); ptab = this exponent's table.
+LH_DEV LhExpParts lh_pow_parts(const LhPowCoef& k, const double* __restrict__ ptab, const LhPowArg& a)
+{
+    double g = k.c[4];
+    g = lh_fma(g, a.t, k.c[3]);
+    g = lh_fma(g, a.t, k.c[2]);
+    g = lh_fma(g, a.t, k.c[1]);
+    g = lh_fma(g, a.t, k.c[0]);
+    LhExpParts o;
+    o.p = a.t * g;
+    o.s = ptab[a.j] * ptab[a.be];
+    return o;
+}
+
+LH_DEV double lh_pow_fixed(const LhPowCoef& k, const double* __restrict__ ptab, const LhPowArg& a)
+{
+    const LhExpParts e = lh_pow_parts(k, ptab, a);
+    return lh_fma(e.s, e.p, e.s);
+}
+
+// Host side: coefficients and table of one exponent (long double; entries are correctly rounded in all but ~1e-3 of
+// the cases, 0.5 ulp + 2^-64 otherwise).  g interpolates ((1 + t)^c - 1)/t at the 5 Chebyshev nodes of the t range:
+// error <= |binom(c, 6)| a^5 / 16 relative to 1 (a = 2^-8): < 2e-18 for |c| <= 4.
+#include <math.h>
+static inline void lh_pow_build(double c, const double* log_tab /* (r_j, L_j) pairs */, LhPowCoef* coef, double* ptab)
+{
+    const long double cl = (long double)c;
+    for (int j = 0; j < LH_LOG_TAB; ++j) ptab[j] = (double)powl((long double)log_tab[2 * j], -cl);
+    ptab[LH_LOG_TAB] = 0.0;                                        // e <= -64: x^c -> 0
+    for (int e = -LH_POW_EMIN + 1; e <= 1; ++e) ptab[LH_LOG_TAB + LH_POW_EMIN + e] = (double)exp2l((long double)e * cl);
+    // t range of the decomposition: [lo r - 1, hi r - 1] over the intervals; symmetric bound a
+    const long double a = 0.0039215L * 1.02L;
+    const int n = LH_POW_DEG + 1;
+    long double x[LH_POW_DEG + 1], M[LH_POW_DEG + 1][LH_POW_DEG + 2];
+    for (int i = 0; i < n; ++i) {
+        x[i] = cosl((2 * i + 1) * 3.14159265358979323846264338327950288L / (2 * n));   // in [-1, 1]; t = a x
+        const long double t = a * x[i];
+        const long double gt = expm1l(cl * log1pl(t)) / t;
+        long double pw = 1.0L;
+        for (int k = 0; k < n; ++k) { M[i][k] = pw; pw *= x[i]; }
+        M[i][n] = gt;
+    }
+    for (int col = 0; col < n; ++col) {                             // Gauss-Jordan with partial pivoting
+        int piv = col;
+        for (int r = col + 1; r < n; ++r) if (fabsl(M[r][col]) > fabsl(M[piv][col])) piv = r;
+        for (int k = 0; k <= n; ++k) { const long double tmp = M[col][k]; M[col][k] = M[piv][k]; M[piv][k] = tmp; }
+        for (int r = 0; r < n; ++r) {
+            if (r == col) continue;
+            const long double f = M[r][col] / M[col][col];
+            for (int k = col; k <= n; ++k) M[r][k] -= f * M[col][k];
+        }
+    }
+    long double sc = 1.0L;
+    for (int k = 0; k < n; ++k) { coef->c[k] = (double)(M[k][n] / M[k][k] / sc); sc *= a; }
+}

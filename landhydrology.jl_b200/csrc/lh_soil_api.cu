@@ -88,6 +88,10 @@ struct lh_soil_ctx {
     int32_t npartials = 0;
     double* budget_dev = nullptr;                // 2 doubles (+2 for the all-reduce result)
     double* colp_dev = nullptr;                  // [LHCP_COUNT][ncol_pad] per-column derived parameters (heterogeneous soils)
+    double* pow_tab_dev = nullptr;               // LHPW_COUNT fixed-exponent power tables (lh_math.cuh), built at create
+    std::vector<double> pow_tab;                 // their host copy
+    double* diag_dev = nullptr;                  // scratch field of lh_soil_diagnostic (lazily allocated)
+    bool theta_i_ptr_out = false;                // lh_soil_device_ptr handed out θ_i: the ICE kernels stay selected
     double* fused_partials = nullptr;            // [shape.nblocks][2] budget sums left by the last-stage launches
     int64_t fused_nblocks = 0;
     bool budget_fresh = false;                   // fused_partials describe the current state U
@@ -197,6 +201,17 @@ void derive_phys(const lh_soil_config& cfg, LhPhys& d)
     d.imp_on = q.impedance_factor != LH_FACTOR_NONE;
     d.om_zero = q.nu_ss_om == 0.0;
     d.log2_Sr_sat = log2(q.nu * d.inv_nu);
+    d.pow_p1_Sr_sat = (double)powl((long double)(q.nu * d.inv_nu), (long double)d.kersten_p1);
+}
+
+// Coefficients (into the parameter block) and tables of the three per-model exponents: 1/m, m and the Kersten exponent.
+void derive_pow(LhDevParams& d, std::vector<double>& tab)
+{
+    tab.assign((size_t)LHPW_COUNT * LH_POW_DOUBLES, 0.0);
+    const double* log_tab = d.mc + LHC_TAB0 + LH_TAB_LOG;
+    lh_pow_build(d.vg_inv_m, log_tab, &d.pw[LHPW_INVM], tab.data() + (size_t)LHPW_INVM * LH_POW_DOUBLES);
+    lh_pow_build(d.vg_m, log_tab, &d.pw[LHPW_M], tab.data() + (size_t)LHPW_M * LH_POW_DOUBLES);
+    lh_pow_build(d.kersten_p1, log_tab, &d.pw[LHPW_P1], tab.data() + (size_t)LHPW_P1 * LH_POW_DOUBLES);
 }
 
 LhDevParams derive_params(const lh_soil_config& cfg)
@@ -224,6 +239,8 @@ void free_all(lh_soil_ctx* c)
     if (c->bc_dev) cudaFree(c->bc_dev);
     if (c->fused_partials) cudaFree(c->fused_partials);
     if (c->colp_dev) cudaFree(c->colp_dev);
+    if (c->pow_tab_dev) cudaFree(c->pow_tab_dev);
+    if (c->diag_dev) cudaFree(c->diag_dev);
     if (c->nonfinite_dev) cudaFree(c->nonfinite_dev);
     if (c->ev_start) cudaEventDestroy(c->ev_start);
     if (c->ev_stop) cudaEventDestroy(c->ev_stop);
@@ -399,7 +416,7 @@ int32_t detect_ice(lh_soil_ctx* c)
     int h = 0;
     LH_CUDA(c, cudaMemcpyAsync(&h, flag, sizeof h, cudaMemcpyDeviceToHost, c->stream));
     LH_CUDA(c, cudaStreamSynchronize(c->stream));
-    c->has_ice = h != 0;
+    c->has_ice = h != 0 || c->theta_i_ptr_out;   // a caller holding the raw θ_i pointer may write ice at any time
     update_kernel_flags(c);
     return LH_OK;
 }
@@ -419,6 +436,7 @@ void fill_args(lh_soil_ctx* c, int stage, double dt, LhKernelArgs& a)
     else { a.io.out_th = c->V[0]; a.io.out_re = c->V[2]; }
     a.zc = c->zc_dev;
     a.colp = c->colp_dev;
+    a.pow_tab = c->pow_tab_dev;
     a.budget_partials = c->fused_partials;
     a.ncol = c->ncol;
     a.ncol_pad = c->ncol_pad;
@@ -494,6 +512,7 @@ int32_t lh_soil_create(const lh_soil_config* cfg, lh_soil_ctx** out)
     c->nlayer = cfg->nlayer;
     c->model = cfg->model;
     c->dp = derive_params(*cfg);
+    derive_pow(c->dp, c->pow_tab);
     c->force_general_vg = (cfg->flags & LH_FLAG_GENERAL_VG) != 0;
     c->bcv[LH_BCV_TOP_ENERGY] = cfg->top.energy_value;
     c->bcv[LH_BCV_TOP_HYDROLOGY] = cfg->top.hydrology_value;
@@ -558,6 +577,8 @@ int32_t lh_soil_create(const lh_soil_config* cfg, lh_soil_ctx** out)
         LH_CREATE_CUDA(cudaStreamSynchronize(c->stream));
         LH_CREATE_CUDA(lh_launch_fill_profile(c->zc_dev + c->nlayer, c->U[3], c->nlayer, c->ncol_pad, c->stream));
     }
+    LH_CREATE_CUDA(cudaMalloc(&c->pow_tab_dev, c->pow_tab.size() * sizeof(double)));
+    LH_CREATE_CUDA(cudaMemcpyAsync(c->pow_tab_dev, c->pow_tab.data(), c->pow_tab.size() * sizeof(double), cudaMemcpyHostToDevice, c->stream));
     c->npartials = (int32_t)std::min<int64_t>(1024, std::max<int64_t>(1, (c->ncol + 255) / 256));
     LH_CREATE_CUDA(cudaMalloc(&c->partials, 2 * c->npartials * sizeof(double)));
     LH_CREATE_CUDA(cudaMalloc(&c->budget_dev, 4 * sizeof(double)));
@@ -905,13 +926,10 @@ int32_t lh_soil_diagnostic(lh_soil_ctx* c, int32_t which, double* host, int64_t 
     if (!c || !host) return LH_ERR_INVALID_ARG;
     if (which < 0 || which >= LH_NUM_DIAGS) return fail(c, LH_ERR_INVALID_ARG, "bad diagnostic id %d", which);
     LH_CUDA(c, cudaSetDevice(c->device));
-    const size_t fb = field_bytes(c);
-    // reuse (or create) a tendency buffer as scratch
-    const int slot = has_water(c->model) ? 0 : 2;
-    if (!c->tend[slot]) LH_CUDA(c, cudaMalloc(&c->tend[slot], fb));
-    LH_CUDA(c, lh_launch_diagnostic(c->model, which, c->dp, c->U[0], c->U[1], c->U[2], c->U[3], c->tend[slot],
+    if (!c->diag_dev) LH_CUDA(c, cudaMalloc(&c->diag_dev, field_bytes(c)));      // its own scratch: tendencies stay untouched
+    LH_CUDA(c, lh_launch_diagnostic(c->model, which, c->dp, c->pow_tab_dev, c->U[0], c->U[1], c->U[2], c->U[3], c->diag_dev,
                                     (int64_t)c->ncol_pad * c->nlayer, c->colp_dev, c->ncol_pad, c->stream));
-    return download_field(c, c->tend[slot], host, cs, ls);
+    return download_field(c, c->diag_dev, host, cs, ls);
 }
 
 int32_t lh_soil_eval_math(lh_soil_ctx* c, int32_t fn, const double* x, double* y, int64_t n)
@@ -959,11 +977,13 @@ int32_t lh_soil_device_ptr(lh_soil_ctx* c, int32_t field, void** dptr, int64_t* 
 {
     if (!c || !dptr) return LH_ERR_INVALID_ARG;
     if (!field_ok(field) || !c->U[field]) return fail(c, LH_ERR_INVALID_ARG, "field %d does not exist", field);
+    LH_CUDA(c, cudaSetDevice(c->device));
     *dptr = c->U[field];
     c->external_writes = true;
     if (ncol_padded) *ncol_padded = c->ncol_pad;
     if (field == LH_FIELD_THETA_I) {   // the caller may write ice through the raw pointer: assume it does
         c->has_ice = true;
+        c->theta_i_ptr_out = true;     // sticky: a later all-zero θ_i upload does not switch back to the !ICE kernels
         update_kernel_flags(c);
     }
     return LH_OK;

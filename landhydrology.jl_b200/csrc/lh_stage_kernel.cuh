@@ -83,7 +83,8 @@ __device__ __forceinline__ Flux boundary_flux(const P& p, const double* __restri
             f.w = -c.K;                                                      // :328-356 (K of the centre cell)
         } else if (h_kind == LH_BC_DIRICHLET) {                              // :371-401
             double K_f, psi_f, l_;
-            lh_water_closures<ICE, GEN, (FLAGS & LH_FLAG_VG2) != 0, false>(p, tab, th_f, ti, T_f, K_f, psi_f, l_);
+            LhPowArg a_;
+            lh_water_closures<ICE, GEN, (FLAGS & LH_FLAG_VG2) != 0, false>(p, tab, th_f, ti, T_f, K_f, psi_f, l_, a_);
             double flux = (-K_f * (psi_f - c.psi + p.half_dz)) * p.inv_half_dz;
             f.w = is_bottom ? -flux : flux;
         }
@@ -195,7 +196,7 @@ __device__ __forceinline__ void lh_stage_body_impl(const LhKernelArgs& A, const 
 
     // shared memory: the exp2 / log2 tables, then per (g, w): one Slot (chunk-face exchange) and one input ring
     const double* tab = smem;
-    double* warp_base = smem + LH_TAB_DOUBLES + LH_RED_DOUBLES + (size_t)(g * W + w) * (Slot<MODEL>::doubles + RING_DOUBLES);
+    double* warp_base = smem + LH_TAB_ALL + LH_RED_DOUBLES + (size_t)(g * W + w) * (Slot<MODEL>::doubles + RING_DOUBLES);
     double* slot = warp_base + lane;
     double* sm_bot = slot;                               // Q of the chunk's first cell
     double* sm_top = slot + NQv * 32;                    // Q of the chunk's last cell
@@ -414,7 +415,7 @@ __device__ __forceinline__ void lh_stage_body_impl(const LhKernelArgs& A, const 
                 bud_w += __shfl_down_sync(0xffffffffu, bud_w, o);
                 bud_e += __shfl_down_sync(0xffffffffu, bud_e, o);
             }
-            double* red = smem + LH_TAB_DOUBLES;
+            double* red = smem + LH_TAB_ALL;
             const int wib = g * W + w;
             if (lane == 0) { red[2 * wib] = bud_w; red[2 * wib + 1] = bud_e; }
             __syncthreads();
@@ -474,7 +475,7 @@ lh_soil_stage_kernel(const __grid_constant__ LhKernelArgs A)
     // behind the previous stage's tail — what matters when a launch is only ~80 us (column shards at 8 GPUs).
     asm volatile("griddepcontrol.launch_dependents;");
 #endif
-    lh_stage_tables(A.p, smem, (threadIdx.z * blockDim.y + threadIdx.y) * 32 + threadIdx.x, blockDim.x * blockDim.y * blockDim.z);
+    lh_stage_tables(A.p, A.pow_tab, smem, (threadIdx.z * blockDim.y + threadIdx.y) * 32 + threadIdx.x, blockDim.x * blockDim.y * blockDim.z);
 #if LH_PDL
     asm volatile("griddepcontrol.wait;" ::: "memory");
 #endif
@@ -493,7 +494,7 @@ __global__ void __launch_bounds__(LhBounds<FLAGS>::max_threads, 1)
 lh_soil_ssprk33_persistent_kernel(const __grid_constant__ LhKernelArgs A)
 {
     extern __shared__ __align__(16) double smem[];
-    lh_stage_tables(A.p, smem, (threadIdx.z * blockDim.y + threadIdx.y) * 32 + threadIdx.x, blockDim.x * blockDim.y * blockDim.z);
+    lh_stage_tables(A.p, A.pow_tab, smem, (threadIdx.z * blockDim.y + threadIdx.y) * 32 + threadIdx.x, blockDim.x * blockDim.y * blockDim.z);
     __syncthreads();
     // stage 1 as passed: in = U, out = V
     const double* Uth = A.io.in_th;

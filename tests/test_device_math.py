@@ -103,3 +103,32 @@ def test_sqrt_rcp_div(mathlib):
     a = rng.uniform(-1e8, 1e8, len(x))
     q = _call(mathlib, "lhm_div", a, x)
     assert _ulp_err(q, [mp.mpf(float(u)) / mp.mpf(float(v)) for u, v in zip(a, x)]).max() <= 1.0
+
+
+@pytest.mark.parametrize("c", [1.0 / (1.0 - 1.0 / 1.56), 1.0 - 1.0 / 1.56, 1.0 / (1.0 - 1.0 / 3.96), 1.0 - 1.0 / 3.96,
+                               0.5, 2.0, (1.0 - 0.24 * 0.92) / 2.0, 0.3896, 3.7])
+def test_pow_fixed(mathlib, c):
+    """lh_pow_fixed: x^c with per-exponent tables (the van Genuchten 1/m, m and the Kersten exponent)."""
+    rng = np.random.default_rng(5)
+    x = np.concatenate([rng.uniform(1e-6, 1.4, 6000), 1.0 + rng.uniform(-4e-3, 4e-3, 1500), 2.0 ** rng.uniform(-60, 0, 1500),
+                        [0.5, 1.0, 0.70710678118654752, 1.4142135623730951, 1.0 - 2.0 ** -53, 1.0 + 2.0 ** -52]])
+    mp.mp.dps = 40
+    y = _call(mathlib, "lhm_pow", x, np.array([c, 0.0] + [0.0] * (len(x) - 2)))
+    exact = [mp.mpf(float(v)) ** mp.mpf(c) for v in x]
+    err = _ulp_err(y, exact)
+    assert err.max() <= 2.5, err.max()
+    # x^c - 1 and 1 - x^c keep their relative accuracy around x = 1 (central interval: s == 1 exactly)
+    near = (x >= 1.0 - 2.0 ** -9) & (x <= 1.0 + 2.0 ** -8)      # the interval around m = 1: r = A = B = 1 exactly
+    ym1 = _call(mathlib, "lhm_pow", x, np.array([c, 1.0] + [0.0] * (len(x) - 2)))
+    om = _call(mathlib, "lhm_pow", x, np.array([c, 2.0] + [0.0] * (len(x) - 2)))
+    ex1 = [e - 1 for e in exact]
+    e1 = _ulp_err(ym1[near], [e for e, k in zip(ex1, near) if k])
+    assert e1.max() <= 64.0, e1.max()     # degree-4 g: |binom(c, 6)| a^5 / 16 / c <= 7e-15 relative (the literal 1 - x^c of
+                                          # the reference is off by 1.1e-16 / |1 - x^c| there: >= 3e-14)
+    assert np.array_equal(om, -ym1) or np.allclose(om, -ym1, rtol=1e-15, atol=0)
+    rel = np.abs(ym1 - np.array([float(e) for e in ex1])) / np.maximum(np.abs(ym1), 1e-300)
+    assert rel[~near & (x > 0.01)].max() <= 3e-13 / min(c, 1.0)
+    # below 2^-64 the power reads as 0; negative arguments give finite garbage (callers that need a NaN flag test the
+    # sign themselves: lh_pow_bad)
+    sp = _call(mathlib, "lhm_pow", np.array([2.0 ** -70, 0.0, -0.3]), np.array([c, 0.0, 0.0]))
+    assert sp[0] == 0.0 and sp[1] == 0.0 and np.isfinite(sp[2])
