@@ -11,16 +11,28 @@ which fits one GPU (2.7 GB).  For N > 1 the SAME 2^20 columns are cut into conti
 process per GPU, no data-path collective ("scaling": "strong"); NCCL is used only for the 2-double
 budget all-reduce, which is timed separately.
 
-One JSON line on stdout (rank 0).  value = whole-job cell-steps/s with the state resident in HBM,
-timed with CUDA events on the ctx stream (max over ranks).  e2e = the same job through the C ABI
-from pinned HOST buffers: H2D state upload + K x (step with a host-built bc table + budget read) +
-D2H state download, wall-clocked with a device sync on both sides; the columns are cut into --e2e-shards shards (one ctx,
-stream and host thread each) whose transfers take turns on the PCIe link and overlap the kernels of the other shards.
+One JSON line on stdout (rank 0).
+
+value   whole-job cell-steps/s with the state resident in HBM.  A timed BLOCK is exactly K steps, bracketed by a
+        barrier and a device synchronisation, timed with CUDA events on the ctx stream (max over ranks).  Blocks are
+        repeated back to back until at least --min-seconds (3 s) of device time have been measured; `value` is the MEDIAN
+        block (sustained clocks), the first (burst) block and the spread are in `sustained`.
+roofline  contract fraction (SURVEY §8d bytes: θ_i counted in every stage) AND the on-wire fraction (the bytes the
+        launched kernel variant really moves), with the variant named by the library itself (lh_soil_kernel_info).
+e2e     the same job through the C ABI from pinned HOST buffers: H2D state upload + K x (step with a host-built bc
+        table + budget read) + D2H state download, wall clock with a device sync on both sides; the columns are cut
+        into --e2e-shards shards (one ctx, stream and host thread each) whose transfers take turns on the PCIe link
+        and overlap the kernels of the other shards.
+cpu_baseline / --impl reference   the C restatement of the reference CPU path (OpenMP over columns) on the SAME
+        column set and layer count (full 2^20 x 64 unless K + W is so large that the run would not end in minutes).
+extra.variants  the kernel specialisations real soils hit (general van Genuchten n, ice, impedance + viscosity,
+        Richards, heterogeneous columns) and the other BASELINE shapes, timed in this process (tools/variants.py).
 """
 from __future__ import annotations
 
 import argparse
 import json
+import math
 import os
 import subprocess
 import sys
@@ -32,11 +44,12 @@ import numpy as np
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 sys.path.insert(0, os.path.join(ROOT, "tests"))
+sys.path.insert(0, os.path.join(ROOT, "tools"))
 
 METRIC = "soil cell-steps/sec (fp64, coupled water+heat, SSPRK33)"
 UNIT = "cell-steps/s"
-BYTES_PER_CELL_STEP = {"coupled": 152, "richards": 88}     # BASELINE.md §3 (algorithmic, per-stage fusion)
-REF_SAMPLE_COLS = 16384                                    # bounded sample for the CPU arms
+BYTES_PER_CELL_STEP = {"coupled": 152, "richards": 88}     # BASELINE.md §3 (algorithmic, per-stage fusion; the contract figure)
+REF_MAX_STEPS_FULL = 60                                    # reference arm: the full column set while K + W <= this
 
 
 def parse_args():
@@ -48,11 +61,16 @@ def parse_args():
     ap.add_argument("--model", default="coupled", choices=["coupled", "richards"])
     ap.add_argument("--ncol", type=int, default=1 << 20)
     ap.add_argument("--nlayer", type=int, default=64)
+    ap.add_argument("--min-seconds", type=float, default=3.0,
+                    help="repeat the timed K-step block until this much device time has been measured (sustained clocks)")
     ap.add_argument("--general-vg", action="store_true",
                     help="never use the van Genuchten n == 2 square-root specialisation (LH_FLAG_GENERAL_VG)")
+    ap.add_argument("--ice", action="store_true", help="θ_i ~ U(0, 0.05) in every cell: the ICE kernel variants")
     ap.add_argument("--launch", default="auto", choices=["auto", "stage", "persistent"],
                     help="lh_soil_step_ssprk33 strategy: one launch per stage, one persistent launch per call, or the library's "
-                         "own choice (persistent for small launch-bound grids of <= 3 waves)")
+                         "own choice (persistent only for small, launch-bound grids of <= 1.5 waves of resident blocks)")
+    ap.add_argument("--no-chain", action="store_true",
+                    help="whole-grid dependency between consecutive stage launches (LH_FLAG_NO_CHAIN) instead of block-to-block")
     ap.add_argument("--het", action="store_true",
                     help="heterogeneous soils: random per-column nu / theta_r / van Genuchten n, alpha / Ksat (lh_soil_set_column_params)")
     ap.add_argument("--e2e-shards", type=int, default=8,
@@ -60,13 +78,14 @@ def parse_args():
                          "one shard, the steps of another and the download of a third overlap; 1 = a single ctx")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-variants", action="store_true", help="skip the extra.variants table (N = 1 only)")
     return ap.parse_args()
 
 
-def make_workload(w, model, ncol, nlayer, col_range):
+def make_workload(w, model, ncol, nlayer, col_range, ice=False):
     if model == "coupled":
-        return w.coupled_workload(ncol=ncol, nlayer=nlayer, col_range=col_range)
-    return w.richards_workload(ncol=ncol, nlayer=nlayer, col_range=col_range,
+        return w.coupled_workload(ncol=ncol, nlayer=nlayer, col_range=col_range, ice=ice)
+    return w.richards_workload(ncol=ncol, nlayer=nlayer, col_range=col_range, ice=ice,
                                zlim=(-1.5 * nlayer / 100.0, 0.0))
 
 
@@ -95,7 +114,7 @@ class ClockSampler:
     def start(self):
         try:
             self.proc = subprocess.Popen(
-                ["nvidia-smi", f"--id={self.device}", f"--query-gpu={self.FIELDS}", "--format=csv,noheader,nounits", "-lms", "100"],
+                ["nvidia-smi", f"--id={self.device}", f"--query-gpu={self.FIELDS}", "--format=csv,noheader,nounits", "-lms", "50"],
                 stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             self.thread = threading.Thread(target=self._read, daemon=True)
             self.thread.start()
@@ -108,23 +127,24 @@ class ClockSampler:
 
     def stop(self, t0, t1):
         if self.proc is None:
-            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"], "samples": 0}
         time.sleep(0.15)
         self.proc.terminate()
-        rows = [l for (ts, l) in self.lines if t0 - 0.05 <= ts <= t1 + 0.15] or [l for _, l in self.lines]
-        sm, smax, reasons = [], None, set()
+        rows = [l for (ts, l) in self.lines if t0 + 0.05 <= ts <= t1]     # strictly inside the timed region
+        sm, power, smax, reasons = [], [], None, set()
         for l in rows:
             parts = [x.strip() for x in l.split(",")]
             if len(parts) < 9:
                 continue
             try:
-                sm.append(float(parts[1])); smax = float(parts[2])
+                sm.append(float(parts[1])); smax = float(parts[2]); power.append(float(parts[3]))
             except ValueError:
                 continue
             for name, val in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), parts[5:9]):
                 if val.lower().startswith("active"):
                     reasons.add(name)
-        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": smax,
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_min_mhz": float(np.min(sm)) if sm else None,
+                "sm_max_mhz": smax, "power_w_median": float(np.median(power)) if power else None,
                 "reasons": sorted(reasons), "samples": len(sm)}
 
 
@@ -148,11 +168,11 @@ def bc_table_for(wl, t0, dt, nsteps):
     return np.broadcast_to(vals, (nsteps, 3, 4)).copy()
 
 
-def time_oracle(w, lh, graft, model, nlayer, steps, warmup, target_seconds=None):
-    """The reference's CPU path (C restatement, OpenMP over columns) on a bounded sample."""
+def time_oracle(w, lh, graft, model, ncol, nlayer, steps, warmup, target_seconds=None, ice=False):
+    """The reference's CPU path (C restatement, OpenMP over columns) on `ncol` columns of the same workload."""
     import ctypes as C
 
-    wl = make_workload(w, model, REF_SAMPLE_COLS, nlayer, (0, REF_SAMPLE_COLS))
+    wl = make_workload(w, model, ncol, nlayer, (0, ncol), ice=ice)
     lib = lh.SoilLibrary(graft.build_oracle(), "lho_")
     # all the host threads this process may use (torchrun exports OMP_NUM_THREADS=1: override it)
     set_threads = lib.raw("lho_soil_set_num_threads")
@@ -164,17 +184,21 @@ def time_oracle(w, lh, graft, model, nlayer, steps, warmup, target_seconds=None)
     cores = int(nthreads())
     ctx = lh.SoilContext(lib, wl.config())
     wl.upload(ctx)
-    ctx.step(0.0, wl.dt, max(1, warmup) if target_seconds is None else 1)
+    t0 = time.perf_counter()
+    ctx.step(0.0, wl.dt, 1)
+    one = time.perf_counter() - t0
+    if max(0, warmup - 1) > 0:
+        ctx.step(0.0, wl.dt, warmup - 1)
     if target_seconds is not None:
-        t0 = time.perf_counter(); ctx.step(0.0, wl.dt, 1); one = time.perf_counter() - t0
         steps = int(min(max(2, round(target_seconds / max(one, 1e-6))), 200))
     t0 = time.perf_counter()
     ctx.step(0.0, wl.dt, steps)
     sec = time.perf_counter() - t0
     value = wl.cells * steps / sec
-    sample = (f"{REF_SAMPLE_COLS} columns x {nlayer} layers ({wl.cells} cells) of the same {model} workload, "
-              f"{steps} SSPRK33 steps, {sec:.1f} s")
-    return value, cores, sample, sec, steps, wl
+    sample = (f"{ncol} columns x {nlayer} layers ({wl.cells} cells) of the same {model} workload, "
+              f"{steps} SSPRK33 steps after {max(1, warmup)} warm-up step(s), {sec:.1f} s")
+    ctx.close()
+    return value, cores, sample, sec, steps
 
 
 def main():
@@ -200,7 +224,6 @@ def _main(args, result_stream):
     lh = graft.load_package()
     import workloads as w
 
-    model_id = {"coupled": lh._abi.LH_MODEL_COUPLED, "richards": lh._abi.LH_MODEL_RICHARDS}[args.model]
     config = {
         "workload": f"{args.ncol} columns x {args.nlayer} layers, {args.model} "
                     f"(BASELINE.json configs[3]: 1M columns x 64 layers coupled water+heat)"
@@ -208,19 +231,23 @@ def _main(args, result_stream):
         "columns": args.ncol, "layers": args.nlayer, "stepper": "SSPRK33, fused RHS+stage kernel",
         "sharding": f"contiguous column ranges over {world} GPU(s), no halo",
         "l2": "state (2.7 GB at N=1) is larger than the 126 MB L2; no flush needed",
-        "closures": "general van Genuchten n (log/exp form)" if (args.general_vg or args.model != "coupled")
+        "closures": "general van Genuchten n (fixed-exponent power tables)" if (args.general_vg or args.model != "coupled")
                     else "n = 2 of the coupled.jl parameters -> square-root specialisation (automatic; --general-vg disables)",
+        "ice": bool(args.ice),
     }
 
     # ---------------- reference arm: the reference's CPU implementation of the path -----------------
     if args.impl == "reference":
         if rank != 0:
             return 0
-        value, cores, sample, sec, steps, wl = time_oracle(w, lh, graft, args.model, args.nlayer, args.steps, args.warmup)
+        total = args.steps + max(1, args.warmup)
+        ref_cols = args.ncol if total <= REF_MAX_STEPS_FULL else max(16384, (args.ncol * REF_MAX_STEPS_FULL // total) // 16384 * 16384)
+        value, cores, sample, sec, steps = time_oracle(w, lh, graft, args.model, ref_cols, args.nlayer, args.steps, args.warmup, ice=args.ice)
         line = {
             "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * sec / steps, "higher_is_better": True,
             "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic", "config": config,
+            "same_config": ref_cols == args.ncol,
             "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample,
                              "note": "C restatement of the reference CPU path (Julia is not installable here), OpenMP over columns"},
             "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
@@ -240,11 +267,12 @@ def _main(args, result_stream):
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
 
     lo, hi = lh.shard_range(args.ncol, world, rank)
-    wl = make_workload(w, args.model, args.ncol, args.nlayer, (lo, hi))
+    wl = make_workload(w, args.model, args.ncol, args.nlayer, (lo, hi), ice=args.ice)
     wl.device = local_rank
     lib = lh.cuda_library()
-    flags = (lh._abi.LH_FLAG_GENERAL_VG if args.general_vg else 0) | \
-            {"auto": 0, "stage": lh._abi.LH_FLAG_STAGE_LAUNCHES, "persistent": lh._abi.LH_FLAG_PERSISTENT}[args.launch]
+    A = lh._abi
+    flags = (A.LH_FLAG_GENERAL_VG if args.general_vg else 0) | (A.LH_FLAG_NO_CHAIN if args.no_chain else 0) | \
+            {"auto": 0, "stage": A.LH_FLAG_STAGE_LAUNCHES, "persistent": A.LH_FLAG_PERSISTENT}[args.launch]
     ctx = lh.SoilContext(lib, wl.config(flags=flags))
     if args.het:
         rng = np.random.default_rng(11 + rank)
@@ -261,6 +289,7 @@ def _main(args, result_stream):
             pass
         eng = _Eng(); eng.lib = lib; eng.ctx = ctx
         lh.init_budget_comm(eng, dist)
+    kernel_info = ctx.kernel_info()
 
     def barrier():
         torch.cuda.synchronize()
@@ -268,29 +297,49 @@ def _main(args, result_stream):
             dist.barrier()
         ctx.sync()
 
+    def rank_max(x):
+        tt = torch.tensor(x, dtype=torch.float64, device="cuda")
+        if world > 1:
+            dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+        return tt.cpu().numpy()
+
     # warm-up (W >= 3 untimed steps)
     t = 0.0
     ctx.step(t, wl.dt, args.warmup)
     ctx.sync()
     t += args.warmup * wl.dt
 
-    # ---- timed region: exactly K steps, state resident in HBM, CUDA events on the ctx stream ----
+    # ---- timed region: blocks of exactly K steps, state resident in HBM, CUDA events on the ctx stream ----
     sampler = ClockSampler(local_rank)
     if rank == 0:
         sampler.start()
-        time.sleep(0.25)
+        time.sleep(0.3)
+
+    def timed_block():
+        nonlocal t
+        barrier()
+        ctx.step(t, wl.dt, args.steps)
+        ms, launches = ctx.last_step_timing()          # cudaEventElapsedTime(start, stop) on the ctx stream; syncs on stop
+        t += args.steps * wl.dt
+        return ms, launches
+
     barrier()
     w0 = time.perf_counter()
-    ctx.step(t, wl.dt, args.steps)
-    ms, launches = ctx.last_step_timing()          # cudaEventElapsedTime(start, stop) on the ctx stream
+    ms0, launches = timed_block()
+    ms0 = float(rank_max([ms0])[0])
+    nblocks = int(min(2000, max(3, math.ceil(args.min_seconds * 1e3 / max(ms0, 1e-3)))))
+    block_ms = [ms0]
+    for _ in range(nblocks - 1):
+        ms, launches = timed_block()
+        block_ms.append(ms)
     barrier()
     w1 = time.perf_counter()
     clocks = sampler.stop(w0, w1) if rank == 0 else None
-    t += args.steps * wl.dt
-    ms_t = torch.tensor([ms], dtype=torch.float64, device="cuda")
-    if world > 1:
-        dist.all_reduce(ms_t, op=dist.ReduceOp.MAX)
-    ms_max = float(ms_t.item())
+    block_ms = rank_max(block_ms)                          # per block: the slowest rank
+    ms_med = float(np.median(block_ms))
+    if rank == 0 and (clocks is None or not clocks.get("samples")):
+        raise SystemExit(f"clock sampler recorded no nvidia-smi sample inside the {w1 - w0:.2f} s timed region: "
+                         "the measurement cannot be vetted for throttling (is nvidia-smi on PATH?)")
 
     # ---- the one collective: global water/energy budgets ----
     budgets = ctx.budgets_allreduce() if world > 1 else ctx.budgets()     # first call: NCCL lazy set-up
@@ -323,6 +372,7 @@ def _main(args, result_stream):
         # shard k+1 uploads and shard k-1 downloads, instead of all shards moving in lockstep.
         up_done = [threading.Event() for _ in range(S)]
         down_done = [threading.Event() for _ in range(S)]
+        step_budgets = np.zeros((S, K, 2))
 
         def run_shard(k, sub, c0, c1):
             if k > 0:
@@ -331,10 +381,18 @@ def _main(args, result_stream):
                 sub.set_state(fid, a[c0:c1])                   # H2D (+ layout transform on device)
             up_done[k].set()
             tt = 0.0
-            for _ in range(K):
+            pending = None
+            for s in range(K):
                 sub.step(tt, wl.dt, 1, table)                  # host-evaluated bc values for the 3 stage times
-                sub.budgets()                                  # D2H read of the step's result (16 B)
+                # D2H read of the step's result (16 B), non-blocking: the copy is enqueued behind the step and collected
+                # after the NEXT step has been enqueued, so the stream never drains between steps.
+                nxt = sub.budgets_async()
+                if pending is not None:
+                    step_budgets[k, s - 1] = sub.budgets_wait(pending)
+                pending = nxt
                 tt += wl.dt
+            if pending is not None:
+                step_budgets[k, K - 1] = sub.budgets_wait(pending)
             if k > 0:
                 down_done[k - 1].wait()
             for fid, a in out.items():
@@ -353,10 +411,9 @@ def _main(args, result_stream):
                 sub.sync()
         barrier()
         e_sec = time.perf_counter() - e0
-        e_t = torch.tensor([e_sec], dtype=torch.float64, device="cuda")
-        if world > 1:
-            dist.all_reduce(e_t, op=dist.ReduceOp.MAX)
-        e_sec = float(e_t.item())
+        e_sec = float(rank_max([e_sec])[0])
+        if not np.all(np.isfinite(step_budgets)):
+            raise SystemExit("non-finite per-step budgets in the e2e leg")
         cells_total = args.ncol * args.nlayer
         nfields_in, nfields_out = len(host), len(out)
         e2e = {
@@ -364,11 +421,14 @@ def _main(args, result_stream):
             "h2d_bytes_per_step": int(nfields_in * cells_total * 8 / K + 96),
             "d2h_bytes_per_step": int(nfields_out * cells_total * 8 / K + 16),
             "what": f"lh_soil_set_state x{nfields_in} (pinned host, reference layout) + {K} x [lh_soil_step_ssprk33(1 step, bc table) + "
-                    f"lh_soil_budgets] + lh_soil_get_state x{nfields_out}, over {S} column shard(s) per GPU (one ctx and host thread "
-                    f"each, transfers overlapping kernels); wall clock, max over ranks",
+                    f"lh_soil_budgets_async/wait (16 B D2H per step)] + lh_soil_get_state x{nfields_out}, over {S} column shard(s) per GPU "
+                    f"(one ctx and host thread each, transfers overlapping kernels); wall clock, max over ranks",
             "shards_per_gpu": S,
             "seconds": e_sec,
         }
+        for sub, _, _ in subs:
+            if sub is not ctx:
+                sub.close()
 
     if rank != 0:
         if world > 1:
@@ -376,57 +436,107 @@ def _main(args, result_stream):
         return 0
 
     cells_total = args.ncol * args.nlayer
-    value = cells_total * args.steps / (ms_max * 1e-3)
+    value = cells_total * args.steps / (ms_med * 1e-3)
     peak, peak_src = load_peaks()
     cells_rank = (hi - lo) * args.nlayer
     persistent = int(launches) != 3 * args.steps
+    wire_bpcs = None
+    try:
+        wire_bpcs = int(kernel_info.rsplit("=", 1)[1])
+    except Exception:
+        pass
     if not persistent:
         # dominant kernel = lh_soil_stage_kernel<model, stage 1|2|3>: every launch in the timed region is one of its three
         # stage instantiations; per-launch figures are the averages over the 3K launches.
         bpcs = BYTES_PER_CELL_STEP[args.model]
-        bytes_per_launch = cells_rank * bpcs / 3.0
-        launch_ms = ms_max / (3 * args.steps)
+        nl = 3 * args.steps
         kernel = "lh_soil_stage_kernel (fused closures + stencil + SSPRK33 stage)"
-        note = ("per-launch average over the 3 stage launches of each step (40/56/56 B per cell coupled, 24/32/32 Richards); "
-                "besides HBM the kernel is bounded by issue slots: an fp64 instruction holds the issue port for two "
-                "cycles on B200 (DESIGN.md §4.1)")
+        note = ("per-launch average over the 3 stage launches of each step (contract: 40/56/56 B per cell coupled, 24/32/32 Richards). "
+                "`frac` credits the SURVEY §8d contract bytes; `frac_on_wire` the bytes the launched variant really moves (the !ICE "
+                "variants never read theta_i). The kernel is bounded by issue slots, not HBM: an fp64 instruction holds the issue "
+                "port for two cycles on B200 (DESIGN.md §4.1), see `issue_model`")
     else:
         # one persistent launch for all K steps: a block keeps its columns, the stage registers stay in L2, and the
         # compulsory traffic of a launch is one read of the state and one write of the prognostic fields per STEP
         bpcs = {"coupled": 40, "richards": 24}[args.model]
-        bytes_per_launch = cells_rank * bpcs * args.steps / max(int(launches), 1)
-        launch_ms = ms_max / max(int(launches), 1)
+        wire_bpcs = bpcs - (0 if args.ice or args.model != "coupled" else 8)
+        nl = max(int(launches), 1)
         kernel = "lh_soil_ssprk33_persistent_kernel (all stages of all steps in one launch, columns L2-resident)"
         note = ("persistent launch (grid of few waves): algorithmic bytes are 40 B (coupled) / 24 B (Richards) per cell-STEP, "
                 "the path is issue-bound, not HBM-bound (DESIGN.md §4.1)")
-    achieved = bytes_per_launch / (launch_ms * 1e-3) / 1e9
-    traffic = None
+    launch_ms = ms_med / nl
+    achieved = cells_rank * bpcs * args.steps / nl / (launch_ms * 1e-3) / 1e9
+    on_wire = cells_rank * (wire_bpcs or bpcs) * args.steps / nl / (launch_ms * 1e-3) / 1e9
+    traffic, traffic_src = None, None
     tpath = os.path.join(ROOT, "profiles", "dram_traffic.json")
-    if os.path.exists(tpath) and not persistent:
+    if os.path.exists(tpath) and not persistent and not (args.ice or args.het or args.general_vg):
         try:
             traffic = json.load(open(tpath)).get(f"{args.model}_{args.ncol}x{args.nlayer}_bytes_per_launch")
             if traffic is not None:
                 traffic = traffic * cells_rank / (args.ncol * args.nlayer)     # measured at N = 1; per launch of this rank's shard
+                traffic_src = "profiles/dram_traffic.json (CACHED ncu --set full capture of this command, not measured in this run)"
         except Exception:
             traffic = None
-    config["launch"] = "persistent (1 launch per call)" if persistent else "3 launches per step"
+    config["launch"] = "persistent (1 launch per call)" if persistent else "3 launches per step, chained block to block"
+    if args.no_chain:
+        config["launch"] = "3 launches per step, whole-grid dependency (LH_FLAG_NO_CHAIN)"
     line = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
-        "ms_per_step": ms_max / args.steps, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
+        "ms_per_step": ms_med / args.steps, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
         "dtype": "f64", "data": "synthetic", "config": config, "clocks": clocks,
-        "gpu_launches": int(launches),
+        "gpu_launches": int(launches) * len(block_ms),
+        "sustained": {
+            "what": f"{len(block_ms)} back-to-back timed blocks of exactly {args.steps} steps; value = median block",
+            "blocks": len(block_ms), "device_seconds": float(np.sum(block_ms)) * 1e-3,
+            "ms_per_step_first_block": float(block_ms[0]) / args.steps, "ms_per_step_min": float(np.min(block_ms)) / args.steps,
+            "ms_per_step_median": ms_med / args.steps, "ms_per_step_max": float(np.max(block_ms)) / args.steps,
+            "value_first_block": cells_total * args.steps / (float(block_ms[0]) * 1e-3),
+        },
         "roofline": {
             "bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-            "traffic": traffic, "peak_source": peak_src,
-            "kernel": kernel, "algorithmic_bytes_per_cell_step": bpcs, "launch_ms": launch_ms, "note": note,
+            "achieved_on_wire": on_wire, "frac_on_wire": on_wire / peak,
+            "traffic": traffic, "traffic_source": traffic_src, "peak_source": peak_src,
+            "kernel": kernel, "variant": kernel_info,
+            "algorithmic_bytes_per_cell_step": bpcs, "on_wire_bytes_per_cell_step": wire_bpcs, "launch_ms": launch_ms, "note": note,
         },
         "budgets": {"water": float(budgets[0]), "energy": float(budgets[1]), "allreduce_ms": budget_ms},
     }
+    # issue-slot model of the launched variant (static SASS counts of the layer loop, profiles/r02_sass_loop_mix.json)
+    try:
+        mix = json.load(open(os.path.join(ROOT, "profiles", "r02_sass_loop_mix.json")))
+        key = kernel_info.split("FLAGS=")[1].split(":")[0]
+        mkey = f"{ {'coupled': 2, 'richards': 0}[args.model] }_{key}"
+        if mkey in mix and clocks and clocks.get("sm_mhz"):
+            m = mix[mkey]
+            cyc = m["cycles_per_warp_cell_stage_mean"]
+            sm_count = torch.cuda.get_device_properties(local_rank).multi_processor_count
+            ceiling = sm_count * 4 * clocks["sm_mhz"] * 1e6 * 32 / cyc / 3.0 * world
+            line["roofline"]["issue_model"] = {
+                "cycles_per_warp_cell_stage": cyc, "fp64_per_cell_stage": m["fp64_mean"], "other_per_cell_stage": m["other_mean"],
+                "ceiling_cell_steps_per_s_at_measured_clock": ceiling, "frac_of_issue_ceiling": value / ceiling,
+                "what": "2 x fp64 + other warp-instructions per cell and stage in the layer loop (cuobjdump -sass, "
+                        "profiles/r02_sass_loop_mix.json) x 4 schedulers x SMs x median SM clock"}
+    except Exception:
+        pass
     if e2e is not None:
         line["e2e"] = e2e
+    ctx.close()
+    del host
     if world == 1 and not args.no_cpu_baseline:
-        v, cores, sample, sec, steps, _ = time_oracle(w, lh, graft, args.model, args.nlayer, 0, 0, target_seconds=12.0)
+        v, cores, sample, sec, steps = time_oracle(w, lh, graft, args.model, args.ncol, args.nlayer, 0, 1, target_seconds=12.0, ice=args.ice)
         line["cpu_baseline"] = {"value": v, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample}
+    if world == 1 and not args.no_variants:
+        import variants as V
+
+        rows = {}
+        for name, spec in V.variant_specs(lh, w).items():
+            try:
+                rows[name] = V.measure(lh, spec, steps=args.steps, warmup=args.warmup, reps=5, device=local_rank)
+            except Exception as exc:                      # a variant that fails must not hide the headline
+                rows[name] = {"error": f"{type(exc).__name__}: {exc}"}
+        line["extra"] = {"variants": rows,
+                         "variants_note": "same process, same GPU, CUDA events on the ctx stream, median of 5 blocks of K steps each "
+                                          "(small configs: 50 K steps per block); frac_contract / frac_on_wire as in `roofline`"}
     print(json.dumps(line), file=result_stream)
     result_stream.flush()
     if world > 1:

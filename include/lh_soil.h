@@ -157,6 +157,10 @@ typedef struct lh_soil_config {
  * Results are bit-identical either way.                                                          */
 #define LH_FLAG_STAGE_LAUNCHES 4 /* always one launch per stage                                  */
 #define LH_FLAG_PERSISTENT     8 /* always the persistent launch                                 */
+/* Consecutive stage launches are chained block to block (block j of a stage starts as soon as block j of the previous
+ * stage has published its results, instead of after the whole previous grid): the launch tail is paid once per call,
+ * not once per stage.  Results are bit-identical.  This flag restores the whole-grid dependency (for measurements). */
+#define LH_FLAG_NO_CHAIN      16
 
 typedef struct lh_soil_ctx lh_soil_ctx;
 
@@ -299,6 +303,11 @@ int32_t lh_soil_eval_math(lh_soil_ctx* ctx, int32_t fn, const double* x, double*
 /* Device time (ms) spent in the kernels of the last lh_soil_step_ssprk33 call, measured with
  * CUDA events on the ctx stream, and the number of kernels it launched.                     */
 int32_t lh_soil_last_step_timing(lh_soil_ctx* ctx, double* ms_out, int64_t* launches_out);
+
+/* One line describing what lh_soil_step_ssprk33 launches for the current state of the ctx: kernel template and variant
+ * flags (ICE / GEN / VG2 / HET), block and grid shape, launch strategy, and the HBM bytes per cell-step that variant
+ * moves.  For benchmark records (bench.py prints it next to the roofline figures).                                  */
+int32_t lh_soil_kernel_info(lh_soil_ctx* ctx, char* buf, int64_t cap);
 
 /* Raw device pointer of a field's column-fastest SoA block [layer][ncol_padded] and the
  * padded column stride, for zero-copy interop (e.g. wrapping in a torch tensor).            */

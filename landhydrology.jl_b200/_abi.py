@@ -38,6 +38,7 @@ LH_FLAG_CHECK_FINITE = 1
 LH_FLAG_GENERAL_VG = 2
 LH_FLAG_STAGE_LAUNCHES = 4
 LH_FLAG_PERSISTENT = 8
+LH_FLAG_NO_CHAIN = 16
 
 
 class SoilError(RuntimeError):
@@ -143,6 +144,7 @@ _SIGNATURES = {
     "soil_sync": ([_vp], C.c_int32),
     "soil_eval_math": ([_vp, C.c_int32, _dp, _dp, C.c_int64], C.c_int32),
     "soil_last_step_timing": ([_vp, _dp, C.POINTER(C.c_int64)], C.c_int32),
+    "soil_kernel_info": ([_vp, C.c_char_p, C.c_int64], C.c_int32),
     "soil_device_ptr": ([_vp, C.c_int32, C.POINTER(_vp), C.POINTER(C.c_int64)], C.c_int32),
     "soil_comm_unique_id": ([C.POINTER(C.c_uint8)], C.c_int32),
     "soil_comm_init": ([_vp, C.c_int32, C.c_int32, C.POINTER(C.c_uint8)], C.c_int32),
@@ -382,6 +384,12 @@ class SoilContext:
         n = C.c_int64()
         self._check(self.lib.soil_last_step_timing(self._h, C.byref(ms), C.byref(n)))
         return ms.value, n.value
+
+    def kernel_info(self) -> str:
+        """``lh_soil_kernel_info``: the kernel variant, launch shape and strategy the next step call will use."""
+        buf = C.create_string_buffer(512)
+        self._check(self.lib.soil_kernel_info(self._h, buf, 512))
+        return buf.value.decode()
 
     def device_ptr(self, field: int):
         p = _vp()

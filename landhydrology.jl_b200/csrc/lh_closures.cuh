@@ -160,11 +160,11 @@ __device__ __forceinline__ void lh_water_closures(const P& p, const double* __re
     if (VG2) {
         // ---- n = 2: square roots only.  One rsqrt(S) gives both sqrt(S) = S r and 1/S = r r.
         const double rS = lh_rsqrt(S_K);
-        const double sw = lh_sqrt((1.0 - S_eff) * (1.0 + S_eff));            // (1 - S^(1/m))^m
+        const double sw = lh_sqrt_fast((1.0 - S_eff) * (1.0 + S_eff));       // (1 - S^(1/m))^m
         double inv_S_eff = rS * rS, swK = sw;
         if (icy) {
             inv_S_eff = lh_rcp(S_eff);
-            swK = lh_sqrt((1.0 - S_K) * (1.0 + S_K));
+            swK = lh_sqrt_fast((1.0 - S_K) * (1.0 + S_K));
         }
         psi_unsat = p.neg_inv_alpha * (sw * inv_S_eff);                      // :196-200
         const double t = (S_K * S_K) * lh_rcp(1.0 + swK);                    // 1 - (1 - S^(1/m))^m

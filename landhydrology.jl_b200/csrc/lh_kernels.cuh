@@ -51,6 +51,15 @@ struct LhKernelArgs {
     int32_t Lc;            // layers per thread (vertical chunk)
     int32_t W;             // chunks per column = blockDim.y
     int32_t top_e_kind, top_h_kind, bot_e_kind, bot_h_kind;
+    // Stage-to-stage chaining (one-stage launches).  Block j of a stage launch touches only its own column groups, and
+    // so does block j of the next launch (same launch shape), so the only true dependency between consecutive stage
+    // launches is block j -> block j.  Every block publishes chain_flags[j] = chain_set when its stores are visible
+    // (fence + release store); with chain_wait != 0 the next launch's block j waits for chain_flags[j] == chain_wait
+    // INSTEAD of griddepcontrol.wait (whole previous grid completed and flushed): the next stage starts filling the SM
+    // slots the previous one frees during its last wave, and the per-launch tail (~half a block time per SM, 8 % of a
+    // 131 072-column shard's launch) is paid once per call instead of once per stage.  chain_wait == 0: full dependency.
+    int32_t* chain_flags;  // [nblocks] or NULL
+    int32_t chain_wait, chain_set;
     // persistent SSPRK33 launches only
     int64_t nsteps;
     const double* bc_dev;  // NULL (io.bcv for every stage) or nsteps * 3 * 4 boundary values in device memory

@@ -98,6 +98,16 @@ LH_DEV double lh_sqrt(double x)
     return lh_fma(lh_fma(-g, g, x), 0.5 * r, g);       // one correction of g = x r: <= 1 ulp
 }
 
+// sqrt(x) = x rsqrt(x) without the final correction (~1.5 ulp, 3 fp64 operations fewer): for the square roots whose
+// result is multiplied into a product that is itself a few ulp from the literal form.  Same zero / negative handling.
+LH_DEV double lh_sqrt_fast(double x)
+{
+    const double s0 = lh_rsqrt_seed(x);
+    const int32_t hi = lh_hi(s0);
+    const double r0 = lh_mk(((uint32_t)hi > 0x7fe00000u && hi > 0) ? 0x7fe00000 : hi, lh_lo(s0));
+    return x * lh_rsqrt_refine(x, r0);
+}
+
 // ---------------------------------------------------------------------------------------------------
 // Every transcendental on the soil path is a power x^c, so base 2 serves everywhere and saves the ln 2
 // scalings of a natural log/exp pair.  Both functions are table driven; `tab` points at the LH_TAB_DOUBLES

@@ -62,6 +62,9 @@ NcclApi& nccl()
 thread_local char g_create_err[256] = "";
 }  // namespace
 
+struct lh_soil_ctx;
+static bool use_persistent(const lh_soil_ctx* c);
+
 // ------------------------------------------------------------------------------------------------
 // Context
 // ------------------------------------------------------------------------------------------------
@@ -96,6 +99,11 @@ struct lh_soil_ctx {
     int64_t fused_nblocks = 0;
     bool budget_fresh = false;                   // fused_partials describe the current state U
     bool external_writes = false;                // lh_soil_device_ptr handed out U: never trust the fused sums
+    int32_t* chain_dev = nullptr;                // per-block completion flags of the stage launches (LhKernelArgs::chain_flags)
+    int64_t chain_cap = 0;                       // blocks the flag array holds
+    int32_t chain_seq = 0;                       // value the last stage launch published; only ever grows, so that a flag
+                                                 // left over from an earlier launch can never equal a value waited for
+    bool chain_break = true;                     // the next stage launch takes the whole-grid dependency (first launch, new shape)
     double* bc_dev = nullptr;                    // boundary-value table of a persistent launch
     int64_t bc_dev_steps = 0;
     unsigned long long* nonfinite_dev = nullptr;
@@ -237,6 +245,7 @@ void free_all(lh_soil_ctx* c)
     if (c->partials) cudaFree(c->partials);
     if (c->budget_dev) cudaFree(c->budget_dev);
     if (c->bc_dev) cudaFree(c->bc_dev);
+    if (c->chain_dev) cudaFree(c->chain_dev);
     if (c->fused_partials) cudaFree(c->fused_partials);
     if (c->colp_dev) cudaFree(c->colp_dev);
     if (c->pow_tab_dev) cudaFree(c->pow_tab_dev);
@@ -398,6 +407,17 @@ void update_kernel_flags(lh_soil_ctx* c)
                       (het ? LH_FLAG_HET : 0);
     c->shape = lh_choose_shape(c->model, c->ncol_pad, c->nlayer, c->sm_count, het);   // the HET variants have a smaller warp budget
     c->budget_fresh = false;
+    // The block -> column-group map may have changed: the next stage launch takes the full grid dependency.  (The flags
+    // keep their values; a later chained launch waits for the value ITS predecessor publishes.)
+    c->chain_break = true;
+    if (c->chain_cap < c->shape.nblocks) {
+        if (c->chain_dev) { cudaStreamSynchronize(c->stream); cudaFree(c->chain_dev); }
+        c->chain_dev = nullptr;
+        c->chain_cap = 0;
+        if (cudaMalloc(&c->chain_dev, (size_t)c->shape.nblocks * sizeof(int32_t)) == cudaSuccess &&
+            cudaMemset(c->chain_dev, 0, (size_t)c->shape.nblocks * sizeof(int32_t)) == cudaSuccess) c->chain_cap = c->shape.nblocks;
+        else { if (c->chain_dev) cudaFree(c->chain_dev); c->chain_dev = nullptr; }     // stage launches then never chain
+    }
     if (c->fused_nblocks < c->shape.nblocks) {        // per-block budget sums of the last-stage launches
         if (c->fused_partials) cudaFree(c->fused_partials);
         c->fused_partials = nullptr;
@@ -456,6 +476,29 @@ void fill_args(lh_soil_ctx* c, int stage, double dt, LhKernelArgs& a)
     a.io.budget = 0;
     a.nsteps = 0;
     a.bc_dev = nullptr;
+    a.chain_flags = nullptr;
+    a.chain_wait = a.chain_set = 0;
+}
+
+// Every one-stage launch goes through here: block j waits for block j of the previous stage launch of this ctx (same
+// shape since then, see update_kernel_flags) instead of the whole previous grid, and publishes its own completion.
+// Anything else enqueued on the stream in between (copies, transposes, budget kernels: none of them triggers dependents
+// early) is fully ordered before the launch by the stream itself.
+cudaError_t launch_chained(lh_soil_ctx* c, int stage, LhKernelArgs& a)
+{
+    if (c->chain_dev && !(c->cfg.flags & LH_FLAG_NO_CHAIN)) {
+        a.chain_flags = c->chain_dev;
+        if (c->chain_seq == 0x7fffffff) {                // (2^31 launches: start over behind a full synchronisation)
+            cudaStreamSynchronize(c->stream);
+            cudaMemset(c->chain_dev, 0, (size_t)c->chain_cap * sizeof(int32_t));
+            c->chain_seq = 0;
+            c->chain_break = true;
+        }
+        a.chain_wait = c->chain_break ? 0 : c->chain_seq;       // 0: griddepcontrol.wait
+        a.chain_set = ++c->chain_seq;
+        c->chain_break = false;
+    }
+    return lh_launch_stage(c->model, stage, c->kernel_flags, a, c->shape, c->stream);
 }
 
 int32_t check_finite(lh_soil_ctx* c)
@@ -469,6 +512,19 @@ int32_t check_finite(lh_soil_ctx* c)
     LH_CUDA(c, cudaStreamSynchronize(c->stream));
     if (cnt) return fail(c, LH_ERR_NONFINITE, "%llu non-finite state values (the reference raises DomainError)", cnt);
     return LH_OK;
+}
+
+// HBM bytes per cell and SSPRK33 step the selected kernel variant moves (per-stage launches): every stage reads the
+// stage input, stages 2 and 3 also u^n, every stage writes the prognostic fields; θ_i is read only by the ICE variants,
+// the prescribed T only by the Richards variants with the viscosity factor on.
+int lh_bytes_on_wire(const lh_soil_ctx* c)
+{
+    const int nprog = c->model == LH_MODEL_COUPLED ? 2 : 1;
+    int per_stage_in = nprog;                                        // stage input of the prognostic fields
+    if (c->model == LH_MODEL_HEAT) per_stage_in += 1;                // prescribed ϑ_l
+    if (c->kernel_flags & LH_FLAG_ICE) per_stage_in += 1;            // θ_i
+    if (c->model == LH_MODEL_RICHARDS && (c->kernel_flags & LH_FLAG_GEN)) per_stage_in += 1;   // prescribed T row
+    return 8 * (3 * per_stage_in + 2 * nprog + 3 * nprog);
 }
 
 }  // namespace
@@ -680,7 +736,7 @@ static int32_t launch_stage(lh_soil_ctx* c, int stage, double dt)
 {
     LhKernelArgs a;
     fill_args(c, stage, dt, a);
-    LH_CUDA(c, lh_launch_stage(c->model, stage, c->kernel_flags, a, c->shape, c->stream));
+    LH_CUDA(c, launch_chained(c, stage, a));
     return LH_OK;
 }
 
@@ -882,7 +938,7 @@ int32_t lh_soil_step(lh_soil_ctx* c, const lh_soil_stepper* sp, double t, double
                 a.io.sa = sp->a[i]; a.io.sb = sp->b[i];
                 a.io.first2n = i == 0;
             }
-            LH_CUDA(c, lh_launch_stage(c->model, stage, c->kernel_flags, a, c->shape, c->stream));
+            LH_CUDA(c, launch_chained(c, stage, a));
         }
     }
     LH_CUDA(c, cudaEventRecord(c->ev_stop, c->stream));
@@ -970,6 +1026,23 @@ int32_t lh_soil_last_step_timing(lh_soil_ctx* c, double* ms_out, int64_t* launch
     LH_CUDA(c, cudaEventElapsedTime(&ms, c->ev_start, c->ev_stop));
     if (ms_out) *ms_out = (double)ms;
     if (launches_out) *launches_out = c->last_launches;
+    return LH_OK;
+}
+
+int32_t lh_soil_kernel_info(lh_soil_ctx* c, char* buf, int64_t cap)
+{
+    if (!c || !buf || cap < 1) return LH_ERR_INVALID_ARG;
+    const int f = c->kernel_flags;
+    const bool persistent = use_persistent(c);
+    snprintf(buf, (size_t)cap,
+             "%s<MODEL=%d,%sFLAGS=%d:%s%s%s%s> block=(32,W=%d,G=%d) layers/thread=%d blocks=%lld smem=%zu waves=%.2f "
+             "launch=%s chain=%s bytes/cell-step(on wire)=%d",
+             persistent ? "lh_soil_ssprk33_persistent_kernel" : "lh_soil_stage_kernel", c->model, persistent ? "" : "STAGE=1|2|3,", f,
+             (f & LH_FLAG_ICE) ? "ICE" : "!ICE", (f & LH_FLAG_GEN) ? "+GEN" : "", (f & LH_FLAG_VG2) ? "+VG2" : "", (f & LH_FLAG_HET) ? "+HET" : "",
+             c->shape.W, c->shape.G, c->shape.Lc, (long long)c->shape.nblocks, c->shape.smem_bytes, c->shape.waves,
+             persistent ? "persistent(1 per call)" : "per-stage(3 per step)",
+             (!persistent && c->chain_dev && !(c->cfg.flags & LH_FLAG_NO_CHAIN)) ? "block-to-block" : "whole-grid",
+             lh_bytes_on_wire(c));
     return LH_OK;
 }
 

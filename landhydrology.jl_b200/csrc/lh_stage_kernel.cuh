@@ -155,7 +155,7 @@ constexpr int LH_RED_DOUBLES = 2 * LH_WARPS_PER_SM;      // per-warp budget part
 template <int MODEL> struct Slot { static constexpr int NQv = NQ<MODEL>::value; static constexpr int doubles = (2 * NQv + 6) * 32; };
 
 // 16-byte cp.async that bypasses L1 (.cg): global -> shared without allocating an L1 line while in flight.
-__device__ __forceinline__ void lh_cp16(uint32_t dst, const double* src, bool pred)
+__device__ __forceinline__ void lh_cp16(uint32_t dst, const void* src, bool pred)
 {
     asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %2, 0;\n\t@p cp.async.cg.shared.global [%0], [%1], 16;\n\t}"
                  ::"r"(dst), "l"(src), "r"((int)pred) : "memory");
@@ -236,23 +236,24 @@ __device__ __forceinline__ void lh_stage_body_impl(const LhKernelArgs& A, const 
     }
     const bool upper = lane >= 16;
     const int sub = lane & 15;
-    const double* sp[NG];                     // this lane's source (column pair) of copy instruction g, layer 0
+    // Running pointers, advanced by one layer (stride_b bytes) per request: a 64-bit add each, instead of rebuilding
+    // base + 8 * (column + layer * stride) for every copy (6 integer instructions per copy in the first build).
+    const int64_t stride_b = stride * (int64_t)sizeof(double);
+    const char* sp[NG];                       // this lane's source (column pair) of copy instruction g, next layer to request
     uint32_t doff[NG];                        // and its destination offset inside a ring cell
     bool pred[NG];
 #pragma unroll
     for (int gi = 0; gi < NG; ++gi) {
         const int lo = 2 * gi, hi = 2 * gi + 1 < NROWS ? 2 * gi + 1 : 2 * gi;
-        sp[gi] = (upper ? rowptr[hi] : rowptr[lo]) + col0 + 2 * sub;
+        sp[gi] = reinterpret_cast<const char*>((upper ? rowptr[hi] : rowptr[lo]) + col0 + 2 * sub + (int64_t)a * stride);
         doff[gi] = (uint32_t)((upper ? rowpos[hi] : rowpos[lo]) * 256 + sub * 16);
         pred[gi] = !upper || 2 * gi + 1 < NROWS;
     }
     const uint32_t ring_w = (uint32_t)__cvta_generic_to_shared(warp_base + Slot<MODEL>::doubles);   // warp's ring, lane 0
-    int64_t o_ld = (int64_t)a * stride;       // element offset of the next cell to request
-    auto issue = [&](uint32_t d, int i) {     // request cell i (whose offset o_ld is) into the ring cell at d (lane-0 address)
+    auto issue = [&](uint32_t d, int i) {     // request cell i (the next layer of sp[]) into the ring cell at d (lane-0 address)
         if (i < b) {
 #pragma unroll
-            for (int gi = 0; gi < NG; ++gi) lh_cp16(d + doff[gi], sp[gi] + o_ld, pred[gi]);
-            o_ld += stride;
+            for (int gi = 0; gi < NG; ++gi) { lh_cp16(d + doff[gi], sp[gi], pred[gi]); sp[gi] += stride_b; }
         }
         asm volatile("cp.async.commit_group;" ::: "memory");
     };
@@ -290,34 +291,38 @@ __device__ __forceinline__ void lh_stage_body_impl(const LhKernelArgs& A, const 
         return o;
     };
     const double cdt = STAGE == 6 ? io.dt /* the caller passes cdt itself */ : STAGE == 0 ? -p.inv_dz : (STAGE == 3 ? -2.0 * (io.dt * p.inv_dz) : STAGE == 4 ? -((io.sg * io.dt) * p.inv_dz) : -(io.dt * p.inv_dz));
-    double* o2th = io.out2_th + col;     // 2N stages: the residual register r
-    double* o2re = io.out2_re + col;
     // The last SSPRK33 stage writes the new state: its values are summed on the way out (water and energy budgets of this
     // thread's cells), so that lh_soil_budgets after a step needs no pass over the state.
     constexpr bool BUDGET = STAGE == 3 || STAGE == 6;
     const bool budget = BUDGET && (STAGE == 3 || io.budget) && A.budget_partials != nullptr;     // block-uniform
     double bud_w = 0.0, bud_e = 0.0;
-    auto store_cell = [&](int64_t o, const Base& base, const Flux& lo, const Flux& hi) {
+    // Output addresses are byte offsets from the column's layer-0 element; the layer loop advances ONE running offset
+    // per trip (write_next) instead of rebuilding 8 * (column + layer * stride) per store.
+    char* const oth_c = reinterpret_cast<char*>(oth);
+    char* const ore_c = reinterpret_cast<char*>(ore);
+    char* const o2th_c = reinterpret_cast<char*>(io.out2_th + col);     // 2N stages: the residual register r
+    char* const o2re_c = reinterpret_cast<char*>(io.out2_re + col);
+    auto store_cell = [&](int64_t ob, const Base& base, const Flux& lo, const Flux& hi) {
         if constexpr (MODEL != 1) {
             const double v = stage_out<STAGE>(base.th, hi.w - lo.w, cdt, io.sg);
-            if constexpr (STAGE == 5) { o2th[o] = v; oth[o] = fma(io.sb, v, base.th2); }
-            else oth[o] = v;
+            if constexpr (STAGE == 5) { *reinterpret_cast<double*>(o2th_c + ob) = v; *reinterpret_cast<double*>(oth_c + ob) = fma(io.sb, v, base.th2); }
+            else *reinterpret_cast<double*>(oth_c + ob) = v;
             if constexpr (BUDGET) bud_w += v;
         }
         if constexpr (MODEL != 0) {
             const double v = stage_out<STAGE>(base.re, hi.e - lo.e, cdt, io.sg);
-            if constexpr (STAGE == 5) { o2re[o] = v; ore[o] = fma(io.sb, v, base.re2); }
-            else ore[o] = v;
+            if constexpr (STAGE == 5) { *reinterpret_cast<double*>(o2re_c + ob) = v; *reinterpret_cast<double*>(ore_c + ob) = fma(io.sb, v, base.re2); }
+            else *reinterpret_cast<double*>(ore_c + ob) = v;
             if constexpr (BUDGET) bud_e += v;
         }
     };
-    int64_t o_st = (int64_t)(a + 1) * stride;   // element offset of the next cell to store (cell a is stored last)
+    int64_t o_st = (int64_t)(a + 1) * stride_b;   // byte offset of the next cell to store (cell a is stored last)
     auto write_next = [&](const Base& base, const Flux& lo, const Flux& hi) {
         store_cell(o_st, base, lo, hi);
-        o_st += stride;
+        o_st += stride_b;
     };
     auto write_at = [&](int i, const Base& base, const Flux& lo, const Flux& hi) {
-        store_cell((int64_t)i * stride, base, lo, hi);
+        store_cell((int64_t)i * stride_b, base, lo, hi);
     };
 
     Q<MODEL> prev;            // closures of the last evaluated cell
@@ -376,9 +381,9 @@ __device__ __forceinline__ void lh_stage_body_impl(const LhKernelArgs& A, const 
             c.K = 0.0; c.psi = 0.0; c.kappa = 0.0; c.T = 288.0; c.dT = 0.0;
             if constexpr (MODEL != 1) { c.K = first.K; c.psi = first.psi; }
             if constexpr (MODEL != 0) c.T = first.T;
-            else if (need_T) c.T = pT[0];
+            else if (need_T) c.T = __ldcg(pT);
             F_lo = boundary_flux<MODEL, FLAGS>(p, tab, A.bot_e_kind, A.bot_h_kind, io.bcv[LH_BCV_BOTTOM_ENERGY],
-                                               io.bcv[LH_BCV_BOTTOM_HYDROLOGY], true, pth[0], ICE ? pti[0] : 0.0, c);
+                                               io.bcv[LH_BCV_BOTTOM_HYDROLOGY], true, __ldcg(pth), ICE ? __ldcg(pti) : 0.0, c);
         } else {
             F_lo = face_flux<MODEL>(p, q_load<MODEL>(sm_top - (Slot<MODEL>::doubles + RING_DOUBLES)), first);   // top of chunk w-1
         }
@@ -388,9 +393,9 @@ __device__ __forceinline__ void lh_stage_body_impl(const LhKernelArgs& A, const 
             c.K = 0.0; c.psi = 0.0; c.kappa = 0.0; c.T = 288.0; c.dT = 0.0;
             if constexpr (MODEL != 1) { c.K = prev.K; c.psi = prev.psi; }
             if constexpr (MODEL != 0) c.T = prev.T;
-            else if (need_T) c.T = pT[o];
+            else if (need_T) c.T = __ldcg(pT + o);
             F_hi = boundary_flux<MODEL, FLAGS>(p, tab, A.top_e_kind, A.top_h_kind, io.bcv[LH_BCV_TOP_ENERGY],
-                                               io.bcv[LH_BCV_TOP_HYDROLOGY], false, pth[o], ICE ? pti[o] : 0.0, c);
+                                               io.bcv[LH_BCV_TOP_HYDROLOGY], false, __ldcg(pth + o), ICE ? __ldcg(pti + o) : 0.0, c);
         } else {
             F_hi = face_flux<MODEL>(p, prev, q_load<MODEL>(sm_bot + (Slot<MODEL>::doubles + RING_DOUBLES)));    // bot of chunk w+1
         }
@@ -475,12 +480,31 @@ lh_soil_stage_kernel(const __grid_constant__ LhKernelArgs A)
     // behind the previous stage's tail — what matters when a launch is only ~80 us (column shards at 8 GPUs).
     asm volatile("griddepcontrol.launch_dependents;");
 #endif
-    lh_stage_tables(A.p, A.pow_tab, smem, (threadIdx.z * blockDim.y + threadIdx.y) * 32 + threadIdx.x, blockDim.x * blockDim.y * blockDim.z);
+    const int tid = (threadIdx.z * blockDim.y + threadIdx.y) * 32 + threadIdx.x;
+    lh_stage_tables(A.p, A.pow_tab, smem, tid, blockDim.x * blockDim.y * blockDim.z);
+    if (A.chain_flags != nullptr && A.chain_wait != 0) {
+        // this block's predecessor: block blockIdx.x of the previous stage launch (same columns); see LhKernelArgs
+        if (tid == 0) {
+            const int32_t* f = A.chain_flags + blockIdx.x;
+            int32_t v;
+            for (;;) {
+                asm volatile("ld.acquire.gpu.global.s32 %0, [%1];" : "=r"(v) : "l"(f) : "memory");
+                if (v == A.chain_wait) break;
+                __nanosleep(64);
+            }
+        }
+    } else {
 #if LH_PDL
-    asm volatile("griddepcontrol.wait;" ::: "memory");
+        asm volatile("griddepcontrol.wait;" ::: "memory");
 #endif
+    }
     __syncthreads();
     lh_stage_body<MODEL, STAGE, FLAGS>(A, A.io, smem);
+    if (A.chain_flags != nullptr) {
+        __threadfence();                  // every thread's stores are visible device-wide before the flag is
+        __syncthreads();
+        if (tid == 0) asm volatile("st.release.gpu.global.s32 [%0], %1;" ::"l"(A.chain_flags + blockIdx.x), "r"(A.chain_set) : "memory");
+    }
 }
 
 // A.nsteps whole SSPRK33 steps in one launch.  A block keeps its column groups for all 3 nsteps stages: columns

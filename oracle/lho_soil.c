@@ -920,6 +920,13 @@ int32_t lho_soil_set_column_params(lho_soil_ctx* c, const double* nu, const doub
 
 int32_t lho_soil_sync(lho_soil_ctx* c) { (void)c; return LH_OK; }
 
+int32_t lho_soil_kernel_info(lho_soil_ctx* c, char* buf, int64_t cap)
+{
+    if (!c || !buf || cap < 1) return LH_ERR_INVALID_ARG;
+    snprintf(buf, (size_t)cap, "oracle: CPU restatement of the reference path (no kernels), %d OpenMP thread(s)", lho_soil_num_threads());
+    return LH_OK;
+}
+
 /* libm versions of the functions the device library hand-writes */
 int32_t lho_soil_eval_math(lho_soil_ctx* c, int32_t fn, const double* x, double* y, int64_t n)
 {

@@ -45,6 +45,7 @@
 #define lh_soil_comm_unique_id    lho_soil_comm_unique_id
 #define lh_soil_comm_init         lho_soil_comm_init
 #define lh_soil_budgets_allreduce lho_soil_budgets_allreduce
+#define lh_soil_kernel_info       lho_soil_kernel_info
 
 #include "../include/lh_soil.h"
 
