@@ -224,6 +224,53 @@ int32_t lh_soil_stage_ssprk33(lh_soil_ctx* ctx, int32_t stage, double dt);
 int32_t lh_soil_step_ssprk33(lh_soil_ctx* ctx, double t, double dt, int64_t nsteps,
                              const double* bc_table);
 
+/* Time-dependent prescribed profiles (make_update_aux, right_hand_side.jl:54-81: T(z,t) of PrescribedTemperatureModel,
+ * ϑ_l(z,t) / θ_i(z,t) of PrescribedHydrologyModel) without a host round trip per stage: the host evaluates the profile
+ * closures AHEAD for the stage times of the coming steps and uploads them as `nrows` rows of nlayer doubles; every stage
+ * launch of lh_soil_stage_ssprk33 / lh_soil_step_ssprk33 / lh_soil_step / lh_soil_run then consumes the next row
+ * (row r = r-th stage launch after this call; SSPRK33: step s, stage i -> row 3 s + i, times t, t + dt, t + dt/2),
+ * broadcasting it to every column on the device before the launch.  table == NULL removes the table (the field keeps
+ * its last values).  Running out of rows is LH_ERR_STATE.                                                            */
+int32_t lh_soil_set_aux_table(lh_soil_ctx* ctx, int32_t field, const double* table, int64_t nrows);
+
+/* ---- run!(simulation) with saveat and per-step diagnostics in ONE call ------------------------------------------
+ * Replaces the solve! loop behind run! (simulation.jl:86-87) together with the `saveat` / callback keywords every
+ * reference test passes (simulation.jl:64-70; richards_equation.jl:66-78, coupled.jl:94-98): nsteps SSPRK33 steps,
+ * the budgets every `budget_every` steps and a snapshot of the listed fields every `save_every` steps (plus the initial
+ * state with save_first, DiffEq's save_start).  Snapshots are copied device-to-device on the compute stream, which goes
+ * on stepping at once; layout transform and PCIe transfer run on the ctx's copy stream, two snapshots deep, so a
+ * snapshot costs the run nothing unless PCIe is the bottleneck.  Budgets arrive through a pinned ring, 16 bytes per
+ * budget point.  save_out should be pinned host memory (lh_soil_alloc_host) for the copies to be asynchronous.
+ * Snapshot s, field save_fields[k], column c, layer l lands at
+ *     save_out[s * snapshot_stride + k * field_stride + c * col_stride + l * layer_stride]
+ * with (col_stride, layer_stride) = (nlayer, 1) (the reference's parent(Y.soil) layout) or (1, >= ncol).
+ * The call returns when every snapshot and budget has arrived.                                                       */
+typedef struct lh_soil_run_opts {
+    int32_t struct_size;          /* sizeof(lh_soil_run_opts)                                        */
+    int32_t save_first;           /* != 0: snapshot 0 is the state before the first step             */
+    const double* bc_table;       /* NULL or nsteps*3*4 boundary values (as lh_soil_step_ssprk33)    */
+    int64_t budget_every;         /* 0: no budgets; k: after steps k, 2k, ...                        */
+    double* budgets_out;          /* [nsteps / budget_every][2]                                      */
+    int64_t save_every;           /* 0: no periodic snapshots; k: after steps k, 2k, ...             */
+    int32_t nsave_fields;
+    int32_t save_fields[LH_NUM_FIELDS];
+    int32_t reserved;
+    double* save_out;
+    int64_t snapshot_stride, field_stride, col_stride, layer_stride;   /* in elements                */
+} lh_soil_run_opts;
+int32_t lh_soil_run(lh_soil_ctx* ctx, double t0, double dt, int64_t nsteps, const lh_soil_run_opts* opts);
+
+/* Checkpoint / restart: everything a ctx needs to continue a run bit for bit (fields in device layout, current boundary
+ * values, position in the prescribed-profile tables).  Parameters, BC kinds and per-column parameters are part of the
+ * configuration, not of the checkpoint: load into a ctx created (and configured) the same way.                       */
+int64_t lh_soil_checkpoint_bytes(const lh_soil_ctx* ctx);
+int32_t lh_soil_checkpoint_save(lh_soil_ctx* ctx, void* buf, int64_t capacity);
+int32_t lh_soil_checkpoint_load(lh_soil_ctx* ctx, const void* buf, int64_t bytes);
+
+/* Pinned (page-locked) host memory for state buffers: transfers from / to it are asynchronous and run at PCIe speed. */
+int32_t lh_soil_alloc_host(int64_t bytes, void** out);
+int32_t lh_soil_free_host(void* p);
+
 /* ---- other explicit steppers on the same fused kernel ----------------------------------
  * The reference's test driver also imports SSPRK73 and CarpenterKennedy2N54 next to SSPRK33
  * (test/runtests.jl:5-10); only SSPRK33 is ever used.  The fused RHS+stage kernel generalises by
@@ -268,6 +315,13 @@ int32_t lh_soil_budgets(lh_soil_ctx* ctx, double out[2]);
 /* Right after lh_soil_step_ssprk33 / lh_soil_stage_ssprk33(3) this costs one small reduction: the last stage has
  * already summed, per thread block, the values it wrote.  After an upload or a generic stepper it is one pass over the
  * state.  Both are fixed-shape trees (bitwise reproducible for a given shard).                                     */
+/* Non-blocking form: enqueues the reduction and a 16-byte copy into a pinned slot of the ctx behind whatever is already
+ * on the ctx stream and returns a ticket at once; lh_soil_budgets_wait blocks until THAT result has arrived (not until the
+ * stream is idle).  A host that reads the budgets after every step (the reference's callbacks do, simulation.jl:64-70)
+ * can enqueue step n+1 before it collects the budgets of step n, so the stream never drains.  At most 8 tickets may be
+ * outstanding (LH_ERR_STATE beyond that); results are identical to lh_soil_budgets.                                  */
+int32_t lh_soil_budgets_async(lh_soil_ctx* ctx, int64_t* ticket_out);
+int32_t lh_soil_budgets_wait(lh_soil_ctx* ctx, int64_t ticket, double out[2]);
 /* Column-integrated boundary fluxes of the last rhs/stage call are not stored; conservation
  * tests use budgets before/after a step.                                                    */
 

@@ -32,6 +32,7 @@ LH_ERR_STATE = -8
 LH_MODEL_RICHARDS, LH_MODEL_HEAT, LH_MODEL_COUPLED = 0, 1, 2
 LH_BC_NONE, LH_BC_FLUX, LH_BC_DIRICHLET, LH_BC_FREE_DRAINAGE = 0, 1, 2, 3
 LH_FIELD_THETA_L, LH_FIELD_THETA_I, LH_FIELD_RHO_E_INT, LH_FIELD_T = 0, 1, 2, 3
+LH_NUM_FIELDS = 4
 LH_DIAG_K, LH_DIAG_PSI, LH_DIAG_KAPPA, LH_DIAG_T = 0, 1, 2, 3
 LH_BCV_TOP_ENERGY, LH_BCV_TOP_HYDROLOGY, LH_BCV_BOTTOM_ENERGY, LH_BCV_BOTTOM_HYDROLOGY = 0, 1, 2, 3
 LH_FLAG_CHECK_FINITE = 1
@@ -121,6 +122,21 @@ class lh_soil_stepper(C.Structure):
 _dp = C.POINTER(C.c_double)
 _vp = C.c_void_p
 
+
+class lh_soil_run_opts(C.Structure):
+    _fields_ = [
+        ("struct_size", C.c_int32), ("save_first", C.c_int32), ("bc_table", _dp),
+        ("budget_every", C.c_int64), ("budgets_out", _dp), ("save_every", C.c_int64),
+        ("nsave_fields", C.c_int32), ("save_fields", C.c_int32 * LH_NUM_FIELDS), ("reserved", C.c_int32),
+        ("save_out", _dp), ("snapshot_stride", C.c_int64), ("field_stride", C.c_int64),
+        ("col_stride", C.c_int64), ("layer_stride", C.c_int64),
+    ]
+
+    def __init__(self, *a, **kw):
+        super().__init__(*a, **kw)
+        self.struct_size = C.sizeof(lh_soil_run_opts)
+
+
 # name -> (argtypes, restype); every entry is declared in include/lh_soil.h
 _SIGNATURES = {
     "soil_abi_version": ([], C.c_int32),
@@ -140,6 +156,15 @@ _SIGNATURES = {
     "soil_stepper_named": ([C.c_int32, C.POINTER(lh_soil_stepper)], C.c_int32),
     "soil_step": ([_vp, C.POINTER(lh_soil_stepper), C.c_double, C.c_double, C.c_int64, _dp], C.c_int32),
     "soil_budgets": ([_vp, _dp], C.c_int32),
+    "soil_set_aux_table": ([_vp, C.c_int32, _dp, C.c_int64], C.c_int32),
+    "soil_run": ([_vp, C.c_double, C.c_double, C.c_int64, C.POINTER(lh_soil_run_opts)], C.c_int32),
+    "soil_checkpoint_bytes": ([_vp], C.c_int64),
+    "soil_checkpoint_save": ([_vp, _vp, C.c_int64], C.c_int32),
+    "soil_checkpoint_load": ([_vp, _vp, C.c_int64], C.c_int32),
+    "soil_alloc_host": ([C.c_int64, C.POINTER(_vp)], C.c_int32),
+    "soil_free_host": ([_vp], C.c_int32),
+    "soil_budgets_async": ([_vp, C.POINTER(C.c_int64)], C.c_int32),
+    "soil_budgets_wait": ([_vp, C.c_int64, _dp], C.c_int32),
     "soil_diagnostic": ([_vp, C.c_int32, _dp, C.c_int64, C.c_int64], C.c_int32),
     "soil_sync": ([_vp], C.c_int32),
     "soil_eval_math": ([_vp, C.c_int32, _dp, _dp, C.c_int64], C.c_int32),
@@ -361,6 +386,79 @@ class SoilContext:
     def budgets(self) -> np.ndarray:
         out = np.empty(2, dtype=np.float64)
         self._check(self.lib.soil_budgets(self._h, _as_double_ptr(out)))
+        return out
+
+    def set_aux_table(self, field: int, table: Optional[np.ndarray]):
+        """``lh_soil_set_aux_table``: rows of a prescribed profile for the coming stage launches ([nrows, nlayer])."""
+        if table is None:
+            self._check(self.lib.soil_set_aux_table(self._h, int(field), None, 0))
+            return
+        table = np.ascontiguousarray(table, dtype=np.float64)
+        if table.ndim != 2 or table.shape[1] != self.nlayer:
+            raise ValueError(f"aux table must have shape (nrows, {self.nlayer})")
+        self._check(self.lib.soil_set_aux_table(self._h, int(field), _as_double_ptr(table), table.shape[0]))
+
+    def run(self, t0: float, dt: float, nsteps: int, *, bc_table: Optional[np.ndarray] = None, budget_every: int = 0,
+            save_every: int = 0, save_first: bool = False, save_fields: Sequence[int] = (), save_out: Optional[np.ndarray] = None):
+        """``lh_soil_run``: nsteps SSPRK33 steps with budgets every ``budget_every`` and snapshots every ``save_every`` steps
+        in one call.  Returns ``(budgets [nb, 2] or None, snapshots [ns, nfields, ncol, nlayer] or None)``; ``save_out``
+        may be a preallocated (ideally pinned) array of that shape."""
+        o = lh_soil_run_opts()
+        keep = []
+        if bc_table is not None:
+            bc_table = np.ascontiguousarray(bc_table, dtype=np.float64)
+            if bc_table.size != nsteps * 12:
+                raise ValueError("bc_table must hold nsteps*3*4 doubles")
+            o.bc_table = _as_double_ptr(bc_table)
+            keep.append(bc_table)
+        budgets = None
+        if budget_every > 0:
+            budgets = np.zeros((nsteps // budget_every, 2), dtype=np.float64)
+            o.budget_every = int(budget_every)
+            o.budgets_out = _as_double_ptr(budgets)
+        snaps = None
+        fields = [int(f) for f in save_fields]
+        if (save_every > 0 or save_first) and fields:
+            ns = (nsteps // save_every if save_every > 0 else 0) + (1 if save_first else 0)
+            shape = (ns, len(fields), self.ncol, self.nlayer)
+            if save_out is not None:
+                if save_out.shape != shape or save_out.dtype != np.float64 or not save_out.flags.c_contiguous:
+                    raise ValueError(f"save_out must be a C-contiguous float64 array of shape {shape}")
+                snaps = save_out
+            else:
+                snaps = np.empty(shape, dtype=np.float64)
+            o.save_every = int(save_every)
+            o.save_first = 1 if save_first else 0
+            o.nsave_fields = len(fields)
+            for k, f in enumerate(fields):
+                o.save_fields[k] = f
+            o.save_out = _as_double_ptr(snaps)
+            o.snapshot_stride = len(fields) * self.ncol * self.nlayer
+            o.field_stride = self.ncol * self.nlayer
+            o.col_stride, o.layer_stride = self.nlayer, 1
+        self._check(self.lib.soil_run(self._h, float(t0), float(dt), int(nsteps), C.byref(o)))
+        return budgets, snaps
+
+    def checkpoint(self) -> np.ndarray:
+        """``lh_soil_checkpoint_save`` into a fresh byte array."""
+        n = int(self.lib.soil_checkpoint_bytes(self._h))
+        buf = np.empty(n, dtype=np.uint8)
+        self._check(self.lib.soil_checkpoint_save(self._h, buf.ctypes.data_as(_vp), n))
+        return buf
+
+    def restore(self, buf: np.ndarray):
+        buf = np.ascontiguousarray(buf, dtype=np.uint8)
+        self._check(self.lib.soil_checkpoint_load(self._h, buf.ctypes.data_as(_vp), buf.size))
+
+    def budgets_async(self) -> int:
+        """``lh_soil_budgets_async``: enqueue the budget read behind the work already on the stream; returns a ticket."""
+        t = C.c_int64()
+        self._check(self.lib.soil_budgets_async(self._h, C.byref(t)))
+        return t.value
+
+    def budgets_wait(self, ticket: int) -> np.ndarray:
+        out = np.empty(2, dtype=np.float64)
+        self._check(self.lib.soil_budgets_wait(self._h, int(ticket), _as_double_ptr(out)))
         return out
 
     def budgets_allreduce(self) -> np.ndarray:

@@ -143,11 +143,13 @@ __device__ __forceinline__ void lh_water_closures(const P& p, const double* __re
     const double safe = !(th <= p.theta_r_eps) ? th : p.theta_r_eps;
     const double num = THR0 ? safe : safe - p.theta_r;                       // THR0: theta_r == 0 is known
     const double S_K = num * p.inv_nu_thr;                                   // porosity = nu (:163/:311)
-    const bool icy = ICE && (ti != 0.0);
+    // The ICE variants take the two-saturation path for EVERY cell (straight-line code): a per-lane test for ti != 0 made the
+    // layer loop divergent (10 reconvergence points, spills) and saved nothing in a warp that holds both kinds of cells.
+    constexpr bool icy = ICE;
     double S_eff = S_K;                                                      // porosity = nu_eff (:235)
     const double den_K = THR0 ? p.nu : p.nu_thr;
     double den_eff = den_K;
-    if (icy) { den_eff = nu_eff - p.theta_r; S_eff = lh_div(num, den_eff); }
+    if (icy) { den_eff = THR0 ? nu_eff : nu_eff - p.theta_r; S_eff = lh_div(num, den_eff); }
     // The reference branches on the ROUNDED quotients (S_l_eff <= 1, S < 1).  A correctly rounded num/den is < 1
     // exactly when num < den, and at num == den both branches of the pressure head give 0, so the branches are
     // decided on num and den themselves: the product num (1/den) used for S here can be 1 - 2^-53 where the
@@ -312,7 +314,7 @@ __device__ __forceinline__ double lh_thermal_conductivity(const P& p, const doub
         return lh_fma(K_e, p.k_unfrozen_minus_dry, p.kappa_dry);   // (the per-column view overrides both members)
     }
     double k_sat = p.k_unfrozen;                                             // :114-128; x^1 * y^0 is exact
-    if (ti != 0.0) k_sat = lh_exp2(mc, tab, lh_div(tl * p.log2_k_unfrozen + ti * p.log2_k_frozen, tw));
+    k_sat = lh_exp2(mc, tab, lh_div_fast(tl * p.log2_k_unfrozen + ti * p.log2_k_frozen, tw));   // ti == 0: 2^(log2 k_u), 1 ulp from k_u
     k_sat = (tw < LH_EPS) ? 0.0 : k_sat;
     return K_e * k_sat + (1.0 - K_e) * p.kappa_dry;                          // thermal_conductivity :185-188
 }

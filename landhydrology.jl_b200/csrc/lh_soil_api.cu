@@ -63,7 +63,6 @@ thread_local char g_create_err[256] = "";
 }  // namespace
 
 struct lh_soil_ctx;
-static bool use_persistent(const lh_soil_ctx* c);
 
 // ------------------------------------------------------------------------------------------------
 // Context
@@ -90,6 +89,13 @@ struct lh_soil_ctx {
     double* partials = nullptr;
     int32_t npartials = 0;
     double* budget_dev = nullptr;                // 2 doubles (+2 for the all-reduce result)
+    // lh_soil_budgets_async: a ring of pinned result slots, one event each
+    static constexpr int BUDGET_SLOTS = 8;
+    double* budget_ring_dev = nullptr;           // [BUDGET_SLOTS][2]
+    double* budget_ring_host = nullptr;          // pinned, [BUDGET_SLOTS][2]
+    cudaEvent_t budget_ev[BUDGET_SLOTS] = {};
+    int64_t budget_ticket[BUDGET_SLOTS] = {};    // ticket whose result the slot holds (0: free)
+    int64_t budget_next_ticket = 1;
     double* colp_dev = nullptr;                  // [LHCP_COUNT][ncol_pad] per-column derived parameters (heterogeneous soils)
     double* pow_tab_dev = nullptr;               // LHPW_COUNT fixed-exponent power tables (lh_math.cuh), built at create
     std::vector<double> pow_tab;                 // their host copy
@@ -104,6 +110,16 @@ struct lh_soil_ctx {
     int32_t chain_seq = 0;                       // value the last stage launch published; only ever grows, so that a flag
                                                  // left over from an earlier launch can never equal a value waited for
     bool chain_break = true;                     // the next stage launch takes the whole-grid dependency (first launch, new shape)
+    // lh_soil_set_aux_table: time-dependent prescribed profiles, one row of nlayer values per stage launch
+    double* aux_tab_dev[LH_NUM_FIELDS] = {nullptr, nullptr, nullptr, nullptr};
+    int64_t aux_tab_rows[LH_NUM_FIELDS] = {0, 0, 0, 0};
+    int64_t aux_row = 0;                         // next row to consume
+    // lh_soil_run: budget history and double-buffered snapshots
+    double* hist_dev = nullptr;                  // [hist_cap][2]
+    double* hist_host = nullptr;                 // pinned
+    int64_t hist_cap = 0;
+    double* snap_dev[2][LH_NUM_FIELDS] = {{nullptr, nullptr, nullptr, nullptr}, {nullptr, nullptr, nullptr, nullptr}};
+    cudaEvent_t ev_snap_ready[2] = {nullptr, nullptr}, ev_snap_done[2] = {nullptr, nullptr};
     double* bc_dev = nullptr;                    // boundary-value table of a persistent launch
     int64_t bc_dev_steps = 0;
     unsigned long long* nonfinite_dev = nullptr;
@@ -244,8 +260,17 @@ void free_all(lh_soil_ctx* c)
     if (c->zc_dev) cudaFree(c->zc_dev);
     if (c->partials) cudaFree(c->partials);
     if (c->budget_dev) cudaFree(c->budget_dev);
+    if (c->budget_ring_dev) cudaFree(c->budget_ring_dev);
+    if (c->budget_ring_host) cudaFreeHost(c->budget_ring_host);
+    for (auto& e : c->budget_ev) if (e) cudaEventDestroy(e);
     if (c->bc_dev) cudaFree(c->bc_dev);
     if (c->chain_dev) cudaFree(c->chain_dev);
+    for (auto& p : c->aux_tab_dev) if (p) cudaFree(p);
+    if (c->hist_dev) cudaFree(c->hist_dev);
+    if (c->hist_host) cudaFreeHost(c->hist_host);
+    for (auto& b : c->snap_dev) for (auto& p : b) if (p) cudaFree(p);
+    for (auto& e : c->ev_snap_ready) if (e) cudaEventDestroy(e);
+    for (auto& e : c->ev_snap_done) if (e) cudaEventDestroy(e);
     if (c->fused_partials) cudaFree(c->fused_partials);
     if (c->colp_dev) cudaFree(c->colp_dev);
     if (c->pow_tab_dev) cudaFree(c->pow_tab_dev);
@@ -531,6 +556,10 @@ int lh_bytes_on_wire(const lh_soil_ctx* c)
 
 extern "C" {
 
+static bool use_persistent(const lh_soil_ctx* c);
+static int32_t local_budgets(lh_soil_ctx* c);
+static int32_t apply_aux_tables(lh_soil_ctx* c);
+
 int32_t lh_soil_abi_version(void) { return LH_SOIL_ABI_VERSION; }
 
 const char* lh_soil_last_error(const lh_soil_ctx* ctx) { return ctx ? ctx->err : g_create_err; }
@@ -785,7 +814,9 @@ int32_t lh_soil_stage_ssprk33(lh_soil_ctx* c, int32_t stage, double dt)
     if (!c) return LH_ERR_INVALID_ARG;
     if (stage < 1 || stage > 3) return fail(c, LH_ERR_INVALID_ARG, "stage must be 1, 2 or 3");
     LH_CUDA(c, cudaSetDevice(c->device));
-    int32_t st = launch_stage(c, stage, dt);
+    int32_t st = apply_aux_tables(c);
+    if (st != LH_OK) return st;
+    st = launch_stage(c, stage, dt);
     if (st == LH_OK && stage == 3) c->budget_fresh = c->fused_partials != nullptr;   // stages 1, 2 do not touch U
     return st;
 }
@@ -801,13 +832,34 @@ static bool use_persistent(const lh_soil_ctx* c)
     return c->shape.waves <= 1.5;
 }
 
-int32_t lh_soil_step_ssprk33(lh_soil_ctx* c, double t, double dt, int64_t nsteps, const double* bc_table)
+static bool has_aux_table(const lh_soil_ctx* c)
 {
-    (void)t;
-    if (!c) return LH_ERR_INVALID_ARG;
-    if (nsteps < 0) return fail(c, LH_ERR_INVALID_ARG, "nsteps < 0");
-    LH_CUDA(c, cudaSetDevice(c->device));
-    const bool persistent = use_persistent(c) && nsteps > 0;
+    for (int f = 0; f < LH_NUM_FIELDS; ++f) if (c->aux_tab_dev[f]) return true;
+    return false;
+}
+
+// Before a stage launch: broadcast the next row of every prescribed-profile table into its field (device side, no host
+// round trip: what update_aux! does in the reference before every rhs! call, right_hand_side.jl:54-81).
+static int32_t apply_aux_tables(lh_soil_ctx* c)
+{
+    bool any = false;
+    for (int f = 0; f < LH_NUM_FIELDS; ++f) {
+        if (!c->aux_tab_dev[f]) continue;
+        if (c->aux_row >= c->aux_tab_rows[f])
+            return fail(c, LH_ERR_STATE, "prescribed-profile table of field %d exhausted (%lld rows): upload the rows of the next stages with lh_soil_set_aux_table",
+                        f, (long long)c->aux_tab_rows[f]);
+        LH_CUDA(c, lh_launch_fill_profile(c->aux_tab_dev[f] + c->aux_row * c->nlayer, c->U[f], c->nlayer, c->ncol_pad, c->stream));
+        any = true;
+    }
+    if (any) ++c->aux_row;
+    return LH_OK;
+}
+
+// nsteps SSPRK33 steps enqueued on the ctx stream (no timing events, no synchronisation).
+static int32_t advance_ssprk33(lh_soil_ctx* c, double dt, int64_t nsteps, const double* bc_table, int64_t* launches_out)
+{
+    const bool tables = has_aux_table(c);
+    const bool persistent = use_persistent(c) && nsteps > 0 && !tables;
     if (persistent && bc_table) {
         if (c->bc_dev_steps < nsteps) {
             if (c->bc_dev) { LH_CUDA(c, cudaFree(c->bc_dev)); c->bc_dev = nullptr; c->bc_dev_steps = 0; }
@@ -817,7 +869,6 @@ int32_t lh_soil_step_ssprk33(lh_soil_ctx* c, double t, double dt, int64_t nsteps
         // pageable source: the call returns once the table has been staged, so the host buffer is only borrowed
         LH_CUDA(c, cudaMemcpyAsync(c->bc_dev, bc_table, (size_t)nsteps * 12 * sizeof(double), cudaMemcpyHostToDevice, c->stream));
     }
-    LH_CUDA(c, cudaEventRecord(c->ev_start, c->stream));
     int64_t launches = 0;
     if (persistent) {
         const int64_t MAX_STEPS_PER_LAUNCH = 4096;
@@ -834,17 +885,255 @@ int32_t lh_soil_step_ssprk33(lh_soil_ctx* c, double t, double dt, int64_t nsteps
         for (int64_t s = 0; s < nsteps; ++s) {
             for (int stage = 1; stage <= 3; ++stage) {
                 if (bc_table) memcpy(c->bcv, bc_table + (s * 3 + (stage - 1)) * 4, sizeof c->bcv);
-                int32_t st = launch_stage(c, stage, dt);
-                if (st != LH_OK) return st;
+                int32_t st;
+                if (tables && (st = apply_aux_tables(c)) != LH_OK) return st;
+                if ((st = launch_stage(c, stage, dt)) != LH_OK) return st;
             }
         }
         launches = 3 * nsteps;
     }
+    if (nsteps > 0) c->budget_fresh = c->fused_partials != nullptr;       // the last stage-3 launch summed what it wrote
+    if (launches_out) *launches_out += launches;
+    return LH_OK;
+}
+
+int32_t lh_soil_step_ssprk33(lh_soil_ctx* c, double t, double dt, int64_t nsteps, const double* bc_table)
+{
+    (void)t;
+    if (!c) return LH_ERR_INVALID_ARG;
+    if (nsteps < 0) return fail(c, LH_ERR_INVALID_ARG, "nsteps < 0");
+    LH_CUDA(c, cudaSetDevice(c->device));
+    LH_CUDA(c, cudaEventRecord(c->ev_start, c->stream));
+    int64_t launches = 0;
+    int32_t st = advance_ssprk33(c, dt, nsteps, bc_table, &launches);
+    if (st != LH_OK) return st;
     LH_CUDA(c, cudaEventRecord(c->ev_stop, c->stream));
     c->timing_valid = true;
     c->last_launches = launches;
-    if (nsteps > 0) c->budget_fresh = c->fused_partials != nullptr;       // the last stage-3 launch summed what it wrote
     if (c->cfg.flags & LH_FLAG_CHECK_FINITE) return check_finite(c);
+    return LH_OK;
+}
+
+int32_t lh_soil_set_aux_table(lh_soil_ctx* c, int32_t field, const double* table, int64_t nrows)
+{
+    if (!c) return LH_ERR_INVALID_ARG;
+    if (!field_ok(field) || !c->U[field]) return fail(c, LH_ERR_INVALID_ARG, "field %d does not exist for model kind %d", field, c->model);
+    const bool prescribed = (c->model == LH_MODEL_RICHARDS && field == LH_FIELD_T) ||
+                            (c->model == LH_MODEL_HEAT && (field == LH_FIELD_THETA_L || field == LH_FIELD_THETA_I));
+    if (!prescribed) return fail(c, LH_ERR_INVALID_ARG, "field %d is not a prescribed profile of model kind %d", field, c->model);
+    LH_CUDA(c, cudaSetDevice(c->device));
+    LH_CUDA(c, cudaStreamSynchronize(c->stream));
+    if (c->aux_tab_dev[field]) { LH_CUDA(c, cudaFree(c->aux_tab_dev[field])); c->aux_tab_dev[field] = nullptr; c->aux_tab_rows[field] = 0; }
+    c->aux_row = 0;                                     // every table restarts at its first row
+    if (!table || nrows <= 0) return LH_OK;
+    const size_t bytes = (size_t)nrows * c->nlayer * sizeof(double);
+    LH_CUDA(c, cudaMalloc(&c->aux_tab_dev[field], bytes));
+    LH_CUDA(c, cudaMemcpyAsync(c->aux_tab_dev[field], table, bytes, cudaMemcpyHostToDevice, c->stream));
+    LH_CUDA(c, cudaStreamSynchronize(c->stream));
+    c->aux_tab_rows[field] = nrows;
+    if (field == LH_FIELD_THETA_I) {                    // ice anywhere in the table selects the ICE kernels for the whole run
+        bool ice = false;
+        for (int64_t i = 0; i < nrows * c->nlayer && !ice; ++i) ice = !(table[i] == 0.0);
+        if (ice && !c->has_ice) { c->has_ice = true; c->theta_i_ptr_out = true; update_kernel_flags(c); }
+    }
+    return LH_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+// lh_soil_run: a whole run!() with saveat snapshots and per-step budgets inside ONE call
+// ------------------------------------------------------------------------------------------------
+namespace {
+// Non-blocking download of one SoA field into a dense host block, everything on copy_stream.
+int32_t enqueue_download(lh_soil_ctx* c, const double* soa, double* host, int64_t cs, int64_t ls)
+{
+    const int n = c->nlayer;
+    if (cs == 1 || c->ncol == 1) {
+        LH_CUDA(c, cudaMemcpy2DAsync(host, ls * sizeof(double), soa, c->ncol_pad * sizeof(double), c->ncol * sizeof(double), n,
+                                     cudaMemcpyDeviceToHost, c->copy_stream));
+        return LH_OK;
+    }
+    int k = 0;
+    for (int64_t c0 = 0; c0 < c->ncol; c0 += c->chunk_cols, k ^= 1) {
+        const int64_t m = std::min<int64_t>(c->chunk_cols, c->ncol - c0);
+        LH_CUDA(c, lh_launch_from_soa(soa, c->stage_dev[k], c0, m, n, c->ncol_pad, c->copy_stream));
+        LH_CUDA(c, cudaMemcpyAsync(host + c0 * n, c->stage_dev[k], (size_t)m * n * sizeof(double), cudaMemcpyDeviceToHost, c->copy_stream));
+    }
+    return LH_OK;
+}
+}  // namespace
+
+int32_t lh_soil_run(lh_soil_ctx* c, double t0, double dt, int64_t nsteps, const lh_soil_run_opts* o)
+{
+    (void)t0;
+    if (!c || !o) return LH_ERR_INVALID_ARG;
+    if (o->struct_size != (int32_t)sizeof(lh_soil_run_opts)) return fail(c, LH_ERR_INVALID_ARG, "lh_soil_run_opts.struct_size mismatch");
+    if (nsteps < 0 || o->budget_every < 0 || o->save_every < 0) return fail(c, LH_ERR_INVALID_ARG, "negative step count or cadence");
+    if (o->budget_every > 0 && !o->budgets_out) return fail(c, LH_ERR_INVALID_ARG, "budget_every > 0 needs budgets_out");
+    const bool saving = o->save_every > 0 || o->save_first;
+    if (saving) {
+        if (!o->save_out || o->nsave_fields < 1 || o->nsave_fields > LH_NUM_FIELDS) return fail(c, LH_ERR_INVALID_ARG, "snapshots need save_out and 1..%d fields", LH_NUM_FIELDS);
+        for (int k = 0; k < o->nsave_fields; ++k)
+            if (!field_ok(o->save_fields[k]) || !c->U[o->save_fields[k]]) return fail(c, LH_ERR_INVALID_ARG, "snapshot field %d does not exist", o->save_fields[k]);
+        const bool ref_layout = o->layer_stride == 1 && o->col_stride == c->nlayer;
+        const bool soa_layout = o->col_stride == 1 && o->layer_stride >= c->ncol;
+        if (!ref_layout && !soa_layout && c->ncol != 1)
+            return fail(c, LH_ERR_INVALID_ARG, "snapshots are written densely: (col_stride, layer_stride) = (nlayer, 1) or (1, >= ncol)");
+    }
+    LH_CUDA(c, cudaSetDevice(c->device));
+    int32_t st;
+    const int64_t nb = o->budget_every > 0 ? nsteps / o->budget_every : 0;
+    if (nb > c->hist_cap) {
+        if (c->hist_dev) { LH_CUDA(c, cudaFree(c->hist_dev)); c->hist_dev = nullptr; }
+        if (c->hist_host) { LH_CUDA(c, cudaFreeHost(c->hist_host)); c->hist_host = nullptr; }
+        c->hist_cap = 0;
+        LH_CUDA(c, cudaMalloc(&c->hist_dev, (size_t)nb * 2 * sizeof(double)));
+        LH_CUDA(c, cudaMallocHost(&c->hist_host, (size_t)nb * 2 * sizeof(double)));
+        c->hist_cap = nb;
+    }
+    if (saving) {
+        if ((st = ensure_staging(c)) != LH_OK) return st;
+        for (int b = 0; b < 2; ++b) {
+            if (!c->ev_snap_ready[b]) LH_CUDA(c, cudaEventCreateWithFlags(&c->ev_snap_ready[b], cudaEventDisableTiming));
+            if (!c->ev_snap_done[b]) LH_CUDA(c, cudaEventCreateWithFlags(&c->ev_snap_done[b], cudaEventDisableTiming));
+            for (int k = 0; k < o->nsave_fields; ++k) {
+                const int f = o->save_fields[k];
+                if (!c->snap_dev[b][f]) LH_CUDA(c, cudaMalloc(&c->snap_dev[b][f], field_bytes(c)));
+            }
+        }
+    }
+    int64_t nsnap = 0;
+    // Snapshot: the state is copied device-to-device on the compute stream (0.2 ms per GB), which then goes on stepping;
+    // the transposes and the PCIe transfer of the copy run on copy_stream, two snapshots deep.
+    auto snapshot = [&]() -> int32_t {
+        const int b = (int)(nsnap & 1);
+        if (nsnap >= 2) LH_CUDA(c, cudaStreamWaitEvent(c->stream, c->ev_snap_done[b], 0));
+        for (int k = 0; k < o->nsave_fields; ++k) {
+            const int f = o->save_fields[k];
+            LH_CUDA(c, cudaMemcpyAsync(c->snap_dev[b][f], c->U[f], field_bytes(c), cudaMemcpyDeviceToDevice, c->stream));
+        }
+        LH_CUDA(c, cudaEventRecord(c->ev_snap_ready[b], c->stream));
+        LH_CUDA(c, cudaStreamWaitEvent(c->copy_stream, c->ev_snap_ready[b], 0));
+        for (int k = 0; k < o->nsave_fields; ++k) {
+            const int f = o->save_fields[k];
+            int32_t s2 = enqueue_download(c, c->snap_dev[b][f], o->save_out + nsnap * o->snapshot_stride + k * o->field_stride, o->col_stride, o->layer_stride);
+            if (s2 != LH_OK) return s2;
+        }
+        LH_CUDA(c, cudaEventRecord(c->ev_snap_done[b], c->copy_stream));
+        ++nsnap;
+        return LH_OK;
+    };
+
+    LH_CUDA(c, cudaEventRecord(c->ev_start, c->stream));
+    int64_t launches = 0, done = 0, nbud = 0;
+    if (o->save_first && (st = snapshot()) != LH_OK) return st;
+    while (done < nsteps) {
+        int64_t n = nsteps - done;
+        if (o->budget_every > 0) n = std::min<int64_t>(n, o->budget_every - done % o->budget_every);
+        if (o->save_every > 0) n = std::min<int64_t>(n, o->save_every - done % o->save_every);
+        if ((st = advance_ssprk33(c, dt, n, o->bc_table ? o->bc_table + done * 12 : nullptr, &launches)) != LH_OK) return st;
+        done += n;
+        if (o->budget_every > 0 && done % o->budget_every == 0) {
+            if ((st = local_budgets(c)) != LH_OK) return st;
+            LH_CUDA(c, cudaMemcpyAsync(c->hist_dev + 2 * nbud, c->budget_dev, 2 * sizeof(double), cudaMemcpyDeviceToDevice, c->stream));
+            LH_CUDA(c, cudaMemcpyAsync(c->hist_host + 2 * nbud, c->hist_dev + 2 * nbud, 2 * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+            ++nbud;
+        }
+        if (o->save_every > 0 && done % o->save_every == 0 && (st = snapshot()) != LH_OK) return st;
+    }
+    LH_CUDA(c, cudaEventRecord(c->ev_stop, c->stream));
+    c->timing_valid = true;
+    c->last_launches = launches;
+    LH_CUDA(c, cudaStreamSynchronize(c->stream));
+    LH_CUDA(c, cudaStreamSynchronize(c->copy_stream));
+    for (int64_t k = 0; k < nbud; ++k) {
+        o->budgets_out[2 * k] = c->hist_host[2 * k];
+        o->budgets_out[2 * k + 1] = c->U[2] ? c->hist_host[2 * k + 1] : 0.0;
+    }
+    if (c->cfg.flags & LH_FLAG_CHECK_FINITE) return check_finite(c);
+    return LH_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+// Checkpoint / restart: the device state as it is (padded SoA blocks), bit for bit
+// ------------------------------------------------------------------------------------------------
+namespace {
+struct LhCheckpointHeader {
+    char magic[8];            // "LHSOILCK"
+    int32_t abi, model, nlayer, field_mask;
+    int64_t ncol, ncol_pad;
+    double bcv[4];
+    int64_t aux_row;
+};
+int checkpoint_mask(const lh_soil_ctx* c) { int m = 0; for (int f = 0; f < LH_NUM_FIELDS; ++f) if (c->U[f]) m |= 1 << f; return m; }
+}  // namespace
+
+int64_t lh_soil_checkpoint_bytes(const lh_soil_ctx* c)
+{
+    if (!c) return LH_ERR_INVALID_ARG;
+    int nf = 0;
+    for (int f = 0; f < LH_NUM_FIELDS; ++f) nf += c->U[f] != nullptr;
+    return (int64_t)sizeof(LhCheckpointHeader) + (int64_t)nf * (int64_t)field_bytes(c);
+}
+
+int32_t lh_soil_checkpoint_save(lh_soil_ctx* c, void* buf, int64_t cap)
+{
+    if (!c || !buf) return LH_ERR_INVALID_ARG;
+    if (cap < lh_soil_checkpoint_bytes(c)) return fail(c, LH_ERR_INVALID_ARG, "checkpoint buffer too small (%lld < %lld bytes)", (long long)cap, (long long)lh_soil_checkpoint_bytes(c));
+    LH_CUDA(c, cudaSetDevice(c->device));
+    LhCheckpointHeader h;
+    memset(&h, 0, sizeof h);
+    memcpy(h.magic, "LHSOILCK", 8);
+    h.abi = LH_SOIL_ABI_VERSION; h.model = c->model; h.nlayer = c->nlayer; h.field_mask = checkpoint_mask(c);
+    h.ncol = c->ncol; h.ncol_pad = c->ncol_pad; h.aux_row = c->aux_row;
+    memcpy(h.bcv, c->bcv, sizeof h.bcv);
+    memcpy(buf, &h, sizeof h);
+    char* dst = (char*)buf + sizeof h;
+    for (int f = 0; f < LH_NUM_FIELDS; ++f) {
+        if (!c->U[f]) continue;
+        LH_CUDA(c, cudaMemcpyAsync(dst, c->U[f], field_bytes(c), cudaMemcpyDeviceToHost, c->stream));
+        dst += field_bytes(c);
+    }
+    LH_CUDA(c, cudaStreamSynchronize(c->stream));
+    return LH_OK;
+}
+
+int32_t lh_soil_checkpoint_load(lh_soil_ctx* c, const void* buf, int64_t bytes)
+{
+    if (!c || !buf) return LH_ERR_INVALID_ARG;
+    LhCheckpointHeader h;
+    if (bytes < (int64_t)sizeof h) return fail(c, LH_ERR_INVALID_ARG, "checkpoint truncated");
+    memcpy(&h, buf, sizeof h);
+    if (memcmp(h.magic, "LHSOILCK", 8) != 0 || h.abi != LH_SOIL_ABI_VERSION) return fail(c, LH_ERR_INVALID_ARG, "not a checkpoint of this ABI version");
+    if (h.model != c->model || h.nlayer != c->nlayer || h.ncol != c->ncol || h.ncol_pad != c->ncol_pad || h.field_mask != checkpoint_mask(c))
+        return fail(c, LH_ERR_INVALID_ARG, "checkpoint is of another problem (model %d, %lld x %d) than this ctx (model %d, %lld x %d)",
+                    h.model, (long long)h.ncol, h.nlayer, c->model, (long long)c->ncol, c->nlayer);
+    if (bytes < lh_soil_checkpoint_bytes(c)) return fail(c, LH_ERR_INVALID_ARG, "checkpoint truncated");
+    LH_CUDA(c, cudaSetDevice(c->device));
+    const char* src = (const char*)buf + sizeof h;
+    for (int f = 0; f < LH_NUM_FIELDS; ++f) {
+        if (!c->U[f]) continue;
+        LH_CUDA(c, cudaMemcpyAsync(c->U[f], src, field_bytes(c), cudaMemcpyHostToDevice, c->stream));
+        src += field_bytes(c);
+    }
+    LH_CUDA(c, cudaStreamSynchronize(c->stream));
+    memcpy(c->bcv, h.bcv, sizeof c->bcv);
+    c->aux_row = h.aux_row;
+    c->budget_fresh = false;
+    return detect_ice(c);
+}
+
+int32_t lh_soil_alloc_host(int64_t bytes, void** out)
+{
+    if (!out || bytes < 0) return LH_ERR_INVALID_ARG;
+    *out = nullptr;
+    cudaError_t e = cudaMallocHost(out, (size_t)std::max<int64_t>(bytes, 1));
+    if (e != cudaSuccess) return fail(nullptr, LH_ERR_CUDA, "cudaMallocHost(%lld) failed: %s", (long long)bytes, cudaGetErrorString(e));
+    return LH_OK;
+}
+
+int32_t lh_soil_free_host(void* p)
+{
+    if (p && cudaFreeHost(p) != cudaSuccess) return LH_ERR_CUDA;
     return LH_OK;
 }
 
@@ -912,6 +1201,7 @@ int32_t lh_soil_step(lh_soil_ctx* c, const lh_soil_stepper* sp, double t, double
     for (int64_t s = 0; s < nsteps; ++s) {
         for (int i = 0; i < ns; ++i) {
             if (bc_table) memcpy(c->bcv, bc_table + (s * ns + i) * 4, sizeof c->bcv);
+            { int32_t st_ = apply_aux_tables(c); if (st_ != LH_OK) return st_; }
             LhKernelArgs a;
             int stage;
             if (sp->kind == LH_STEPPER_SHU_OSHER) {
@@ -974,6 +1264,44 @@ int32_t lh_soil_budgets(lh_soil_ctx* c, double out[2])
     LH_CUDA(c, cudaMemcpyAsync(out, c->budget_dev, 2 * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
     LH_CUDA(c, cudaStreamSynchronize(c->stream));
     if (!c->U[2]) out[1] = 0.0;
+    return LH_OK;
+}
+
+int32_t lh_soil_budgets_async(lh_soil_ctx* c, int64_t* ticket_out)
+{
+    if (!c || !ticket_out) return LH_ERR_INVALID_ARG;
+    LH_CUDA(c, cudaSetDevice(c->device));
+    if (!c->budget_ring_dev) {
+        LH_CUDA(c, cudaMalloc(&c->budget_ring_dev, lh_soil_ctx::BUDGET_SLOTS * 2 * sizeof(double)));
+        LH_CUDA(c, cudaMallocHost(&c->budget_ring_host, lh_soil_ctx::BUDGET_SLOTS * 2 * sizeof(double)));
+        for (auto& e : c->budget_ev) LH_CUDA(c, cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+    }
+    const int64_t ticket = c->budget_next_ticket;
+    const int slot = (int)(ticket % lh_soil_ctx::BUDGET_SLOTS);
+    if (c->budget_ticket[slot] != 0)
+        return fail(c, LH_ERR_STATE, "lh_soil_budgets_async: %d results outstanding, collect one with lh_soil_budgets_wait first", lh_soil_ctx::BUDGET_SLOTS);
+    int32_t st = local_budgets(c);
+    if (st != LH_OK) return st;
+    // budget_dev is overwritten by the next budget call: park this result in its own slot before the copy to the host
+    LH_CUDA(c, cudaMemcpyAsync(c->budget_ring_dev + 2 * slot, c->budget_dev, 2 * sizeof(double), cudaMemcpyDeviceToDevice, c->stream));
+    LH_CUDA(c, cudaMemcpyAsync(c->budget_ring_host + 2 * slot, c->budget_ring_dev + 2 * slot, 2 * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+    LH_CUDA(c, cudaEventRecord(c->budget_ev[slot], c->stream));
+    c->budget_ticket[slot] = ticket;
+    ++c->budget_next_ticket;
+    *ticket_out = ticket;
+    return LH_OK;
+}
+
+int32_t lh_soil_budgets_wait(lh_soil_ctx* c, int64_t ticket, double out[2])
+{
+    if (!c || !out) return LH_ERR_INVALID_ARG;
+    const int slot = (int)(ticket % lh_soil_ctx::BUDGET_SLOTS);
+    if (ticket <= 0 || c->budget_ticket[slot] != ticket) return fail(c, LH_ERR_STATE, "lh_soil_budgets_wait: unknown or already collected ticket %lld", (long long)ticket);
+    LH_CUDA(c, cudaSetDevice(c->device));
+    LH_CUDA(c, cudaEventSynchronize(c->budget_ev[slot]));
+    out[0] = c->budget_ring_host[2 * slot];
+    out[1] = c->U[2] ? c->budget_ring_host[2 * slot + 1] : 0.0;
+    c->budget_ticket[slot] = 0;
     return LH_OK;
 }
 

@@ -247,6 +247,12 @@ struct lho_soil_ctx {
     double* Fe;
     double* colp[5];      /* per-column nu, theta_r, vg_n, vg_alpha, Ksat (NULL: uniform), lho_soil_set_column_params */
     double bcv[4];
+    double* aux_tab[LH_NUM_FIELDS]; /* lho_soil_set_aux_table: [nrows][nlayer] per prescribed field */
+    int64_t aux_rows[LH_NUM_FIELDS];
+    int64_t aux_row;
+    double async_bud[8][2];  /* lho_soil_budgets_async results by ticket % 8 */
+    int64_t async_ticket[8];
+    int64_t next_ticket;
     double last_ms;
     int64_t last_launches;
     char err[256];
@@ -375,6 +381,7 @@ int32_t lho_soil_destroy(lho_soil_ctx* c)
     for (int k = 0; k < 3; ++k) { free(c->u1[k]); free(c->tend[k]); }
     free(c->Fw); free(c->Fe);
     for (int k = 0; k < 5; ++k) free(c->colp[k]);
+    for (int k = 0; k < LH_NUM_FIELDS; ++k) free(c->aux_tab[k]);
     free(c);
     return LH_OK;
 }
@@ -663,10 +670,47 @@ static int prognostic(int model, int field)
     return 1;                                                          /* (ϑ_l, θ_i, ρe_int) */
 }
 
+/* update_aux! before a stage (right_hand_side.jl:54-81) from the rows the host evaluated ahead (lh_soil_set_aux_table). */
+static int32_t apply_aux_tables(lho_soil_ctx* c)
+{
+    int any = 0;
+    for (int f = 0; f < LH_NUM_FIELDS; ++f) {
+        if (!c->aux_tab[f]) continue;
+        if (c->aux_row >= c->aux_rows[f]) return fail(c, LH_ERR_STATE, "prescribed-profile table exhausted");
+        const double* row = c->aux_tab[f] + c->aux_row * c->nlayer;
+        for (int64_t col = 0; col < c->ncol; ++col)
+            for (int i = 0; i < c->nlayer; ++i) c->f[f][col * c->nlayer + i] = row[i];
+        any = 1;
+    }
+    if (any) ++c->aux_row;
+    return LH_OK;
+}
+
+int32_t lho_soil_set_aux_table(lho_soil_ctx* c, int32_t field, const double* table, int64_t nrows)
+{
+    if (!c) return LH_ERR_INVALID_ARG;
+    if (field < 0 || field >= LH_NUM_FIELDS) return fail(c, LH_ERR_INVALID_ARG, "bad field id");
+    const int model = c->cfg.model;
+    const int prescribed = (model == LH_MODEL_RICHARDS && field == LH_FIELD_T) ||
+                           (model == LH_MODEL_HEAT && (field == LH_FIELD_THETA_L || field == LH_FIELD_THETA_I));
+    if (!prescribed) return fail(c, LH_ERR_INVALID_ARG, "field is not a prescribed profile of this model");
+    free(c->aux_tab[field]);
+    c->aux_tab[field] = NULL;
+    c->aux_rows[field] = 0;
+    c->aux_row = 0;
+    if (!table || nrows <= 0) return LH_OK;
+    const size_t cnt = (size_t)nrows * c->nlayer;
+    c->aux_tab[field] = (double*)malloc(cnt * sizeof(double));
+    memcpy(c->aux_tab[field], table, cnt * sizeof(double));
+    c->aux_rows[field] = nrows;
+    return LH_OK;
+}
+
 int32_t lho_soil_stage_ssprk33(lho_soil_ctx* c, int32_t stage, double dt)
 {
     if (!c) return LH_ERR_INVALID_ARG;
     if (stage < 1 || stage > 3) return fail(c, LH_ERR_INVALID_ARG, "stage must be 1, 2 or 3");
+    { int32_t st_ = apply_aux_tables(c); if (st_ != LH_OK) return st_; }
     const int model = c->cfg.model;
     const size_t cells = (size_t)c->ncol * c->nlayer;
     /* stage input: u0 for stage 1, the stage buffer otherwise (non-prognostic slots always
@@ -801,6 +845,7 @@ int32_t lho_soil_step(lho_soil_ctx* c, const lh_soil_stepper* sp, double t, doub
     for (int64_t s = 0; s < nsteps; ++s) {
         for (int i = 0; i < ns; ++i) {
             if (bc_table) memcpy(c->bcv, bc_table + (s * ns + i) * 4, sizeof c->bcv);
+            { int32_t st_ = apply_aux_tables(c); if (st_ != LH_OK) return st_; }
             if (sp->kind == LH_STEPPER_SHU_OSHER) {
                 /* stage input: u^n for the first stage, the stage register otherwise; the last stage
                  * writes u^{n+1} over u^n                                                           */
@@ -870,6 +915,105 @@ int32_t lho_soil_budgets(lho_soil_ctx* c, double out[2])
 }
 
 int32_t lho_soil_budgets_allreduce(lho_soil_ctx* c, double out[2]) { return lho_soil_budgets(c, out); }
+
+/* lh_soil_run: the plain loop the device version overlaps. */
+int32_t lho_soil_run(lho_soil_ctx* c, double t0, double dt, int64_t nsteps, const lh_soil_run_opts* o)
+{
+    if (!c || !o) return LH_ERR_INVALID_ARG;
+    if (o->struct_size != (int32_t)sizeof(lh_soil_run_opts)) return fail(c, LH_ERR_INVALID_ARG, "lh_soil_run_opts.struct_size mismatch");
+    if (nsteps < 0 || o->budget_every < 0 || o->save_every < 0) return fail(c, LH_ERR_INVALID_ARG, "negative step count or cadence");
+    if (o->budget_every > 0 && !o->budgets_out) return fail(c, LH_ERR_INVALID_ARG, "budget_every > 0 needs budgets_out");
+    const int saving = o->save_every > 0 || o->save_first;
+    if (saving && (!o->save_out || o->nsave_fields < 1 || o->nsave_fields > LH_NUM_FIELDS)) return fail(c, LH_ERR_INVALID_ARG, "snapshots need save_out and fields");
+    int64_t nsnap = 0, nbud = 0;
+    int32_t st;
+    if (o->save_first) {
+        for (int k = 0; k < o->nsave_fields; ++k)
+            if ((st = lho_soil_get_state(c, o->save_fields[k], o->save_out + nsnap * o->snapshot_stride + k * o->field_stride, o->col_stride, o->layer_stride)) != LH_OK) return st;
+        ++nsnap;
+    }
+    for (int64_t s = 0; s < nsteps; ++s) {
+        if ((st = lho_soil_step_ssprk33(c, t0 + s * dt, dt, 1, o->bc_table ? o->bc_table + s * 12 : NULL)) != LH_OK) return st;
+        if (o->budget_every > 0 && (s + 1) % o->budget_every == 0) { lho_soil_budgets(c, o->budgets_out + 2 * nbud); ++nbud; }
+        if (o->save_every > 0 && (s + 1) % o->save_every == 0) {
+            for (int k = 0; k < o->nsave_fields; ++k)
+                if ((st = lho_soil_get_state(c, o->save_fields[k], o->save_out + nsnap * o->snapshot_stride + k * o->field_stride, o->col_stride, o->layer_stride)) != LH_OK) return st;
+            ++nsnap;
+        }
+    }
+    return LH_OK;
+}
+
+/* Checkpoints of the oracle: its own layout, same entry points. */
+int64_t lho_soil_checkpoint_bytes(const lho_soil_ctx* c)
+{
+    if (!c) return LH_ERR_INVALID_ARG;
+    return (int64_t)(sizeof(int64_t) * 4 + sizeof(double) * 4 + (size_t)LH_NUM_FIELDS * c->ncol * c->nlayer * sizeof(double));
+}
+
+int32_t lho_soil_checkpoint_save(lho_soil_ctx* c, void* buf, int64_t cap)
+{
+    if (!c || !buf) return LH_ERR_INVALID_ARG;
+    if (cap < lho_soil_checkpoint_bytes(c)) return fail(c, LH_ERR_INVALID_ARG, "checkpoint buffer too small");
+    char* p = (char*)buf;
+    int64_t h[4] = {0x4c484f43, c->ncol, c->nlayer, c->aux_row};
+    memcpy(p, h, sizeof h); p += sizeof h;
+    memcpy(p, c->bcv, sizeof c->bcv); p += sizeof c->bcv;
+    const size_t fb = (size_t)c->ncol * c->nlayer * sizeof(double);
+    for (int k = 0; k < LH_NUM_FIELDS; ++k) { memcpy(p, c->f[k], fb); p += fb; }
+    return LH_OK;
+}
+
+int32_t lho_soil_checkpoint_load(lho_soil_ctx* c, const void* buf, int64_t bytes)
+{
+    if (!c || !buf) return LH_ERR_INVALID_ARG;
+    if (bytes < lho_soil_checkpoint_bytes(c)) return fail(c, LH_ERR_INVALID_ARG, "checkpoint truncated");
+    const char* p = (const char*)buf;
+    int64_t h[4];
+    memcpy(h, p, sizeof h); p += sizeof h;
+    if (h[0] != 0x4c484f43 || h[1] != c->ncol || h[2] != c->nlayer) return fail(c, LH_ERR_INVALID_ARG, "checkpoint is of another problem");
+    c->aux_row = h[3];
+    memcpy(c->bcv, p, sizeof c->bcv); p += sizeof c->bcv;
+    const size_t fb = (size_t)c->ncol * c->nlayer * sizeof(double);
+    for (int k = 0; k < LH_NUM_FIELDS; ++k) { memcpy(c->f[k], p, fb); p += fb; }
+    return LH_OK;
+}
+
+int32_t lho_soil_alloc_host(int64_t bytes, void** out)
+{
+    if (!out || bytes < 0) return LH_ERR_INVALID_ARG;
+    *out = malloc((size_t)(bytes > 0 ? bytes : 1));
+    return *out ? LH_OK : LH_ERR_INVALID_ARG;
+}
+
+int32_t lho_soil_free_host(void* p) { free(p); return LH_OK; }
+
+/* The CPU has no stream: the "asynchronous" form computes at once and hands the result out on wait. */
+int32_t lho_soil_budgets_async(lho_soil_ctx* c, int64_t* ticket_out)
+{
+    if (!c || !ticket_out) return LH_ERR_INVALID_ARG;
+    if (c->next_ticket < 1) c->next_ticket = 1;
+    const int64_t t = c->next_ticket;
+    const int slot = (int)(t % 8);
+    if (c->async_ticket[slot] != 0) return fail(c, LH_ERR_STATE, "lho_soil_budgets_async: 8 results outstanding");
+    int32_t st = lho_soil_budgets(c, c->async_bud[slot]);
+    if (st != LH_OK) return st;
+    c->async_ticket[slot] = t;
+    c->next_ticket = t + 1;
+    *ticket_out = t;
+    return LH_OK;
+}
+
+int32_t lho_soil_budgets_wait(lho_soil_ctx* c, int64_t ticket, double out[2])
+{
+    if (!c || !out) return LH_ERR_INVALID_ARG;
+    const int slot = (int)(ticket % 8);
+    if (ticket <= 0 || c->async_ticket[slot] != ticket) return fail(c, LH_ERR_STATE, "lho_soil_budgets_wait: unknown ticket");
+    out[0] = c->async_bud[slot][0];
+    out[1] = c->async_bud[slot][1];
+    c->async_ticket[slot] = 0;
+    return LH_OK;
+}
 
 int32_t lho_soil_diagnostic(lho_soil_ctx* c, int32_t which, double* host, int64_t cs, int64_t ls)
 {

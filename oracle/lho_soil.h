@@ -46,6 +46,15 @@
 #define lh_soil_comm_init         lho_soil_comm_init
 #define lh_soil_budgets_allreduce lho_soil_budgets_allreduce
 #define lh_soil_kernel_info       lho_soil_kernel_info
+#define lh_soil_budgets_async     lho_soil_budgets_async
+#define lh_soil_budgets_wait      lho_soil_budgets_wait
+#define lh_soil_set_aux_table     lho_soil_set_aux_table
+#define lh_soil_run               lho_soil_run
+#define lh_soil_checkpoint_bytes  lho_soil_checkpoint_bytes
+#define lh_soil_checkpoint_save   lho_soil_checkpoint_save
+#define lh_soil_checkpoint_load   lho_soil_checkpoint_load
+#define lh_soil_alloc_host        lho_soil_alloc_host
+#define lh_soil_free_host         lho_soil_free_host
 
 #include "../include/lh_soil.h"
 

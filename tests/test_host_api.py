@@ -284,7 +284,7 @@ def test_bench_reference_arm_json_line():
     import sys
 
     res = subprocess.run([sys.executable, w.ROOT + "/bench.py", "--impl", "reference", "--steps", "1", "--warmup", "1",
-                          "--ncol", "1048576"], capture_output=True, text=True, timeout=600)
+                          "--ncol", "16384"], capture_output=True, text=True, timeout=600)
     assert res.returncode == 0, res.stderr[-2000:]
     lines = [l for l in res.stdout.splitlines() if l.strip()]
     assert len(lines) == 1, res.stdout
@@ -295,6 +295,7 @@ def test_bench_reference_arm_json_line():
     assert d["impl"] == "reference" and d["dtype"] == "f64" and d["unit"] == "cell-steps/s" and d["value"] > 0
     assert d["cpu_baseline"]["kind"] == "port" and d["cpu_baseline"]["cores"] >= 1 and "workload" in d["config"]
     assert d["e2e"]["h2d_bytes_per_step"] == 0 and d["e2e"]["d2h_bytes_per_step"] == 0
+    assert d["same_config"] is True and "16384 columns x 64 layers" in d["cpu_baseline"]["sample"]    # the whole column set, not a sample
 
 
 @pytest.mark.gpu
@@ -305,8 +306,8 @@ def test_bench_b200_arm_json_line():
     import subprocess
     import sys
 
-    res = subprocess.run([sys.executable, w.ROOT + "/bench.py", "--ncol", "65536", "--steps", "3", "--warmup", "3"],
-                         capture_output=True, text=True, timeout=900)
+    res = subprocess.run([sys.executable, w.ROOT + "/bench.py", "--ncol", "65536", "--steps", "3", "--warmup", "3", "--no-variants",
+                          "--min-seconds", "0.5"], capture_output=True, text=True, timeout=900)
     assert res.returncode == 0, res.stderr[-2000:]
     lines = [l for l in res.stdout.splitlines() if l.strip()]
     assert len(lines) == 1, res.stdout
@@ -314,8 +315,12 @@ def test_bench_b200_arm_json_line():
     for key in ("metric", "value", "unit", "n_gpus", "steps", "warmup", "ms_per_step", "higher_is_better", "scaling", "vs_baseline",
                 "dtype", "data", "config", "clocks", "gpu_launches", "roofline", "e2e", "cpu_baseline", "budgets"):
         assert key in d, key
-    assert d["n_gpus"] == 1 and d["steps"] == 3 and d["gpu_launches"] in (9, 1) and d["value"] > 1e9
+    nb = d["sustained"]["blocks"]
+    assert nb >= 3 and d["sustained"]["device_seconds"] >= 0.5
+    assert d["n_gpus"] == 1 and d["steps"] == 3 and d["gpu_launches"] in (9 * nb, nb) and d["value"] > 1e9
+    assert d["clocks"]["samples"] >= 1 and d["clocks"]["sm_mhz"] > 0
     r = d["roofline"]
     assert r["bound"] == "hbm" and 0 < r["frac"] < 1.2 and abs(r["frac"] - r["achieved"] / r["peak"]) < 1e-12
+    assert 0 < r["frac_on_wire"] <= r["frac"] and r["on_wire_bytes_per_cell_step"] in (128, 32) and "FLAGS=4" in r["variant"]
     assert d["e2e"]["h2d_bytes_per_step"] > 0 and d["e2e"]["d2h_bytes_per_step"] > 0 and 0 < d["e2e"]["value"] < d["value"]
     assert d["cpu_baseline"]["kind"] == "port" and d["cpu_baseline"]["value"] > 0
