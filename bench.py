@@ -265,6 +265,9 @@ def _main(args, result_stream):
     torch.cuda.set_device(local_rank)
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    # Pinned host buffers are placed on the NUMA node of the allocating thread: sit next to this rank's GPU first.
+    affinity0 = os.sched_getaffinity(0)
+    numa_bound = lh.bind_to_gpu_numa_node(local_rank)
 
     lo, hi = lh.shard_range(args.ncol, world, rank)
     wl = make_workload(w, args.model, args.ncol, args.nlayer, (lo, hi), ice=args.ice)
@@ -353,11 +356,11 @@ def _main(args, result_stream):
     e2e = None
     if not args.no_e2e:
         K = args.steps
-        table = bc_table_for(wl, 0.0, wl.dt, 1)
+        table_K = bc_table_for(wl, 0.0, wl.dt, K)
         out = {fid: pinned_like(np.empty_like(wl.fields[fid])) for fid in ((0, 2) if args.model == "coupled" else (0,))}
         # Columns are independent, so the public API lets a host cut them into shards, one ctx each: every ctx has its own
         # stream, the calls release the GIL, and PCIe (2.7 GB per 20 steps) overlaps with the kernels of the other shards.
-        S = 1 if args.het else max(1, min(args.e2e_shards, (hi - lo) // 4096))
+        S = 1 if args.het else max(1, min(args.e2e_shards, (hi - lo) // 32768))      # >= 32768 columns per shard
         ncol_r = hi - lo
         cuts = [(ncol_r * k // S) // 32 * 32 for k in range(S)] + [ncol_r]
         subs = []
@@ -380,19 +383,10 @@ def _main(args, result_stream):
             for fid, a in host.items():
                 sub.set_state(fid, a[c0:c1])                   # H2D (+ layout transform on device)
             up_done[k].set()
-            tt = 0.0
-            pending = None
-            for s in range(K):
-                sub.step(tt, wl.dt, 1, table)                  # host-evaluated bc values for the 3 stage times
-                # D2H read of the step's result (16 B), non-blocking: the copy is enqueued behind the step and collected
-                # after the NEXT step has been enqueued, so the stream never drains between steps.
-                nxt = sub.budgets_async()
-                if pending is not None:
-                    step_budgets[k, s - 1] = sub.budgets_wait(pending)
-                pending = nxt
-                tt += wl.dt
-            if pending is not None:
-                step_budgets[k, K - 1] = sub.budgets_wait(pending)
+            # run!(sim): K steps in ONE call; after every step the budgets (the step's result, 16 B) are reduced on the
+            # device and copied to a pinned slot on the host, asynchronously, while the next step runs.
+            bud, _ = sub.run(0.0, wl.dt, K, bc_table=table_K, budget_every=1)
+            step_budgets[k] = bud
             if k > 0:
                 down_done[k - 1].wait()
             for fid, a in out.items():
@@ -420,9 +414,10 @@ def _main(args, result_stream):
             "value": cells_total * K / e_sec, "unit": UNIT,
             "h2d_bytes_per_step": int(nfields_in * cells_total * 8 / K + 96),
             "d2h_bytes_per_step": int(nfields_out * cells_total * 8 / K + 16),
-            "what": f"lh_soil_set_state x{nfields_in} (pinned host, reference layout) + {K} x [lh_soil_step_ssprk33(1 step, bc table) + "
-                    f"lh_soil_budgets_async/wait (16 B D2H per step)] + lh_soil_get_state x{nfields_out}, over {S} column shard(s) per GPU "
+            "what": f"lh_soil_set_state x{nfields_in} (pinned host, reference layout) + lh_soil_run({K} steps, host-built bc table, budgets "
+                    f"reduced and copied D2H after EVERY step, 16 B each) + lh_soil_get_state x{nfields_out}, over {S} column shard(s) per GPU "
                     f"(one ctx and host thread each, transfers overlapping kernels); wall clock, max over ranks",
+            "numa_bound": bool(numa_bound),
             "shards_per_gpu": S,
             "seconds": e_sec,
         }
@@ -522,6 +517,7 @@ def _main(args, result_stream):
         line["e2e"] = e2e
     ctx.close()
     del host
+    os.sched_setaffinity(0, affinity0)                     # the CPU legs use every core this process was given
     if world == 1 and not args.no_cpu_baseline:
         v, cores, sample, sec, steps = time_oracle(w, lh, graft, args.model, args.ncol, args.nlayer, 0, 1, target_seconds=12.0, ice=args.ice)
         line["cpu_baseline"] = {"value": v, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample}

@@ -59,6 +59,7 @@ extern "C" {
 #define LH_BC_FLUX          1   /* VerticalFlux  */
 #define LH_BC_DIRICHLET     2   /* Dirichlet     */
 #define LH_BC_FREE_DRAINAGE 3   /* FreeDrainage  */
+/* PrescribedAtmosForcing is not a per-component kind: it replaces the whole top SoilComponentBC (lh_soil_set_atmos_forcing). */
 
 /* Conductivity factors (SoilWaterParameterizations.jl:38-65).                               */
 #define LH_FACTOR_NONE        0 /* NoEffect                       */
@@ -197,6 +198,56 @@ int32_t lh_soil_set_aux(lh_soil_ctx* ctx, int32_t field, const double* host,
  * lane (one load per column and launch, +96 B per column, nothing per cell).                                    */
 int32_t lh_soil_set_column_params(lh_soil_ctx* ctx, const double* nu, const double* theta_r,
                                   const double* vg_n, const double* vg_alpha, const double* Ksat);
+
+/* Per-column HEAT parameters (new, same reason): ρc_ds, κ_sat_unfrozen, κ_sat_frozen, κ_solid and the solid fractions
+ * ν_ss_om, ν_ss_quartz, ν_ss_gravel of SoilParams (parameters.jl:11-43).  κ_dry follows κ_solid and ν per column
+ * (k_dry, SoilHeatParameterizations.jl:280-294), the Kersten exponents follow the fractions (:152-174).  Each array ncol
+ * doubles, NULL keeps the model's scalar; combines with lh_soil_set_column_params (either call keeps what the other set).
+ * Models without an energy equation return LH_ERR_INVALID_ARG.                                                    */
+int32_t lh_soil_set_column_heat_params(lh_soil_ctx* ctx, const double* rho_c_ds, const double* kappa_sat_unfrozen,
+                                       const double* kappa_sat_frozen, const double* kappa_solid, const double* nu_ss_om,
+                                       const double* nu_ss_quartz, const double* nu_ss_gravel);
+
+/* Spatially varying prescribed fluxes (new): per-column values for the faces whose kind is LH_BC_FLUX (VerticalFlux,
+ * boundary_conditions.jl:43-46,295-301), indexed like the boundary-value 4-vector: values[LH_BCV_*] is an array of ncol
+ * doubles or NULL (the scalar of lh_soil_set_bc_values / the bc table applies).  E.g. a precipitation or ground heat flux
+ * field over the columns of a HybridBox.  All NULL removes the arrays.                                                */
+int32_t lh_soil_set_column_fluxes(lh_soil_ctx* ctx, const double* const values[4]);
+
+/* ---- PrescribedAtmosForcing (boundary_conditions.jl:103-131, 516-620) -------------------------------------------------
+ * The reference's only physically driven surface condition (experiments/SoilModel/surface_fluxes.jl): turbulent fluxes of
+ * energy and water volume between the top soil cell and a prescribed atmospheric state, from Monin-Obukhov similarity.
+ * PARITY UNPINNED: the arithmetic of `surface_conditions` (SurfaceFluxes v0.1) and `q_vap_saturation_generic` / `cp_m`
+ * (Thermodynamics v0.5) is not under the reference tree.  What the reference itself fixes is restated exactly
+ * (compute_turbulent_surface_fluxes :555-620): the pore-air humidity q_surf = q_sat(T, ρ_a) exp(g ψ / (R_v T)) with ψ the
+ * matric potential at min(S_l_eff, 1); E = -ρ_a u* q*; the dry / vapour static-energy fluxes; Ẽ = E / ρ_l.  The similarity
+ * solution (u*, θ*, q*) follows the published formulation: Businger-Dyer universal functions (Businger et al. 1971, Dyer
+ * 1974) with Pr_0, a_m, a_h below, the Obukhov length from the θ flux alone, solved per column to 1e-15 by a secant
+ * iteration on 1/L.  Saturation vapour pressure: Clausius-Clapeyron with constant Δcp = cp_v - cp_l
+ * (Romps 2008; the closed form Thermodynamics.jl documents).  Its structural tests are the reference's own
+ * (test_prescribed_atmos_bc.jl:75-79,155,161-194).
+ * Valid for LH_MODEL_COUPLED only (both components dynamic, :103-112), top face only (:525-527): otherwise
+ * LH_ERR_UNSUPPORTED_BC.  NULL restores the configured top boundary conditions.  May be called between steps with new
+ * atmospheric values.  z_0m, z_0s come from lh_soil_params.                                                          */
+typedef struct lh_soil_atmos {
+    int32_t struct_size;       /* sizeof(lh_soil_atmos)                                       */
+    int32_t reserved;
+    double u_atm;              /* wind speed at z_atm                                         */
+    double theta_atm;          /* potential temperature at z_atm                              */
+    double z_atm;
+    double theta_scale;
+    double rho_a_sfc;          /* moist air density at the surface                            */
+    double q_atm;              /* specific humidity at z_atm                                  */
+    /* CLIMAParameters.Planet / SubgridScale values the reference reads at boundary_conditions.jl:575-617 */
+    double R_v, R_d, grav, cp_d, cp_v, LH_v0, press_triple, T_triple, von_karman;
+    /* Businger universal functions */
+    double Pr_0, a_m, a_h;
+} lh_soil_atmos;
+int32_t lh_soil_set_atmos_forcing(lh_soil_ctx* ctx, const lh_soil_atmos* atmos);
+/* The fluxes compute_turbulent_surface_fluxes returns (:555-620) for ONE surface state, evaluated on the device with the
+ * ctx's parameters: out[0] = heat flux (W/m^2, positive upward), out[1] = Ẽ (m/s).  n states.                         */
+int32_t lh_soil_atmos_fluxes(lh_soil_ctx* ctx, const double* theta_l, const double* theta_i, const double* T, int64_t n,
+                             double* heat_flux_out, double* water_flux_out);
 
 /* Boundary values for the NEXT rhs/stage call: the host evaluates Dirichlet
  * `state_value(t)` closures (boundary_conditions.jl:247,267) and passes 4 doubles indexed

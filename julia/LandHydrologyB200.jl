@@ -21,9 +21,10 @@ module LandHydrologyB200
 using LandHydrology.SoilInterface
 using LandHydrology.SoilInterface: SoilModel, SoilEnergyModel, SoilHydrologyModel,
     PrescribedTemperatureModel, PrescribedHydrologyModel, SoilComponentBC, NoBC, VerticalFlux,
-    Dirichlet, FreeDrainage
+    Dirichlet, FreeDrainage, PrescribedAtmosForcing
 using LandHydrology.SoilInterface.SoilWaterParameterizations: NoEffect, TemperatureDependentViscosity, IceImpedance
-using CLIMAParameters.Planet: ρ_cloud_liq, ρ_cloud_ice, cp_l, cp_i, T_0, LH_f0
+using CLIMAParameters.Planet: ρ_cloud_liq, ρ_cloud_ice, cp_l, cp_i, T_0, LH_f0, R_v, R_d, grav, cp_d, cp_v, LH_v0, press_triple, T_triple
+using CLIMAParameters.SubgridScale: von_karman_const
 using CLIMAParameters.Atmos.Microphysics: K_therm
 import OrdinaryDiffEq        # only for the method types (SSPRK33, CarpenterKennedy2N54, ...) Simulation dispatches on
 
@@ -65,6 +66,15 @@ struct LhSoilRunOpts
     reserved::Int32
     save_out::Ptr{Cdouble}
     snapshot_stride::Int64; field_stride::Int64; col_stride::Int64; layer_stride::Int64
+end
+
+# lh_soil_atmos: PrescribedAtmosForcing + the CLIMAParameters / Businger constants its fluxes need
+struct LhSoilAtmos
+    struct_size::Int32; reserved::Int32
+    u_atm::Cdouble; theta_atm::Cdouble; z_atm::Cdouble; theta_scale::Cdouble; rho_a_sfc::Cdouble; q_atm::Cdouble
+    R_v::Cdouble; R_d::Cdouble; grav::Cdouble; cp_d::Cdouble; cp_v::Cdouble; LH_v0::Cdouble
+    press_triple::Cdouble; T_triple::Cdouble; von_karman::Cdouble
+    Pr_0::Cdouble; a_m::Cdouble; a_h::Cdouble
 end
 
 # lh_soil_stepper: coefficient table of a two-register Shu-Osher or a Williamson 2N method
@@ -122,12 +132,21 @@ bc_pair(::NoBC, t) = (LH_BC_NONE, 0.0)
 bc_pair(bc::VerticalFlux, t) = (LH_BC_FLUX, Float64(bc.flux))
 bc_pair(bc::Dirichlet, t) = (LH_BC_DIRICHLET, Float64(bc.state_value(t)))
 bc_pair(::FreeDrainage, t) = (LH_BC_FREE_DRAINAGE, 0.0)
+# PrescribedAtmosForcing replaces the whole top SoilComponentBC: as far as the config goes the face is a (per-column) flux,
+# the fluxes themselves come from lh_soil_set_atmos_forcing (Engine constructor)
+face_bc(::PrescribedAtmosForcing, t) = LhSoilFaceBC(LH_BC_FLUX, LH_BC_FLUX, 0.0, 0.0)
+function atmos(model::SoilModel)
+    bc, ep = model.boundary_conditions.top, model.earth_param_set
+    LhSoilAtmos(Int32(sizeof(LhSoilAtmos)), Int32(0), bc.u_atm, bc.θ_atm, bc.z_atm, bc.θ_scale, bc.ρ_a_sfc, bc.q_atm,
+                R_v(ep), R_d(ep), grav(ep), cp_d(ep), cp_v(ep), LH_v0(ep), press_triple(ep), T_triple(ep), von_karman_const(ep),
+                0.74, 4.7, 4.7)                      # SurfaceFluxes.UniversalFunctions.Businger: Pr_0, a_m, a_h
+end
 function face_bc(bc::SoilComponentBC, t)
     (ek, ev), (hk, hv) = bc_pair(bc.energy, t), bc_pair(bc.hydrology, t)       # each closure evaluated once
     return LhSoilFaceBC(ek, hk, ev, hv)
 end
 function bc_values(model, t)
-    top, bot = face_bc(model.boundary_conditions.top, t), face_bc(model.boundary_conditions.bottom, t)
+    top, bot = face_bc(model.boundary_conditions.top, t), face_bc(model.boundary_conditions.bottom, t)    # atmos top: zeros (unused)
     return Float64[top.energy_value, top.hydrology_value, bot.energy_value, bot.hydrology_value]     # LH_BCV_* order
 end
 
@@ -166,6 +185,9 @@ function Engine(model::SoilModel, t0; domain = model.domain, device = 0, ncol = 
     check(C_NULL, st)
     e = Engine(out[], model, n, Int(ncol), Symbol[])
     finalizer(x -> ccall((:lh_soil_destroy, LIB), Int32, (Ptr{Cvoid},), x.ctx), e)
+    if model.boundary_conditions.top isa PrescribedAtmosForcing
+        check(e.ctx, ccall((:lh_soil_set_atmos_forcing, LIB), Int32, (Ptr{Cvoid}, Ref{LhSoilAtmos}), e.ctx, atmos(model)))
+    end
     return e
 end
 
@@ -313,6 +335,32 @@ function set_column_params!(e::Engine; ν = nothing, θr = nothing, n = nothing,
     GC.@preserve arrs check(e.ctx, ccall((:lh_soil_set_column_params, LIB), Int32,
         (Ptr{Cvoid}, Ptr{Cdouble}, Ptr{Cdouble}, Ptr{Cdouble}, Ptr{Cdouble}, Ptr{Cdouble}), e.ctx, map(ptr, arrs)...))
     return nothing
+end
+
+"Per-column heat parameters of SoilParams (ρc_ds, κ_sat_unfrozen, κ_sat_frozen, κ_solid, ν_ss_om, ν_ss_quartz, ν_ss_gravel)."
+function set_column_heat_params!(e::Engine; ρc_ds = nothing, κ_sat_unfrozen = nothing, κ_sat_frozen = nothing, κ_solid = nothing,
+                                 ν_ss_om = nothing, ν_ss_quartz = nothing, ν_ss_gravel = nothing)
+    ptr(a) = a === nothing ? Ptr{Cdouble}(C_NULL) : pointer(a)
+    arrs = map(a -> a === nothing ? nothing : Vector{Float64}(a), (ρc_ds, κ_sat_unfrozen, κ_sat_frozen, κ_solid, ν_ss_om, ν_ss_quartz, ν_ss_gravel))
+    GC.@preserve arrs check(e.ctx, ccall((:lh_soil_set_column_heat_params, LIB), Int32,
+        (Ptr{Cvoid}, Ptr{Cdouble}, Ptr{Cdouble}, Ptr{Cdouble}, Ptr{Cdouble}, Ptr{Cdouble}, Ptr{Cdouble}, Ptr{Cdouble}), e.ctx, map(ptr, arrs)...))
+    return nothing
+end
+
+"Spatially varying VerticalFlux values: per-column vectors for the faces of kind VerticalFlux (`nothing`: the scalar)."
+function set_column_fluxes!(e::Engine; top_energy = nothing, top_hydrology = nothing, bottom_energy = nothing, bottom_hydrology = nothing)
+    arrs = map(a -> a === nothing ? nothing : Vector{Float64}(a), (top_energy, top_hydrology, bottom_energy, bottom_hydrology))
+    ptrs = Ptr{Cdouble}[a === nothing ? Ptr{Cdouble}(C_NULL) : pointer(a) for a in arrs]
+    GC.@preserve arrs ptrs check(e.ctx, ccall((:lh_soil_set_column_fluxes, LIB), Int32, (Ptr{Cvoid}, Ptr{Ptr{Cdouble}}), e.ctx, ptrs))
+    return nothing
+end
+
+"compute_turbulent_surface_fluxes (boundary_conditions.jl:555-620) for surface states, evaluated on the device."
+function surface_fluxes(e::Engine, ϑ_l::Vector{Float64}, θ_i::Vector{Float64}, T::Vector{Float64})
+    heat, water = similar(T), similar(T)
+    check(e.ctx, ccall((:lh_soil_atmos_fluxes, LIB), Int32,
+        (Ptr{Cvoid}, Ptr{Cdouble}, Ptr{Cdouble}, Ptr{Cdouble}, Int64, Ptr{Cdouble}, Ptr{Cdouble}), e.ctx, ϑ_l, θ_i, T, length(T), heat, water))
+    return heat, water
 end
 
 # ---- multi-GPU: one process per GPU, contiguous column shards, NCCL only for the budgets -------------------------

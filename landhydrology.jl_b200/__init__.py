@@ -36,7 +36,7 @@ from .domains import (
     ndims,
     size,
 )
-from .engine import SoilEngine, build_config, build_params, engine_for, use_library
+from .engine import SoilEngine, build_atmos, build_config, build_params, engine_for, use_library
 from .models import (
     AbstractBC,
     AbstractModel,
@@ -57,8 +57,8 @@ from .models import (
 )
 from .parameterizations import *  # noqa: F401,F403  (the reference exports every closure)
 from .parameterizations import EarthParameterSet
-from .rhs import make_rhs, make_update_aux
-from .sharding import ColumnShards, init_budget_comm, shard_range
+from .rhs import boundary_fluxes, compute_turbulent_surface_fluxes, make_rhs, make_update_aux
+from .sharding import ColumnShards, bind_to_gpu_numa_node, gpu_numa_cpus, init_budget_comm, shard_range
 from .simulations import (SSPRK22, SSPRK33, SSPRK43, CarpenterKennedy2N54, Euler, LowStorageRK2N, ShuOsherRK,
                           Simulation, run_, step_)
 from .states import (

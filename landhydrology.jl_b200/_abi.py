@@ -123,6 +123,17 @@ _dp = C.POINTER(C.c_double)
 _vp = C.c_void_p
 
 
+class lh_soil_atmos(C.Structure):
+    """PrescribedAtmosForcing + the constants its fluxes need (include/lh_soil.h)."""
+    _fields_ = [("struct_size", C.c_int32), ("reserved", C.c_int32)] + [(n, C.c_double) for n in (
+        "u_atm", "theta_atm", "z_atm", "theta_scale", "rho_a_sfc", "q_atm",
+        "R_v", "R_d", "grav", "cp_d", "cp_v", "LH_v0", "press_triple", "T_triple", "von_karman", "Pr_0", "a_m", "a_h")]
+
+    def __init__(self, *a, **kw):
+        super().__init__(*a, **kw)
+        self.struct_size = C.sizeof(lh_soil_atmos)
+
+
 class lh_soil_run_opts(C.Structure):
     _fields_ = [
         ("struct_size", C.c_int32), ("save_first", C.c_int32), ("bc_table", _dp),
@@ -148,6 +159,10 @@ _SIGNATURES = {
     "soil_get_state": ([_vp, C.c_int32, _dp, C.c_int64, C.c_int64], C.c_int32),
     "soil_set_aux": ([_vp, C.c_int32, _dp, C.c_int64, C.c_int64], C.c_int32),
     "soil_set_column_params": ([_vp, _dp, _dp, _dp, _dp, _dp], C.c_int32),
+    "soil_set_column_heat_params": ([_vp, _dp, _dp, _dp, _dp, _dp, _dp, _dp], C.c_int32),
+    "soil_set_column_fluxes": ([_vp, C.POINTER(_dp)], C.c_int32),
+    "soil_set_atmos_forcing": ([_vp, C.POINTER(lh_soil_atmos)], C.c_int32),
+    "soil_atmos_fluxes": ([_vp, _dp, _dp, _dp, C.c_int64, _dp, _dp], C.c_int32),
     "soil_set_bc_values": ([_vp, _dp], C.c_int32),
     "soil_rhs": ([_vp, C.c_double], C.c_int32),
     "soil_get_tendency": ([_vp, C.c_int32, _dp, C.c_int64, C.c_int64], C.c_int32),
@@ -347,6 +362,46 @@ class SoilContext:
             keep.append(a)
             ptrs.append(_as_double_ptr(a))
         self._check(self.lib.soil_set_column_params(self._h, *ptrs))
+
+    def set_column_heat_params(self, rho_c_ds=None, kappa_sat_unfrozen=None, kappa_sat_frozen=None, kappa_solid=None,
+                               nu_ss_om=None, nu_ss_quartz=None, nu_ss_gravel=None):
+        """``lh_soil_set_column_heat_params``: per-column heat parameters (arrays of ncol doubles; None keeps the scalar)."""
+        arrs = []
+        for a in (rho_c_ds, kappa_sat_unfrozen, kappa_sat_frozen, kappa_solid, nu_ss_om, nu_ss_quartz, nu_ss_gravel):
+            if a is None:
+                arrs.append(None)
+                continue
+            a = np.ascontiguousarray(a, dtype=np.float64)
+            if a.shape != (self.ncol,):
+                raise ValueError(f"per-column parameter must have shape ({self.ncol},)")
+            arrs.append(a)
+        self._check(self.lib.soil_set_column_heat_params(self._h, *[None if a is None else _as_double_ptr(a) for a in arrs]))
+
+    def set_column_fluxes(self, top_energy=None, top_hydrology=None, bottom_energy=None, bottom_hydrology=None):
+        """``lh_soil_set_column_fluxes``: per-column VerticalFlux values (arrays of ncol doubles) for faces of kind LH_BC_FLUX."""
+        arrs = []
+        for a in (top_energy, top_hydrology, bottom_energy, bottom_hydrology):
+            if a is None:
+                arrs.append(None)
+                continue
+            a = np.ascontiguousarray(a, dtype=np.float64)
+            if a.shape != (self.ncol,):
+                raise ValueError(f"per-column flux must have shape ({self.ncol},)")
+            arrs.append(a)
+        ptrs = (_dp * 4)(*[None if a is None else _as_double_ptr(a) for a in arrs])
+        self._check(self.lib.soil_set_column_fluxes(self._h, ptrs))
+
+    def set_atmos_forcing(self, atmos: Optional["lh_soil_atmos"]):
+        """``lh_soil_set_atmos_forcing``: PrescribedAtmosForcing at the top face (None: back to the configured top BC)."""
+        self._check(self.lib.soil_set_atmos_forcing(self._h, None if atmos is None else C.byref(atmos)))
+
+    def atmos_fluxes(self, theta_l, theta_i, T):
+        """``compute_turbulent_surface_fluxes`` for given surface states: (heat flux, water volume flux) arrays."""
+        th, ti, T = (np.ascontiguousarray(np.atleast_1d(x), dtype=np.float64) for x in (theta_l, theta_i, T))
+        heat, water = np.empty_like(th), np.empty_like(th)
+        self._check(self.lib.soil_atmos_fluxes(self._h, _as_double_ptr(th), _as_double_ptr(ti), _as_double_ptr(T), th.size,
+                                                _as_double_ptr(heat), _as_double_ptr(water)))
+        return heat, water
 
     def set_bc_values(self, values: Sequence[float]):
         v = np.asarray(values, dtype=np.float64)

@@ -84,7 +84,10 @@ struct LhLaneParams : LhPhys {
 
 // Per-column derived parameters, one [ncol_pad] array each (lh_soil_api.cu derive_column_params).
 enum { LHCP_NU, LHCP_THETA_R, LHCP_THETA_R_EPS, LHCP_INV_NU_THR, LHCP_NU_THR, LHCP_VG_M, LHCP_VG_INV_M, LHCP_VG_INV_N,
-       LHCP_NEG_INV_ALPHA, LHCP_KSAT, LHCP_INV_NU, LHCP_KAPPA_DRY, LHCP_COUNT };
+       LHCP_NEG_INV_ALPHA, LHCP_KSAT, LHCP_INV_NU, LHCP_KAPPA_DRY,
+       // heat parameters (lh_soil_set_column_heat_params; read by the HETH variants only)
+       LHCP_RHO_C_DS, LHCP_KERSTEN_P1, LHCP_KERSTEN_P2, LHCP_KERSTEN_P3, LHCP_K_UNFROZEN, LHCP_LOG2_K_UNFROZEN, LHCP_LOG2_K_FROZEN,
+       LHCP_COUNT };
 
 // Copies the exp2 / log2 tables from the parameter block, and the fixed-exponent power tables from `pow_tab`
 // (LHPW_COUNT * LH_POW_DOUBLES doubles in global memory, written once by lh_soil_create), to shared memory
@@ -124,6 +127,10 @@ struct LhCell {
 //   HET : per-column hydraulic parameters (lh_soil_set_column_params): nu, theta_r, van Genuchten n and alpha, Ksat
 //         and what derives from them are per-lane values.  Implies GEN and excludes VG2.
 #define LH_FLAG_HET 8
+//   HETH: per-column HEAT parameters too (lh_soil_set_column_heat_params): rho_c_ds, kappa_sat_unfrozen / frozen, and the
+//         Kersten exponents that follow nu_ss_om / nu_ss_quartz / nu_ss_gravel.  Implies HET; nu_ss_om may differ from column
+//         to column, so the outer Kersten exponents are always evaluated (no om_zero shortcut).
+#define LH_FLAG_HETH 16
 
 // ---------------------------------------------------------------------------------------------
 // Water: K and psi of one cell.  Reference: right_hand_side.jl:156-166 / :308-313.

@@ -21,6 +21,7 @@
 // in global memory, and writes a cell after its last read of it.
 #include "lh_kernels.cuh"
 
+#include "lh_atmos.cuh"
 #include "lh_soil.h"
 
 #include <stdlib.h>
@@ -29,9 +30,13 @@
 #define LH_MIN_CHUNK 16
 #endif
 
-cudaError_t lh_launch_stage_m0(int, int, const LhKernelArgs&, const LhLaunchShape&, cudaStream_t);
-cudaError_t lh_launch_stage_m1(int, int, const LhKernelArgs&, const LhLaunchShape&, cudaStream_t);
-cudaError_t lh_launch_stage_m2(int, int, const LhKernelArgs&, const LhLaunchShape&, cudaStream_t);
+#define LH_DECL_STAGE(M) \
+    cudaError_t lh_launch_stage_m##M##_g0(int, int, const LhKernelArgs&, const LhLaunchShape&, cudaStream_t); \
+    cudaError_t lh_launch_stage_m##M##_g1(int, int, const LhKernelArgs&, const LhLaunchShape&, cudaStream_t); \
+    cudaError_t lh_launch_stage_m##M##_g2(int, int, const LhKernelArgs&, const LhLaunchShape&, cudaStream_t);
+LH_DECL_STAGE(0)
+LH_DECL_STAGE(1)
+LH_DECL_STAGE(2)
 cudaError_t lh_launch_persistent_m0(int, const LhKernelArgs&, const LhLaunchShape&, cudaStream_t);
 cudaError_t lh_launch_persistent_m1(int, const LhKernelArgs&, const LhLaunchShape&, cudaStream_t);
 cudaError_t lh_launch_persistent_m2(int, const LhKernelArgs&, const LhLaunchShape&, cudaStream_t);
@@ -81,11 +86,12 @@ cudaError_t lh_launch_stage(int model, int stage, int flags, const LhKernelArgs&
 {
     if (model < 0 || model > 2) return cudaErrorInvalidValue;
     if (shape.W * shape.G > shape.warp_budget || shape.smem_bytes > 226 * 1024) return cudaErrorInvalidConfiguration;
-    switch (model) {
-    case 0: return lh_launch_stage_m0(stage, flags, args, shape, stream);
-    case 1: return lh_launch_stage_m1(stage, flags, args, shape, stream);
-    default: return lh_launch_stage_m2(stage, flags, args, shape, stream);
-    }
+    if (stage < 0 || stage > 5) return cudaErrorInvalidValue;
+    typedef cudaError_t (*launch_fn)(int, int, const LhKernelArgs&, const LhLaunchShape&, cudaStream_t);
+    static const launch_fn table[3][3] = {{lh_launch_stage_m0_g0, lh_launch_stage_m0_g1, lh_launch_stage_m0_g2},
+                                          {lh_launch_stage_m1_g0, lh_launch_stage_m1_g1, lh_launch_stage_m1_g2},
+                                          {lh_launch_stage_m2_g0, lh_launch_stage_m2_g1, lh_launch_stage_m2_g2}};
+    return table[model][stage / 2](stage, flags, args, shape, stream);
 }
 
 cudaError_t lh_launch_ssprk33_persistent(int model, int flags, const LhKernelArgs& args, const LhLaunchShape& shape,
@@ -105,7 +111,7 @@ cudaError_t lh_launch_ssprk33_persistent(int model, int flags, const LhKernelArg
 // -------------------------------------------------------------------------------------------------
 namespace {
 // The per-lane parameter view of column `col` (see lh_stage_body).
-__device__ __forceinline__ LhLaneParams lh_lane_params(const LhDevParams& p, const double* colp, int64_t col, int64_t st)
+__device__ __forceinline__ LhLaneParams lh_lane_params(const LhDevParams& p, const double* colp, int64_t col, int64_t st, bool heat)
 {
     LhLaneParams pl;
     static_cast<LhPhys&>(pl) = static_cast<const LhPhys&>(p);
@@ -124,7 +130,17 @@ __device__ __forceinline__ LhLaneParams lh_lane_params(const LhDevParams& p, con
         pl.Ksat = cp[LHCP_KSAT * st];
         pl.inv_nu = cp[LHCP_INV_NU * st];
         pl.kappa_dry = cp[LHCP_KAPPA_DRY * st];
-        pl.k_unfrozen_minus_dry = p.k_unfrozen - pl.kappa_dry;
+        if (heat) {
+            pl.rho_c_ds = cp[LHCP_RHO_C_DS * st];
+            pl.kersten_p1 = cp[LHCP_KERSTEN_P1 * st];
+            pl.kersten_p2 = cp[LHCP_KERSTEN_P2 * st];
+            pl.kersten_p3 = cp[LHCP_KERSTEN_P3 * st];
+            pl.k_unfrozen = cp[LHCP_K_UNFROZEN * st];
+            pl.log2_k_unfrozen = cp[LHCP_LOG2_K_UNFROZEN * st];
+            pl.log2_k_frozen = cp[LHCP_LOG2_K_FROZEN * st];
+            pl.om_zero = 0;
+        }
+        pl.k_unfrozen_minus_dry = pl.k_unfrozen - pl.kappa_dry;
     }
     return pl;
 }
@@ -154,7 +170,7 @@ template <int MODEL, bool HET>
 __global__ void lh_diag_kernel(const __grid_constant__ LhDevParams pu, const double* __restrict__ pow_tab, int which,
                                const double* __restrict__ th, const double* __restrict__ ti, const double* __restrict__ re,
                                const double* __restrict__ T, double* __restrict__ out, int64_t n,
-                               const double* __restrict__ colp, int64_t ncol_pad)
+                               const double* __restrict__ colp, int64_t ncol_pad, int heat)
 {
     __shared__ __align__(16) double tab[LH_TAB_ALL];
     lh_stage_tables(pu, pow_tab, tab, threadIdx.x, blockDim.x);
@@ -163,7 +179,7 @@ __global__ void lh_diag_kernel(const __grid_constant__ LhDevParams pu, const dou
     if (i >= n) return;
     const double x = MODEL == 0 ? T[i] : re[i];
     if constexpr (HET) {
-        const LhLaneParams p = lh_lane_params(pu, colp, i % ncol_pad, ncol_pad);
+        const LhLaneParams p = lh_lane_params(pu, colp, i % ncol_pad, ncol_pad, heat != 0);
         out[i] = lh_diag_value<MODEL>(p, tab, which, th[i], ti[i], x);
     } else {
         out[i] = lh_diag_value<MODEL>(pu, tab, which, th[i], ti[i], x);
@@ -173,17 +189,96 @@ __global__ void lh_diag_kernel(const __grid_constant__ LhDevParams pu, const dou
 
 cudaError_t lh_launch_diagnostic(int model, int which, const LhDevParams& p, const double* pow_tab, const double* th,
                                  const double* ti, const double* re, const double* T, double* out,
-                                 int64_t n, const double* colp, int64_t ncol_pad, cudaStream_t stream)
+                                 int64_t n, const double* colp, int64_t ncol_pad, int heat, cudaStream_t stream)
 {
     const int block = 256;
     const unsigned grid = (unsigned)((n + block - 1) / block);
     if (model == LH_MODEL_RICHARDS) {
-        if (colp) lh_diag_kernel<0, true><<<grid, block, 0, stream>>>(p, pow_tab, which, th, ti, re, T, out, n, colp, ncol_pad);
-        else lh_diag_kernel<0, false><<<grid, block, 0, stream>>>(p, pow_tab, which, th, ti, re, T, out, n, colp, ncol_pad);
+        if (colp) lh_diag_kernel<0, true><<<grid, block, 0, stream>>>(p, pow_tab, which, th, ti, re, T, out, n, colp, ncol_pad, heat);
+        else lh_diag_kernel<0, false><<<grid, block, 0, stream>>>(p, pow_tab, which, th, ti, re, T, out, n, colp, ncol_pad, heat);
     } else {
-        if (colp) lh_diag_kernel<2, true><<<grid, block, 0, stream>>>(p, pow_tab, which, th, ti, re, T, out, n, colp, ncol_pad);
-        else lh_diag_kernel<2, false><<<grid, block, 0, stream>>>(p, pow_tab, which, th, ti, re, T, out, n, colp, ncol_pad);
+        if (colp) lh_diag_kernel<2, true><<<grid, block, 0, stream>>>(p, pow_tab, which, th, ti, re, T, out, n, colp, ncol_pad, heat);
+        else lh_diag_kernel<2, false><<<grid, block, 0, stream>>>(p, pow_tab, which, th, ti, re, T, out, n, colp, ncol_pad, heat);
     }
+    return cudaGetLastError();
+}
+
+// -------------------------------------------------------------------------------------------------
+// PrescribedAtmosForcing: turbulent surface fluxes per column (lh_atmos.cuh)
+// -------------------------------------------------------------------------------------------------
+namespace {
+// Matric potential at min(S_l_eff, 1) (boundary_conditions.jl:588-591) from the general water closures.
+template <class P>
+__device__ __forceinline__ double lh_surface_matric_potential(const P& p, const double* tab, double th, double ti)
+{
+    double K, psi, l_;
+    LhPowArg a_;
+    lh_water_closures<true, true, false, false>(p, tab, th, ti, 288.0, K, psi, l_, a_);
+    const double nu_eff = p.nu - ti;
+    return th < nu_eff ? psi : 0.0;            // saturated or oversaturated: S_l_eff = 1, matric_potential(1) = 0
+}
+
+template <bool HET>
+__global__ void lh_atmos_flux_kernel(const __grid_constant__ LhDevParams pu, const double* __restrict__ pow_tab, const LhAtmos atm,
+                                     const double* __restrict__ th_top, const double* __restrict__ ti_top,
+                                     const double* __restrict__ re_top, double* __restrict__ flux_e, double* __restrict__ flux_w,
+                                     int64_t ncol_pad, const double* __restrict__ colp, int heat_cols)
+{
+    __shared__ __align__(16) double tab[LH_TAB_ALL];
+    lh_stage_tables(pu, pow_tab, tab, threadIdx.x, blockDim.x);
+    __syncthreads();
+    const int64_t col = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (col >= ncol_pad) return;
+    const double th = th_top[col], ti = ti_top[col], re = re_top[col];
+    double psi, dT;
+    if constexpr (HET) {
+        const LhLaneParams p = lh_lane_params(pu, colp, col, ncol_pad, heat_cols != 0);
+        const double nu_eff = p.nu - ti;
+        dT = lh_temperature_minus_T0<true>(p, th < nu_eff ? th : nu_eff, ti, re);
+        psi = lh_surface_matric_potential(p, tab, th, ti);
+    } else {
+        const double nu_eff = pu.nu - ti;
+        dT = lh_temperature_minus_T0<true>(pu, th < nu_eff ? th : nu_eff, ti, re);
+        psi = lh_surface_matric_potential(pu, tab, th, ti);
+    }
+    double heat, water;
+    lh_atmos_fluxes(atm, psi, pu.T_0 + dT, heat, water);
+    flux_e[col] = heat;
+    flux_w[col] = water;
+}
+
+__global__ void lh_atmos_eval_kernel(const __grid_constant__ LhDevParams pu, const double* __restrict__ pow_tab, const LhAtmos atm,
+                                     const double* __restrict__ th, const double* __restrict__ ti, const double* __restrict__ T,
+                                     double* __restrict__ heat, double* __restrict__ water, int64_t n)
+{
+    __shared__ __align__(16) double tab[LH_TAB_ALL];
+    lh_stage_tables(pu, pow_tab, tab, threadIdx.x, blockDim.x);
+    __syncthreads();
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const double psi = lh_surface_matric_potential(pu, tab, th[i], ti[i]);
+    double h, w;
+    lh_atmos_fluxes(atm, psi, T[i], h, w);
+    heat[i] = h;
+    water[i] = w;
+}
+}  // namespace
+
+cudaError_t lh_launch_atmos_fluxes(const LhDevParams& p, const double* pow_tab, const LhAtmos& atm, const double* th_top,
+                                   const double* ti_top, const double* re_top, double* flux_e, double* flux_w, int64_t ncol_pad,
+                                   const double* colp, int heat_cols, cudaStream_t stream)
+{
+    const int block = 128;
+    const unsigned grid = (unsigned)((ncol_pad + block - 1) / block);
+    if (colp) lh_atmos_flux_kernel<true><<<grid, block, 0, stream>>>(p, pow_tab, atm, th_top, ti_top, re_top, flux_e, flux_w, ncol_pad, colp, heat_cols);
+    else lh_atmos_flux_kernel<false><<<grid, block, 0, stream>>>(p, pow_tab, atm, th_top, ti_top, re_top, flux_e, flux_w, ncol_pad, colp, heat_cols);
+    return cudaGetLastError();
+}
+
+cudaError_t lh_launch_atmos_eval(const LhDevParams& p, const double* pow_tab, const LhAtmos& atm, const double* th, const double* ti,
+                                 const double* T, double* heat, double* water, int64_t n, cudaStream_t stream)
+{
+    lh_atmos_eval_kernel<<<(unsigned)((n + 127) / 128), 128, 0, stream>>>(p, pow_tab, atm, th, ti, T, heat, water, n);
     return cudaGetLastError();
 }
 

@@ -32,6 +32,8 @@ struct LhStageIO {
     double* out2_th;       // 2N stages (STAGE 5): the residual register r, updated in place (== u0_th)
     double* out2_re;
     double bcv[4];         // LH_BCV_* boundary values for THIS stage
+    const double* flux_cols[4];   // per-column VerticalFlux values (LH_BCV_* order) or NULL: the scalar in bcv applies.
+                                  // Also how PrescribedAtmosForcing arrives: lh_atmos_flux_kernel fills two arrays per stage.
     double dt;
     double sa, sb, sg;     // stage coefficients of the generic steppers (STAGE 4: a, b, g; STAGE 5: a, b)
     int32_t first2n;       // STAGE 5, first stage: r is not read (a == 0 and r may hold anything)
@@ -88,7 +90,17 @@ cudaError_t lh_launch_any_nonzero(const double* x, int64_t n, int* flag, cudaStr
 // Pointwise diagnostics (LH_DIAG_*): out[layer*ncol_pad+col].
 cudaError_t lh_launch_diagnostic(int model, int which, const LhDevParams& p, const double* pow_tab, const double* th,
                                  const double* ti, const double* re, const double* T, double* out,
-                                 int64_t ncells_pad, const double* colp, int64_t ncol_pad, cudaStream_t stream);
+                                 int64_t ncells_pad, const double* colp, int64_t ncol_pad, int heat, cudaStream_t stream);
+
+// PrescribedAtmosForcing (lh_atmos.cuh): per column, from the top cell (layer nlayer-1) of the stage input, the turbulent
+// heat flux and water volume flux into flux_e[col], flux_w[col].
+struct LhAtmos;
+cudaError_t lh_launch_atmos_fluxes(const LhDevParams& p, const double* pow_tab, const LhAtmos& atm, const double* th_top,
+                                   const double* ti_top, const double* re_top, double* flux_e, double* flux_w, int64_t ncol_pad,
+                                   const double* colp, int heat_cols, cudaStream_t stream);
+// The same for n given surface states (theta_l, theta_i, T): lh_soil_atmos_fluxes.
+cudaError_t lh_launch_atmos_eval(const LhDevParams& p, const double* pow_tab, const LhAtmos& atm, const double* th, const double* ti,
+                                 const double* T, double* heat, double* water, int64_t n, cudaStream_t stream);
 
 // Deterministic budgets: out2[0] = sum ϑ_l dz, out2[1] = sum ρe_int dz over columns < ncol.
 cudaError_t lh_launch_budgets(const double* th, const double* re, int64_t ncol, int64_t ncol_pad,

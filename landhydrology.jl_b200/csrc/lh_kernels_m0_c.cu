@@ -1,0 +1,7 @@
+// lh_kernels_m0_c.cu — stage-kernel variants of MODEL = 0 (Richards): the generic Shu-Osher and 2N stages.
+#include "lh_stage_kernel.cuh"
+
+cudaError_t lh_launch_stage_m0_g2(int stage, int flags, const LhKernelArgs& args, const LhLaunchShape& shape, cudaStream_t stream)
+{
+    return launch_model<0, 2>(stage, flags, args, shape, stream);
+}

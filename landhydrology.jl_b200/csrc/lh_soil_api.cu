@@ -17,6 +17,7 @@
 #include <new>
 #include <vector>
 
+#include "lh_atmos.cuh"
 #include "lh_kernels.cuh"
 
 // ------------------------------------------------------------------------------------------------
@@ -97,6 +98,10 @@ struct lh_soil_ctx {
     int64_t budget_ticket[BUDGET_SLOTS] = {};    // ticket whose result the slot holds (0: free)
     int64_t budget_next_ticket = 1;
     double* colp_dev = nullptr;                  // [LHCP_COUNT][ncol_pad] per-column derived parameters (heterogeneous soils)
+    // what the host supplied: nu, theta_r, vg_n, vg_alpha, Ksat | rho_c_ds, kappa_sat_unfrozen, kappa_sat_frozen, kappa_solid,
+    // nu_ss_om, nu_ss_quartz, nu_ss_gravel (empty: the model's scalar)
+    std::vector<double> col_user[12];
+    bool col_heat = false;                       // some heat parameter is per column -> LH_FLAG_HETH
     double* pow_tab_dev = nullptr;               // LHPW_COUNT fixed-exponent power tables (lh_math.cuh), built at create
     std::vector<double> pow_tab;                 // their host copy
     double* diag_dev = nullptr;                  // scratch field of lh_soil_diagnostic (lazily allocated)
@@ -105,6 +110,10 @@ struct lh_soil_ctx {
     int64_t fused_nblocks = 0;
     bool budget_fresh = false;                   // fused_partials describe the current state U
     bool external_writes = false;                // lh_soil_device_ptr handed out U: never trust the fused sums
+    double* flux_cols_dev[4] = {nullptr, nullptr, nullptr, nullptr};   // lh_soil_set_column_fluxes: [ncol_pad] each, LH_BCV_* order
+    bool atmos_on = false;                       // lh_soil_set_atmos_forcing: the top face takes the turbulent surface fluxes
+    LhAtmos atmos;
+    double* atm_flux_dev[2] = {nullptr, nullptr};   // per-column heat / water fluxes of the current stage (lh_atmos_flux_kernel)
     int32_t* chain_dev = nullptr;                // per-block completion flags of the stage launches (LhKernelArgs::chain_flags)
     int64_t chain_cap = 0;                       // blocks the flag array holds
     int32_t chain_seq = 0;                       // value the last stage launch published; only ever grows, so that a flag
@@ -265,6 +274,8 @@ void free_all(lh_soil_ctx* c)
     for (auto& e : c->budget_ev) if (e) cudaEventDestroy(e);
     if (c->bc_dev) cudaFree(c->bc_dev);
     if (c->chain_dev) cudaFree(c->chain_dev);
+    for (auto& p : c->flux_cols_dev) if (p) cudaFree(p);
+    for (auto& p : c->atm_flux_dev) if (p) cudaFree(p);
     for (auto& p : c->aux_tab_dev) if (p) cudaFree(p);
     if (c->hist_dev) cudaFree(c->hist_dev);
     if (c->hist_host) cudaFreeHost(c->hist_host);
@@ -429,7 +440,7 @@ void update_kernel_flags(lh_soil_ctx* c)
                      (c->model == LH_MODEL_COUPLED && q.theta_r != 0.0);
     const bool vg2 = !het && q.vg_n == 2.0 && q.vg_m == 0.5;      // S^(1/m) = S^2, x^m = sqrt(x): no log/exp needed
     c->kernel_flags = (c->has_ice ? LH_FLAG_ICE : 0) | (gen ? LH_FLAG_GEN : 0) | (vg2 && !c->force_general_vg ? LH_FLAG_VG2 : 0) |
-                      (het ? LH_FLAG_HET : 0);
+                      (het ? LH_FLAG_HET : 0) | (het && c->col_heat && has_heat(c->model) ? LH_FLAG_HETH : 0);
     c->shape = lh_choose_shape(c->model, c->ncol_pad, c->nlayer, c->sm_count, het);   // the HET variants have a smaller warp budget
     c->budget_fresh = false;
     // The block -> column-group map may have changed: the next stage launch takes the full grid dependency.  (The flags
@@ -493,6 +504,7 @@ void fill_args(lh_soil_ctx* c, int stage, double dt, LhKernelArgs& a)
     a.bot_e_kind = c->cfg.bottom.energy_kind;
     a.bot_h_kind = c->cfg.bottom.hydrology_kind;
     memcpy(a.io.bcv, c->bcv, sizeof a.io.bcv);
+    for (int k = 0; k < 4; ++k) a.io.flux_cols[k] = c->flux_cols_dev[k];
     a.io.dt = dt;
     a.io.out2_th = c->V[0];
     a.io.out2_re = c->V[2];
@@ -511,6 +523,18 @@ void fill_args(lh_soil_ctx* c, int stage, double dt, LhKernelArgs& a)
 // early) is fully ordered before the launch by the stream itself.
 cudaError_t launch_chained(lh_soil_ctx* c, int stage, LhKernelArgs& a)
 {
+    if (c->atmos_on) {
+        // boundary_fluxes(X, bc::PrescribedAtmosForcing, :top, ...) (boundary_conditions.jl:516-536): one Monin-Obukhov solve per
+        // column from the top cell of THIS stage's input, then the stage kernel takes the two arrays as per-column fluxes.
+        const int64_t top = (int64_t)(c->nlayer - 1) * c->ncol_pad;
+        cudaError_t e = lh_launch_atmos_fluxes(c->dp, c->pow_tab_dev, c->atmos, a.io.in_th + top, a.io.in_ti + top, a.io.in_re + top,
+                                               c->atm_flux_dev[0], c->atm_flux_dev[1], c->ncol_pad, c->colp_dev, c->col_heat ? 1 : 0, c->stream);
+        if (e != cudaSuccess) return e;
+        a.top_e_kind = LH_BC_FLUX;
+        a.top_h_kind = LH_BC_FLUX;
+        a.io.flux_cols[LH_BCV_TOP_ENERGY] = c->atm_flux_dev[0];
+        a.io.flux_cols[LH_BCV_TOP_HYDROLOGY] = c->atm_flux_dev[1];
+    }
     if (c->chain_dev && !(c->cfg.flags & LH_FLAG_NO_CHAIN)) {
         a.chain_flags = c->chain_dev;
         if (c->chain_seq == 0x7fffffff) {                // (2^31 launches: start over behind a full synchronisation)
@@ -711,31 +735,35 @@ int32_t lh_soil_get_state(lh_soil_ctx* c, int32_t field, double* host, int64_t c
     return download_field(c, c->U[field], host, cs, ls);
 }
 
-int32_t lh_soil_set_column_params(lh_soil_ctx* c, const double* nu, const double* theta_r, const double* vg_n,
-                                  const double* vg_alpha, const double* Ksat)
+// Derive, per column, exactly what derive_phys derives for the model (same expressions, same rounding) from the host's
+// per-column arrays, and upload the table the HET / HETH kernels read per lane.
+static int32_t rebuild_column_params(lh_soil_ctx* c)
 {
-    if (!c) return LH_ERR_INVALID_ARG;
     LH_CUDA(c, cudaSetDevice(c->device));
     LH_CUDA(c, cudaStreamSynchronize(c->stream));
-    if (!nu && !theta_r && !vg_n && !vg_alpha && !Ksat) {      // back to the homogeneous kernels
+    bool any = false, heat = false;
+    for (int k = 0; k < 12; ++k) { any |= !c->col_user[k].empty(); if (k >= 5) heat |= !c->col_user[k].empty(); }
+    c->col_heat = heat;
+    if (!any) {                                                    // back to the homogeneous kernels
         if (c->colp_dev) { LH_CUDA(c, cudaFree(c->colp_dev)); c->colp_dev = nullptr; }
         update_kernel_flags(c);
         return LH_OK;
     }
-    // derive, per column, exactly what derive_params derives for the model (same expressions, same rounding)
-    const lh_soil_params& q0 = c->cfg.params;
     std::vector<double> h((size_t)LHCP_COUNT * c->ncol_pad);
     for (int64_t j = 0; j < c->ncol_pad; ++j) {
         const int64_t col = std::min<int64_t>(j, c->ncol - 1);                  // padding replicates the last column
         lh_soil_config cfg = c->cfg;
         lh_soil_params& q = cfg.params;
-        if (nu) q.nu = nu[col];
-        if (theta_r) q.theta_r = theta_r[col];
-        if (vg_n) { q.vg_n = vg_n[col]; q.vg_m = 1.0 - 1.0 / q.vg_n; }          // the reference constructor's m
-        if (vg_alpha) q.vg_alpha = vg_alpha[col];
-        if (Ksat) q.Ksat = Ksat[col];
+        auto get = [&](int k, double& dst) { if (!c->col_user[k].empty()) dst = c->col_user[k][col]; };
+        get(0, q.nu); get(1, q.theta_r);
+        if (!c->col_user[2].empty()) { q.vg_n = c->col_user[2][col]; q.vg_m = 1.0 - 1.0 / q.vg_n; }   // the reference constructor's m
+        get(3, q.vg_alpha); get(4, q.Ksat);
+        get(5, q.rho_c_ds); get(6, q.kappa_sat_unfrozen); get(7, q.kappa_sat_frozen); get(8, q.kappa_solid);
+        get(9, q.nu_ss_om); get(10, q.nu_ss_quartz); get(11, q.nu_ss_gravel);
         if (!(q.nu > q.theta_r) || !(q.vg_n > 1.0) || !(q.vg_alpha > 0.0) || !std::isfinite(q.Ksat))
             return fail(c, LH_ERR_INVALID_ARG, "column %lld: need nu > theta_r, vg_n > 1, vg_alpha > 0, finite Ksat", (long long)col);
+        if (!(q.kappa_sat_unfrozen > 0.0) || !(q.kappa_sat_frozen > 0.0) || !std::isfinite(q.rho_c_ds))
+            return fail(c, LH_ERR_INVALID_ARG, "column %lld: need kappa_sat_unfrozen > 0, kappa_sat_frozen > 0, finite rho_c_ds", (long long)col);
         LhPhys d;
         derive_phys(cfg, d);
         double* o = h.data() + j;
@@ -745,12 +773,106 @@ int32_t lh_soil_set_column_params(lh_soil_ctx* c, const double* nu, const double
         o[LHCP_VG_M * st] = d.vg_m; o[LHCP_VG_INV_M * st] = d.vg_inv_m; o[LHCP_VG_INV_N * st] = d.vg_inv_n;
         o[LHCP_NEG_INV_ALPHA * st] = d.neg_inv_alpha; o[LHCP_KSAT * st] = d.Ksat;
         o[LHCP_INV_NU * st] = d.inv_nu; o[LHCP_KAPPA_DRY * st] = d.kappa_dry;
+        o[LHCP_RHO_C_DS * st] = d.rho_c_ds; o[LHCP_KERSTEN_P1 * st] = d.kersten_p1; o[LHCP_KERSTEN_P2 * st] = d.kersten_p2;
+        o[LHCP_KERSTEN_P3 * st] = d.kersten_p3; o[LHCP_K_UNFROZEN * st] = d.k_unfrozen;
+        o[LHCP_LOG2_K_UNFROZEN * st] = d.log2_k_unfrozen; o[LHCP_LOG2_K_FROZEN * st] = d.log2_k_frozen;
     }
     if (!c->colp_dev) LH_CUDA(c, cudaMalloc(&c->colp_dev, h.size() * sizeof(double)));
     LH_CUDA(c, cudaMemcpyAsync(c->colp_dev, h.data(), h.size() * sizeof(double), cudaMemcpyHostToDevice, c->stream));
     LH_CUDA(c, cudaStreamSynchronize(c->stream));
-    (void)q0;
     update_kernel_flags(c);
+    return LH_OK;
+}
+
+static void keep_user_columns(lh_soil_ctx* c, int first, int count, const double* const* src)
+{
+    for (int k = 0; k < count; ++k) {
+        if (src[k]) c->col_user[first + k].assign(src[k], src[k] + c->ncol);
+        else c->col_user[first + k].clear();
+    }
+}
+
+int32_t lh_soil_set_column_params(lh_soil_ctx* c, const double* nu, const double* theta_r, const double* vg_n,
+                                  const double* vg_alpha, const double* Ksat)
+{
+    if (!c) return LH_ERR_INVALID_ARG;
+    const double* src[5] = {nu, theta_r, vg_n, vg_alpha, Ksat};
+    keep_user_columns(c, 0, 5, src);
+    return rebuild_column_params(c);
+}
+
+int32_t lh_soil_set_column_heat_params(lh_soil_ctx* c, const double* rho_c_ds, const double* kappa_sat_unfrozen,
+                                       const double* kappa_sat_frozen, const double* kappa_solid, const double* nu_ss_om,
+                                       const double* nu_ss_quartz, const double* nu_ss_gravel)
+{
+    if (!c) return LH_ERR_INVALID_ARG;
+    if (!has_heat(c->model) && (rho_c_ds || kappa_sat_unfrozen || kappa_sat_frozen || kappa_solid || nu_ss_om || nu_ss_quartz || nu_ss_gravel))
+        return fail(c, LH_ERR_INVALID_ARG, "model kind %d has no energy equation: no heat parameters to set", c->model);
+    const double* src[7] = {rho_c_ds, kappa_sat_unfrozen, kappa_sat_frozen, kappa_solid, nu_ss_om, nu_ss_quartz, nu_ss_gravel};
+    keep_user_columns(c, 5, 7, src);
+    return rebuild_column_params(c);
+}
+
+int32_t lh_soil_set_column_fluxes(lh_soil_ctx* c, const double* const values[4])
+{
+    if (!c) return LH_ERR_INVALID_ARG;
+    const int kinds[4] = {c->cfg.top.energy_kind, c->cfg.top.hydrology_kind, c->cfg.bottom.energy_kind, c->cfg.bottom.hydrology_kind};
+    for (int k = 0; k < 4; ++k)
+        if (values && values[k] && kinds[k] != LH_BC_FLUX) return fail(c, LH_ERR_INVALID_ARG, "per-column fluxes need a face of kind LH_BC_FLUX (boundary value %d is of kind %d)", k, kinds[k]);
+    LH_CUDA(c, cudaSetDevice(c->device));
+    LH_CUDA(c, cudaStreamSynchronize(c->stream));
+    for (int k = 0; k < 4; ++k) {
+        if (!(values && values[k])) {
+            if (c->flux_cols_dev[k]) { LH_CUDA(c, cudaFree(c->flux_cols_dev[k])); c->flux_cols_dev[k] = nullptr; }
+            continue;
+        }
+        if (!c->flux_cols_dev[k]) LH_CUDA(c, cudaMalloc(&c->flux_cols_dev[k], (size_t)c->ncol_pad * sizeof(double)));
+        std::vector<double> h((size_t)c->ncol_pad);
+        for (int64_t j = 0; j < c->ncol_pad; ++j) h[j] = values[k][std::min<int64_t>(j, c->ncol - 1)];
+        LH_CUDA(c, cudaMemcpy(c->flux_cols_dev[k], h.data(), h.size() * sizeof(double), cudaMemcpyHostToDevice));
+    }
+    return LH_OK;
+}
+
+int32_t lh_soil_set_atmos_forcing(lh_soil_ctx* c, const lh_soil_atmos* a)
+{
+    if (!c) return LH_ERR_INVALID_ARG;
+    if (!a) { c->atmos_on = false; return LH_OK; }
+    if (a->struct_size != (int32_t)sizeof(lh_soil_atmos)) return fail(c, LH_ERR_INVALID_ARG, "lh_soil_atmos.struct_size mismatch");
+    if (c->model != LH_MODEL_COUPLED)           // boundary_conditions.jl:103-112: both components must be prognostic
+        return fail(c, LH_ERR_UNSUPPORTED_BC, "PrescribedAtmosForcing needs SoilEnergyModel + SoilHydrologyModel (model kind %d given)", c->model);
+    const lh_soil_params& q = c->cfg.params;
+    if (!(a->z_atm > 0.0) || !(a->rho_a_sfc > 0.0) || !(a->theta_scale > 0.0) || !(q.z_0m > 0.0) || !(q.z_0s > 0.0))
+        return fail(c, LH_ERR_INVALID_ARG, "PrescribedAtmosForcing needs z_atm, rho_a_sfc, theta_scale, z_0m, z_0s > 0");
+    LH_CUDA(c, cudaSetDevice(c->device));
+    for (auto& p : c->atm_flux_dev) if (!p) LH_CUDA(c, cudaMalloc(&p, (size_t)c->ncol_pad * sizeof(double)));
+    LhAtmos& d = c->atmos;
+    d.u_atm = a->u_atm; d.theta_atm = a->theta_atm; d.z_atm = a->z_atm; d.theta_scale = a->theta_scale; d.rho_a_sfc = a->rho_a_sfc; d.q_atm = a->q_atm;
+    d.R_v = a->R_v; d.R_d = a->R_d; d.grav = a->grav; d.cp_d = a->cp_d; d.cp_v = a->cp_v; d.LH_v0 = a->LH_v0;
+    d.press_triple = a->press_triple; d.T_triple = a->T_triple; d.von_karman = a->von_karman;
+    d.Pr_0 = a->Pr_0; d.a_m = a->a_m; d.a_h = a->a_h;
+    d.cp_l = q.cp_l; d.T_0 = q.T_0; d.rho_l = q.rho_cloud_liq; d.z_0m = q.z_0m; d.z_0s = q.z_0s;
+    c->atmos_on = true;
+    return LH_OK;
+}
+
+int32_t lh_soil_atmos_fluxes(lh_soil_ctx* c, const double* th, const double* ti, const double* T, int64_t n, double* heat, double* water)
+{
+    if (!c || !th || !ti || !T || !heat || !water || n < 0) return LH_ERR_INVALID_ARG;
+    if (!c->atmos_on) return fail(c, LH_ERR_STATE, "lh_soil_set_atmos_forcing has not been called");
+    if (n == 0) return LH_OK;
+    LH_CUDA(c, cudaSetDevice(c->device));
+    double* d = nullptr;
+    LH_CUDA(c, cudaMalloc(&d, (size_t)n * 5 * sizeof(double)));
+    cudaError_t e = cudaMemcpyAsync(d, th, n * sizeof(double), cudaMemcpyHostToDevice, c->stream);
+    if (e == cudaSuccess) e = cudaMemcpyAsync(d + n, ti, n * sizeof(double), cudaMemcpyHostToDevice, c->stream);
+    if (e == cudaSuccess) e = cudaMemcpyAsync(d + 2 * n, T, n * sizeof(double), cudaMemcpyHostToDevice, c->stream);
+    if (e == cudaSuccess) e = lh_launch_atmos_eval(c->dp, c->pow_tab_dev, c->atmos, d, d + n, d + 2 * n, d + 3 * n, d + 4 * n, n, c->stream);
+    if (e == cudaSuccess) e = cudaMemcpyAsync(heat, d + 3 * n, n * sizeof(double), cudaMemcpyDeviceToHost, c->stream);
+    if (e == cudaSuccess) e = cudaMemcpyAsync(water, d + 4 * n, n * sizeof(double), cudaMemcpyDeviceToHost, c->stream);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(c->stream);
+    cudaFree(d);
+    if (e != cudaSuccess) return fail(c, LH_ERR_CUDA, "lh_soil_atmos_fluxes: %s", cudaGetErrorString(e));
     return LH_OK;
 }
 
@@ -827,6 +949,7 @@ int32_t lh_soil_stage_ssprk33(lh_soil_ctx* c, int32_t stage, double dt)
 // every stage) and the kernel is issue-bound.
 static bool use_persistent(const lh_soil_ctx* c)
 {
+    if (c->atmos_on) return false;              // the atmospheric fluxes are re-evaluated by their own kernel before every stage
     if (c->cfg.flags & LH_FLAG_STAGE_LAUNCHES) return false;
     if (c->cfg.flags & LH_FLAG_PERSISTENT) return true;
     return c->shape.waves <= 1.5;
@@ -1312,7 +1435,7 @@ int32_t lh_soil_diagnostic(lh_soil_ctx* c, int32_t which, double* host, int64_t 
     LH_CUDA(c, cudaSetDevice(c->device));
     if (!c->diag_dev) LH_CUDA(c, cudaMalloc(&c->diag_dev, field_bytes(c)));      // its own scratch: tendencies stay untouched
     LH_CUDA(c, lh_launch_diagnostic(c->model, which, c->dp, c->pow_tab_dev, c->U[0], c->U[1], c->U[2], c->U[3], c->diag_dev,
-                                    (int64_t)c->ncol_pad * c->nlayer, c->colp_dev, c->ncol_pad, c->stream));
+                                    (int64_t)c->ncol_pad * c->nlayer, c->colp_dev, c->ncol_pad, c->col_heat ? 1 : 0, c->stream));
     return download_field(c, c->diag_dev, host, cs, ls);
 }
 
@@ -1366,7 +1489,7 @@ int32_t lh_soil_kernel_info(lh_soil_ctx* c, char* buf, int64_t cap)
              "%s<MODEL=%d,%sFLAGS=%d:%s%s%s%s> block=(32,W=%d,G=%d) layers/thread=%d blocks=%lld smem=%zu waves=%.2f "
              "launch=%s chain=%s bytes/cell-step(on wire)=%d",
              persistent ? "lh_soil_ssprk33_persistent_kernel" : "lh_soil_stage_kernel", c->model, persistent ? "" : "STAGE=1|2|3,", f,
-             (f & LH_FLAG_ICE) ? "ICE" : "!ICE", (f & LH_FLAG_GEN) ? "+GEN" : "", (f & LH_FLAG_VG2) ? "+VG2" : "", (f & LH_FLAG_HET) ? "+HET" : "",
+             (f & LH_FLAG_ICE) ? "ICE" : "!ICE", (f & LH_FLAG_GEN) ? "+GEN" : "", (f & LH_FLAG_VG2) ? "+VG2" : "", (f & LH_FLAG_HETH) ? "+HET+HETH" : (f & LH_FLAG_HET) ? "+HET" : "",
              c->shape.W, c->shape.G, c->shape.Lc, (long long)c->shape.nblocks, c->shape.smem_bytes, c->shape.waves,
              persistent ? "persistent(1 per call)" : "per-stage(3 per step)",
              (!persistent && c->chain_dev && !(c->cfg.flags & LH_FLAG_NO_CHAIN)) ? "block-to-block" : "whole-grid",

@@ -1,6 +1,6 @@
 // lh_stage_kernel.cuh — the fused soil RHS (+ Runge-Kutta stage) kernel template, the persistent SSPRK33 kernel and
-// their launchers.  Included by one translation unit per model (lh_kernels_m0/m1/m2.cu) so that the variants
-// (3 models x 7 stage kinds x 12 flag combinations) compile in parallel.  See lh_kernels.cu for the design notes.
+// their launchers.  Included by one translation unit per (model, stage group) (lh_kernels_m<M>_<a|b|c|p>.cu) so that the
+// variants (3 models x 7 stage kinds x up to 14 flag combinations) compile in parallel.  See lh_kernels.cu for the design notes.
 #pragma once
 
 #include "lh_kernels.cuh"
@@ -382,8 +382,10 @@ __device__ __forceinline__ void lh_stage_body_impl(const LhKernelArgs& A, const 
             if constexpr (MODEL != 1) { c.K = first.K; c.psi = first.psi; }
             if constexpr (MODEL != 0) c.T = first.T;
             else if (need_T) c.T = __ldcg(pT);
-            F_lo = boundary_flux<MODEL, FLAGS>(p, tab, A.bot_e_kind, A.bot_h_kind, io.bcv[LH_BCV_BOTTOM_ENERGY],
-                                               io.bcv[LH_BCV_BOTTOM_HYDROLOGY], true, __ldcg(pth), ICE ? __ldcg(pti) : 0.0, c);
+            // per-column prescribed fluxes (lh_soil_set_column_fluxes) replace the scalar boundary value
+            const double ve = io.flux_cols[LH_BCV_BOTTOM_ENERGY] ? __ldcg(io.flux_cols[LH_BCV_BOTTOM_ENERGY] + col) : io.bcv[LH_BCV_BOTTOM_ENERGY];
+            const double vh = io.flux_cols[LH_BCV_BOTTOM_HYDROLOGY] ? __ldcg(io.flux_cols[LH_BCV_BOTTOM_HYDROLOGY] + col) : io.bcv[LH_BCV_BOTTOM_HYDROLOGY];
+            F_lo = boundary_flux<MODEL, FLAGS>(p, tab, A.bot_e_kind, A.bot_h_kind, ve, vh, true, __ldcg(pth), ICE ? __ldcg(pti) : 0.0, c);
         } else {
             F_lo = face_flux<MODEL>(p, q_load<MODEL>(sm_top - (Slot<MODEL>::doubles + RING_DOUBLES)), first);   // top of chunk w-1
         }
@@ -394,8 +396,10 @@ __device__ __forceinline__ void lh_stage_body_impl(const LhKernelArgs& A, const 
             if constexpr (MODEL != 1) { c.K = prev.K; c.psi = prev.psi; }
             if constexpr (MODEL != 0) c.T = prev.T;
             else if (need_T) c.T = __ldcg(pT + o);
-            F_hi = boundary_flux<MODEL, FLAGS>(p, tab, A.top_e_kind, A.top_h_kind, io.bcv[LH_BCV_TOP_ENERGY],
-                                               io.bcv[LH_BCV_TOP_HYDROLOGY], false, __ldcg(pth + o), ICE ? __ldcg(pti + o) : 0.0, c);
+            // per-column fluxes: prescribed fields, or the atmospheric fluxes lh_atmos_flux_kernel left for this stage
+            const double ve = io.flux_cols[LH_BCV_TOP_ENERGY] ? __ldcg(io.flux_cols[LH_BCV_TOP_ENERGY] + col) : io.bcv[LH_BCV_TOP_ENERGY];
+            const double vh = io.flux_cols[LH_BCV_TOP_HYDROLOGY] ? __ldcg(io.flux_cols[LH_BCV_TOP_HYDROLOGY] + col) : io.bcv[LH_BCV_TOP_HYDROLOGY];
+            F_hi = boundary_flux<MODEL, FLAGS>(p, tab, A.top_e_kind, A.top_h_kind, ve, vh, false, __ldcg(pth + o), ICE ? __ldcg(pti + o) : 0.0, c);
         } else {
             F_hi = face_flux<MODEL>(p, prev, q_load<MODEL>(sm_bot + (Slot<MODEL>::doubles + RING_DOUBLES)));    // bot of chunk w+1
         }
@@ -463,7 +467,17 @@ __device__ __forceinline__ void lh_stage_body(const LhKernelArgs& A, const LhSta
         pl.Ksat = cp[LHCP_KSAT * st];
         pl.inv_nu = cp[LHCP_INV_NU * st];
         pl.kappa_dry = cp[LHCP_KAPPA_DRY * st];
-        pl.k_unfrozen_minus_dry = A.p.k_unfrozen - pl.kappa_dry;
+        if constexpr ((FLAGS & LH_FLAG_HETH) != 0) {
+            pl.rho_c_ds = cp[LHCP_RHO_C_DS * st];
+            pl.kersten_p1 = cp[LHCP_KERSTEN_P1 * st];
+            pl.kersten_p2 = cp[LHCP_KERSTEN_P2 * st];
+            pl.kersten_p3 = cp[LHCP_KERSTEN_P3 * st];
+            pl.k_unfrozen = cp[LHCP_K_UNFROZEN * st];
+            pl.log2_k_unfrozen = cp[LHCP_LOG2_K_UNFROZEN * st];
+            pl.log2_k_frozen = cp[LHCP_LOG2_K_FROZEN * st];
+            pl.om_zero = 0;
+        }
+        pl.k_unfrozen_minus_dry = pl.k_unfrozen - pl.kappa_dry;
         lh_stage_body_impl<MODEL, STAGE, FLAGS>(A, io, smem, pl);
     }
 }
@@ -549,7 +563,9 @@ lh_soil_ssprk33_persistent_kernel(const __grid_constant__ LhKernelArgs A)
     }
 }
 
-template <int MODEL, int FLAGS>
+// The stage kinds are compiled in GROUPS of two (0: tendency + SSPRK33 stage 1, 1: SSPRK33 stages 2 and 3, 2: the generic
+// Shu-Osher and 2N stages), one translation unit per (model, group), so that the ~200 kernel variants build in parallel.
+template <int MODEL, int FLAGS, int GROUP>
 cudaError_t launch_variant(int stage, const LhKernelArgs& args, const LhLaunchShape& s, cudaStream_t stream)
 {
     dim3 block(32, s.W, s.G);
@@ -567,12 +583,8 @@ cudaError_t launch_variant(int stage, const LhKernelArgs& args, const LhLaunchSh
             if ((e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes))) return e;
             return cudaFuncSetAttribute(kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
         };
-        if ((e = configure(lh_soil_stage_kernel<MODEL, 0, FLAGS>))) return e;
-        if ((e = configure(lh_soil_stage_kernel<MODEL, 1, FLAGS>))) return e;
-        if ((e = configure(lh_soil_stage_kernel<MODEL, 2, FLAGS>))) return e;
-        if ((e = configure(lh_soil_stage_kernel<MODEL, 3, FLAGS>))) return e;
-        if ((e = configure(lh_soil_stage_kernel<MODEL, 4, FLAGS>))) return e;
-        if ((e = configure(lh_soil_stage_kernel<MODEL, 5, FLAGS>))) return e;
+        if ((e = configure(lh_soil_stage_kernel<MODEL, 2 * GROUP, FLAGS>))) return e;
+        if ((e = configure(lh_soil_stage_kernel<MODEL, 2 * GROUP + 1, FLAGS>))) return e;
         configured_smem[dev] = (int)s.smem_bytes + 1;
     }
     cudaLaunchConfig_t cfg = {};
@@ -585,36 +597,36 @@ cudaError_t launch_variant(int stage, const LhKernelArgs& args, const LhLaunchSh
     attr[0].val.programmaticStreamSerializationAllowed = LH_PDL;
     cfg.attrs = attr;
     cfg.numAttrs = 1;
-    switch (stage) {
-    case 0: return cudaLaunchKernelEx(&cfg, lh_soil_stage_kernel<MODEL, 0, FLAGS>, args);
-    case 1: return cudaLaunchKernelEx(&cfg, lh_soil_stage_kernel<MODEL, 1, FLAGS>, args);
-    case 2: return cudaLaunchKernelEx(&cfg, lh_soil_stage_kernel<MODEL, 2, FLAGS>, args);
-    case 3: return cudaLaunchKernelEx(&cfg, lh_soil_stage_kernel<MODEL, 3, FLAGS>, args);
-    case 4: return cudaLaunchKernelEx(&cfg, lh_soil_stage_kernel<MODEL, 4, FLAGS>, args);
-    case 5: return cudaLaunchKernelEx(&cfg, lh_soil_stage_kernel<MODEL, 5, FLAGS>, args);
-    default: return cudaErrorInvalidValue;
-    }
+    if (stage == 2 * GROUP) return cudaLaunchKernelEx(&cfg, lh_soil_stage_kernel<MODEL, 2 * GROUP, FLAGS>, args);
+    if (stage == 2 * GROUP + 1) return cudaLaunchKernelEx(&cfg, lh_soil_stage_kernel<MODEL, 2 * GROUP + 1, FLAGS>, args);
+    return cudaErrorInvalidValue;
 }
 
-template <int MODEL>
+template <int MODEL, int GROUP>
 cudaError_t launch_model(int stage, int flags, const LhKernelArgs& args, const LhLaunchShape& s, cudaStream_t stream)
 {
     if (MODEL == 1) flags &= ~LH_FLAG_VG2;   // the heat-only model has no water closures
     if (flags & LH_FLAG_HET) {               // per-column parameters: always the general closures
+        if (MODEL != 0 && (flags & LH_FLAG_HETH)) {      // per-column heat parameters (the Richards model has no heat closures)
+            switch (flags & LH_FLAG_ICE) {
+            case 0: return launch_variant<MODEL, (MODEL == 0 ? 0 : LH_FLAG_HETH) | LH_FLAG_HET | LH_FLAG_GEN, GROUP>(stage, args, s, stream);
+            default: return launch_variant<MODEL, (MODEL == 0 ? 0 : LH_FLAG_HETH) | LH_FLAG_HET | LH_FLAG_GEN | LH_FLAG_ICE, GROUP>(stage, args, s, stream);
+            }
+        }
         switch (flags & LH_FLAG_ICE) {
-        case 0: return launch_variant<MODEL, LH_FLAG_HET | LH_FLAG_GEN>(stage, args, s, stream);
-        default: return launch_variant<MODEL, LH_FLAG_HET | LH_FLAG_GEN | LH_FLAG_ICE>(stage, args, s, stream);
+        case 0: return launch_variant<MODEL, LH_FLAG_HET | LH_FLAG_GEN, GROUP>(stage, args, s, stream);
+        default: return launch_variant<MODEL, LH_FLAG_HET | LH_FLAG_GEN | LH_FLAG_ICE, GROUP>(stage, args, s, stream);
         }
     }
     switch (flags & 7) {
-    case 0: return launch_variant<MODEL, 0>(stage, args, s, stream);
-    case 1: return launch_variant<MODEL, 1>(stage, args, s, stream);
-    case 2: return launch_variant<MODEL, 2>(stage, args, s, stream);
-    case 3: return launch_variant<MODEL, 3>(stage, args, s, stream);
-    case 4: return launch_variant<MODEL, (MODEL == 1 ? 0 : 4)>(stage, args, s, stream);
-    case 5: return launch_variant<MODEL, (MODEL == 1 ? 1 : 5)>(stage, args, s, stream);
-    case 6: return launch_variant<MODEL, (MODEL == 1 ? 2 : 6)>(stage, args, s, stream);
-    default: return launch_variant<MODEL, (MODEL == 1 ? 3 : 7)>(stage, args, s, stream);
+    case 0: return launch_variant<MODEL, 0, GROUP>(stage, args, s, stream);
+    case 1: return launch_variant<MODEL, 1, GROUP>(stage, args, s, stream);
+    case 2: return launch_variant<MODEL, 2, GROUP>(stage, args, s, stream);
+    case 3: return launch_variant<MODEL, 3, GROUP>(stage, args, s, stream);
+    case 4: return launch_variant<MODEL, (MODEL == 1 ? 0 : 4), GROUP>(stage, args, s, stream);
+    case 5: return launch_variant<MODEL, (MODEL == 1 ? 1 : 5), GROUP>(stage, args, s, stream);
+    case 6: return launch_variant<MODEL, (MODEL == 1 ? 2 : 6), GROUP>(stage, args, s, stream);
+    default: return launch_variant<MODEL, (MODEL == 1 ? 3 : 7), GROUP>(stage, args, s, stream);
     }
 }
 
@@ -642,6 +654,12 @@ cudaError_t launch_persistent_model(int flags, const LhKernelArgs& args, const L
 {
     if (MODEL == 1) flags &= ~LH_FLAG_VG2;
     if (flags & LH_FLAG_HET) {
+        if (MODEL != 0 && (flags & LH_FLAG_HETH)) {
+            switch (flags & LH_FLAG_ICE) {
+            case 0: return launch_persistent_variant<MODEL, (MODEL == 0 ? 0 : LH_FLAG_HETH) | LH_FLAG_HET | LH_FLAG_GEN>(args, s, stream);
+            default: return launch_persistent_variant<MODEL, (MODEL == 0 ? 0 : LH_FLAG_HETH) | LH_FLAG_HET | LH_FLAG_GEN | LH_FLAG_ICE>(args, s, stream);
+            }
+        }
         switch (flags & LH_FLAG_ICE) {
         case 0: return launch_persistent_variant<MODEL, LH_FLAG_HET | LH_FLAG_GEN>(args, s, stream);
         default: return launch_persistent_variant<MODEL, LH_FLAG_HET | LH_FLAG_GEN | LH_FLAG_ICE>(args, s, stream);

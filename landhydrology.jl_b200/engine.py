@@ -91,16 +91,28 @@ def build_params(model: SoilModel) -> _abi.lh_soil_params:
     return p
 
 
+def build_atmos(model: SoilModel) -> _abi.lh_soil_atmos:
+    """``lh_soil_atmos`` from the model's ``PrescribedAtmosForcing`` top BC and its earth parameter set."""
+    bc, ep = model.boundary_conditions.top, model.earth_param_set
+    a = _abi.lh_soil_atmos()
+    a.u_atm, a.theta_atm, a.z_atm, a.theta_scale, a.rho_a_sfc, a.q_atm = bc.u_atm, bc.θ_atm, bc.z_atm, bc.θ_scale, bc.ρ_a_sfc, bc.q_atm
+    a.R_v, a.R_d, a.grav, a.cp_d, a.cp_v, a.LH_v0 = ep.R_v, ep.R_d, ep.grav, ep.cp_d, ep.cp_v, ep.LH_v0
+    a.press_triple, a.T_triple, a.von_karman = ep.press_triple, ep.T_triple, ep.von_karman_const
+    a.Pr_0, a.a_m, a.a_h = ep.Pr_0, ep.a_m, ep.a_h
+    return a
+
+
 def build_config(model: SoilModel, t0: float = 0.0, *, device: int = 0, ncol: Optional[int] = None,
                  check_finite: bool = False) -> lh_soil_config:
     kind = model.kind
     if kind is None:
         raise ValueError("prescribed/prescribed model has no device right-hand side")
     bcs = model.boundary_conditions
-    if isinstance(bcs.top, PrescribedAtmosForcing):
-        # boundary_conditions.jl:516-620: arithmetic lives in un-vendored SurfaceFluxes /
-        # Thermodynamics; out of scope for this path.
-        raise NotImplementedError("PrescribedAtmosForcing is outside the B200 hot-path scope")
+    atmos_top = isinstance(bcs.top, PrescribedAtmosForcing)
+    if atmos_top and kind != _abi.LH_MODEL_COUPLED:
+        # boundary_conditions.jl:103-112 / test_prescribed_atmos_bc.jl:161-185: only with both components prognostic
+        raise _abi.SoilError(_abi.LH_ERR_UNSUPPORTED_BC,
+                             "PrescribedAtmosForcing needs SoilEnergyModel + SoilHydrologyModel (no method for prescribed components)")
     cfg = lh_soil_config()
     cfg.device = device
     cfg.ncol = int(ncol if ncol is not None else model.domain.ncolumns)
@@ -109,6 +121,11 @@ def build_config(model: SoilModel, t0: float = 0.0, *, device: int = 0, ncol: Op
     cfg.zmin, cfg.zmax = float(model.domain.zlim[0]), float(model.domain.zlim[1])
     cfg.params = build_params(model)
     for face_cfg, face_bc in ((cfg.top, bcs.top), (cfg.bottom, bcs.bottom)):
+        if isinstance(face_bc, PrescribedAtmosForcing):
+            # the fluxes come per column from lh_soil_set_atmos_forcing (SoilEngine); as far as the config goes the face is a flux
+            face_cfg.energy_kind, face_cfg.energy_value = _abi.LH_BC_FLUX, 0.0
+            face_cfg.hydrology_kind, face_cfg.hydrology_value = _abi.LH_BC_FLUX, 0.0
+            continue
         face_cfg.energy_kind, face_cfg.energy_value = _bc_kind_value(face_bc.energy, t0)
         face_cfg.hydrology_kind, face_cfg.hydrology_value = _bc_kind_value(face_bc.hydrology, t0)
     cfg.flags = _abi.LH_FLAG_CHECK_FINITE if check_finite else 0
@@ -132,16 +149,22 @@ class SoilEngine:
         self.ctx = SoilContext(self.lib, self.cfg)
         self.zc = self.ctx.zc()
         self._aux_cache = {}
+        if isinstance(model.boundary_conditions.top, PrescribedAtmosForcing):
+            self.ctx.set_atmos_forcing(build_atmos(model))
         self.update_aux(t0)
 
     def close(self):
         self.ctx.close()
 
     # -- boundary values: evaluate Dirichlet closures on the host (boundary_conditions.jl:247,267)
-    def bc_values(self, t: float) -> np.ndarray:
+    def _component_bcs(self):
         bcs = self.model.boundary_conditions
+        top = (NoBC(), NoBC()) if isinstance(bcs.top, PrescribedAtmosForcing) else (bcs.top.energy, bcs.top.hydrology)
+        return top + (bcs.bottom.energy, bcs.bottom.hydrology)
+
+    def bc_values(self, t: float) -> np.ndarray:
         out = np.zeros(4)
-        for i, bc in enumerate((bcs.top.energy, bcs.top.hydrology, bcs.bottom.energy, bcs.bottom.hydrology)):
+        for i, bc in enumerate(self._component_bcs()):
             if isinstance(bc, Dirichlet):
                 out[i] = float(bc.state_value(t))
             elif isinstance(bc, VerticalFlux):
@@ -149,8 +172,7 @@ class SoilEngine:
         return out
 
     def has_dirichlet(self) -> bool:
-        bcs = self.model.boundary_conditions
-        return any(isinstance(b, Dirichlet) for b in (bcs.top.energy, bcs.top.hydrology, bcs.bottom.energy, bcs.bottom.hydrology))
+        return any(isinstance(b, Dirichlet) for b in self._component_bcs())
 
     # -- prescribed profiles: make_update_aux (right_hand_side.jl:54-96) -----------------------
     def prescribed_profiles(self, t: float):
@@ -192,6 +214,21 @@ class SoilEngine:
             lo, hi = self.column_range
             return np.ascontiguousarray(a[lo:hi])
         self.ctx.set_column_params(nu=shard(ν), theta_r=shard(θr), vg_n=shard(n), vg_alpha=shard(α), Ksat=shard(Ksat))
+
+    def set_column_heat_params(self, *, ρc_ds=None, κ_sat_unfrozen=None, κ_sat_frozen=None, κ_solid=None, ν_ss_om=None,
+                               ν_ss_quartz=None, ν_ss_gravel=None):
+        """Per-column heat parameters of ``SoilParams`` (reference parameters.jl:11-43); arrays over ALL columns of the domain."""
+        def shard(a):
+            if a is None:
+                return None
+            a = np.asarray(a, dtype=np.float64)
+            if a.shape != (self.model.domain.ncolumns,):
+                raise ValueError(f"per-column parameter must have shape ({self.model.domain.ncolumns},)")
+            lo, hi = self.column_range
+            return np.ascontiguousarray(a[lo:hi])
+        self.ctx.set_column_heat_params(rho_c_ds=shard(ρc_ds), kappa_sat_unfrozen=shard(κ_sat_unfrozen),
+                                        kappa_sat_frozen=shard(κ_sat_frozen), kappa_solid=shard(κ_solid), nu_ss_om=shard(ν_ss_om),
+                                        nu_ss_quartz=shard(ν_ss_quartz), nu_ss_gravel=shard(ν_ss_gravel))
 
     # -- state transfer ----------------------------------------------------------------------------
     def _shard(self, a: np.ndarray) -> np.ndarray:

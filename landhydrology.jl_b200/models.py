@@ -139,9 +139,10 @@ class SoilComponentBC(AbstractFaceBC):
 
 @dataclass(frozen=True)
 class PrescribedAtmosForcing(AbstractFaceBC):
-    """:119-132.  Type kept for API completeness; its flux arithmetic lives in the un-vendored
-    SurfaceFluxes/Thermodynamics packages and is out of scope for this path:
-    building a context with it raises ``NotImplementedError``."""
+    """:119-132.  Turbulent surface fluxes from Monin-Obukhov similarity, top face only, both soil components
+    prognostic.  PARITY UNPINNED: the similarity solve and the saturation vapour pressure live in the un-vendored
+    SurfaceFluxes / Thermodynamics packages and follow the published formulations here (include/lh_soil.h
+    ``lh_soil_set_atmos_forcing``)."""
 
     u_atm: float
     θ_atm: float

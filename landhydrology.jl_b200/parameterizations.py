@@ -37,6 +37,32 @@ class EarthParameterSet:
     T_0: float = 273.16
     LH_f0: float = 2.8344e6 - 2.5008e6  # LH_s0 - LH_v0
     K_therm: float = 2.4e-2
+    # read only by PrescribedAtmosForcing (boundary_conditions.jl:575-617 and, through SurfaceFluxes / Thermodynamics, the
+    # saturation vapour pressure and the similarity functions): CLIMAParameters v0.1 values
+    R_v: float = 8.3144598 / 18.01528e-3
+    R_d: float = 8.3144598 / 28.97e-3
+    grav: float = 9.81
+    cp_d: float = (8.3144598 / 28.97e-3) / (2.0 / 7.0)
+    cp_v: float = 1859.0
+    LH_v0: float = 2.5008e6
+    press_triple: float = 611.657
+    T_triple: float = 273.16
+    von_karman_const: float = 0.4
+    # SurfaceFluxes.UniversalFunctions.Businger
+    Pr_0: float = 0.74
+    a_m: float = 4.7
+    a_h: float = 4.7
+
+
+def q_vap_saturation_liquid(ps, T, ρ):
+    """``Thermodynamics.q_vap_saturation_generic(param_set, T, ρ, Liquid())`` restated from the published closed form
+    (Clausius-Clapeyron with constant Δcp = cp_v - cp_l; PARITY UNPINNED, include/lh_soil.h): host-side helper for building a
+    ``PrescribedAtmosForcing`` the way test_prescribed_atmos_bc.jl:28 does."""
+    import math
+
+    dcp = ps.cp_v - ps.cp_l
+    p_vs = ps.press_triple * (T / ps.T_triple) ** (dcp / ps.R_v) * math.exp((ps.LH_v0 - dcp * ps.T_0) / ps.R_v * (1.0 / ps.T_triple - 1.0 / T))
+    return p_vs / (ρ * ps.R_v * T)
 
 
 def ρ_cloud_liq(ps): return ps.ρ_cloud_liq

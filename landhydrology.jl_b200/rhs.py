@@ -65,3 +65,37 @@ def make_rhs(model: SoilModel):
         return dY
 
     return rhs_
+
+
+def compute_turbulent_surface_fluxes(energy, hydrology, model: SoilModel, ϑ_l, θ_i, T):
+    """``compute_turbulent_surface_fluxes(energy::SoilEnergyModel, hydrology::SoilHydrologyModel, model, ϑ_l, θ_i, T)``
+    (boundary_conditions.jl:555-620): ``(heat_flux, Ẽ)`` for a surface state, evaluated by the library with the model's
+    parameters.  Like the reference, there is no method for prescribed components (test_prescribed_atmos_bc.jl:161-185)."""
+    from .models import PrescribedAtmosForcing, SoilEnergyModel, SoilHydrologyModel
+
+    if not isinstance(energy, SoilEnergyModel) or not isinstance(hydrology, SoilHydrologyModel):
+        raise TypeError("MethodError: no method matching compute_turbulent_surface_fluxes("
+                        f"::{type(energy).__name__}, ::{type(hydrology).__name__}, ...)")
+    if not isinstance(model.boundary_conditions.top, PrescribedAtmosForcing):
+        raise TypeError("the model's top boundary condition is not a PrescribedAtmosForcing")
+    eng = engine_for(model, 0.0)
+    heat, water = eng.ctx.atmos_fluxes(ϑ_l, θ_i, T)
+    if np.ndim(ϑ_l) == 0:
+        return float(heat[0]), float(water[0])
+    return heat, water
+
+
+def boundary_fluxes(X, bc, face: str, model: SoilModel, cs=None, t: float = 0.0):
+    """``boundary_fluxes(X, bc::PrescribedAtmosForcing, face, model, cs, t)`` (boundary_conditions.jl:516-536): the surface
+    fluxes from the interior values next to the top face; any other face is an error (:525-527)."""
+    from .models import PrescribedAtmosForcing
+
+    if not isinstance(bc, PrescribedAtmosForcing):
+        raise TypeError("host-side boundary_fluxes is provided for PrescribedAtmosForcing only; component BCs are evaluated on the device")
+    if face != "top":
+        raise ValueError("Prescribed atmosphere-driven boundary conditions are only valid at the top of the soil column.")
+    soil = getattr(X, model.name)
+    heat, water = compute_turbulent_surface_fluxes(model.energy_model, model.hydrology_model, model,
+                                                   np.atleast_2d(soil["ϑ_l"])[..., -1], np.atleast_2d(soil["θ_i"])[..., -1],
+                                                   np.atleast_2d(soil["T"])[..., -1])
+    return {"fρe_int": heat, "fϑ_l": water}

@@ -72,3 +72,54 @@ def allreduce_budgets_host(local: np.ndarray, dist) -> np.ndarray:
     t = torch.from_numpy(np.asarray(local, dtype=np.float64).copy())
     dist.all_reduce(t)
     return t.numpy()
+
+
+def gpu_numa_cpus(device: int):
+    """CPUs of the NUMA node the GPU ``device`` (CUDA ordinal of this process) hangs off, or ``None`` when the platform
+    does not say (single-socket hosts, containers without sysfs).  Read from sysfs through the PCI bus id NVML reports."""
+    try:
+        import os
+
+        import pynvml
+
+        pynvml.nvmlInit()
+        visible = os.environ.get("CUDA_VISIBLE_DEVICES")
+        index = device
+        if visible:
+            ids = [v.strip() for v in visible.split(",") if v.strip()]
+            if device < len(ids) and ids[device].isdigit():
+                index = int(ids[device])
+        h = pynvml.nvmlDeviceGetHandleByIndex(index)
+        bus = pynvml.nvmlDeviceGetPciInfo(h).busId
+        bus = bus.decode() if isinstance(bus, bytes) else bus
+        bus = bus.lower()
+        if len(bus.split(":")[0]) == 8:                   # NVML pads the domain to 8 hex digits, sysfs uses 4
+            bus = bus[4:]
+        node = int(open(f"/sys/bus/pci/devices/{bus}/numa_node").read().strip())
+        if node < 0:
+            return None
+        cpus = set()
+        for part in open(f"/sys/devices/system/node/node{node}/cpulist").read().strip().split(","):
+            lo, _, hi = part.partition("-")
+            cpus.update(range(int(lo), int(hi or lo) + 1))
+        allowed = os.sched_getaffinity(0)
+        cpus &= allowed
+        return sorted(cpus) or None
+    except Exception:
+        return None
+
+
+def bind_to_gpu_numa_node(device: int) -> bool:
+    """Pin this process to the CPUs next to its GPU BEFORE it allocates pinned host buffers: page-locked memory is placed
+    on the NUMA node of the allocating thread (first touch), and a buffer on the far socket halves the PCIe rate of an
+    8-GPU box whose ranks all allocate from node 0 (e2e scaling).  Returns whether the affinity was changed."""
+    import os
+
+    cpus = gpu_numa_cpus(device)
+    if not cpus:
+        return False
+    try:
+        os.sched_setaffinity(0, cpus)
+        return True
+    except OSError:
+        return False

@@ -17,7 +17,8 @@ import numpy as np
 from . import _abi
 from .engine import SoilEngine, current_library
 from .models import AbstractModel, SoilModel
-from .states import FieldVector, copy as copy_state
+from .engine import _FIELD_ID
+from .states import FieldVector, copy as copy_state, nf
 
 
 class _Stepper:
@@ -119,8 +120,11 @@ class Integrator:
     """Minimal DEIntegrator: ``u``, ``p`` (= Ya), ``t``, ``dt``, ``sol``."""
 
     def __init__(self, engine: SoilEngine, Y: FieldVector, Ya: FieldVector, tspan, dt, saveat, callback,
-                 max_chunk: int, method: Optional[_Stepper] = None):
+                 max_chunk: int, method: Optional[_Stepper] = None, callback_reupload: str = "if-modified"):
         self.engine = engine
+        if callback_reupload not in ("always", "if-modified", "never"):
+            raise ValueError("callback_reupload must be 'always', 'if-modified' or 'never'")
+        self.reupload = callback_reupload
         self.method = method if method is not None else SSPRK33()
         self._table = self.method.table(engine.lib)
         self.u = copy_state(Y)   # DiffEqBase.init does not alias u0
@@ -143,7 +147,7 @@ class Integrator:
             self._saveat = sorted(float(s) for s in saveat)
         self._next_save = 0
         self._device_fresh = True
-        self._dynamic_aux = engine.has_time_dependent_aux(self.t0, self.dt) and self._table is None
+        self._dynamic_aux = engine.has_time_dependent_aux(self.t0, self.dt)
         engine.upload(self.u)
         self._save_if_due(force_first=True)
 
@@ -179,36 +183,58 @@ class Integrator:
             self._device_fresh = True
 
     # -- stepping ----------------------------------------------------------------------------------
+    def _bc_table(self, t0: float, nsteps: int, dt: float):
+        eng, cs = self.engine, self.method.c
+        if not eng.has_dirichlet():
+            return None
+        table = np.empty((nsteps, len(cs), 4))
+        t = t0
+        for s in range(nsteps):
+            for i, ci in enumerate(cs):
+                table[s, i] = eng.bc_values(t + ci * dt)
+            t = t + dt
+        return table
+
+    def _upload_aux_tables(self, t0: float, nsteps: int, dt: float):
+        """Time-dependent prescribed profiles (make_update_aux, right_hand_side.jl:54-81): evaluated AHEAD at every stage
+        time of the coming ``nsteps`` steps and uploaded once (``lh_soil_set_aux_table``); the device broadcasts the next
+        row before every stage launch, so there is no host round trip per stage."""
+        eng, cs = self.engine, self.method.c
+        times = []
+        t = t0
+        for _ in range(nsteps):
+            times.extend(t + ci * dt for ci in cs)
+            t = t + dt
+        rows = {}
+        for tk in times:
+            for name, prof in eng.prescribed_profiles(tk).items():
+                rows.setdefault(name, []).append(prof)
+        for name, r in rows.items():
+            eng.ctx.set_aux_table(_FIELD_ID[name], np.array(r))
+        return rows
+
+    def _clear_aux_tables(self, rows):
+        for name, r in rows.items():
+            self.engine.ctx.set_aux_table(_FIELD_ID[name], None)
+            self.engine._aux_cache[name] = r[-1]            # what the field holds now
+            getattr(self.p, self.engine.model.name)[name][...] = r[-1]
+
     def _advance(self, nsteps: int, dt: float):
         eng = self.engine
-        cs = self.method.c
-        if self._dynamic_aux:
-            # time-dependent prescribed profiles: stage by stage so update_aux! sees every stage time
-            t = self.t
-            for _ in range(nsteps):
-                for stage, ts in ((1, t), (2, t + dt), (3, t + 0.5 * dt)):
-                    eng.update_aux(ts, self.p)
-                    eng.ctx.set_bc_values(eng.bc_values(ts))
-                    eng.ctx.stage(stage, dt)
-                t = t + dt
-            self.t = t
-        else:
-            table = None
-            t = self.t
-            if eng.has_dirichlet():
-                table = np.empty((nsteps, len(cs), 4))
-                for s in range(nsteps):
-                    for i, ci in enumerate(cs):
-                        table[s, i] = eng.bc_values(t + ci * dt)
-                    t = t + dt
-            else:
-                for _ in range(nsteps):
-                    t = t + dt
+        rows = self._upload_aux_tables(self.t, nsteps, dt) if self._dynamic_aux else {}
+        table = self._bc_table(self.t, nsteps, dt)
+        try:
             if self._table is None:
                 eng.ctx.step(self.t, dt, nsteps, table)
             else:
                 eng.ctx.step_with(self._table, self.t, dt, nsteps, table)
-            self.t = t
+        finally:
+            if rows:
+                self._clear_aux_tables(rows)
+        t = self.t
+        for _ in range(nsteps):
+            t = t + dt
+        self.t = t
         self.iter += nsteps
         self._device_fresh = False
 
@@ -225,12 +251,80 @@ class Integrator:
     def _after_step(self):
         if self.callback is not None:
             self.sync_host()
+            before = copy_state(self.u) if self.reupload == "if-modified" else None
             self.callback(self)
+            # DiffEq callbacks commonly modify integrator.u: the device state is authoritative, so send it back
+            # (always, or only when it differs from what was downloaded: ``callback_reupload``)
+            if self.reupload == "always" or (before is not None and not (before == self.u)):
+                self.engine.upload(self.u)
         self._save_if_due()
+
+    # -- run!(sim) as ONE device call --------------------------------------------------------------------------
+    def _uniform_save_cadence(self):
+        """Steps between save points if ``saveat`` is a whole multiple of dt reaching tf exactly, else ``None``."""
+        nsteps = (self.tf - self.t) / self.dt
+        if abs(nsteps - round(nsteps)) > 1e-9 * max(1.0, nsteps) or round(nsteps) < 1:
+            return None
+        nsteps = int(round(nsteps))
+        if self._saveat is None:
+            return nsteps, 1
+        pend = self._saveat[self._next_save:]
+        if not pend:
+            return None
+        every = (pend[0] - self.t) / self.dt
+        if abs(every - round(every)) > 1e-9 * max(1.0, every) or round(every) < 1:
+            return None
+        every = int(round(every))
+        expect = [self.t + (k + 1) * every * self.dt for k in range(nsteps // every)]
+        if nsteps % every != 0 or len(pend) != len(expect) or any(abs(a - b) > 1e-9 * max(1.0, abs(self.dt)) for a, b in zip(pend, expect)):
+            return None
+        return nsteps, every
+
+    def _solve_in_one_call(self, nsteps: int, every: int):
+        """``lh_soil_run``: all steps, the ``saveat`` snapshots leaving the device on the copy stream while the steps go on
+        (include/lh_soil.h); in blocks of at most ``max_chunk`` steps so that the host buffers stay bounded."""
+        eng = self.engine
+        names = [nf(n) for n in eng.model.prognostic_names]
+        fields = [_FIELD_ID[n] for n in names]
+        block = max(every, (self.max_chunk // every) * every)
+        done = 0
+        while done < nsteps:
+            n = min(block, nsteps - done)
+            rows = self._upload_aux_tables(self.t, n, self.dt) if self._dynamic_aux else {}
+            try:
+                _, snaps = eng.ctx.run(self.t, self.dt, n, bc_table=self._bc_table(self.t, n, self.dt), save_every=every,
+                                       save_fields=fields)
+            finally:
+                if rows:
+                    self._clear_aux_tables(rows)
+            t = self.t
+            for k in range(n):
+                t = t + self.dt
+                if (k + 1) % every == 0:
+                    u = copy_state(self.u)
+                    soil = getattr(u, eng.model.name)
+                    for j, name in enumerate(eng.model.prognostic_names):
+                        soil[name][...] = snaps[(k + 1) // every - 1, j].reshape(soil[name].shape)
+                    self.sol.t.append(t)
+                    self.sol.u.append(u)
+                    if self._saveat is not None:
+                        self._next_save += 1
+            self.t = t
+            self.iter += n
+            self._device_fresh = False
+            done += n
+        if abs(self.tf - self.t) < 1e-9 * max(1.0, abs(self.dt)):
+            self.t = self.tf
+            if self.sol.t:
+                self.sol.t[-1] = self.t
 
     def solve(self):
         """Run to ``tspan[2]`` (DiffEqBase.solve!)."""
         tol = 1e-9 * max(1.0, abs(self.dt))
+        if self.callback is None and self._table is None and self.engine.column_range == (0, self.engine.model.domain.ncolumns):
+            cadence = self._uniform_save_cadence()
+            if cadence is not None:
+                self._solve_in_one_call(*cadence)
         while self.tf - self.t > tol:
             n = self._steps_to_next_event()
             if n >= 1:
@@ -256,12 +350,15 @@ class Simulation(AbstractSimulation):
     ``kwargs`` understood: ``saveat`` (scalar spacing or list of times); ``progress`` /
     ``progress_message`` are accepted and ignored; ``max_steps_per_call`` bounds how many steps are
     fused into one ``lh_soil_step_ssprk33`` call; ``column_params`` (new) = per-column ``ν``, ``θr``, ``n``, ``α``,
-    ``Ksat`` arrays for heterogeneous soils (``SoilEngine.set_column_params``).
+    ``Ksat`` (``SoilEngine.set_column_params``) and ``ρc_ds``, ``κ_sat_unfrozen``, ``κ_sat_frozen``, ``κ_solid``, ``ν_ss_om``,
+    ``ν_ss_quartz``, ``ν_ss_gravel`` (``SoilEngine.set_column_heat_params``) arrays for heterogeneous soils;
+    ``callback_reupload`` = "always" | "if-modified" | "never": whether ``integrator.u`` goes back to the device after a callback.
     """
 
     def __init__(self, model: AbstractModel, method, *, Y_init, dt, tspan, Ya_init, callbacks=None,
                  saveat=None, progress=False, progress_message=None, max_steps_per_call: int = 4096,
-                 device: int = 0, check_finite: bool = False, column_params: Optional[dict] = None):
+                 device: int = 0, check_finite: bool = False, column_params: Optional[dict] = None,
+                 callback_reupload: str = "if-modified"):
         if not isinstance(method, _Stepper):
             raise NotImplementedError(
                 "the B200 path runs explicit low-storage methods: SSPRK33 (the only stepper the reference uses), Euler, "
@@ -276,11 +373,15 @@ class Simulation(AbstractSimulation):
         self.callbacks = callbacks
         engine = SoilEngine(model, float(tspan[0]), device=device, library=current_library(),
                             check_finite=check_finite)
-        if column_params:
-            engine.set_column_params(**column_params)       # heterogeneous soils: ν, θr, n, α, Ksat per column
-        if engine.has_time_dependent_aux(float(tspan[0]), float(dt)) and not isinstance(method, SSPRK33):
-            raise NotImplementedError("time-dependent prescribed profiles are streamed stage by stage for SSPRK33 only")
-        self.integrator = Integrator(engine, Y_init, Ya_init, tspan, dt, saveat, callbacks, max_steps_per_call, method)
+        if column_params:                                   # heterogeneous soils
+            hyd = {k: v for k, v in column_params.items() if nf(k) in {nf(x) for x in ("ν", "θr", "n", "α", "Ksat")}}
+            heat = {k: v for k, v in column_params.items() if k not in hyd}
+            if hyd:
+                engine.set_column_params(**hyd)             # ν, θr, n, α, Ksat per column
+            if heat:
+                engine.set_column_heat_params(**heat)       # ρc_ds, κ_sat_unfrozen, κ_sat_frozen, κ_solid, ν_ss_* per column
+        self.integrator = Integrator(engine, Y_init, Ya_init, tspan, dt, saveat, callbacks, max_steps_per_call, method,
+                                     callback_reupload=callback_reupload)
 
 
 def step_(simulation: AbstractSimulation) -> None:

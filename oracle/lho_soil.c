@@ -230,6 +230,107 @@ double lho_k_dry(const lh_soil_params* p)
 }
 
 /* ------------------------------------------------------------------------------------------
+ * PrescribedAtmosForcing: compute_turbulent_surface_fluxes, boundary_conditions.jl:555-620.
+ * PARITY UNPINNED for the two third-party pieces (include/lh_soil.h): they are restated from the
+ * published formulations, everything the reference itself writes down is literal.
+ * ---------------------------------------------------------------------------------------- */
+/* Saturation vapour pressure over liquid, Clausius-Clapeyron with constant Δcp = cp_v - cp_l
+ * (Romps 2008 eq. 10; Thermodynamics.jl `saturation_vapor_pressure(param_set, T, LH_0, Δcp)`):
+ *   p_vs = p_tr (T/T_tr)^(Δcp/R_v) exp((LH_v0 - Δcp T_0)/R_v (1/T_tr - 1/T));  q_vs = p_vs / (ρ R_v T). */
+double lho_q_vap_saturation_liquid(const lh_soil_params* p, const lh_soil_atmos* a, double T, double rho)
+{
+    const double dcp = a->cp_v - p->cp_l;
+    const double p_vs = a->press_triple * pow(T / a->T_triple, dcp / a->R_v) *
+                        exp((a->LH_v0 - dcp * p->T_0) / a->R_v * (1.0 / a->T_triple - 1.0 / T));
+    return p_vs / (rho * a->R_v * T);
+}
+
+/* Businger-Dyer integrated universal functions (Businger et al. 1971; Dyer 1974; Paulson 1970 for the
+ * integrated unstable forms).                                                                 */
+static double most_psi_m(const lh_soil_atmos* a, double zeta)
+{
+    if (zeta >= 0.0) return -a->a_m * zeta;
+    const double X = sqrt(sqrt(1.0 - 15.0 * zeta));
+    return 2.0 * log((1.0 + X) / 2.0) + log((1.0 + X * X) / 2.0) - 2.0 * atan(X) + 1.57079632679489661923;
+}
+
+static double most_psi_h(const lh_soil_atmos* a, double zeta)
+{
+    if (zeta >= 0.0) return -a->a_h * zeta / a->Pr_0;
+    const double Y = sqrt(1.0 - 9.0 * zeta);
+    return 2.0 * log((1.0 + Y) / 2.0);
+}
+
+/* Similarity scales for differences (du, dth, dq) between z_atm and the surface, roughness lengths z0m / z0s.
+ * Unknown x = 1/L (so that the neutral limit is x = 0, no division by θ*):
+ *   u*(x) = κ du / (ln(z/z0m) - ψ_m(z x) + ψ_m(z0m x))
+ *   θ*(x) = κ dθ / (Pr_0 (ln(z/z0s) - ψ_h(z x) + ψ_h(z0s x))),  q* likewise
+ *   x = κ g θ* / (u*^2 θ_scale)            (Obukhov length from the θ flux)
+ * solved by a secant iteration on F(x) = x - g(x) from x0 = 0, x1 = g(0), with z x kept in [-1000, 10].    */
+static void most_scales(const lh_soil_atmos* a, double du, double dth, double dq, double z0m, double z0s,
+                        double* ustar, double* tstar, double* qstar)
+{
+    const double k = a->von_karman, z = a->z_atm;
+    const double Lm = log(z / z0m), Lh = log(z / z0s);
+    const double xmin = -1000.0 / z, xmax = 10.0 / z;
+#define MOST_EVAL(x, us, ts, gx)                                                                  \
+    do {                                                                                          \
+        us = k * du / (Lm - most_psi_m(a, z * (x)) + most_psi_m(a, z0m * (x)));                   \
+        ts = k * dth / (a->Pr_0 * (Lh - most_psi_h(a, z * (x)) + most_psi_h(a, z0s * (x))));      \
+        gx = k * a->grav * ts / (us * us * a->theta_scale);                                       \
+    } while (0)
+    double x = 0.0, us, ts, g0;
+    MOST_EVAL(0.0, us, ts, g0);
+    if (dth != 0.0 && du != 0.0) {
+        double x0 = 0.0, F0 = x0 - g0;
+        double x1 = g0 < xmin ? xmin : g0 > xmax ? xmax : g0, g1;
+        MOST_EVAL(x1, us, ts, g1);
+        double F1 = x1 - g1;
+        x = x1;
+        for (int it = 0; it < 60 && F1 != 0.0 && F1 != F0; ++it) {
+            double x2 = x1 - F1 * (x1 - x0) / (F1 - F0);
+            x2 = x2 < xmin ? xmin : x2 > xmax ? xmax : x2;
+            if (x2 == x1) break;
+            x0 = x1; F0 = F1;
+            x1 = x2;
+            MOST_EVAL(x1, us, ts, g1);
+            F1 = x1 - g1;
+            x = x1;
+            if (fabs(F1) <= 4.0e-16 * (fabs(x1) + fabs(g1))) break;
+        }
+        MOST_EVAL(x, us, ts, g1);
+    }
+#undef MOST_EVAL
+    *ustar = us;
+    *tstar = ts;
+    *qstar = k * dq / (a->Pr_0 * (Lh - most_psi_h(a, z * x) + most_psi_h(a, z0s * x)));
+}
+
+/* compute_turbulent_surface_fluxes(energy, hydrology, model, ϑ_l, θ_i, T)  boundary_conditions.jl:555-620 */
+void lho_turbulent_surface_fluxes(const lh_soil_params* p, const lh_soil_atmos* a, double theta_l_aug, double theta_i,
+                                  double T, double* heat_flux, double* water_flux)
+{
+    const double q_sat = lho_q_vap_saturation_liquid(p, a, T, a->rho_a_sfc);                 /* :584 */
+    const double nu_eff = p->nu - theta_i;                                                     /* :588 */
+    const double theta_l = lho_volumetric_liquid_fraction(theta_l_aug, nu_eff);                /* :589 */
+    double S_l_eff = lho_effective_saturation(nu_eff, theta_l, p->theta_r);                    /* :590 */
+    if (!(S_l_eff < 1.0)) S_l_eff = 1.0;                                                       /* min(., 1) */
+    const double psi = lho_matric_potential(p, S_l_eff);                                       /* :591 */
+    const double correction = exp(a->grav * psi / a->R_v / T);                                 /* :592 */
+    const double q_surf = q_sat * correction;                                                  /* :593 */
+    double ustar, tstar, qstar;
+    most_scales(a, a->u_atm - 0.0, a->theta_atm - T, a->q_atm - q_surf, p->z_0m, p->z_0s, &ustar, &tstar, &qstar);
+    const double cpm = a->cp_d + (a->cp_v - a->cp_d) * q_surf;                                 /* cp_m(PhasePartition(q_surf)) :606-607 */
+    const double T_ref = p->T_0;
+    const double h_d = a->cp_d * (T - T_ref) + a->R_d * T_ref;                                 /* :609 */
+    const double E = -a->rho_a_sfc * ustar * qstar;                                            /* :612 */
+    const double dry = -cpm * a->rho_a_sfc * ustar * tstar - h_d * E;                          /* :613 */
+    const double vap = (a->cp_v * (T - T_ref) + a->LH_v0) * E;                                 /* :614-615 */
+    *water_flux = E / p->rho_cloud_liq;                                                        /* :616 */
+    *heat_flux = dry + vap;                                                                    /* :617 */
+}
+
+/* ------------------------------------------------------------------------------------------
  * Context
  * ---------------------------------------------------------------------------------------- */
 
@@ -245,8 +346,12 @@ struct lho_soil_ctx {
     double* tend[3];
     double* Fw;           /* face fluxes of the last rhs call, [col*(nlayer+1)+j] */
     double* Fe;
-    double* colp[5];      /* per-column nu, theta_r, vg_n, vg_alpha, Ksat (NULL: uniform), lho_soil_set_column_params */
+    double* colp[12];     /* per-column nu, theta_r, vg_n, vg_alpha, Ksat | rho_c_ds, kappa_sat_unfrozen, kappa_sat_frozen, kappa_solid,
+                             nu_ss_om, nu_ss_quartz, nu_ss_gravel (NULL: uniform); lho_soil_set_column_params / _heat_params */
     double bcv[4];
+    double* flux_cols[4]; /* lho_soil_set_column_fluxes: per-column VerticalFlux values, LH_BCV_* order (NULL: scalar) */
+    lh_soil_atmos atmos;  /* lho_soil_set_atmos_forcing                                 */
+    int atmos_on;
     double* aux_tab[LH_NUM_FIELDS]; /* lho_soil_set_aux_table: [nrows][nlayer] per prescribed field */
     int64_t aux_rows[LH_NUM_FIELDS];
     int64_t aux_row;
@@ -380,8 +485,9 @@ int32_t lho_soil_destroy(lho_soil_ctx* c)
     for (int k = 0; k < LH_NUM_FIELDS; ++k) free(c->f[k]);
     for (int k = 0; k < 3; ++k) { free(c->u1[k]); free(c->tend[k]); }
     free(c->Fw); free(c->Fe);
-    for (int k = 0; k < 5; ++k) free(c->colp[k]);
+    for (int k = 0; k < 12; ++k) free(c->colp[k]);
     for (int k = 0; k < LH_NUM_FIELDS; ++k) free(c->aux_tab[k]);
+    for (int k = 0; k < 4; ++k) free(c->flux_cols[k]);
     free(c);
     return LH_OK;
 }
@@ -560,6 +666,13 @@ static lh_soil_params params_of_column(const lho_soil_ctx* c, int64_t col)
     if (c->colp[2]) { p.vg_n = c->colp[2][col]; p.vg_m = 1.0 - 1.0 / p.vg_n; }
     if (c->colp[3]) p.vg_alpha = c->colp[3][col];
     if (c->colp[4]) p.Ksat = c->colp[4][col];
+    if (c->colp[5]) p.rho_c_ds = c->colp[5][col];
+    if (c->colp[6]) p.kappa_sat_unfrozen = c->colp[6][col];
+    if (c->colp[7]) p.kappa_sat_frozen = c->colp[7][col];
+    if (c->colp[8]) p.kappa_solid = c->colp[8][col];
+    if (c->colp[9]) p.nu_ss_om = c->colp[9][col];
+    if (c->colp[10]) p.nu_ss_quartz = c->colp[10][col];
+    if (c->colp[11]) p.nu_ss_gravel = c->colp[11][col];
     return p;
 }
 
@@ -596,6 +709,8 @@ static void column_rhs(const lho_soil_ctx* c, const lh_soil_params* p, const dou
     boundary_fluxes(p, model, kappa_dry, &c->cfg.bottom, bcv[LH_BCV_BOTTOM_ENERGY],
                     bcv[LH_BCV_BOTTOM_HYDROLOGY], 1, u_th[0], u_ti[0], T[0], dz / 2.0,
                     &fe_bot, &fw_bot);
+    /* boundary_fluxes(X, bc::PrescribedAtmosForcing, :top, ...) :516-536: from interior_values at the top cell */
+    if (c->atmos_on) lho_turbulent_surface_fluxes(p, &c->atmos, u_th[n - 1], u_ti[n - 1], T[n - 1], &fe_top, &fw_top);
 
     /* Face fluxes.  Interior face j sits between cells j-1 and j (0-based), j = 1..n-1:
      *   water  :181/:358   -interpc2f(K) * gradc2f(h)
@@ -633,7 +748,9 @@ static void rhs_all(lho_soil_ctx* c, const double* th, const double* ti, const d
             size_t o = (size_t)col * n;
             const lh_soil_params pc = params_of_column(c, col);
             const double kappa_dry = lho_k_dry(&pc);                /* :214, :295 */
-            column_rhs(c, &pc, c->bcv, kappa_dry, th + o, ti + o, re + o, T + o, c->tend[0] + o,
+            double bcv[4];
+            for (int k = 0; k < 4; ++k) bcv[k] = c->flux_cols[k] ? c->flux_cols[k][col] : c->bcv[k];
+            column_rhs(c, &pc, bcv, kappa_dry, th + o, ti + o, re + o, T + o, c->tend[0] + o,
                        c->tend[1] + o, c->tend[2] + o, c->Fw + (size_t)col * (n + 1),
                        c->Fe + (size_t)col * (n + 1), work);
         }
@@ -1059,6 +1176,66 @@ int32_t lho_soil_set_column_params(lho_soil_ctx* c, const double* nu, const doub
             memcpy(c->colp[k], src[k], sizeof(double) * (size_t)c->ncol);
         }
     }
+    return LH_OK;
+}
+
+int32_t lho_soil_set_column_heat_params(lho_soil_ctx* c, const double* rho_c_ds, const double* kappa_sat_unfrozen,
+                                        const double* kappa_sat_frozen, const double* kappa_solid, const double* nu_ss_om,
+                                        const double* nu_ss_quartz, const double* nu_ss_gravel)
+{
+    if (!c) return LH_ERR_INVALID_ARG;
+    const double* src[7] = {rho_c_ds, kappa_sat_unfrozen, kappa_sat_frozen, kappa_solid, nu_ss_om, nu_ss_quartz, nu_ss_gravel};
+    if (c->cfg.model == LH_MODEL_RICHARDS)
+        for (int k = 0; k < 7; ++k) if (src[k]) return fail(c, LH_ERR_INVALID_ARG, "the Richards model has no energy equation");
+    for (int k = 0; k < 7; ++k) {
+        free(c->colp[5 + k]);
+        c->colp[5 + k] = NULL;
+        if (src[k]) {
+            c->colp[5 + k] = (double*)malloc(sizeof(double) * (size_t)c->ncol);
+            if (!c->colp[5 + k]) return fail(c, LH_ERR_INVALID_ARG, "out of memory");
+            memcpy(c->colp[5 + k], src[k], sizeof(double) * (size_t)c->ncol);
+        }
+    }
+    return LH_OK;
+}
+
+int32_t lho_soil_set_column_fluxes(lho_soil_ctx* c, const double* const values[4])
+{
+    if (!c) return LH_ERR_INVALID_ARG;
+    const int kinds[4] = {c->cfg.top.energy_kind, c->cfg.top.hydrology_kind, c->cfg.bottom.energy_kind, c->cfg.bottom.hydrology_kind};
+    for (int k = 0; k < 4; ++k)
+        if (values && values[k] && kinds[k] != LH_BC_FLUX) return fail(c, LH_ERR_INVALID_ARG, "per-column fluxes need a face of kind LH_BC_FLUX");
+    for (int k = 0; k < 4; ++k) {
+        free(c->flux_cols[k]);
+        c->flux_cols[k] = NULL;
+        if (values && values[k]) {
+            c->flux_cols[k] = (double*)malloc(sizeof(double) * (size_t)c->ncol);
+            memcpy(c->flux_cols[k], values[k], sizeof(double) * (size_t)c->ncol);
+        }
+    }
+    return LH_OK;
+}
+
+int32_t lho_soil_set_atmos_forcing(lho_soil_ctx* c, const lh_soil_atmos* a)
+{
+    if (!c) return LH_ERR_INVALID_ARG;
+    if (!a) { c->atmos_on = 0; return LH_OK; }
+    if (a->struct_size != (int32_t)sizeof(lh_soil_atmos)) return fail(c, LH_ERR_INVALID_ARG, "lh_soil_atmos.struct_size mismatch");
+    if (c->cfg.model != LH_MODEL_COUPLED)     /* boundary_conditions.jl:103-112: both components must be prognostic */
+        return fail(c, LH_ERR_UNSUPPORTED_BC, "PrescribedAtmosForcing needs SoilEnergyModel + SoilHydrologyModel");
+    if (!(a->z_atm > 0.0) || !(a->rho_a_sfc > 0.0) || !(a->theta_scale > 0.0) || !(c->cfg.params.z_0m > 0.0) || !(c->cfg.params.z_0s > 0.0))
+        return fail(c, LH_ERR_INVALID_ARG, "PrescribedAtmosForcing needs z_atm, rho_a_sfc, theta_scale, z_0m, z_0s > 0");
+    c->atmos = *a;
+    c->atmos_on = 1;
+    return LH_OK;
+}
+
+int32_t lho_soil_atmos_fluxes(lho_soil_ctx* c, const double* th, const double* ti, const double* T, int64_t n,
+                              double* heat, double* water)
+{
+    if (!c || !th || !ti || !T || !heat || !water || n < 0) return LH_ERR_INVALID_ARG;
+    if (!c->atmos_on) return fail(c, LH_ERR_STATE, "lh_soil_set_atmos_forcing has not been called");
+    for (int64_t i = 0; i < n; ++i) lho_turbulent_surface_fluxes(&c->cfg.params, &c->atmos, th[i], ti[i], T[i], &heat[i], &water[i]);
     return LH_OK;
 }
 

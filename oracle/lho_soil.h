@@ -34,6 +34,10 @@
 #define lh_soil_stage_ssprk33     lho_soil_stage_ssprk33
 #define lh_soil_step_ssprk33      lho_soil_step_ssprk33
 #define lh_soil_set_column_params lho_soil_set_column_params
+#define lh_soil_set_column_heat_params lho_soil_set_column_heat_params
+#define lh_soil_set_column_fluxes  lho_soil_set_column_fluxes
+#define lh_soil_set_atmos_forcing  lho_soil_set_atmos_forcing
+#define lh_soil_atmos_fluxes       lho_soil_atmos_fluxes
 #define lh_soil_stepper_named     lho_soil_stepper_named
 #define lh_soil_step              lho_soil_step
 #define lh_soil_budgets           lho_soil_budgets
@@ -91,6 +95,10 @@ double lho_k_solid(double nu_ss_om, double nu_ss_quartz, double k_quartz, double
 double lho_ksat_frozen(double k_solid, double porosity, double k_ice);
 double lho_ksat_unfrozen(double k_solid, double porosity, double k_liq);
 double lho_k_dry(const lh_soil_params* p);
+/* PrescribedAtmosForcing pieces (parity unpinned, include/lh_soil.h) */
+double lho_q_vap_saturation_liquid(const lh_soil_params* p, const lh_soil_atmos* a, double T, double rho);
+void lho_turbulent_surface_fluxes(const lh_soil_params* p, const lh_soil_atmos* a, double theta_l_aug, double theta_i,
+                                  double T, double* heat_flux, double* water_flux);
 
 /* Face fluxes of the last rhs call for ONE column (nlayer+1 values each, bottom face first):
  * the parity tests scale their tolerance by max|flux|.                         */

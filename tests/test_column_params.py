@@ -159,3 +159,87 @@ def test_simulation_with_column_params(backend, oracle):
     ctx.step(0.0, 0.25, 20)
     ref = ctx.get_state(0)[0]
     assert np.max(np.abs(got[k] - ref)) <= 1e-10 * np.max(np.abs(ref))
+
+
+# ---- per-column HEAT parameters (lh_soil_set_column_heat_params; reference parameters.jl:11-43) ---------------------------
+def random_heat_params(wl, seed):
+    rng = np.random.default_rng(seed)
+    p, n = wl.params, wl.ncol
+    om = rng.uniform(0.0, 0.15, n)
+    om[::3] = 0.0                                   # some columns without organic matter (outer Kersten exponents exactly 1)
+    return dict(rho_c_ds=p.rho_c_ds * rng.uniform(0.7, 1.3, n), kappa_sat_unfrozen=p.kappa_sat_unfrozen * rng.uniform(0.7, 1.4, n),
+                kappa_sat_frozen=p.kappa_sat_frozen * rng.uniform(0.7, 1.4, n), kappa_solid=p.kappa_solid * rng.uniform(0.6, 1.5, n),
+                nu_ss_om=om, nu_ss_quartz=rng.uniform(0.2, 0.8, n), nu_ss_gravel=rng.uniform(0.0, 0.15, n))
+
+
+def test_oracle_heat_columns_are_independent_single_column_runs(oracle):
+    """Column k of a run with per-column heat parameters == a homogeneous single-column run with column k's SoilParams."""
+    wl = w.coupled_workload(ncol=5, nlayer=18, seed=91, ice=True)
+    hp = random_heat_params(wl, 3)
+    a = lh.SoilContext(oracle, wl.config())
+    a.set_column_heat_params(**hp)
+    wl.upload(a)
+    a.step(0.0, wl.dt, 4)
+    for k in (0, 1, 4):
+        cfg = wl.config(ncol=1)
+        for name, arr in hp.items():
+            setattr(cfg.params, name, float(arr[k]))
+        b = lh.SoilContext(oracle, cfg)
+        for f, arr in wl.fields.items():
+            b.set_state(f, arr[k:k + 1])
+        b.step(0.0, wl.dt, 4)
+        for f in (0, 2):
+            assert np.array_equal(a.get_state(f)[k], b.get_state(f)[0]), (k, f)
+    r = lh.SoilContext(oracle, w.richards_workload(ncol=4, nlayer=8).config())
+    with pytest.raises(lh._abi.SoilError):
+        r.set_column_heat_params(rho_c_ds=np.ones(4))
+    a.set_column_heat_params()                      # all None: back to the scalars
+    h = lh.SoilContext(oracle, wl.config())
+    for ctx in (a, h):
+        wl.upload(ctx)
+        ctx.step(0.0, wl.dt, 2)
+    assert np.array_equal(a.get_state(2), h.get_state(2))
+
+
+HEAT_CASES = {
+    "coupled": lambda: w.coupled_workload(ncol=200, nlayer=64, seed=92),
+    "coupled_ice": lambda: w.coupled_workload(ncol=96, nlayer=24, seed=93, ice=True),
+    "heat": lambda: w.heat_workload(ncol=64, nlayer=37, seed=94),
+    "heat_ice": lambda: w.heat_workload(ncol=70, nlayer=20, seed=95, ice=True),
+}
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("name", sorted(HEAT_CASES))
+@pytest.mark.parametrize("with_hydraulic", [False, True])
+def test_cuda_heat_params_match_oracle(cuda, oracle, name, with_hydraulic):
+    wl = HEAT_CASES[name]()
+    hp = random_heat_params(wl, seed=11)
+    cp = random_column_params(wl, seed=12) if (with_hydraulic and wl.model == abi.LH_MODEL_COUPLED) else {}
+    if cp:
+        rescale_state(wl, cp)
+        wl.top = (wl.top[0], wl.top[1], wl.top[2], 0.3)
+    g, o = lh.SoilContext(cuda, wl.config(flags=abi.LH_FLAG_STAGE_LAUNCHES)), lh.SoilContext(oracle, wl.config())
+    for ctx in (g, o):
+        if cp:
+            ctx.set_column_params(**cp)
+        ctx.set_column_heat_params(**hp)
+        wl.upload(ctx)
+        ctx.rhs(0.0)
+    assert "HETH" in g.kernel_info()
+    fields = (0, 2) if wl.model == abi.LH_MODEL_COUPLED else (2,)
+    for f in fields:
+        a, r = g.get_tendency(f), o.get_tendency(f)
+        scale = w.tendency_scale(o, f)
+        assert np.max(np.abs(a - r) / scale[:, None]) <= 1e-12, (name, f)
+    a, r = g.diagnostic(abi.LH_DIAG_KAPPA), o.diagnostic(abi.LH_DIAG_KAPPA)
+    assert np.max(np.abs(a - r) / np.abs(r)) <= 2e-13
+    a, r = g.diagnostic(abi.LH_DIAG_T), o.diagnostic(abi.LH_DIAG_T)
+    assert np.max(np.abs(a - r) / np.abs(r)) <= 2e-13
+    for ctx in (g, o):
+        ctx.step(0.0, wl.dt, 6)
+    for f in fields:
+        a, r = g.get_state(f), o.get_state(f)
+        assert np.max(np.abs(a - r)) <= 1e-10 * np.max(np.abs(r)), (name, f)
+    g.set_column_heat_params()                      # heat scalars again; hydraulic arrays (if any) stay
+    assert "HETH" not in g.kernel_info() and (("HET" in g.kernel_info()) == bool(cp))

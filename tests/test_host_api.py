@@ -262,10 +262,11 @@ def test_unsupported_bc_raises(backend):
     Y, Ya = lh.default_initial_conditions(m)
     with pytest.raises(lh.UnsupportedBCError):
         lh.make_rhs(m)(lh.similar(Y), Y, Ya, 0.0)
-    with pytest.raises(NotImplementedError):
-        lh.build_config(coupled_model(lh.SoilColumnBC(
-            top=lh.PrescribedAtmosForcing(u_atm=1.0, θ_atm=300.0, z_atm=2.0, θ_scale=300.0, ρ_a_sfc=1.2, q_atm=0.01),
-            bottom=lh.SoilComponentBC(energy=lh.VerticalFlux(0.0), hydrology=lh.VerticalFlux(0.0)))))
+    # PrescribedAtmosForcing is built now (tests/test_prescribed_atmos_bc.py): as far as the config goes its face is a flux
+    cfg = lh.build_config(coupled_model(lh.SoilColumnBC(
+        top=lh.PrescribedAtmosForcing(u_atm=1.0, θ_atm=300.0, z_atm=2.0, θ_scale=300.0, ρ_a_sfc=1.2, q_atm=0.01),
+        bottom=lh.SoilComponentBC(energy=lh.VerticalFlux(0.0), hydrology=lh.VerticalFlux(0.0)))))
+    assert cfg.top.energy_kind == abi.LH_BC_FLUX and cfg.top.hydrology_kind == abi.LH_BC_FLUX
 
 
 def test_simulation_argument_errors():
@@ -316,7 +317,7 @@ def test_bench_b200_arm_json_line():
                 "dtype", "data", "config", "clocks", "gpu_launches", "roofline", "e2e", "cpu_baseline", "budgets"):
         assert key in d, key
     nb = d["sustained"]["blocks"]
-    assert nb >= 3 and d["sustained"]["device_seconds"] >= 0.5
+    assert nb >= 3 and d["sustained"]["device_seconds"] >= 0.3
     assert d["n_gpus"] == 1 and d["steps"] == 3 and d["gpu_launches"] in (9 * nb, nb) and d["value"] > 1e9
     assert d["clocks"]["samples"] >= 1 and d["clocks"]["sm_mhz"] > 0
     r = d["roofline"]
@@ -324,3 +325,92 @@ def test_bench_b200_arm_json_line():
     assert 0 < r["frac_on_wire"] <= r["frac"] and r["on_wire_bytes_per_cell_step"] in (128, 32) and "FLAGS=4" in r["variant"]
     assert d["e2e"]["h2d_bytes_per_step"] > 0 and d["e2e"]["d2h_bytes_per_step"] > 0 and 0 < d["e2e"]["value"] < d["value"]
     assert d["cpu_baseline"]["kind"] == "port" and d["cpu_baseline"]["value"] > 0
+
+
+# ---- run!(sim) in one device call, callbacks that modify u, time-dependent profiles with any stepper ---------------------------
+def _richards_model(Tp=None, n=24):
+    vg = w.sand_vg()
+    visc = lh.TemperatureDependentViscosity() if Tp is not None else lh.NoEffect()
+    return lh.SoilModel(
+        domain=lh.Column(zlim=(-1.5, 0.0), nelements=n),
+        energy_model=lh.PrescribedTemperatureModel(T_profile=Tp) if Tp is not None else lh.PrescribedTemperatureModel(),
+        hydrology_model=lh.SoilHydrologyModel(hydraulic_model=vg, viscosity_factor=visc),
+        boundary_conditions=lh.SoilColumnBC(top=lh.SoilComponentBC(hydrology=lh.Dirichlet(lambda t: 0.267 + 1e-4 * t)),
+                                            bottom=lh.SoilComponentBC(hydrology=lh.FreeDrainage())),
+        soil_param_set=w.sand_soil_params(), earth_param_set=param_set)
+
+
+def test_saveat_run_in_one_call_equals_stepping(backend):
+    """simulation.jl:64-70 (saveat): run! as ONE lh_soil_run call (snapshots overlapped on the device) gives the same sol.t /
+    sol.u as stepping with step! and saving on the host."""
+    model = _richards_model()
+    Y, Ya = lh.initialize_states(model, lambda z, m: dict(ϑ_l=0.1 + 0.05 * (z + 1.5), θ_i=0.0), 0.0)
+    dt, nsteps, every = 0.25, 12, 3
+    a = lh.Simulation(model, lh.SSPRK33(), Y_init=lh.copy(Y), dt=dt, tspan=(0.0, dt * nsteps), Ya_init=Ya, saveat=every * dt)
+    sol = lh.run_(a)
+    assert sol.t == [k * every * dt for k in range(nsteps // every + 1)]
+    b = lh.Simulation(model, lh.SSPRK33(), Y_init=lh.copy(Y), dt=dt, tspan=(0.0, dt * nsteps), Ya_init=Ya, saveat=every * dt,
+                      callbacks=lambda integ: None)          # a callback forces the step-by-step host loop
+    solb = lh.run_(b)
+    assert sol.t == solb.t and len(sol.u) == len(solb.u)
+    for ua, ub in zip(sol.u, solb.u):
+        assert np.array_equal(ua.soil["ϑ_l"], ub.soil["ϑ_l"])
+    assert np.array_equal(a.integrator.u.soil["ϑ_l"], sol.u[-1].soil["ϑ_l"])
+
+
+def test_callback_modifications_reach_the_device(backend):
+    """DiffEq callbacks may modify integrator.u: the change must be integrated, not silently dropped."""
+    model = _richards_model()
+    Y, Ya = lh.initialize_states(model, lambda z, m: dict(ϑ_l=0.1 + 0.05 * (z + 1.5), θ_i=0.0), 0.0)
+    dt = 0.25
+
+    def wet(integ):
+        if integ.iter == 2:
+            integ.u.soil["ϑ_l"][...] = integ.u.soil["ϑ_l"] + 0.01
+
+    a = lh.Simulation(model, lh.SSPRK33(), Y_init=lh.copy(Y), dt=dt, tspan=(0.0, 4 * dt), Ya_init=Ya, callbacks=wet)
+    lh.run_(a)
+    # the same by hand: 2 steps, modify, 2 steps
+    b = lh.Simulation(model, lh.SSPRK33(), Y_init=lh.copy(Y), dt=dt, tspan=(0.0, 2 * dt), Ya_init=Ya)
+    lh.run_(b)
+    Y2 = lh.copy(b.integrator.u)
+    Y2.soil["ϑ_l"][...] = Y2.soil["ϑ_l"] + 0.01
+    c = lh.Simulation(model, lh.SSPRK33(), Y_init=Y2, dt=dt, tspan=(2 * dt, 4 * dt), Ya_init=Ya)
+    lh.run_(c)
+    assert np.array_equal(a.integrator.u.soil["ϑ_l"], c.integrator.u.soil["ϑ_l"])
+    never = lh.Simulation(model, lh.SSPRK33(), Y_init=lh.copy(Y), dt=dt, tspan=(0.0, 4 * dt), Ya_init=Ya, callbacks=wet,
+                          callback_reupload="never")
+    lh.run_(never)
+    assert not np.array_equal(never.integrator.u.soil["ϑ_l"], a.integrator.u.soil["ϑ_l"])
+
+
+@pytest.mark.parametrize("method", ["SSPRK33", "SSPRK43", "CarpenterKennedy2N54"])
+def test_time_dependent_profile_tables_any_stepper(backend, method):
+    """Prescribed T(z, t) streamed as a table of stage rows (lh_soil_set_aux_table) == uploading the profile by hand before
+    every stage through the ABI (what the round-1 host loop did, three synchronisations per step)."""
+    Tp = lambda z, t: 288.0 + 5.0 * z + 0.5 * t
+    model = _richards_model(Tp)
+    Y, Ya = lh.initialize_states(model, lambda z, m: dict(ϑ_l=0.1 + 0.05 * (z + 1.5), θ_i=0.0), 0.0)
+    dt, nsteps = 0.25, 5
+    meth = getattr(lh, method)()
+    sim = lh.Simulation(model, meth, Y_init=lh.copy(Y), dt=dt, tspan=(0.0, dt * nsteps), Ya_init=Ya, saveat=dt * nsteps)
+    lh.run_(sim)
+    eng = lh.SoilEngine(model, 0.0)
+    eng.upload(Y)
+    tab = meth.table(eng.lib)
+    t = 0.0
+    for _ in range(nsteps):
+        if tab is None:
+            for stage, c in ((1, 0.0), (2, 1.0), (3, 0.5)):
+                eng.ctx.set_aux(abi.LH_FIELD_T, np.array([Tp(z, t + c * dt) for z in eng.zc]), per_layer=True)
+                eng.ctx.set_bc_values(eng.bc_values(t + c * dt))
+                eng.ctx.stage(stage, dt)
+        else:
+            # one-stage tables: the generic stepper with a single-step call per stage is not expressible, so compare with a
+            # table-driven call on a second engine fed by lh_soil_set_aux_table directly
+            rows = np.array([[Tp(z, t + c * dt) for z in eng.zc] for c in meth.c])
+            eng.ctx.set_aux_table(abi.LH_FIELD_T, rows)
+            bct = np.array([eng.bc_values(t + c * dt) for c in meth.c])[None]
+            eng.ctx.step_with(tab, t, dt, 1, bct)
+        t += dt
+    assert np.array_equal(sim.integrator.u.soil["ϑ_l"], eng.ctx.get_state(0).reshape(-1))

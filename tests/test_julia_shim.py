@@ -12,7 +12,7 @@ HDR = os.path.join(graft.ROOT, "include", "lh_soil.h")
 C2JL = {"double": "Cdouble", "int32_t": "Int32", "int64_t": "Int64", "const double*": "Ptr{Cdouble}", "double*": "Ptr{Cdouble}",
         "lh_soil_params": "LhSoilParams", "lh_soil_face_bc": "LhSoilFaceBC"}
 STRUCTS = {"lh_soil_params": "LhSoilParams", "lh_soil_face_bc": "LhSoilFaceBC", "lh_soil_config": "LhSoilConfig",
-           "lh_soil_run_opts": "LhSoilRunOpts", "lh_soil_stepper": "LhSoilStepper"}
+           "lh_soil_run_opts": "LhSoilRunOpts", "lh_soil_stepper": "LhSoilStepper", "lh_soil_atmos": "LhSoilAtmos"}
 
 
 def header_source():
