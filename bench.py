@@ -340,7 +340,10 @@ def _main(args, result_stream):
     clocks = sampler.stop(w0, w1) if rank == 0 else None
     block_ms = rank_max(block_ms)                          # per block: the slowest rank
     ms_med = float(np.median(block_ms))
-    if rank == 0 and (clocks is None or not clocks.get("samples")):
+    if rank == 0 and (clocks is None or not clocks.get("samples")) and (w1 - w0) < 0.25 and args.min_seconds < 0.25:
+        # profiling runs (--min-seconds 0 under ncu): a timed region shorter than a few sampling periods cannot be vetted
+        clocks = dict(clocks or {}, note=f"timed region {w1 - w0:.3f} s is shorter than the 50 ms sampling period allows; not vetted")
+    elif rank == 0 and (clocks is None or not clocks.get("samples")):
         raise SystemExit(f"clock sampler recorded no nvidia-smi sample inside the {w1 - w0:.2f} s timed region: "
                          "the measurement cannot be vetted for throttling (is nvidia-smi on PATH?)")
 
@@ -464,9 +467,10 @@ def _main(args, result_stream):
     on_wire = cells_rank * (wire_bpcs or bpcs) * args.steps / nl / (launch_ms * 1e-3) / 1e9
     traffic, traffic_src = None, None
     tpath = os.path.join(ROOT, "profiles", "dram_traffic.json")
-    if os.path.exists(tpath) and not persistent and not (args.ice or args.het or args.general_vg):
+    if os.path.exists(tpath) and not persistent and not args.het:
         try:
-            traffic = json.load(open(tpath)).get(f"{args.model}_{args.ncol}x{args.nlayer}_bytes_per_launch")
+            tkey = args.model + ("_general_vg" if (args.general_vg and args.model == "coupled") else "") + ("_ice" if args.ice else "")
+            traffic = json.load(open(tpath)).get(f"{tkey}_{args.ncol}x{args.nlayer}_bytes_per_launch")
             if traffic is not None:
                 traffic = traffic * cells_rank / (args.ncol * args.nlayer)     # measured at N = 1; per launch of this rank's shard
                 traffic_src = "profiles/dram_traffic.json (CACHED ncu --set full capture of this command, not measured in this run)"

@@ -208,6 +208,14 @@ int32_t lh_soil_set_column_heat_params(lh_soil_ctx* ctx, const double* rho_c_ds,
                                        const double* kappa_sat_frozen, const double* kappa_solid, const double* nu_ss_om,
                                        const double* nu_ss_quartz, const double* nu_ss_gravel);
 
+/* Layered soils: per-CELL hydraulic parameters (new): ν, θr, van Genuchten n and α, K_sat as fields over (column, layer),
+ * addressed host[col * col_stride + layer * layer_stride] like a state field; NULL keeps the per-column value (or the
+ * model's scalar) for that parameter, all NULL removes the fields.  The kernels then re-read nine derived values per cell and
+ * stage (+72 B per cell and stage on top of the state traffic: the path becomes HBM-heavier).  κ_dry follows
+ * ν cell by cell (k_dry, SoilHeatParameterizations.jl:280-294).  Heat parameters stay per column.                      */
+int32_t lh_soil_set_cell_params(lh_soil_ctx* ctx, const double* nu, const double* theta_r, const double* vg_n,
+                                const double* vg_alpha, const double* Ksat, int64_t col_stride, int64_t layer_stride);
+
 /* Spatially varying prescribed fluxes (new): per-column values for the faces whose kind is LH_BC_FLUX (VerticalFlux,
  * boundary_conditions.jl:43-46,295-301), indexed like the boundary-value 4-vector: values[LH_BCV_*] is an array of ncol
  * doubles or NULL (the scalar of lh_soil_set_bc_values / the bc table applies).  E.g. a precipitation or ground heat flux

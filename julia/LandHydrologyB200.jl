@@ -337,6 +337,15 @@ function set_column_params!(e::Engine; ν = nothing, θr = nothing, n = nothing,
     return nothing
 end
 
+"Layered soils: per-cell ν, θr, n, α, Ksat as (n, ncol) matrices (layer fastest), `nothing` keeps the per-column value."
+function set_cell_params!(e::Engine; ν = nothing, θr = nothing, n = nothing, α = nothing, Ksat = nothing)
+    ptr(a) = a === nothing ? Ptr{Cdouble}(C_NULL) : pointer(a)
+    arrs = map(a -> a === nothing ? nothing : Matrix{Float64}(a), (ν, θr, n, α, Ksat))
+    GC.@preserve arrs check(e.ctx, ccall((:lh_soil_set_cell_params, LIB), Int32,
+        (Ptr{Cvoid}, Ptr{Cdouble}, Ptr{Cdouble}, Ptr{Cdouble}, Ptr{Cdouble}, Ptr{Cdouble}, Int64, Int64), e.ctx, map(ptr, arrs)..., e.n, 1))
+    return nothing
+end
+
 "Per-column heat parameters of SoilParams (ρc_ds, κ_sat_unfrozen, κ_sat_frozen, κ_solid, ν_ss_om, ν_ss_quartz, ν_ss_gravel)."
 function set_column_heat_params!(e::Engine; ρc_ds = nothing, κ_sat_unfrozen = nothing, κ_sat_frozen = nothing, κ_solid = nothing,
                                  ν_ss_om = nothing, ν_ss_quartz = nothing, ν_ss_gravel = nothing)

@@ -160,6 +160,7 @@ _SIGNATURES = {
     "soil_set_aux": ([_vp, C.c_int32, _dp, C.c_int64, C.c_int64], C.c_int32),
     "soil_set_column_params": ([_vp, _dp, _dp, _dp, _dp, _dp], C.c_int32),
     "soil_set_column_heat_params": ([_vp, _dp, _dp, _dp, _dp, _dp, _dp, _dp], C.c_int32),
+    "soil_set_cell_params": ([_vp, _dp, _dp, _dp, _dp, _dp, C.c_int64, C.c_int64], C.c_int32),
     "soil_set_column_fluxes": ([_vp, C.POINTER(_dp)], C.c_int32),
     "soil_set_atmos_forcing": ([_vp, C.POINTER(lh_soil_atmos)], C.c_int32),
     "soil_atmos_fluxes": ([_vp, _dp, _dp, _dp, C.c_int64, _dp, _dp], C.c_int32),
@@ -376,6 +377,20 @@ class SoilContext:
                 raise ValueError(f"per-column parameter must have shape ({self.ncol},)")
             arrs.append(a)
         self._check(self.lib.soil_set_column_heat_params(self._h, *[None if a is None else _as_double_ptr(a) for a in arrs]))
+
+    def set_cell_params(self, nu=None, theta_r=None, vg_n=None, vg_alpha=None, Ksat=None):
+        """``lh_soil_set_cell_params``: per-cell (layered) hydraulic parameters, arrays of shape (ncol, nlayer); None keeps the
+        per-column value or the model's scalar."""
+        arrs = []
+        for a in (nu, theta_r, vg_n, vg_alpha, Ksat):
+            if a is None:
+                arrs.append(None)
+                continue
+            a = np.ascontiguousarray(a, dtype=np.float64)
+            if a.shape != (self.ncol, self.nlayer):
+                raise ValueError(f"per-cell parameter must have shape ({self.ncol}, {self.nlayer})")
+            arrs.append(a)
+        self._check(self.lib.soil_set_cell_params(self._h, *[None if a is None else _as_double_ptr(a) for a in arrs], self.nlayer, 1))
 
     def set_column_fluxes(self, top_energy=None, top_hydrology=None, bottom_energy=None, bottom_hydrology=None):
         """``lh_soil_set_column_fluxes``: per-column VerticalFlux values (arrays of ncol doubles) for faces of kind LH_BC_FLUX."""

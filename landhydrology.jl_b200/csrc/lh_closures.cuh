@@ -89,6 +89,30 @@ enum { LHCP_NU, LHCP_THETA_R, LHCP_THETA_R_EPS, LHCP_INV_NU_THR, LHCP_NU_THR, LH
        LHCP_RHO_C_DS, LHCP_KERSTEN_P1, LHCP_KERSTEN_P2, LHCP_KERSTEN_P3, LHCP_K_UNFROZEN, LHCP_LOG2_K_UNFROZEN, LHCP_LOG2_K_FROZEN,
        LHCP_COUNT };
 
+// Per-cell derived parameter fields, [LHCELL_COUNT][nlayer][ncol_pad] (lh_soil_api.cu rebuild_cell_params); the cheap
+// derivatives (theta_r + eps, nu - theta_r, 1 - m, kappa_unfrozen - kappa_dry) are formed in the kernel.
+enum { LHCELL_NU, LHCELL_THETA_R, LHCELL_INV_NU_THR, LHCELL_VG_M, LHCELL_VG_INV_M, LHCELL_NEG_INV_ALPHA, LHCELL_KSAT,
+       LHCELL_INV_NU, LHCELL_KAPPA_DRY, LHCELL_COUNT };
+
+// Overwrites the cell-dependent members of a lane's parameter view from the per-cell fields: cp points at this lane's
+// element of field 0 for the cell, fs is the field stride (nlayer * ncol_pad).
+__device__ __forceinline__ void lh_load_cell_params(LhLaneParams& p, const double* __restrict__ cp, int64_t fs)
+{
+    p.nu = __ldg(cp + LHCELL_NU * fs);
+    p.theta_r = __ldg(cp + LHCELL_THETA_R * fs);
+    p.inv_nu_thr = __ldg(cp + LHCELL_INV_NU_THR * fs);
+    p.vg_m = __ldg(cp + LHCELL_VG_M * fs);
+    p.vg_inv_m = __ldg(cp + LHCELL_VG_INV_M * fs);
+    p.neg_inv_alpha = __ldg(cp + LHCELL_NEG_INV_ALPHA * fs);
+    p.Ksat = __ldg(cp + LHCELL_KSAT * fs);
+    p.inv_nu = __ldg(cp + LHCELL_INV_NU * fs);
+    p.kappa_dry = __ldg(cp + LHCELL_KAPPA_DRY * fs);
+    p.theta_r_eps = p.theta_r + LH_EPS;
+    p.nu_thr = p.nu - p.theta_r;
+    p.vg_inv_n = 1.0 - p.vg_m;                       // 1/n = 1 - m (Mualem), within 1 ulp of the quotient
+    p.k_unfrozen_minus_dry = p.k_unfrozen - p.kappa_dry;
+}
+
 // Copies the exp2 / log2 tables from the parameter block, and the fixed-exponent power tables from `pow_tab`
 // (LHPW_COUNT * LH_POW_DOUBLES doubles in global memory, written once by lh_soil_create), to shared memory
 // (LH_TAB_ALL doubles, 16-byte aligned destination); the caller must __syncthreads().
@@ -131,6 +155,10 @@ struct LhCell {
 //         Kersten exponents that follow nu_ss_om / nu_ss_quartz / nu_ss_gravel.  Implies HET; nu_ss_om may differ from column
 //         to column, so the outer Kersten exponents are always evaluated (no om_zero shortcut).
 #define LH_FLAG_HETH 16
+//   CELLP: per-CELL hydraulic parameters (lh_soil_set_cell_params: layered soils): the lane's nu, theta_r, van Genuchten and
+//         Ksat values (and what derives from them) are re-read from LHCELL_COUNT fields before every cell (+72 B per cell and
+//         stage).  Implies HET (and HETH for the models with an energy equation).
+#define LH_FLAG_CELLP 32
 
 // ---------------------------------------------------------------------------------------------
 // Water: K and psi of one cell.  Reference: right_hand_side.jl:156-166 / :308-313.

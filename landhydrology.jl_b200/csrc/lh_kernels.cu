@@ -170,7 +170,7 @@ template <int MODEL, bool HET>
 __global__ void lh_diag_kernel(const __grid_constant__ LhDevParams pu, const double* __restrict__ pow_tab, int which,
                                const double* __restrict__ th, const double* __restrict__ ti, const double* __restrict__ re,
                                const double* __restrict__ T, double* __restrict__ out, int64_t n,
-                               const double* __restrict__ colp, int64_t ncol_pad, int heat)
+                               const double* __restrict__ colp, int64_t ncol_pad, int heat, const double* __restrict__ cellp)
 {
     __shared__ __align__(16) double tab[LH_TAB_ALL];
     lh_stage_tables(pu, pow_tab, tab, threadIdx.x, blockDim.x);
@@ -179,7 +179,8 @@ __global__ void lh_diag_kernel(const __grid_constant__ LhDevParams pu, const dou
     if (i >= n) return;
     const double x = MODEL == 0 ? T[i] : re[i];
     if constexpr (HET) {
-        const LhLaneParams p = lh_lane_params(pu, colp, i % ncol_pad, ncol_pad, heat != 0);
+        LhLaneParams p = lh_lane_params(pu, colp, i % ncol_pad, ncol_pad, heat != 0);
+        if (cellp) lh_load_cell_params(p, cellp + i, n);          // n = nlayer * ncol_pad = the field stride
         out[i] = lh_diag_value<MODEL>(p, tab, which, th[i], ti[i], x);
     } else {
         out[i] = lh_diag_value<MODEL>(pu, tab, which, th[i], ti[i], x);
@@ -189,16 +190,16 @@ __global__ void lh_diag_kernel(const __grid_constant__ LhDevParams pu, const dou
 
 cudaError_t lh_launch_diagnostic(int model, int which, const LhDevParams& p, const double* pow_tab, const double* th,
                                  const double* ti, const double* re, const double* T, double* out,
-                                 int64_t n, const double* colp, int64_t ncol_pad, int heat, cudaStream_t stream)
+                                 int64_t n, const double* colp, int64_t ncol_pad, int heat, const double* cellp, cudaStream_t stream)
 {
     const int block = 256;
     const unsigned grid = (unsigned)((n + block - 1) / block);
     if (model == LH_MODEL_RICHARDS) {
-        if (colp) lh_diag_kernel<0, true><<<grid, block, 0, stream>>>(p, pow_tab, which, th, ti, re, T, out, n, colp, ncol_pad, heat);
-        else lh_diag_kernel<0, false><<<grid, block, 0, stream>>>(p, pow_tab, which, th, ti, re, T, out, n, colp, ncol_pad, heat);
+        if (colp) lh_diag_kernel<0, true><<<grid, block, 0, stream>>>(p, pow_tab, which, th, ti, re, T, out, n, colp, ncol_pad, heat, cellp);
+        else lh_diag_kernel<0, false><<<grid, block, 0, stream>>>(p, pow_tab, which, th, ti, re, T, out, n, colp, ncol_pad, heat, cellp);
     } else {
-        if (colp) lh_diag_kernel<2, true><<<grid, block, 0, stream>>>(p, pow_tab, which, th, ti, re, T, out, n, colp, ncol_pad, heat);
-        else lh_diag_kernel<2, false><<<grid, block, 0, stream>>>(p, pow_tab, which, th, ti, re, T, out, n, colp, ncol_pad, heat);
+        if (colp) lh_diag_kernel<2, true><<<grid, block, 0, stream>>>(p, pow_tab, which, th, ti, re, T, out, n, colp, ncol_pad, heat, cellp);
+        else lh_diag_kernel<2, false><<<grid, block, 0, stream>>>(p, pow_tab, which, th, ti, re, T, out, n, colp, ncol_pad, heat, cellp);
     }
     return cudaGetLastError();
 }
@@ -222,7 +223,8 @@ template <bool HET>
 __global__ void lh_atmos_flux_kernel(const __grid_constant__ LhDevParams pu, const double* __restrict__ pow_tab, const LhAtmos atm,
                                      const double* __restrict__ th_top, const double* __restrict__ ti_top,
                                      const double* __restrict__ re_top, double* __restrict__ flux_e, double* __restrict__ flux_w,
-                                     int64_t ncol_pad, const double* __restrict__ colp, int heat_cols)
+                                     int64_t ncol_pad, const double* __restrict__ colp, int heat_cols,
+                                     const double* __restrict__ cellp_top, int64_t cell_fs)
 {
     __shared__ __align__(16) double tab[LH_TAB_ALL];
     lh_stage_tables(pu, pow_tab, tab, threadIdx.x, blockDim.x);
@@ -232,7 +234,8 @@ __global__ void lh_atmos_flux_kernel(const __grid_constant__ LhDevParams pu, con
     const double th = th_top[col], ti = ti_top[col], re = re_top[col];
     double psi, dT;
     if constexpr (HET) {
-        const LhLaneParams p = lh_lane_params(pu, colp, col, ncol_pad, heat_cols != 0);
+        LhLaneParams p = lh_lane_params(pu, colp, col, ncol_pad, heat_cols != 0);
+        if (cellp_top) lh_load_cell_params(p, cellp_top + col, cell_fs);
         const double nu_eff = p.nu - ti;
         dT = lh_temperature_minus_T0<true>(p, th < nu_eff ? th : nu_eff, ti, re);
         psi = lh_surface_matric_potential(p, tab, th, ti);
@@ -266,12 +269,12 @@ __global__ void lh_atmos_eval_kernel(const __grid_constant__ LhDevParams pu, con
 
 cudaError_t lh_launch_atmos_fluxes(const LhDevParams& p, const double* pow_tab, const LhAtmos& atm, const double* th_top,
                                    const double* ti_top, const double* re_top, double* flux_e, double* flux_w, int64_t ncol_pad,
-                                   const double* colp, int heat_cols, cudaStream_t stream)
+                                   const double* colp, int heat_cols, const double* cellp_top, int64_t cell_fs, cudaStream_t stream)
 {
     const int block = 128;
     const unsigned grid = (unsigned)((ncol_pad + block - 1) / block);
-    if (colp) lh_atmos_flux_kernel<true><<<grid, block, 0, stream>>>(p, pow_tab, atm, th_top, ti_top, re_top, flux_e, flux_w, ncol_pad, colp, heat_cols);
-    else lh_atmos_flux_kernel<false><<<grid, block, 0, stream>>>(p, pow_tab, atm, th_top, ti_top, re_top, flux_e, flux_w, ncol_pad, colp, heat_cols);
+    if (colp) lh_atmos_flux_kernel<true><<<grid, block, 0, stream>>>(p, pow_tab, atm, th_top, ti_top, re_top, flux_e, flux_w, ncol_pad, colp, heat_cols, cellp_top, cell_fs);
+    else lh_atmos_flux_kernel<false><<<grid, block, 0, stream>>>(p, pow_tab, atm, th_top, ti_top, re_top, flux_e, flux_w, ncol_pad, colp, heat_cols, cellp_top, cell_fs);
     return cudaGetLastError();
 }
 

@@ -17,7 +17,7 @@
 #endif
 #define LH_WARPS_PER_SM 20
 #define LH_WARPS_PER_SM_HET 16
-template <int FLAGS> struct LhBounds { static constexpr int max_threads = ((FLAGS & LH_FLAG_HET) ? LH_WARPS_PER_SM_HET : LH_WARPS_PER_SM) * 32; };
+template <int FLAGS> struct LhBounds { static constexpr int max_threads = ((FLAGS & LH_FLAG_HET) ? LH_WARPS_PER_SM_HET : LH_WARPS_PER_SM) * 32; };   // CELLP implies HET
 
 // What one stage reads and writes (device pointers to column-fastest SoA blocks) and its scalars.
 struct LhStageIO {
@@ -46,6 +46,7 @@ struct LhKernelArgs {
     const double* zc;      // nlayer centre coordinates
     const double* pow_tab; // LHPW_COUNT fixed-exponent power tables (lh_math.cuh), written once by lh_soil_create
     const double* colp;    // HET variants: [LHCP_COUNT][ncol_pad] per-column derived parameters
+    const double* cellp;   // CELLP variants: [LHCELL_COUNT][nlayer][ncol_pad] per-cell derived parameters
     double* budget_partials;   // [nblocks][2]: per-block sums of the ϑ_l and ρe_int values the last stage writes (or NULL)
     int64_t ncol;          // valid columns (<= ncol_pad): the padding is left out of the budgets
     int64_t ncol_pad;
@@ -90,14 +91,14 @@ cudaError_t lh_launch_any_nonzero(const double* x, int64_t n, int* flag, cudaStr
 // Pointwise diagnostics (LH_DIAG_*): out[layer*ncol_pad+col].
 cudaError_t lh_launch_diagnostic(int model, int which, const LhDevParams& p, const double* pow_tab, const double* th,
                                  const double* ti, const double* re, const double* T, double* out,
-                                 int64_t ncells_pad, const double* colp, int64_t ncol_pad, int heat, cudaStream_t stream);
+                                 int64_t ncells_pad, const double* colp, int64_t ncol_pad, int heat, const double* cellp, cudaStream_t stream);
 
 // PrescribedAtmosForcing (lh_atmos.cuh): per column, from the top cell (layer nlayer-1) of the stage input, the turbulent
 // heat flux and water volume flux into flux_e[col], flux_w[col].
 struct LhAtmos;
 cudaError_t lh_launch_atmos_fluxes(const LhDevParams& p, const double* pow_tab, const LhAtmos& atm, const double* th_top,
                                    const double* ti_top, const double* re_top, double* flux_e, double* flux_w, int64_t ncol_pad,
-                                   const double* colp, int heat_cols, cudaStream_t stream);
+                                   const double* colp, int heat_cols, const double* cellp_top, int64_t cell_fs, cudaStream_t stream);
 // The same for n given surface states (theta_l, theta_i, T): lh_soil_atmos_fluxes.
 cudaError_t lh_launch_atmos_eval(const LhDevParams& p, const double* pow_tab, const LhAtmos& atm, const double* th, const double* ti,
                                  const double* T, double* heat, double* water, int64_t n, cudaStream_t stream);

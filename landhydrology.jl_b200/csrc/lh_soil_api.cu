@@ -102,6 +102,9 @@ struct lh_soil_ctx {
     // nu_ss_om, nu_ss_quartz, nu_ss_gravel (empty: the model's scalar)
     std::vector<double> col_user[12];
     bool col_heat = false;                       // some heat parameter is per column -> LH_FLAG_HETH
+    // lh_soil_set_cell_params: nu, theta_r, vg_n, vg_alpha, Ksat per CELL, dense [col * nlayer + layer] (empty: per column / scalar)
+    std::vector<double> cell_user[5];
+    double* cellp_dev = nullptr;                 // [LHCELL_COUNT][nlayer][ncol_pad] derived per-cell parameters -> LH_FLAG_CELLP
     double* pow_tab_dev = nullptr;               // LHPW_COUNT fixed-exponent power tables (lh_math.cuh), built at create
     std::vector<double> pow_tab;                 // their host copy
     double* diag_dev = nullptr;                  // scratch field of lh_soil_diagnostic (lazily allocated)
@@ -284,6 +287,7 @@ void free_all(lh_soil_ctx* c)
     for (auto& e : c->ev_snap_done) if (e) cudaEventDestroy(e);
     if (c->fused_partials) cudaFree(c->fused_partials);
     if (c->colp_dev) cudaFree(c->colp_dev);
+    if (c->cellp_dev) cudaFree(c->cellp_dev);
     if (c->pow_tab_dev) cudaFree(c->pow_tab_dev);
     if (c->diag_dev) cudaFree(c->diag_dev);
     if (c->nonfinite_dev) cudaFree(c->nonfinite_dev);
@@ -440,7 +444,8 @@ void update_kernel_flags(lh_soil_ctx* c)
                      (c->model == LH_MODEL_COUPLED && q.theta_r != 0.0);
     const bool vg2 = !het && q.vg_n == 2.0 && q.vg_m == 0.5;      // S^(1/m) = S^2, x^m = sqrt(x): no log/exp needed
     c->kernel_flags = (c->has_ice ? LH_FLAG_ICE : 0) | (gen ? LH_FLAG_GEN : 0) | (vg2 && !c->force_general_vg ? LH_FLAG_VG2 : 0) |
-                      (het ? LH_FLAG_HET : 0) | (het && c->col_heat && has_heat(c->model) ? LH_FLAG_HETH : 0);
+                      (het ? LH_FLAG_HET : 0) | (het && c->col_heat && has_heat(c->model) ? LH_FLAG_HETH : 0) |
+                      (het && c->cellp_dev ? LH_FLAG_CELLP : 0);
     c->shape = lh_choose_shape(c->model, c->ncol_pad, c->nlayer, c->sm_count, het);   // the HET variants have a smaller warp budget
     c->budget_fresh = false;
     // The block -> column-group map may have changed: the next stage launch takes the full grid dependency.  (The flags
@@ -492,6 +497,7 @@ void fill_args(lh_soil_ctx* c, int stage, double dt, LhKernelArgs& a)
     else { a.io.out_th = c->V[0]; a.io.out_re = c->V[2]; }
     a.zc = c->zc_dev;
     a.colp = c->colp_dev;
+    a.cellp = c->cellp_dev;
     a.pow_tab = c->pow_tab_dev;
     a.budget_partials = c->fused_partials;
     a.ncol = c->ncol;
@@ -528,7 +534,8 @@ cudaError_t launch_chained(lh_soil_ctx* c, int stage, LhKernelArgs& a)
         // column from the top cell of THIS stage's input, then the stage kernel takes the two arrays as per-column fluxes.
         const int64_t top = (int64_t)(c->nlayer - 1) * c->ncol_pad;
         cudaError_t e = lh_launch_atmos_fluxes(c->dp, c->pow_tab_dev, c->atmos, a.io.in_th + top, a.io.in_ti + top, a.io.in_re + top,
-                                               c->atm_flux_dev[0], c->atm_flux_dev[1], c->ncol_pad, c->colp_dev, c->col_heat ? 1 : 0, c->stream);
+                                               c->atm_flux_dev[0], c->atm_flux_dev[1], c->ncol_pad, c->colp_dev, (c->col_heat || c->cellp_dev) ? 1 : 0,
+                                               c->cellp_dev ? c->cellp_dev + top : nullptr, (int64_t)c->nlayer * c->ncol_pad, c->stream);
         if (e != cudaSuccess) return e;
         a.top_e_kind = LH_BC_FLUX;
         a.top_h_kind = LH_BC_FLUX;
@@ -573,6 +580,7 @@ int lh_bytes_on_wire(const lh_soil_ctx* c)
     if (c->model == LH_MODEL_HEAT) per_stage_in += 1;                // prescribed ϑ_l
     if (c->kernel_flags & LH_FLAG_ICE) per_stage_in += 1;            // θ_i
     if (c->model == LH_MODEL_RICHARDS && (c->kernel_flags & LH_FLAG_GEN)) per_stage_in += 1;   // prescribed T row
+    if (c->kernel_flags & LH_FLAG_CELLP) per_stage_in += LHCELL_COUNT;   // per-cell parameter fields
     return 8 * (3 * per_stage_in + 2 * nprog + 3 * nprog);
 }
 
@@ -741,10 +749,12 @@ static int32_t rebuild_column_params(lh_soil_ctx* c)
 {
     LH_CUDA(c, cudaSetDevice(c->device));
     LH_CUDA(c, cudaStreamSynchronize(c->stream));
-    bool any = false, heat = false;
+    bool any = false, heat = false, cells = false;
     for (int k = 0; k < 12; ++k) { any |= !c->col_user[k].empty(); if (k >= 5) heat |= !c->col_user[k].empty(); }
+    for (int k = 0; k < 5; ++k) cells |= !c->cell_user[k].empty();
     c->col_heat = heat;
-    if (!any) {                                                    // back to the homogeneous kernels
+    if (!cells && c->cellp_dev) { LH_CUDA(c, cudaFree(c->cellp_dev)); c->cellp_dev = nullptr; }
+    if (!any && !cells) {                                          // back to the homogeneous kernels
         if (c->colp_dev) { LH_CUDA(c, cudaFree(c->colp_dev)); c->colp_dev = nullptr; }
         update_kernel_flags(c);
         return LH_OK;
@@ -780,6 +790,38 @@ static int32_t rebuild_column_params(lh_soil_ctx* c)
     if (!c->colp_dev) LH_CUDA(c, cudaMalloc(&c->colp_dev, h.size() * sizeof(double)));
     LH_CUDA(c, cudaMemcpyAsync(c->colp_dev, h.data(), h.size() * sizeof(double), cudaMemcpyHostToDevice, c->stream));
     LH_CUDA(c, cudaStreamSynchronize(c->stream));
+    if (cells) {
+        // per-cell fields: the same derivation cell by cell (the column's / model's values for what is not given per cell)
+        const int n = c->nlayer;
+        const size_t fs = (size_t)n * c->ncol_pad;
+        std::vector<double> hc((size_t)LHCELL_COUNT * fs);
+        for (int64_t j = 0; j < c->ncol_pad; ++j) {
+            const int64_t col = std::min<int64_t>(j, c->ncol - 1);
+            lh_soil_config cfg = c->cfg;
+            lh_soil_params& q = cfg.params;
+            auto getc = [&](int k, double& dst) { if (!c->col_user[k].empty()) dst = c->col_user[k][col]; };
+            getc(0, q.nu); getc(1, q.theta_r);
+            if (!c->col_user[2].empty()) q.vg_n = c->col_user[2][col];
+            getc(3, q.vg_alpha); getc(4, q.Ksat); getc(8, q.kappa_solid);
+            const lh_soil_params qcol = q;
+            for (int i = 0; i < n; ++i) {
+                q = qcol;
+                auto get = [&](int k, double& dst) { if (!c->cell_user[k].empty()) dst = c->cell_user[k][(size_t)col * n + i]; };
+                get(0, q.nu); get(1, q.theta_r); get(2, q.vg_n); get(3, q.vg_alpha); get(4, q.Ksat);
+                q.vg_m = 1.0 - 1.0 / q.vg_n;
+                if (!(q.nu > q.theta_r) || !(q.vg_n > 1.0) || !(q.vg_alpha > 0.0) || !std::isfinite(q.Ksat))
+                    return fail(c, LH_ERR_INVALID_ARG, "column %lld layer %d: need nu > theta_r, vg_n > 1, vg_alpha > 0, finite Ksat", (long long)col, i);
+                LhPhys d;
+                derive_phys(cfg, d);
+                double* o = hc.data() + (size_t)i * c->ncol_pad + j;
+                o[LHCELL_NU * fs] = d.nu; o[LHCELL_THETA_R * fs] = d.theta_r; o[LHCELL_INV_NU_THR * fs] = d.inv_nu_thr;
+                o[LHCELL_VG_M * fs] = d.vg_m; o[LHCELL_VG_INV_M * fs] = d.vg_inv_m; o[LHCELL_NEG_INV_ALPHA * fs] = d.neg_inv_alpha;
+                o[LHCELL_KSAT * fs] = d.Ksat; o[LHCELL_INV_NU * fs] = d.inv_nu; o[LHCELL_KAPPA_DRY * fs] = d.kappa_dry;
+            }
+        }
+        if (!c->cellp_dev) LH_CUDA(c, cudaMalloc(&c->cellp_dev, hc.size() * sizeof(double)));
+        LH_CUDA(c, cudaMemcpy(c->cellp_dev, hc.data(), hc.size() * sizeof(double), cudaMemcpyHostToDevice));
+    }
     update_kernel_flags(c);
     return LH_OK;
 }
@@ -798,6 +840,21 @@ int32_t lh_soil_set_column_params(lh_soil_ctx* c, const double* nu, const double
     if (!c) return LH_ERR_INVALID_ARG;
     const double* src[5] = {nu, theta_r, vg_n, vg_alpha, Ksat};
     keep_user_columns(c, 0, 5, src);
+    return rebuild_column_params(c);
+}
+
+int32_t lh_soil_set_cell_params(lh_soil_ctx* c, const double* nu, const double* theta_r, const double* vg_n, const double* vg_alpha,
+                                const double* Ksat, int64_t cs, int64_t ls)
+{
+    if (!c) return LH_ERR_INVALID_ARG;
+    const double* src[5] = {nu, theta_r, vg_n, vg_alpha, Ksat};
+    const int n = c->nlayer;
+    for (int k = 0; k < 5; ++k) {
+        if (!src[k]) { c->cell_user[k].clear(); continue; }
+        c->cell_user[k].resize((size_t)c->ncol * n);
+        for (int64_t col = 0; col < c->ncol; ++col)
+            for (int i = 0; i < n; ++i) c->cell_user[k][(size_t)col * n + i] = src[k][col * cs + (int64_t)i * ls];
+    }
     return rebuild_column_params(c);
 }
 
@@ -1435,7 +1492,7 @@ int32_t lh_soil_diagnostic(lh_soil_ctx* c, int32_t which, double* host, int64_t 
     LH_CUDA(c, cudaSetDevice(c->device));
     if (!c->diag_dev) LH_CUDA(c, cudaMalloc(&c->diag_dev, field_bytes(c)));      // its own scratch: tendencies stay untouched
     LH_CUDA(c, lh_launch_diagnostic(c->model, which, c->dp, c->pow_tab_dev, c->U[0], c->U[1], c->U[2], c->U[3], c->diag_dev,
-                                    (int64_t)c->ncol_pad * c->nlayer, c->colp_dev, c->ncol_pad, c->col_heat ? 1 : 0, c->stream));
+                                    (int64_t)c->ncol_pad * c->nlayer, c->colp_dev, c->ncol_pad, (c->col_heat || c->cellp_dev) ? 1 : 0, c->cellp_dev, c->stream));
     return download_field(c, c->diag_dev, host, cs, ls);
 }
 
@@ -1489,7 +1546,7 @@ int32_t lh_soil_kernel_info(lh_soil_ctx* c, char* buf, int64_t cap)
              "%s<MODEL=%d,%sFLAGS=%d:%s%s%s%s> block=(32,W=%d,G=%d) layers/thread=%d blocks=%lld smem=%zu waves=%.2f "
              "launch=%s chain=%s bytes/cell-step(on wire)=%d",
              persistent ? "lh_soil_ssprk33_persistent_kernel" : "lh_soil_stage_kernel", c->model, persistent ? "" : "STAGE=1|2|3,", f,
-             (f & LH_FLAG_ICE) ? "ICE" : "!ICE", (f & LH_FLAG_GEN) ? "+GEN" : "", (f & LH_FLAG_VG2) ? "+VG2" : "", (f & LH_FLAG_HETH) ? "+HET+HETH" : (f & LH_FLAG_HET) ? "+HET" : "",
+             (f & LH_FLAG_ICE) ? "ICE" : "!ICE", (f & LH_FLAG_GEN) ? "+GEN" : "", (f & LH_FLAG_VG2) ? "+VG2" : "", (f & LH_FLAG_CELLP) ? "+HET+CELLP" : (f & LH_FLAG_HETH) ? "+HET+HETH" : (f & LH_FLAG_HET) ? "+HET" : "",
              c->shape.W, c->shape.G, c->shape.Lc, (long long)c->shape.nblocks, c->shape.smem_bytes, c->shape.waves,
              persistent ? "persistent(1 per call)" : "per-stage(3 per step)",
              (!persistent && c->chain_dev && !(c->cfg.flags & LH_FLAG_NO_CHAIN)) ? "block-to-block" : "whole-grid",

@@ -172,7 +172,7 @@ __device__ __forceinline__ double lh_lds(uint32_t addr)
 // tables already staged at its start.  Contains ONE __syncthreads (the chunk-face exchange): every thread of
 // the block must call it.
 template <int MODEL, int STAGE, int FLAGS, class P>
-__device__ __forceinline__ void lh_stage_body_impl(const LhKernelArgs& A, const LhStageIO& io, double* smem, const P& p)
+__device__ __forceinline__ void lh_stage_body_impl(const LhKernelArgs& A, const LhStageIO& io, double* smem, P& p)
 {
     constexpr int NQv = NQ<MODEL>::value;
     constexpr bool ICE = (FLAGS & LH_FLAG_ICE) != 0;
@@ -275,7 +275,12 @@ __device__ __forceinline__ void lh_stage_body_impl(const LhKernelArgs& A, const 
         issue(d_next, i_next);
         return r;
     };
+    // CELLP: the lane's hydraulic parameters change from cell to cell: re-read them right before the closures
+    constexpr bool CELLP = (FLAGS & LH_FLAG_CELLP) != 0;
+    const int64_t cell_fs = (int64_t)A.nlayer * stride;
+    const double* cellp_next = CELLP ? A.cellp + col + (int64_t)a * stride : nullptr;      // cell the next eval() is for
     auto eval = [&](const Raw& r) {
+        if constexpr (CELLP) { lh_load_cell_params(p, cellp_next, cell_fs); cellp_next += stride; }
         const LhCell c = lh_cell_closures<MODEL, FLAGS>(p, tab, r.th, r.ti, r.x);
         Cell<MODEL> o;
         if constexpr (MODEL == 0) { o.q.K = c.K; o.q.psi = c.psi; }
@@ -382,6 +387,7 @@ __device__ __forceinline__ void lh_stage_body_impl(const LhKernelArgs& A, const 
             if constexpr (MODEL != 1) { c.K = first.K; c.psi = first.psi; }
             if constexpr (MODEL != 0) c.T = first.T;
             else if (need_T) c.T = __ldcg(pT);
+            if constexpr (CELLP) lh_load_cell_params(p, A.cellp + col, cell_fs);              // the bottom cell's parameters
             // per-column prescribed fluxes (lh_soil_set_column_fluxes) replace the scalar boundary value
             const double ve = io.flux_cols[LH_BCV_BOTTOM_ENERGY] ? __ldcg(io.flux_cols[LH_BCV_BOTTOM_ENERGY] + col) : io.bcv[LH_BCV_BOTTOM_ENERGY];
             const double vh = io.flux_cols[LH_BCV_BOTTOM_HYDROLOGY] ? __ldcg(io.flux_cols[LH_BCV_BOTTOM_HYDROLOGY] + col) : io.bcv[LH_BCV_BOTTOM_HYDROLOGY];
@@ -396,6 +402,7 @@ __device__ __forceinline__ void lh_stage_body_impl(const LhKernelArgs& A, const 
             if constexpr (MODEL != 1) { c.K = prev.K; c.psi = prev.psi; }
             if constexpr (MODEL != 0) c.T = prev.T;
             else if (need_T) c.T = __ldcg(pT + o);
+            if constexpr (CELLP) lh_load_cell_params(p, A.cellp + col + o, cell_fs);          // the top cell's parameters
             // per-column fluxes: prescribed fields, or the atmospheric fluxes lh_atmos_flux_kernel left for this stage
             const double ve = io.flux_cols[LH_BCV_TOP_ENERGY] ? __ldcg(io.flux_cols[LH_BCV_TOP_ENERGY] + col) : io.bcv[LH_BCV_TOP_ENERGY];
             const double vh = io.flux_cols[LH_BCV_TOP_HYDROLOGY] ? __ldcg(io.flux_cols[LH_BCV_TOP_HYDROLOGY] + col) : io.bcv[LH_BCV_TOP_HYDROLOGY];
@@ -445,7 +452,7 @@ template <int MODEL, int STAGE, int FLAGS>
 __device__ __forceinline__ void lh_stage_body(const LhKernelArgs& A, const LhStageIO& io, double* smem)
 {
     if constexpr ((FLAGS & LH_FLAG_HET) == 0) {
-        lh_stage_body_impl<MODEL, STAGE, FLAGS>(A, io, smem, A.p);
+        lh_stage_body_impl<MODEL, STAGE, FLAGS, const LhDevParams>(A, io, smem, A.p);
     } else {
         const int g = __shfl_sync(0xffffffffu, (int)threadIdx.z, 0);
         int64_t col = ((int64_t)blockIdx.x * blockDim.z + g) * 32 + threadIdx.x;
@@ -478,7 +485,7 @@ __device__ __forceinline__ void lh_stage_body(const LhKernelArgs& A, const LhSta
             pl.om_zero = 0;
         }
         pl.k_unfrozen_minus_dry = pl.k_unfrozen - pl.kappa_dry;
-        lh_stage_body_impl<MODEL, STAGE, FLAGS>(A, io, smem, pl);
+        lh_stage_body_impl<MODEL, STAGE, FLAGS, LhLaneParams>(A, io, smem, pl);
     }
 }
 
@@ -517,7 +524,8 @@ lh_soil_stage_kernel(const __grid_constant__ LhKernelArgs A)
     if (A.chain_flags != nullptr) {
         __threadfence();                  // every thread's stores are visible device-wide before the flag is
         __syncthreads();
-        if (tid == 0) asm volatile("st.release.gpu.global.s32 [%0], %1;" ::"l"(A.chain_flags + blockIdx.x), "r"(A.chain_set) : "memory");
+        if ((threadIdx.x | threadIdx.y | threadIdx.z) == 0)      // (not `tid`: keeping it live across the layer loop costs 4 moves per cell)
+            asm volatile("st.release.gpu.global.s32 [%0], %1;" ::"l"(A.chain_flags + blockIdx.x), "r"(A.chain_set) : "memory");
     }
 }
 
@@ -607,6 +615,11 @@ cudaError_t launch_model(int stage, int flags, const LhKernelArgs& args, const L
 {
     if (MODEL == 1) flags &= ~LH_FLAG_VG2;   // the heat-only model has no water closures
     if (flags & LH_FLAG_HET) {               // per-column parameters: always the general closures
+        if (flags & LH_FLAG_CELLP) {         // per-cell hydraulic parameters (with the per-column heat parameters where there is heat)
+            constexpr int F = LH_FLAG_CELLP | LH_FLAG_HET | LH_FLAG_GEN | (MODEL == 0 ? 0 : LH_FLAG_HETH);
+            return (flags & LH_FLAG_ICE) ? launch_variant<MODEL, F | LH_FLAG_ICE, GROUP>(stage, args, s, stream)
+                                         : launch_variant<MODEL, F, GROUP>(stage, args, s, stream);
+        }
         if (MODEL != 0 && (flags & LH_FLAG_HETH)) {      // per-column heat parameters (the Richards model has no heat closures)
             switch (flags & LH_FLAG_ICE) {
             case 0: return launch_variant<MODEL, (MODEL == 0 ? 0 : LH_FLAG_HETH) | LH_FLAG_HET | LH_FLAG_GEN, GROUP>(stage, args, s, stream);
@@ -654,6 +667,11 @@ cudaError_t launch_persistent_model(int flags, const LhKernelArgs& args, const L
 {
     if (MODEL == 1) flags &= ~LH_FLAG_VG2;
     if (flags & LH_FLAG_HET) {
+        if (flags & LH_FLAG_CELLP) {
+            constexpr int F = LH_FLAG_CELLP | LH_FLAG_HET | LH_FLAG_GEN | (MODEL == 0 ? 0 : LH_FLAG_HETH);
+            return (flags & LH_FLAG_ICE) ? launch_persistent_variant<MODEL, F | LH_FLAG_ICE>(args, s, stream)
+                                         : launch_persistent_variant<MODEL, F>(args, s, stream);
+        }
         if (MODEL != 0 && (flags & LH_FLAG_HETH)) {
             switch (flags & LH_FLAG_ICE) {
             case 0: return launch_persistent_variant<MODEL, (MODEL == 0 ? 0 : LH_FLAG_HETH) | LH_FLAG_HET | LH_FLAG_GEN>(args, s, stream);

@@ -215,6 +215,19 @@ class SoilEngine:
             return np.ascontiguousarray(a[lo:hi])
         self.ctx.set_column_params(nu=shard(ν), theta_r=shard(θr), vg_n=shard(n), vg_alpha=shard(α), Ksat=shard(Ksat))
 
+    def set_cell_params(self, *, ν=None, θr=None, n=None, α=None, Ksat=None):
+        """Layered soils: per-CELL ``ν``, ``θr``, van Genuchten ``n`` and ``α``, ``Ksat`` — arrays of shape (ncolumns, nelements)
+        over ALL columns of the domain (this engine takes its own column range)."""
+        def shard(a):
+            if a is None:
+                return None
+            a = np.asarray(a, dtype=np.float64)
+            if a.shape != (self.model.domain.ncolumns, self.model.domain.nelements):
+                raise ValueError(f"per-cell parameter must have shape ({self.model.domain.ncolumns}, {self.model.domain.nelements})")
+            lo, hi = self.column_range
+            return np.ascontiguousarray(a[lo:hi])
+        self.ctx.set_cell_params(nu=shard(ν), theta_r=shard(θr), vg_n=shard(n), vg_alpha=shard(α), Ksat=shard(Ksat))
+
     def set_column_heat_params(self, *, ρc_ds=None, κ_sat_unfrozen=None, κ_sat_frozen=None, κ_solid=None, ν_ss_om=None,
                                ν_ss_quartz=None, ν_ss_gravel=None):
         """Per-column heat parameters of ``SoilParams`` (reference parameters.jl:11-43); arrays over ALL columns of the domain."""

@@ -349,6 +349,7 @@ struct lho_soil_ctx {
     double* colp[12];     /* per-column nu, theta_r, vg_n, vg_alpha, Ksat | rho_c_ds, kappa_sat_unfrozen, kappa_sat_frozen, kappa_solid,
                              nu_ss_om, nu_ss_quartz, nu_ss_gravel (NULL: uniform); lho_soil_set_column_params / _heat_params */
     double bcv[4];
+    double* cellp[5];     /* lho_soil_set_cell_params: per-cell nu, theta_r, vg_n, vg_alpha, Ksat, [col * nlayer + layer] (NULL: per column) */
     double* flux_cols[4]; /* lho_soil_set_column_fluxes: per-column VerticalFlux values, LH_BCV_* order (NULL: scalar) */
     lh_soil_atmos atmos;  /* lho_soil_set_atmos_forcing                                 */
     int atmos_on;
@@ -488,6 +489,7 @@ int32_t lho_soil_destroy(lho_soil_ctx* c)
     for (int k = 0; k < 12; ++k) free(c->colp[k]);
     for (int k = 0; k < LH_NUM_FIELDS; ++k) free(c->aux_tab[k]);
     for (int k = 0; k < 4; ++k) free(c->flux_cols[k]);
+    for (int k = 0; k < 5; ++k) free(c->cellp[k]);
     free(c);
     return LH_OK;
 }
@@ -676,9 +678,27 @@ static lh_soil_params params_of_column(const lho_soil_ctx* c, int64_t col)
     return p;
 }
 
+/* The parameter set of one CELL: the column's, with the per-cell overrides of lho_soil_set_cell_params. */
+static lh_soil_params params_of_cell(const lho_soil_ctx* c, const lh_soil_params* pcol, int64_t col, int i)
+{
+    lh_soil_params p = *pcol;
+    const size_t o = (size_t)col * c->nlayer + i;
+    if (c->cellp[0]) p.nu = c->cellp[0][o];
+    if (c->cellp[1]) p.theta_r = c->cellp[1][o];
+    if (c->cellp[2]) { p.vg_n = c->cellp[2][o]; p.vg_m = 1.0 - 1.0 / p.vg_n; }
+    if (c->cellp[3]) p.vg_alpha = c->cellp[3][o];
+    if (c->cellp[4]) p.Ksat = c->cellp[4][o];
+    return p;
+}
+
+static int has_cell_params(const lho_soil_ctx* c)
+{
+    return c->cellp[0] || c->cellp[1] || c->cellp[2] || c->cellp[3] || c->cellp[4];
+}
+
 /* One column.  u_th/u_ti/u_re/u_T: nlayer values each (layer 0 = bottom).  work: 5*nlayer.
  * Fw/Fe: nlayer+1 face fluxes (outputs).                                                    */
-static void column_rhs(const lho_soil_ctx* c, const lh_soil_params* p, const double bcv[4], double kappa_dry,
+static void column_rhs(const lho_soil_ctx* c, int64_t col, const lh_soil_params* p, const double bcv[4], double kappa_dry,
                        const double* u_th, const double* u_ti, const double* u_re,
                        const double* u_T, double* d_th, double* d_ti, double* d_re,
                        double* Fw, double* Fe, double* work)
@@ -692,25 +712,36 @@ static void column_rhs(const lho_soil_ctx* c, const lh_soil_params* p, const dou
     double* T = work + 3 * n;
     double* eK = work + 4 * n;
 
+    const int layered = has_cell_params(c);
+    lh_soil_params p_bot = *p, p_top = *p;          /* the parameters the boundary fluxes see: those of the cell next to the face */
+    double kd_bot = kappa_dry, kd_top = kappa_dry;
     for (int i = 0; i < n; ++i) {
-        cell_closures cc = closures_at(p, model, kappa_dry, u_th[i], u_ti[i], u_re[i], u_T[i]);
+        lh_soil_params pi = *p;
+        double kd = kappa_dry;
+        if (layered) {
+            pi = params_of_cell(c, p, col, i);
+            kd = lho_k_dry(&pi);
+            if (i == 0) { p_bot = pi; kd_bot = kd; }
+            if (i == n - 1) { p_top = pi; kd_top = kd; }
+        }
+        cell_closures cc = closures_at(&pi, model, kd, u_th[i], u_ti[i], u_re[i], u_T[i]);
         K[i] = cc.K;
         h[i] = cc.psi + c->zc[i];                                   /* :167, :314 */
         kappa[i] = cc.kappa;
         T[i] = cc.T;
         /* ρe_int_l * K, :306 and :364 */
-        eK[i] = (model == LH_MODEL_COUPLED) ? lho_volumetric_internal_energy_liq(p, cc.T) * cc.K : 0.0;
+        eK[i] = (model == LH_MODEL_COUPLED) ? lho_volumetric_internal_energy_liq(&pi, cc.T) * cc.K : 0.0;
     }
 
     double fe_top, fw_top, fe_bot, fw_bot;
-    boundary_fluxes(p, model, kappa_dry, &c->cfg.top, bcv[LH_BCV_TOP_ENERGY],
+    boundary_fluxes(&p_top, model, kd_top, &c->cfg.top, bcv[LH_BCV_TOP_ENERGY],
                     bcv[LH_BCV_TOP_HYDROLOGY], 0, u_th[n - 1], u_ti[n - 1], T[n - 1], dz / 2.0,
                     &fe_top, &fw_top);
-    boundary_fluxes(p, model, kappa_dry, &c->cfg.bottom, bcv[LH_BCV_BOTTOM_ENERGY],
+    boundary_fluxes(&p_bot, model, kd_bot, &c->cfg.bottom, bcv[LH_BCV_BOTTOM_ENERGY],
                     bcv[LH_BCV_BOTTOM_HYDROLOGY], 1, u_th[0], u_ti[0], T[0], dz / 2.0,
                     &fe_bot, &fw_bot);
     /* boundary_fluxes(X, bc::PrescribedAtmosForcing, :top, ...) :516-536: from interior_values at the top cell */
-    if (c->atmos_on) lho_turbulent_surface_fluxes(p, &c->atmos, u_th[n - 1], u_ti[n - 1], T[n - 1], &fe_top, &fw_top);
+    if (c->atmos_on) lho_turbulent_surface_fluxes(&p_top, &c->atmos, u_th[n - 1], u_ti[n - 1], T[n - 1], &fe_top, &fw_top);
 
     /* Face fluxes.  Interior face j sits between cells j-1 and j (0-based), j = 1..n-1:
      *   water  :181/:358   -interpc2f(K) * gradc2f(h)
@@ -750,7 +781,7 @@ static void rhs_all(lho_soil_ctx* c, const double* th, const double* ti, const d
             const double kappa_dry = lho_k_dry(&pc);                /* :214, :295 */
             double bcv[4];
             for (int k = 0; k < 4; ++k) bcv[k] = c->flux_cols[k] ? c->flux_cols[k][col] : c->bcv[k];
-            column_rhs(c, &pc, bcv, kappa_dry, th + o, ti + o, re + o, T + o, c->tend[0] + o,
+            column_rhs(c, col, &pc, bcv, kappa_dry, th + o, ti + o, re + o, T + o, c->tend[0] + o,
                        c->tend[1] + o, c->tend[2] + o, c->Fw + (size_t)col * (n + 1),
                        c->Fe + (size_t)col * (n + 1), work);
         }
@@ -1146,10 +1177,12 @@ int32_t lho_soil_diagnostic(lho_soil_ctx* c, int32_t which, double* host, int64_
         for (int i = 0; i < n; ++i) {
             size_t o = (size_t)col * n + i;
             int m = has_heat(model) ? LH_MODEL_COUPLED : LH_MODEL_RICHARDS;
-            cell_closures cc = closures_at(&pc, m, kappa_dry, c->f[0][o], c->f[1][o],
+            const lh_soil_params pi = has_cell_params(c) ? params_of_cell(c, &pc, col, i) : pc;
+            const double kd = has_cell_params(c) ? lho_k_dry(&pi) : kappa_dry;
+            cell_closures cc = closures_at(&pi, m, kd, c->f[0][o], c->f[1][o],
                                            c->f[2][o], c->f[3][o]);
             if (which == LH_DIAG_KAPPA && !has_heat(model)) {
-                cell_closures ch = closures_at(&pc, LH_MODEL_HEAT, kappa_dry, c->f[0][o],
+                cell_closures ch = closures_at(&pi, LH_MODEL_HEAT, kd, c->f[0][o],
                                                c->f[1][o], 0.0, c->f[3][o]);
                 cc.kappa = ch.kappa;
             }
@@ -1175,6 +1208,23 @@ int32_t lho_soil_set_column_params(lho_soil_ctx* c, const double* nu, const doub
             if (!c->colp[k]) return fail(c, LH_ERR_INVALID_ARG, "out of memory");
             memcpy(c->colp[k], src[k], sizeof(double) * (size_t)c->ncol);
         }
+    }
+    return LH_OK;
+}
+
+int32_t lho_soil_set_cell_params(lho_soil_ctx* c, const double* nu, const double* theta_r, const double* vg_n,
+                                 const double* vg_alpha, const double* Ksat, int64_t cs, int64_t ls)
+{
+    if (!c) return LH_ERR_INVALID_ARG;
+    const double* src[5] = {nu, theta_r, vg_n, vg_alpha, Ksat};
+    const int n = c->nlayer;
+    for (int k = 0; k < 5; ++k) {
+        free(c->cellp[k]);
+        c->cellp[k] = NULL;
+        if (!src[k]) continue;
+        c->cellp[k] = (double*)malloc(sizeof(double) * (size_t)c->ncol * n);
+        for (int64_t col = 0; col < c->ncol; ++col)
+            for (int i = 0; i < n; ++i) c->cellp[k][(size_t)col * n + i] = src[k][col * cs + (int64_t)i * ls];
     }
     return LH_OK;
 }

@@ -36,6 +36,7 @@
 #define lh_soil_set_column_params lho_soil_set_column_params
 #define lh_soil_set_column_heat_params lho_soil_set_column_heat_params
 #define lh_soil_set_column_fluxes  lho_soil_set_column_fluxes
+#define lh_soil_set_cell_params    lho_soil_set_cell_params
 #define lh_soil_set_atmos_forcing  lho_soil_set_atmos_forcing
 #define lh_soil_atmos_fluxes       lho_soil_atmos_fluxes
 #define lh_soil_stepper_named     lho_soil_stepper_named

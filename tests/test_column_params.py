@@ -243,3 +243,114 @@ def test_cuda_heat_params_match_oracle(cuda, oracle, name, with_hydraulic):
         assert np.max(np.abs(a - r)) <= 1e-10 * np.max(np.abs(r)), (name, f)
     g.set_column_heat_params()                      # heat scalars again; hydraulic arrays (if any) stay
     assert "HETH" not in g.kernel_info() and (("HET" in g.kernel_info()) == bool(cp))
+
+
+# ---- per-CELL (layered) hydraulic parameters (lh_soil_set_cell_params) ---------------------------------------------------
+def random_cell_params(wl, seed, which=("nu", "theta_r", "vg_n", "vg_alpha", "Ksat")):
+    """Soil horizons: piecewise-constant in depth with per-column horizon depths, plus a little cell noise."""
+    rng = np.random.default_rng(seed)
+    p, nc, n = wl.params, wl.ncol, wl.nlayer
+    horizon = (np.arange(n)[None, :] >= rng.integers(1, max(2, n - 1), nc)[:, None]).astype(float)   # 0 below, 1 above the interface
+    def two(lo, hi):
+        a, b = rng.uniform(lo, hi, (nc, 1)), rng.uniform(lo, hi, (nc, 1))
+        return (a + (b - a) * horizon) * rng.uniform(0.99, 1.01, (nc, n))
+    out = {}
+    if "nu" in which:
+        out["nu"] = p.nu * two(0.9, 1.15)
+    if "theta_r" in which:
+        out["theta_r"] = two(0.0, 0.05)
+    if "vg_n" in which:
+        out["vg_n"] = two(1.4, 3.5)
+    if "vg_alpha" in which:
+        out["vg_alpha"] = p.vg_alpha * two(0.6, 1.8)
+    if "Ksat" in which:
+        out["Ksat"] = p.Ksat * 10.0 ** two(-1.0, 1.0)
+    return out
+
+
+def rescale_state_cells(wl, cp):
+    p = wl.params
+    S = (wl.fields[0] - p.theta_r) / ((p.nu - wl.fields[1]) - p.theta_r)
+    nu = cp.get("nu", np.full((wl.ncol, wl.nlayer), p.nu))
+    thr = cp.get("theta_r", np.full((wl.ncol, wl.nlayer), p.theta_r))
+    wl.fields[0] = thr + S * ((nu - wl.fields[1]) - thr)
+
+
+def test_oracle_cell_params_semantics(oracle):
+    """Constant fields == the homogeneous model bit for bit; per-cell fields constant in depth == per-column arrays."""
+    wl = w.coupled_workload(ncol=5, nlayer=14, seed=96, zlim=(-1.4, 0.0))
+    p = wl.params
+    ones = np.ones((5, 14))
+    a, b = lh.SoilContext(oracle, wl.config()), lh.SoilContext(oracle, wl.config())
+    b.set_cell_params(nu=p.nu * ones, theta_r=p.theta_r * ones, vg_n=p.vg_n * ones, vg_alpha=p.vg_alpha * ones, Ksat=p.Ksat * ones)
+    for ctx in (a, b):
+        wl.upload(ctx)
+        ctx.step(0.0, wl.dt, 3)
+    for f in (0, 2):
+        assert np.array_equal(a.get_state(f), b.get_state(f))
+    ks = p.Ksat * np.array([1.0, 2.0, 0.5, 1.0, 3.0])
+    c, d = lh.SoilContext(oracle, wl.config()), lh.SoilContext(oracle, wl.config())
+    c.set_column_params(Ksat=ks)
+    d.set_cell_params(Ksat=ks[:, None] * ones)
+    for ctx in (c, d):
+        wl.upload(ctx)
+        ctx.step(0.0, wl.dt, 3)
+    assert np.array_equal(c.get_state(0), d.get_state(0)) and not np.array_equal(a.get_state(0), c.get_state(0))
+    # a less conductive top horizon slows the infiltration front coming from the Dirichlet top
+    e = lh.SoilContext(oracle, wl.config())
+    k2 = p.Ksat * ones.copy(); k2[:, 10:] *= 0.01
+    e.set_cell_params(Ksat=k2)
+    wl.upload(e)
+    e.step(0.0, wl.dt, 3)
+    assert not np.array_equal(e.get_state(0), a.get_state(0))
+    with pytest.raises(ValueError):
+        e.set_cell_params(nu=np.ones((5, 13)))
+    e.set_cell_params()
+    wl.upload(e)
+    e.step(0.0, wl.dt, 3)
+    assert np.array_equal(e.get_state(0), a.get_state(0))
+
+
+CELL_CASES = {
+    "coupled": lambda: w.coupled_workload(ncol=200, nlayer=64, seed=97),
+    "coupled_ice": lambda: w.coupled_workload(ncol=96, nlayer=24, seed=98, ice=True, viscosity=lh.TemperatureDependentViscosity(),
+                                              impedance=lh.IceImpedance()),
+    "richards": lambda: w.richards_workload(ncol=130, nlayer=100, seed=99),
+    "richards_tall": lambda: w.richards_workload(ncol=40, nlayer=300, seed=100, zlim=(-4.5, 0.0)),
+    "heat": lambda: w.heat_workload(ncol=64, nlayer=37, seed=101),
+}
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("name", sorted(CELL_CASES))
+@pytest.mark.parametrize("launch", ["stage", "persistent"])
+def test_cuda_cell_params_match_oracle(cuda, oracle, name, launch):
+    wl = CELL_CASES[name]()
+    cp = random_cell_params(wl, seed=17)
+    rescale_state_cells(wl, cp)
+    if wl.model == abi.LH_MODEL_COUPLED:
+        wl.top = (wl.top[0], wl.top[1], wl.top[2], 0.3)
+    flags = abi.LH_FLAG_STAGE_LAUNCHES if launch == "stage" else abi.LH_FLAG_PERSISTENT
+    g, o = lh.SoilContext(cuda, wl.config(flags=flags)), lh.SoilContext(oracle, wl.config())
+    for ctx in (g, o):
+        ctx.set_cell_params(**cp)
+        if name == "coupled":                       # together with per-column heat parameters
+            ctx.set_column_heat_params(**random_heat_params(wl, 18))
+        wl.upload(ctx)
+        ctx.rhs(0.0)
+    assert "CELLP" in g.kernel_info()
+    fields = (0, 2) if wl.model == abi.LH_MODEL_COUPLED else (0,) if wl.model == abi.LH_MODEL_RICHARDS else (2,)
+    for f in fields:
+        a, r = g.get_tendency(f), o.get_tendency(f)
+        scale = w.tendency_scale(o, f)
+        assert np.max(np.abs(a - r) / scale[:, None]) <= 1e-12, (name, f)
+    for which in (abi.LH_DIAG_K, abi.LH_DIAG_PSI, abi.LH_DIAG_KAPPA):
+        a, r = g.diagnostic(which), o.diagnostic(which)
+        assert np.max(np.abs(a - r) / np.maximum(np.abs(r), 1e-300)) <= 2e-13, (name, which)
+    for ctx in (g, o):
+        ctx.step(0.0, wl.dt, 6)
+    for f in fields:
+        a, r = g.get_state(f), o.get_state(f)
+        assert np.max(np.abs(a - r)) <= 1e-10 * np.max(np.abs(r)), (name, f)
+    g.set_cell_params()
+    assert "CELLP" not in g.kernel_info()
