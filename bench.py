@@ -50,6 +50,8 @@ METRIC = "soil cell-steps/sec (fp64, coupled water+heat, SSPRK33)"
 UNIT = "cell-steps/s"
 BYTES_PER_CELL_STEP = {"coupled": 152, "richards": 88}     # BASELINE.md §3 (algorithmic, per-stage fusion; the contract figure)
 REF_MAX_STEPS_FULL = 60                                    # reference arm: the full column set while K + W <= this
+DEVICE = "cuda"                                            # tests/test_bench_multirank.py drives the N > 1 control flow on CPU (gloo)
+EXIT_HARD = True                                           # multi-rank runs end with os._exit after the last barrier
 
 
 def parse_args():
@@ -151,7 +153,7 @@ class ClockSampler:
 def pinned_like(a: np.ndarray) -> np.ndarray:
     import torch
 
-    t = torch.empty(a.shape, dtype=torch.float64, pin_memory=True)
+    t = torch.empty(a.shape, dtype=torch.float64, pin_memory=(DEVICE == "cuda"))
     out = t.numpy()
     out[...] = a
     out_base_keepalive.append(t)
@@ -264,7 +266,8 @@ def _main(args, result_stream):
         raise SystemExit("bench.py needs a CUDA device: this path has no CPU fallback")
     torch.cuda.set_device(local_rank)
     if world > 1:
-        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+        if not dist.is_initialized():
+            dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
     # Pinned host buffers are placed on the NUMA node of the allocating thread: sit next to this rank's GPU first.
     affinity0 = os.sched_getaffinity(0)
     numa_bound = lh.bind_to_gpu_numa_node(local_rank)
@@ -301,7 +304,7 @@ def _main(args, result_stream):
         ctx.sync()
 
     def rank_max(x):
-        tt = torch.tensor(x, dtype=torch.float64, device="cuda")
+        tt = torch.tensor(x, dtype=torch.float64, device=DEVICE)
         if world > 1:
             dist.all_reduce(tt, op=dist.ReduceOp.MAX)
         return tt.cpu().numpy()
@@ -428,9 +431,27 @@ def _main(args, result_stream):
             if sub is not ctx:
                 sub.close()
 
-    if rank != 0:
+    def finish_distributed():
+        """End of a multi-rank run.  ncclCommDestroy is an intra-node collective ("all ranks on the same node should call [it]
+        to avoid a hang"): in round 2 rank 0 closed its ctx (and with it the library's budget communicator) while the other
+        ranks were already tearing down torch's group or gone, and the N = 2 and N = 4 runs never returned.  Nothing is torn
+        down piecemeal any more: every rank waits at one last barrier (so nobody leaves while a peer is still inside a
+        collective), the result line is already on stdout, and the process ends with os._exit — no communicator destructor
+        runs, in any order.  A watchdog covers a barrier that does not return."""
         if world > 1:
-            dist.destroy_process_group()
+            result_stream.flush()
+            sys.stderr.flush()
+            t_kill = threading.Timer(60.0, lambda: os._exit(0))
+            t_kill.daemon = True
+            t_kill.start()
+            try:
+                dist.barrier()
+            finally:
+                if EXIT_HARD:
+                    os._exit(0)
+
+    if rank != 0:
+        finish_distributed()
         return 0
 
     cells_total = args.ncol * args.nlayer
@@ -519,8 +540,9 @@ def _main(args, result_stream):
         pass
     if e2e is not None:
         line["e2e"] = e2e
-    ctx.close()
-    del host
+    if world == 1:
+        ctx.close()                                        # free the 2.7 GB before the CPU baseline and the variant table
+        del host
     os.sched_setaffinity(0, affinity0)                     # the CPU legs use every core this process was given
     if world == 1 and not args.no_cpu_baseline:
         v, cores, sample, sec, steps = time_oracle(w, lh, graft, args.model, args.ncol, args.nlayer, 0, 1, target_seconds=12.0, ice=args.ice)
@@ -539,8 +561,7 @@ def _main(args, result_stream):
                                           "(small configs: 50 K steps per block); frac_contract / frac_on_wire as in `roofline`"}
     print(json.dumps(line), file=result_stream)
     result_stream.flush()
-    if world > 1:
-        dist.destroy_process_group()
+    finish_distributed()
     return 0
 
 
