@@ -59,7 +59,8 @@ def _worker(rank, world, port, out_dir, extra):
 
 
 @pytest.mark.timeout(600)
-@pytest.mark.parametrize("world,extra", [(2, []), (3, ["--model", "richards"]), (2, ["--no-e2e", "--general-vg"])])
+@pytest.mark.parametrize("world,extra", [(2, []), (3, ["--model", "richards"]), (2, ["--no-e2e", "--general-vg"]),
+                                         (1, ["--no-variants", "--no-cpu-baseline", "--ice"])])
 def test_bench_multi_rank_control_flow_terminates(tmp_path, world, extra):
     port = 29500 + (os.getpid() % 2000) + world
     mp.start_processes(_worker, args=(world, port, str(tmp_path), extra), nprocs=world, join=True, start_method="spawn")
