@@ -52,6 +52,13 @@ BYTES_PER_CELL_STEP = {"coupled": 152, "richards": 88}     # BASELINE.md §3 (al
 REF_MAX_STEPS_FULL = 60                                    # reference arm: the full column set while K + W <= this
 DEVICE = "cuda"                                            # tests/test_bench_multirank.py drives the N > 1 control flow on CPU (gloo)
 EXIT_HARD = True                                           # multi-rank runs end with os._exit after the last barrier
+E2E_DEADLINE_S = 240.0                                     # a multi-rank e2e leg that has not finished by then is reported as failed
+_T0 = time.perf_counter()
+
+
+def progress(msg):
+    """Phase marker on stderr (never stdout): a run that stops somewhere says where (round 2's first N > 1 run hung silently)."""
+    print(f"[bench rank {os.environ.get('RANK', '0')} +{time.perf_counter() - _T0:7.2f}s] {msg}", file=sys.stderr, flush=True)
 
 
 def parse_args():
@@ -213,6 +220,9 @@ def main():
     try:
         return _main(args, real_stdout)
     finally:
+        import faulthandler
+
+        faulthandler.cancel_dump_traceback_later()
         real_stdout.flush()
 
 
@@ -221,10 +231,16 @@ def _main(args, result_stream):
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
 
+    import faulthandler
+
     import __graft_entry__ as graft
 
     lh = graft.load_package()
     import workloads as w
+
+    # A run that stops somewhere must say where and must end: Python stacks of every thread go to stderr if the whole run
+    # is still going after 25 minutes, and the process exits (the driver then sees a failed run with a reason, not a hang).
+    faulthandler.dump_traceback_later(1500.0, exit=True, file=sys.stderr)
 
     config = {
         "workload": f"{args.ncol} columns x {args.nlayer} layers, {args.model} "
@@ -272,6 +288,7 @@ def _main(args, result_stream):
     affinity0 = os.sched_getaffinity(0)
     numa_bound = lh.bind_to_gpu_numa_node(local_rank)
 
+    progress(f"world {world}: process group up, numa_bound={bool(numa_bound)}")
     lo, hi = lh.shard_range(args.ncol, world, rank)
     wl = make_workload(w, args.model, args.ncol, args.nlayer, (lo, hi), ice=args.ice)
     wl.device = local_rank
@@ -296,6 +313,7 @@ def _main(args, result_stream):
         eng = _Eng(); eng.lib = lib; eng.ctx = ctx
         lh.init_budget_comm(eng, dist)
     kernel_info = ctx.kernel_info()
+    progress(f"columns [{lo}, {hi}) uploaded; {kernel_info}")
 
     def barrier():
         torch.cuda.synchronize()
@@ -314,6 +332,7 @@ def _main(args, result_stream):
     ctx.step(t, wl.dt, args.warmup)
     ctx.sync()
     t += args.warmup * wl.dt
+    progress(f"{args.warmup} warm-up steps done")
 
     # ---- timed region: blocks of exactly K steps, state resident in HBM, CUDA events on the ctx stream ----
     sampler = ClockSampler(local_rank)
@@ -343,6 +362,7 @@ def _main(args, result_stream):
     clocks = sampler.stop(w0, w1) if rank == 0 else None
     block_ms = rank_max(block_ms)                          # per block: the slowest rank
     ms_med = float(np.median(block_ms))
+    progress(f"timed region done: {len(block_ms)} blocks of {args.steps} steps, median {ms_med / args.steps:.4f} ms/step")
     if rank == 0 and (clocks is None or not clocks.get("samples")) and (w1 - w0) < 0.25 and args.min_seconds < 0.25:
         # profiling runs (--min-seconds 0 under ncu): a timed region shorter than a few sampling periods cannot be vetted
         clocks = dict(clocks or {}, note=f"timed region {w1 - w0:.3f} s is shorter than the 50 ms sampling period allows; not vetted")
@@ -357,10 +377,118 @@ def _main(args, result_stream):
     budget_ms = 1e3 * (time.perf_counter() - tb0)
     if not np.all(np.isfinite(budgets)):
         raise SystemExit(f"non-finite budgets after the timed steps: {budgets}")
+    progress(f"budgets {'all-reduced over ' + str(world) + ' ranks' if world > 1 else 'read'} in {budget_ms:.3f} ms")
+
+    def finish_distributed():
+        """End of a multi-rank run.  ncclCommDestroy is an intra-node collective ("all ranks on the same node should call [it]
+        to avoid a hang"): in round 2 rank 0 closed its ctx (and with it the library's budget communicator) while the other
+        ranks were already tearing down torch's group or gone, and the N = 2 and N = 4 runs never returned.  Nothing is torn
+        down piecemeal any more: every rank waits at one last barrier (so nobody leaves while a peer is still inside a
+        collective), the result line is already on stdout, and the process ends with os._exit — no communicator destructor
+        runs, in any order.  A watchdog covers a barrier that does not return."""
+        if world > 1:
+            result_stream.flush()
+            sys.stderr.flush()
+            t_kill = threading.Timer(60.0, lambda: os._exit(0))
+            t_kill.daemon = True
+            t_kill.start()
+            try:
+                dist.barrier()
+            finally:
+                if EXIT_HARD:
+                    os._exit(0)
+
+    def make_line(e2e):
+        cells_total = args.ncol * args.nlayer
+        value = cells_total * args.steps / (ms_med * 1e-3)
+        peak, peak_src = load_peaks()
+        cells_rank = (hi - lo) * args.nlayer
+        persistent = int(launches) != 3 * args.steps
+        wire_bpcs = None
+        try:
+            wire_bpcs = int(kernel_info.rsplit("=", 1)[1])
+        except Exception:
+            pass
+        if not persistent:
+            # dominant kernel = lh_soil_stage_kernel<model, stage 1|2|3>: every launch in the timed region is one of its three
+            # stage instantiations; per-launch figures are the averages over the 3K launches.
+            bpcs = BYTES_PER_CELL_STEP[args.model]
+            nl = 3 * args.steps
+            kernel = "lh_soil_stage_kernel (fused closures + stencil + SSPRK33 stage)"
+            note = ("per-launch average over the 3 stage launches of each step (contract: 40/56/56 B per cell coupled, 24/32/32 Richards). "
+                    "`frac` credits the SURVEY §8d contract bytes; `frac_on_wire` the bytes the launched variant really moves (the !ICE "
+                    "variants never read theta_i). The kernel is bounded by issue slots, not HBM: an fp64 instruction holds the issue "
+                    "port for two cycles on B200 (DESIGN.md §4.1), see `issue_model`")
+        else:
+            # one persistent launch for all K steps: a block keeps its columns, the stage registers stay in L2, and the
+            # compulsory traffic of a launch is one read of the state and one write of the prognostic fields per STEP
+            bpcs = {"coupled": 40, "richards": 24}[args.model]
+            wire_bpcs = bpcs - (0 if args.ice or args.model != "coupled" else 8)
+            nl = max(int(launches), 1)
+            kernel = "lh_soil_ssprk33_persistent_kernel (all stages of all steps in one launch, columns L2-resident)"
+            note = ("persistent launch (grid of few waves): algorithmic bytes are 40 B (coupled) / 24 B (Richards) per cell-STEP, "
+                    "the path is issue-bound, not HBM-bound (DESIGN.md §4.1)")
+        launch_ms = ms_med / nl
+        achieved = cells_rank * bpcs * args.steps / nl / (launch_ms * 1e-3) / 1e9
+        on_wire = cells_rank * (wire_bpcs or bpcs) * args.steps / nl / (launch_ms * 1e-3) / 1e9
+        traffic, traffic_src = None, None
+        tpath = os.path.join(ROOT, "profiles", "dram_traffic.json")
+        if os.path.exists(tpath) and not persistent and not args.het:
+            try:
+                tkey = args.model + ("_general_vg" if (args.general_vg and args.model == "coupled") else "") + ("_ice" if args.ice else "")
+                traffic = json.load(open(tpath)).get(f"{tkey}_{args.ncol}x{args.nlayer}_bytes_per_launch")
+                if traffic is not None:
+                    traffic = traffic * cells_rank / (args.ncol * args.nlayer)     # measured at N = 1; per launch of this rank's shard
+                    traffic_src = "profiles/dram_traffic.json (CACHED ncu --set full capture of this command, not measured in this run)"
+            except Exception:
+                traffic = None
+        config["launch"] = "persistent (1 launch per call)" if persistent else "3 launches per step, chained block to block"
+        if args.no_chain:
+            config["launch"] = "3 launches per step, whole-grid dependency (LH_FLAG_NO_CHAIN)"
+        line = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": ms_med / args.steps, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
+            "dtype": "f64", "data": "synthetic", "config": config, "clocks": clocks,
+            "gpu_launches": int(launches) * len(block_ms),
+            "sustained": {
+                "what": f"{len(block_ms)} back-to-back timed blocks of exactly {args.steps} steps; value = median block",
+                "blocks": len(block_ms), "device_seconds": float(np.sum(block_ms)) * 1e-3,
+                "ms_per_step_first_block": float(block_ms[0]) / args.steps, "ms_per_step_min": float(np.min(block_ms)) / args.steps,
+                "ms_per_step_median": ms_med / args.steps, "ms_per_step_max": float(np.max(block_ms)) / args.steps,
+                "value_first_block": cells_total * args.steps / (float(block_ms[0]) * 1e-3),
+            },
+            "roofline": {
+                "bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                "achieved_on_wire": on_wire, "frac_on_wire": on_wire / peak,
+                "traffic": traffic, "traffic_source": traffic_src, "peak_source": peak_src,
+                "kernel": kernel, "variant": kernel_info,
+                "algorithmic_bytes_per_cell_step": bpcs, "on_wire_bytes_per_cell_step": wire_bpcs, "launch_ms": launch_ms, "note": note,
+            },
+            "budgets": {"water": float(budgets[0]), "energy": float(budgets[1]), "allreduce_ms": budget_ms},
+        }
+        # issue-slot model of the launched variant (static SASS counts of the layer loop, profiles/r02_sass_loop_mix.json)
+        try:
+            mix = json.load(open(os.path.join(ROOT, "profiles", "r02_sass_loop_mix.json")))
+            key = kernel_info.split("FLAGS=")[1].split(":")[0]
+            mkey = f"{ {'coupled': 2, 'richards': 0}[args.model] }_{key}"
+            if mkey in mix and clocks and clocks.get("sm_mhz"):
+                m = mix[mkey]
+                cyc = m["cycles_per_warp_cell_stage_mean"]
+                sm_count = torch.cuda.get_device_properties(local_rank).multi_processor_count
+                ceiling = sm_count * 4 * clocks["sm_mhz"] * 1e6 * 32 / cyc / 3.0 * world
+                line["roofline"]["issue_model"] = {
+                    "cycles_per_warp_cell_stage": cyc, "fp64_per_cell_stage": m["fp64_mean"], "other_per_cell_stage": m["other_mean"],
+                    "ceiling_cell_steps_per_s_at_measured_clock": ceiling, "frac_of_issue_ceiling": value / ceiling,
+                    "what": "2 x fp64 + other warp-instructions per cell and stage in the layer loop (cuobjdump -sass, "
+                            "profiles/r02_sass_loop_mix.json) x 4 schedulers x SMs x median SM clock"}
+        except Exception:
+            pass
+        if e2e is not None:
+            line["e2e"] = e2e
+        return line
 
     # ---- e2e through the C ABI from pinned host buffers ----
-    e2e = None
-    if not args.no_e2e:
+    def run_e2e():
         K = args.steps
         table_K = bc_table_for(wl, 0.0, wl.dt, K)
         out = {fid: pinned_like(np.empty_like(wl.fields[fid])) for fid in ((0, 2) if args.model == "coupled" else (0,))}
@@ -431,115 +559,44 @@ def _main(args, result_stream):
             if sub is not ctx:
                 sub.close()
 
-    def finish_distributed():
-        """End of a multi-rank run.  ncclCommDestroy is an intra-node collective ("all ranks on the same node should call [it]
-        to avoid a hang"): in round 2 rank 0 closed its ctx (and with it the library's budget communicator) while the other
-        ranks were already tearing down torch's group or gone, and the N = 2 and N = 4 runs never returned.  Nothing is torn
-        down piecemeal any more: every rank waits at one last barrier (so nobody leaves while a peer is still inside a
-        collective), the result line is already on stdout, and the process ends with os._exit — no communicator destructor
-        runs, in any order.  A watchdog covers a barrier that does not return."""
-        if world > 1:
-            result_stream.flush()
-            sys.stderr.flush()
-            t_kill = threading.Timer(60.0, lambda: os._exit(0))
-            t_kill.daemon = True
-            t_kill.start()
-            try:
-                dist.barrier()
-            finally:
-                if EXIT_HARD:
-                    os._exit(0)
+        return e2e
+
+    # The line is complete without the e2e leg; that leg runs under a deadline so that a transfer or a shard thread that never
+    # returns (on any rank) costs the run its e2e number, not its result: at the deadline every rank dumps its Python stacks,
+    # rank 0 prints the line with the failure recorded in `e2e`, and the processes end.
+    emit_lock = threading.Lock()
+    emitted = []
+
+    def emit(line):
+        with emit_lock:
+            if not emitted:
+                emitted.append(True)
+                print(json.dumps(line), file=result_stream)
+                result_stream.flush()
+
+    def e2e_deadline():
+        progress(f"e2e leg still running after {E2E_DEADLINE_S:.0f} s: giving up on it")
+        faulthandler.dump_traceback(file=sys.stderr, all_threads=True)
+        if rank == 0:
+            emit(make_line({"value": None, "unit": UNIT, "h2d_bytes_per_step": None, "d2h_bytes_per_step": None,
+                            "error": f"the e2e leg did not finish within {E2E_DEADLINE_S:.0f} s on some rank (stacks on stderr)"}))
+        sys.stderr.flush()
+        os._exit(0)                                        # the failure is on record in the line; a non-zero rank exit would make torchrun tear rank 0 down mid-print
+
+    e2e = None
+    if not args.no_e2e:
+        watchdog = threading.Timer(E2E_DEADLINE_S, e2e_deadline)
+        watchdog.daemon = True
+        watchdog.start()
+        e2e = run_e2e()
+        watchdog.cancel()
+        progress(f"e2e leg done: {e2e['seconds']:.4f} s over {e2e['shards_per_gpu']} shard(s) per GPU")
 
     if rank != 0:
         finish_distributed()
         return 0
 
-    cells_total = args.ncol * args.nlayer
-    value = cells_total * args.steps / (ms_med * 1e-3)
-    peak, peak_src = load_peaks()
-    cells_rank = (hi - lo) * args.nlayer
-    persistent = int(launches) != 3 * args.steps
-    wire_bpcs = None
-    try:
-        wire_bpcs = int(kernel_info.rsplit("=", 1)[1])
-    except Exception:
-        pass
-    if not persistent:
-        # dominant kernel = lh_soil_stage_kernel<model, stage 1|2|3>: every launch in the timed region is one of its three
-        # stage instantiations; per-launch figures are the averages over the 3K launches.
-        bpcs = BYTES_PER_CELL_STEP[args.model]
-        nl = 3 * args.steps
-        kernel = "lh_soil_stage_kernel (fused closures + stencil + SSPRK33 stage)"
-        note = ("per-launch average over the 3 stage launches of each step (contract: 40/56/56 B per cell coupled, 24/32/32 Richards). "
-                "`frac` credits the SURVEY §8d contract bytes; `frac_on_wire` the bytes the launched variant really moves (the !ICE "
-                "variants never read theta_i). The kernel is bounded by issue slots, not HBM: an fp64 instruction holds the issue "
-                "port for two cycles on B200 (DESIGN.md §4.1), see `issue_model`")
-    else:
-        # one persistent launch for all K steps: a block keeps its columns, the stage registers stay in L2, and the
-        # compulsory traffic of a launch is one read of the state and one write of the prognostic fields per STEP
-        bpcs = {"coupled": 40, "richards": 24}[args.model]
-        wire_bpcs = bpcs - (0 if args.ice or args.model != "coupled" else 8)
-        nl = max(int(launches), 1)
-        kernel = "lh_soil_ssprk33_persistent_kernel (all stages of all steps in one launch, columns L2-resident)"
-        note = ("persistent launch (grid of few waves): algorithmic bytes are 40 B (coupled) / 24 B (Richards) per cell-STEP, "
-                "the path is issue-bound, not HBM-bound (DESIGN.md §4.1)")
-    launch_ms = ms_med / nl
-    achieved = cells_rank * bpcs * args.steps / nl / (launch_ms * 1e-3) / 1e9
-    on_wire = cells_rank * (wire_bpcs or bpcs) * args.steps / nl / (launch_ms * 1e-3) / 1e9
-    traffic, traffic_src = None, None
-    tpath = os.path.join(ROOT, "profiles", "dram_traffic.json")
-    if os.path.exists(tpath) and not persistent and not args.het:
-        try:
-            tkey = args.model + ("_general_vg" if (args.general_vg and args.model == "coupled") else "") + ("_ice" if args.ice else "")
-            traffic = json.load(open(tpath)).get(f"{tkey}_{args.ncol}x{args.nlayer}_bytes_per_launch")
-            if traffic is not None:
-                traffic = traffic * cells_rank / (args.ncol * args.nlayer)     # measured at N = 1; per launch of this rank's shard
-                traffic_src = "profiles/dram_traffic.json (CACHED ncu --set full capture of this command, not measured in this run)"
-        except Exception:
-            traffic = None
-    config["launch"] = "persistent (1 launch per call)" if persistent else "3 launches per step, chained block to block"
-    if args.no_chain:
-        config["launch"] = "3 launches per step, whole-grid dependency (LH_FLAG_NO_CHAIN)"
-    line = {
-        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
-        "ms_per_step": ms_med / args.steps, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
-        "dtype": "f64", "data": "synthetic", "config": config, "clocks": clocks,
-        "gpu_launches": int(launches) * len(block_ms),
-        "sustained": {
-            "what": f"{len(block_ms)} back-to-back timed blocks of exactly {args.steps} steps; value = median block",
-            "blocks": len(block_ms), "device_seconds": float(np.sum(block_ms)) * 1e-3,
-            "ms_per_step_first_block": float(block_ms[0]) / args.steps, "ms_per_step_min": float(np.min(block_ms)) / args.steps,
-            "ms_per_step_median": ms_med / args.steps, "ms_per_step_max": float(np.max(block_ms)) / args.steps,
-            "value_first_block": cells_total * args.steps / (float(block_ms[0]) * 1e-3),
-        },
-        "roofline": {
-            "bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-            "achieved_on_wire": on_wire, "frac_on_wire": on_wire / peak,
-            "traffic": traffic, "traffic_source": traffic_src, "peak_source": peak_src,
-            "kernel": kernel, "variant": kernel_info,
-            "algorithmic_bytes_per_cell_step": bpcs, "on_wire_bytes_per_cell_step": wire_bpcs, "launch_ms": launch_ms, "note": note,
-        },
-        "budgets": {"water": float(budgets[0]), "energy": float(budgets[1]), "allreduce_ms": budget_ms},
-    }
-    # issue-slot model of the launched variant (static SASS counts of the layer loop, profiles/r02_sass_loop_mix.json)
-    try:
-        mix = json.load(open(os.path.join(ROOT, "profiles", "r02_sass_loop_mix.json")))
-        key = kernel_info.split("FLAGS=")[1].split(":")[0]
-        mkey = f"{ {'coupled': 2, 'richards': 0}[args.model] }_{key}"
-        if mkey in mix and clocks and clocks.get("sm_mhz"):
-            m = mix[mkey]
-            cyc = m["cycles_per_warp_cell_stage_mean"]
-            sm_count = torch.cuda.get_device_properties(local_rank).multi_processor_count
-            ceiling = sm_count * 4 * clocks["sm_mhz"] * 1e6 * 32 / cyc / 3.0 * world
-            line["roofline"]["issue_model"] = {
-                "cycles_per_warp_cell_stage": cyc, "fp64_per_cell_stage": m["fp64_mean"], "other_per_cell_stage": m["other_mean"],
-                "ceiling_cell_steps_per_s_at_measured_clock": ceiling, "frac_of_issue_ceiling": value / ceiling,
-                "what": "2 x fp64 + other warp-instructions per cell and stage in the layer loop (cuobjdump -sass, "
-                        "profiles/r02_sass_loop_mix.json) x 4 schedulers x SMs x median SM clock"}
-    except Exception:
-        pass
-    if e2e is not None:
-        line["e2e"] = e2e
+    line = make_line(e2e)
     if world == 1:
         ctx.close()                                        # free the 2.7 GB before the CPU baseline and the variant table
         del host
@@ -559,8 +616,8 @@ def _main(args, result_stream):
         line["extra"] = {"variants": rows,
                          "variants_note": "same process, same GPU, CUDA events on the ctx stream, median of 5 blocks of K steps each "
                                           "(small configs: 50 K steps per block); frac_contract / frac_on_wire as in `roofline`"}
-    print(json.dumps(line), file=result_stream)
-    result_stream.flush()
+    emit(line)
+    progress("result line written")
     finish_distributed()
     return 0
 

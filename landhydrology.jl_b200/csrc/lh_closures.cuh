@@ -21,10 +21,21 @@
 // tables of lh_math.cuh, staged in shared memory by every kernel (lh_stage_tables).
 #pragma once
 
-#include <cuda_runtime.h>
 #include <stdint.h>
 
 #include "lh_math.cuh"
+
+// The same source compiles on the host (LH_MATH_HOST, as lh_math.cuh): tests/support/device_closures_host.cpp evaluates the
+// closures of every kernel variant on the CPU against the oracle.  Test infrastructure only; on the device LH_DEVFN is exactly
+// `__device__` + `__forceinline__` and `lh_ldg` is `__ldg`.
+#ifdef LH_MATH_HOST
+#define LH_DEVFN static inline
+#define lh_ldg(p) (*(p))
+#else
+#include <cuda_runtime.h>
+#define LH_DEVFN __device__ __forceinline__
+#define lh_ldg(p) __ldg(p)
+#endif
 
 #define LH_EPS 2.220446049250313e-16
 
@@ -96,17 +107,17 @@ enum { LHCELL_NU, LHCELL_THETA_R, LHCELL_INV_NU_THR, LHCELL_VG_M, LHCELL_VG_INV_
 
 // Overwrites the cell-dependent members of a lane's parameter view from the per-cell fields: cp points at this lane's
 // element of field 0 for the cell, fs is the field stride (nlayer * ncol_pad).
-__device__ __forceinline__ void lh_load_cell_params(LhLaneParams& p, const double* __restrict__ cp, int64_t fs)
+LH_DEVFN void lh_load_cell_params(LhLaneParams& p, const double* __restrict__ cp, int64_t fs)
 {
-    p.nu = __ldg(cp + LHCELL_NU * fs);
-    p.theta_r = __ldg(cp + LHCELL_THETA_R * fs);
-    p.inv_nu_thr = __ldg(cp + LHCELL_INV_NU_THR * fs);
-    p.vg_m = __ldg(cp + LHCELL_VG_M * fs);
-    p.vg_inv_m = __ldg(cp + LHCELL_VG_INV_M * fs);
-    p.neg_inv_alpha = __ldg(cp + LHCELL_NEG_INV_ALPHA * fs);
-    p.Ksat = __ldg(cp + LHCELL_KSAT * fs);
-    p.inv_nu = __ldg(cp + LHCELL_INV_NU * fs);
-    p.kappa_dry = __ldg(cp + LHCELL_KAPPA_DRY * fs);
+    p.nu = lh_ldg(cp + LHCELL_NU * fs);
+    p.theta_r = lh_ldg(cp + LHCELL_THETA_R * fs);
+    p.inv_nu_thr = lh_ldg(cp + LHCELL_INV_NU_THR * fs);
+    p.vg_m = lh_ldg(cp + LHCELL_VG_M * fs);
+    p.vg_inv_m = lh_ldg(cp + LHCELL_VG_INV_M * fs);
+    p.neg_inv_alpha = lh_ldg(cp + LHCELL_NEG_INV_ALPHA * fs);
+    p.Ksat = lh_ldg(cp + LHCELL_KSAT * fs);
+    p.inv_nu = lh_ldg(cp + LHCELL_INV_NU * fs);
+    p.kappa_dry = lh_ldg(cp + LHCELL_KAPPA_DRY * fs);
     p.theta_r_eps = p.theta_r + LH_EPS;
     p.nu_thr = p.nu - p.theta_r;
     p.vg_inv_n = 1.0 - p.vg_m;                       // 1/n = 1 - m (Mualem), within 1 ulp of the quotient
@@ -116,7 +127,7 @@ __device__ __forceinline__ void lh_load_cell_params(LhLaneParams& p, const doubl
 // Copies the exp2 / log2 tables from the parameter block, and the fixed-exponent power tables from `pow_tab`
 // (LHPW_COUNT * LH_POW_DOUBLES doubles in global memory, written once by lh_soil_create), to shared memory
 // (LH_TAB_ALL doubles, 16-byte aligned destination); the caller must __syncthreads().
-__device__ __forceinline__ void lh_stage_tables(const LhDevParams& p, const double* __restrict__ pow_tab, double* tab_smem,
+LH_DEVFN void lh_stage_tables(const LhDevParams& p, const double* __restrict__ pow_tab, double* tab_smem,
                                                 int linear_tid, int nthreads)
 {
     for (int k = linear_tid; k < LH_TAB_DOUBLES; k += nthreads) tab_smem[k] = p.mc[LHC_TAB0 + k];
@@ -168,7 +179,7 @@ struct LhCell {
 // yield NaN/garbage only where the select discards them).
 // ---------------------------------------------------------------------------------------------
 template <bool ICE, bool GEN, bool VG2, bool NEED_LOG, bool THR0 = false, class P = LhDevParams>
-__device__ __forceinline__ void lh_water_closures(const P& p, const double* __restrict__ tab,
+LH_DEVFN void lh_water_closures(const P& p, const double* __restrict__ tab,
                                                   double th, double ti, double T,
                                                   double& K_out, double& psi_out, double& logS_K, LhPowArg& argS_K)
 {
@@ -296,7 +307,7 @@ __device__ __forceinline__ void lh_water_closures(const P& p, const double* __re
 //   Kersten base E3 - c^3 is ~0 and K_e vanishes either way.)
 // ---------------------------------------------------------------------------------------------
 template <bool ICE, bool GEN, bool REUSE, class P = LhDevParams>
-__device__ __forceinline__ double lh_thermal_conductivity(const P& p, const double* __restrict__ tab,
+LH_DEVFN double lh_thermal_conductivity(const P& p, const double* __restrict__ tab,
                                                           double tl, double ti, bool unsat, double logS, const LhPowArg& argS)
 {
     const double* __restrict__ mc = p.mc;
@@ -356,7 +367,7 @@ __device__ __forceinline__ double lh_thermal_conductivity(const P& p, const doub
 
 // Temperature from ρe_int (SoilHeatParameterizations.jl:42-79): returns T - T_0 (the quotient); T = T_0 + it.
 template <bool ICE, class P = LhDevParams>
-__device__ __forceinline__ double lh_temperature_minus_T0(const P& p, double tl, double ti, double re)
+LH_DEVFN double lh_temperature_minus_T0(const P& p, double tl, double ti, double re)
 {
     if (ICE) {
         const double rho_c_s = p.rho_c_ds + tl * p.rhocp_l + ti * p.rhocp_i; // :65-79
@@ -369,7 +380,7 @@ __device__ __forceinline__ double lh_temperature_minus_T0(const P& p, double tl,
 // All closures of one cell for model MODEL (0 Richards, 1 heat, 2 coupled).
 //   Richards: T_or_re = prescribed T.   heat/coupled: T_or_re = ρe_int.
 template <int MODEL, int FLAGS, class P = LhDevParams>
-__device__ __forceinline__ LhCell lh_cell_closures(const P& p, const double* __restrict__ tab,
+LH_DEVFN LhCell lh_cell_closures(const P& p, const double* __restrict__ tab,
                                                    double th, double ti, double T_or_re)
 {
     constexpr bool ICE = (FLAGS & LH_FLAG_ICE) != 0, GEN = (FLAGS & LH_FLAG_GEN) != 0, VG2 = (FLAGS & LH_FLAG_VG2) != 0;
@@ -397,7 +408,7 @@ __device__ __forceinline__ LhCell lh_cell_closures(const P& p, const double* __r
 
 // κ at a boundary "face state" (boundary_conditions.jl:429-436).
 template <int FLAGS, class P = LhDevParams>
-__device__ __forceinline__ double lh_face_kappa(const P& p, const double* __restrict__ tab, double th, double ti)
+LH_DEVFN double lh_face_kappa(const P& p, const double* __restrict__ tab, double th, double ti)
 {
     constexpr bool ICE = (FLAGS & LH_FLAG_ICE) != 0, GEN = (FLAGS & LH_FLAG_GEN) != 0;
     const double nu_eff = ICE ? p.nu - ti : p.nu;

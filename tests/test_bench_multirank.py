@@ -48,6 +48,13 @@ def _worker(rank, world, port, out_dir, extra):
             return {"sm_mhz": 1500.0, "sm_min_mhz": 1500.0, "sm_max_mhz": 1965.0, "power_w_median": 0.0, "reasons": [], "samples": 3}
 
     bench.ClockSampler = FakeSampler
+    if "--hang-e2e-on-rank-1" in extra:                     # the e2e leg of one rank never returns: the deadline path must still print
+        extra = [x for x in extra if x != "--hang-e2e-on-rank-1"]
+        bench.E2E_DEADLINE_S = 3.0
+        if rank == 1:
+            import time
+
+            lh.SoilContext.run = lambda *_a, **_k: time.sleep(3600)
     dist.init_process_group("gloo", rank=rank, world_size=world)
     argv = ["bench.py", "--gpus", str(world), "--steps", "2", "--warmup", "1", "--ncol", "768", "--nlayer", "12", "--min-seconds", "0.01"] + extra
     sys.argv = argv
@@ -72,3 +79,18 @@ def test_bench_multi_rank_control_flow_terminates(tmp_path, world, extra):
     assert "cpu_baseline" not in d and "extra" not in d      # N = 1 only
     for r in range(1, world):
         assert open(tmp_path / f"out_{r}.txt").read().strip() == ""    # the other ranks print nothing
+
+
+@pytest.mark.timeout(300)
+def test_bench_e2e_deadline_still_prints_the_line(tmp_path):
+    """One rank's e2e leg never returns (a stuck transfer, a shard thread that deadlocks): every rank gives up at the deadline,
+    rank 0 prints the complete line with the failure recorded under `e2e`, and all processes exit 0 (a non-zero rank would make
+    torchrun kill rank 0)."""
+    world = 2
+    port = 29500 + (os.getpid() % 2000) + 7
+    mp.start_processes(_worker, args=(world, port, str(tmp_path), ["--hang-e2e-on-rank-1"]), nprocs=world, join=True, start_method="spawn")
+    lines = [l for l in open(tmp_path / "out_0.txt").read().splitlines() if l.strip()]
+    assert len(lines) == 1
+    d = json.loads(lines[0])
+    assert d["n_gpus"] == 2 and d["value"] > 0 and d["sustained"]["blocks"] >= 3 and "roofline" in d
+    assert d["e2e"]["value"] is None and "did not finish" in d["e2e"]["error"]
