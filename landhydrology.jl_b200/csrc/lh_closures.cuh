@@ -25,8 +25,8 @@
 
 #include "lh_math.cuh"
 
-// The same source compiles on the host (LH_MATH_HOST, as lh_math.cuh): tests/support/device_closures_host.cpp evaluates the
-// closures of every kernel variant on the CPU against the oracle.  Test infrastructure only; on the device LH_DEVFN is exactly
+// The same source compiles on the host (LH_MATH_HOST, as lh_math.cuh): tests/support/hostemu builds the whole library for the
+// CPU-only test run (every kernel variant against the oracle).  Test infrastructure only; on the device LH_DEVFN is exactly
 // `__device__` + `__forceinline__` and `lh_ldg` is `__ldg`.
 #ifdef LH_MATH_HOST
 #define LH_DEVFN static inline

@@ -1,6 +1,6 @@
 // lh_derive.h — host side: the constants the closures use, derived from lh_soil_config (all fp64, computed once in
 // lh_soil_create; per column / per cell in rebuild_column_params).  Shared by csrc/lh_soil_api.cu and the host build of the
-// closures that tests/support/device_closures_host.cpp checks against the oracle on the CPU.
+// product sources that tests/support/hostemu compiles for the CPU-only test run.
 #pragma once
 
 #include <math.h>

@@ -22,6 +22,7 @@
 #include "lh_kernels.cuh"
 
 #include "lh_atmos.cuh"
+#include "lh_ptx.cuh"
 #include "lh_soil.h"
 
 #include <stdlib.h>
@@ -195,11 +196,11 @@ cudaError_t lh_launch_diagnostic(int model, int which, const LhDevParams& p, con
     const int block = 256;
     const unsigned grid = (unsigned)((n + block - 1) / block);
     if (model == LH_MODEL_RICHARDS) {
-        if (colp) lh_diag_kernel<0, true><<<grid, block, 0, stream>>>(p, pow_tab, which, th, ti, re, T, out, n, colp, ncol_pad, heat, cellp);
-        else lh_diag_kernel<0, false><<<grid, block, 0, stream>>>(p, pow_tab, which, th, ti, re, T, out, n, colp, ncol_pad, heat, cellp);
+        if (colp) LH_LAUNCH((lh_diag_kernel<0, true>), grid, block, 0, stream, p, pow_tab, which, th, ti, re, T, out, n, colp, ncol_pad, heat, cellp);
+        else LH_LAUNCH((lh_diag_kernel<0, false>), grid, block, 0, stream, p, pow_tab, which, th, ti, re, T, out, n, colp, ncol_pad, heat, cellp);
     } else {
-        if (colp) lh_diag_kernel<2, true><<<grid, block, 0, stream>>>(p, pow_tab, which, th, ti, re, T, out, n, colp, ncol_pad, heat, cellp);
-        else lh_diag_kernel<2, false><<<grid, block, 0, stream>>>(p, pow_tab, which, th, ti, re, T, out, n, colp, ncol_pad, heat, cellp);
+        if (colp) LH_LAUNCH((lh_diag_kernel<2, true>), grid, block, 0, stream, p, pow_tab, which, th, ti, re, T, out, n, colp, ncol_pad, heat, cellp);
+        else LH_LAUNCH((lh_diag_kernel<2, false>), grid, block, 0, stream, p, pow_tab, which, th, ti, re, T, out, n, colp, ncol_pad, heat, cellp);
     }
     return cudaGetLastError();
 }
@@ -273,15 +274,15 @@ cudaError_t lh_launch_atmos_fluxes(const LhDevParams& p, const double* pow_tab, 
 {
     const int block = 128;
     const unsigned grid = (unsigned)((ncol_pad + block - 1) / block);
-    if (colp) lh_atmos_flux_kernel<true><<<grid, block, 0, stream>>>(p, pow_tab, atm, th_top, ti_top, re_top, flux_e, flux_w, ncol_pad, colp, heat_cols, cellp_top, cell_fs);
-    else lh_atmos_flux_kernel<false><<<grid, block, 0, stream>>>(p, pow_tab, atm, th_top, ti_top, re_top, flux_e, flux_w, ncol_pad, colp, heat_cols, cellp_top, cell_fs);
+    if (colp) LH_LAUNCH((lh_atmos_flux_kernel<true>), grid, block, 0, stream, p, pow_tab, atm, th_top, ti_top, re_top, flux_e, flux_w, ncol_pad, colp, heat_cols, cellp_top, cell_fs);
+    else LH_LAUNCH((lh_atmos_flux_kernel<false>), grid, block, 0, stream, p, pow_tab, atm, th_top, ti_top, re_top, flux_e, flux_w, ncol_pad, colp, heat_cols, cellp_top, cell_fs);
     return cudaGetLastError();
 }
 
 cudaError_t lh_launch_atmos_eval(const LhDevParams& p, const double* pow_tab, const LhAtmos& atm, const double* th, const double* ti,
                                  const double* T, double* heat, double* water, int64_t n, cudaStream_t stream)
 {
-    lh_atmos_eval_kernel<<<(unsigned)((n + 127) / 128), 128, 0, stream>>>(p, pow_tab, atm, th, ti, T, heat, water, n);
+    LH_LAUNCH((lh_atmos_eval_kernel), (unsigned)((n + 127) / 128), 128, 0, stream, p, pow_tab, atm, th, ti, T, heat, water, n);
     return cudaGetLastError();
 }
 
@@ -347,14 +348,14 @@ cudaError_t lh_launch_budgets(const double* th, const double* re, int64_t ncol, 
                               int32_t nlayer, double dz, double* partials, int32_t npartials,
                               double* out2, cudaStream_t stream)
 {
-    lh_budget_partial_kernel<<<npartials, BUDGET_THREADS, 0, stream>>>(th, re, ncol, ncol_pad, nlayer, partials);
-    lh_budget_final_kernel<<<1, BUDGET_THREADS, 0, stream>>>(partials, npartials, dz, out2);
+    LH_LAUNCH((lh_budget_partial_kernel), npartials, BUDGET_THREADS, 0, stream, th, re, ncol, ncol_pad, nlayer, partials);
+    LH_LAUNCH((lh_budget_final_kernel), 1, BUDGET_THREADS, 0, stream, partials, npartials, dz, out2);
     return cudaGetLastError();
 }
 
 cudaError_t lh_launch_budgets_from_partials(const double* partials, int64_t npartials, double dz, double* out2, cudaStream_t stream)
 {
-    lh_budget_final_kernel<<<1, BUDGET_THREADS, 0, stream>>>(partials, npartials, dz, out2);
+    LH_LAUNCH((lh_budget_final_kernel), 1, BUDGET_THREADS, 0, stream, partials, npartials, dz, out2);
     return cudaGetLastError();
 }
 
@@ -439,7 +440,7 @@ cudaError_t lh_launch_to_soa(const double* staged, double* soa, int64_t col0, in
                              int32_t nlayer, int64_t ncol_pad, cudaStream_t stream)
 {
     dim3 block(32, 8), grid((unsigned)((ncols + 31) / 32), (unsigned)((nlayer + 31) / 32));
-    lh_to_soa_kernel<<<grid, block, 0, stream>>>(staged, soa, col0, ncols, nlayer, ncol_pad);
+    LH_LAUNCH((lh_to_soa_kernel), grid, block, 0, stream, staged, soa, col0, ncols, nlayer, ncol_pad);
     return cudaGetLastError();
 }
 
@@ -447,7 +448,7 @@ cudaError_t lh_launch_from_soa(const double* soa, double* staged, int64_t col0, 
                                int32_t nlayer, int64_t ncol_pad, cudaStream_t stream)
 {
     dim3 block(32, 8), grid((unsigned)((ncols + 31) / 32), (unsigned)((nlayer + 31) / 32));
-    lh_from_soa_kernel<<<grid, block, 0, stream>>>(soa, staged, col0, ncols, nlayer, ncol_pad);
+    LH_LAUNCH((lh_from_soa_kernel), grid, block, 0, stream, soa, staged, col0, ncols, nlayer, ncol_pad);
     return cudaGetLastError();
 }
 
@@ -455,7 +456,7 @@ cudaError_t lh_launch_fill_profile(const double* profile, double* soa, int32_t n
                                    cudaStream_t stream)
 {
     const int64_t n = (int64_t)nlayer * ncol_pad;
-    lh_fill_profile_kernel<<<(unsigned)((n + 255) / 256), 256, 0, stream>>>(profile, soa, nlayer, ncol_pad);
+    LH_LAUNCH((lh_fill_profile_kernel), (unsigned)((n + 255) / 256), 256, 0, stream, profile, soa, nlayer, ncol_pad);
     return cudaGetLastError();
 }
 
@@ -464,7 +465,7 @@ cudaError_t lh_launch_fill_padding(double* soa, int64_t ncol, int64_t ncol_pad, 
 {
     const int64_t n = (ncol_pad - ncol) * nlayer;
     if (n <= 0) return cudaSuccess;
-    lh_fill_padding_kernel<<<(unsigned)((n + 255) / 256), 256, 0, stream>>>(soa, ncol, ncol_pad, nlayer);
+    LH_LAUNCH((lh_fill_padding_kernel), (unsigned)((n + 255) / 256), 256, 0, stream, soa, ncol, ncol_pad, nlayer);
     return cudaGetLastError();
 }
 
@@ -496,19 +497,19 @@ __global__ void lh_eval_math_kernel(const __grid_constant__ LhDevParams p, int f
 
 cudaError_t lh_launch_eval_math(const LhDevParams& p, int fn, const double* x, double* y, int64_t n, cudaStream_t stream)
 {
-    lh_eval_math_kernel<<<(unsigned)((n + 255) / 256), 256, 0, stream>>>(p, fn, x, y, n);
+    LH_LAUNCH((lh_eval_math_kernel), (unsigned)((n + 255) / 256), 256, 0, stream, p, fn, x, y, n);
     return cudaGetLastError();
 }
 
 cudaError_t lh_launch_any_nonzero(const double* x, int64_t n, int* flag, cudaStream_t stream)
 {
-    lh_any_nonzero_kernel<<<592, 256, 0, stream>>>(x, n, flag);
+    LH_LAUNCH((lh_any_nonzero_kernel), 592, 256, 0, stream, x, n, flag);
     return cudaGetLastError();
 }
 
 cudaError_t lh_launch_count_nonfinite(const double* soa, int64_t n, unsigned long long* count,
                                       cudaStream_t stream)
 {
-    lh_count_nonfinite_kernel<<<592, 256, 0, stream>>>(soa, n, count);
+    LH_LAUNCH((lh_count_nonfinite_kernel), 592, 256, 0, stream, soa, n, count);
     return cudaGetLastError();
 }

@@ -4,6 +4,7 @@
 #pragma once
 
 #include "lh_kernels.cuh"
+#include "lh_ptx.cuh"
 
 #include "lh_soil.h"
 
@@ -154,20 +155,6 @@ constexpr int LH_RED_DOUBLES = 2 * LH_WARPS_PER_SM;      // per-warp budget part
 
 template <int MODEL> struct Slot { static constexpr int NQv = NQ<MODEL>::value; static constexpr int doubles = (2 * NQv + 6) * 32; };
 
-// 16-byte cp.async that bypasses L1 (.cg): global -> shared without allocating an L1 line while in flight.
-__device__ __forceinline__ void lh_cp16(uint32_t dst, const void* src, bool pred)
-{
-    asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %2, 0;\n\t@p cp.async.cg.shared.global [%0], [%1], 16;\n\t}"
-                 ::"r"(dst), "l"(src), "r"((int)pred) : "memory");
-}
-template <int OFF>
-__device__ __forceinline__ double lh_lds(uint32_t addr)
-{
-    double v;
-    asm volatile("ld.shared.f64 %0, [%1+%2];" : "=d"(v) : "r"(addr), "n"(OFF) : "memory");
-    return v;
-}
-
 // One stage over this block's column groups.  `smem` = the block's dynamic shared memory with the exp2 / log2
 // tables already staged at its start.  Contains ONE __syncthreads (the chunk-face exchange): every thread of
 // the block must call it.
@@ -255,12 +242,12 @@ __device__ __forceinline__ void lh_stage_body_impl(const LhKernelArgs& A, const 
 #pragma unroll
             for (int gi = 0; gi < NG; ++gi) { lh_cp16(d + doff[gi], sp[gi], pred[gi]); sp[gi] += stride_b; }
         }
-        asm volatile("cp.async.commit_group;" ::: "memory");
+        lh_cp_commit();
     };
     // wait for the oldest outstanding cell, read it from the ring cell at d, then request cell i_next into d_next
     const uint32_t lane8 = (uint32_t)lane * 8;
     auto load_raw = [&](uint32_t d, uint32_t d_next, int i_next) {
-        asm volatile("cp.async.wait_group %0;" ::"n"(RING_DEPTH - 2) : "memory");
+        lh_cp_wait<RING_DEPTH - 2>();
         __syncwarp();
         const uint32_t dl = d + lane8;
         Raw r;
@@ -493,13 +480,13 @@ template <int MODEL, int STAGE, int FLAGS>
 __global__ void __launch_bounds__(LhBounds<FLAGS>::max_threads, 1)
 lh_soil_stage_kernel(const __grid_constant__ LhKernelArgs A)
 {
-    extern __shared__ __align__(16) double smem[];
+    LH_DYN_SMEM(double, smem);
 #if LH_PDL
     // Programmatic dependent launch: the NEXT stage's blocks may be scheduled as soon as this grid's blocks have
     // all started, into the SM slots its last wave frees; they stage their tables (parameter block only) and then
     // wait here until the previous stage has completed and flushed.  Hides the launch gap and the block prologue
     // behind the previous stage's tail — what matters when a launch is only ~80 us (column shards at 8 GPUs).
-    asm volatile("griddepcontrol.launch_dependents;");
+    lh_pdl_launch_dependents();
 #endif
     const int tid = (threadIdx.z * blockDim.y + threadIdx.y) * 32 + threadIdx.x;
     lh_stage_tables(A.p, A.pow_tab, smem, tid, blockDim.x * blockDim.y * blockDim.z);
@@ -507,16 +494,14 @@ lh_soil_stage_kernel(const __grid_constant__ LhKernelArgs A)
         // this block's predecessor: block blockIdx.x of the previous stage launch (same columns); see LhKernelArgs
         if (tid == 0) {
             const int32_t* f = A.chain_flags + blockIdx.x;
-            int32_t v;
             for (;;) {
-                asm volatile("ld.acquire.gpu.global.s32 %0, [%1];" : "=r"(v) : "l"(f) : "memory");
-                if (v == A.chain_wait) break;
+                if (lh_ld_acquire(f) == A.chain_wait) break;
                 __nanosleep(64);
             }
         }
     } else {
 #if LH_PDL
-        asm volatile("griddepcontrol.wait;" ::: "memory");
+        lh_pdl_wait();
 #endif
     }
     __syncthreads();
@@ -525,7 +510,7 @@ lh_soil_stage_kernel(const __grid_constant__ LhKernelArgs A)
         __threadfence();                  // every thread's stores are visible device-wide before the flag is
         __syncthreads();
         if ((threadIdx.x | threadIdx.y | threadIdx.z) == 0)      // (not `tid`: keeping it live across the layer loop costs 4 moves per cell)
-            asm volatile("st.release.gpu.global.s32 [%0], %1;" ::"l"(A.chain_flags + blockIdx.x), "r"(A.chain_set) : "memory");
+            lh_st_release(A.chain_flags + blockIdx.x, A.chain_set);
     }
 }
 
@@ -539,7 +524,7 @@ template <int MODEL, int FLAGS>
 __global__ void __launch_bounds__(LhBounds<FLAGS>::max_threads, 1)
 lh_soil_ssprk33_persistent_kernel(const __grid_constant__ LhKernelArgs A)
 {
-    extern __shared__ __align__(16) double smem[];
+    LH_DYN_SMEM(double, smem);
     lh_stage_tables(A.p, A.pow_tab, smem, (threadIdx.z * blockDim.y + threadIdx.y) * 32 + threadIdx.x, blockDim.x * blockDim.y * blockDim.z);
     __syncthreads();
     // stage 1 as passed: in = U, out = V
@@ -658,7 +643,7 @@ cudaError_t launch_persistent_variant(const LhKernelArgs& args, const LhLaunchSh
         if ((e = cudaFuncSetAttribute(lh_soil_ssprk33_persistent_kernel<MODEL, FLAGS>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared))) return e;
         configured_smem[dev] = (int)s.smem_bytes + 1;
     }
-    lh_soil_ssprk33_persistent_kernel<MODEL, FLAGS><<<grid, block, s.smem_bytes, stream>>>(args);
+    LH_LAUNCH((lh_soil_ssprk33_persistent_kernel<MODEL, FLAGS>), grid, block, s.smem_bytes, stream, args);
     return cudaGetLastError();
 }
 

@@ -13,11 +13,30 @@ def pytest_configure(config):
     config.addinivalue_line("markers", "gpu: needs a CUDA device (run on the B200 box with -m gpu)")
 
 
-@pytest.fixture(scope="session")
-def lh():
+HOSTEMU = os.environ.get("LH_TEST_HOSTEMU") == "1"
+
+
+def _load_package():
     import __graft_entry__ as graft
 
-    return graft.load_package()
+    lh = graft.load_package()
+    if HOSTEMU and not getattr(lh, "_hostemu_patched", False):
+        # TEST PROCESS ONLY (tests/test_hostemu.py starts it): the `-m gpu` tests run against the host-emulated build of the
+        # product's own sources (tests/hostemu.py) instead of csrc/liblh_soil.so.  The package itself knows nothing of it.
+        import hostemu
+
+        lh.cuda_library = lambda: hostemu.library(lh)
+        lh._hostemu_patched = True
+    return lh
+
+
+if HOSTEMU:
+    _load_package()
+
+
+@pytest.fixture(scope="session")
+def lh():
+    return _load_package()
 
 
 @pytest.fixture(scope="session")

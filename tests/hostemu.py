@@ -1,0 +1,88 @@
+"""Host emulation of the PRODUCT library, for the CPU-only test run (test infrastructure; see tests/support/hostemu/).
+
+``build()`` compiles landhydrology.jl_b200/csrc/*.cu — the same sources nvcc compiles for sm_100a — with g++ against
+tests/support/hostemu/cuda_runtime.h and links them with the fiber scheduler (hostemu.cpp) into
+tests/support/hostemu/_build/liblh_soil_hostemu.so (git-ignored, cached on source mtimes).  ``library()`` opens it as a
+``SoilLibrary`` with the product's own symbol names, so every test written against the CUDA library can also run against the
+emulated build.  Never imported by the package, by bench.py or by ``__graft_entry__``."""
+from __future__ import annotations
+
+import ctypes as C
+import os
+import subprocess
+from concurrent.futures import ThreadPoolExecutor
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+CSRC = os.path.join(ROOT, "landhydrology.jl_b200", "csrc")
+EMU = os.path.join(ROOT, "tests", "support", "hostemu")
+BUILD = os.path.join(EMU, "_build")
+LIB = os.path.join(BUILD, "liblh_soil_hostemu.so")
+
+# -O1: the 230-odd kernel variants compile in ~1 min on 8 cores and run ~20x faster than at -O0.  -ffp-contract=off: an FMA
+# is fused exactly where the source says lh_fma / fma, as nvcc's --fmad=true would only ADD contractions of a*b+c written
+# out — the closures avoid those on purpose (every such expression is spelled with fma), so both builds round alike.
+CXXFLAGS = ["-std=c++17", "-O1", "-g", "-fPIC", "-ffp-contract=off", "-fno-strict-aliasing", "-DLH_HOSTEMU=1", "-DLH_MATH_HOST=1",
+            "-I", EMU, "-I", CSRC, "-I", os.path.join(ROOT, "include")]
+
+
+def _sources():
+    cu = sorted(os.path.join(CSRC, f) for f in os.listdir(CSRC) if f.endswith(".cu"))
+    deps = sorted(os.path.join(CSRC, f) for f in os.listdir(CSRC) if f.endswith((".cuh", ".h", ".inc")))
+    deps += [os.path.join(EMU, f) for f in ("cuda_runtime.h", "hostemu.cpp", "exports.map")] + [os.path.join(ROOT, "include", "lh_soil.h"), __file__]
+    return cu, deps
+
+
+def build(force: bool = False) -> str:
+    cu, deps = _sources()
+    newest = max(os.path.getmtime(p) for p in cu + deps)
+    if not force and os.path.exists(LIB) and os.path.getmtime(LIB) >= newest:
+        return LIB
+    os.makedirs(BUILD, exist_ok=True)
+    env = {k: v for k, v in os.environ.items() if k not in ("CC", "CXX")}
+
+    def compile_one(src):
+        obj = os.path.join(BUILD, os.path.basename(src) + ".o")
+        if not force and os.path.exists(obj) and os.path.getmtime(obj) >= max(os.path.getmtime(src), max(os.path.getmtime(d) for d in deps)):
+            return obj
+        cmd = ["g++", *CXXFLAGS, "-x", "c++", "-c", src, "-o", obj]
+        res = subprocess.run(cmd, capture_output=True, text=True, env=env)
+        if res.returncode != 0:
+            raise RuntimeError("host-emulation build failed:\n" + " ".join(cmd) + "\n" + res.stdout + res.stderr)
+        return obj
+
+    with ThreadPoolExecutor(max(1, len(os.sched_getaffinity(0)))) as pool:
+        objs = list(pool.map(compile_one, cu + [os.path.join(EMU, "hostemu.cpp")]))
+    # -Bsymbolic + the export map: calls inside the library bind inside the library whatever else the test process has loaded
+    cmd = ["g++", "-shared", "-Wl,-Bsymbolic", "-Wl,--version-script=" + os.path.join(EMU, "exports.map"), "-o", LIB + ".tmp", *objs, "-ldl", "-lpthread"]
+    res = subprocess.run(cmd, capture_output=True, text=True, env=env)
+    if res.returncode != 0:
+        raise RuntimeError("host-emulation link failed:\n" + res.stdout + res.stderr)
+    os.replace(LIB + ".tmp", LIB)
+    return LIB
+
+
+_lib = None
+
+
+def library(lh):
+    """The emulated build as a ``SoilLibrary`` (product symbol names, prefix ``lh_``)."""
+    global _lib
+    if _lib is None:
+        _lib = lh.SoilLibrary(build(), "lh_")
+    return _lib
+
+
+def controls():
+    """ctypes handle with the emulator's knobs: lh_emu_set_schedule, lh_emu_set_cp_async_lazy, lh_emu_set_sm_count, ..."""
+    h = C.CDLL(build())
+    h.lh_emu_set_schedule.argtypes = [C.c_int, C.c_uint64]
+    h.lh_emu_set_schedule.restype = C.c_int
+    h.lh_emu_set_cp_async_lazy.argtypes = [C.c_int]
+    h.lh_emu_set_cp_async_lazy.restype = C.c_int
+    h.lh_emu_set_device_count.argtypes = [C.c_int]
+    h.lh_emu_set_device_count.restype = C.c_int
+    h.lh_emu_set_sm_count.argtypes = [C.c_int]
+    h.lh_emu_set_sm_count.restype = C.c_int
+    h.lh_emu_launch_count.argtypes = []
+    h.lh_emu_launch_count.restype = C.c_uint64
+    return h

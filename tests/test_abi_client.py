@@ -62,7 +62,7 @@ def test_c_client_against_oracle(client, tmp_path):
 def test_c_client_cuda_matches_oracle(client, tmp_path, shape):
     ncol, nlayer = shape
     o = _split(_run(client, graft.build_oracle(), "lho_", str(tmp_path / "oracle.bin"), ncol, nlayer), ncol, nlayer)
-    g = _split(_run(client, graft.build_cuda(), "lh_", str(tmp_path / "cuda.bin"), ncol, nlayer), ncol, nlayer)
+    g = _split(_run(client, graft.load_package().cuda_library().path, "lh_", str(tmp_path / "cuda.bin"), ncol, nlayer), ncol, nlayer)
     cells = ncol * nlayer
     for f in range(2):       # tendencies: 1e-11 of the field's max norm (the strict, cancellation-aware gate is test_gpu_parity.py)
         r, a = o["tendency"][f * cells:(f + 1) * cells], g["tendency"][f * cells:(f + 1) * cells]
