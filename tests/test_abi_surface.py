@@ -137,3 +137,12 @@ def test_product_never_references_oracle():
                 if re.search(r"liblho_soil|lho_soil|oracle/|np_soil", text):
                     hits.append(os.path.join(dirpath, f))
     assert not hits, hits
+    # nor can any product or measurement path load the host-emulated test build (tests/support/hostemu): no Python file of the
+    # package, bench.py or __graft_entry__.py mentions it (the csrc headers name it in comments only: lh_ptx.cuh's LH_HOSTEMU guard)
+    emu_hits = []
+    for path in [os.path.join(d, f) for d, _, fs in os.walk(pkg) for f in fs if f.endswith(".py")] + \
+            [os.path.join(ROOT, "bench.py"), os.path.join(ROOT, "__graft_entry__.py")] + \
+            [os.path.join(ROOT, "tools", f) for f in os.listdir(os.path.join(ROOT, "tools")) if f.endswith(".py")]:
+        if re.search(r"hostemu|LH_HOSTEMU", open(path, errors="ignore").read()):
+            emu_hits.append(path)
+    assert not emu_hits, emu_hits

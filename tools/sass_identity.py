@@ -4,7 +4,7 @@
     python tools/sass_identity.py --record profiles/<name>.json     # fingerprint the current build
     python tools/sass_identity.py --check  profiles/<name>.json     # which kernels differ from the recorded build?
 
-A host-side refactor (launch spelling, header moves, the host-emulation hooks of tests/support/hostemu) must leave every
+A host-side refactor (launch spelling, header moves, the hooks of the CPU-only test build) must leave every
 kernel's machine code untouched: `--check` against the fingerprints of the last build whose `-m gpu` suite ran green on a B200
 proves it without a GPU.  A kernel change shows up as exactly the set of variants it was meant to touch."""
 import argparse
