@@ -1058,6 +1058,11 @@ namespace {
 int32_t enqueue_download(lh_soil_ctx* c, const double* soa, double* host, int64_t cs, int64_t ls)
 {
     const int n = c->nlayer;
+    if (cs == 1 && n == 1) {   // a single layer: the row of columns is contiguous whatever the layer stride says (a 2-D copy
+                               // would be handed a destination pitch smaller than its width: the reference layout has ls = 1)
+        LH_CUDA(c, cudaMemcpyAsync(host, soa, c->ncol * sizeof(double), cudaMemcpyDeviceToHost, c->copy_stream));
+        return LH_OK;
+    }
     if (cs == 1 || c->ncol == 1) {
         LH_CUDA(c, cudaMemcpy2DAsync(host, ls * sizeof(double), soa, c->ncol_pad * sizeof(double), c->ncol * sizeof(double), n,
                                      cudaMemcpyDeviceToHost, c->copy_stream));

@@ -56,6 +56,22 @@ def test_run_equals_the_step_loop(lib, case):
         assert np.array_equal(a.get_state(f), b.get_state(f))
 
 
+def test_run_snapshots_of_a_one_layer_domain(lib):
+    """nlayer == 1 with several columns: in the reference layout (col_stride = nlayer = 1, layer_stride = 1) a snapshot is one
+    contiguous row of columns.  (Found by the random API sequences of tests/test_hostemu_fuzz.py: the overlapped snapshot path
+    handed cudaMemcpy2DAsync a destination pitch of 8 bytes for a 79-column row and the run failed with `invalid argument`;
+    the blocking lh_soil_get_state path had the single-layer case, the snapshot path did not.)"""
+    wl = w.coupled_workload(ncol=79, nlayer=1, seed=104, zlim=(-0.1, 0.0))
+    a, b = _ctx(lib, wl), _ctx(lib, wl)
+    _, snaps = a.run(0.0, wl.dt, 4, save_every=2, save_first=True, save_fields=(0, 2))
+    assert snaps.shape == (3, 2, 79, 1)
+    ref = [[b.get_state(f) for f in (0, 2)]]
+    for s in range(2):
+        b.step(2 * s * wl.dt, wl.dt, 2)
+        ref.append([b.get_state(f) for f in (0, 2)])
+    assert np.array_equal(snaps, np.array(ref))
+
+
 def test_run_argument_checks(lib):
     wl = w.coupled_workload(ncol=8, nlayer=6, seed=103, zlim=(-0.6, 0.0))
     ctx = _ctx(lib, wl)
