@@ -511,20 +511,27 @@ def _main(args, result_stream):
         down_done = [threading.Event() for _ in range(S)]
         step_budgets = np.zeros((S, K, 2))
 
+        marks = np.zeros((S, 6))                               # per shard: upload start / end, run end, download start / end (s)
+
         def run_shard(k, sub, c0, c1):
             if k > 0:
                 up_done[k - 1].wait()
+            marks[k, 0] = time.perf_counter()
             for fid, a in host.items():
                 sub.set_state(fid, a[c0:c1])                   # H2D (+ layout transform on device)
+            marks[k, 1] = time.perf_counter()
             up_done[k].set()
             # run!(sim): K steps in ONE call; after every step the budgets (the step's result, 16 B) are reduced on the
             # device and copied to a pinned slot on the host, asynchronously, while the next step runs.
             bud, _ = sub.run(0.0, wl.dt, K, bc_table=table_K, budget_every=1)
+            marks[k, 2] = time.perf_counter()
             step_budgets[k] = bud
             if k > 0:
                 down_done[k - 1].wait()
+            marks[k, 3] = time.perf_counter()
             for fid, a in out.items():
                 sub.get_state(fid, a[c0:c1])                   # D2H
+            marks[k, 4] = time.perf_counter()
             down_done[k].set()
 
         barrier()
@@ -554,6 +561,20 @@ def _main(args, result_stream):
             "numa_bound": bool(numa_bound),
             "shards_per_gpu": S,
             "seconds": e_sec,
+        }
+        # where the wall time of this rank's e2e leg went (host clocks around the blocking calls of each shard's thread)
+        up_s, run_s, down_s = marks[:, 1] - marks[:, 0], marks[:, 2] - marks[:, 1], marks[:, 4] - marks[:, 3]
+        up_bytes = nfields_in * (hi - lo) * args.nlayer * 8
+        down_bytes = nfields_out * (hi - lo) * args.nlayer * 8
+        e2e["breakdown_rank0"] = {
+            "what": "per-shard host wall clock of the blocking calls: upload (H2D + device transpose), lh_soil_run (K steps, competing "
+                    "with the other shards' kernels and transposes), download (device transpose + D2H); uploads / downloads of the "
+                    "shards take turns, so their sums are the time the PCIe link was claimed in each direction",
+            "upload_s_sum": float(up_s.sum()), "run_s_mean": float(run_s.mean()), "run_s_max": float(run_s.max()), "download_s_sum": float(down_s.sum()),
+            "h2d_GBps_while_uploading": float(up_bytes / max(up_s.sum(), 1e-9) / 1e9),
+            "d2h_GBps_while_downloading": float(down_bytes / max(down_s.sum(), 1e-9) / 1e9),
+            "first_upload_to_last_upload_end_s": float(marks[:, 1].max() - marks[:, 0].min()),
+            "last_upload_end_to_last_download_end_s": float(marks[:, 4].max() - marks[:, 1].max()),
         }
         for sub, _, _ in subs:
             if sub is not ctx:
