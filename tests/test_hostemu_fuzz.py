@@ -131,6 +131,14 @@ def _sequence(rng, wl, g, o, nops):
                 new = cur * (1.0 + 1e-3 * rng.standard_normal(cur.shape))
                 if f == 0:
                     new = np.minimum(new, 0.98 * (wl.params.nu - o.get_state(1))) if not het else cur
+                    if not het and wl.model == COUPLED and rng.random() < 0.4:
+                        # a few exactly saturated, oversaturated and almost dry cells: the saturated branches of the pressure
+                        # head and the conductivity, the residual-water clamp
+                        room = wl.params.nu - o.get_state(1)
+                        pick = rng.random(cur.shape)
+                        new = np.where(pick < 0.03, room, new)
+                        new = np.where((pick >= 0.03) & (pick < 0.06), room * (1.0 + 2e-4), new)
+                        new = np.where((pick >= 0.06) & (pick < 0.09), wl.params.theta_r + 0.02 * room, new)
             for c in both:
                 c.set_state(f, new)
         elif op == "stepper":
