@@ -148,6 +148,42 @@ def test_fresh_device_memory_is_poisoned_and_never_read(emu):
     assert np.all(np.isfinite(ctx.budgets()))
 
 
+def test_contexts_on_concurrent_host_threads(emu):
+    """bench.py's e2e leg and any multi-threaded host drive several contexts from several host threads at once (one ctx, one
+    stream and one thread per column shard).  The library keeps per-process state (the per-variant shared-memory configuration
+    cache, the NCCL loader) and per-thread state (the create-time error string): every shard must come out bit-identical to the
+    same shard run alone."""
+    from concurrent.futures import ThreadPoolExecutor
+
+    wl = w.coupled_workload(ncol=256, nlayer=24, seed=31)
+    cuts = [0, 64, 96, 192, 256]
+    K = 3
+
+    def shard(k):
+        c0, c1 = cuts[k], cuts[k + 1]
+        ctx = lh.SoilContext(emu, wl.config(ncol=c1 - c0, flags=STAGE if k % 2 else 0))
+        for f, a in wl.fields.items():
+            ctx.set_state(f, np.ascontiguousarray(a[c0:c1]))
+        bud, _ = ctx.run(0.0, wl.dt, K, budget_every=1)
+        out = {f: ctx.get_state(f) for f in (0, 2)}
+        ctx.close()
+        return out, bud
+
+    alone = [shard(k) for k in range(4)]
+    with ThreadPoolExecutor(4) as pool:
+        together = list(pool.map(shard, range(4)))
+    for (sa, ba), (st, bt) in zip(alone, together):
+        assert np.array_equal(ba, bt)
+        for f in sa:
+            assert np.array_equal(sa[f], st[f])
+    # and the shards are the columns of the unsharded run
+    whole = lh.SoilContext(emu, wl.config())
+    wl.upload(whole)
+    whole.step(0.0, wl.dt, K)
+    for f in (0, 2):
+        assert np.array_equal(np.concatenate([t_[0][f] for t_ in together]), whole.get_state(f))
+
+
 # The driver's `-m gpu` suite against the emulated build.  Left out (by wall time on 8 host cores, not by outcome — every one of
 # them passes on the emulated build when given the minutes): cases sized for a real GPU (>= 5e4 columns, the full C4 shape),
 # the reference's long integrations (20 000 to 138 240 steps), and what needs torch.cuda, NCCL or nvidia-smi.
