@@ -180,6 +180,9 @@ const char* lh_soil_last_error(const lh_soil_ctx* ctx);
 int32_t lh_soil_get_zc(const lh_soil_ctx* ctx, double* zc_out);
 
 /* ---- state / aux transfer (replaces initialize_states, initial_conditions.jl:101-107) - */
+/* set_state borrows `host` for the call only: it returns once the last byte has left the host buffer.  The layout transform of
+ * the last blocks may still be queued on the ctx stream then; every later call on this ctx is ordered behind it.  (Only a
+ * caller that reads the raw pointer of lh_soil_device_ptr on a stream of its own must call lh_soil_sync first.)            */
 int32_t lh_soil_set_state(lh_soil_ctx* ctx, int32_t field, const double* host,
                           int64_t col_stride, int64_t layer_stride);
 int32_t lh_soil_get_state(lh_soil_ctx* ctx, int32_t field, double* host,
@@ -423,7 +426,8 @@ int32_t lh_soil_last_step_timing(lh_soil_ctx* ctx, double* ms_out, int64_t* laun
 int32_t lh_soil_kernel_info(lh_soil_ctx* ctx, char* buf, int64_t cap);
 
 /* Raw device pointer of a field's column-fastest SoA block [layer][ncol_padded] and the
- * padded column stride, for zero-copy interop (e.g. wrapping in a torch tensor).            */
+ * padded column stride, for zero-copy interop (e.g. wrapping in a torch tensor).  Work this ctx has enqueued (uploads, steps)
+ * is ordered on the ctx's own stream: call lh_soil_sync before touching the memory from another stream.                  */
 int32_t lh_soil_device_ptr(lh_soil_ctx* ctx, int32_t field, void** dptr, int64_t* ncol_padded);
 
 /* ---- multi-GPU: column shards, one ctx per GPU/process ------------------------------- */

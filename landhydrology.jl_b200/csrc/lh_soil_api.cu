@@ -306,7 +306,12 @@ int32_t upload_field(lh_soil_ctx* c, double* soa, const double* host, int64_t cs
         LH_CUDA(c, cudaEventRecord(c->ev_xpose[k], c->stream));
     }
     LH_CUDA(c, lh_launch_fill_padding(soa, c->ncol, c->ncol_pad, n, c->stream));
-    LH_CUDA(c, cudaStreamSynchronize(c->stream));   // host pointers are borrowed for the call only
+    // Host pointers are borrowed for the call only: wait for the LAST H2D COPY, not for the transposes that trail it on the
+    // compute stream.  Everything that consumes the field afterwards is enqueued on that same stream (or waits for it: downloads,
+    // snapshots, lh_soil_sync), and a staging block is only overwritten after its ev_xpose event — so returning here lets the
+    // next upload (this ctx's next field, or another shard's) claim the PCIe link while the transposes are still queued behind
+    // other contexts' stage kernels.  In a sharded end-to-end run that removes one full drain of the GPU queue per field.
+    LH_CUDA(c, cudaStreamSynchronize(c->copy_stream));
     return LH_OK;
 }
 
