@@ -635,8 +635,10 @@ def _main(args, result_stream):
             except Exception as exc:                      # a variant that fails must not hide the headline
                 rows[name] = {"error": f"{type(exc).__name__}: {exc}"}
         line["extra"] = {"variants": rows,
-                         "variants_note": "same process, same GPU, CUDA events on the ctx stream, median of 5 blocks of K steps each "
-                                          "(small configs: 50 K steps per block); frac_contract / frac_on_wire as in `roofline`"}
+                         "variants_note": "same process, same GPU, CUDA events on the ctx stream; per variant the MEDIAN of back-to-back "
+                                          "blocks of K steps (small configs: 50 K) covering >= 1 s of device time, i.e. sustained "
+                                          "(power-capped) clocks like `value`; cell_steps_per_s_first_block is the burst figure; "
+                                          "frac_contract / frac_on_wire as in `roofline`"}
     emit(line)
     progress("result line written")
     finish_distributed()

@@ -77,8 +77,10 @@ def variant_specs(lh, w, quick=False):
     return S
 
 
-def measure(lh, spec, steps=20, warmup=3, reps=3, device=0):
-    """Median of `reps` timed blocks of `steps` SSPRK33 steps (CUDA events on the ctx stream)."""
+def measure(lh, spec, steps=20, warmup=3, reps=3, device=0, min_seconds=1.0):
+    """Median of the timed blocks of `steps` SSPRK33 steps (CUDA events on the ctx stream): at least `reps` blocks, repeated back
+    to back until `min_seconds` of device time have been measured (the board settles at its power-capped clock within a few
+    hundred milliseconds of fp64 load: a handful of 20-step blocks alone would be a burst-clock figure), at most 400 blocks."""
     wl = spec["make"]()
     wl.device = device
     ctx = lh.SoilContext(lh.cuda_library(), wl.config(flags=spec.get("flags", 0)))
@@ -91,7 +93,7 @@ def measure(lh, spec, steps=20, warmup=3, reps=3, device=0):
         ctx.sync()
         ms_all = []
         launches = 0
-        for _ in range(reps):
+        while len(ms_all) < reps or (sum(ms_all) < min_seconds * 1e3 and len(ms_all) < 400):
             ctx.step(0.0, wl.dt, k)
             ms, launches = ctx.last_step_timing()
             ms_all.append(ms)
@@ -106,6 +108,8 @@ def measure(lh, spec, steps=20, warmup=3, reps=3, device=0):
     row = {"ncol": wl.ncol, "nlayer": wl.nlayer, "cell_steps_per_s": v, "ms_per_step": ms / k,
            "frac_contract": v * contract / 1e9 / peak, "frac_on_wire": v * wire / 1e9 / peak,
            "bytes_contract": contract, "bytes_on_wire": wire, "launches_per_block": int(launches), "steps_per_block": k,
+           "blocks": len(ms_all), "device_seconds": float(sum(ms_all)) * 1e-3,
+           "cell_steps_per_s_first_block": wl.cells * k / (ms_all[0] * 1e-3),
            "finite": bool(np.all(np.isfinite(bud)))}
     if info:
         row["kernel"] = info
