@@ -238,8 +238,12 @@ bool field_ok(int f) { return f >= 0 && f < LH_NUM_FIELDS; }
 int32_t ensure_staging(lh_soil_ctx* c)
 {
     if (c->stage_dev[0]) return LH_OK;
-    // ~32 MiB blocks: large enough for PCIe efficiency, small enough to pipeline copy and transpose
-    int64_t cols = std::max<int64_t>(32, (32ll << 20) / ((int64_t)c->nlayer * 8));
+    // ~32 MiB blocks: large enough for PCIe efficiency, small enough to pipeline copy and transpose.  (LH_STAGE_BLOCK_BYTES,
+    // read here, once per ctx: a tuning knob, and how the tests push many small blocks through the two-buffer pipeline.)
+    const char* env_block = getenv("LH_STAGE_BLOCK_BYTES");
+    const long long env_bytes = env_block ? atoll(env_block) : 0;
+    const int64_t block_bytes = env_bytes > 0 ? (int64_t)env_bytes : (int64_t)(32ll << 20);
+    int64_t cols = std::max<int64_t>(32, block_bytes / ((int64_t)c->nlayer * 8));
     cols = std::min<int64_t>((cols + 31) / 32 * 32, c->ncol_pad);
     c->chunk_cols = cols;
     const size_t bytes = (size_t)cols * c->nlayer * sizeof(double);

@@ -61,6 +61,49 @@ def build(force: bool = False) -> str:
     return LIB
 
 
+def build_mutant(name: str, filename: str, old: str, new: str) -> str:
+    """A copy of the emulated library in which csrc/<filename> has `old` replaced by `new` — a deliberately broken product, for
+    checking that the tests which claim to detect a class of bug really do (tests/test_hostemu.py).  A mutation of
+    lh_soil_api.cu recompiles only that translation unit (the kernels' objects are those of the regular build); a mutation of
+    a header recompiles everything from a patched copy of csrc/."""
+    build()
+    src = open(os.path.join(CSRC, filename)).read()
+    assert src.count(old) == 1, "mutation site not found exactly once"
+    text = src.replace(old, new)
+    mdir = os.path.join(BUILD, "mutants", name)
+    mlib, stamp = os.path.join(mdir, "libmutant.so"), os.path.join(mdir, "patched_source")
+    if os.path.exists(mlib) and os.path.exists(stamp) and open(stamp).read() == text and os.path.getmtime(mlib) >= os.path.getmtime(LIB):
+        return mlib
+    os.makedirs(mdir, exist_ok=True)
+    env = {k: v for k, v in os.environ.items() if k not in ("CC", "CXX")}
+    link = ["g++", "-shared", "-Wl,-Bsymbolic", "-Wl,--version-script=" + os.path.join(EMU, "exports.map"), "-o", mlib]
+    if filename == "lh_soil_api.cu":
+        msrc, mobj = os.path.join(mdir, "lh_soil_api.cu"), os.path.join(mdir, "lh_soil_api.cu.o")
+        open(msrc, "w").write(text)
+        subprocess.run(["g++", *CXXFLAGS, "-x", "c++", "-c", msrc, "-o", mobj], check=True, env=env)
+        objs = [os.path.join(BUILD, f) for f in os.listdir(BUILD) if f.endswith(".o") and f != "lh_soil_api.cu.o"] + [mobj]
+    else:
+        import shutil
+
+        mcsrc = os.path.join(mdir, "csrc")
+        shutil.rmtree(mcsrc, ignore_errors=True)
+        shutil.copytree(CSRC, mcsrc, ignore=shutil.ignore_patterns("*.so", "*.o"))
+        open(os.path.join(mcsrc, filename), "w").write(text)
+        flags = [f if f != CSRC else mcsrc for f in CXXFLAGS]
+        units = sorted(os.path.join(mcsrc, f) for f in os.listdir(mcsrc) if f.endswith(".cu")) + [os.path.join(EMU, "hostemu.cpp")]
+
+        def compile_one(src_path):
+            obj = os.path.join(mdir, os.path.basename(src_path) + ".o")
+            subprocess.run(["g++", *flags, "-x", "c++", "-c", src_path, "-o", obj], check=True, env=env)
+            return obj
+
+        with ThreadPoolExecutor(max(1, len(os.sched_getaffinity(0)))) as pool:
+            objs = list(pool.map(compile_one, units))
+    subprocess.run([*link, *objs, "-ldl", "-lpthread"], check=True, env=env)
+    open(stamp, "w").write(text)
+    return mlib
+
+
 _lib = None
 
 
@@ -72,9 +115,9 @@ def library(lh):
     return _lib
 
 
-def controls():
+def controls(path=None):
     """ctypes handle with the emulator's knobs: lh_emu_set_schedule, lh_emu_set_cp_async_lazy, lh_emu_set_sm_count, ..."""
-    h = C.CDLL(build())
+    h = C.CDLL(path or build())
     h.lh_emu_set_schedule.argtypes = [C.c_int, C.c_uint64]
     h.lh_emu_set_schedule.restype = C.c_int
     h.lh_emu_set_cp_async_lazy.argtypes = [C.c_int]
@@ -83,6 +126,8 @@ def controls():
     h.lh_emu_set_device_count.restype = C.c_int
     h.lh_emu_set_sm_count.argtypes = [C.c_int]
     h.lh_emu_set_sm_count.restype = C.c_int
+    h.lh_emu_set_async.argtypes = [C.c_int, C.c_uint64]
+    h.lh_emu_set_async.restype = C.c_int
     h.lh_emu_launch_count.argtypes = []
     h.lh_emu_launch_count.restype = C.c_uint64
     return h

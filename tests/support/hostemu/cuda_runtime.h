@@ -22,6 +22,8 @@
 
 #include <algorithm>
 #include <functional>
+#include <tuple>
+#include <type_traits>
 
 // ---------------------------------------------------------------- language surface
 #define __device__
@@ -63,11 +65,13 @@ void lh_emu_fault(const char* what);
 // wait_group allows.  Return the previous value.
 int lh_emu_set_schedule(int policy, uint64_t seed);
 int lh_emu_set_cp_async_lazy(int lazy);
+int lh_emu_set_async(int mode, uint64_t seed);   // 0 synchronous, 1 deferred (lazy), 2 deferred (seeded random interleaving)
 int lh_emu_set_device_count(int n);
 int lh_emu_set_sm_count(int n);
 uint64_t lh_emu_launch_count(void);
 }
-void lh_emu_launch(dim3 grid, dim3 block, size_t smem_bytes, const std::function<void()>& thread_body);
+struct LhEmuStream;
+void lh_emu_launch(LhEmuStream* stream, dim3 grid, dim3 block, size_t smem_bytes, std::function<void()> thread_body);
 
 // threadIdx.x etc.: objects whose members convert to the calling fiber's coordinate (not macros: cudaLaunchConfig_t has
 // members called gridDim / blockDim)
@@ -139,8 +143,9 @@ static inline void lh_pdl_wait() {}               // launches are synchronous: t
 static inline int32_t lh_ld_acquire(const int32_t* p) { return *(const volatile int32_t*)p; }
 static inline void lh_st_release(int32_t* p, int32_t v) { *(volatile int32_t*)p = v; }
 #define LH_UNPAREN(...) __VA_ARGS__
+// arguments are captured BY VALUE, as a CUDA launch copies them: an asynchronous-mode launch runs after the caller has returned
 #define LH_LAUNCH(kernel, grid, block, smem, stream, ...) \
-    lh_emu_launch(dim3(grid), dim3(block), (size_t)(smem), [&]() { LH_UNPAREN kernel(__VA_ARGS__); })
+    lh_emu_launch(stream, dim3(grid), dim3(block), (size_t)(smem), [=]() { LH_UNPAREN kernel(__VA_ARGS__); })
 #define LH_DYN_SMEM(type, name) type* const name = reinterpret_cast<type*>(lh_emu_self()->smem)
 
 // ---------------------------------------------------------------- runtime API
@@ -194,6 +199,7 @@ template <class F> static inline cudaError_t cudaFuncSetAttribute(F, cudaFuncAtt
 template <class... Params, class... Args>
 static inline cudaError_t cudaLaunchKernelEx(const cudaLaunchConfig_t* cfg, void (*kernel)(Params...), Args&&... args)
 {
-    lh_emu_launch(cfg->gridDim, cfg->blockDim, cfg->dynamicSmemBytes, [&]() { kernel(args...); });
+    auto bound = std::make_tuple(std::decay_t<Args>(args)...);          // by value, as a CUDA launch copies its arguments
+    lh_emu_launch(cfg->stream, cfg->gridDim, cfg->blockDim, cfg->dynamicSmemBytes, [kernel, bound]() { std::apply(kernel, bound); });
     return cudaSuccess;
 }

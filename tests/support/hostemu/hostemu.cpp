@@ -57,7 +57,10 @@ struct LhEmuCtx { ucontext_t uc; };
 #endif
 
 #include <atomic>
+#include <memory>
 #include <condition_variable>
+#include <deque>
+#include <functional>
 #include <mutex>
 #include <thread>
 #include <unordered_map>
@@ -262,8 +265,146 @@ cudaError_t guarded_free(void* p, bool host)
 
 }  // namespace
 
-struct LhEmuStream { int device; };
-struct LhEmuEvent { double t_ms; bool recorded; };
+// ---------------------------------------------------------------------- streams and events
+// Synchronous mode (default): every operation completes inside the call that enqueues it.
+// Asynchronous modes (lh_emu_set_async): a stream is a FIFO of deferred operations, an event completes when its record is
+// executed, cudaStreamWaitEvent blocks the waiting stream's queue.  Work is executed only when something forces it — a
+// stream / event synchronisation, a blocking copy, cudaFree — and then (mode 1, "lazy") only what that call needs, in
+// dependency order, or (mode 2, "random") seeded random runnable operations of ANY stream until the call's condition holds.
+// Both are legal executions of the same CUDA program; a host layer whose stream / event dependencies are complete computes the
+// same bits in all three modes, one that relies on "the other stream has surely finished by now" does not.
+struct LhEmuOp {
+    enum Kind { RUN, RECORD, WAIT } kind;
+    std::function<void()> fn;
+    LhEmuEvent* ev = nullptr;
+    uint64_t seq = 0;
+};
+struct LhEmuStream { int device; std::deque<LhEmuOp> q; bool visiting = false; };
+struct LhEmuEvent {
+    double t_ms = 0.0;
+    uint64_t recorded = 0, completed = 0;            // records enqueued / executed
+    std::deque<std::pair<uint64_t, LhEmuStream*>> where;   // (sequence number, stream) of the records still queued
+};
+
+namespace {
+std::atomic<int> g_async{0};
+std::recursive_mutex g_api;                          // asynchronous modes: one API call at a time
+std::vector<LhEmuStream*> g_streams;                 // never shrinks (streams and events are leaked in asynchronous modes)
+uint64_t g_async_rng = 0x2545F4914F6CDD1Dull;
+
+double now_ms()
+{
+    timespec ts;
+    clock_gettime(CLOCK_MONOTONIC, &ts);
+    return ts.tv_sec * 1e3 + ts.tv_nsec * 1e-6;
+}
+
+bool head_runnable(LhEmuStream* s)
+{
+    if (s->q.empty()) return false;
+    const LhEmuOp& op = s->q.front();
+    return op.kind != LhEmuOp::WAIT || op.ev->completed >= op.seq;
+}
+
+void exec_head(LhEmuStream* s)
+{
+    LhEmuOp op = std::move(s->q.front());
+    s->q.pop_front();
+    if (op.kind == LhEmuOp::RUN) op.fn();
+    else if (op.kind == LhEmuOp::RECORD) {
+        op.ev->completed = std::max(op.ev->completed, op.seq);
+        op.ev->t_ms = now_ms();
+        while (!op.ev->where.empty() && op.ev->where.front().first <= op.seq) op.ev->where.pop_front();
+    }
+}
+
+void event_complete_lazy(LhEmuEvent* e, uint64_t seq);
+
+// lazy: execute the operations of s in order, pulling in other streams only where a wait needs them
+void stream_step_lazy(LhEmuStream* s)
+{
+    if (s->visiting) die("stream dependency cycle: a stream waits for an event that can only complete after the wait itself");
+    s->visiting = true;
+    LhEmuOp& op = s->q.front();
+    if (op.kind == LhEmuOp::WAIT && op.ev->completed < op.seq) event_complete_lazy(op.ev, op.seq);
+    exec_head(s);
+    s->visiting = false;
+}
+
+void event_complete_lazy(LhEmuEvent* e, uint64_t seq)
+{
+    while (e->completed < seq) {
+        LhEmuStream* t = nullptr;
+        for (auto& w : e->where) if (w.first >= seq) { t = w.second; break; }
+        if (!t || t->q.empty()) die("deadlock: waiting for an event whose record is not queued anywhere");
+        stream_step_lazy(t);
+    }
+}
+
+template <class Pred> void progress_until(Pred done, LhEmuStream* want_stream, LhEmuEvent* want_event, uint64_t want_seq)
+{
+    while (!done()) {
+        if (g_async.load() == 2) {
+            std::vector<LhEmuStream*> runnable;
+            for (auto* s : g_streams) if (head_runnable(s)) runnable.push_back(s);
+            if (runnable.empty()) die("deadlock: nothing is runnable but a synchronisation is outstanding");
+            g_async_rng = g_async_rng * 6364136223846793005ull + 1442695040888963407ull;
+            exec_head(runnable[(g_async_rng >> 33) % runnable.size()]);
+        } else if (want_stream) {
+            stream_step_lazy(want_stream);
+        } else {
+            event_complete_lazy(want_event, want_seq);
+        }
+    }
+}
+
+void drain_stream(LhEmuStream* s) { progress_until([&] { return s->q.empty(); }, s, nullptr, 0); }
+void drain_all()
+{
+    for (size_t k = 0; k < g_streams.size(); ++k) drain_stream(g_streams[k]);
+}
+
+// a little background progress in random mode, so that not everything happens at the synchronisation points
+void background_progress()
+{
+    if (g_async.load() != 2) return;
+    g_async_rng = g_async_rng * 6364136223846793005ull + 1442695040888963407ull;
+    int n = (int)((g_async_rng >> 40) % 4);
+    while (n-- > 0) {
+        std::vector<LhEmuStream*> runnable;
+        for (auto* s : g_streams) if (head_runnable(s)) runnable.push_back(s);
+        if (runnable.empty()) return;
+        g_async_rng = g_async_rng * 6364136223846793005ull + 1442695040888963407ull;
+        exec_head(runnable[(g_async_rng >> 33) % runnable.size()]);
+    }
+}
+
+bool is_pinned_host(const void* p, size_t bytes)
+{
+    std::lock_guard<std::mutex> lock(g_alloc_mutex);
+    for (auto& kv : g_allocs)
+        if (kv.second.host && (const char*)p >= (const char*)kv.first && (const char*)p + bytes <= (const char*)kv.first + kv.second.bytes) return true;
+    return false;
+}
+bool is_device(const void* p)
+{
+    std::lock_guard<std::mutex> lock(g_alloc_mutex);
+    for (auto& kv : g_allocs)
+        if (!kv.second.host && (const char*)p >= (const char*)kv.first && (const char*)p < (const char*)kv.first + std::max<size_t>(kv.second.bytes, 1)) return true;
+    return false;
+}
+
+// enqueue fn on stream s (asynchronous modes) or run it now
+void submit(LhEmuStream* s, std::function<void()> fn)
+{
+    if (!g_async.load() || !s) { fn(); return; }
+    LhEmuOp op;
+    op.kind = LhEmuOp::RUN;
+    op.fn = std::move(fn);
+    s->q.push_back(std::move(op));
+    background_progress();
+}
+}  // namespace
 
 // ---------------------------------------------------------------------- device-side hooks
 extern "C" {
@@ -464,7 +605,17 @@ Pool* pool()
 
 }  // namespace
 
-void lh_emu_launch(dim3 grid, dim3 block, size_t smem_bytes, const std::function<void()>& body)
+static void launch_now(dim3 grid, dim3 block, size_t smem_bytes, const std::function<void()>& body);
+
+void lh_emu_launch(cudaStream_t stream, dim3 grid, dim3 block, size_t smem_bytes, std::function<void()> body)
+{
+    if (tl_self) die("kernel launch from inside a kernel");
+    if (!g_async.load()) { launch_now(grid, block, smem_bytes, body); return; }
+    std::lock_guard<std::recursive_mutex> lock(g_api);
+    submit(stream, [=]() { launch_now(grid, block, smem_bytes, body); });
+}
+
+static void launch_now(dim3 grid, dim3 block, size_t smem_bytes, const std::function<void()>& body)
 {
     if (tl_self) die("kernel launch from inside a kernel");
     const size_t nthreads = (size_t)block.x * block.y * block.z;
@@ -534,40 +685,129 @@ cudaError_t cudaGetDeviceProperties(cudaDeviceProp* p, int d)
     return cudaSuccess;
 }
 cudaError_t lh_emu_malloc(void** p, size_t bytes) { return guarded_alloc(p, bytes, false); }
-cudaError_t cudaFree(void* p) { return guarded_free(p, false); }
+cudaError_t cudaFree(void* p)
+{
+    if (g_async.load()) { std::lock_guard<std::recursive_mutex> lock(g_api); drain_all(); }    // cudaFree synchronises the device
+    return guarded_free(p, false);
+}
 cudaError_t lh_emu_malloc_host(void** p, size_t bytes) { return guarded_alloc(p, bytes, true); }
-cudaError_t cudaFreeHost(void* p) { return guarded_free(p, true); }
+cudaError_t cudaFreeHost(void* p)
+{
+    if (g_async.load()) { std::lock_guard<std::recursive_mutex> lock(g_api); drain_all(); }
+    return guarded_free(p, true);
+}
+// Blocking copies and memsets on the legacy default stream: the product's streams are cudaStreamNonBlocking, so these do NOT
+// wait for them — they happen now.
 cudaError_t cudaMemcpy(void* dst, const void* src, size_t bytes, cudaMemcpyKind) { memmove(dst, src, bytes); return cudaSuccess; }
-cudaError_t cudaMemcpyAsync(void* dst, const void* src, size_t bytes, cudaMemcpyKind, cudaStream_t) { memmove(dst, src, bytes); return cudaSuccess; }
-cudaError_t cudaMemcpy2DAsync(void* dst, size_t dpitch, const void* src, size_t spitch, size_t width, size_t height, cudaMemcpyKind, cudaStream_t)
+cudaError_t cudaMemset(void* p, int v, size_t bytes) { memset(p, v, bytes); return cudaSuccess; }
+
+static cudaError_t copy_async(cudaStream_t s, void* dst, size_t dpitch, const void* src, size_t spitch, size_t width, size_t height)
+{
+    auto body = [=]() { for (size_t r = 0; r < height; ++r) memmove((char*)dst + r * dpitch, (const char*)src + r * spitch, width); };
+    if (!g_async.load() || !s) { body(); return cudaSuccess; }
+    std::lock_guard<std::recursive_mutex> lock(g_api);
+    const size_t src_span = height ? (height - 1) * spitch + width : 0, dst_span = height ? (height - 1) * dpitch + width : 0;
+    const bool src_dev = is_device(src), dst_dev = is_device(dst);
+    if (!src_dev && !is_pinned_host(src, src_span)) {
+        // pageable source: the bytes are staged before the call returns — the caller may reuse the buffer at once
+        auto staged = std::make_shared<std::vector<char>>(height * width);
+        for (size_t r = 0; r < height; ++r) memcpy(staged->data() + r * width, (const char*)src + r * spitch, width);
+        submit(s, [=]() { for (size_t r = 0; r < height; ++r) memmove((char*)dst + r * dpitch, staged->data() + r * width, width); });
+        return cudaSuccess;
+    }
+    if (!dst_dev && !is_pinned_host(dst, dst_span)) {
+        // pageable destination: the call returns when the data has arrived, i.e. it waits for the stream up to this copy
+        drain_stream(s);
+        body();
+        return cudaSuccess;
+    }
+    submit(s, body);                                  // device <-> device, device <-> pinned host: truly asynchronous
+    return cudaSuccess;
+}
+cudaError_t cudaMemcpyAsync(void* dst, const void* src, size_t bytes, cudaMemcpyKind, cudaStream_t s) { return copy_async(s, dst, bytes, src, bytes, bytes, 1); }
+cudaError_t cudaMemcpy2DAsync(void* dst, size_t dpitch, const void* src, size_t spitch, size_t width, size_t height, cudaMemcpyKind, cudaStream_t s)
 {
     if (width > dpitch || width > spitch) return cudaErrorInvalidValue;
-    for (size_t r = 0; r < height; ++r) memmove((char*)dst + r * dpitch, (const char*)src + r * spitch, width);
-    return cudaSuccess;
+    return copy_async(s, dst, dpitch, src, spitch, width, height);
 }
-cudaError_t cudaMemset(void* p, int v, size_t bytes) { memset(p, v, bytes); return cudaSuccess; }
-cudaError_t cudaMemsetAsync(void* p, int v, size_t bytes, cudaStream_t) { memset(p, v, bytes); return cudaSuccess; }
-cudaError_t cudaStreamCreateWithFlags(cudaStream_t* s, unsigned) { *s = new LhEmuStream{tl_device}; return cudaSuccess; }
-cudaError_t cudaStreamDestroy(cudaStream_t s) { delete s; return cudaSuccess; }
-cudaError_t cudaStreamSynchronize(cudaStream_t) { return cudaSuccess; }
-cudaError_t cudaStreamWaitEvent(cudaStream_t, cudaEvent_t, unsigned) { return cudaSuccess; }
-cudaError_t cudaEventCreate(cudaEvent_t* e) { *e = new LhEmuEvent{0.0, false}; return cudaSuccess; }
-cudaError_t cudaEventCreateWithFlags(cudaEvent_t* e, unsigned) { return cudaEventCreate(e); }
-cudaError_t cudaEventDestroy(cudaEvent_t e) { delete e; return cudaSuccess; }
-cudaError_t cudaEventRecord(cudaEvent_t e, cudaStream_t)
+cudaError_t cudaMemsetAsync(void* p, int v, size_t bytes, cudaStream_t s)
 {
-    timespec ts;
-    clock_gettime(CLOCK_MONOTONIC, &ts);
-    e->t_ms = ts.tv_sec * 1e3 + ts.tv_nsec * 1e-6;
-    e->recorded = true;
+    if (!g_async.load() || !s) { memset(p, v, bytes); return cudaSuccess; }
+    std::lock_guard<std::recursive_mutex> lock(g_api);
+    submit(s, [=]() { memset(p, v, bytes); });
     return cudaSuccess;
 }
-cudaError_t cudaEventSynchronize(cudaEvent_t) { return cudaSuccess; }
+cudaError_t cudaStreamCreateWithFlags(cudaStream_t* s, unsigned)
+{
+    std::lock_guard<std::recursive_mutex> lock(g_api);
+    *s = new LhEmuStream();
+    (*s)->device = tl_device;
+    g_streams.push_back(*s);                          // streams are never freed: queued operations may outlive their handle
+    return cudaSuccess;
+}
+cudaError_t cudaStreamDestroy(cudaStream_t s)
+{
+    std::lock_guard<std::recursive_mutex> lock(g_api);
+    if (s) drain_stream(s);                           // CUDA lets the queued work finish; here it finishes now
+    return cudaSuccess;
+}
+cudaError_t cudaStreamSynchronize(cudaStream_t s)
+{
+    if (!g_async.load() || !s) return cudaSuccess;
+    std::lock_guard<std::recursive_mutex> lock(g_api);
+    drain_stream(s);
+    return cudaSuccess;
+}
+cudaError_t cudaStreamWaitEvent(cudaStream_t s, cudaEvent_t e, unsigned)
+{
+    if (!g_async.load() || !s) return cudaSuccess;
+    std::lock_guard<std::recursive_mutex> lock(g_api);
+    if (e->recorded == 0 || e->completed >= e->recorded) return cudaSuccess;      // never recorded, or already complete: no-op
+    LhEmuOp op;
+    op.kind = LhEmuOp::WAIT;
+    op.ev = e;
+    op.seq = e->recorded;                             // the most recent record at the time of THIS call
+    s->q.push_back(std::move(op));
+    return cudaSuccess;
+}
+cudaError_t cudaEventCreate(cudaEvent_t* e) { *e = new LhEmuEvent(); return cudaSuccess; }
+cudaError_t cudaEventCreateWithFlags(cudaEvent_t* e, unsigned) { return cudaEventCreate(e); }
+cudaError_t cudaEventDestroy(cudaEvent_t) { return cudaSuccess; }                  // leaked: a queued record / wait may still name it
+cudaError_t cudaEventRecord(cudaEvent_t e, cudaStream_t s)
+{
+    std::lock_guard<std::recursive_mutex> lock(g_api);
+    ++e->recorded;
+    if (!g_async.load() || !s) { e->completed = e->recorded; e->t_ms = now_ms(); return cudaSuccess; }
+    LhEmuOp op;
+    op.kind = LhEmuOp::RECORD;
+    op.ev = e;
+    op.seq = e->recorded;
+    e->where.emplace_back(op.seq, s);
+    s->q.push_back(std::move(op));
+    background_progress();
+    return cudaSuccess;
+}
+cudaError_t cudaEventSynchronize(cudaEvent_t e)
+{
+    if (!g_async.load()) return cudaSuccess;
+    std::lock_guard<std::recursive_mutex> lock(g_api);
+    const uint64_t want = e->recorded;
+    progress_until([&] { return e->completed >= want; }, nullptr, e, want);
+    return cudaSuccess;
+}
 cudaError_t cudaEventElapsedTime(float* ms, cudaEvent_t a, cudaEvent_t b)
 {
-    if (!a->recorded || !b->recorded) return cudaErrorInvalidValue;
+    std::lock_guard<std::recursive_mutex> lock(g_api);
+    if (a->recorded == 0 || b->recorded == 0 || a->completed < a->recorded || b->completed < b->recorded) return cudaErrorInvalidValue;
     *ms = (float)(b->t_ms - a->t_ms);
     return cudaSuccess;
+}
+int lh_emu_set_async(int mode, uint64_t seed)
+{
+    std::lock_guard<std::recursive_mutex> lock(g_api);
+    if (g_async.load()) drain_all();
+    g_async_rng = seed * 0x9e3779b97f4a7c15ull + 0x2545F4914F6CDD1Dull;
+    return g_async.exchange(mode < 0 || mode > 2 ? 0 : mode);
 }
 
 }  // extern "C"

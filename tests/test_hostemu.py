@@ -109,6 +109,35 @@ def test_kernels_are_schedule_and_copy_timing_independent_and_match_oracle(emu, 
     assert np.allclose(ref[2], o.budgets(), rtol=1e-12, atol=0.0)
 
 
+def test_schedule_and_copy_timing_fuzz_detects_a_missing_syncwarp():
+    """The test of the test for the kernel side: a MUTANT stage kernel without the __syncwarp() between cp.async.wait_group and
+    the reads of the ring (a lane reads values another lane's copy delivered).  One thread order happens to work — the mutant
+    would pass a plain parity run — but not all of them."""
+    mlib = hostemu.build_mutant(
+        "ring_read_without_syncwarp", "lh_stage_kernel.cuh",
+        "        lh_cp_wait<RING_DEPTH - 2>();\n        __syncwarp();\n",
+        "        lh_cp_wait<RING_DEPTH - 2>();\n")
+    lib, ctl = lh.SoilLibrary(mlib, "lh_"), hostemu.controls(mlib)
+    wl = w.coupled_workload(ncol=70, nlayer=64, seed=11)
+
+    def run(policy, seed, lazy):
+        ctl.lh_emu_set_schedule(policy, seed)
+        ctl.lh_emu_set_cp_async_lazy(lazy)
+        try:
+            g = lh.SoilContext(lib, wl.config(flags=STAGE))
+            wl.upload(g)
+            g.step(0.0, wl.dt, 2)
+            out = g.get_state(0)
+            g.close()
+            return out
+        finally:
+            ctl.lh_emu_set_schedule(0, 1)
+            ctl.lh_emu_set_cp_async_lazy(0)
+
+    runs = [run(p, s, z) for p, s, z in [(0, 1, 0), (0, 1, 1), (1, 1, 0), (1, 1, 1), (2, 7, 0), (2, 8, 1)]]
+    assert any(not np.array_equal(runs[0], r, equal_nan=True) for r in runs[1:])
+
+
 def test_launch_shapes_of_a_148_sm_device_are_the_ones_emulated(emu, knobs):
     """lh_choose_shape sees the 148 SMs of a B200 (so the chunking, block shapes and the persistent / per-stage choice are the
     GPU's), and a different SM count really changes the shape (the knob works)."""
@@ -146,6 +175,105 @@ def test_fresh_device_memory_is_poisoned_and_never_read(emu):
     ctx.step(0.0, wl.dt, 2)
     assert np.all(np.isfinite(ctx.get_state(0))) and np.all(np.isfinite(ctx.get_state(2)))
     assert np.all(np.isfinite(ctx.budgets()))
+
+
+def _async_scenario(emu, knobs, mode, seed):
+    """Uploads in three host layouts (dense, strided gather, column-fastest), a run with per-step budgets and overlapped
+    snapshots, a ticketed budget read with steps enqueued behind it, per-column parameters, a checkpoint round trip, downloads."""
+    knobs.lh_emu_set_async(mode, seed)
+    try:
+        wl = w.coupled_workload(ncol=300, nlayer=24, seed=7)
+        g = lh.SoilContext(emu, wl.config(flags=STAGE))
+        wl.upload(g)
+        wide = np.zeros((300, 48))
+        wide[:, ::2] = wl.fields[0]
+        g.set_state(0, wide[:, ::2])                                  # layer stride 2: gathered through the pinned staging blocks
+        soa = np.ascontiguousarray(wl.fields[2].T)
+        g.set_state(2, soa.T)                                         # column-fastest host block: the 2-D copy path
+        bud, snaps = g.run(0.0, wl.dt, 5, budget_every=1, save_every=2, save_first=True, save_fields=(0, 2))
+        ticket = g.budgets_async()
+        g.step(5 * wl.dt, wl.dt, 2)
+        b2 = g.budgets_wait(ticket)
+        g.set_column_params(Ksat=wl.params.Ksat * np.linspace(0.5, 2.0, 300))
+        g.step(7 * wl.dt, wl.dt, 1)
+        ck = g.checkpoint()
+        g.step(8 * wl.dt, wl.dt, 2)
+        after = g.get_state(0)
+        g.restore(ck)
+        g.step(8 * wl.dt, wl.dt, 2)
+        out = (g.get_state(0), g.get_state(2), bud, snaps, b2, after, g.budgets())
+        g.close()
+        return out
+    finally:
+        knobs.lh_emu_set_async(0, 1)
+
+
+def test_stream_and_event_dependencies_are_complete(emu, knobs, monkeypatch):
+    """The host layer overlaps PCIe copies, layout transposes, snapshots and steps on two streams per context.  Under the
+    emulator's asynchronous modes nothing runs until a synchronisation forces it, and then either only what that synchronisation
+    needs (lazy) or a seeded random interleaving of everything runnable: a missing event wait or a staging block reused too early
+    gives different bits.  LH_STAGE_BLOCK_BYTES = 4096 pushes ten staging blocks per field through the two-buffer pipelines."""
+    monkeypatch.setenv("LH_STAGE_BLOCK_BYTES", "4096")                # read by the library when a ctx first needs its staging blocks
+    ref = _async_scenario(emu, knobs, 0, 1)
+    assert np.array_equal(ref[0], ref[5])                             # restart == uninterrupted, bit for bit
+    for mode, seed in [(1, 1), (2, 1), (2, 2), (2, 3)]:
+        got = _async_scenario(emu, knobs, mode, seed)
+        for a, b in zip(ref, got):
+            assert np.array_equal(a, b), (mode, seed)
+
+
+def test_asynchronous_modes_detect_a_missing_event_wait(monkeypatch):
+    """The test of the test: a MUTANT of the product in which the layout transpose of an upload no longer waits for its H2D copy
+    (one cudaStreamWaitEvent removed from upload_field).  Synchronously executed it computes the right answer — exactly why such
+    a bug survives ordinary tests; under deferred execution it does not."""
+    mlib = hostemu.build_mutant(
+        "upload_transpose_without_copy_wait", "lh_soil_api.cu",
+        "        LH_CUDA(c, cudaStreamWaitEvent(c->stream, c->ev_copy[k], 0));\n        LH_CUDA(c, lh_launch_to_soa(",
+        "        LH_CUDA(c, lh_launch_to_soa(")
+    monkeypatch.setenv("LH_STAGE_BLOCK_BYTES", "4096")
+    lib, ctl = lh.SoilLibrary(mlib, "lh_"), hostemu.controls(mlib)
+    wl = w.coupled_workload(ncol=300, nlayer=24, seed=7)
+
+    def run(mode, seed):
+        ctl.lh_emu_set_async(mode, seed)
+        try:
+            g = lh.SoilContext(lib, wl.config())
+            wl.upload(g)
+            g.step(0.0, wl.dt, 2)
+            out = g.get_state(0)
+            g.close()
+            return out
+        finally:
+            ctl.lh_emu_set_async(0, 1)
+
+    ref = run(0, 1)
+    o = lh.SoilContext(w.oracle_library(), wl.config())
+    wl.upload(o)
+    o.step(0.0, wl.dt, 2)
+    assert np.max(np.abs(ref - o.get_state(0))) <= 1e-10 * np.max(np.abs(ref))       # the mutant passes a synchronous parity test
+    assert not np.array_equal(run(1, 1), ref)                                         # lazy execution exposes it
+    assert any(not np.array_equal(run(2, s), ref) for s in (1, 2, 3, 4))              # and so does random interleaving
+
+
+def test_deferred_execution_is_real_and_the_raw_pointer_rule_holds(emu, knobs):
+    """Negative control for the test above, and the documented rule of lh_soil_device_ptr (include/lh_soil.h): lh_soil_set_state
+    returns when the host buffer is free, the layout transform may still be queued on the ctx stream.  In lazy mode the raw
+    pointer really shows the old contents until lh_soil_sync — so the asynchronous modes do defer work."""
+    import ctypes as C
+
+    wl = w.coupled_workload(ncol=64, nlayer=8, seed=7, zlim=(-0.8, 0.0))
+    knobs.lh_emu_set_async(1, 1)
+    try:
+        g = lh.SoilContext(emu, wl.config())
+        g.set_state(2, wl.fields[2])
+        ptr, ncp = g.device_ptr(2)
+        view = lambda: np.ctypeslib.as_array(C.cast(ptr, C.POINTER(C.c_double)), shape=(8, ncp))[:, :64].T.copy()
+        assert not np.array_equal(view(), wl.fields[2])
+        g.sync()
+        assert np.array_equal(view(), wl.fields[2])
+        g.close()
+    finally:
+        knobs.lh_emu_set_async(0, 1)
 
 
 def test_contexts_on_concurrent_host_threads(emu):
