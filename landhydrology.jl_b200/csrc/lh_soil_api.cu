@@ -133,6 +133,7 @@ struct lh_soil_ctx {
     int64_t hist_cap = 0;
     double* snap_dev[2][LH_NUM_FIELDS] = {{nullptr, nullptr, nullptr, nullptr}, {nullptr, nullptr, nullptr, nullptr}};
     cudaEvent_t ev_snap_ready[2] = {nullptr, nullptr}, ev_snap_done[2] = {nullptr, nullptr};
+    cudaEvent_t ev_hist = nullptr;               // lh_soil_run: a step's budgets are in the history buffer (the copy stream waits for it)
     double* bc_dev = nullptr;                    // boundary-value table of a persistent launch
     int64_t bc_dev_steps = 0;
     unsigned long long* nonfinite_dev = nullptr;
@@ -216,6 +217,7 @@ void free_all(lh_soil_ctx* c)
     for (auto& b : c->snap_dev) for (auto& p : b) if (p) cudaFree(p);
     for (auto& e : c->ev_snap_ready) if (e) cudaEventDestroy(e);
     for (auto& e : c->ev_snap_done) if (e) cudaEventDestroy(e);
+    if (c->ev_hist) cudaEventDestroy(c->ev_hist);
     if (c->fused_partials) cudaFree(c->fused_partials);
     if (c->colp_dev) cudaFree(c->colp_dev);
     if (c->cellp_dev) cudaFree(c->cellp_dev);
@@ -529,7 +531,7 @@ int lh_bytes_on_wire(const lh_soil_ctx* c)
 extern "C" {
 
 static bool use_persistent(const lh_soil_ctx* c);
-static int32_t local_budgets(lh_soil_ctx* c);
+static int32_t local_budgets(lh_soil_ctx* c, double* out_dev = nullptr);
 static int32_t apply_aux_tables(lh_soil_ctx* c);
 
 int32_t lh_soil_abi_version(void) { return LH_SOIL_ABI_VERSION; }
@@ -976,11 +978,14 @@ static int32_t apply_aux_tables(lh_soil_ctx* c)
 }
 
 // nsteps SSPRK33 steps enqueued on the ctx stream (no timing events, no synchronisation).
-static int32_t advance_ssprk33(lh_soil_ctx* c, double dt, int64_t nsteps, const double* bc_table, int64_t* launches_out)
+// bc_dev_ready: the rows of bc_table for these steps are already in device memory there (lh_soil_run uploads the table of the
+// whole run once; bc_table itself is still needed for the boundary values the ctx keeps after the call).
+static int32_t advance_ssprk33(lh_soil_ctx* c, double dt, int64_t nsteps, const double* bc_table, int64_t* launches_out,
+                               const double* bc_dev_ready = nullptr)
 {
     const bool tables = has_aux_table(c);
     const bool persistent = use_persistent(c) && nsteps > 0 && !tables;
-    if (persistent && bc_table) {
+    if (persistent && bc_table && !bc_dev_ready) {
         if (c->bc_dev_steps < nsteps) {
             if (c->bc_dev) { LH_CUDA(c, cudaFree(c->bc_dev)); c->bc_dev = nullptr; c->bc_dev_steps = 0; }
             LH_CUDA(c, cudaMalloc(&c->bc_dev, (size_t)nsteps * 12 * sizeof(double)));
@@ -996,7 +1001,7 @@ static int32_t advance_ssprk33(lh_soil_ctx* c, double dt, int64_t nsteps, const 
             LhKernelArgs a;
             fill_args(c, 1, dt, a);
             a.nsteps = std::min<int64_t>(MAX_STEPS_PER_LAUNCH, nsteps - s0);
-            a.bc_dev = bc_table ? c->bc_dev + s0 * 12 : nullptr;
+            a.bc_dev = bc_table ? (bc_dev_ready ? bc_dev_ready : c->bc_dev) + s0 * 12 : nullptr;
             LH_CUDA(c, lh_launch_ssprk33_persistent(c->model, c->kernel_flags, a, c->shape, c->stream));
             ++launches;
         }
@@ -1115,6 +1120,7 @@ int32_t lh_soil_run(lh_soil_ctx* c, double t0, double dt, int64_t nsteps, const 
         LH_CUDA(c, cudaMallocHost(&c->hist_host, (size_t)nb * 2 * sizeof(double)));
         c->hist_cap = nb;
     }
+    if (nb > 0 && !c->ev_hist) LH_CUDA(c, cudaEventCreateWithFlags(&c->ev_hist, cudaEventDisableTiming));
     if (saving) {
         if ((st = ensure_staging(c)) != LH_OK) return st;
         for (int b = 0; b < 2; ++b) {
@@ -1148,6 +1154,19 @@ int32_t lh_soil_run(lh_soil_ctx* c, double t0, double dt, int64_t nsteps, const 
         return LH_OK;
     };
 
+    // Persistent launches read their boundary values from device memory.  The table of the WHOLE run goes up once, before the
+    // first step: uploaded per advance call (every step when the budgets are read every step) each cudaMemcpyAsync from the
+    // caller's pageable table would first synchronise the ctx stream — the host would block once per step, and the copy would
+    // queue behind other contexts' transfers.
+    const bool table_on_device = o->bc_table && nsteps > 0 && use_persistent(c) && !has_aux_table(c);
+    if (table_on_device) {
+        if (c->bc_dev_steps < nsteps) {
+            if (c->bc_dev) { LH_CUDA(c, cudaFree(c->bc_dev)); c->bc_dev = nullptr; c->bc_dev_steps = 0; }
+            LH_CUDA(c, cudaMalloc(&c->bc_dev, (size_t)nsteps * 12 * sizeof(double)));
+            c->bc_dev_steps = nsteps;
+        }
+        LH_CUDA(c, cudaMemcpyAsync(c->bc_dev, o->bc_table, (size_t)nsteps * 12 * sizeof(double), cudaMemcpyHostToDevice, c->stream));
+    }
     LH_CUDA(c, cudaEventRecord(c->ev_start, c->stream));
     int64_t launches = 0, done = 0, nbud = 0;
     if (o->save_first && (st = snapshot()) != LH_OK) return st;
@@ -1155,12 +1174,18 @@ int32_t lh_soil_run(lh_soil_ctx* c, double t0, double dt, int64_t nsteps, const 
         int64_t n = nsteps - done;
         if (o->budget_every > 0) n = std::min<int64_t>(n, o->budget_every - done % o->budget_every);
         if (o->save_every > 0) n = std::min<int64_t>(n, o->save_every - done % o->save_every);
-        if ((st = advance_ssprk33(c, dt, n, o->bc_table ? o->bc_table + done * 12 : nullptr, &launches)) != LH_OK) return st;
+        if ((st = advance_ssprk33(c, dt, n, o->bc_table ? o->bc_table + done * 12 : nullptr, &launches,
+                                  table_on_device ? c->bc_dev + done * 12 : nullptr)) != LH_OK) return st;
         done += n;
         if (o->budget_every > 0 && done % o->budget_every == 0) {
-            if ((st = local_budgets(c)) != LH_OK) return st;
-            LH_CUDA(c, cudaMemcpyAsync(c->hist_dev + 2 * nbud, c->budget_dev, 2 * sizeof(double), cudaMemcpyDeviceToDevice, c->stream));
-            LH_CUDA(c, cudaMemcpyAsync(c->hist_host + 2 * nbud, c->hist_dev + 2 * nbud, 2 * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+            // The reduction writes this step's pair straight into its own slot of the history buffer, and the 16-byte D2H read
+            // of it goes to the COPY stream behind an event: nothing the compute stream has to wait for ever sits in a copy
+            // engine's queue — with other contexts' 32 MiB transfers ahead of it there, a per-step copy on the compute
+            // stream would stall the next step's launches for the length of a transfer block.
+            if ((st = local_budgets(c, c->hist_dev + 2 * nbud)) != LH_OK) return st;
+            LH_CUDA(c, cudaEventRecord(c->ev_hist, c->stream));
+            LH_CUDA(c, cudaStreamWaitEvent(c->copy_stream, c->ev_hist, 0));
+            LH_CUDA(c, cudaMemcpyAsync(c->hist_host + 2 * nbud, c->hist_dev + 2 * nbud, 2 * sizeof(double), cudaMemcpyDeviceToHost, c->copy_stream));
             ++nbud;
         }
         if (o->save_every > 0 && done % o->save_every == 0 && (st = snapshot()) != LH_OK) return st;
@@ -1367,16 +1392,17 @@ int32_t lh_soil_step(lh_soil_ctx* c, const lh_soil_stepper* sp, double t, double
 // Local budgets into c->budget_dev[0..1].  Right after a step the last-stage launches have already summed, per block,
 // the values they wrote (fused epilogue): only the fixed-shape reduction over the blocks is left.  Otherwise (fresh
 // upload, generic stepper, heat-only model whose ϑ_l is prescribed, raw device pointer handed out) one pass over the state.
-static int32_t local_budgets(lh_soil_ctx* c)
+static int32_t local_budgets(lh_soil_ctx* c, double* out_dev)
 {
+    if (!out_dev) out_dev = c->budget_dev;           // lh_soil_run passes the step's own slot of its history buffer
     const bool fused = c->budget_fresh && !c->external_writes && c->fused_partials && has_water(c->model);
     if (fused) {
-        LH_CUDA(c, lh_launch_budgets_from_partials(c->fused_partials, c->shape.nblocks, c->dp.dz, c->budget_dev, c->stream));
+        LH_CUDA(c, lh_launch_budgets_from_partials(c->fused_partials, c->shape.nblocks, c->dp.dz, out_dev, c->stream));
         return LH_OK;
     }
     const double* re = c->U[2] ? c->U[2] : c->U[1];   // no energy model: E budget of θ_i slot is meaningless -> report 0
     LH_CUDA(c, lh_launch_budgets(c->U[0], re, c->ncol, c->ncol_pad, c->nlayer, c->dp.dz, c->partials,
-                                 c->npartials, c->budget_dev, c->stream));
+                                 c->npartials, out_dev, c->stream));
     return LH_OK;
 }
 

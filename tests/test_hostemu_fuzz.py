@@ -163,7 +163,12 @@ def _sequence(rng, wl, g, o, nops):
             se = int(rng.choice([0, 1, 3]))
             first = bool(rng.random() < 0.5)
             fields = list(_prognostic(wl))
-            out = [c.run(t, wl.dt, k, budget_every=be, save_every=se, save_first=first, save_fields=fields if (se or first) else ()) for c in both]
+            table = None
+            if rng.random() < 0.5:                    # a boundary-value table: read from device memory by the persistent launches
+                vals = np.array([wl.top[1], wl.top[3], wl.bottom[1], wl.bottom[3]])
+                table = np.broadcast_to(vals, (k, 3, 4)) * (1.0 + 1e-3 * rng.standard_normal((k, 3, 4)))
+            out = [c.run(t, wl.dt, k, bc_table=table, budget_every=be, save_every=se, save_first=first,
+                         save_fields=fields if (se or first) else ()) for c in both]
             t += k * wl.dt
             (bg, sg), (bo, so) = out
             if be:
