@@ -502,7 +502,12 @@ def _main(args, result_stream):
             c0, c1 = cuts[k], cuts[k + 1]
             sub = ctx if S == 1 else lh.SoilContext(lib, wl.config(ncol=c1 - c0, flags=flags))
             if S > 1:
-                sub.set_state(1, host[1][c0:c1])               # untimed: first-use allocation of the ctx's staging buffers
+                # untimed warm-up of the shard's ctx: first-use allocations (staging blocks, the pinned budget history of
+                # lh_soil_run, events) must not sit inside the timed region, which starts by uploading the state again
+                for fid, a in host.items():
+                    sub.set_state(fid, a[c0:c1])
+                sub.run(0.0, wl.dt, K, bc_table=table_K, budget_every=1)
+                sub.sync()
             subs.append((sub, c0, c1))
 
         # Uploads (and downloads) of the shards take turns on the PCIe link in shard order, so shard k computes while
