@@ -79,6 +79,7 @@ struct lh_soil_ctx {
     LhDevParams dp;
     LhLaunchShape shape;
     cudaStream_t stream = nullptr, copy_stream = nullptr;
+    cudaStream_t flag_stream = nullptr;          // small read-backs that must neither wait in front of kernels nor in front of uploads
     cudaEvent_t ev_start = nullptr, ev_stop = nullptr, ev_copy[2] = {nullptr, nullptr}, ev_xpose[2] = {nullptr, nullptr};
     double* U[LH_NUM_FIELDS] = {nullptr, nullptr, nullptr, nullptr};   // ϑ_l, θ_i, ρe_int, T
     double* V[3] = {nullptr, nullptr, nullptr};                        // stage buffer (ϑ_l, -, ρe_int)
@@ -141,6 +142,12 @@ struct lh_soil_ctx {
     ncclComm_t_ comm = nullptr;
     int nranks = 1, rank = 0;
     bool has_ice = false;        // some θ_i != 0 (θ_i is constant in time: dθ_i ≡ 0), re-evaluated on every θ_i upload
+    // The answer to "any ice?" after a θ_i upload is fetched lazily: the upload only enqueues the scan and a 4-byte read into
+    // pinned memory (its own stream, behind an event); the first call that needs the kernel variant waits for it (resolve_ice).
+    int* ice_flag_dev = nullptr;
+    int* ice_flag_host = nullptr;                // pinned
+    cudaEvent_t ev_ice_scan = nullptr, ev_ice = nullptr;
+    bool ice_pending = false;
     int kernel_flags = 0;        // LH_FLAG_ICE | LH_FLAG_GEN | LH_FLAG_VG2 -> compiled kernel variant
     bool force_general_vg = false;   // LH_FLAG_GENERAL_VG: never take the n == 2 shortcut (benchmark the general path)
     bool timing_valid = false;
@@ -166,6 +173,13 @@ int32_t fail(lh_soil_ctx* ctx, int32_t code, const char* fmt, ...)
         cudaError_t e_ = (expr);                                                                    \
         if (e_ != cudaSuccess)                                                                      \
             return fail(ctx, LH_ERR_CUDA, "%s failed: %s (%s:%d)", #expr, cudaGetErrorString(e_), __FILE__, __LINE__); \
+    } while (0)
+
+int32_t resolve_ice(lh_soil_ctx* c);
+#define LH_RESOLVE(ctx)                                                                             \
+    do {                                                                                            \
+        int32_t r_ = resolve_ice(ctx);                                                              \
+        if (r_ != LH_OK) return r_;                                                                 \
     } while (0)
 
 bool has_water(int m) { return m == LH_MODEL_RICHARDS || m == LH_MODEL_COUPLED; }
@@ -218,6 +232,10 @@ void free_all(lh_soil_ctx* c)
     for (auto& e : c->ev_snap_ready) if (e) cudaEventDestroy(e);
     for (auto& e : c->ev_snap_done) if (e) cudaEventDestroy(e);
     if (c->ev_hist) cudaEventDestroy(c->ev_hist);
+    if (c->ice_flag_dev) cudaFree(c->ice_flag_dev);
+    if (c->ice_flag_host) cudaFreeHost(c->ice_flag_host);
+    if (c->ev_ice_scan) cudaEventDestroy(c->ev_ice_scan);
+    if (c->ev_ice) cudaEventDestroy(c->ev_ice);
     if (c->fused_partials) cudaFree(c->fused_partials);
     if (c->colp_dev) cudaFree(c->colp_dev);
     if (c->cellp_dev) cudaFree(c->cellp_dev);
@@ -230,6 +248,7 @@ void free_all(lh_soil_ctx* c)
     for (auto& e : c->ev_xpose) if (e) cudaEventDestroy(e);
     if (c->stream) cudaStreamDestroy(c->stream);
     if (c->copy_stream) cudaStreamDestroy(c->copy_stream);
+    if (c->flag_stream) cudaStreamDestroy(c->flag_stream);
     delete c;
 }
 
@@ -410,17 +429,35 @@ void update_kernel_flags(lh_soil_ctx* c)
     }
 }
 
-// θ_i was (re)written: is there any ice?  One pass over the field; θ_i never changes afterwards.
+// The pending answer of the last θ_i scan, if any: wait for it and select the kernel variant.  Called at the top of every entry
+// point that launches kernels, reports the variant or changes what selects it.
+int32_t resolve_ice(lh_soil_ctx* c)
+{
+    if (!c->ice_pending) return LH_OK;
+    LH_CUDA(c, cudaSetDevice(c->device));
+    LH_CUDA(c, cudaEventSynchronize(c->ev_ice));
+    c->ice_pending = false;
+    c->has_ice = *c->ice_flag_host != 0 || c->theta_i_ptr_out;   // a caller holding the raw θ_i pointer may write ice at any time
+    update_kernel_flags(c);
+    return LH_OK;
+}
+
+// θ_i was (re)written: is there any ice?  One pass over the field; θ_i never changes afterwards.  Only ENQUEUED here — an upload
+// must not drain the ctx stream (the next field's H2D copy, or another shard's, is waiting for the PCIe link), and the 4-byte
+// answer must not sit in front of this stream's kernels in a copy engine's queue, nor in front of the next field's H2D copies on
+// the copy stream: it travels on a stream of its own.
 int32_t detect_ice(lh_soil_ctx* c)
 {
-    int* flag = (int*)c->nonfinite_dev;
-    LH_CUDA(c, cudaMemsetAsync(flag, 0, sizeof(int), c->stream));
-    LH_CUDA(c, lh_launch_any_nonzero(c->U[1], (int64_t)c->ncol_pad * c->nlayer, flag, c->stream));
-    int h = 0;
-    LH_CUDA(c, cudaMemcpyAsync(&h, flag, sizeof h, cudaMemcpyDeviceToHost, c->stream));
-    LH_CUDA(c, cudaStreamSynchronize(c->stream));
-    c->has_ice = h != 0 || c->theta_i_ptr_out;   // a caller holding the raw θ_i pointer may write ice at any time
-    update_kernel_flags(c);
+    int32_t st = resolve_ice(c);                 // two θ_i uploads in a row: the first answer is consumed before its slot is reused
+    if (st != LH_OK) return st;
+    LH_CUDA(c, cudaMemsetAsync(c->ice_flag_dev, 0, sizeof(int), c->stream));
+    LH_CUDA(c, lh_launch_any_nonzero(c->U[1], (int64_t)c->ncol_pad * c->nlayer, c->ice_flag_dev, c->stream));
+    LH_CUDA(c, cudaEventRecord(c->ev_ice_scan, c->stream));
+    LH_CUDA(c, cudaStreamWaitEvent(c->flag_stream, c->ev_ice_scan, 0));
+    LH_CUDA(c, cudaMemcpyAsync(c->ice_flag_host, c->ice_flag_dev, sizeof(int), cudaMemcpyDeviceToHost, c->flag_stream));
+    LH_CUDA(c, cudaEventRecord(c->ev_ice, c->flag_stream));
+    c->ice_pending = true;
+    c->budget_fresh = false;
     return LH_OK;
 }
 
@@ -594,6 +631,7 @@ int32_t lh_soil_create(const lh_soil_config* cfg, lh_soil_ctx** out)
     c->sm_count = prop.multiProcessorCount;
     LH_CREATE_CUDA(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
     LH_CREATE_CUDA(cudaStreamCreateWithFlags(&c->copy_stream, cudaStreamNonBlocking));
+    LH_CREATE_CUDA(cudaStreamCreateWithFlags(&c->flag_stream, cudaStreamNonBlocking));
     LH_CREATE_CUDA(cudaEventCreate(&c->ev_start));
     LH_CREATE_CUDA(cudaEventCreate(&c->ev_stop));
     for (int k = 0; k < 2; ++k) {
@@ -642,6 +680,10 @@ int32_t lh_soil_create(const lh_soil_config* cfg, lh_soil_ctx** out)
     LH_CREATE_CUDA(cudaMalloc(&c->partials, 2 * c->npartials * sizeof(double)));
     LH_CREATE_CUDA(cudaMalloc(&c->budget_dev, 4 * sizeof(double)));
     LH_CREATE_CUDA(cudaMalloc(&c->nonfinite_dev, sizeof(unsigned long long)));
+    LH_CREATE_CUDA(cudaMalloc(&c->ice_flag_dev, sizeof(int)));
+    LH_CREATE_CUDA(cudaMallocHost(&c->ice_flag_host, sizeof(int)));
+    LH_CREATE_CUDA(cudaEventCreateWithFlags(&c->ev_ice_scan, cudaEventDisableTiming));
+    LH_CREATE_CUDA(cudaEventCreateWithFlags(&c->ev_ice, cudaEventDisableTiming));
     LH_CREATE_CUDA(cudaStreamSynchronize(c->stream));
 #undef LH_CREATE_CUDA
     *out = c;
@@ -689,6 +731,7 @@ int32_t lh_soil_get_state(lh_soil_ctx* c, int32_t field, double* host, int64_t c
 // per-column arrays, and upload the table the HET / HETH kernels read per lane.
 static int32_t rebuild_column_params(lh_soil_ctx* c)
 {
+    LH_RESOLVE(c);
     LH_CUDA(c, cudaSetDevice(c->device));
     LH_CUDA(c, cudaStreamSynchronize(c->stream));
     bool any = false, heat = false, cells = false;
@@ -815,6 +858,7 @@ int32_t lh_soil_set_column_heat_params(lh_soil_ctx* c, const double* rho_c_ds, c
 int32_t lh_soil_set_column_fluxes(lh_soil_ctx* c, const double* const values[4])
 {
     if (!c) return LH_ERR_INVALID_ARG;
+    LH_RESOLVE(c);
     const int kinds[4] = {c->cfg.top.energy_kind, c->cfg.top.hydrology_kind, c->cfg.bottom.energy_kind, c->cfg.bottom.hydrology_kind};
     for (int k = 0; k < 4; ++k)
         if (values && values[k] && kinds[k] != LH_BC_FLUX) return fail(c, LH_ERR_INVALID_ARG, "per-column fluxes need a face of kind LH_BC_FLUX (boundary value %d is of kind %d)", k, kinds[k]);
@@ -836,6 +880,7 @@ int32_t lh_soil_set_column_fluxes(lh_soil_ctx* c, const double* const values[4])
 int32_t lh_soil_set_atmos_forcing(lh_soil_ctx* c, const lh_soil_atmos* a)
 {
     if (!c) return LH_ERR_INVALID_ARG;
+    LH_RESOLVE(c);
     if (!a) { c->atmos_on = false; return LH_OK; }
     if (a->struct_size != (int32_t)sizeof(lh_soil_atmos)) return fail(c, LH_ERR_INVALID_ARG, "lh_soil_atmos.struct_size mismatch");
     if (c->model != LH_MODEL_COUPLED)           // boundary_conditions.jl:103-112: both components must be prognostic
@@ -858,6 +903,7 @@ int32_t lh_soil_set_atmos_forcing(lh_soil_ctx* c, const lh_soil_atmos* a)
 int32_t lh_soil_atmos_fluxes(lh_soil_ctx* c, const double* th, const double* ti, const double* T, int64_t n, double* heat, double* water)
 {
     if (!c || !th || !ti || !T || !heat || !water || n < 0) return LH_ERR_INVALID_ARG;
+    LH_RESOLVE(c);
     if (!c->atmos_on) return fail(c, LH_ERR_STATE, "lh_soil_set_atmos_forcing has not been called");
     if (n == 0) return LH_OK;
     LH_CUDA(c, cudaSetDevice(c->device));
@@ -894,6 +940,7 @@ int32_t lh_soil_rhs(lh_soil_ctx* c, double t)
 {
     (void)t;
     if (!c) return LH_ERR_INVALID_ARG;
+    LH_RESOLVE(c);
     LH_CUDA(c, cudaSetDevice(c->device));
     const size_t fb = field_bytes(c);
     if (has_water(c->model) && !c->tend[0]) LH_CUDA(c, cudaMalloc(&c->tend[0], fb));
@@ -933,6 +980,7 @@ int32_t lh_soil_get_tendency(lh_soil_ctx* c, int32_t field, double* host, int64_
 int32_t lh_soil_stage_ssprk33(lh_soil_ctx* c, int32_t stage, double dt)
 {
     if (!c) return LH_ERR_INVALID_ARG;
+    LH_RESOLVE(c);
     if (stage < 1 || stage > 3) return fail(c, LH_ERR_INVALID_ARG, "stage must be 1, 2 or 3");
     LH_CUDA(c, cudaSetDevice(c->device));
     int32_t st = apply_aux_tables(c);
@@ -1026,6 +1074,7 @@ int32_t lh_soil_step_ssprk33(lh_soil_ctx* c, double t, double dt, int64_t nsteps
 {
     (void)t;
     if (!c) return LH_ERR_INVALID_ARG;
+    LH_RESOLVE(c);
     if (nsteps < 0) return fail(c, LH_ERR_INVALID_ARG, "nsteps < 0");
     LH_CUDA(c, cudaSetDevice(c->device));
     LH_CUDA(c, cudaEventRecord(c->ev_start, c->stream));
@@ -1042,6 +1091,7 @@ int32_t lh_soil_step_ssprk33(lh_soil_ctx* c, double t, double dt, int64_t nsteps
 int32_t lh_soil_set_aux_table(lh_soil_ctx* c, int32_t field, const double* table, int64_t nrows)
 {
     if (!c) return LH_ERR_INVALID_ARG;
+    LH_RESOLVE(c);
     if (!field_ok(field) || !c->U[field]) return fail(c, LH_ERR_INVALID_ARG, "field %d does not exist for model kind %d", field, c->model);
     const bool prescribed = (c->model == LH_MODEL_RICHARDS && field == LH_FIELD_T) ||
                             (c->model == LH_MODEL_HEAT && (field == LH_FIELD_THETA_L || field == LH_FIELD_THETA_I));
@@ -1096,6 +1146,7 @@ int32_t lh_soil_run(lh_soil_ctx* c, double t0, double dt, int64_t nsteps, const 
 {
     (void)t0;
     if (!c || !o) return LH_ERR_INVALID_ARG;
+    LH_RESOLVE(c);
     if (o->struct_size != (int32_t)sizeof(lh_soil_run_opts)) return fail(c, LH_ERR_INVALID_ARG, "lh_soil_run_opts.struct_size mismatch");
     if (nsteps < 0 || o->budget_every < 0 || o->save_every < 0) return fail(c, LH_ERR_INVALID_ARG, "negative step count or cadence");
     if (o->budget_every > 0 && !o->budgets_out) return fail(c, LH_ERR_INVALID_ARG, "budget_every > 0 needs budgets_out");
@@ -1179,13 +1230,13 @@ int32_t lh_soil_run(lh_soil_ctx* c, double t0, double dt, int64_t nsteps, const 
         done += n;
         if (o->budget_every > 0 && done % o->budget_every == 0) {
             // The reduction writes this step's pair straight into its own slot of the history buffer, and the 16-byte D2H read
-            // of it goes to the COPY stream behind an event: nothing the compute stream has to wait for ever sits in a copy
+            // of it goes to the small-read-back stream behind an event: nothing the compute stream has to wait for ever sits in a copy
             // engine's queue — with other contexts' 32 MiB transfers ahead of it there, a per-step copy on the compute
             // stream would stall the next step's launches for the length of a transfer block.
             if ((st = local_budgets(c, c->hist_dev + 2 * nbud)) != LH_OK) return st;
             LH_CUDA(c, cudaEventRecord(c->ev_hist, c->stream));
-            LH_CUDA(c, cudaStreamWaitEvent(c->copy_stream, c->ev_hist, 0));
-            LH_CUDA(c, cudaMemcpyAsync(c->hist_host + 2 * nbud, c->hist_dev + 2 * nbud, 2 * sizeof(double), cudaMemcpyDeviceToHost, c->copy_stream));
+            LH_CUDA(c, cudaStreamWaitEvent(c->flag_stream, c->ev_hist, 0));
+            LH_CUDA(c, cudaMemcpyAsync(c->hist_host + 2 * nbud, c->hist_dev + 2 * nbud, 2 * sizeof(double), cudaMemcpyDeviceToHost, c->flag_stream));
             ++nbud;
         }
         if (o->save_every > 0 && done % o->save_every == 0 && (st = snapshot()) != LH_OK) return st;
@@ -1195,6 +1246,7 @@ int32_t lh_soil_run(lh_soil_ctx* c, double t0, double dt, int64_t nsteps, const 
     c->last_launches = launches;
     LH_CUDA(c, cudaStreamSynchronize(c->stream));
     LH_CUDA(c, cudaStreamSynchronize(c->copy_stream));
+    LH_CUDA(c, cudaStreamSynchronize(c->flag_stream));
     for (int64_t k = 0; k < nbud; ++k) {
         o->budgets_out[2 * k] = c->hist_host[2 * k];
         o->budgets_out[2 * k + 1] = c->U[2] ? c->hist_host[2 * k + 1] : 0.0;
@@ -1228,6 +1280,7 @@ int64_t lh_soil_checkpoint_bytes(const lh_soil_ctx* c)
 int32_t lh_soil_checkpoint_save(lh_soil_ctx* c, void* buf, int64_t cap)
 {
     if (!c || !buf) return LH_ERR_INVALID_ARG;
+    LH_RESOLVE(c);
     if (cap < lh_soil_checkpoint_bytes(c)) return fail(c, LH_ERR_INVALID_ARG, "checkpoint buffer too small (%lld < %lld bytes)", (long long)cap, (long long)lh_soil_checkpoint_bytes(c));
     LH_CUDA(c, cudaSetDevice(c->device));
     LhCheckpointHeader h;
@@ -1250,6 +1303,7 @@ int32_t lh_soil_checkpoint_save(lh_soil_ctx* c, void* buf, int64_t cap)
 int32_t lh_soil_checkpoint_load(lh_soil_ctx* c, const void* buf, int64_t bytes)
 {
     if (!c || !buf) return LH_ERR_INVALID_ARG;
+    LH_RESOLVE(c);
     LhCheckpointHeader h;
     if (bytes < (int64_t)sizeof h) return fail(c, LH_ERR_INVALID_ARG, "checkpoint truncated");
     memcpy(&h, buf, sizeof h);
@@ -1341,6 +1395,7 @@ int32_t lh_soil_step(lh_soil_ctx* c, const lh_soil_stepper* sp, double t, double
 {
     (void)t;
     if (!c || !sp) return LH_ERR_INVALID_ARG;
+    LH_RESOLVE(c);
     if (nsteps < 0) return fail(c, LH_ERR_INVALID_ARG, "nsteps < 0");
     if (sp->nstages < 1 || sp->nstages > LH_MAX_STAGES) return fail(c, LH_ERR_INVALID_ARG, "stepper.nstages must be 1..%d", LH_MAX_STAGES);
     if (sp->kind != LH_STEPPER_SHU_OSHER && sp->kind != LH_STEPPER_2N) return fail(c, LH_ERR_INVALID_ARG, "unknown stepper kind %d", sp->kind);
@@ -1409,6 +1464,7 @@ static int32_t local_budgets(lh_soil_ctx* c, double* out_dev)
 int32_t lh_soil_budgets(lh_soil_ctx* c, double out[2])
 {
     if (!c || !out) return LH_ERR_INVALID_ARG;
+    LH_RESOLVE(c);
     LH_CUDA(c, cudaSetDevice(c->device));
     int32_t st = local_budgets(c);
     if (st != LH_OK) return st;
@@ -1421,6 +1477,7 @@ int32_t lh_soil_budgets(lh_soil_ctx* c, double out[2])
 int32_t lh_soil_budgets_async(lh_soil_ctx* c, int64_t* ticket_out)
 {
     if (!c || !ticket_out) return LH_ERR_INVALID_ARG;
+    LH_RESOLVE(c);
     LH_CUDA(c, cudaSetDevice(c->device));
     if (!c->budget_ring_dev) {
         LH_CUDA(c, cudaMalloc(&c->budget_ring_dev, lh_soil_ctx::BUDGET_SLOTS * 2 * sizeof(double)));
@@ -1459,6 +1516,7 @@ int32_t lh_soil_budgets_wait(lh_soil_ctx* c, int64_t ticket, double out[2])
 int32_t lh_soil_diagnostic(lh_soil_ctx* c, int32_t which, double* host, int64_t cs, int64_t ls)
 {
     if (!c || !host) return LH_ERR_INVALID_ARG;
+    LH_RESOLVE(c);
     if (which < 0 || which >= LH_NUM_DIAGS) return fail(c, LH_ERR_INVALID_ARG, "bad diagnostic id %d", which);
     LH_CUDA(c, cudaSetDevice(c->device));
     if (!c->diag_dev) LH_CUDA(c, cudaMalloc(&c->diag_dev, field_bytes(c)));      // its own scratch: tendencies stay untouched
@@ -1490,6 +1548,7 @@ int32_t lh_soil_eval_math(lh_soil_ctx* c, int32_t fn, const double* x, double* y
 int32_t lh_soil_sync(lh_soil_ctx* c)
 {
     if (!c) return LH_ERR_INVALID_ARG;
+    LH_RESOLVE(c);
     LH_CUDA(c, cudaSetDevice(c->device));
     LH_CUDA(c, cudaStreamSynchronize(c->stream));
     return LH_OK;
@@ -1511,6 +1570,7 @@ int32_t lh_soil_last_step_timing(lh_soil_ctx* c, double* ms_out, int64_t* launch
 int32_t lh_soil_kernel_info(lh_soil_ctx* c, char* buf, int64_t cap)
 {
     if (!c || !buf || cap < 1) return LH_ERR_INVALID_ARG;
+    LH_RESOLVE(c);
     const int f = c->kernel_flags;
     const bool persistent = use_persistent(c);
     snprintf(buf, (size_t)cap,
@@ -1528,6 +1588,7 @@ int32_t lh_soil_kernel_info(lh_soil_ctx* c, char* buf, int64_t cap)
 int32_t lh_soil_device_ptr(lh_soil_ctx* c, int32_t field, void** dptr, int64_t* ncol_padded)
 {
     if (!c || !dptr) return LH_ERR_INVALID_ARG;
+    LH_RESOLVE(c);
     if (!field_ok(field) || !c->U[field]) return fail(c, LH_ERR_INVALID_ARG, "field %d does not exist", field);
     LH_CUDA(c, cudaSetDevice(c->device));
     *dptr = c->U[field];
@@ -1573,6 +1634,7 @@ int32_t lh_soil_comm_init(lh_soil_ctx* c, int32_t nranks, int32_t rank, const ui
 int32_t lh_soil_budgets_allreduce(lh_soil_ctx* c, double out[2])
 {
     if (!c || !out) return LH_ERR_INVALID_ARG;
+    LH_RESOLVE(c);
     if (!c->comm) return fail(c, LH_ERR_STATE, "lh_soil_comm_init has not been called");
     NcclApi& n = nccl();
     LH_CUDA(c, cudaSetDevice(c->device));

@@ -276,6 +276,55 @@ def test_deferred_execution_is_real_and_the_raw_pointer_rule_holds(emu, knobs):
         knobs.lh_emu_set_async(0, 1)
 
 
+@pytest.mark.parametrize("op", ["rhs", "stages", "step", "stepper", "run", "colp_then_step", "checkpoint_then_step", "info"])
+def test_first_call_after_an_ice_upload_uses_the_ice_kernels(emu, oracle, op):
+    """The scan that answers "any ice?" after a theta_i upload is only enqueued by the upload; whichever call comes next and
+    launches kernels (or reports / changes the variant) must wait for the answer first.  A ctx that has already stepped with the
+    ice-free kernels gets ice uploaded, then `op` — the result must be the oracle's."""
+    wl = w.coupled_workload(ncol=40, nlayer=12, seed=23, zlim=(-1.2, 0.0))
+    g, o = lh.SoilContext(emu, wl.config(flags=STAGE)), lh.SoilContext(oracle, wl.config())
+    ice = np.random.default_rng(3).uniform(0.0, 0.03, wl.fields[1].shape)
+    for c in (g, o):
+        wl.upload(c)
+        c.step(0.0, wl.dt, 1)
+    assert "!ICE" in g.kernel_info()
+    th = np.minimum(o.get_state(0), 0.95 * (wl.params.nu - ice))
+    for c in (g, o):
+        c.set_state(1, ice)
+        c.set_state(0, th)
+    if op == "info":
+        assert ":ICE" in g.kernel_info()
+        return
+    for c in (g, o):
+        if op == "rhs":
+            c.rhs(0.0)
+        elif op == "stages":
+            for k in (1, 2, 3):
+                c.stage(k, wl.dt)
+        elif op == "step":
+            c.step(wl.dt, wl.dt, 2)
+        elif op == "stepper":
+            t = abi.lh_soil_stepper()
+            assert c.lib.soil_stepper_named(abi.LH_METHOD_SSPRK43, t) == abi.LH_OK
+            c.step_with(t, wl.dt, wl.dt, 2)
+        elif op == "run":
+            c.run(wl.dt, wl.dt, 3, budget_every=1)
+        elif op == "colp_then_step":
+            c.set_column_params(Ksat=wl.params.Ksat * np.linspace(0.5, 2.0, wl.ncol))
+            c.step(wl.dt, wl.dt, 2)
+        elif op == "checkpoint_then_step":
+            c.restore(c.checkpoint())
+            c.step(wl.dt, wl.dt, 2)
+    if op == "rhs":
+        for f in (0, 2):
+            scale = w.tendency_scale(o, f)
+            assert np.max(np.abs(g.get_tendency(f) - o.get_tendency(f)) / scale[:, None]) <= 1e-12, (op, f)
+    for f in (0, 2):
+        a, r = g.get_state(f), o.get_state(f)
+        assert np.max(np.abs(a - r)) <= 1e-10 * np.max(np.abs(r)), (op, f)
+    assert ":ICE" in g.kernel_info()
+
+
 def test_contexts_on_concurrent_host_threads(emu):
     """bench.py's e2e leg and any multi-threaded host drive several contexts from several host threads at once (one ctx, one
     stream and one thread per column shard).  The library keeps per-process state (the per-variant shared-memory configuration
