@@ -623,6 +623,25 @@ def _main(args, result_stream):
         return 0
 
     line = make_line(e2e)
+    # From here on the line only GROWS (CPU baseline, variant table).  If one of those legs never returns, the line as it stood
+    # at the last completed leg is printed instead of nothing: `tail_json` is refreshed after every leg and variant row.
+    tail_json = [json.dumps(line)]
+
+    def tail_deadline():
+        progress("the CPU-baseline / variant legs are still running after 15 minutes: printing the line without what is missing")
+        faulthandler.dump_traceback(file=sys.stderr, all_threads=True)
+        with emit_lock:
+            if not emitted:
+                emitted.append(True)
+                print(tail_json[0], file=result_stream)
+                result_stream.flush()
+        sys.stderr.flush()
+        os._exit(0)
+
+    tail_watchdog = threading.Timer(900.0, tail_deadline)
+    tail_watchdog.daemon = True
+    if world == 1:
+        tail_watchdog.start()
     if world == 1:
         ctx.close()                                        # free the 2.7 GB before the CPU baseline and the variant table
         del host
@@ -630,20 +649,26 @@ def _main(args, result_stream):
     if world == 1 and not args.no_cpu_baseline:
         v, cores, sample, sec, steps = time_oracle(w, lh, graft, args.model, args.ncol, args.nlayer, 0, 1, target_seconds=12.0, ice=args.ice)
         line["cpu_baseline"] = {"value": v, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample}
+        tail_json[0] = json.dumps(line)
+        progress(f"cpu baseline done: {v:.4g} {UNIT} on {cores} cores")
     if world == 1 and not args.no_variants:
         import variants as V
 
         rows = {}
+        vnote = "variant table incomplete: the run was cut off after these rows"
         for name, spec in V.variant_specs(lh, w).items():
             try:
                 rows[name] = V.measure(lh, spec, steps=args.steps, warmup=args.warmup, reps=5, device=local_rank)
             except Exception as exc:                      # a variant that fails must not hide the headline
                 rows[name] = {"error": f"{type(exc).__name__}: {exc}"}
+            tail_json[0] = json.dumps(dict(line, extra={"variants": dict(rows), "variants_note": vnote}))
+            progress(f"variant {name}: {rows[name].get('cell_steps_per_s', rows[name].get('error'))}")
         line["extra"] = {"variants": rows,
                          "variants_note": "same process, same GPU, CUDA events on the ctx stream; per variant the MEDIAN of back-to-back "
                                           "blocks of K steps (small configs: 50 K) covering >= 1 s of device time, i.e. sustained "
                                           "(power-capped) clocks like `value`; cell_steps_per_s_first_block is the burst figure; "
                                           "frac_contract / frac_on_wire as in `roofline`"}
+    tail_watchdog.cancel()
     emit(line)
     progress("result line written")
     finish_distributed()

@@ -67,7 +67,7 @@ def _worker(rank, world, port, out_dir, extra):
 
 @pytest.mark.timeout(600)
 @pytest.mark.parametrize("world,extra", [(2, []), (3, ["--model", "richards"]), (2, ["--no-e2e", "--general-vg"]),
-                                         (1, ["--no-variants", "--no-cpu-baseline", "--ice"])])
+                                         (1, ["--no-variants", "--no-cpu-baseline", "--ice"]), (1, ["--no-variants", "--no-e2e"])])
 def test_bench_multi_rank_control_flow_terminates(tmp_path, world, extra):
     port = 29500 + (os.getpid() % 2000) + world
     mp.start_processes(_worker, args=(world, port, str(tmp_path), extra), nprocs=world, join=True, start_method="spawn")
@@ -76,7 +76,7 @@ def test_bench_multi_rank_control_flow_terminates(tmp_path, world, extra):
     d = json.loads(lines[0])
     assert d["n_gpus"] == world and d["steps"] == 2 and d["scaling"] == "strong" and d["sustained"]["blocks"] >= 3
     assert ("e2e" in d) == ("--no-e2e" not in extra)
-    assert "cpu_baseline" not in d and "extra" not in d      # N = 1 only
+    assert ("cpu_baseline" in d) == (world == 1 and "--no-cpu-baseline" not in extra) and "extra" not in d      # CPU leg at N = 1 only
     for r in range(1, world):
         assert open(tmp_path / f"out_{r}.txt").read().strip() == ""    # the other ranks print nothing
 
