@@ -32,9 +32,11 @@ def peak_gbs():
 # Contract bytes per cell-step (θ_i read in every stage, never written) and what a launched variant
 # really moves: the !ICE kernels do not read θ_i (-8 B per stage); Richards reads the prescribed T only when the
 # viscosity factor needs it (+8 B per stage, outside the contract figure).
-def bytes_per_cell_step(model: str, ice: bool, reads_T: bool = False):
+def bytes_per_cell_step(model: str, ice: bool, reads_T: bool = False, cell_params: bool = False):
     contract = {"coupled": 152, "richards": 88, "heat": 88}[model]
     wire = contract - (0 if ice else 24) + (24 if reads_T else 0)
+    if cell_params:
+        wire += 3 * 72                  # nine per-cell parameter fields read in every stage, outside the contract figure
     return contract, wire
 
 
@@ -68,6 +70,29 @@ def variant_specs(lh, w, quick=False):
         make=lambda: w.richards_workload(ncol=RS[0], nlayer=RS[1], ice=True, viscosity=visc(), impedance=imp()),
         model="richards", ice=True, reads_T=True)
     S["richards_het"] = dict(make=lambda: w.richards_workload(ncol=RS[0], nlayer=RS[1]), model="richards", post=het)
+
+    # N4 of SURVEY §8(f): per-column HEAT parameters (HETH variants) and per-cell (layered) hydraulic parameters (CELLP variants).
+    # A quarter of the C4 columns: the per-cell derivation of nine fields runs on the host, once, at 0.2 us per cell.
+    Q4 = (C4[0] // 4, C4[1])
+
+    def het_heat(ctx, wl):
+        het(ctx, wl)
+        rng = np.random.default_rng(12)
+        n_ = wl.ncol
+        ctx.set_column_heat_params(rho_c_ds=wl.params.rho_c_ds * rng.uniform(0.8, 1.2, n_),
+                                   kappa_sat_unfrozen=wl.params.kappa_sat_unfrozen * rng.uniform(0.8, 1.2, n_),
+                                   nu_ss_om=rng.uniform(0.0, 0.2, n_))
+
+    def cell_params(ctx, wl):
+        rng = np.random.default_rng(13)
+        shape = (wl.ncol, wl.nlayer)
+        ctx.set_cell_params(vg_n=rng.uniform(1.5, 3.5, shape), Ksat=wl.params.Ksat * 10.0 ** rng.uniform(-1.0, 1.0, shape))
+
+    S["coupled_het_heat_params"] = dict(make=lambda: w.coupled_workload(ncol=Q4[0], nlayer=Q4[1]), model="coupled", post=het_heat)
+    S["coupled_cell_params"] = dict(make=lambda: w.coupled_workload(ncol=Q4[0], nlayer=Q4[1]), model="coupled", post=cell_params,
+                                    cell_params=True)
+    S["richards_cell_params"] = dict(make=lambda: w.richards_workload(ncol=Q4[0], nlayer=Q4[1], zlim=(-0.96, 0.0)), model="richards",
+                                     post=cell_params, cell_params=True)
     S["C5_coupled_16_layers"] = dict(make=lambda: w.coupled_workload(ncol=cells // 16, nlayer=16, zlim=(-0.5, 0.0)), model="coupled")
     S["C5_coupled_1024_layers"] = dict(make=lambda: w.coupled_workload(ncol=cells // 1024, nlayer=1024, zlim=(-32.0, 0.0)), model="coupled")
     S["C5_richards_16_layers"] = dict(make=lambda: w.richards_workload(ncol=cells // 16, nlayer=16, zlim=(-0.24, 0.0)), model="richards")
@@ -102,7 +127,7 @@ def measure(lh, spec, steps=20, warmup=3, reps=3, device=0, min_seconds=1.0):
         info = ctx.kernel_info() if hasattr(ctx, "kernel_info") else None
     finally:
         ctx.close()
-    contract, wire = bytes_per_cell_step(spec["model"], spec.get("ice", False), spec.get("reads_T", False))
+    contract, wire = bytes_per_cell_step(spec["model"], spec.get("ice", False), spec.get("reads_T", False), spec.get("cell_params", False))
     v = wl.cells * k / (ms * 1e-3)
     peak = peak_gbs()
     row = {"ncol": wl.ncol, "nlayer": wl.nlayer, "cell_steps_per_s": v, "ms_per_step": ms / k,
