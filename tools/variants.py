@@ -88,6 +88,17 @@ def variant_specs(lh, w, quick=False):
         shape = (wl.ncol, wl.nlayer)
         ctx.set_cell_params(vg_n=rng.uniform(1.5, 3.5, shape), Ksat=wl.params.Ksat * 10.0 ** rng.uniform(-1.0, 1.0, shape))
 
+    def atmos(ctx, wl):
+        # PrescribedAtmosForcing at the top face (N3): one Monin-Obukhov solve per column before every stage launch
+        ep = lh.EarthParameterSet()
+        a = A.lh_soil_atmos()
+        a.u_atm, a.theta_atm, a.z_atm, a.theta_scale, a.rho_a_sfc, a.q_atm = 2.0, 288.0, 2.0, 290.0, 1.17, 0.006
+        a.R_v, a.R_d, a.grav, a.cp_d, a.cp_v, a.LH_v0 = ep.R_v, ep.R_d, ep.grav, ep.cp_d, ep.cp_v, ep.LH_v0
+        a.press_triple, a.T_triple, a.von_karman = ep.press_triple, ep.T_triple, ep.von_karman_const
+        a.Pr_0, a.a_m, a.a_h = ep.Pr_0, ep.a_m, ep.a_h
+        ctx.set_atmos_forcing(a)
+
+    S["coupled_atmos_forcing"] = dict(make=lambda: w.coupled_workload(ncol=C4[0], nlayer=C4[1]), model="coupled", post=atmos)
     S["coupled_het_heat_params"] = dict(make=lambda: w.coupled_workload(ncol=Q4[0], nlayer=Q4[1]), model="coupled", post=het_heat)
     S["coupled_cell_params"] = dict(make=lambda: w.coupled_workload(ncol=Q4[0], nlayer=Q4[1]), model="coupled", post=cell_params,
                                     cell_params=True)
