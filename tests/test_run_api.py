@@ -72,6 +72,27 @@ def test_run_snapshots_of_a_one_layer_domain(lib):
     assert np.array_equal(snaps, np.array(ref))
 
 
+def test_run_snapshots_in_the_column_fastest_layout(lib):
+    """Snapshots may also be written column-fastest, (col_stride, layer_stride) = (1, >= ncol) — the layout of the device
+    arrays, a strided 2-D copy with no transpose.  Same numbers as the reference layout, transposed; the gap columns of a
+    padded layer stride are left untouched."""
+    import ctypes as C
+
+    wl = w.coupled_workload(ncol=70, nlayer=9, seed=105, zlim=(-0.9, 0.0))
+    a, b = _ctx(lib, wl), _ctx(lib, wl)
+    _, ref = a.run(0.0, wl.dt, 4, save_every=2, save_first=True, save_fields=(0, 2))          # (3, 2, ncol, nlayer)
+    pad = 75                                                                                   # layer stride > ncol
+    out = np.full((3, 2, wl.nlayer, pad), -7.0)
+    o = abi.lh_soil_run_opts()
+    o.save_every, o.save_first, o.nsave_fields = 2, 1, 2
+    o.save_fields[0], o.save_fields[1] = 0, 2
+    o.save_out = out.ctypes.data_as(C.POINTER(C.c_double))
+    o.snapshot_stride, o.field_stride, o.col_stride, o.layer_stride = 2 * wl.nlayer * pad, wl.nlayer * pad, 1, pad
+    assert lib.soil_run(b._h, 0.0, wl.dt, 4, C.byref(o)) == abi.LH_OK
+    assert np.array_equal(out[..., :70].transpose(0, 1, 3, 2), ref)
+    assert np.all(out[..., 70:] == -7.0)
+
+
 def test_run_argument_checks(lib):
     wl = w.coupled_workload(ncol=8, nlayer=6, seed=103, zlim=(-0.6, 0.0))
     ctx = _ctx(lib, wl)
