@@ -93,6 +93,32 @@ def test_run_snapshots_in_the_column_fastest_layout(lib):
     assert np.all(out[..., 70:] == -7.0)
 
 
+def test_host_buffers_allocated_by_the_library(lib):
+    """lh_soil_alloc_host / lh_soil_free_host: page-locked host memory for hosts without an allocator of their own (a Julia
+    caller); used here as upload source, download target and snapshot destination."""
+    import ctypes as C
+
+    wl = w.coupled_workload(ncol=50, nlayer=10, seed=106, zlim=(-1.0, 0.0))
+    nbytes = 3 * 2 * 50 * 10 * 8
+    p = C.c_void_p()
+    assert lib.soil_alloc_host(nbytes, C.byref(p)) == abi.LH_OK and p.value
+    try:
+        buf = np.ctypeslib.as_array(C.cast(p, C.POINTER(C.c_double)), shape=(3, 2, 50, 10))
+        a, b = _ctx(lib, wl), _ctx(lib, wl)
+        buf[0, 0] = wl.fields[0] * 0.99
+        for c in (a, b):
+            c.set_state(0, buf[0, 0])                                # upload straight from the library's buffer
+        _, ref = b.run(0.0, wl.dt, 4, save_every=2, save_first=True, save_fields=(0, 2))
+        _, snaps = a.run(0.0, wl.dt, 4, save_every=2, save_first=True, save_fields=(0, 2), save_out=buf)
+        assert snaps is buf and np.array_equal(buf, ref)
+        a.get_state(2, out=buf[1, 1])
+        assert np.array_equal(buf[1, 1], b.get_state(2))
+    finally:
+        assert lib.soil_free_host(p) == abi.LH_OK
+    assert lib.soil_alloc_host(-1, C.byref(p)) == abi.LH_ERR_INVALID_ARG
+    assert lib.soil_free_host(None) == abi.LH_OK
+
+
 def test_run_argument_checks(lib):
     wl = w.coupled_workload(ncol=8, nlayer=6, seed=103, zlim=(-0.6, 0.0))
     ctx = _ctx(lib, wl)
