@@ -190,7 +190,17 @@ def _async_scenario(emu, knobs, mode, seed):
         g.set_state(0, wide[:, ::2])                                  # layer stride 2: gathered through the pinned staging blocks
         soa = np.ascontiguousarray(wl.fields[2].T)
         g.set_state(2, soa.T)                                         # column-fastest host block: the 2-D copy path
-        bud, snaps = g.run(0.0, wl.dt, 5, budget_every=1, save_every=2, save_first=True, save_fields=(0, 2))
+        # snapshots into PINNED host memory (lh_soil_alloc_host): their D2H copies are truly asynchronous — a pageable numpy
+        # destination would make every copy a synchronisation point and hide a missing dependency
+        import ctypes as C
+
+        pin = C.c_void_p()
+        assert emu.soil_alloc_host(3 * 2 * 300 * 24 * 8, C.byref(pin)) == abi.LH_OK
+        pinned = np.ctypeslib.as_array(C.cast(pin, C.POINTER(C.c_double)), shape=(3, 2, 300, 24))
+        bud, _ = g.run(0.0, wl.dt, 5, budget_every=1, save_every=2, save_first=True, save_fields=(0, 2), save_out=pinned)
+        snaps = pinned.copy()
+        pinned[0, 0] = snaps[2, 0]
+        g.set_state(0, pinned[0, 0])                                  # and an upload from pinned memory: read when the copy runs
         ticket = g.budgets_async()
         g.step(5 * wl.dt, wl.dt, 2)
         b2 = g.budgets_wait(ticket)
@@ -203,6 +213,7 @@ def _async_scenario(emu, knobs, mode, seed):
         g.step(8 * wl.dt, wl.dt, 2)
         out = (g.get_state(0), g.get_state(2), bud, snaps, b2, after, g.budgets())
         g.close()
+        assert emu.soil_free_host(pin) == abi.LH_OK
         return out
     finally:
         knobs.lh_emu_set_async(0, 1)

@@ -167,8 +167,22 @@ def _sequence(rng, wl, g, o, nops):
             if rng.random() < 0.5:                    # a boundary-value table: read from device memory by the persistent launches
                 vals = np.array([wl.top[1], wl.top[3], wl.bottom[1], wl.bottom[3]])
                 table = np.broadcast_to(vals, (k, 3, 4)) * (1.0 + 1e-3 * rng.standard_normal((k, 3, 4)))
-            out = [c.run(t, wl.dt, k, bc_table=table, budget_every=be, save_every=se, save_first=first,
-                         save_fields=fields if (se or first) else ()) for c in both]
+            kw = dict(bc_table=table, budget_every=be, save_every=se, save_first=first, save_fields=fields if (se or first) else ())
+            ns = (k // se if se else 0) + (1 if first else 0)
+            pin = None
+            if ns and rng.random() < 0.5:
+                # snapshots into pinned memory from the library: D2H copies that really are asynchronous (a pageable numpy
+                # destination turns each of them into a synchronisation point)
+                pin = C.c_void_p()
+                shape = (ns, len(fields), wl.ncol, wl.nlayer)
+                assert g.lib.soil_alloc_host(int(np.prod(shape)) * 8, C.byref(pin)) == abi.LH_OK
+                dest = np.ctypeslib.as_array(C.cast(pin, C.POINTER(C.c_double)), shape=shape)
+                bg, sg = g.run(t, wl.dt, k, save_out=dest, **kw)
+                sg = sg.copy()
+                assert g.lib.soil_free_host(pin) == abi.LH_OK
+                out = [(bg, sg), o.run(t, wl.dt, k, **kw)]
+            else:
+                out = [c.run(t, wl.dt, k, **kw) for c in both]
             t += k * wl.dt
             (bg, sg), (bo, so) = out
             if be:
