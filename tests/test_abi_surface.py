@@ -5,6 +5,7 @@ import ctypes as C
 import os
 import re
 import subprocess
+import sys
 
 import pytest
 
@@ -146,3 +147,18 @@ def test_product_never_references_oracle():
         if re.search(r"hostemu|LH_HOSTEMU", open(path, errors="ignore").read()):
             emu_hits.append(path)
     assert not emu_hits, emu_hits
+
+
+def test_device_code_is_byte_identical_to_the_last_gpu_verified_build():
+    """Everything after commit 24b093f was done without a GPU.  What was allowed to change is HOST code (launch spelling, the
+    transfer pipelines of the C ABI, bench.py): every kernel's SASS must still hash to the fingerprint of the build whose `-m gpu`
+    suite last ran green on a B200 (profiles/r02_sass_fingerprints_gpu_verified.json, tools/sass_identity.py)."""
+    import shutil
+
+    if not shutil.which("cuobjdump"):
+        pytest.skip("cuobjdump not on PATH")
+    w.graft.build_cuda()
+    res = subprocess.run([sys.executable, os.path.join(ROOT, "tools", "sass_identity.py"), "--check",
+                          os.path.join(ROOT, "profiles", "r02_sass_fingerprints_gpu_verified.json")], capture_output=True, text=True)
+    assert res.returncode == 0, res.stdout[-2000:] + res.stderr[-2000:]
+    assert "268 identical, 0 changed, 0 new, 0 gone" in res.stdout, res.stdout
