@@ -128,6 +128,10 @@ def controls(path=None):
     h.lh_emu_set_sm_count.restype = C.c_int
     h.lh_emu_set_async.argtypes = [C.c_int, C.c_uint64]
     h.lh_emu_set_async.restype = C.c_int
+    h.lh_emu_live_handles.argtypes = []
+    h.lh_emu_live_handles.restype = C.c_int64
+    h.lh_emu_live_allocations.argtypes = []
+    h.lh_emu_live_allocations.restype = C.c_uint64
     h.lh_emu_launch_count.argtypes = []
     h.lh_emu_launch_count.restype = C.c_uint64
     return h

@@ -69,6 +69,8 @@ int lh_emu_set_async(int mode, uint64_t seed);   // 0 synchronous, 1 deferred (l
 int lh_emu_set_device_count(int n);
 int lh_emu_set_sm_count(int n);
 uint64_t lh_emu_launch_count(void);
+int64_t lh_emu_live_handles(void);            // streams + events created and not yet destroyed
+uint64_t lh_emu_live_allocations(void);      // cudaMalloc / cudaMallocHost blocks not yet freed
 }
 struct LhEmuStream;
 void lh_emu_launch(LhEmuStream* stream, dim3 grid, dim3 block, size_t smem_bytes, std::function<void()> thread_body);

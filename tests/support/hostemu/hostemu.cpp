@@ -74,6 +74,7 @@ std::atomic<int> g_cp_lazy{0};
 std::atomic<int> g_devices{1};
 std::atomic<int> g_sms{148};
 std::atomic<uint64_t> g_launches{0};
+std::atomic<int64_t> g_live_handles{0};           // streams + events created and not yet destroyed
 
 constexpr size_t STACK_BYTES = 512 * 1024;
 
@@ -499,6 +500,12 @@ int lh_emu_set_cp_async_lazy(int lazy) { return g_cp_lazy.exchange(lazy != 0); }
 int lh_emu_set_device_count(int n) { return g_devices.exchange(n < 0 ? 0 : n); }
 int lh_emu_set_sm_count(int n) { return g_sms.exchange(n < 1 ? 1 : n); }
 uint64_t lh_emu_launch_count(void) { return g_launches.load(); }
+int64_t lh_emu_live_handles(void) { return g_live_handles.load(); }
+uint64_t lh_emu_live_allocations(void)
+{
+    std::lock_guard<std::mutex> lock(g_alloc_mutex);
+    return (uint64_t)g_allocs.size();
+}
 
 }  // extern "C"
 
@@ -743,12 +750,13 @@ cudaError_t cudaStreamCreateWithFlags(cudaStream_t* s, unsigned)
     *s = new LhEmuStream();
     (*s)->device = tl_device;
     g_streams.push_back(*s);                          // streams are never freed: queued operations may outlive their handle
+    ++g_live_handles;
     return cudaSuccess;
 }
 cudaError_t cudaStreamDestroy(cudaStream_t s)
 {
     std::lock_guard<std::recursive_mutex> lock(g_api);
-    if (s) drain_stream(s);                           // CUDA lets the queued work finish; here it finishes now
+    if (s) { drain_stream(s); --g_live_handles; }     // CUDA lets the queued work finish; here it finishes now
     return cudaSuccess;
 }
 cudaError_t cudaStreamSynchronize(cudaStream_t s)
@@ -770,9 +778,9 @@ cudaError_t cudaStreamWaitEvent(cudaStream_t s, cudaEvent_t e, unsigned)
     s->q.push_back(std::move(op));
     return cudaSuccess;
 }
-cudaError_t cudaEventCreate(cudaEvent_t* e) { *e = new LhEmuEvent(); return cudaSuccess; }
+cudaError_t cudaEventCreate(cudaEvent_t* e) { *e = new LhEmuEvent(); ++g_live_handles; return cudaSuccess; }
 cudaError_t cudaEventCreateWithFlags(cudaEvent_t* e, unsigned) { return cudaEventCreate(e); }
-cudaError_t cudaEventDestroy(cudaEvent_t) { return cudaSuccess; }                  // leaked: a queued record / wait may still name it
+cudaError_t cudaEventDestroy(cudaEvent_t e) { if (e) --g_live_handles; return cudaSuccess; }   // memory leaked on purpose: a queued record / wait may still name it
 cudaError_t cudaEventRecord(cudaEvent_t e, cudaStream_t s)
 {
     std::lock_guard<std::recursive_mutex> lock(g_api);

@@ -43,6 +43,19 @@ def knobs():
     h.lh_emu_set_device_count(1)
 
 
+F_ = abi.LH_BC_FLUX
+
+
+def _atmos():
+    ep = lh.EarthParameterSet()
+    a = abi.lh_soil_atmos()
+    a.u_atm, a.theta_atm, a.z_atm, a.theta_scale, a.rho_a_sfc, a.q_atm = 2.0, 288.0, 2.0, 290.0, 1.17, 0.006
+    a.R_v, a.R_d, a.grav, a.cp_d, a.cp_v, a.LH_v0 = ep.R_v, ep.R_d, ep.grav, ep.cp_d, ep.cp_v, ep.LH_v0
+    a.press_triple, a.T_triple, a.von_karman = ep.press_triple, ep.T_triple, ep.von_karman_const
+    a.Pr_0, a.a_m, a.a_h = ep.Pr_0, ep.a_m, ep.a_h
+    return a
+
+
 def _visc():
     return lh.TemperatureDependentViscosity()
 
@@ -334,6 +347,42 @@ def test_first_call_after_an_ice_upload_uses_the_ice_kernels(emu, oracle, op):
         a, r = g.get_state(f), o.get_state(f)
         assert np.max(np.abs(a - r)) <= 1e-10 * np.max(np.abs(r)), (op, f)
     assert ":ICE" in g.kernel_info()
+
+
+def test_destroy_frees_every_device_and_pinned_allocation(emu, knobs):
+    """A ctx that has used every lazily allocated resource — staging blocks, tendency buffers, diagnostic scratch, per-column and
+    per-cell parameter tables, flux fields, atmospheric flux arrays, the budget ring, the run history and snapshot buffers, a
+    boundary table on the device, a profile table — returns every cudaMalloc / cudaMallocHost block, stream and event on lh_soil_destroy."""
+    before, handles = knobs.lh_emu_live_allocations(), knobs.lh_emu_live_handles()
+    for model in ("coupled", "richards", "heat"):
+        if model == "coupled":
+            wl = w.coupled_workload(ncol=40, nlayer=12, seed=41, zlim=(-1.2, 0.0), ice=True, top=(F_, -1.0, F_, -1e-8), bottom=(F_, 0.0, F_, 0.0))
+        elif model == "richards":
+            wl = w.richards_workload(ncol=40, nlayer=12, seed=42, zlim=(-1.2, 0.0), viscosity=_visc())
+        else:
+            wl = w.heat_workload(ncol=40, nlayer=12, seed=43, zlim=(0.0, 1.0))
+        g = lh.SoilContext(emu, wl.config(flags=PERSIST))
+        wl.upload(g)
+        g.rhs(0.0)
+        g.diagnostic(abi.LH_DIAG_K)
+        fields = {"coupled": (0, 2), "richards": (0,), "heat": (2,)}[model]
+        table = np.broadcast_to(np.array([wl.top[1], wl.top[3], wl.bottom[1], wl.bottom[3]]), (3, 3, 4)).copy()
+        g.run(0.0, wl.dt, 3, bc_table=table, budget_every=1, save_every=1, save_first=True, save_fields=fields)
+        g.budgets_wait(g.budgets_async())
+        if model != "heat":
+            g.set_column_params(Ksat=wl.params.Ksat * np.linspace(0.5, 2.0, 40))
+            g.set_cell_params(vg_n=np.full((40, 12), 2.5))
+        if model == "coupled":
+            g.set_column_heat_params(rho_c_ds=np.full(40, wl.params.rho_c_ds))
+            g.set_column_fluxes(top_energy=np.full(40, -1.0))
+            g.set_atmos_forcing(_atmos())
+        if model == "richards":
+            g.set_aux_table(abi.LH_FIELD_T, np.full((3, 12), 290.0))
+        g.step(0.0, wl.dt, 1)
+        g.restore(g.checkpoint())
+        g.close()
+    assert knobs.lh_emu_live_allocations() == before
+    assert knobs.lh_emu_live_handles() == handles                    # and every stream and event it created
 
 
 def test_contexts_on_concurrent_host_threads(emu):
