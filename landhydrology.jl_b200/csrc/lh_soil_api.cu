@@ -258,18 +258,19 @@ bool field_ok(int f) { return f >= 0 && f < LH_NUM_FIELDS; }
 
 int32_t ensure_staging(lh_soil_ctx* c)
 {
-    if (c->stage_dev[0]) return LH_OK;
+    if (c->stage_dev[0] && c->stage_dev[1] && c->stage_host) return LH_OK;     // (all three: an earlier attempt may have run out of memory half way)
     // ~32 MiB blocks: large enough for PCIe efficiency, small enough to pipeline copy and transpose.  (LH_STAGE_BLOCK_BYTES,
     // read here, once per ctx: a tuning knob, and how the tests push many small blocks through the two-buffer pipeline.)
     const char* env_block = getenv("LH_STAGE_BLOCK_BYTES");
     const long long env_bytes = env_block ? atoll(env_block) : 0;
     const int64_t block_bytes = env_bytes > 0 ? (int64_t)env_bytes : (int64_t)(32ll << 20);
-    int64_t cols = std::max<int64_t>(32, block_bytes / ((int64_t)c->nlayer * 8));
-    cols = std::min<int64_t>((cols + 31) / 32 * 32, c->ncol_pad);
-    c->chunk_cols = cols;
-    const size_t bytes = (size_t)cols * c->nlayer * sizeof(double);
-    for (int k = 0; k < 2; ++k) LH_CUDA(c, cudaMalloc(&c->stage_dev[k], bytes));
-    LH_CUDA(c, cudaMallocHost(&c->stage_host, 2 * bytes));
+    if (c->chunk_cols == 0) {                    // (a retry after a failed attempt keeps the block size of the blocks it already has)
+        int64_t cols = std::max<int64_t>(32, block_bytes / ((int64_t)c->nlayer * 8));
+        c->chunk_cols = std::min<int64_t>((cols + 31) / 32 * 32, c->ncol_pad);
+    }
+    const size_t bytes = (size_t)c->chunk_cols * c->nlayer * sizeof(double);
+    for (int k = 0; k < 2; ++k) if (!c->stage_dev[k]) LH_CUDA(c, cudaMalloc(&c->stage_dev[k], bytes));
+    if (!c->stage_host) LH_CUDA(c, cudaMallocHost(&c->stage_host, 2 * bytes));
     return LH_OK;
 }
 
@@ -1479,11 +1480,10 @@ int32_t lh_soil_budgets_async(lh_soil_ctx* c, int64_t* ticket_out)
     if (!c || !ticket_out) return LH_ERR_INVALID_ARG;
     LH_RESOLVE(c);
     LH_CUDA(c, cudaSetDevice(c->device));
-    if (!c->budget_ring_dev) {
-        LH_CUDA(c, cudaMalloc(&c->budget_ring_dev, lh_soil_ctx::BUDGET_SLOTS * 2 * sizeof(double)));
-        LH_CUDA(c, cudaMallocHost(&c->budget_ring_host, lh_soil_ctx::BUDGET_SLOTS * 2 * sizeof(double)));
-        for (auto& e : c->budget_ev) LH_CUDA(c, cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
-    }
+    // (each piece on its own: an earlier attempt may have run out of memory half way)
+    if (!c->budget_ring_dev) LH_CUDA(c, cudaMalloc(&c->budget_ring_dev, lh_soil_ctx::BUDGET_SLOTS * 2 * sizeof(double)));
+    if (!c->budget_ring_host) LH_CUDA(c, cudaMallocHost(&c->budget_ring_host, lh_soil_ctx::BUDGET_SLOTS * 2 * sizeof(double)));
+    for (auto& e : c->budget_ev) if (!e) LH_CUDA(c, cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
     const int64_t ticket = c->budget_next_ticket;
     const int slot = (int)(ticket % lh_soil_ctx::BUDGET_SLOTS);
     if (c->budget_ticket[slot] != 0)

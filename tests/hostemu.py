@@ -130,6 +130,8 @@ def controls(path=None):
     h.lh_emu_set_async.restype = C.c_int
     h.lh_emu_live_handles.argtypes = []
     h.lh_emu_live_handles.restype = C.c_int64
+    h.lh_emu_fail_allocation_in.argtypes = [C.c_int64]
+    h.lh_emu_fail_allocation_in.restype = None
     h.lh_emu_live_allocations.argtypes = []
     h.lh_emu_live_allocations.restype = C.c_uint64
     h.lh_emu_launch_count.argtypes = []

@@ -70,6 +70,7 @@ int lh_emu_set_device_count(int n);
 int lh_emu_set_sm_count(int n);
 uint64_t lh_emu_launch_count(void);
 int64_t lh_emu_live_handles(void);            // streams + events created and not yet destroyed
+void lh_emu_fail_allocation_in(int64_t n);     // n more cudaMalloc / cudaMallocHost calls succeed, the next fails once (-1: off)
 uint64_t lh_emu_live_allocations(void);      // cudaMalloc / cudaMallocHost blocks not yet freed
 }
 struct LhEmuStream;

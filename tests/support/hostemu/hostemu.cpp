@@ -74,7 +74,8 @@ std::atomic<int> g_cp_lazy{0};
 std::atomic<int> g_devices{1};
 std::atomic<int> g_sms{148};
 std::atomic<uint64_t> g_launches{0};
-std::atomic<int64_t> g_live_handles{0};           // streams + events created and not yet destroyed
+std::atomic<int64_t> g_live_handles{0};
+std::atomic<int64_t> g_fail_alloc_in{-1};         // >= 0: that many more allocations succeed, the next one fails (then -1 again)           // streams + events created and not yet destroyed
 
 constexpr size_t STACK_BYTES = 512 * 1024;
 
@@ -239,6 +240,8 @@ std::unordered_map<void*, Allocation> g_allocs;
 cudaError_t guarded_alloc(void** out, size_t bytes, bool host)
 {
     if (!out) return cudaErrorInvalidValue;
+    *out = nullptr;
+    if (g_fail_alloc_in.load() >= 0 && g_fail_alloc_in.fetch_sub(1) == 0) return cudaErrorMemoryAllocation;   // injected failure
     const size_t page = (size_t)sysconf(_SC_PAGESIZE);
     const size_t need = (bytes + 15) / 16 * 16;
     const size_t body = (std::max<size_t>(need, 16) + page - 1) / page * page;
@@ -501,6 +504,7 @@ int lh_emu_set_device_count(int n) { return g_devices.exchange(n < 0 ? 0 : n); }
 int lh_emu_set_sm_count(int n) { return g_sms.exchange(n < 1 ? 1 : n); }
 uint64_t lh_emu_launch_count(void) { return g_launches.load(); }
 int64_t lh_emu_live_handles(void) { return g_live_handles.load(); }
+void lh_emu_fail_allocation_in(int64_t n) { g_fail_alloc_in.store(n); }
 uint64_t lh_emu_live_allocations(void)
 {
     std::lock_guard<std::mutex> lock(g_alloc_mutex);

@@ -385,6 +385,65 @@ def test_destroy_frees_every_device_and_pinned_allocation(emu, knobs):
     assert knobs.lh_emu_live_handles() == handles                    # and every stream and event it created
 
 
+def test_every_allocation_site_fails_cleanly_and_recovers(emu, knobs, oracle):
+    """Out-of-memory injection: the n-th cudaMalloc / cudaMallocHost of a session fails, for every n a session reaches.  The
+    failing call must return LH_ERR_CUDA naming the site (never crash, never leak), and the SAME call must succeed when repeated
+    with memory available again — no half-allocated staging blocks or budget ring left behind — and give the oracle's numbers."""
+    wl = w.coupled_workload(ncol=40, nlayer=12, seed=41, zlim=(-1.2, 0.0), ice=True)
+    o = lh.SoilContext(oracle, wl.config())
+    wl.upload(o)
+    o.run(0.0, wl.dt, 2)
+    o.set_column_params(Ksat=wl.params.Ksat * np.linspace(0.5, 2.0, 40))
+    o.set_cell_params(vg_n=np.full((40, 12), 2.5))
+    o.step(0.0, wl.dt, 1)
+    ref = o.get_state(0)
+    base, handles = knobs.lh_emu_live_allocations(), knobs.lh_emu_live_handles()
+
+    def session(g):
+        yield "upload", lambda: wl.upload(g)
+        yield "rhs", lambda: g.rhs(0.0)
+        yield "diag", lambda: g.diagnostic(abi.LH_DIAG_K)
+        yield "run", lambda: g.run(0.0, wl.dt, 2, budget_every=1, save_every=1, save_fields=(0, 2))
+        yield "async", lambda: g.budgets_wait(g.budgets_async())
+        yield "params", lambda: (g.set_column_params(Ksat=wl.params.Ksat * np.linspace(0.5, 2.0, 40)), g.set_cell_params(vg_n=np.full((40, 12), 2.5)))
+        yield "step", lambda: g.step(0.0, wl.dt, 1)
+
+    failures = 0
+    for n in range(80):
+        knobs.lh_emu_fail_allocation_in(n)
+        g = None
+        try:
+            try:
+                g = lh.SoilContext(emu, wl.config())
+            except lh._abi.SoilError as e:
+                failures += 1
+                assert "out of memory" in str(e)
+                continue
+            for name, call in session(g):
+                try:
+                    call()
+                except lh._abi.SoilError as e:
+                    failures += 1
+                    assert "out of memory" in str(e), (n, name, e)
+                    knobs.lh_emu_fail_allocation_in(-1)
+                    if name == "params":                     # the column parameters were set before the per-cell ones failed
+                        g.set_column_params()
+                        g.set_cell_params()
+                    if name in ("upload", "params"):
+                        wl.upload(g)                         # a half-finished upload leaves the state to the caller: redo it
+                        if name == "params":
+                            g.run(0.0, wl.dt, 2)
+                    call()                                   # the same call, with memory available again
+            a = g.get_state(0)
+            assert np.max(np.abs(a - ref)) <= 1e-10 * np.max(np.abs(ref)), n
+        finally:
+            knobs.lh_emu_fail_allocation_in(-1)
+            if g is not None:
+                g.close()
+        assert knobs.lh_emu_live_allocations() == base and knobs.lh_emu_live_handles() == handles, n
+    assert failures >= 25                                    # create: 12 sites, the session: 16 more
+
+
 def test_contexts_on_concurrent_host_threads(emu):
     """bench.py's e2e leg and any multi-threaded host drive several contexts from several host threads at once (one ctx, one
     stream and one thread per column shard).  The library keeps per-process state (the per-variant shared-memory configuration
