@@ -104,6 +104,19 @@ def build_mutant(name: str, filename: str, old: str, new: str) -> str:
     return mlib
 
 
+def build_fake_nccl() -> str:
+    """tests/support/hostemu/fake_nccl.cpp as .../_build/fake_nccl/libnccl.so.2 (soname libnccl.so.2): the multi-rank path of the
+    emulated build, with host threads as ranks.  Load it (RTLD_GLOBAL) before the product library first asks for NCCL."""
+    src = os.path.join(EMU, "fake_nccl.cpp")
+    out = os.path.join(BUILD, "fake_nccl", "libnccl.so.2")
+    if os.path.exists(out) and os.path.getmtime(out) >= os.path.getmtime(src):
+        return out
+    os.makedirs(os.path.dirname(out), exist_ok=True)
+    env = {k: v for k, v in os.environ.items() if k not in ("CC", "CXX")}
+    subprocess.run(["g++", "-std=c++17", "-O1", "-fPIC", "-shared", "-Wl,-soname,libnccl.so.2", src, "-o", out, "-lpthread"], check=True, env=env)
+    return out
+
+
 _lib = None
 
 

@@ -480,6 +480,22 @@ def test_contexts_on_concurrent_host_threads(emu):
         assert np.array_equal(np.concatenate([t_[0][f] for t_ in together]), whole.get_state(f))
 
 
+@pytest.mark.parametrize("world,ncol", [(2, 4096), (3, 1000)])
+def test_column_shards_with_the_budget_allreduce(world, ncol):
+    """tests/test_multi_gpu.py::test_two_gpu_sharded_run_matches_single without GPUs: host threads are the ranks, each with a ctx
+    over its contiguous column range on the emulated build, and tests/support/hostemu/fake_nccl.cpp (soname libnccl.so.2, loaded
+    first so that the product's own dlopen finds it) is the communicator — lh_soil_comm_unique_id / lh_soil_comm_init /
+    lh_soil_budgets_allreduce of the unchanged product code.  In a child process: this one may have the real libnccl mapped."""
+    import json
+
+    script = os.path.join(w.ROOT, "tests", "support", "hostemu", "multirank_session.py")
+    r = subprocess.run([sys.executable, script, str(world), str(ncol), "24", "4"], capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0, r.stdout[-1500:] + r.stderr[-1500:]
+    d = json.loads(r.stdout.strip().splitlines()[-1])
+    assert d["shards_bit_identical"] and d["same_total_on_every_rank"] and d["total_is_sum_of_locals"], d
+    assert d["total_vs_unsharded_rel"] <= 1e-13 and d["conserved_rel"] <= 1e-12, d        # zero-flux faces: budgets conserved
+
+
 # The driver's `-m gpu` suite against the emulated build.  Left out (by wall time on 8 host cores, not by outcome — every one of
 # them passes on the emulated build when given the minutes): cases sized for a real GPU (>= 5e4 columns, the full C4 shape),
 # the reference's long integrations (20 000 to 138 240 steps), and what needs torch.cuda, NCCL or nvidia-smi.
