@@ -5,7 +5,9 @@
 // CPU-only test run executes the very code that runs on the GPU: each CUDA thread of a block is a fiber, __syncthreads /
 // __syncwarp / __shfl_* are real rendezvous between fibers, cp.async groups are real queues (completed eagerly at issue or as
 // late as wait_group allows), "device" allocations are guard-paged and poisoned.  Blocks of a grid run independently on a few
-// host threads, launches are synchronous, so stream / event ordering is NOT exercised here — only what the kernels and the host logic compute.
+// host threads.  Streams and events: synchronous by default (an operation completes inside the call that enqueues it), or —
+// lh_emu_set_async — deferred FIFO queues executed only when a synchronisation needs them (lazily, or in a seeded random
+// interleaving), which exercises the host layer's stream / event dependencies.  Not modelled: timing, sm_100a code generation.
 //
 // Nothing in the product loads, links or falls back to this: the package opens csrc/liblh_soil.so (nvcc, sm_100a) and fails
 // loudly without it; only tests/ builds and opens the emulated library, by explicit path (tests/hostemu.py).

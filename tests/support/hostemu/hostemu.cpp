@@ -12,7 +12,9 @@
 //   * "device" memory: every allocation ends at a PROT_NONE guard page (an out-of-bounds access past the end faults at the
 //     offending instruction) and is filled with a signalling pattern (NaN for doubles), so nothing can depend on fresh device
 //     memory being zero.
-//   * streams and events exist but everything completes inside the call that enqueues it.
+//   * streams and events: by default everything completes inside the call that enqueues it; lh_emu_set_async turns streams into
+//     deferred queues (see "streams and events" below).
+//   * controls for tests: allocation-failure injection, live allocation / handle counts, device and SM count.
 #include "cuda_runtime.h"
 
 #include <errno.h>
