@@ -496,6 +496,49 @@ def test_column_shards_with_the_budget_allreduce(world, ncol):
     assert d["total_vs_unsharded_rel"] <= 1e-13 and d["conserved_rel"] <= 1e-12, d        # zero-flux faces: budgets conserved
 
 
+@pytest.mark.parametrize("model", ["coupled", "richards", "heat"])
+def test_misuse_returns_a_status_and_leaves_the_ctx_usable(emu, model):
+    """Out-of-range field / diagnostic / stage / method / function ids, NULL pointers, a negative step count, wrong struct sizes,
+    a junk checkpoint, an unknown budget ticket, a bad rank: every call returns a non-zero status (never a crash: device memory is
+    guard-paged here), and the ctx still steps afterwards."""
+    import ctypes as C
+
+    wl = {"coupled": lambda: w.coupled_workload(ncol=10, nlayer=6, seed=1, zlim=(-0.6, 0.0)),
+          "richards": lambda: w.richards_workload(ncol=10, nlayer=6, seed=1, zlim=(-0.6, 0.0)),
+          "heat": lambda: w.heat_workload(ncol=10, nlayer=6, seed=1, zlim=(0.0, 0.6))}[model]()
+    g = lh.SoilContext(emu, wl.config())
+    wl.upload(g)
+    h, buf = g._h, np.zeros((10, 6))
+    dp = C.POINTER(C.c_double)
+    p = buf.ctypes.data_as(dp)
+    vp = buf.ctypes.data_as(C.c_void_p)
+    calls = []
+    for f in (-5, -1, 4, 7, 100, 2 ** 31 - 1):
+        calls += [lambda f=f: emu.soil_set_state(h, f, p, 6, 1), lambda f=f: emu.soil_get_state(h, f, p, 6, 1),
+                  lambda f=f: emu.soil_get_tendency(h, f, p, 6, 1), lambda f=f: emu.soil_diagnostic(h, f, p, 6, 1),
+                  lambda f=f: emu.soil_stage_ssprk33(h, f + 10, 1.0), lambda f=f: emu.soil_set_aux_table(h, f, p, 2),
+                  lambda f=f: emu.soil_eval_math(h, f + 20, p, p, 4), lambda f=f: emu.soil_device_ptr(h, f, C.byref(C.c_void_p()), None),
+                  lambda f=f: emu.soil_stepper_named(f + 10, C.byref(abi.lh_soil_stepper()))]
+    bad_kind, bad_stages = abi.lh_soil_stepper(), abi.lh_soil_stepper()
+    bad_kind.kind, bad_kind.nstages = 7, 2
+    bad_stages.kind, bad_stages.nstages = abi.LH_STEPPER_SHU_OSHER, 99
+    too_many, wrong_size = abi.lh_soil_run_opts(), abi.lh_soil_run_opts()
+    too_many.save_every, too_many.nsave_fields = 1, 9
+    wrong_size.struct_size = 3
+    calls += [lambda: emu.soil_set_state(h, 0, None, 6, 1), lambda: emu.soil_get_state(h, 0, None, 6, 1),
+              lambda: emu.soil_step_ssprk33(h, 0.0, 1.0, -3, None), lambda: emu.soil_budgets(h, None), lambda: emu.soil_run(h, 0.0, 1.0, 2, None),
+              lambda: emu.soil_budgets_wait(h, 12345, p), lambda: emu.soil_checkpoint_save(h, vp, 8),
+              lambda: emu.soil_checkpoint_load(h, vp, buf.nbytes), lambda: emu.soil_comm_init(h, 2, 5, (C.c_uint8 * 128)()),
+              lambda: emu.soil_step(h, C.byref(bad_kind), 0.0, 1.0, 1, None), lambda: emu.soil_step(h, C.byref(bad_stages), 0.0, 1.0, 1, None),
+              lambda: emu.soil_run(h, 0.0, 1.0, 2, C.byref(too_many)), lambda: emu.soil_run(h, 0.0, 1.0, 2, C.byref(wrong_size))]
+    for k, call in enumerate(calls):
+        assert call() != abi.LH_OK, k
+    g.step(0.0, wl.dt, 1)
+    f = 2 if model == "heat" else 0
+    assert np.all(np.isfinite(g.get_state(f)))
+    g.close()
+
+
 # The driver's `-m gpu` suite against the emulated build.  Left out (by wall time on 8 host cores, not by outcome — every one of
 # them passes on the emulated build when given the minutes): cases sized for a real GPU (>= 5e4 columns, the full C4 shape),
 # the reference's long integrations (20 000 to 138 240 steps), and what needs torch.cuda, NCCL or nvidia-smi.
